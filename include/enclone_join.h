@@ -1,0 +1,218 @@
+/* enclone_join.h — C ABI of the B200 clonotype-join library (libenclone_join.so).
+ *
+ * This is the drop-in boundary for ONE hot path of 10XGenomics/enclone: the call
+ *
+ *   enclone::join::join_exacts(is_bcr, to_bc, refdata, ctl, exact_clonotypes, info,
+ *                              raw_joins, sr, dref) -> EquivRel
+ *
+ * made once per run from enclone_stuff::start::main_enclone_start, which the in-tree
+ * code reaches at enclone_main/src/main_enclone.rs:36 (the callee crates are the
+ * un-vendored git dependency enclone_ranger@cbd15ef, Cargo.lock:632-634; see
+ * SURVEY.md §0.2 and §8(b)).  There is no FFI in the reference; these entry points
+ * are what a thin Rust `extern "C"` crate would bind (INTEGRATION.md shows the stub).
+ *
+ * Conventions: plain pointers and sizes, little-endian PODs, no callbacks, no
+ * exceptions across the boundary; every function returns 0 or a negative EJOIN_E_*.
+ * The caller owns everything reachable from ejoin_pack_t for the duration of the
+ * call; the library owns everything reachable from ejoin_result_t until
+ * ejoin_result_free().  One ejoin_run*() at a time per handle.
+ */
+#ifndef ENCLONE_JOIN_H
+#define ENCLONE_JOIN_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EJOIN_ABI_VERSION 1
+#define EJOIN_NONE 0xFFFFFFFFu   /* Option::None for u32 ids                      */
+#define EJOIN_NONE16 0xFFFFu     /* Option::None for u16 region bounds            */
+
+/* error codes */
+#define EJOIN_OK 0
+#define EJOIN_E_ARG (-1)         /* bad argument / inconsistent pack              */
+#define EJOIN_E_CUDA (-2)        /* CUDA runtime error (message in last_error)    */
+#define EJOIN_E_NOGPU (-3)       /* no CUDA device: the product path has no CPU fallback */
+#define EJOIN_E_UNSUPPORTED (-4) /* input outside documented limits               */
+#define EJOIN_E_NOMEM (-5)
+
+/* ---------------------------------------------------------------------------
+ * JoinPack: the flattened view of (exact_clonotypes, info, refdata, dref) that
+ * join_exacts reads.  Field provenance: SURVEY.md §8(a) table T.
+ * Index k runs over `info` (Vec<CloneInfo>) IN THE CALLER'S SORTED ORDER
+ * (CloneInfo's derived Ord, `lens` first); chain c = 0 is the heavy/TRB chain
+ * (TigData1.left), c = 1 the light/TRA chain.  An entry with one chain
+ * (CloneInfo.lens.len() == 1) has len[1][k] == 0 and is never joined
+ * (enclone_help/src/help1.rs:270-276).
+ * ------------------------------------------------------------------------- */
+typedef struct ejoin_pack {
+    uint32_t abi_version;        /* EJOIN_ABI_VERSION                             */
+    uint32_t n_info;             /* info.len()                                    */
+    uint32_t n_exact;            /* exact_clonotypes.len()                        */
+    uint32_t n_refseq;           /* entries in the germline sequence table        */
+    uint32_t is_bcr;             /* join_exacts(is_bcr, ..)                       */
+    uint32_t reserved0;
+
+    /* ---- per info entry ---- */
+    const uint32_t *exact_id;    /* [n_info] CloneInfo.clonotype_id               */
+    const uint16_t *len[2];      /* [n_info] CloneInfo.lens[c] = tigs[c].len()    */
+    const uint64_t *tig_off[2];  /* [n_info] byte offset of tigs[c] in tig_arena  */
+    const uint8_t  *tig_arena;   /* CloneInfo.tigs: ASCII V..J, '-' marks a deletion */
+    uint64_t        tig_arena_bytes;
+    const uint8_t  *has_del[2];  /* [n_info] CloneInfo.has_del[c]                 */
+    const uint16_t *cdr3_len[2]; /* [n_info] CloneInfo.cdr3s[c].len() (nt)        */
+    const uint64_t *cdr3_off[2]; /* [n_info] byte offset of cdr3s[c] in cdr3_arena */
+    const uint8_t  *cdr3_arena;  /* CloneInfo.cdr3s: ASCII, ACGT only             */
+    uint64_t        cdr3_arena_bytes;
+    const uint16_t *cdr3_start[2]; /* [n_info] TigData1.cdr3_start (in V..J coords) */
+    const uint32_t *v_ref_id[2]; /* [n_info] CloneInfo.vsids[c] (universal ref id) */
+    const uint32_t *j_ref_id[2]; /* [n_info] CloneInfo.jsids[c]                   */
+    const uint32_t *dref_id[2];  /* [n_info] CloneInfo.dref[c], EJOIN_NONE if no donor allele */
+    const uint32_t *vs_seq[2];   /* [n_info] refseq index of CloneInfo.vs[c] (donor allele / indel-edited V actually compared) */
+    const uint32_t *js_seq[2];   /* [n_info] refseq index of CloneInfo.js[c]      */
+    const uint32_t *vname_id[2]; /* [n_info] id of refdata.name[v_ref_id] with any trailing "*.." removed */
+    const uint32_t *vuni_seq[2]; /* [n_info] refseq index of refdata.refs[v_ref_id] (universal V) */
+    const uint32_t *utr_seq[2];  /* [n_info] refseq index of refdata.refs[u_ref_id], EJOIN_NONE if u_ref_id is None */
+    const uint32_t *c_ref_id_light; /* [n_info] share[light].c_ref_id, EJOIN_NONE if None */
+    const uint16_t *hcomp;       /* [n_info] share[heavy].jun.hcomp               */
+    /* heavy-chain region starts in V..J coordinates (TigData1.fr1_start, cdr1_start, ...); EJOIN_NONE16 = None */
+    const uint16_t *fr1_start, *cdr1_start, *fr2_start, *cdr2_start, *fr3_start;
+
+    /* ---- per exact subclonotype ---- */
+    const uint32_t *nchains;     /* [n_exact] ExactClonotype.share.len()          */
+    const uint32_t *ncells;      /* [n_exact] ExactClonotype.ncells()             */
+    const uint32_t *donor_lo;    /* [n_exact] min over cells of clones[i][0].donor_index, EJOIN_NONE if all None */
+    const uint32_t *donor_hi;    /* [n_exact] max over cells, EJOIN_NONE if all None */
+
+    /* ---- germline sequence table (ASCII): universal V/J refs, donor alleles,
+     *      indel-edited V refs, 5'UTR refs ---- */
+    const uint64_t *refseq_off;  /* [n_refseq] byte offset into refseq_arena      */
+    const uint32_t *refseq_len;  /* [n_refseq]                                    */
+    const uint8_t  *refseq_arena;
+    uint64_t        refseq_arena_bytes;
+} ejoin_pack_t;
+
+/* Join parameters: EncloneControl.{join_alg_opt, heur, clono_filt_opt_def} as
+ * scalars (defaults from enclone_help/src/help1.rs:300-363
+ * and pages/cellranger.html.src:55-247).  ejoin_params_default() fills them. */
+typedef struct ejoin_params {
+    double  max_score;           /* MAX_SCORE, 100000                              */
+    double  mult_pow;            /* MULT_POW, 80                                   */
+    double  join_cdr3_ident;     /* JOIN_CDR3_IDENT, 85 (%)                        */
+    double  fwr1_cdr12_delta;    /* 20 (%)                                         */
+    int32_t cdr3_normal_len;     /* CDR3_NORMAL_LEN, 42                            */
+    int32_t auto_share;          /* AUTO_SHARES, 15                                */
+    int32_t comp_filt;           /* hcomp - cd >= 8                                */
+    int32_t comp_filt_bound;     /* diffs outside junction <= 80                   */
+    int32_t max_cdr3_diffs;      /* MAX_CDR3_DIFFS, 1000 (off)                     */
+    int32_t cdr3_mult;           /* CDR3_MULT, 5                                   */
+    int32_t max_degradation;     /* MAX_DEGRADATION, 2                             */
+    int32_t max_diffs;           /* MAX_DIFFS, 1000000 (off for BCR)               */
+    int32_t max_diffs_tcr;       /* total-difference cap applied when !is_bcr, 5 */
+    int32_t ref_v_trim;          /* 15                                             */
+    int32_t ref_j_trim;          /* 15                                             */
+    int32_t easy;                /* EASY                                           */
+    int32_t old_light;           /* OLD_LIGHT                                      */
+    int32_t old_mult;            /* OLD_MULT (unsupported on the GPU: EJOIN_E_UNSUPPORTED) */
+    int32_t mix_donors;          /* MIX_DONORS (clono_filt_opt_def.donor)          */
+    int32_t reserved[5];
+} ejoin_params_t;
+
+/* One emitted join = one PotentialJoin that survived. */
+typedef struct ejoin_edge {
+    uint32_t k1, k2;             /* info indices, k1 < k2                          */
+    int32_t  shares[2];          /* per reference choice u (u < nrefs)             */
+    int32_t  indeps[2];
+    uint16_t shares_details[2][4]; /* [u][V_heavy, J_heavy, V_light, J_light]       */
+    uint16_t nrefs;              /* 1 or 2                                         */
+    uint16_t cd;                 /* CDR3 nt differences, both chains               */
+    uint16_t cd_chain[2];
+    uint32_t diffs;              /* total V..J differences, both chains            */
+    uint16_t k, d;               /* k = min indeps + 2 d, d = min shares           */
+    uint32_t n;                  /* 3 * (len0 + len1)                              */
+    uint8_t  err;                /* cross-donor join under MIX_DONORS ("JOIN ERROR") */
+    uint8_t  accept_reason;      /* bit0 score<=max_score, bit1 shares>=auto_share, bit2 hcomp exception */
+    uint16_t reserved;
+    double   p1, mult, score;
+} ejoin_edge_t;
+
+typedef struct ejoin_stats {
+    uint64_t n_buckets;          /* runs of equal lens                             */
+    uint64_t n_groups;           /* (lens, cdr3 lens) comparison groups            */
+    uint64_t pairs_candidate;    /* sum over buckets of n_b (n_b-1)/2 : the metric's "pairs" */
+    uint64_t pairs_compared;     /* pairs whose CDR3s were XOR/popcount-compared (tier 1)    */
+    uint64_t pairs_tier2;        /* tier-1 survivors fully scored                  */
+    uint64_t pairs_accepted;     /* pairs passing join_one                         */
+    uint64_t pairs_generic;      /* tier-2 pairs routed to the bytewise path       */
+    uint64_t edges_after_prune;  /* accepted edges kept for the ordered replay     */
+    uint64_t gpu_launches;       /* kernels launched by this call                  */
+    uint64_t h2d_bytes, d2h_bytes;
+    double   ms_h2d, ms_device, ms_d2h, ms_host_post, ms_total; /* wall, host clock */
+    double   ms_kernel_tier1, ms_kernel_tier2, ms_kernel_pack, ms_kernel_other; /* CUDA events */
+} ejoin_stats_t;
+
+typedef struct ejoin_result {
+    uint64_t      n_edges;
+    ejoin_edge_t *edges;         /* raw_joins, in the reference's emit order       */
+    uint32_t     *class_of;      /* [n_info] EquivRel partition as min-member labels (finish_join) */
+    uint32_t      n_info;
+    uint32_t      n_classes;
+    ejoin_stats_t stats;
+} ejoin_result_t;
+
+/* Raw accepted edge as produced on one device before the ordered replay; the unit
+ * gathered across GPUs (the only collective). */
+typedef struct ejoin_raw_edge {
+    uint32_t k1, k2;
+    uint16_t cd, d;              /* for the two-cell rule                          */
+    uint32_t flags;
+} ejoin_raw_edge_t;
+
+typedef struct ejoin_handle ejoin_handle_t;
+
+void ejoin_params_default(ejoin_params_t *p);
+
+/* device = CUDA ordinal.  Fails with EJOIN_E_NOGPU when no device is usable. */
+int  ejoin_create(ejoin_handle_t **h, const ejoin_params_t *p, int device);
+void ejoin_destroy(ejoin_handle_t *h);
+const char *ejoin_last_error(const ejoin_handle_t *h);
+
+/* The whole join stage on one GPU: H2D, pack, score, compact, union-find, D2H,
+ * ordered replay.  Equivalent of join_exacts + finish_join. */
+int  ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pack, ejoin_result_t *out);
+void ejoin_result_free(ejoin_result_t *r);
+
+/* Multi-GPU decomposition (one process per GPU):
+ *   every rank: ejoin_plan_shards() -> which buckets this rank owns (size-aware LPT),
+ *               ejoin_run_shard()   -> accepted raw edges for those buckets (global info ids),
+ *   all-gather the raw edges (NCCL; done by the host framework),
+ *   then       ejoin_finish()       -> ordered replay, per-edge payload, partition. */
+int  ejoin_plan_shards(const ejoin_pack_t *pack, int world_size, uint32_t *bucket_owner /* [n_buckets] */,
+                       uint32_t *bucket_start /* [n_buckets+1] */, uint32_t cap_buckets, uint32_t *n_buckets);
+int  ejoin_run_shard(ejoin_handle_t *h, const ejoin_pack_t *pack, int rank, int world_size,
+                     ejoin_raw_edge_t **edges, uint64_t *n_edges, ejoin_stats_t *stats);
+void ejoin_raw_free(ejoin_raw_edge_t *edges);
+int  ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pack, const ejoin_raw_edge_t *edges,
+                  uint64_t n_edges, ejoin_result_t *out);
+
+/* Device-resident variant used to time the device side alone: upload once, then
+ * ejoin_run_resident() repeats pack+score+compact+union-find on the resident input. */
+int  ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pack);
+int  ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats);
+
+/* Pinned host memory for the caller's flat buffers (so H2D runs at link speed). */
+void *ejoin_host_alloc(size_t bytes);
+void  ejoin_host_free(void *p);
+
+/* The probability table entry the device uses: P(at most k-d distinct values in k
+ * draws with replacement from n) — exposed so tests can pin it to the known-answer
+ * vector (enclone_exec/testx/inputs/outputs/enclone_test256_output:55-56). */
+double ejoin_p1(uint32_t k, uint32_t d, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENCLONE_JOIN_H */

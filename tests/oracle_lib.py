@@ -1,0 +1,96 @@
+"""ctypes wrapper of oracle/libjoin_oracle.so — the CPU restatement of the reference join.
+
+Lives under tests/ on purpose: only tests, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may touch oracle/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from enclone_b200._abi import EDGE_DTYPE, EjoinEdge, EjoinPack, EjoinParams, EjoinResult, default_params
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "libjoin_oracle.so")
+
+
+class OracleStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_buckets", "pairs_candidate", "pairs_evaluated", "pairs_same_cdr3_len",
+                                          "pairs_tier2", "pairs_accepted")] + [("ms_total", C.c_double), ("threads", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")])
+        L = C.CDLL(_SO)
+        L.oracle_p1.restype = C.c_double
+        L.oracle_p1.argtypes = [C.c_uint32] * 3
+        L.oracle_join_one.restype = C.c_int
+        L.oracle_join_one.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.c_uint32, C.c_uint32,
+                                      C.POINTER(EjoinEdge), C.c_void_p]
+        L.oracle_fwr1_cdr12_counts.restype = C.c_int
+        L.oracle_fwr1_cdr12_counts.argtypes = [C.POINTER(EjoinPack), C.c_uint32, C.c_uint32, C.POINTER(C.c_int * 4)]
+        L.oracle_join_exacts.restype = C.c_int
+        L.oracle_join_exacts.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.c_int, C.c_uint32, C.c_uint32,
+                                         C.POINTER(EjoinResult), C.POINTER(OracleStats)]
+        L.oracle_accept_graph.restype = C.c_int
+        L.oracle_accept_graph.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.c_uint32, C.c_uint32,
+                                          C.POINTER(C.POINTER(EjoinEdge)), C.POINTER(C.c_uint64)]
+        L.oracle_result_free.argtypes = [C.POINTER(EjoinResult)]
+        L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_prepare.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def p1(k, d, n):
+    return lib().oracle_p1(k, d, n)
+
+
+def join_one(pack_struct, params, k1, k2):
+    e = EjoinEdge()
+    ok = lib().oracle_join_one(C.byref(pack_struct), C.byref(params), k1, k2, C.byref(e), None)
+    return bool(ok), e
+
+
+def region_counts(pack_struct, k1, k2):
+    out = (C.c_int * 4)()
+    ok = lib().oracle_fwr1_cdr12_counts(C.byref(pack_struct), k1, k2, C.byref(out))
+    return bool(ok), list(out)
+
+
+def _edges_to_numpy(ptr, n):
+    if n == 0:
+        return np.zeros(0, EDGE_DTYPE)
+    buf = C.string_at(ptr, n * C.sizeof(EjoinEdge))
+    return np.frombuffer(buf, dtype=EDGE_DTYPE).copy()
+
+
+def join_exacts(pack_struct, params=None, threads=1, bucket_lo=0, bucket_hi=0xFFFFFFFF):
+    """Returns (edges ndarray in raw_joins order, class_of ndarray, stats dict)."""
+    params = params or default_params()
+    L = lib()
+    L.oracle_prepare(600)
+    res, st = EjoinResult(), OracleStats()
+    rc = L.oracle_join_exacts(C.byref(pack_struct), C.byref(params), threads, bucket_lo, bucket_hi, C.byref(res), C.byref(st))
+    if rc != 0:
+        raise RuntimeError(f"oracle_join_exacts: {rc}")
+    edges = _edges_to_numpy(res.edges, res.n_edges)
+    cls = np.ctypeslib.as_array(res.class_of, shape=(res.n_info,)).copy() if res.n_info else np.zeros(0, np.uint32)
+    stats = {n: getattr(st, n) for n, _ in st._fields_}
+    L.oracle_result_free(C.byref(res))
+    return edges, cls, stats
+
+
+def accept_graph(pack_struct, params, i, j):
+    ep, n = C.POINTER(EjoinEdge)(), C.c_uint64()
+    lib().oracle_accept_graph(C.byref(pack_struct), C.byref(params), i, j, C.byref(ep), C.byref(n))
+    out = _edges_to_numpy(ep, n.value)
+    lib().oracle_free(ep)
+    return out
