@@ -1,0 +1,64 @@
+"""Loads libenclone_join.so (the CUDA product library).  No fallback: if the library is
+missing or no CUDA device is usable, calls raise."""
+import ctypes as C
+import os
+
+from ._abi import EjoinEdge, EjoinPack, EjoinParams, EjoinRawEdge, EjoinResult, EjoinStats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libenclone_join.so")
+
+# every symbol include/enclone_join.h declares
+EXPORTS = [
+    "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
+    "ejoin_plan_shards", "ejoin_run_shard", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_run_resident",
+    "ejoin_host_alloc", "ejoin_host_free", "ejoin_p1",
+]
+
+_lib = None
+
+
+class EjoinError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libenclone_join error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the join has no CPU fallback)")
+    L = C.CDLL(SO_PATH)
+    H = C.c_void_p
+    L.ejoin_params_default.argtypes = [C.POINTER(EjoinParams)]
+    L.ejoin_create.argtypes = [C.POINTER(H), C.POINTER(EjoinParams), C.c_int]
+    L.ejoin_create.restype = C.c_int
+    L.ejoin_destroy.argtypes = [H]
+    L.ejoin_last_error.argtypes = [H]
+    L.ejoin_last_error.restype = C.c_char_p
+    L.ejoin_run.argtypes = [H, C.POINTER(EjoinPack), C.POINTER(EjoinResult)]
+    L.ejoin_run.restype = C.c_int
+    L.ejoin_result_free.argtypes = [C.POINTER(EjoinResult)]
+    L.ejoin_plan_shards.argtypes = [C.POINTER(EjoinPack), C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32,
+                                    C.POINTER(C.c_uint32)]
+    L.ejoin_plan_shards.restype = C.c_int
+    L.ejoin_run_shard.argtypes = [H, C.POINTER(EjoinPack), C.c_int, C.c_int, C.POINTER(C.POINTER(EjoinRawEdge)),
+                                  C.POINTER(C.c_uint64), C.POINTER(EjoinStats)]
+    L.ejoin_run_shard.restype = C.c_int
+    L.ejoin_raw_free.argtypes = [C.POINTER(EjoinRawEdge)]
+    L.ejoin_finish.argtypes = [H, C.POINTER(EjoinPack), C.POINTER(EjoinRawEdge), C.c_uint64, C.POINTER(EjoinResult)]
+    L.ejoin_finish.restype = C.c_int
+    L.ejoin_upload.argtypes = [H, C.POINTER(EjoinPack)]
+    L.ejoin_upload.restype = C.c_int
+    L.ejoin_run_resident.argtypes = [H, C.POINTER(EjoinStats)]
+    L.ejoin_run_resident.restype = C.c_int
+    L.ejoin_host_alloc.argtypes = [C.c_size_t]
+    L.ejoin_host_alloc.restype = C.c_void_p
+    L.ejoin_host_free.argtypes = [C.c_void_p]
+    L.ejoin_p1.argtypes = [C.c_uint32] * 3
+    L.ejoin_p1.restype = C.c_double
+    _lib = L
+    return L

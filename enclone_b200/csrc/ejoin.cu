@@ -1,0 +1,819 @@
+// ejoin.cu — host orchestration and C ABI (include/enclone_join.h) of the B200 clonotype join.
+//
+// Replaces, behind the reference's own seam, the call
+//   enclone::join::join_exacts(..) -> EquivRel  (+ raw_joins, join_info)
+// reached in-tree at enclone_main/src/main_enclone.rs:36.
+// There is NO CPU fallback in this file: without a CUDA device every entry point fails
+// with EJOIN_E_NOGPU.  The host does only what the reference's own host-side epilogue does
+// (ordered replay of the accepted edges = A.7/A.8, finish_join) plus table preparation.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "ejoin_kernels.cuh"
+
+namespace {
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// bump allocator over one DevBuf
+struct Arena {
+    DevBuf buf;
+    size_t off = 0;
+    void reset() { off = 0; }
+    template <typename T> T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *r = reinterpret_cast<T *>(static_cast<char *>(buf.p) + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+struct Sizer {                 // same walk as Arena, to size it first
+    size_t off = 0;
+    void take(size_t bytes) { off = (off + 255) & ~(size_t)255; off += bytes; }
+};
+
+}  // namespace
+
+struct ejoin_handle {
+    int device = 0;
+    ejoin_params_t params;
+    std::string err;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {};
+    int is_bcr = 1;
+    int tables_is_bcr = -1;
+    int sm_count = 148;
+    // resident input + work buffers
+    Arena in_arena, work;
+    DevIn din;
+    uint32_t n = 0;            // entries uploaded
+    uint32_t k_base = 0;       // info index of uploaded entry 0
+    uint64_t tig_bytes = 0;
+    uint64_t h2d_bytes = 0;
+    bool uploaded = false;
+    // tables (cached across runs)
+    DevBuf d_counters, d_presL, d_presC, d_p1ptrs, d_multinfo, d_multpool, d_cdmax, d_p1scratch, d_Ls, d_tabptrs;
+    std::vector<double *> p1_host_ptrs;            // [8192] device pointers (host copy)
+    std::vector<MultInfo> multinfo_host;           // [65536]
+    std::vector<double> multpool_host;
+    std::vector<uint16_t> cdmax_host;
+    std::vector<DevBuf> p1_tables;
+    unsigned long long cand_cap = 0;
+    // work pointers of the last pipeline run
+    EntryMeta *meta = nullptr; uint32_t *c3 = nullptr; uint4 *t2 = nullptr; uint32_t *k_to_s = nullptr;
+    unsigned long long *kept_keys = nullptr, *kept_vals = nullptr;
+    DevCounters counters;
+    ejoin_stats_t stats;
+    uint64_t launches = 0;
+    // pinned staging for results
+    void *pin = nullptr; size_t pin_cap = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return EJOIN_E_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int fail(ejoin_handle *h, int code, const std::string &msg) { h->err = msg; return code; }
+
+DevParams dev_params(const ejoin_params_t &p, int is_bcr) {
+    DevParams d;
+    d.max_score = p.max_score; d.join_cdr3_ident = p.join_cdr3_ident; d.fwr1_cdr12_delta = p.fwr1_cdr12_delta;
+    d.auto_share = p.auto_share; d.comp_filt = p.comp_filt; d.comp_filt_bound = p.comp_filt_bound;
+    d.max_cdr3_diffs = p.max_cdr3_diffs; d.cdr3_mult = p.cdr3_mult; d.max_degradation = p.max_degradation;
+    d.max_diffs = p.max_diffs; d.max_diffs_tcr = p.max_diffs_tcr; d.ref_v_trim = p.ref_v_trim; d.ref_j_trim = p.ref_j_trim;
+    d.old_light = p.old_light; d.mix_donors = p.mix_donors; d.is_bcr = is_bcr;
+    return d;
+}
+
+int ensure_pin(ejoin_handle *h, size_t bytes) {
+    if (bytes <= h->pin_cap) return 0;
+    if (h->pin) cudaFreeHost(h->pin);
+    h->pin = nullptr; h->pin_cap = 0;
+    CK(cudaMallocHost(&h->pin, bytes + bytes / 2 + 4096));
+    h->pin_cap = bytes + bytes / 2 + 4096;
+    return 0;
+}
+
+// cd cap per total CDR3 length: the largest cd passing MAX_CDR3_DIFFS, the TCR rule and
+// "100*(1 - cd/total) >= JOIN_CDR3_IDENT" evaluated with the oracle's exact expression.
+void build_cdmax(ejoin_handle *h, int is_bcr) {
+    h->cdmax_host.assign(C3_MAX_TOTAL + 1, 0xFFFF);
+    for (int total = 0; total <= C3_MAX_TOTAL; total++) {
+        int best = -1;
+        for (int cd = 0; cd <= total; cd++) {
+            if (!is_bcr && cd > 0) break;
+            if (cd > h->params.max_cdr3_diffs) break;
+            double ident = 100.0 * (1.0 - (double)cd / (double)(total));
+            if (ident < h->params.join_cdr3_ident) break;
+            best = cd;
+        }
+        h->cdmax_host[total] = best < 0 ? 0xFFFF : (uint16_t)best;
+    }
+}
+
+// mult = MULT_POW ^ (sum_c CDR3_NORMAL_LEN * cd_c / n_c), with the host libm pow, in the
+// oracle's floating-point order (help1.rs:300-306).
+double mult_value(const ejoin_params_t &p, int cd0, int n0, int cd1, int n1) {
+    double cdx = 0.0;
+    cdx += (double)p.cdr3_normal_len * (double)cd0 / (double)n0;
+    cdx += (double)p.cdr3_normal_len * (double)cd1 / (double)n1;
+    return pow(p.mult_pow, cdx);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// p1 on the host: the same double-double recurrence as k_p1_tables (dd.cuh).
+// ---------------------------------------------------------------------------------------------
+extern "C" double ejoin_p1(uint32_t k, uint32_t d, uint32_t n) {
+    if (d == 0) return 1.0;
+    if (d > k) d = k;
+    const double nn = (double)n;
+    std::vector<dd_t> F(k + 2);
+    F[0] = dd_from(1.0);
+    for (uint32_t u = 0; u <= k; u++) F[u + 1] = p1_f_step(F[u], (int)u, nn);
+    std::vector<dd_t> prev(d + 1), cur(d + 1);
+    for (uint32_t j = 0; j <= d; j++) prev[j] = dd_from(j == 0 ? 1.0 : 0.0);
+    for (uint32_t kk = 1; kk <= k; kk++) {
+        for (uint32_t j = 0; j < d; j++) cur[j] = p1_b_step((int)kk, (int)j, prev[j > 0 ? j - 1 : 0], prev[j], nn);
+        std::swap(prev, cur);
+    }
+    dd_t p = dd_from(1.0);
+    for (uint32_t j = 0; j < d; j++) {
+        dd_t T = j <= k ? dd_mul(prev[j], F[k - j]) : dd_from(0.0);
+        p = dd_sub(p, T);
+    }
+    double v = dd_to_double(p);
+    return v < 0.0 ? 0.0 : v;
+}
+
+extern "C" void ejoin_params_default(ejoin_params_t *p) {
+    memset(p, 0, sizeof(*p));
+    p->max_score = 100000.0; p->mult_pow = 80.0; p->join_cdr3_ident = 85.0; p->fwr1_cdr12_delta = 20.0;
+    p->cdr3_normal_len = 42; p->auto_share = 15; p->comp_filt = 8; p->comp_filt_bound = 80; p->max_cdr3_diffs = 1000;
+    p->cdr3_mult = 5; p->max_degradation = 2; p->max_diffs = 1000000; p->max_diffs_tcr = 5; p->ref_v_trim = 15; p->ref_j_trim = 15;
+}
+
+extern "C" int ejoin_create(ejoin_handle_t **out, const ejoin_params_t *p, int device) {
+    if (!out || !p) return EJOIN_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return EJOIN_E_NOGPU; }
+    ejoin_handle *h = new ejoin_handle();
+    h->device = device; h->params = *p;
+    *out = h;                                    // so the caller can read last_error on failure
+    if (p->old_mult) return fail(h, EJOIN_E_UNSUPPORTED, "OLD_MULT is not supported by the GPU path");
+    if (p->auto_share > P1_DCAP) return fail(h, EJOIN_E_UNSUPPORTED, "AUTO_SHARES above the p1 table depth");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    CK(h->d_counters.ensure(sizeof(DevCounters)));
+    CK(h->d_presL.ensure(8192 / 8));
+    CK(h->d_presC.ensure(65536 / 8));
+    CK(h->d_p1ptrs.ensure(8192 * sizeof(double *)));
+    CK(h->d_multinfo.ensure(65536 * sizeof(MultInfo)));
+    CK(h->d_cdmax.ensure((C3_MAX_TOTAL + 1) * sizeof(uint16_t)));
+    h->p1_host_ptrs.assign(8192, nullptr);
+    MultInfo none; none.off = 0xFFFFFFFFu; none.d1p1 = 0;
+    h->multinfo_host.assign(65536, none);
+    CK(cudaMemsetAsync(h->d_p1ptrs.p, 0, 8192 * sizeof(double *), h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return EJOIN_OK;
+}
+
+extern "C" void ejoin_destroy(ejoin_handle_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    h->in_arena.buf.release(); h->work.buf.release();
+    for (DevBuf *b : { &h->d_counters, &h->d_presL, &h->d_presC, &h->d_p1ptrs, &h->d_multinfo, &h->d_multpool, &h->d_cdmax, &h->d_p1scratch,
+                       &h->d_Ls, &h->d_tabptrs })
+        b->release();
+    for (auto &t : h->p1_tables) t.release();
+    if (h->pin) cudaFreeHost(h->pin);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" const char *ejoin_last_error(const ejoin_handle_t *h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" void *ejoin_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void ejoin_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+namespace {
+
+int check_pack(ejoin_handle *h, const ejoin_pack_t *pk) {
+    if (!pk) return fail(h, EJOIN_E_ARG, "null pack");
+    if (pk->abi_version != EJOIN_ABI_VERSION) return fail(h, EJOIN_E_ARG, "abi_version mismatch");
+    if (pk->n_info && (!pk->exact_id || !pk->len[0] || !pk->len[1] || !pk->tig_arena || !pk->cdr3_arena || !pk->nchains))
+        return fail(h, EJOIN_E_ARG, "null array in pack");
+    return 0;
+}
+
+// H2D of the entries [lo,hi) (whole arrays for the per-exact and germline tables).
+int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t hi) {
+    int rc = check_pack(h, pk);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const uint32_t n = hi - lo;
+    // arena slices actually referenced by [lo,hi)
+    uint64_t tlo = 0, thi = pk->tig_arena_bytes, clo = 0, chi = pk->cdr3_arena_bytes;
+    if (lo != 0 || hi != pk->n_info) {
+        tlo = ~0ull; thi = 0; clo = ~0ull; chi = 0;
+        for (uint32_t k = lo; k < hi; k++)
+            for (int c = 0; c < 2; c++) {
+                uint64_t o = pk->tig_off[c][k], e = o + pk->len[c][k];
+                tlo = std::min(tlo, o); thi = std::max(thi, e);
+                o = pk->cdr3_off[c][k]; e = o + pk->cdr3_len[c][k];
+                clo = std::min(clo, o); chi = std::max(chi, e);
+            }
+        if (n == 0) { tlo = thi = clo = chi = 0; }
+    }
+    Sizer sz;
+    const size_t n1 = n ? n : 1;
+    sz.take(4 * n1);                                   // exact_id
+    for (int c = 0; c < 2; c++) { sz.take(2 * n1); sz.take(8 * n1); sz.take(n1); sz.take(2 * n1); sz.take(8 * n1); sz.take(2 * n1); for (int i = 0; i < 8; i++) sz.take(4 * n1); }
+    sz.take(4 * n1); for (int i = 0; i < 6; i++) sz.take(2 * n1);
+    for (int i = 0; i < 4; i++) sz.take(4 * (size_t)std::max(1u, pk->n_exact));
+    sz.take(8 * (size_t)std::max(1u, pk->n_refseq)); sz.take(4 * (size_t)std::max(1u, pk->n_refseq));
+    sz.take(thi - tlo + 64); sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64);
+    CK(h->in_arena.buf.ensure(sz.off + 4096));
+    h->in_arena.reset();
+    Arena &A = h->in_arena;
+    uint64_t bytes = 0;
+    DevIn &d = h->din;
+    memset(&d, 0, sizeof(d));
+    d.n_info = n; d.n_exact = pk->n_exact; d.n_refseq = pk->n_refseq;
+    auto up = [&](auto *&dst, const auto *src, size_t count) -> cudaError_t {
+        using T = std::remove_cv_t<std::remove_pointer_t<std::remove_reference_t<decltype(dst)>>>;
+        T *p = A.take<T>(count ? count : 1);
+        dst = p;
+        if (!count) return cudaSuccess;
+        bytes += count * sizeof(T);
+        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->st);
+    };
+    CK(up(d.exact_id, pk->exact_id + lo, n));
+    for (int c = 0; c < 2; c++) {
+        CK(up(d.len[c], pk->len[c] + lo, n));
+        CK(up(d.tig_off[c], pk->tig_off[c] + lo, n));
+        CK(up(d.has_del[c], pk->has_del[c] + lo, n));
+        CK(up(d.cdr3_len[c], pk->cdr3_len[c] + lo, n));
+        CK(up(d.cdr3_off[c], pk->cdr3_off[c] + lo, n));
+        CK(up(d.cdr3_start[c], pk->cdr3_start[c] + lo, n));
+        CK(up(d.v_ref_id[c], pk->v_ref_id[c] + lo, n));
+        CK(up(d.j_ref_id[c], pk->j_ref_id[c] + lo, n));
+        CK(up(d.dref_id[c], pk->dref_id[c] + lo, n));
+        CK(up(d.vs_seq[c], pk->vs_seq[c] + lo, n));
+        CK(up(d.js_seq[c], pk->js_seq[c] + lo, n));
+        CK(up(d.vname_id[c], pk->vname_id[c] + lo, n));
+        CK(up(d.vuni_seq[c], pk->vuni_seq[c] + lo, n));
+        CK(up(d.utr_seq[c], pk->utr_seq[c] + lo, n));
+    }
+    CK(up(d.c_ref_id_light, pk->c_ref_id_light + lo, n));
+    CK(up(d.hcomp, pk->hcomp + lo, n));
+    CK(up(d.fr1, pk->fr1_start + lo, n)); CK(up(d.cdr1, pk->cdr1_start + lo, n)); CK(up(d.fr2, pk->fr2_start + lo, n));
+    CK(up(d.cdr2, pk->cdr2_start + lo, n)); CK(up(d.fr3, pk->fr3_start + lo, n));
+    CK(up(d.nchains, pk->nchains, pk->n_exact)); CK(up(d.ncells, pk->ncells, pk->n_exact));
+    CK(up(d.donor_lo, pk->donor_lo, pk->n_exact)); CK(up(d.donor_hi, pk->donor_hi, pk->n_exact));
+    CK(up(d.refseq_off, pk->refseq_off, pk->n_refseq)); CK(up(d.refseq_len, pk->refseq_len, pk->n_refseq));
+    CK(up(d.tig_arena, pk->tig_arena + tlo, thi - tlo));
+    CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
+    CK(up(d.refseq_arena, pk->refseq_arena, pk->refseq_arena_bytes));
+    // the offsets index the original arenas: rebase the device pointers instead of the offsets
+    d.tig_arena -= tlo; d.cdr3_arena -= clo;
+    h->n = n; h->k_base = lo; h->tig_bytes = thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
+    return 0;
+}
+
+// Prepare p1 / mult / cdmax tables for what this input contains (one small D2H + sync).
+int prepare_tables(ejoin_handle *h, int is_bcr) {
+    std::vector<uint32_t> presL(8192 / 32), presC(65536 / 32);
+    CK(cudaMemcpyAsync(presL.data(), h->d_presL.p, 8192 / 8, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(presC.data(), h->d_presC.p, 65536 / 8, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&h->counters, h->d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (h->counters.err & ERR_CDR3_TOO_LONG) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 exceeds 255 nt (or 256 nt for both chains)");
+    if (h->counters.err & ERR_LEN_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "V..J lengths of one entry sum to 8192 or more");
+    // p1 tables for new L
+    std::vector<uint32_t> newL;
+    for (uint32_t L = 0; L < 8192; L++)
+        if ((presL[L >> 5] >> (L & 31)) & 1u)
+            if (!h->p1_host_ptrs[L]) newL.push_back(L);
+    const size_t tab_bytes = (size_t)P1_DCAP * P1_KCAP * sizeof(double);
+    const size_t BATCH = 32;
+    if (!newL.empty()) {
+        CK(h->d_p1scratch.ensure(BATCH * (size_t)P1_KCAP * P1_DCAP * sizeof(dd_t)));
+        CK(h->d_Ls.ensure(BATCH * sizeof(uint32_t)));
+        CK(h->d_tabptrs.ensure(BATCH * sizeof(double *)));
+    }
+    for (size_t b0 = 0; b0 < newL.size(); b0 += BATCH) {
+        size_t nb = std::min(BATCH, newL.size() - b0);
+        std::vector<double *> ptrs(nb);
+        for (size_t i = 0; i < nb; i++) {
+            h->p1_tables.emplace_back();
+            CK(h->p1_tables.back().ensure(tab_bytes));
+            ptrs[i] = (double *)h->p1_tables.back().p;
+            h->p1_host_ptrs[newL[b0 + i]] = ptrs[i];
+        }
+        CK(cudaMemcpyAsync(h->d_Ls.p, newL.data() + b0, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, h->st));
+        CK(cudaMemcpyAsync(h->d_tabptrs.p, ptrs.data(), nb * sizeof(double *), cudaMemcpyHostToDevice, h->st));
+        k_p1_tables<<<(unsigned)nb, P1_DCAP, 0, h->st>>>((const uint32_t *)h->d_Ls.p, (double *const *)h->d_tabptrs.p, (dd_t *)h->d_p1scratch.p);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->st));          // ptrs / newL staging is reused by the next batch
+    }
+    if (!newL.empty())
+        CK(cudaMemcpyAsync(h->d_p1ptrs.p, h->p1_host_ptrs.data(), 8192 * sizeof(double *), cudaMemcpyHostToDevice, h->st));
+    // cd caps (and the mult tables sized by them) depend on is_bcr: rebuild when it changes
+    if (h->tables_is_bcr != is_bcr) {
+        build_cdmax(h, is_bcr);
+        CK(cudaMemcpyAsync(h->d_cdmax.p, h->cdmax_host.data(), (C3_MAX_TOTAL + 1) * sizeof(uint16_t), cudaMemcpyHostToDevice, h->st));
+        MultInfo none; none.off = 0xFFFFFFFFu; none.d1p1 = 0;
+        h->multinfo_host.assign(65536, none);
+        h->multpool_host.clear();
+        h->tables_is_bcr = is_bcr;
+    }
+    // mult tables for new (cl0, cl1)
+    bool newmult = false;
+    for (uint32_t cc = 0; cc < 65536; cc++) {
+        if (!((presC[cc >> 5] >> (cc & 31)) & 1u)) continue;
+        if (h->multinfo_host[cc].off != 0xFFFFFFFFu) continue;
+        const int n0 = (int)(cc >> 8), n1 = (int)(cc & 255);
+        int cdm = h->cdmax_host[n0 + n1];
+        if (cdm == 0xFFFF) cdm = 0;
+        const int D0 = std::min(n0, cdm), D1 = std::min(n1, cdm);
+        MultInfo mi; mi.off = (uint32_t)h->multpool_host.size(); mi.d1p1 = (uint32_t)(D1 + 1);
+        for (int a = 0; a <= D0; a++)
+            for (int b = 0; b <= D1; b++) h->multpool_host.push_back(mult_value(h->params, a, n0, b, n1));
+        h->multinfo_host[cc] = mi;
+        newmult = true;
+    }
+    if (newmult) {
+        CK(h->d_multpool.ensure(h->multpool_host.size() * sizeof(double) + 64));
+        CK(cudaMemcpyAsync(h->d_multpool.p, h->multpool_host.data(), h->multpool_host.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CK(cudaMemcpyAsync(h->d_multinfo.p, h->multinfo_host.data(), 65536 * sizeof(MultInfo), cudaMemcpyHostToDevice, h->st));
+        CK(cudaStreamSynchronize(h->st));          // multpool_host may reallocate on the next call
+    }
+    return 0;
+}
+
+// The device pipeline on the resident input: keys -> sort -> groups -> pack -> tier 1 ->
+// tier 2 -> prune -> sort of the kept edges.  Ends with the counters on the host.
+int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase) {
+    if (!h->uploaded) return fail(h, EJOIN_E_ARG, "nothing uploaded");
+    CK(cudaSetDevice(h->device));
+    const uint32_t n = h->n;
+    const DevParams pr = dev_params(h->params, is_bcr);
+    memset(&h->counters, 0, sizeof(h->counters));
+    h->stats.ms_kernel_pack = h->stats.ms_kernel_tier1 = h->stats.ms_kernel_tier2 = h->stats.ms_kernel_other = 0;
+    if (h->cand_cap == 0) h->cand_cap = std::max<unsigned long long>(1ull << 20, 16ull * n);
+    if (n == 0) return 0;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const unsigned long long cap = h->cand_cap;
+        // ---- size and carve the work arena ----
+        size_t cub_bytes = 0, tmpb = 0;
+        const size_t nsort = (size_t)std::max<unsigned long long>(n, cap);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmpb, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                        (unsigned long long *)nullptr, nsort);
+        cub_bytes = std::max(cub_bytes, tmpb);
+        cub::DeviceRunLengthEncode::Encode(nullptr, tmpb, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (uint32_t *)nullptr,
+                                           (uint32_t *)nullptr, (int)n);
+        cub_bytes = std::max(cub_bytes, tmpb);
+        cub::DeviceScan::InclusiveScan(nullptr, tmpb, (uint32_t *)nullptr, (uint32_t *)nullptr, MaxOp(), (int)n);
+        cub_bytes = std::max(cub_bytes, tmpb);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpb, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+        cub_bytes = std::max(cub_bytes, tmpb);
+        const size_t t2_units = 3 * ((size_t)(h->tig_bytes / 128) + 2 * (size_t)n) + 16;
+        const size_t c3_words = (size_t)n * 2 * T1_WMAX + 4 * (size_t)n + 64;
+        Sizer sz;
+        sz.take(8 * (size_t)n); sz.take(8 * (size_t)n); sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);   // keys, keys_out, vals, perm
+        sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // head_pos, bucket_start
+        sz.take(8 * (size_t)n + 8); sz.take(4 * (size_t)n + 4); sz.take(64);                                // uniq, counts, num_runs
+        sz.take(sizeof(GroupInfo) * ((size_t)n + 1));
+        sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // t2sizes, t2off
+        sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
+        sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // k_to_s, minnbr
+        sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);                        // cand, generic, acc
+        sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // prune keys/vals in+out
+        sz.take(cub_bytes + 256);
+        sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1));                   // payload staging (taken later)
+        CK(h->work.buf.ensure(sz.off + 4096));
+        h->work.reset();
+        Arena &A = h->work;
+        unsigned long long *keys = A.take<unsigned long long>(n), *keys_out = A.take<unsigned long long>(n);
+        uint32_t *vals = A.take<uint32_t>(n), *perm = A.take<uint32_t>(n);
+        uint32_t *head_pos = A.take<uint32_t>(n), *bucket_start = A.take<uint32_t>(n);
+        unsigned long long *uniq = A.take<unsigned long long>((size_t)n + 1);
+        uint32_t *counts = A.take<uint32_t>((size_t)n + 1), *num_runs = A.take<uint32_t>(16);
+        GroupInfo *groups = A.take<GroupInfo>((size_t)n + 1);
+        uint32_t *t2sizes = A.take<uint32_t>(n), *t2off = A.take<uint32_t>(n);
+        EntryMeta *meta = A.take<EntryMeta>(n);
+        uint32_t *c3 = A.take<uint32_t>(c3_words);
+        uint4 *t2 = A.take<uint4>(t2_units);
+        uint32_t *k_to_s = A.take<uint32_t>(n), *minnbr = A.take<uint32_t>(n);
+        uint2 *cand = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
+        ejoin_raw_edge_t *acc = A.take<ejoin_raw_edge_t>(cap);
+        unsigned long long *pk_in = A.take<unsigned long long>(cap), *pv_in = A.take<unsigned long long>(cap);
+        unsigned long long *pk_out = A.take<unsigned long long>(cap), *pv_out = A.take<unsigned long long>(cap);
+        void *cub_tmp = A.take<char>(cub_bytes + 256);
+        h->meta = meta; h->c3 = c3; h->t2 = t2; h->k_to_s = k_to_s; h->kept_keys = pk_out; h->kept_vals = pv_out;
+        DevCounters *ctr = (DevCounters *)h->d_counters.p;
+        const unsigned nb256 = (n + 255) / 256;
+        cudaStream_t st = h->st;
+
+        CK(cudaEventRecord(h->ev[0], st));
+        CK(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), st));
+        CK(cudaMemsetAsync(h->d_presL.p, 0, 8192 / 8, st));
+        CK(cudaMemsetAsync(h->d_presC.p, 0, 65536 / 8, st));
+        k_bucket_heads<<<nb256, 256, 0, st>>>(h->din, head_pos);
+        size_t tb = cub_bytes;
+        cub::DeviceScan::InclusiveScan(cub_tmp, tb, head_pos, bucket_start, MaxOp(), (int)n, st);
+        k_entry_keys<<<nb256, 256, 0, st>>>(h->din, bucket_start, keys, vals, (uint32_t *)h->d_presL.p, (uint32_t *)h->d_presC.p, ctr);
+        h->launches += 3;
+        CK(cudaGetLastError());
+        int rc = prepare_tables(h, is_bcr);         // one sync; cached after the first run
+        if (rc) return rc;
+        const DevCounters first = h->counters;
+        tb = cub_bytes;
+        cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys, keys_out, vals, perm, (int)n, 0, 64, st);
+        tb = cub_bytes;
+        cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
+        k_group_scan<<<1, 1024, 0, st>>>(uniq, counts, num_runs, groups, (const uint16_t *)h->d_cdmax.p, ctr);
+        k_t2_sizes<<<nb256, 256, 0, st>>>(h->din, perm, ctr, t2sizes);
+        tb = cub_bytes;
+        cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t2sizes, t2off, (int)n, st);
+        h->launches += 8;                           // radix sort passes + RLE + scans, counted conservatively below
+        CK(cudaEventRecord(h->ev[1], st));
+        k_pack<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, perm, groups, t2off, ctr, meta, c3, t2, k_to_s, pr.ref_v_trim,
+                                                                        pr.ref_j_trim);
+        k_fill_u32<<<nb256, 256, 0, st>>>(minnbr, 0xFFFFFFFFu, n);
+        h->launches += 2;
+        CK(cudaEventRecord(h->ev[2], st));
+        DevTables tbs;
+        tbs.meta = meta; tbs.c3 = c3; tbs.t2 = t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
+        tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p;
+        tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
+        k_tier1<<<h->sm_count * 8, T1_TILE, 0, st>>>(groups, c3, ctr, cand, cap, stride, phase);
+        CK(cudaEventRecord(h->ev[3], st));
+        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, cand, cap, generic_q, acc, minnbr, 0);
+        k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, minnbr, 0);
+        CK(cudaEventRecord(h->ev[4], st));
+        k_prune<<<h->sm_count * 8, 256, 0, st>>>(acc, ctr, cap, minnbr, pk_in, pv_in);
+        h->launches += 4;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        h->counters.pairs_candidate = first.pairs_candidate; h->counters.n_buckets = first.n_buckets;
+        if (h->counters.err & ERR_CDR3_BAD_CHAR) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 contains a character outside ACGT");
+        if (h->counters.err & ERR_BAD_REFSEQ) return fail(h, EJOIN_E_ARG, "vs_seq/js_seq index outside the germline table");
+        if (h->counters.err & ERR_K_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "a pair has 1024 or more mutations (p1 table width)");
+        if (h->counters.n_cand > cap || h->counters.n_generic > cap || h->counters.n_accept > cap) {
+            // candidate buffer too small: the counts are exact, so one retry suffices
+            h->cand_cap = std::max(h->counters.n_cand, std::max(h->counters.n_generic, h->counters.n_accept)) + 1024;
+            continue;
+        }
+        const unsigned long long nk = h->counters.n_kept;
+        if (nk) {
+            tb = cub_bytes;
+            cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nk, 0, 64, st);
+            h->launches += 4;
+        }
+        CK(cudaEventRecord(h->ev[5], st));
+        CK(cudaStreamSynchronize(st));
+        float ms;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->stats.ms_kernel_pack = ms;
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->stats.ms_kernel_tier1 = ms;
+        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->stats.ms_kernel_tier2 = ms;
+        float tot;
+        cudaEventElapsedTime(&tot, h->ev[0], h->ev[5]);
+        h->stats.ms_device = tot;
+        h->stats.ms_kernel_other = tot - h->stats.ms_kernel_pack - h->stats.ms_kernel_tier1 - h->stats.ms_kernel_tier2;
+        return 0;
+    }
+    return fail(h, EJOIN_E_NOMEM, "candidate buffer kept overflowing");
+}
+
+void fill_stats(ejoin_handle *h, ejoin_stats_t *s) {
+    const DevCounters &c = h->counters;
+    s->n_buckets = c.n_buckets; s->n_groups = c.n_groups; s->pairs_candidate = c.pairs_candidate; s->pairs_compared = c.pairs_compared;
+    s->pairs_tier2 = c.pairs_tier2; s->pairs_accepted = c.n_accept; s->pairs_generic = c.n_generic; s->edges_after_prune = c.n_kept;
+    s->gpu_launches = h->launches; s->h2d_bytes = h->h2d_bytes;
+    s->ms_kernel_pack = h->stats.ms_kernel_pack; s->ms_kernel_tier1 = h->stats.ms_kernel_tier1; s->ms_kernel_tier2 = h->stats.ms_kernel_tier2;
+    s->ms_kernel_other = h->stats.ms_kernel_other; s->ms_device = h->stats.ms_device;
+}
+
+struct UF {
+    std::vector<uint32_t> p;
+    explicit UF(size_t n) : p(n) { for (size_t i = 0; i < n; i++) p[i] = (uint32_t)i; }
+    uint32_t find(uint32_t a) {
+        uint32_t r = a;
+        while (p[r] != r) r = p[r];
+        while (p[a] != r) { uint32_t nx = p[a]; p[a] = r; a = nx; }
+        return r;
+    }
+    bool join(uint32_t a, uint32_t b) {          // the smaller index stays the root: labels = min member
+        a = find(a); b = find(b);
+        if (a == b) return false;
+        if (a < b) p[b] = a; else p[a] = b;
+        return true;
+    }
+};
+
+// Ordered replay over the accepted edges sorted by (k1,k2): join_core's skip-if-same-class
+// (A.3/A.8), the two-cell rule (A.6) and the emit (A.7).  Returns the emitted (k1,k2).
+void replay(const ejoin_pack_t *pk, const ejoin_params_t &pr, const unsigned long long *keys, const unsigned long long *vals, size_t ne,
+            std::vector<uint2> &final_pairs) {
+    UF uf(pk->n_info);
+    std::vector<size_t> forest;
+    forest.reserve(std::min<size_t>(ne, pk->n_info));
+    for (size_t i = 0; i < ne; i++) {
+        uint32_t k1 = (uint32_t)(keys[i] >> 32), k2 = (uint32_t)keys[i];
+        if (uf.join(k1, k2)) forest.push_back(i);
+    }
+    std::vector<uint32_t> size(pk->n_info, 0);
+    for (uint32_t k = 0; k < pk->n_info; k++) size[uf.find(k)]++;
+    for (size_t i : forest) {
+        uint32_t k1 = (uint32_t)(keys[i] >> 32), k2 = (uint32_t)keys[i];
+        if (size[uf.find(k1)] == 2) {
+            uint32_t cells = pk->ncells[pk->exact_id[k1]] + pk->ncells[pk->exact_id[k2]];
+            uint32_t cd = (uint32_t)(vals[i] & 0xFFFF), d = (uint32_t)((vals[i] >> 16) & 0xFFFF);
+            if (cells == 2 && !pr.easy && !(cd <= d)) continue;     // help1.rs:349-353
+        }
+        final_pairs.push_back(make_uint2(k1, k2));
+    }
+}
+
+// finish_join (A.7): partition over all info entries from the emitted edges plus the
+// same-exact-subclonotype links; labels are min members.
+void finish_partition(const ejoin_pack_t *pk, const ejoin_edge_t *edges, size_t ne, ejoin_result_t *out) {
+    const uint32_t n = pk->n_info;
+    UF uf(n);
+    for (size_t i = 0; i < ne; i++) uf.join(edges[i].k1, edges[i].k2);
+    std::vector<int64_t> first(pk->n_exact, -1);
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t x = pk->exact_id[k];
+        if (x >= pk->n_exact) continue;
+        if (first[x] < 0) first[x] = k; else uf.join((uint32_t)first[x], k);
+    }
+    out->class_of = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    out->n_info = n;
+    uint32_t ncls = 0;
+    for (uint32_t k = 0; k < n; k++) { out->class_of[k] = uf.find(k); ncls += out->class_of[k] == k; }
+    out->n_classes = ncls;
+}
+
+// payload of the emitted edges on the device (k_payload), into out->edges
+int payload(ejoin_handle *h, int is_bcr, const std::vector<uint2> &pairs, ejoin_result_t *out) {
+    const size_t ne = pairs.size();
+    out->n_edges = ne;
+    out->edges = (ejoin_edge_t *)malloc(sizeof(ejoin_edge_t) * (ne ? ne : 1));
+    if (!ne) return 0;
+    const DevParams pr = dev_params(h->params, is_bcr);
+    // reuse the candidate region of the work arena (its contents are dead by now)
+    Arena &A = h->work;
+    const size_t save = A.off;
+    uint2 *d_pairs = A.take<uint2>(ne);
+    ejoin_edge_t *d_out = A.take<ejoin_edge_t>(ne);
+    if (A.off > A.buf.cap) {
+        A.off = save;
+        return fail(h, EJOIN_E_NOMEM, "work arena too small for the payload");
+    }
+    CK(cudaMemcpyAsync(d_pairs, pairs.data(), ne * sizeof(uint2), cudaMemcpyHostToDevice, h->st));
+    DevTables tbs;
+    tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
+    tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
+    k_payload<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, (DevCounters *)h->d_counters.p, h->k_to_s, d_pairs, (uint32_t)ne, h->k_base, d_out);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out->edges, d_out, ne * sizeof(ejoin_edge_t), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    A.off = save;
+    h->stats.d2h_bytes += ne * sizeof(ejoin_edge_t);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pk) {
+    if (!h) return EJOIN_E_ARG;
+    int rc = upload_range(h, pk, 0, pk ? pk->n_info : 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->st));
+    h->is_bcr = (int)pk->is_bcr;
+    return 0;
+}
+
+extern "C" int ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats) {
+    if (!h) return EJOIN_E_ARG;
+    h->launches = 0;
+    int rc = device_pipeline(h, h->is_bcr, 1, 0);
+    if (rc) return rc;
+    if (stats) { memset(stats, 0, sizeof(*stats)); fill_stats(h, stats); }
+    return 0;
+}
+
+static int finish_common(ejoin_handle *h, const ejoin_pack_t *pk, const unsigned long long *keys, const unsigned long long *vals, size_t nk,
+                         ejoin_result_t *out) {
+    double t0 = now_ms();
+    std::vector<uint2> fin;
+    replay(pk, h->params, keys, vals, nk, fin);
+    int rc = payload(h, (int)pk->is_bcr, fin, out);
+    if (rc) return rc;
+    finish_partition(pk, out->edges, out->n_edges, out);
+    h->stats.ms_host_post = now_ms() - t0;
+    return 0;
+}
+
+extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result_t *out) {
+    if (!h || !out) return EJOIN_E_ARG;
+    memset(out, 0, sizeof(*out));
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->launches = 0;
+    const double t0 = now_ms();
+    int rc = upload_range(h, pk, 0, pk ? pk->n_info : 0);
+    if (rc) return rc;
+    h->is_bcr = (int)pk->is_bcr;
+    CK(cudaStreamSynchronize(h->st));
+    const double t1 = now_ms();
+    rc = device_pipeline(h, (int)pk->is_bcr, 1, 0);
+    if (rc) return rc;
+    const double t2 = now_ms();
+    const size_t nk = (size_t)h->counters.n_kept;
+    rc = ensure_pin(h, 16 * nk + 64);
+    if (rc) return rc;
+    unsigned long long *hk = (unsigned long long *)h->pin, *hv = hk + nk;
+    if (nk) {
+        CK(cudaMemcpyAsync(hk, h->kept_keys, 8 * nk, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaMemcpyAsync(hv, h->kept_vals, 8 * nk, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+    }
+    h->stats.d2h_bytes = 16 * nk + sizeof(DevCounters);
+    const double t3 = now_ms();
+    rc = finish_common(h, pk, hk, hv, nk, out);
+    if (rc) return rc;
+    const double t4 = now_ms();
+    fill_stats(h, &out->stats);
+    out->stats.ms_h2d = t1 - t0; out->stats.ms_d2h = t3 - t2; out->stats.ms_host_post = t4 - t3; out->stats.ms_total = t4 - t0;
+    out->stats.d2h_bytes = h->stats.d2h_bytes;
+    out->stats.gpu_launches = h->launches;
+    return 0;
+}
+
+extern "C" void ejoin_result_free(ejoin_result_t *r) {
+    if (!r) return;
+    free(r->edges); free(r->class_of);
+    memset(r, 0, sizeof(*r));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU decomposition: contiguous, cost-balanced bucket ranges.
+// ---------------------------------------------------------------------------------------------
+extern "C" int ejoin_plan_shards(const ejoin_pack_t *pk, int world, uint32_t *owner, uint32_t *bstart, uint32_t cap, uint32_t *nb_out) {
+    if (!pk || world < 1 || !nb_out) return EJOIN_E_ARG;
+    std::vector<uint32_t> bs;
+    for (uint32_t k = 0; k < pk->n_info; k++)
+        if (k == 0 || pk->len[0][k] != pk->len[0][k - 1] || pk->len[1][k] != pk->len[1][k - 1]) bs.push_back(k);
+    const uint32_t nb = (uint32_t)bs.size();
+    bs.push_back(pk->n_info);
+    *nb_out = nb;
+    if (!owner || !bstart) return 0;
+    if (cap < nb) return EJOIN_E_ARG;
+    // cost = candidate pairs + a linear term for packing; contiguous split at equal prefix cost
+    std::vector<double> cost(nb);
+    double total = 0;
+    for (uint32_t b = 0; b < nb; b++) { double m = bs[b + 1] - bs[b]; cost[b] = m * (m - 1) / 2 + 64.0 * m; total += cost[b]; }
+    double acc = 0;
+    int r = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        // move to the next rank when this bucket's midpoint passes the rank's boundary
+        while (r < world - 1 && acc + cost[b] / 2 > total * (r + 1) / world) r++;
+        owner[b] = (uint32_t)r;
+        acc += cost[b];
+        bstart[b] = bs[b];
+    }
+    bstart[nb] = pk->n_info;
+    return 0;
+}
+
+extern "C" int ejoin_run_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int rank, int world, ejoin_raw_edge_t **edges, uint64_t *n_edges,
+                               ejoin_stats_t *stats) {
+    if (!h || !pk || !edges || !n_edges || rank < 0 || rank >= world) return EJOIN_E_ARG;
+    *edges = nullptr; *n_edges = 0;
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->launches = 0;
+    const double t0 = now_ms();
+    uint32_t nb = 0;
+    ejoin_plan_shards(pk, world, nullptr, nullptr, 0, &nb);
+    std::vector<uint32_t> owner(nb + 1), bstart(nb + 2);
+    ejoin_plan_shards(pk, world, owner.data(), bstart.data(), nb, &nb);
+    // giant-bucket case: if one bucket holds most of the work, every rank takes all entries and
+    // an interleaved share of the tier-1 tiles instead (stride mode)
+    double total = 0, biggest = 0;
+    for (uint32_t b = 0; b < nb; b++) { double m = bstart[b + 1] - bstart[b]; double c = m * (m - 1) / 2; total += c; biggest = std::max(biggest, c); }
+    const bool stride_mode = world > 1 && biggest > 1.25 * total / world;
+    uint32_t lo = 0, hi = pk->n_info;
+    if (!stride_mode && world > 1) {
+        lo = hi = 0;
+        bool any = false;
+        for (uint32_t b = 0; b < nb; b++)
+            if ((int)owner[b] == rank) { if (!any) { lo = bstart[b]; any = true; } hi = bstart[b + 1]; }
+    }
+    int rc = upload_range(h, pk, lo, hi);
+    if (rc) return rc;
+    h->is_bcr = (int)pk->is_bcr;
+    CK(cudaStreamSynchronize(h->st));
+    const double t1 = now_ms();
+    rc = device_pipeline(h, (int)pk->is_bcr, stride_mode ? (uint32_t)world : 1u, stride_mode ? (uint32_t)rank : 0u);
+    if (rc) return rc;
+    const double t2 = now_ms();
+    const size_t nk = (size_t)h->counters.n_kept;
+    rc = ensure_pin(h, 16 * nk + 64);
+    if (rc) return rc;
+    unsigned long long *hk = (unsigned long long *)h->pin, *hv = hk + nk;
+    if (nk) {
+        CK(cudaMemcpyAsync(hk, h->kept_keys, 8 * nk, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaMemcpyAsync(hv, h->kept_vals, 8 * nk, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+    }
+    ejoin_raw_edge_t *e = (ejoin_raw_edge_t *)malloc(sizeof(ejoin_raw_edge_t) * (nk ? nk : 1));
+    for (size_t i = 0; i < nk; i++) {
+        e[i].k1 = (uint32_t)(hk[i] >> 32) + lo; e[i].k2 = (uint32_t)hk[i] + lo;
+        e[i].cd = (uint16_t)(hv[i] & 0xFFFF); e[i].d = (uint16_t)((hv[i] >> 16) & 0xFFFF); e[i].flags = (uint32_t)(hv[i] >> 32);
+    }
+    *edges = e; *n_edges = nk;
+    const double t3 = now_ms();
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        fill_stats(h, stats);
+        stats->ms_h2d = t1 - t0; stats->ms_d2h = t3 - t2; stats->ms_total = t3 - t0; stats->d2h_bytes = 16 * nk + sizeof(DevCounters);
+        stats->gpu_launches = h->launches;
+    }
+    return 0;
+}
+
+extern "C" void ejoin_raw_free(ejoin_raw_edge_t *e) { free(e); }
+
+// Ordered replay + payload + partition from gathered raw edges.  The handle must still hold
+// the upload that covers every entry the edges touch (its own shard, or everything in
+// stride mode).
+extern "C" int ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pk, const ejoin_raw_edge_t *edges, uint64_t n_edges, ejoin_result_t *out) {
+    if (!h || !pk || !out || (n_edges && !edges)) return EJOIN_E_ARG;
+    memset(out, 0, sizeof(*out));
+    std::vector<std::pair<unsigned long long, unsigned long long>> kv(n_edges);
+    for (uint64_t i = 0; i < n_edges; i++) {
+        kv[i].first = ((unsigned long long)edges[i].k1 << 32) | edges[i].k2;
+        kv[i].second = ((unsigned long long)edges[i].flags << 32) | ((unsigned long long)edges[i].d << 16) | edges[i].cd;
+    }
+    std::sort(kv.begin(), kv.end());
+    kv.erase(std::unique(kv.begin(), kv.end(), [](auto &a, auto &b) { return a.first == b.first; }), kv.end());
+    std::vector<unsigned long long> keys(kv.size()), vals(kv.size());
+    for (size_t i = 0; i < kv.size(); i++) { keys[i] = kv[i].first; vals[i] = kv[i].second; }
+    // payload works in the handle's local index space
+    int rc = finish_common(h, pk, keys.data(), vals.data(), keys.size(), out);
+    if (rc) return rc;
+    fill_stats(h, &out->stats);
+    out->stats.ms_host_post = h->stats.ms_host_post;
+    return 0;
+}

@@ -1,0 +1,146 @@
+// ejoin_dev.cuh — device-side data layout and kernels of the B200 clonotype join.
+//
+// Path restated: join_exacts -> join_core -> join_one (enclone_ranger@cbd15ef, absent from
+// /root/reference; spec: enclone_help/src/help1.rs:270-363).
+// Layout in HBM:
+//   c3 rows   per comparison group (same V..J lengths, same CDR3 lengths): both CDR3s
+//             concatenated, 1 bit-plane pair per 32 bases: [H0..H(W-1) | L0..L(W-1)] u32 words.
+//             base code = 2*H + L, A,C,G,T = 0,1,2,3.  diff mask of 32 bases = (H^H')|(L^L').
+//   t2 rows   per entry, per chain, per 128-base block: three 128-bit rows
+//             [H x4 | L x4 | M x4]; M = 1 where the base differs from the entry's own germline
+//             inside the V window [0,|v|-15) or the J window [n-(|j|-15), n)
+//             (windows: enclone_tail/src/print_clonotypes/print_utils5.rs:78-81).
+//   meta      128-byte record per entry (ids, lengths, region bounds, mutation counts, flags).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/enclone_join.h"
+#include "dd.cuh"
+
+#define T1_TILE 128          // entries per tier-1 tile side; CTA = 128 threads
+#define T1_WMAX 8            // 32-base words per plane of the concatenated CDR3s (<= 256 nt)
+#define C3_MAX_TOTAL (32 * T1_WMAX)
+#define FLAG_GENERIC0 1u     // chain 0 needs the bytewise path (has_del, non-ACGT, overlapping windows)
+#define FLAG_GENERIC1 2u
+#define ERR_CDR3_TOO_LONG 1u
+#define ERR_CDR3_BAD_CHAR 2u
+#define ERR_BAD_REFSEQ 4u
+#define ERR_K_TOO_LARGE 8u
+#define ERR_LEN_TOO_LARGE 16u
+
+struct __align__(16) EntryMeta {
+    uint32_t k;              // info index
+    uint32_t t2off;          // t2 row offset, 16-byte units
+    uint32_t c3off;          // c3 row offset, u32 words
+    uint32_t donor_lo, donor_hi;
+    uint32_t vref[2], jref[2], dref[2];
+    uint32_t vs[2], js[2];
+    uint32_t vname[2];
+    uint32_t c_light;
+    uint16_t len[2], cs[2], cl[2];
+    uint16_t hcomp, fr1, cdr1, fr2, cdr2, fr3;
+    uint16_t m[2];           // germline differences inside the windows, per chain
+    uint16_t vend[2], jstart[2];
+    uint16_t flags;
+    uint16_t pad[9];
+};
+static_assert(sizeof(EntryMeta) == 128, "EntryMeta must be 128 bytes");
+
+struct GroupInfo {           // one comparison group = one run of equal sort keys
+    uint32_t start;          // first sorted position
+    uint32_t n;              // entries
+    uint32_t c3base;         // u32 word offset of the group's c3 rows
+    uint32_t work_off;       // first tier-1 work item
+    uint16_t W;              // words per plane
+    uint16_t cdmax;          // largest cd that passes the CDR3 gates
+    uint16_t tiles;
+    uint16_t pad;
+};
+
+struct DevCounters {         // device-resident scalars (one struct, copied back once)
+    unsigned long long n_valid, n_groups, n_work, c3_words, pairs_compared, pairs_candidate, n_buckets;
+    unsigned long long n_cand, n_generic, n_accept, n_kept, pairs_tier2;
+    unsigned long long work_next;   // dynamic tile scheduler
+    unsigned int err;
+    unsigned int max_k;
+};
+
+struct DevParams {           // ejoin_params_t plus run constants, by value to kernels
+    double max_score, join_cdr3_ident, fwr1_cdr12_delta;
+    int auto_share, comp_filt, comp_filt_bound, max_cdr3_diffs, cdr3_mult, max_degradation;
+    int max_diffs, max_diffs_tcr, ref_v_trim, ref_j_trim, old_light, mix_donors, is_bcr;
+};
+
+struct MultInfo { uint32_t off; uint32_t d1p1; };   // per (cl0,cl1): pool offset, row stride (D1+1); off = ~0 if absent
+
+// Raw input arrays as uploaded (same meaning as ejoin_pack_t)
+struct DevIn {
+    uint32_t n_info, n_exact, n_refseq;
+    const uint32_t *exact_id;
+    const uint16_t *len[2];
+    const uint64_t *tig_off[2];
+    const uint8_t *tig_arena;
+    const uint8_t *has_del[2];
+    const uint16_t *cdr3_len[2];
+    const uint64_t *cdr3_off[2];
+    const uint8_t *cdr3_arena;
+    const uint16_t *cdr3_start[2];
+    const uint32_t *v_ref_id[2], *j_ref_id[2], *dref_id[2], *vs_seq[2], *js_seq[2], *vname_id[2], *vuni_seq[2], *utr_seq[2];
+    const uint32_t *c_ref_id_light;
+    const uint16_t *hcomp, *fr1, *cdr1, *fr2, *cdr2, *fr3;
+    const uint32_t *nchains, *ncells, *donor_lo, *donor_hi;
+    const uint64_t *refseq_off;
+    const uint32_t *refseq_len;
+    const uint8_t *refseq_arena;
+};
+
+// Everything tier 2 needs
+struct DevTables {
+    const EntryMeta *meta;
+    const uint32_t *c3;
+    const uint4 *t2;
+    const double *const *p1tab;     // [len0+len1] -> table [P1_DCAP][P1_KCAP] or null
+    const MultInfo *multinfo;       // [65536]
+    const double *multpool;
+    const uint16_t *cdmax;          // [C3_MAX_TOTAL+1]
+};
+
+__device__ __forceinline__ int base_code(uint8_t b) {
+    // A,C,G,T -> 0,1,2,3 ; anything else -> -1
+    switch (b) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; }
+}
+
+// bits of 32-base word `w` (positions 32w..32w+31) that fall inside [lo,hi)
+__device__ __forceinline__ uint32_t range_mask(int w, int lo, int hi) {
+    int a = lo - 32 * w, b = hi - 32 * w;
+    a = a < 0 ? 0 : a;
+    b = b > 32 ? 32 : b;
+    if (b <= a) return 0u;
+    uint32_t m = (b >= 32) ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    return m & ~((a >= 32) ? 0xFFFFFFFFu : ((1u << a) - 1u));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk TMA copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}

@@ -1,0 +1,779 @@
+// ejoin_kernels.cuh — the sm_100a kernels of the join path.  See ejoin_dev.cuh for layouts.
+#pragma once
+#include <cub/cub.cuh>
+
+#include "ejoin_dev.cuh"
+
+struct MaxOp {
+    template <typename T> __host__ __device__ __forceinline__ T operator()(const T &a, const T &b) const { return a > b ? a : b; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K0  bucket heads: a bucket is a maximal run of equal lens.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bucket_heads(DevIn in, uint32_t *head_pos) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= in.n_info) return;
+    bool head = k == 0 || in.len[0][k] != in.len[0][k - 1] || in.len[1][k] != in.len[1][k - 1];
+    head_pos[k] = head ? k : 0u;
+}
+
+// K1  sort keys + validity + presence bitmaps + candidate-pair count.
+// Entries that can never join (one chain; exact subclonotype without 2 or 3 chains:
+// help1.rs:270-276) get the key ~0 and drop out of every comparison group.
+__global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned long long *keys, uint32_t *vals,
+                             uint32_t *presL, uint32_t *presC, DevCounters *ctr) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long pairs = 0, heads = 0;
+    if (k < in.n_info) {
+        uint32_t l0 = in.len[0][k], l1 = in.len[1][k], c0 = in.cdr3_len[0][k], c1 = in.cdr3_len[1][k];
+        uint32_t e = in.exact_id[k];
+        uint32_t nch = e < in.n_exact ? in.nchains[e] : 0;
+        bool valid = l1 > 0 && nch >= 2 && nch <= 3;
+        unsigned long long key = ~0ull;
+        if (valid) {
+            if (c0 > 255 || c1 > 255 || c0 + c1 > C3_MAX_TOTAL) { atomicOr(&ctr->err, ERR_CDR3_TOO_LONG); valid = false; }
+            else if (l0 + l1 >= 8192) { atomicOr(&ctr->err, ERR_LEN_TOO_LARGE); valid = false; }
+        }
+        if (valid) {
+            key = ((unsigned long long)l0 << 48) | ((unsigned long long)l1 << 32) | ((unsigned long long)c0 << 16) | c1;
+            uint32_t L = l0 + l1, cc = (c0 << 8) | c1;
+            atomicOr(&presL[L >> 5], 1u << (L & 31));
+            atomicOr(&presC[cc >> 5], 1u << (cc & 31));
+        }
+        keys[k] = key;
+        vals[k] = k;
+        pairs = k - bucket_start[k];
+        heads = bucket_start[k] == k;
+    }
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    unsigned long long s = BR(tmp).Sum(pairs);
+    __syncthreads();
+    unsigned long long h = BR(tmp).Sum(heads);
+    if (threadIdx.x == 0) { atomicAdd(&ctr->pairs_candidate, s); atomicAdd(&ctr->n_buckets, h); }
+}
+
+// K2  group table from the run-length encoded sorted keys (single block).
+__global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *uniq, const uint32_t *counts, const uint32_t *num_runs,
+                                                     GroupInfo *groups, const uint16_t *cdmax_tab, DevCounters *ctr) {
+    typedef cub::BlockScan<unsigned long long, 1024> BS;
+    __shared__ typename BS::TempStorage tmp;
+    __shared__ unsigned long long carry[4];
+    if (threadIdx.x == 0) carry[0] = carry[1] = carry[2] = carry[3] = 0;
+    __syncthreads();
+    const uint32_t nr = *num_runs;
+    unsigned long long ngroups = 0;
+    for (uint32_t base = 0; base < nr; base += 1024) {
+        uint32_t r = base + threadIdx.x;
+        unsigned long long n = 0, work = 0, c3w = 0, pairs = 0;
+        uint32_t W = 0, tiles = 0, cdm = 0xFFFF;
+        bool valid = false;
+        if (r < nr) {
+            unsigned long long key = uniq[r];
+            if (key != ~0ull) {
+                valid = true;
+                n = counts[r];
+                uint32_t total = (uint32_t)((key >> 16) & 0xFFFF) + (uint32_t)(key & 0xFFFF);
+                W = (total + 31) / 32;
+                if (W == 0) W = 1;
+                cdm = cdmax_tab[total];
+                tiles = (uint32_t)((n + T1_TILE - 1) / T1_TILE);
+                if (n >= 2 && cdm != 0xFFFF) { work = (unsigned long long)tiles * (tiles + 1) / 2; pairs = n * (n - 1) / 2; }
+                c3w = (n * 2 * W + 3) & ~3ull;
+            }
+        }
+        unsigned long long sn, sw, sc, agg;
+        BS(tmp).ExclusiveSum(n, sn, agg);
+        __syncthreads();
+        unsigned long long aggn = agg;
+        BS(tmp).ExclusiveSum(work, sw, agg);
+        __syncthreads();
+        unsigned long long aggw = agg;
+        BS(tmp).ExclusiveSum(c3w, sc, agg);
+        __syncthreads();
+        unsigned long long aggc = agg;
+        BS(tmp).ExclusiveSum(pairs, pairs, agg);   // only the aggregate is used
+        __syncthreads();
+        if (valid) {
+            GroupInfo g;
+            g.start = (uint32_t)(carry[0] + sn);
+            g.n = (uint32_t)n;
+            g.c3base = (uint32_t)(carry[2] + sc);
+            g.work_off = (uint32_t)(carry[1] + sw);
+            g.W = (uint16_t)W; g.cdmax = (uint16_t)cdm; g.tiles = (uint16_t)tiles; g.pad = 0;
+            groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
+            if (r + 1 > ngroups) ngroups = r + 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry[0] += aggn; carry[1] += aggw; carry[2] += aggc; carry[3] += agg; }
+        __syncthreads();
+    }
+    // number of groups = number of valid runs
+    typedef cub::BlockReduce<unsigned long long, 1024> BR;
+    __shared__ typename BR::TempStorage tmp2;
+    unsigned long long ng = BR(tmp2).Reduce(ngroups, MaxOp());
+    if (threadIdx.x == 0) {
+        ctr->n_groups = ng;
+        ctr->n_valid = carry[0];
+        ctr->n_work = carry[1];
+        ctr->c3_words = carry[2];
+        ctr->pairs_compared = carry[3];
+    }
+}
+
+// per sorted entry: t2 row size in 16-byte units = 3 * (ceil(len0/128) + ceil(len1/128))
+__global__ void k_t2_sizes(DevIn in, const uint32_t *perm, const DevCounters *ctr, uint32_t *sizes) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= in.n_info) return;
+    uint32_t v = 0;
+    if (s < ctr->n_valid) {
+        uint32_t k = perm[s];
+        v = 3u * (((uint32_t)in.len[0][k] + 127) / 128 + ((uint32_t)in.len[1][k] + 127) / 128);
+    }
+    sizes[s] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  pack: one warp per sorted entry.  Builds the c3 row, the t2 rows and the meta record
+// straight from the caller's ASCII bytes (CloneInfo.tigs / cdr3s / vs / js).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(DevIn in, const uint32_t *perm, const GroupInfo *groups, const uint32_t *t2off,
+                                              DevCounters *ctr, EntryMeta *meta, uint32_t *c3, uint4 *t2, uint32_t *k_to_s,
+                                              int ref_v_trim, int ref_j_trim) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nvalid = (uint32_t)ctr->n_valid;
+    if (s >= nvalid) return;
+    const uint32_t k = perm[s];
+    // group of s: binary search on group starts
+    uint32_t lo = 0, hi = (uint32_t)ctr->n_groups;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (groups[mid].start <= s) lo = mid; else hi = mid; }
+    const GroupInfo g = groups[lo];
+    const uint32_t W = g.W;
+    const uint32_t c3off = g.c3base + (s - g.start) * 2 * W;
+    // ---- c3 row: CDR3 of chain 0 then chain 1, as two bit planes ----
+    const uint32_t cl0 = in.cdr3_len[0][k], cl1 = in.cdr3_len[1][k];
+    const uint8_t *q0 = in.cdr3_arena + in.cdr3_off[0][k], *q1 = in.cdr3_arena + in.cdr3_off[1][k];
+    for (uint32_t w = 0; w < W; w++) {
+        uint32_t p = w * 32 + lane;
+        int code = 0;
+        if (p < cl0 + cl1) {
+            code = base_code(p < cl0 ? q0[p] : q1[p - cl0]);
+            if (code < 0) { atomicOr(&ctr->err, ERR_CDR3_BAD_CHAR); code = 0; }
+        }
+        uint32_t H = __ballot_sync(0xFFFFFFFFu, code & 2), L = __ballot_sync(0xFFFFFFFFu, code & 1);
+        if (lane == 0) { c3[c3off + w] = H; c3[c3off + W + w] = L; }
+    }
+    // ---- t2 rows ----
+    uint32_t unit = t2off[s];
+    uint32_t mcount[2] = { 0, 0 };
+    uint32_t flags = 0;
+    uint16_t vend_[2], jstart_[2];
+    for (int c = 0; c < 2; c++) {
+        const uint32_t n = in.len[c][k];
+        const uint8_t *t = in.tig_arena + in.tig_off[c][k];
+        const uint32_t vi = in.vs_seq[c][k], ji = in.js_seq[c][k];
+        bool bad = vi >= in.n_refseq || ji >= in.n_refseq;
+        if (bad) { atomicOr(&ctr->err, ERR_BAD_REFSEQ); }
+        const uint8_t *v = bad ? t : in.refseq_arena + in.refseq_off[vi];
+        const uint8_t *j = bad ? t : in.refseq_arena + in.refseq_off[ji];
+        const int vl = bad ? 0 : (int)in.refseq_len[vi], jl = bad ? 0 : (int)in.refseq_len[ji];
+        int vend = vl - ref_v_trim;
+        if (vend > (int)n) vend = (int)n;
+        if (vend < 0) vend = 0;
+        int jw = jl - ref_j_trim;                 // J window length
+        int jstart = jw > 0 ? (int)n - jw : (int)n;
+        if (jstart < 0) jstart = 0;
+        if (jstart < vend) flags |= (FLAG_GENERIC0 << c);   // overlapping windows: count each separately -> bytewise path
+        if (in.has_del[c][k]) flags |= (FLAG_GENERIC0 << c);
+        vend_[c] = (uint16_t)vend; jstart_[c] = (uint16_t)jstart;
+        const uint32_t nblk = (n + 127) / 128;
+        for (uint32_t b = 0; b < nblk; b++) {
+            uint32_t Hw = 0, Lw = 0, Mw = 0;      // lane w (<4) keeps word w of this block
+            for (uint32_t w = 0; w < 4; w++) {
+                uint32_t p = b * 128 + w * 32 + lane;
+                int code = 0, mut = 0, weird = 0;
+                if (p < n) {
+                    uint8_t ch = t[p];
+                    code = base_code(ch);
+                    if (code < 0) { weird = 1; code = 0; }
+                    if ((int)p < vend) mut = ch != v[p];
+                    else if ((int)p >= jstart) mut = ch != j[jl - ((int)n - (int)p)];
+                }
+                uint32_t H = __ballot_sync(0xFFFFFFFFu, code & 2), L = __ballot_sync(0xFFFFFFFFu, code & 1);
+                uint32_t M = __ballot_sync(0xFFFFFFFFu, mut);
+                if (__any_sync(0xFFFFFFFFu, weird)) flags |= (FLAG_GENERIC0 << c);
+                if (lane == w) { Hw = H; Lw = L; Mw = M; }
+                mcount[c] += __popc(M);
+            }
+            // lanes 0..3 hold the four words of each plane: assemble 128-bit rows
+            uint4 rh, rl, rm;
+            rh.x = __shfl_sync(0xFFFFFFFFu, Hw, 0); rh.y = __shfl_sync(0xFFFFFFFFu, Hw, 1); rh.z = __shfl_sync(0xFFFFFFFFu, Hw, 2); rh.w = __shfl_sync(0xFFFFFFFFu, Hw, 3);
+            rl.x = __shfl_sync(0xFFFFFFFFu, Lw, 0); rl.y = __shfl_sync(0xFFFFFFFFu, Lw, 1); rl.z = __shfl_sync(0xFFFFFFFFu, Lw, 2); rl.w = __shfl_sync(0xFFFFFFFFu, Lw, 3);
+            rm.x = __shfl_sync(0xFFFFFFFFu, Mw, 0); rm.y = __shfl_sync(0xFFFFFFFFu, Mw, 1); rm.z = __shfl_sync(0xFFFFFFFFu, Mw, 2); rm.w = __shfl_sync(0xFFFFFFFFu, Mw, 3);
+            if (lane == 0) { t2[unit] = rh; t2[unit + 1] = rl; t2[unit + 2] = rm; }
+            unit += 3;
+        }
+    }
+    if (lane == 0) {
+        EntryMeta m;
+        memset(&m, 0, sizeof(m));
+        const uint32_t e = in.exact_id[k];
+        m.k = k; m.t2off = t2off[s]; m.c3off = c3off;
+        m.donor_lo = in.donor_lo[e]; m.donor_hi = in.donor_hi[e];
+        for (int c = 0; c < 2; c++) {
+            m.vref[c] = in.v_ref_id[c][k]; m.jref[c] = in.j_ref_id[c][k]; m.dref[c] = in.dref_id[c][k];
+            m.vs[c] = in.vs_seq[c][k]; m.js[c] = in.js_seq[c][k]; m.vname[c] = in.vname_id[c][k];
+            m.len[c] = in.len[c][k]; m.cs[c] = in.cdr3_start[c][k]; m.cl[c] = in.cdr3_len[c][k];
+            m.m[c] = (uint16_t)mcount[c]; m.vend[c] = vend_[c]; m.jstart[c] = jstart_[c];
+        }
+        m.c_light = in.c_ref_id_light[k];
+        m.hcomp = in.hcomp[k]; m.fr1 = in.fr1[k]; m.cdr1 = in.cdr1[k]; m.fr2 = in.fr2[k]; m.cdr2 = in.cdr2[k]; m.fr3 = in.fr3[k];
+        m.flags = (uint16_t)flags;
+        meta[s] = m;
+        k_to_s[k] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  tier 1: all pairs of a comparison group, CDR3 XOR/popcount against the group's cd cap.
+// One CTA (128 threads) per 128x128 tile of the pair triangle; tiles are staged into shared
+// memory with 1-D bulk TMA copies; each thread keeps one A row in registers and sweeps the B
+// rows (broadcast reads).  Survivors are appended with one warp-aggregated atomic per 32x32
+// sub-block.  Work items are handed out by a global atomic counter (persistent CTAs).
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void t1_sweep(const uint32_t *__restrict__ sA, const uint32_t *__restrict__ sB, uint32_t rowsA, uint32_t rowsB,
+                                         bool diag, uint32_t cdmax, uint32_t posA0, uint32_t posB0, uint2 *cand,
+                                         unsigned long long cand_cap, DevCounters *ctr) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    uint32_t aH[W], aL[W];
+    const bool validA = tid < rowsA;
+#pragma unroll
+    for (int w = 0; w < W; w++) { aH[w] = validA ? sA[tid * 2 * W + w] : 0u; aL[w] = validA ? sA[tid * 2 * W + W + w] : 0u; }
+    for (uint32_t b0 = 0; b0 < rowsB; b0 += 32) {
+        // a warp whose A rows all lie at or after this B block has nothing to do on a diagonal tile
+        if (diag && (tid & ~31u) >= b0 + 32) continue;
+        uint32_t bits = 0;
+#pragma unroll 4
+        for (uint32_t bb = 0; bb < 32; bb++) {
+            const uint32_t *rb = sB + (b0 + bb) * 2 * W;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) cnt += __popc((aH[w] ^ rb[w]) | (aL[w] ^ rb[W + w]));
+            bits |= (cnt <= cdmax ? 1u : 0u) << bb;
+        }
+        // mask: rows beyond the tile, invalid A, and (on the diagonal) pairs with b <= a
+        uint32_t nb = rowsB - b0;
+        if (nb < 32) bits &= (1u << nb) - 1u;
+        if (!validA) bits = 0;
+        if (diag) {
+            if (tid >= b0 + 31) bits = 0;
+            else if (tid >= b0) bits &= ~((2u << (tid - b0)) - 1u);
+        }
+        if (__any_sync(0xFFFFFFFFu, bits != 0)) {
+            uint32_t cntl = __popc(bits), incl = cntl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+            uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->n_cand, (unsigned long long)total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cntl);
+            while (bits) {
+                uint32_t bb = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (base < cand_cap) cand[base] = make_uint2(posA0 + tid, posB0 + b0 + bb);
+                base++;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(T1_TILE) k_tier1(const GroupInfo *__restrict__ groups, const uint32_t *__restrict__ c3, DevCounters *ctr,
+                                                   uint2 *cand, unsigned long long cand_cap, uint32_t stride, uint32_t phase) {
+    __shared__ __align__(128) uint32_t sA[T1_TILE * 2 * T1_WMAX];
+    __shared__ __align__(128) uint32_t sB[T1_TILE * 2 * T1_WMAX + 32 * 2 * T1_WMAX];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_item;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    uint32_t parity = 0;
+    const uint32_t ngroups = (uint32_t)ctr->n_groups;
+    const unsigned long long nwork = ctr->n_work;
+    for (;;) {
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&ctr->work_next, 1ull);
+        __syncthreads();
+        const unsigned long long item = (unsigned long long)s_item * stride + phase;
+        if (item >= nwork) break;
+        // group of the item
+        uint32_t lo = 0, hi = ngroups;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (groups[mid].work_off <= item) lo = mid; else hi = mid; }
+        const GroupInfo g = groups[lo];
+        // triangular decode: item t -> (ia <= ib), row ia has (T - ia) items
+        const uint32_t T = g.tiles;
+        uint32_t t = (uint32_t)(item - g.work_off), ia = 0;
+        {
+            // ia = largest i with i*T - i(i-1)/2 <= t
+            double Td = (double)T + 0.5;
+            int guess = (int)(Td - sqrt(Td * Td - 2.0 * (double)t));
+            if (guess < 0) guess = 0;
+            if (guess >= (int)T) guess = (int)T - 1;
+            ia = (uint32_t)guess;
+            while (ia > 0 && (unsigned long long)ia * T - (unsigned long long)ia * (ia - 1) / 2 > t) ia--;
+            while ((unsigned long long)(ia + 1) * T - (unsigned long long)(ia + 1) * ia / 2 <= t) ia++;
+        }
+        const uint32_t ib = ia + (t - (uint32_t)((unsigned long long)ia * T - (unsigned long long)ia * (ia - 1) / 2));
+        const bool diag = ia == ib;
+        const uint32_t W = g.W;
+        const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE), rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
+        const uint32_t *gA = c3 + g.c3base + (size_t)ia * T1_TILE * 2 * W;
+        const uint32_t *gB = c3 + g.c3base + (size_t)ib * T1_TILE * 2 * W;
+        if (tid == 0) {
+            uint32_t bytesA = (rowsA * 2 * W * 4 + 15) & ~15u, bytesB = (rowsB * 2 * W * 4 + 15) & ~15u;
+            fence_proxy_async();
+            mbar_expect_tx(&bar, bytesA + (diag ? 0u : bytesB));
+            tma_load_1d(sA, gA, bytesA, &bar);
+            if (!diag) tma_load_1d(sB, gB, bytesB, &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        const uint32_t *pB = diag ? sA : sB;
+        const uint32_t posA0 = g.start + ia * T1_TILE, posB0 = g.start + ib * T1_TILE;
+        switch (W) {
+            case 1: t1_sweep<1>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+            case 2: t1_sweep<2>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+            case 3: t1_sweep<3>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+            case 4: t1_sweep<4>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+            case 5: t1_sweep<5>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+            case 6: t1_sweep<6>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+            case 7: t1_sweep<7>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+            default: t1_sweep<8>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
+        }
+        __syncthreads();   // everyone is done with the tiles before the next TMA overwrites them
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decision logic shared by the bit-parallel and the bytewise tier-2 paths (App. A.4 j-n).
+// ---------------------------------------------------------------------------------------------
+struct PairCounts {
+    int cd0, cd1, diffs;
+    int shares[2], indeps[2], indeps_out[2];
+    int det[2][4];
+    int nrefs;
+    int dfw, lfw, dc12, l12;     // FWR1 / CDR1+CDR2 region counts; lfw == 0 when the gate is skipped
+};
+
+__device__ __forceinline__ double p1_lookup(const DevTables &tb, int L, int k, int d, DevCounters *ctr) {
+    if (d <= 0) return 1.0;
+    if (d >= P1_DCAP) return 0.0;        // below the reference's double-double noise floor
+    if (k >= P1_KCAP) { atomicOr(&ctr->err, ERR_K_TOO_LARGE); return 1.0; }
+    const double *tab = tb.p1tab[L];
+    return tab[d * P1_KCAP + k];
+}
+
+// returns accept_reason (0 = reject); fills k, d, p1, mult, score
+__device__ __forceinline__ int decide(const DevParams &pr, const DevTables &tb, const EntryMeta &m1, const EntryMeta &m2,
+                                      const PairCounts &pc, DevCounters *ctr, int *kout, int *dout, double *p1o, double *multo,
+                                      double *scoreo) {
+    const int cd = pc.cd0 + pc.cd1;
+    if (pc.nrefs == 2) { int df = pc.shares[0] - pc.shares[1]; if (df < 0) df = -df; if (df > pr.max_degradation) return 0; }
+    int d = pc.shares[0], mi = pc.indeps[0], mo = pc.indeps_out[0];
+    if (pc.nrefs == 2) { d = min(d, pc.shares[1]); mi = min(mi, pc.indeps[1]); mo = min(mo, pc.indeps_out[1]); }
+    const int k = mi + 2 * d;
+    const int L = (int)m1.len[0] + (int)m1.len[1];
+    const double p1 = p1_lookup(tb, L, k, d, ctr);
+    const MultInfo mi2 = tb.multinfo[((uint32_t)m1.cl[0] << 8) | m1.cl[1]];
+    const double mult = tb.multpool[mi2.off + (uint32_t)pc.cd0 * mi2.d1p1 + (uint32_t)pc.cd1];
+    const double score = __dmul_rn(p1, mult);
+    int reason = 0;
+    if (!(score > pr.max_score)) reason |= 1;
+    if (d >= pr.auto_share) reason |= 2;
+    {
+        int hc = min((int)m1.hcomp, (int)m2.hcomp);
+        if (hc - cd >= pr.comp_filt && pc.diffs - cd <= pr.comp_filt_bound) reason |= 4;
+    }
+    if (!reason) return 0;
+    if (pr.is_bcr && pc.lfw > 0) {
+        const double ifw = __dmul_rn(100.0, __dsub_rn(1.0, __ddiv_rn((double)pc.dfw, (double)pc.lfw)));
+        const double i12 = __dmul_rn(100.0, __dsub_rn(1.0, __ddiv_rn((double)pc.dc12, (double)pc.l12)));
+        if (__dsub_rn(ifw, i12) >= pr.fwr1_cdr12_delta) return 0;
+    }
+    {
+        int x = mo > 1 ? mo : 1;
+        if (cd >= pr.cdr3_mult * x) return 0;
+    }
+    *kout = k; *dout = d; *p1o = p1; *multo = mult; *scoreo = score;
+    return reason;
+}
+
+// cheap gates that need only the meta records (App. A.4 e-g); returns 0 = reject, 1 = pass; *err = cross-donor
+__device__ __forceinline__ int meta_gates(const DevParams &pr, const DevIn &in, const EntryMeta &m1, const EntryMeta &m2, int cd, int *err) {
+    int e = 0;
+    if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
+        e = !(m1.donor_lo == m1.donor_hi && m2.donor_lo == m2.donor_hi && m1.donor_lo == m2.donor_lo);
+    *err = e;
+    if (e && !pr.mix_donors) return 0;
+    if (pr.is_bcr && !pr.old_light && cd > 0 && m1.c_light != m2.c_light) return 0;
+    for (int c = 0; c < 2; c++) {
+        if (m1.vname[c] == m2.vname[c]) continue;
+        // V names differ: universal V references must agree after right-truncation, and the
+        // 5'UTR references (when both known) after left-truncation (help1.rs:328-331)
+        uint32_t a = in.vuni_seq[c][m1.k], b = in.vuni_seq[c][m2.k];
+        if (a >= in.n_refseq || b >= in.n_refseq) return 0;
+        uint32_t la = in.refseq_len[a], lb = in.refseq_len[b], mlen = la < lb ? la : lb;
+        const uint8_t *ra = in.refseq_arena + in.refseq_off[a], *rb = in.refseq_arena + in.refseq_off[b];
+        for (uint32_t i = 0; i < mlen; i++) if (ra[i] != rb[i]) return 0;
+        uint32_t ua = in.utr_seq[c][m1.k], ub = in.utr_seq[c][m2.k];
+        if (ua != EJOIN_NONE && ub != EJOIN_NONE && ua < in.n_refseq && ub < in.n_refseq) {
+            uint32_t lua = in.refseq_len[ua], lub = in.refseq_len[ub], mu = lua < lub ? lua : lub;
+            const uint8_t *pa = in.refseq_arena + in.refseq_off[ua] + (lua - mu), *pb = in.refseq_arena + in.refseq_off[ub] + (lub - mu);
+            for (uint32_t i = 0; i < mu; i++) if (pa[i] != pb[i]) return 0;
+        }
+    }
+    return 1;
+}
+
+__device__ __forceinline__ bool region_bounds(const EntryMeta &a, const EntryMeta &b, int *f1, int *c1, int *f2, int *c2, int *f3) {
+    // k1's bounds, provided both entries know all of theirs (oracle_fwr1_cdr12_counts)
+    if (a.fr1 == EJOIN_NONE16 || a.cdr1 == EJOIN_NONE16 || a.fr2 == EJOIN_NONE16 || a.cdr2 == EJOIN_NONE16 || a.fr3 == EJOIN_NONE16) return false;
+    if (b.fr1 == EJOIN_NONE16 || b.cdr1 == EJOIN_NONE16 || b.fr2 == EJOIN_NONE16 || b.cdr2 == EJOIN_NONE16 || b.fr3 == EJOIN_NONE16) return false;
+    *f1 = a.fr1; *c1 = a.cdr1; *f2 = a.fr2; *c2 = a.cdr2; *f3 = a.fr3;
+    if (!(*f1 < *c1 && *c1 <= *f2 && *f2 <= *c2 && *c2 <= *f3 && *f3 <= (int)a.len[0] && (*f2 - *c1) + (*f3 - *c2) > 0)) return false;
+    return true;
+}
+
+__device__ __forceinline__ void emit_raw(const DevParams &pr, DevCounters *ctr, ejoin_raw_edge_t *acc, unsigned long long cap,
+                                         uint32_t *minnbr, uint32_t k1, uint32_t k2, int cd, int d, int reason, int err, bool accepted) {
+    // warp-aggregated append
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t mask = __ballot_sync(__activemask(), accepted);
+    if (!accepted) return;
+    uint32_t leader = __ffs(mask) - 1, rank = __popc(mask & ((1u << lane) - 1u));
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&ctr->n_accept, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader) + rank;
+    if (base < cap) {
+        ejoin_raw_edge_t e;
+        e.k1 = k1; e.k2 = k2; e.cd = (uint16_t)cd; e.d = (uint16_t)min(d, 65535);
+        e.flags = (uint32_t)reason | ((uint32_t)err << 8);
+        acc[base] = e;
+    }
+    atomicMin(&minnbr[k1], k2);
+    atomicMin(&minnbr[k2], k1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  tier 2, bit-parallel: one thread per tier-1 survivor.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *cand,
+                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t *minnbr,
+                                               uint32_t k_base) {
+    unsigned long long ncand = ctr->n_cand;
+    if (ncand > cand_cap) ncand = cand_cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((ncand + 31) & ~31ull);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        bool accepted = false;
+        uint32_t k1 = 0, k2 = 0;
+        int cd = 0, d = 0, reason = 0, err = 0;
+        if (i < ncand) {
+            uint2 c = cand[i];
+            const EntryMeta *pa = &tb.meta[c.x], *pb = &tb.meta[c.y];
+            if (pa->k > pb->k) { const EntryMeta *t = pa; pa = pb; pb = t; }   // k1 < k2 in info order
+            const EntryMeta &m1 = *pa, &m2 = *pb;
+            k1 = m1.k; k2 = m2.k;
+            // CDR3 differences per chain from the c3 rows
+            const uint32_t cl0 = m1.cl[0], total = cl0 + m1.cl[1], W = max(1u, (total + 31) / 32);
+            int cd0 = 0, cdt = 0;
+            for (uint32_t w = 0; w < W; w++) {
+                uint32_t D = (tb.c3[m1.c3off + w] ^ tb.c3[m2.c3off + w]) | (tb.c3[m1.c3off + W + w] ^ tb.c3[m2.c3off + W + w]);
+                cdt += __popc(D);
+                cd0 += __popc(D & range_mask((int)w, 0, (int)cl0));
+            }
+            cd = cdt;
+            const int cd1 = cdt - cd0;
+            bool ok = true;
+            const uint32_t cdm = tb.cdmax[total];
+            if (cdm == 0xFFFF || (uint32_t)cd > cdm) ok = false;       // CDR3 gates (A.4-d), same table as tier 1
+            if (ok && !meta_gates(pr, in, m1, m2, cd, &err)) ok = false;
+            if (ok) {
+                atomicAdd(&ctr->pairs_tier2, 1ull);
+                const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] ||
+                                     m1.vs[1] != m2.vs[1] || m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
+                if (generic) {
+                    unsigned long long q = atomicAdd(&ctr->n_generic, 1ull);
+                    if (q < cand_cap) generic_q[q] = make_uint2(pa == &tb.meta[c.x] ? c.x : c.y, pa == &tb.meta[c.x] ? c.y : c.x);
+                    ok = false;
+                }
+            }
+            if (ok) {
+                PairCounts pc;
+                pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1;
+                for (int c2 = 0; c2 < 2; c2++)
+                    if (m1.vref[c2] != m2.vref[c2] || m1.dref[c2] != m2.dref[c2] || m1.jref[c2] != m2.jref[c2]) pc.nrefs = 2;
+                int diffs = 0, shares = 0;
+                const uint4 *r1 = tb.t2 + m1.t2off, *r2 = tb.t2 + m2.t2off;
+                const uint32_t nblk = ((uint32_t)m1.len[0] + 127) / 128 + ((uint32_t)m1.len[1] + 127) / 128;
+                for (uint32_t b = 0; b < nblk; b++) {
+                    uint4 h1 = r1[3 * b], l1 = r1[3 * b + 1], x1 = r1[3 * b + 2];
+                    uint4 h2 = r2[3 * b], l2 = r2[3 * b + 1], x2 = r2[3 * b + 2];
+                    uint32_t D0 = (h1.x ^ h2.x) | (l1.x ^ l2.x), D1 = (h1.y ^ h2.y) | (l1.y ^ l2.y);
+                    uint32_t D2 = (h1.z ^ h2.z) | (l1.z ^ l2.z), D3 = (h1.w ^ h2.w) | (l1.w ^ l2.w);
+                    diffs += __popc(D0) + __popc(D1) + __popc(D2) + __popc(D3);
+                    shares += __popc(x1.x & x2.x & ~D0) + __popc(x1.y & x2.y & ~D1) + __popc(x1.z & x2.z & ~D2) + __popc(x1.w & x2.w & ~D3);
+                }
+                const int mm = (int)m1.m[0] + (int)m1.m[1] + (int)m2.m[0] + (int)m2.m[1];
+                pc.diffs = diffs;
+                pc.shares[0] = pc.shares[1] = shares;
+                pc.indeps[0] = pc.indeps[1] = mm - 2 * shares;
+                pc.indeps_out[0] = pc.indeps_out[1] = 1 << 20;    // filled below only when the CDR3_MULT rule can bite
+                // total-difference cap (A.4-c)
+                if (!pr.is_bcr || pr.max_diffs < 1000000) {
+                    int cap = pr.max_diffs;
+                    if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
+                    if (diffs > cap) ok = false;
+                }
+                if (ok) {
+                    // FWR1 vs CDR1+CDR2 on the heavy chain (A.4-m)
+                    pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
+                    int f1, c1, f2, c2_, f3;
+                    if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3)) {
+                        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
+                        int dfw = 0, d12 = 0;
+                        for (int w = f1 >> 5; w <= (f3 - 1) >> 5; w++) {
+                            const int blk = w >> 2, q = w & 3;
+                            uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
+                            dfw += __popc(D & range_mask(w, f1, c1));
+                            d12 += __popc(D & (range_mask(w, c1, f2) | range_mask(w, c2_, f3)));
+                        }
+                        pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_);
+                    }
+                    // non-shared mutations outside the CDR3s (A.4-n), only when cd >= CDR3_MULT
+                    if (cd >= pr.cdr3_mult) {
+                        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
+                        int io = 0, blk0 = 0;
+                        for (int c2 = 0; c2 < 2; c2++) {
+                            const int nw = ((int)m1.len[c2] + 127) / 128 * 4;
+                            const int a1 = m1.cs[c2], a2 = m2.cs[c2], cl = m1.cl[c2];
+                            for (int w = 0; w < nw; w++) {
+                                const int blk = blk0 + (w >> 2), q = w & 3;
+                                uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
+                                uint32_t R = range_mask(w, a1, a1 + cl) | range_mask(w, a2, a2 + cl);
+                                io += __popc(w1[blk * 12 + 8 + q] & D & ~R) + __popc(w2[blk * 12 + 8 + q] & D & ~R);
+                            }
+                            blk0 += nw / 4;
+                        }
+                        pc.indeps_out[0] = pc.indeps_out[1] = io;
+                    }
+                    int kk; double p1, mult, score;
+                    reason = decide(pr, tb, m1, m2, pc, ctr, &kk, &d, &p1, &mult, &score);
+                    accepted = reason != 0;
+                }
+            }
+        }
+        emit_raw(pr, ctr, acc, cand_cap, minnbr, k1 + k_base, k2 + k_base, cd, d, reason, err, accepted);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bytewise evaluator: one warp per pair, straight from the ASCII bytes — for entries the
+// bit-parallel path cannot represent (has_del / non-ACGT / overlapping windows), for pairs
+// whose germlines differ (nrefs = 2 with explicit references), and for the full payload of
+// the emitted edges.  Mirrors join_one's loops (App. A.4 c,d,i,m).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t k1 = m1.k, k2 = m2.k;
+    int nrefs = 1;
+    for (int c = 0; c < 2; c++)
+        if (m1.vref[c] != m2.vref[c] || m1.dref[c] != m2.dref[c] || m1.jref[c] != m2.jref[c]) nrefs = 2;
+    pc.nrefs = nrefs;
+    int diffs = 0, cdc[2] = { 0, 0 };
+    int sh[2] = { 0, 0 }, in_[2] = { 0, 0 }, io[2] = { 0, 0 }, det[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+    for (int c = 0; c < 2; c++) {
+        const int n = m1.len[c];
+        const uint8_t *t1 = in.tig_arena + in.tig_off[c][k1], *t2 = in.tig_arena + in.tig_off[c][k2];
+        for (int p = lane; p < n; p += 32) diffs += t1[p] != t2[p];
+        const uint8_t *q1 = in.cdr3_arena + in.cdr3_off[c][k1], *q2 = in.cdr3_arena + in.cdr3_off[c][k2];
+        for (int p = lane; p < (int)m1.cl[c]; p += 32) cdc[c] += q1[p] != q2[p];
+        const int a1 = m1.cs[c], a2 = m2.cs[c], cl = m1.cl[c];
+        for (int u = 0; u < nrefs; u++) {
+            const EntryMeta &mu = u == 0 ? m1 : m2;
+            const uint8_t *v = in.refseq_arena + in.refseq_off[mu.vs[c]], *j = in.refseq_arena + in.refseq_off[mu.js[c]];
+            const int vl = (int)in.refseq_len[mu.vs[c]], jl = (int)in.refseq_len[mu.js[c]];
+            int vend = vl - pr.ref_v_trim;
+            if (vend > n) vend = n;
+            for (int p = lane; p < vend; p += 32) {
+                const uint8_t r = v[p];
+                const int out = !((p >= a1 && p < a1 + cl) || (p >= a2 && p < a2 + cl));
+                if (t1[p] == t2[p]) { if (t1[p] != r) { sh[u]++; det[u][2 * c]++; } }
+                else { int q = (t1[p] != r) + (t2[p] != r); in_[u] += q; if (out) io[u] += q; }
+            }
+            int jstart = n - (jl - pr.ref_j_trim);
+            if (jstart < 0) jstart = 0;
+            if (jl - pr.ref_j_trim > 0)
+                for (int p = jstart + lane; p < n; p += 32) {
+                    const uint8_t r = j[jl - (n - p)];
+                    const int out = !((p >= a1 && p < a1 + cl) || (p >= a2 && p < a2 + cl));
+                    if (t1[p] == t2[p]) { if (t1[p] != r) { sh[u]++; det[u][2 * c + 1]++; } }
+                    else { int q = (t1[p] != r) + (t2[p] != r); in_[u] += q; if (out) io[u] += q; }
+                }
+        }
+    }
+    pc.diffs = warp_sum(diffs); pc.cd0 = warp_sum(cdc[0]); pc.cd1 = warp_sum(cdc[1]);
+    for (int u = 0; u < 2; u++) {
+        pc.shares[u] = warp_sum(sh[u]); pc.indeps[u] = warp_sum(in_[u]); pc.indeps_out[u] = warp_sum(io[u]);
+        for (int q = 0; q < 4; q++) pc.det[u][q] = warp_sum(det[u][q]);
+    }
+    pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
+    int f1, c1, f2, c2, f3;
+    if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2, &f3)) {
+        const uint8_t *t1 = in.tig_arena + in.tig_off[0][k1], *t2 = in.tig_arena + in.tig_off[0][k2];
+        int dfw = 0, d12 = 0;
+        for (int p = f1 + lane; p < c1; p += 32) dfw += t1[p] != t2[p];
+        for (int p = c1 + lane; p < f2; p += 32) d12 += t1[p] != t2[p];
+        for (int p = c2 + lane; p < f3; p += 32) d12 += t1[p] != t2[p];
+        pc.dfw = warp_sum(dfw); pc.dc12 = warp_sum(d12); pc.lfw = c1 - f1; pc.l12 = (f2 - c1) + (f3 - c2);
+    }
+}
+
+// K6  tier 2, bytewise: one warp per queued pair (already past the CDR3 and meta gates).
+__global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *generic_q,
+                                                       unsigned long long cap, ejoin_raw_edge_t *acc, uint32_t *minnbr, uint32_t k_base) {
+    unsigned long long nq = ctr->n_generic;
+    if (nq > cap) nq = cap;
+    const uint32_t lane = threadIdx.x & 31;
+    for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq;
+         i += ((unsigned long long)gridDim.x * blockDim.x) >> 5) {
+        const uint2 c = generic_q[i];
+        const EntryMeta m1 = tb.meta[c.x], m2 = tb.meta[c.y];      // already ordered k1 < k2
+        PairCounts pc;
+        bytewise_counts(in, pr, m1, m2, pc);
+        bool ok = true;
+        if (!pr.is_bcr || pr.max_diffs < 1000000) {
+            int capd = pr.max_diffs;
+            if (!pr.is_bcr && pr.max_diffs_tcr < capd) capd = pr.max_diffs_tcr;
+            if (pc.diffs > capd) ok = false;
+        }
+        int reason = 0, kk = 0, d = 0, err = 0;
+        double p1, mult, score;
+        if (ok) {
+            if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
+                err = !(m1.donor_lo == m1.donor_hi && m2.donor_lo == m2.donor_hi && m1.donor_lo == m2.donor_lo);
+            reason = decide(pr, tb, m1, m2, pc, ctr, &kk, &d, &p1, &mult, &score);
+        }
+        if (lane == 0) emit_raw(pr, ctr, acc, cap, minnbr, m1.k + k_base, m2.k + k_base, pc.cd0 + pc.cd1, d, reason, err, reason != 0);
+    }
+}
+
+// K7  payload: the full PotentialJoin record of each emitted edge, one warp per edge.
+__global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *k_to_s,
+                                                 const uint2 *pairs, uint32_t npairs, uint32_t k_base, ejoin_edge_t *out) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < npairs; i += (gridDim.x * blockDim.x) >> 5) {
+        const uint2 kk2 = pairs[i];
+        const EntryMeta m1 = tb.meta[k_to_s[kk2.x - k_base]], m2 = tb.meta[k_to_s[kk2.y - k_base]];
+        PairCounts pc;
+        bytewise_counts(in, pr, m1, m2, pc);
+        int kk = 0, d = 0, err = 0;
+        double p1 = 0, mult = 0, score = 0;
+        if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
+            err = !(m1.donor_lo == m1.donor_hi && m2.donor_lo == m2.donor_hi && m1.donor_lo == m2.donor_lo);
+        int reason = decide(pr, tb, m1, m2, pc, ctr, &kk, &d, &p1, &mult, &score);
+        if (lane == 0) {
+            ejoin_edge_t e;
+            memset(&e, 0, sizeof(e));
+            e.k1 = kk2.x; e.k2 = kk2.y;
+            for (int u = 0; u < pc.nrefs; u++) {
+                e.shares[u] = pc.shares[u]; e.indeps[u] = pc.indeps[u];
+                for (int q = 0; q < 4; q++) e.shares_details[u][q] = (uint16_t)pc.det[u][q];
+            }
+            e.nrefs = (uint16_t)pc.nrefs; e.cd = (uint16_t)(pc.cd0 + pc.cd1); e.cd_chain[0] = (uint16_t)pc.cd0; e.cd_chain[1] = (uint16_t)pc.cd1;
+            e.diffs = (uint32_t)pc.diffs; e.k = (uint16_t)kk; e.d = (uint16_t)d;
+            e.n = 3u * ((uint32_t)m1.len[0] + (uint32_t)m1.len[1]);
+            e.err = (uint8_t)err; e.accept_reason = (uint8_t)reason;
+            e.p1 = p1; e.mult = mult; e.score = score;
+            out[i] = e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8  prune: an accepted edge (k1,k2) whose endpoints share a smaller common neighbour m < k1 is
+// skipped by the ordered replay (the edges (m,k1),(m,k2) come first: SURVEY §7.4-7, App. A.8),
+// so it can be dropped before the sort.  Kept edges get the 64-bit key k1<<32|k2.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prune(const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *minnbr,
+                        unsigned long long *keys, unsigned long long *vals) {
+    unsigned long long n = ctr->n_accept;
+    if (n > cap) n = cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ull);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        bool keep = false;
+        ejoin_raw_edge_t e;
+        if (i < n) {
+            e = acc[i];
+            uint32_t a = minnbr[e.k1], b = minnbr[e.k2];
+            keep = !(a == b && a < e.k1);
+        }
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
+        if (!mask) continue;
+        const uint32_t lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->n_kept, (unsigned long long)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(mask & ((1u << lane) - 1u));
+        if (keep) {
+            keys[base] = ((unsigned long long)e.k1 << 32) | e.k2;
+            vals[base] = ((unsigned long long)e.flags << 32) | ((unsigned long long)e.d << 16) | e.cd;
+        }
+    }
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// p1 tables: one block per n (= 3 * L), see dd.cuh.  Phase 1: T_j(k) into scratch;
+// phase 2: p1[d][k] = 1 - T_0 - ... - T_{d-1}, clamped at 0 like the reference.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(P1_DCAP) k_p1_tables(const uint32_t *Ls, double *const *tabs, dd_t *scratch) {
+    __shared__ dd_t F[P1_KCAP + 1];
+    __shared__ dd_t B[2][P1_DCAP];
+    const double n = 3.0 * (double)Ls[blockIdx.x];
+    double *tab = tabs[blockIdx.x];
+    dd_t *T = scratch + (size_t)blockIdx.x * P1_KCAP * P1_DCAP;
+    const int j = threadIdx.x;
+    if (j == 0) {
+        dd_t f = dd_from(1.0);
+        F[0] = f;
+        for (int u = 0; u < P1_KCAP; u++) { f = p1_f_step(f, u, n); F[u + 1] = f; }
+    }
+    B[0][j] = dd_from(j == 0 ? 1.0 : 0.0);           // k = 0
+    __syncthreads();
+    T[j] = j == 0 ? F[0] : dd_from(0.0);
+    for (int k = 1; k < P1_KCAP; k++) {
+        const dd_t *prev = B[(k - 1) & 1];
+        dd_t b = p1_b_step(k, j, prev[j > 0 ? j - 1 : 0], prev[j], n);
+        B[k & 1][j] = b;
+        T[(size_t)k * P1_DCAP + j] = j <= k ? dd_mul(b, F[k - j]) : dd_from(0.0);
+        __syncthreads();
+    }
+    for (int k = j; k < P1_KCAP; k += P1_DCAP) {
+        dd_t p = dd_from(1.0);
+        for (int d = 0; d < P1_DCAP; d++) {
+            double v = dd_to_double(p);
+            tab[(size_t)d * P1_KCAP + k] = v < 0.0 ? 0.0 : v;
+            p = dd_sub(p, T[(size_t)k * P1_DCAP + d]);
+        }
+    }
+}

