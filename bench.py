@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — join pairs scored per second on synthetic repertoires (BASELINE.json's metric).
+
+One "step" = one pass of the join stage over the workload.
+  value : device-resident step (inputs already in HBM): keys -> sort -> groups -> pack ->
+          tier 1 -> tier 2 -> prune -> sort of kept edges, wall clock around K steps.
+  e2e   : the same workload through the C-ABI call ejoin_run() with HOST buffers: H2D of
+          the flat JoinPack, the device pipeline, D2H of the edges, ordered replay, payload
+          and partition — the call a user of the library makes.
+  pairs : candidate pairs = sum over lens buckets of n_b (n_b - 1) / 2.
+Workload: BASELINE.json configs[2] (the ~1.6M-cell pooled BCR run the metric's target
+sentence names), which fits one GPU; N > 1 shards its buckets over the ranks (strong scaling).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C3] [--scale S]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    "C1": "synthetic 123085-like BCR, 1,654 cells, 1 donor",
+    "C2": "synthetic 100k-cell BCR repertoire, 1 donor",
+    "C3": "synthetic 1.6M-cell 8-donor pooled BCR repertoire",
+    "C4": "adversarial single giant bucket, 200k exact subclonotypes",
+    "C5": "synthetic 1M-cell 4-donor TCR repertoire",
+}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_workload(name, scale, pinned):
+    """Generate the synthetic repertoire; with pinned=True the big arenas come from
+    ejoin_host_alloc and the smaller arrays are pinned in place (cudaHostRegister)."""
+    from enclone_b200 import synth
+    kw = {}
+    L = None
+    if pinned:
+        from enclone_b200 import _lib
+        L = _lib.load()
+        kw = dict(alloc=C.cast(L.ejoin_host_alloc, C.c_void_p).value, dealloc=C.cast(L.ejoin_host_free, C.c_void_p).value)
+    cfg = dict(synth.CONFIGS[name])
+    cfg["n_cells"] = max(16, int(cfg["n_cells"] * scale))
+    t0 = time.time()
+    sp, truth = synth.generate(copy=False, **cfg, **kw)
+    gen_s = time.time() - t0
+    registered = []
+    if pinned:
+        st = sp.struct
+        n, nx, nr = st.n_info, st.n_exact, st.n_refseq
+        from enclone_b200._abi import _PACK_ARRAYS
+        import numpy as np
+        counts = {"nchains": nx, "ncells": nx, "donor_lo": nx, "donor_hi": nx, "refseq_off": nr, "refseq_len": nr}
+        for fname, dt, per_chain in _PACK_ARRAYS:
+            cnt = counts.get(fname, n)
+            ptrs = [getattr(st, fname)[c] for c in range(2)] if per_chain else [getattr(st, fname)]
+            for p in ptrs:
+                addr = C.cast(p, C.c_void_p).value
+                nbytes = cnt * np.dtype(dt).itemsize
+                if addr and nbytes >= (1 << 16) and L.ejoin_host_register(addr, nbytes) == 0:
+                    registered.append(addr)
+    return sp, gen_s, (L, registered)
+
+
+def cpu_baseline(sp, params, target_s=12.0, steps=1, warmup=0):
+    """The CPU restatement of the reference join (oracle/), all host threads, on a bounded
+    representative sample: every stride-th lens bucket.  Returns (pairs/s, info)."""
+    import oracle_lib as O
+    threads = os.cpu_count() or 1
+    O.lib().oracle_prepare(700)
+    # pilot to size the sample
+    stride = 64
+    t0 = time.time()
+    _, _, st = O.join_exacts(sp.struct, params, threads=threads, stride=stride, phase=1)
+    dt = max(time.time() - t0, 1e-3)
+    est_full = dt * stride
+    stride = max(1, int(round(est_full / target_s)))
+    times, pairs = [], 0
+    for it in range(warmup + steps):
+        t0 = time.time()
+        _, _, st = O.join_exacts(sp.struct, params, threads=threads, stride=stride, phase=0)
+        dt = time.time() - t0
+        if it >= warmup:
+            times.append(dt)
+        pairs = st["pairs_candidate"]
+    sec = sum(times) / len(times)
+    info = {"cores": threads, "kind": "port",
+            "sample": f"every {stride}-th lens bucket of the workload ({st['n_buckets']} buckets scanned, {pairs} candidate pairs, "
+                      f"{st['pairs_evaluated']} evaluated after skip-if-joined, {sec:.2f} s per pass)",
+            "pairs": pairs, "seconds": sec, "stride": stride}
+    return pairs / sec, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = max(args.warmup, 0)
+    K = max(args.steps, 1)
+    from enclone_b200._abi import default_params
+    params = default_params()
+    config = {"workload": f"{args.workload}: {WORKLOADS[args.workload]}" + (f" (scale {args.scale})" if args.scale != 1.0 else ""),
+              "generator": "tools/synth.cpp, seed 20261019+config id", "join_params": "enclone defaults (SURVEY.md table P)"}
+
+    if args.impl == "reference":
+        # The reference's own join is Rust in an un-vendored dependency and cannot be built in this
+        # image, so this arm times the CPU restatement (oracle/) on the host cores.  Rank 0 only.
+        if rank != 0:
+            return
+        sp, gen_s, _ = make_workload(args.workload, args.scale, pinned=False)
+        per_step = max(3.0, min(12.0, 60.0 / (K + W)))
+        val, info = cpu_baseline(sp, params, target_s=per_step, steps=K, warmup=W)
+        config.update({"n_info": sp.n_info})
+        line = {"impl": "reference", "metric": "join pairs scored/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": K,
+                "warmup": W, "ms_per_step": info["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u32 popcount + f64 score", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+                "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from enclone_b200.join import Joiner
+    from enclone_b200._abi import RAW_EDGE_DTYPE
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the join has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sp, gen_s, pin = make_workload(args.workload, args.scale, pinned=True)
+    j = Joiner(params, device=local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- e2e: host buffers -> result, through the C ABI ----------------
+    def e2e_step():
+        if world == 1:
+            return j.run(sp.struct)
+        from enclone_b200.dist import sharded_join
+        pairs, cls, st, fin = sharded_join(j, sp.struct, rank, world, device=dev)   # includes the NCCL all-gather of edges
+        fin.stats.update({k: v for k, v in st.items() if k in ("h2d_bytes", "ms_h2d", "d2h_bytes")})
+        fin.edges = pairs
+        return fin
+
+    for _ in range(W):
+        res = e2e_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        res = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_stats = res.stats
+    # ---------------- value: inputs resident in HBM ----------------
+    if world == 1:
+        j.upload(sp.struct)
+    # (N > 1: run_shard left this rank's shard resident)
+    for _ in range(W):
+        st = j.run_resident()
+    barrier()
+    t0 = time.perf_counter()
+    acc = {}
+    for _ in range(K):
+        st = j.run_resident()
+        for k2, v in st.items():
+            if k2.startswith("ms_"):
+                acc[k2] = acc.get(k2, 0.0) + v
+    barrier()
+    dev_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    tt = torch.tensor([e2e_s, dev_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_s, dev_s = float(tt[0]), float(tt[1])
+    # pairs of the whole job (all ranks): from the bucket scan of the full input
+    if world == 1:
+        pairs_total = int(e2e_stats["pairs_candidate"])
+    else:
+        cnt = torch.tensor([int(st["pairs_candidate"])], device=dev, dtype=torch.int64)
+        dist.all_reduce(cnt)
+        pairs_total = int(cnt[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms = {k2: v / K for k2, v in acc.items()}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    kern = {"tier1": (ms.get("ms_kernel_tier1", 0), st["alg_bytes_tier1"]), "tier2": (ms.get("ms_kernel_tier2", 0), st["alg_bytes_tier2"]),
+            "pack": (ms.get("ms_kernel_pack", 0), st["alg_bytes_pack"])}
+    dom = max(kern, key=lambda k2: kern[k2][0])
+    dom_ms, dom_bytes = kern[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": {"tier1": "k_tier1", "tier2": "k_tier2(+k_tier2_generic)", "pack": "k_pack"}[dom],
+                "achieved": achieved, "peak": peak_hbm, "unit": "GB/s", "frac": achieved / peak_hbm if peak_hbm else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "traffic": None, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                "kernel_ms_all": {k2: kern[k2][0] for k2 in kern}, "device_ms_per_step": ms.get("ms_device")}
+    config.update({"n_info": sp.n_info, "candidate_pairs": pairs_total, "pairs_compared_tier1": int(st["pairs_compared"]),
+                   "pairs_tier2": int(st["pairs_tier2"]), "pairs_accepted": int(st["pairs_accepted"]), "joins_emitted": int(len(res.edges)),
+                   "l2": "inputs (%.0f MB resident) exceed the 126 MB L2; no flush" % (e2e_stats["h2d_bytes"] / 1e6),
+                   "host_buffers": "pinned (ejoin_host_alloc / ejoin_host_register)", "generate_s": round(gen_s, 2),
+                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, contiguous cost-balanced bucket ranges, NCCL all-gather of edges"})
+    line = {"metric": "join pairs scored/sec", "value": pairs_total * K / dev_s, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 popcount + f64 score", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": pairs_total * K / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s / K * 1e3,
+                    "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
+                    "breakdown_ms": {k2: round(e2e_stats[k2], 3) for k2 in ("ms_h2d", "ms_device", "ms_d2h", "ms_host_post", "ms_total")
+                                     if k2 in e2e_stats}},
+            "gpu_launches": int(st["gpu_launches"]) * K, "roofline": roofline}
+    if not args.no_cpu_baseline:
+        val, info = cpu_baseline(sp, params)
+        line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+    print(json.dumps(line))
+    j.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

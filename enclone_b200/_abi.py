@@ -78,7 +78,8 @@ assert EDGE_DTYPE.itemsize == C.sizeof(EjoinEdge), (EDGE_DTYPE.itemsize, C.sizeo
 class EjoinStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_buckets", "n_groups", "pairs_candidate", "pairs_compared", "pairs_tier2", "pairs_accepted",
-        "pairs_generic", "edges_after_prune", "gpu_launches", "h2d_bytes", "d2h_bytes")] + [
+        "pairs_generic", "edges_after_prune", "gpu_launches", "h2d_bytes", "d2h_bytes",
+        "alg_bytes_tier1", "alg_bytes_tier2", "alg_bytes_pack")] + [
         (n, C.c_double) for n in (
             "ms_h2d", "ms_device", "ms_d2h", "ms_host_post", "ms_total",
             "ms_kernel_tier1", "ms_kernel_tier2", "ms_kernel_pack", "ms_kernel_other")]

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(_HERE, "libenclone_join.so")
 EXPORTS = [
     "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
     "ejoin_plan_shards", "ejoin_run_shard", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_run_resident",
-    "ejoin_host_alloc", "ejoin_host_free", "ejoin_p1",
+    "ejoin_host_alloc", "ejoin_host_free", "ejoin_host_register", "ejoin_host_unregister", "ejoin_p1", "ejoin_partition",
 ]
 
 _lib = None
@@ -58,6 +58,13 @@ def load():
     L.ejoin_host_alloc.argtypes = [C.c_size_t]
     L.ejoin_host_alloc.restype = C.c_void_p
     L.ejoin_host_free.argtypes = [C.c_void_p]
+    L.ejoin_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.ejoin_host_register.restype = C.c_int
+    L.ejoin_host_unregister.argtypes = [C.c_void_p]
+    L.ejoin_host_unregister.restype = C.c_int
+    L.ejoin_partition.argtypes = [C.POINTER(EjoinPack), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint64,
+                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.ejoin_partition.restype = C.c_int
     L.ejoin_p1.argtypes = [C.c_uint32] * 3
     L.ejoin_p1.restype = C.c_double
     _lib = L

@@ -241,6 +241,16 @@ extern "C" void *ejoin_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" void ejoin_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int ejoin_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return EJOIN_E_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return EJOIN_E_CUDA; }
+    return EJOIN_OK;
+}
+extern "C" int ejoin_host_unregister(void *p) {
+    if (!p) return EJOIN_E_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return EJOIN_E_CUDA; }
+    return EJOIN_OK;
+}
 
 namespace {
 
@@ -471,7 +481,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         size_t tb = cub_bytes;
         cub::DeviceScan::InclusiveScan(cub_tmp, tb, head_pos, bucket_start, MaxOp(), (int)n, st);
         k_entry_keys<<<nb256, 256, 0, st>>>(h->din, bucket_start, keys, vals, (uint32_t *)h->d_presL.p, (uint32_t *)h->d_presC.p, ctr);
-        h->launches += 3;
+        h->launches += 2;
         CK(cudaGetLastError());
         int rc = prepare_tables(h, is_bcr);         // one sync; cached after the first run
         if (rc) return rc;
@@ -484,7 +494,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_t2_sizes<<<nb256, 256, 0, st>>>(h->din, perm, ctr, t2sizes);
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t2sizes, t2off, (int)n, st);
-        h->launches += 8;                           // radix sort passes + RLE + scans, counted conservatively below
+        h->launches += 2;                           // own kernels only; CUB's sort/RLE/scan launches are not counted
         CK(cudaEventRecord(h->ev[1], st));
         k_pack<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, perm, groups, t2off, ctr, meta, c3, t2, k_to_s, pr.ref_v_trim,
                                                                         pr.ref_j_trim);
@@ -518,7 +528,6 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (nk) {
             tb = cub_bytes;
             cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nk, 0, 64, st);
-            h->launches += 4;
         }
         CK(cudaEventRecord(h->ev[5], st));
         CK(cudaStreamSynchronize(st));
@@ -540,6 +549,8 @@ void fill_stats(ejoin_handle *h, ejoin_stats_t *s) {
     s->n_buckets = c.n_buckets; s->n_groups = c.n_groups; s->pairs_candidate = c.pairs_candidate; s->pairs_compared = c.pairs_compared;
     s->pairs_tier2 = c.pairs_tier2; s->pairs_accepted = c.n_accept; s->pairs_generic = c.n_generic; s->edges_after_prune = c.n_kept;
     s->gpu_launches = h->launches; s->h2d_bytes = h->h2d_bytes;
+    s->alg_bytes_tier1 = c.t1_alg_bytes; s->alg_bytes_tier2 = c.t2_alg_bytes;
+    s->alg_bytes_pack = h->tig_bytes + c.n_valid * sizeof(EntryMeta) + c.c3_words * 4 + c.t2_units * 16;
     s->ms_kernel_pack = h->stats.ms_kernel_pack; s->ms_kernel_tier1 = h->stats.ms_kernel_tier1; s->ms_kernel_tier2 = h->stats.ms_kernel_tier2;
     s->ms_kernel_other = h->stats.ms_kernel_other; s->ms_device = h->stats.ms_device;
 }
@@ -816,4 +827,24 @@ extern "C" int ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pk, const ejo
     fill_stats(h, &out->stats);
     out->stats.ms_host_post = h->stats.ms_host_post;
     return 0;
+}
+
+extern "C" int ejoin_partition(const ejoin_pack_t *pk, const uint32_t *k1, const uint32_t *k2, uint64_t ne, uint32_t *class_of, uint32_t *n_classes) {
+    if (!pk || !class_of || (ne && (!k1 || !k2))) return EJOIN_E_ARG;
+    const uint32_t n = pk->n_info;
+    UF uf(n);
+    for (uint64_t i = 0; i < ne; i++) {
+        if (k1[i] >= n || k2[i] >= n) return EJOIN_E_ARG;
+        uf.join(k1[i], k2[i]);
+    }
+    std::vector<int64_t> first(pk->n_exact, -1);
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t x = pk->exact_id[k];
+        if (x >= pk->n_exact) continue;
+        if (first[x] < 0) first[x] = k; else uf.join((uint32_t)first[x], k);
+    }
+    uint32_t ncls = 0;
+    for (uint32_t k = 0; k < n; k++) { class_of[k] = uf.find(k); ncls += class_of[k] == k; }
+    if (n_classes) *n_classes = ncls;
+    return EJOIN_OK;
 }

@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *u
                                                      GroupInfo *groups, const uint16_t *cdmax_tab, DevCounters *ctr) {
     typedef cub::BlockScan<unsigned long long, 1024> BS;
     __shared__ typename BS::TempStorage tmp;
-    __shared__ unsigned long long carry[4];
-    if (threadIdx.x == 0) carry[0] = carry[1] = carry[2] = carry[3] = 0;
+    __shared__ unsigned long long carry[5];
+    if (threadIdx.x == 0) carry[0] = carry[1] = carry[2] = carry[3] = carry[4] = 0;
     __syncthreads();
     const uint32_t nr = *num_runs;
     unsigned long long ngroups = 0;
@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *u
         BS(tmp).ExclusiveSum(c3w, sc, agg);
         __syncthreads();
         unsigned long long aggc = agg;
-        BS(tmp).ExclusiveSum(pairs, pairs, agg);   // only the aggregate is used
+        unsigned long long t1b = pairs * 16ull * W, aggb;
+        BS(tmp).ExclusiveSum(pairs, pairs, agg);   // only the aggregates are used
+        __syncthreads();
+        BS(tmp).ExclusiveSum(t1b, t1b, aggb);
         __syncthreads();
         if (valid) {
             GroupInfo g;
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *u
             if (r + 1 > ngroups) ngroups = r + 1;
         }
         __syncthreads();
-        if (threadIdx.x == 0) { carry[0] += aggn; carry[1] += aggw; carry[2] += aggc; carry[3] += agg; }
+        if (threadIdx.x == 0) { carry[0] += aggn; carry[1] += aggw; carry[2] += aggc; carry[3] += agg; carry[4] += aggb; }
         __syncthreads();
     }
     // number of groups = number of valid runs
@@ -119,19 +122,25 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *u
         ctr->n_work = carry[1];
         ctr->c3_words = carry[2];
         ctr->pairs_compared = carry[3];
+        ctr->t1_alg_bytes = carry[4];
     }
 }
 
 // per sorted entry: t2 row size in 16-byte units = 3 * (ceil(len0/128) + ceil(len1/128))
-__global__ void k_t2_sizes(DevIn in, const uint32_t *perm, const DevCounters *ctr, uint32_t *sizes) {
+__global__ void __launch_bounds__(256) k_t2_sizes(DevIn in, const uint32_t *perm, DevCounters *ctr, uint32_t *sizes) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= in.n_info) return;
     uint32_t v = 0;
-    if (s < ctr->n_valid) {
-        uint32_t k = perm[s];
-        v = 3u * (((uint32_t)in.len[0][k] + 127) / 128 + ((uint32_t)in.len[1][k] + 127) / 128);
+    if (s < in.n_info) {
+        if (s < ctr->n_valid) {
+            uint32_t k = perm[s];
+            v = 3u * (((uint32_t)in.len[0][k] + 127) / 128 + ((uint32_t)in.len[1][k] + 127) / 128);
+        }
+        sizes[s] = v;
     }
-    sizes[s] = v;
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    unsigned long long tot = BR(tmp).Sum((unsigned long long)v);
+    if (threadIdx.x == 0 && tot) atomicAdd(&ctr->t2_units, tot);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -500,6 +509,7 @@ __global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams
             if (ok && !meta_gates(pr, in, m1, m2, cd, &err)) ok = false;
             if (ok) {
                 atomicAdd(&ctr->pairs_tier2, 1ull);
+                atomicAdd(&ctr->t2_alg_bytes, 2ull * (48ull * (((uint32_t)m1.len[0] + 127) / 128 + ((uint32_t)m1.len[1] + 127) / 128) + 128ull));
                 const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] ||
                                      m1.vs[1] != m2.vs[1] || m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
                 if (generic) {

@@ -150,6 +150,9 @@ typedef struct ejoin_stats {
     uint64_t edges_after_prune;  /* accepted edges kept for the ordered replay     */
     uint64_t gpu_launches;       /* kernels launched by this call                  */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t alg_bytes_tier1;    /* sum over compared pairs of the two c3 rows read (2 * 8W bytes)   */
+    uint64_t alg_bytes_tier2;    /* sum over tier-2 pairs of the two t2 rows + meta records read     */
+    uint64_t alg_bytes_pack;     /* ASCII bytes read + packed rows and meta written by the pack kernel */
     double   ms_h2d, ms_device, ms_d2h, ms_host_post, ms_total; /* wall, host clock */
     double   ms_kernel_tier1, ms_kernel_tier2, ms_kernel_pack, ms_kernel_other; /* CUDA events */
 } ejoin_stats_t;
@@ -198,6 +201,12 @@ void ejoin_raw_free(ejoin_raw_edge_t *edges);
 int  ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pack, const ejoin_raw_edge_t *edges,
                   uint64_t n_edges, ejoin_result_t *out);
 
+/* finish_join on the host from an emitted edge list (k1[i], k2[i]): partition labels (min member)
+ * over all n_info entries, including the same-exact-subclonotype links.  Used by rank 0 after
+ * the gather; needs no GPU and no handle. */
+int  ejoin_partition(const ejoin_pack_t *pack, const uint32_t *k1, const uint32_t *k2, uint64_t n_edges,
+                     uint32_t *class_of /* [n_info] */, uint32_t *n_classes);
+
 /* Device-resident variant used to time the device side alone: upload once, then
  * ejoin_run_resident() repeats pack+score+compact+union-find on the resident input. */
 int  ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pack);
@@ -206,6 +215,9 @@ int  ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats);
 /* Pinned host memory for the caller's flat buffers (so H2D runs at link speed). */
 void *ejoin_host_alloc(size_t bytes);
 void  ejoin_host_free(void *p);
+/* Pin caller-owned buffers in place (e.g. the Vec<u8> arenas the Rust side already holds). */
+int   ejoin_host_register(void *p, size_t bytes);
+int   ejoin_host_unregister(void *p);
 
 /* The probability table entry the device uses: P(at most k-d distinct values in k
  * draws with replacement from n) — exposed so tests can pin it to the known-answer

@@ -525,6 +525,7 @@ typedef struct {
     uint32_t nb;
     _Atomic uint32_t *next;
     evec_t *per_bucket;
+    uint32_t stride, phase;
     ostats_t st;
 } worker_t;
 
@@ -533,6 +534,7 @@ static void *worker_main(void *arg) {
     for (;;) {
         uint32_t b = atomic_fetch_add(w->next, 1);
         if (b >= w->nb) break;
+        if (b % w->stride != w->phase) continue;
         bucket_join(w->pk, w->pr, w->bstart[b], w->bstart[b + 1], &w->per_bucket[b], &w->st);
     }
     return NULL;
@@ -563,9 +565,19 @@ uint32_t *oracle_bucket_scan(const ejoin_pack_t *pk, uint32_t *nb_out) {
 
 /* join_exacts + finish_join.  bucket_lo/bucket_hi restrict the work to a bucket range
  * (used to time a bounded sample); pass 0, UINT32_MAX for everything. */
+int oracle_join_exacts_strided(const ejoin_pack_t *pk, const ejoin_params_t *pr, int threads,
+                               uint32_t bucket_lo, uint32_t bucket_hi, uint32_t stride, uint32_t phase,
+                               ejoin_result_t *out, oracle_stats_t *ost);
 int oracle_join_exacts(const ejoin_pack_t *pk, const ejoin_params_t *pr, int threads,
                        uint32_t bucket_lo, uint32_t bucket_hi, ejoin_result_t *out,
                        oracle_stats_t *ost) {
+    return oracle_join_exacts_strided(pk, pr, threads, bucket_lo, bucket_hi, 1, 0, out, ost);
+}
+/* stride/phase: only buckets b with b % stride == phase are joined (a representative
+ * bounded sample for timing); the rest are left unjoined. */
+int oracle_join_exacts_strided(const ejoin_pack_t *pk, const ejoin_params_t *pr, int threads,
+                               uint32_t bucket_lo, uint32_t bucket_hi, uint32_t stride, uint32_t phase,
+                               ejoin_result_t *out, oracle_stats_t *ost) {
     memset(out, 0, sizeof(*out));
     double t0 = now_ms();
     uint32_t nb_all;
@@ -583,7 +595,7 @@ int oracle_join_exacts(const ejoin_pack_t *pk, const ejoin_params_t *pr, int thr
     pthread_t *th = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
     for (int t = 0; t < threads; t++) {
         ws[t].pk = pk; ws[t].pr = pr; ws[t].bstart = bs; ws[t].nb = nb; ws[t].next = &next;
-        ws[t].per_bucket = per_bucket;
+        ws[t].per_bucket = per_bucket; ws[t].stride = stride ? stride : 1; ws[t].phase = phase;
     }
     if (threads == 1) worker_main(&ws[0]);
     else {

@@ -39,6 +39,9 @@ def lib():
         L.oracle_join_exacts.restype = C.c_int
         L.oracle_join_exacts.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.c_int, C.c_uint32, C.c_uint32,
                                          C.POINTER(EjoinResult), C.POINTER(OracleStats)]
+        L.oracle_join_exacts_strided.restype = C.c_int
+        L.oracle_join_exacts_strided.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.c_int, C.c_uint32, C.c_uint32,
+                                                 C.c_uint32, C.c_uint32, C.POINTER(EjoinResult), C.POINTER(OracleStats)]
         L.oracle_accept_graph.restype = C.c_int
         L.oracle_accept_graph.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.c_uint32, C.c_uint32,
                                           C.POINTER(C.POINTER(EjoinEdge)), C.POINTER(C.c_uint64)]
@@ -72,13 +75,14 @@ def _edges_to_numpy(ptr, n):
     return np.frombuffer(buf, dtype=EDGE_DTYPE).copy()
 
 
-def join_exacts(pack_struct, params=None, threads=1, bucket_lo=0, bucket_hi=0xFFFFFFFF):
+def join_exacts(pack_struct, params=None, threads=1, bucket_lo=0, bucket_hi=0xFFFFFFFF, stride=1, phase=0):
     """Returns (edges ndarray in raw_joins order, class_of ndarray, stats dict)."""
     params = params or default_params()
     L = lib()
     L.oracle_prepare(600)
     res, st = EjoinResult(), OracleStats()
-    rc = L.oracle_join_exacts(C.byref(pack_struct), C.byref(params), threads, bucket_lo, bucket_hi, C.byref(res), C.byref(st))
+    rc = L.oracle_join_exacts_strided(C.byref(pack_struct), C.byref(params), threads, bucket_lo, bucket_hi, stride, phase,
+                                      C.byref(res), C.byref(st))
     if rc != 0:
         raise RuntimeError(f"oracle_join_exacts: {rc}")
     edges = _edges_to_numpy(res.edges, res.n_edges)

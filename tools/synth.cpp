@@ -397,7 +397,7 @@ extern "C" int esynth_generate(const esynth_cfg_t *cfgp, ejoin_pack_t **out, uin
                 // indels (heavy chain, inside FWR3, single codon)
                 if (cfg.is_bcr && rng.uni() < cfg.frac_indel) {
                     uint32_t p = 200 + 3 * rng.below(20);
-                    if (rng.uni() < 0.6) { mb.h[p] = mb.h[p + 1] = mb.h[p + 2] = '-'; mb.del_h = 1; }
+                    if (giant || rng.uni() < 0.6) { mb.h[p] = mb.h[p + 1] = mb.h[p + 2] = '-'; mb.del_h = 1; }
                     else { std::string ins3; for (int i = 0; i < 3; i++) ins3.push_back(rng.base()); mb.h.insert(p, ins3); mb.ins_h = (int)p; }
                 }
                 mb.nch = 2;
