@@ -444,7 +444,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(sizeof(GroupInfo) * ((size_t)n + 1));
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // t2sizes, t2off
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
-        sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // k_to_s, minnbr
+        sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
         sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);                        // cand, generic, acc
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // prune keys/vals in+out
         sz.take(cub_bytes + 256);
@@ -462,7 +462,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         EntryMeta *meta = A.take<EntryMeta>(n);
         uint32_t *c3 = A.take<uint32_t>(c3_words);
         uint4 *t2 = A.take<uint4>(t2_units);
-        uint32_t *k_to_s = A.take<uint32_t>(n), *minnbr = A.take<uint32_t>(n);
+        uint32_t *k_to_s = A.take<uint32_t>(n), *parent = A.take<uint32_t>(n);
+        unsigned long long *f0_key = A.take<unsigned long long>(n), *f0_val = A.take<unsigned long long>(n);
         uint2 *cand = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
         ejoin_raw_edge_t *acc = A.take<ejoin_raw_edge_t>(cap);
         unsigned long long *pk_in = A.take<unsigned long long>(cap), *pv_in = A.take<unsigned long long>(cap);
@@ -498,20 +499,24 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         CK(cudaEventRecord(h->ev[1], st));
         k_pack<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, perm, groups, t2off, ctr, meta, c3, t2, k_to_s, pr.ref_v_trim,
                                                                         pr.ref_j_trim);
-        k_fill_u32<<<nb256, 256, 0, st>>>(minnbr, 0xFFFFFFFFu, n);
+        k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, n);
         h->launches += 2;
         CK(cudaEventRecord(h->ev[2], st));
         DevTables tbs;
         tbs.meta = meta; tbs.c3 = c3; tbs.t2 = t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
         tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p;
         tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
-        k_tier1<<<h->sm_count * 8, T1_TILE, 0, st>>>(groups, c3, ctr, cand, cap, stride, phase);
+        int rows_occ = 4;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_occ, k_join_rows, T1_TILE, 0);
+        if (rows_occ < 1) rows_occ = 1;
+        k_join_rows<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(h->din, tbs, pr, groups, ctr, cand, cap, parent, f0_key, f0_val, stride, phase);
         CK(cudaEventRecord(h->ev[3], st));
-        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, cand, cap, generic_q, acc, minnbr, 0);
-        k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, minnbr, 0);
+        for (int it = 0; it < 10; it++) k_root_jump<<<nb256, 256, 0, st>>>(parent, n);      // 4 hops each: covers chains up to 4^10
+        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, cand, cap, generic_q, acc, parent, 0);
+        k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0);
         CK(cudaEventRecord(h->ev[4], st));
-        k_prune<<<h->sm_count * 8, 256, 0, st>>>(acc, ctr, cap, minnbr, pk_in, pv_in);
-        h->launches += 4;
+        k_collect<<<h->sm_count * 8, 256, 0, st>>>(f0_key, f0_val, n, acc, ctr, cap, pk_in, pv_in);
+        h->launches += 14;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -519,15 +524,17 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (h->counters.err & ERR_CDR3_BAD_CHAR) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 contains a character outside ACGT");
         if (h->counters.err & ERR_BAD_REFSEQ) return fail(h, EJOIN_E_ARG, "vs_seq/js_seq index outside the germline table");
         if (h->counters.err & ERR_K_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "a pair has 1024 or more mutations (p1 table width)");
-        if (h->counters.n_cand > cap || h->counters.n_generic > cap || h->counters.n_accept > cap) {
+        if (h->counters.n_cand > cap || h->counters.n_generic_q > cap || (unsigned long long)n + h->counters.n_accept > cap) {
             // candidate buffer too small: the counts are exact, so one retry suffices
-            h->cand_cap = std::max(h->counters.n_cand, std::max(h->counters.n_generic, h->counters.n_accept)) + 1024;
+            h->cand_cap = std::max(h->counters.n_cand, std::max(h->counters.n_generic_q, (unsigned long long)n + h->counters.n_accept)) + 1024;
             continue;
         }
         const unsigned long long nk = h->counters.n_kept;
+        const unsigned long long nsorted = (unsigned long long)n + std::min<unsigned long long>(h->counters.n_accept, cap);
         if (nk) {
+            // the empty phase-A slots carry the key ~0 and sort to the end: the first n_kept are the edges
             tb = cub_bytes;
-            cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nk, 0, 64, st);
+            cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nsorted, 0, 64, st);
         }
         CK(cudaEventRecord(h->ev[5], st));
         CK(cudaStreamSynchronize(st));

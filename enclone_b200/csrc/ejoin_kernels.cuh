@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *u
                 if (W == 0) W = 1;
                 cdm = cdmax_tab[total];
                 tiles = (uint32_t)((n + T1_TILE - 1) / T1_TILE);
-                if (n >= 2 && cdm != 0xFFFF) { work = (unsigned long long)tiles * (tiles + 1) / 2; pairs = n * (n - 1) / 2; }
+                if (n >= 2 && cdm != 0xFFFF) { work = tiles; pairs = n * (n - 1) / 2; }   // one work item per tile row
                 c3w = (n * 2 * W + 3) & ~3ull;
             }
         }
@@ -246,125 +246,6 @@ __global__ void __launch_bounds__(256) k_pack(DevIn in, const uint32_t *perm, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4  tier 1: all pairs of a comparison group, CDR3 XOR/popcount against the group's cd cap.
-// One CTA (128 threads) per 128x128 tile of the pair triangle; tiles are staged into shared
-// memory with 1-D bulk TMA copies; each thread keeps one A row in registers and sweeps the B
-// rows (broadcast reads).  Survivors are appended with one warp-aggregated atomic per 32x32
-// sub-block.  Work items are handed out by a global atomic counter (persistent CTAs).
-// ---------------------------------------------------------------------------------------------
-template <int W>
-__device__ __forceinline__ void t1_sweep(const uint32_t *__restrict__ sA, const uint32_t *__restrict__ sB, uint32_t rowsA, uint32_t rowsB,
-                                         bool diag, uint32_t cdmax, uint32_t posA0, uint32_t posB0, uint2 *cand,
-                                         unsigned long long cand_cap, DevCounters *ctr) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    uint32_t aH[W], aL[W];
-    const bool validA = tid < rowsA;
-#pragma unroll
-    for (int w = 0; w < W; w++) { aH[w] = validA ? sA[tid * 2 * W + w] : 0u; aL[w] = validA ? sA[tid * 2 * W + W + w] : 0u; }
-    for (uint32_t b0 = 0; b0 < rowsB; b0 += 32) {
-        // a warp whose A rows all lie at or after this B block has nothing to do on a diagonal tile
-        if (diag && (tid & ~31u) >= b0 + 32) continue;
-        uint32_t bits = 0;
-#pragma unroll 4
-        for (uint32_t bb = 0; bb < 32; bb++) {
-            const uint32_t *rb = sB + (b0 + bb) * 2 * W;
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int w = 0; w < W; w++) cnt += __popc((aH[w] ^ rb[w]) | (aL[w] ^ rb[W + w]));
-            bits |= (cnt <= cdmax ? 1u : 0u) << bb;
-        }
-        // mask: rows beyond the tile, invalid A, and (on the diagonal) pairs with b <= a
-        uint32_t nb = rowsB - b0;
-        if (nb < 32) bits &= (1u << nb) - 1u;
-        if (!validA) bits = 0;
-        if (diag) {
-            if (tid >= b0 + 31) bits = 0;
-            else if (tid >= b0) bits &= ~((2u << (tid - b0)) - 1u);
-        }
-        if (__any_sync(0xFFFFFFFFu, bits != 0)) {
-            uint32_t cntl = __popc(bits), incl = cntl;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
-            uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->n_cand, (unsigned long long)total);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cntl);
-            while (bits) {
-                uint32_t bb = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (base < cand_cap) cand[base] = make_uint2(posA0 + tid, posB0 + b0 + bb);
-                base++;
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(T1_TILE) k_tier1(const GroupInfo *__restrict__ groups, const uint32_t *__restrict__ c3, DevCounters *ctr,
-                                                   uint2 *cand, unsigned long long cand_cap, uint32_t stride, uint32_t phase) {
-    __shared__ __align__(128) uint32_t sA[T1_TILE * 2 * T1_WMAX];
-    __shared__ __align__(128) uint32_t sB[T1_TILE * 2 * T1_WMAX + 32 * 2 * T1_WMAX];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t s_item;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-    __syncthreads();
-    uint32_t parity = 0;
-    const uint32_t ngroups = (uint32_t)ctr->n_groups;
-    const unsigned long long nwork = ctr->n_work;
-    for (;;) {
-        if (tid == 0) s_item = (uint32_t)atomicAdd(&ctr->work_next, 1ull);
-        __syncthreads();
-        const unsigned long long item = (unsigned long long)s_item * stride + phase;
-        if (item >= nwork) break;
-        // group of the item
-        uint32_t lo = 0, hi = ngroups;
-        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (groups[mid].work_off <= item) lo = mid; else hi = mid; }
-        const GroupInfo g = groups[lo];
-        // triangular decode: item t -> (ia <= ib), row ia has (T - ia) items
-        const uint32_t T = g.tiles;
-        uint32_t t = (uint32_t)(item - g.work_off), ia = 0;
-        {
-            // ia = largest i with i*T - i(i-1)/2 <= t
-            double Td = (double)T + 0.5;
-            int guess = (int)(Td - sqrt(Td * Td - 2.0 * (double)t));
-            if (guess < 0) guess = 0;
-            if (guess >= (int)T) guess = (int)T - 1;
-            ia = (uint32_t)guess;
-            while (ia > 0 && (unsigned long long)ia * T - (unsigned long long)ia * (ia - 1) / 2 > t) ia--;
-            while ((unsigned long long)(ia + 1) * T - (unsigned long long)(ia + 1) * ia / 2 <= t) ia++;
-        }
-        const uint32_t ib = ia + (t - (uint32_t)((unsigned long long)ia * T - (unsigned long long)ia * (ia - 1) / 2));
-        const bool diag = ia == ib;
-        const uint32_t W = g.W;
-        const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE), rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
-        const uint32_t *gA = c3 + g.c3base + (size_t)ia * T1_TILE * 2 * W;
-        const uint32_t *gB = c3 + g.c3base + (size_t)ib * T1_TILE * 2 * W;
-        if (tid == 0) {
-            uint32_t bytesA = (rowsA * 2 * W * 4 + 15) & ~15u, bytesB = (rowsB * 2 * W * 4 + 15) & ~15u;
-            fence_proxy_async();
-            mbar_expect_tx(&bar, bytesA + (diag ? 0u : bytesB));
-            tma_load_1d(sA, gA, bytesA, &bar);
-            if (!diag) tma_load_1d(sB, gB, bytesB, &bar);
-        }
-        mbar_wait(&bar, parity);
-        parity ^= 1;
-        const uint32_t *pB = diag ? sA : sB;
-        const uint32_t posA0 = g.start + ia * T1_TILE, posB0 = g.start + ib * T1_TILE;
-        switch (W) {
-            case 1: t1_sweep<1>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-            case 2: t1_sweep<2>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-            case 3: t1_sweep<3>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-            case 4: t1_sweep<4>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-            case 5: t1_sweep<5>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-            case 6: t1_sweep<6>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-            case 7: t1_sweep<7>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-            default: t1_sweep<8>(sA, pB, rowsA, rowsB, diag, g.cdmax, posA0, posB0, cand, cand_cap, ctr); break;
-        }
-        __syncthreads();   // everyone is done with the tiles before the next TMA overwrites them
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Decision logic shared by the bit-parallel and the bytewise tier-2 paths (App. A.4 j-n).
 // ---------------------------------------------------------------------------------------------
 struct PairCounts {
@@ -470,18 +351,111 @@ __device__ __forceinline__ void emit_raw(const DevParams &pr, DevCounters *ctr, 
         e.flags = (uint32_t)reason | ((uint32_t)err << 8);
         acc[base] = e;
     }
-    atomicMin(&minnbr[k1], k2);
-    atomicMin(&minnbr[k2], k1);
+    (void)minnbr;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5  tier 2, bit-parallel: one thread per tier-1 survivor.
+// Thread-level full evaluation of one pair (positions sa, sb of one comparison group; the entry
+// with the smaller info index is k1).  Bit-parallel over the t2 rows.  Returns accept_reason
+// (0 = reject) or -1 when the pair needs the bytewise path (has_del / non-ACGT / overlapping
+// windows / different germlines); *scored is set when the pair got past the cheap gates.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa,
+                                               uint32_t sb, int *cd_out, int *d_out, int *err_out, bool *scored, unsigned long long *bytes) {
+    const EntryMeta *pa = &tb.meta[sa], *pb = &tb.meta[sb];
+    if (pa->k > pb->k) { const EntryMeta *t = pa; pa = pb; pb = t; }
+    const EntryMeta &m1 = *pa, &m2 = *pb;
+    *scored = false; *d_out = 0; *err_out = 0;
+    // CDR3 differences per chain from the c3 rows
+    const uint32_t cl0 = m1.cl[0], total = cl0 + m1.cl[1], W = max(1u, (total + 31) / 32);
+    int cd0 = 0, cdt = 0;
+    for (uint32_t w = 0; w < W; w++) {
+        uint32_t D = (tb.c3[m1.c3off + w] ^ tb.c3[m2.c3off + w]) | (tb.c3[m1.c3off + W + w] ^ tb.c3[m2.c3off + W + w]);
+        cdt += __popc(D);
+        cd0 += __popc(D & range_mask((int)w, 0, (int)cl0));
+    }
+    const int cd = cdt, cd1 = cdt - cd0;
+    *cd_out = cd;
+    const uint32_t cdm = tb.cdmax[total];
+    if (cdm == 0xFFFF || (uint32_t)cd > cdm) return 0;          // CDR3 gates (A.4-d), same table as tier 1
+    if (!meta_gates(pr, in, m1, m2, cd, err_out)) return 0;
+    *scored = true;
+    const uint32_t nblk = ((uint32_t)m1.len[0] + 127) / 128 + ((uint32_t)m1.len[1] + 127) / 128;
+    *bytes += 2ull * (48ull * nblk + 128ull);
+    const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] ||
+                         m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
+    if (generic) return -1;
+    PairCounts pc;
+    pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1;
+    for (int c2 = 0; c2 < 2; c2++)
+        if (m1.vref[c2] != m2.vref[c2] || m1.dref[c2] != m2.dref[c2] || m1.jref[c2] != m2.jref[c2]) pc.nrefs = 2;
+    int diffs = 0, shares = 0;
+    const uint4 *r1 = tb.t2 + m1.t2off, *r2 = tb.t2 + m2.t2off;
+    for (uint32_t b = 0; b < nblk; b++) {
+        uint4 h1 = r1[3 * b], l1 = r1[3 * b + 1], x1 = r1[3 * b + 2];
+        uint4 h2 = r2[3 * b], l2 = r2[3 * b + 1], x2 = r2[3 * b + 2];
+        uint32_t D0 = (h1.x ^ h2.x) | (l1.x ^ l2.x), D1 = (h1.y ^ h2.y) | (l1.y ^ l2.y);
+        uint32_t D2 = (h1.z ^ h2.z) | (l1.z ^ l2.z), D3 = (h1.w ^ h2.w) | (l1.w ^ l2.w);
+        diffs += __popc(D0) + __popc(D1) + __popc(D2) + __popc(D3);
+        shares += __popc(x1.x & x2.x & ~D0) + __popc(x1.y & x2.y & ~D1) + __popc(x1.z & x2.z & ~D2) + __popc(x1.w & x2.w & ~D3);
+    }
+    const int mm = (int)m1.m[0] + (int)m1.m[1] + (int)m2.m[0] + (int)m2.m[1];
+    pc.diffs = diffs;
+    pc.shares[0] = pc.shares[1] = shares;
+    pc.indeps[0] = pc.indeps[1] = mm - 2 * shares;
+    pc.indeps_out[0] = pc.indeps_out[1] = 1 << 20;    // filled below only when the CDR3_MULT rule can bite
+    // total-difference cap (A.4-c)
+    if (!pr.is_bcr || pr.max_diffs < 1000000) {
+        int cap = pr.max_diffs;
+        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
+        if (diffs > cap) return 0;
+    }
+    // FWR1 vs CDR1+CDR2 on the heavy chain (A.4-m)
+    pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
+    int f1, c1, f2, c2_, f3;
+    if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3)) {
+        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
+        int dfw = 0, d12 = 0;
+        for (int w = f1 >> 5; w <= (f3 - 1) >> 5; w++) {
+            const int blk = w >> 2, q = w & 3;
+            uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
+            dfw += __popc(D & range_mask(w, f1, c1));
+            d12 += __popc(D & (range_mask(w, c1, f2) | range_mask(w, c2_, f3)));
+        }
+        pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_);
+    }
+    // non-shared mutations outside the CDR3s (A.4-n), only when cd >= CDR3_MULT
+    if (cd >= pr.cdr3_mult) {
+        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
+        int io = 0, blk0 = 0;
+        for (int c2 = 0; c2 < 2; c2++) {
+            const int nw = ((int)m1.len[c2] + 127) / 128 * 4;
+            const int a1 = m1.cs[c2], a2 = m2.cs[c2], cl = m1.cl[c2];
+            for (int w = 0; w < nw; w++) {
+                const int blk = blk0 + (w >> 2), q = w & 3;
+                uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
+                uint32_t R = range_mask(w, a1, a1 + cl) | range_mask(w, a2, a2 + cl);
+                io += __popc(w1[blk * 12 + 8 + q] & D & ~R) + __popc(w2[blk * 12 + 8 + q] & D & ~R);
+            }
+            blk0 += nw / 4;
+        }
+        pc.indeps_out[0] = pc.indeps_out[1] = io;
+    }
+    int kk; double p1, mult, score;
+    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  tier 2, phase B: one thread per recorded survivor; scored only when its endpoints lie in
+// different phase-A trees.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *cand,
-                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t *minnbr,
+                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, const uint32_t *root,
                                                uint32_t k_base) {
+    uint32_t *minnbr = nullptr;
     unsigned long long ncand = ctr->n_cand;
     if (ncand > cand_cap) ncand = cand_cap;
+    unsigned long long my_pairs = 0, my_bytes = 0;      // per-thread tallies, one atomic per warp at the end
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((ncand + 31) & ~31ull);
          i += (unsigned long long)gridDim.x * blockDim.x) {
         bool accepted = false;
@@ -489,102 +463,32 @@ __global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams
         int cd = 0, d = 0, reason = 0, err = 0;
         if (i < ncand) {
             uint2 c = cand[i];
-            const EntryMeta *pa = &tb.meta[c.x], *pb = &tb.meta[c.y];
-            if (pa->k > pb->k) { const EntryMeta *t = pa; pa = pb; pb = t; }   // k1 < k2 in info order
-            const EntryMeta &m1 = *pa, &m2 = *pb;
-            k1 = m1.k; k2 = m2.k;
-            // CDR3 differences per chain from the c3 rows
-            const uint32_t cl0 = m1.cl[0], total = cl0 + m1.cl[1], W = max(1u, (total + 31) / 32);
-            int cd0 = 0, cdt = 0;
-            for (uint32_t w = 0; w < W; w++) {
-                uint32_t D = (tb.c3[m1.c3off + w] ^ tb.c3[m2.c3off + w]) | (tb.c3[m1.c3off + W + w] ^ tb.c3[m2.c3off + W + w]);
-                cdt += __popc(D);
-                cd0 += __popc(D & range_mask((int)w, 0, (int)cl0));
-            }
-            cd = cdt;
-            const int cd1 = cdt - cd0;
-            bool ok = true;
-            const uint32_t cdm = tb.cdmax[total];
-            if (cdm == 0xFFFF || (uint32_t)cd > cdm) ok = false;       // CDR3 gates (A.4-d), same table as tier 1
-            if (ok && !meta_gates(pr, in, m1, m2, cd, &err)) ok = false;
-            if (ok) {
-                atomicAdd(&ctr->pairs_tier2, 1ull);
-                atomicAdd(&ctr->t2_alg_bytes, 2ull * (48ull * (((uint32_t)m1.len[0] + 127) / 128 + ((uint32_t)m1.len[1] + 127) / 128) + 128ull));
-                const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] ||
-                                     m1.vs[1] != m2.vs[1] || m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
-                if (generic) {
-                    unsigned long long q = atomicAdd(&ctr->n_generic, 1ull);
-                    if (q < cand_cap) generic_q[q] = make_uint2(pa == &tb.meta[c.x] ? c.x : c.y, pa == &tb.meta[c.x] ? c.y : c.x);
-                    ok = false;
+            const bool force = c.x >> 31;
+            c.x &= 0x7FFFFFFFu;
+            // a survivor whose endpoints already sit in one phase-A tree cannot be a forest edge
+            // (DESIGN.md §lazy): skip it unscored
+            if (force || root[c.x] != root[c.y]) {
+                bool scored;
+                reason = evaluate_thread(in, tb, pr, ctr, c.x, c.y, &cd, &d, &err, &scored, &my_bytes);
+                my_pairs += scored;
+                if (reason < 0) {
+                    unsigned long long q = atomicAdd(&ctr->n_generic_q, 1ull);
+                    if (q < cand_cap) generic_q[q] = c;            // c.x < c.y positions: already k1 < k2
+                    reason = 0;
                 }
-            }
-            if (ok) {
-                PairCounts pc;
-                pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1;
-                for (int c2 = 0; c2 < 2; c2++)
-                    if (m1.vref[c2] != m2.vref[c2] || m1.dref[c2] != m2.dref[c2] || m1.jref[c2] != m2.jref[c2]) pc.nrefs = 2;
-                int diffs = 0, shares = 0;
-                const uint4 *r1 = tb.t2 + m1.t2off, *r2 = tb.t2 + m2.t2off;
-                const uint32_t nblk = ((uint32_t)m1.len[0] + 127) / 128 + ((uint32_t)m1.len[1] + 127) / 128;
-                for (uint32_t b = 0; b < nblk; b++) {
-                    uint4 h1 = r1[3 * b], l1 = r1[3 * b + 1], x1 = r1[3 * b + 2];
-                    uint4 h2 = r2[3 * b], l2 = r2[3 * b + 1], x2 = r2[3 * b + 2];
-                    uint32_t D0 = (h1.x ^ h2.x) | (l1.x ^ l2.x), D1 = (h1.y ^ h2.y) | (l1.y ^ l2.y);
-                    uint32_t D2 = (h1.z ^ h2.z) | (l1.z ^ l2.z), D3 = (h1.w ^ h2.w) | (l1.w ^ l2.w);
-                    diffs += __popc(D0) + __popc(D1) + __popc(D2) + __popc(D3);
-                    shares += __popc(x1.x & x2.x & ~D0) + __popc(x1.y & x2.y & ~D1) + __popc(x1.z & x2.z & ~D2) + __popc(x1.w & x2.w & ~D3);
-                }
-                const int mm = (int)m1.m[0] + (int)m1.m[1] + (int)m2.m[0] + (int)m2.m[1];
-                pc.diffs = diffs;
-                pc.shares[0] = pc.shares[1] = shares;
-                pc.indeps[0] = pc.indeps[1] = mm - 2 * shares;
-                pc.indeps_out[0] = pc.indeps_out[1] = 1 << 20;    // filled below only when the CDR3_MULT rule can bite
-                // total-difference cap (A.4-c)
-                if (!pr.is_bcr || pr.max_diffs < 1000000) {
-                    int cap = pr.max_diffs;
-                    if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
-                    if (diffs > cap) ok = false;
-                }
-                if (ok) {
-                    // FWR1 vs CDR1+CDR2 on the heavy chain (A.4-m)
-                    pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
-                    int f1, c1, f2, c2_, f3;
-                    if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3)) {
-                        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
-                        int dfw = 0, d12 = 0;
-                        for (int w = f1 >> 5; w <= (f3 - 1) >> 5; w++) {
-                            const int blk = w >> 2, q = w & 3;
-                            uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
-                            dfw += __popc(D & range_mask(w, f1, c1));
-                            d12 += __popc(D & (range_mask(w, c1, f2) | range_mask(w, c2_, f3)));
-                        }
-                        pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_);
-                    }
-                    // non-shared mutations outside the CDR3s (A.4-n), only when cd >= CDR3_MULT
-                    if (cd >= pr.cdr3_mult) {
-                        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
-                        int io = 0, blk0 = 0;
-                        for (int c2 = 0; c2 < 2; c2++) {
-                            const int nw = ((int)m1.len[c2] + 127) / 128 * 4;
-                            const int a1 = m1.cs[c2], a2 = m2.cs[c2], cl = m1.cl[c2];
-                            for (int w = 0; w < nw; w++) {
-                                const int blk = blk0 + (w >> 2), q = w & 3;
-                                uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
-                                uint32_t R = range_mask(w, a1, a1 + cl) | range_mask(w, a2, a2 + cl);
-                                io += __popc(w1[blk * 12 + 8 + q] & D & ~R) + __popc(w2[blk * 12 + 8 + q] & D & ~R);
-                            }
-                            blk0 += nw / 4;
-                        }
-                        pc.indeps_out[0] = pc.indeps_out[1] = io;
-                    }
-                    int kk; double p1, mult, score;
-                    reason = decide(pr, tb, m1, m2, pc, ctr, &kk, &d, &p1, &mult, &score);
-                    accepted = reason != 0;
-                }
+                accepted = reason != 0;
+                k1 = tb.meta[c.x].k; k2 = tb.meta[c.y].k;
+                if (k1 > k2) { uint32_t t = k1; k1 = k2; k2 = t; }
             }
         }
         emit_raw(pr, ctr, acc, cand_cap, minnbr, k1 + k_base, k2 + k_base, cd, d, reason, err, accepted);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_pairs += __shfl_xor_sync(0xFFFFFFFFu, my_pairs, o);
+        my_bytes += __shfl_xor_sync(0xFFFFFFFFu, my_bytes, o);
+    }
+    if ((threadIdx.x & 31) == 0 && my_pairs) { atomicAdd(&ctr->pairs_tier2, my_pairs); atomicAdd(&ctr->t2_alg_bytes, my_bytes); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -657,8 +561,9 @@ __device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const Entr
 
 // K6  tier 2, bytewise: one warp per queued pair (already past the CDR3 and meta gates).
 __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *generic_q,
-                                                       unsigned long long cap, ejoin_raw_edge_t *acc, uint32_t *minnbr, uint32_t k_base) {
-    unsigned long long nq = ctr->n_generic;
+                                                       unsigned long long cap, ejoin_raw_edge_t *acc, uint32_t k_base) {
+    uint32_t *minnbr = nullptr;
+    unsigned long long nq = ctr->n_generic_q;
     if (nq > cap) nq = cap;
     const uint32_t lane = threadIdx.x & 31;
     for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq;
@@ -667,6 +572,7 @@ __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, D
         const EntryMeta m1 = tb.meta[c.x], m2 = tb.meta[c.y];      // already ordered k1 < k2
         PairCounts pc;
         bytewise_counts(in, pr, m1, m2, pc);
+        if (lane == 0) atomicAdd(&ctr->n_generic, 1ull);
         bool ok = true;
         if (!pr.is_bcr || pr.max_diffs < 1000000) {
             int capd = pr.max_diffs;
@@ -717,34 +623,47 @@ __global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevPara
 }
 
 // ---------------------------------------------------------------------------------------------
-// K8  prune: an accepted edge (k1,k2) whose endpoints share a smaller common neighbour m < k1 is
-// skipped by the ordered replay (the edges (m,k1),(m,k2) come first: SURVEY §7.4-7, App. A.8),
-// so it can be dropped before the sort.  Kept edges get the 64-bit key k1<<32|k2.
+// K8  collect: phase-A tree edges (one slot per entry, ~0 = none) followed by the phase-B
+// accepted edges, as (key = k1<<32|k2, val = flags<<32|d<<16|cd) for the sort.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_prune(const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *minnbr,
-                        unsigned long long *keys, unsigned long long *vals) {
-    unsigned long long n = ctr->n_accept;
-    if (n > cap) n = cap;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ull);
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        bool keep = false;
-        ejoin_raw_edge_t e;
+__global__ void __launch_bounds__(256) k_collect(const unsigned long long *f0_key, const unsigned long long *f0_val, uint32_t n,
+                                                 const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap,
+                                                 unsigned long long *keys, unsigned long long *vals) {
+    unsigned long long nacc = ctr->n_accept;
+    if (nacc > cap) nacc = cap;
+    const unsigned long long total = (unsigned long long)n + nacc;
+    unsigned long long mine = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (i >= cap) break;
         if (i < n) {
-            e = acc[i];
-            uint32_t a = minnbr[e.k1], b = minnbr[e.k2];
-            keep = !(a == b && a < e.k1);
-        }
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
-        if (!mask) continue;
-        const uint32_t lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->n_kept, (unsigned long long)__popc(mask));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(mask & ((1u << lane) - 1u));
-        if (keep) {
-            keys[base] = ((unsigned long long)e.k1 << 32) | e.k2;
-            vals[base] = ((unsigned long long)e.flags << 32) | ((unsigned long long)e.d << 16) | e.cd;
+            keys[i] = f0_key[i]; vals[i] = f0_val[i];
+            mine += f0_key[i] != ~0ull;
+        } else {
+            ejoin_raw_edge_t e = acc[i - n];
+            keys[i] = ((unsigned long long)e.k1 << 32) | e.k2;
+            vals[i] = ((unsigned long long)e.flags << 32) | ((unsigned long long)e.d << 16) | e.cd;
+            mine++;
         }
     }
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    unsigned long long s = BR(tmp).Sum(mine);
+    if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_kept, s);
+}
+
+__global__ void k_init_rows(uint32_t *parent, unsigned long long *f0_key, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { parent[i] = i; f0_key[i] = ~0ull; }
+}
+
+// pointer doubling over the phase-A parent pointers (parent[s] < s or == s)
+__global__ void k_root_jump(uint32_t *parent, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = parent[i];
+#pragma unroll 1
+    for (int hop = 0; hop < 4; hop++) { uint32_t q = parent[p]; if (q == p) break; p = q; }
+    parent[i] = p;
 }
 
 __global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
@@ -786,4 +705,206 @@ __global__ void __launch_bounds__(P1_DCAP) k_p1_tables(const uint32_t *Ls, doubl
             p = dd_sub(p, T[(size_t)k * P1_DCAP + d]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative bytewise evaluation of one pair that evaluate_thread() sent back (-1): every
+// lane calls it with the same (sa < sb); the pair is already past the CDR3 and meta gates.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa, uint32_t sb,
+                                      int *cd_out, int *d_out) {
+    const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
+    PairCounts pc;
+    bytewise_counts(in, pr, m1, m2, pc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->n_generic, 1ull);
+    *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
+    if (!pr.is_bcr || pr.max_diffs < 1000000) {
+        int cap = pr.max_diffs;
+        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
+        if (pc.diffs > cap) return 0;
+    }
+    int kk; double p1, mult, score;
+    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  join rows: tier 1 (CDR3 XOR/popcount of all pairs of a comparison group) fused with the
+// lazy phase A of tier 2.
+//
+// Work item = one tile row (group g, B tile ib): the CTA's 128 threads each own one entry b of
+// the B tile (its c3 row in registers) and sweep the A tiles ia = 0..ib in ascending order; A
+// tiles are staged in shared memory with 1-D bulk TMA copies, double buffered on two mbarriers.
+// Inside a group sorted position order == info order, so thread b meets its CDR3 survivors a < b
+// in ascending info order.  Until b has an accepted partner, each survivor is fully scored by the
+// whole warp (evaluate_warp); the first accepted a is b's smallest accepted smaller neighbour,
+// i.e. the edge (a,b) of the lexicographically-first spanning forest that join_core's
+// skip-if-same-class scan would keep.  Later survivors of b are only recorded:
+// phase B (k_tier2) scores them iff their endpoints ended in different phase-A trees.
+// ---------------------------------------------------------------------------------------------
+// A b whose first PHASE_A_MAX_REJECTS scored survivors are all rejected stops scoring inline (one
+// thread scoring thousands of rejected pairs in sequence would stall its whole CTA): it keeps no
+// phase-A edge and hands ALL its remaining survivors to phase B with a force bit, where they are
+// scored in parallel.  Exactness is unaffected: only pairs of b's WITH a phase-A edge are ever
+// skipped.
+#define PHASE_A_MAX_REJECTS 6u
+struct RowCtx {
+    const DevIn *in; const DevTables *tb; const DevParams *pr; DevCounters *ctr;
+    uint2 *cand; unsigned long long cand_cap;
+    uint32_t *parent; unsigned long long *f0_key, *f0_val;
+    unsigned long long evals, bytes;
+};
+
+template <int W>
+__device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
+                                          const uint32_t (&bH)[W], const uint32_t (&bL)[W], bool validB, uint32_t posA0, uint32_t posB,
+                                          bool &found, uint32_t &nrej) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t a0 = 0; a0 < rowsA; a0 += 32) {
+        // on the diagonal tile only a < b counts: a warp whose b's all precede this block is done
+        if (diag && a0 > (tid | 31u)) break;
+        uint32_t bits = 0;
+#pragma unroll 4
+        for (uint32_t aa = 0; aa < 32; aa++) {
+            const uint32_t *ra = sA + (a0 + aa) * 2 * W;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) cnt += __popc((bH[w] ^ ra[w]) | (bL[w] ^ ra[W + w]));
+            bits |= (cnt <= cdmax ? 1u : 0u) << aa;
+        }
+        const uint32_t na = rowsA - a0;
+        if (na < 32) bits &= (1u << na) - 1u;
+        if (!validB) bits = 0;
+        if (diag) {                                  // keep a < b  <=>  a0 + aa < tid
+            if (tid <= a0) bits = 0;
+            else if (tid - a0 < 32) bits &= (1u << (tid - a0)) - 1u;
+        }
+        if (!__any_sync(0xFFFFFFFFu, bits != 0)) continue;
+        // ---- phase A: every lane without a partner scores its own next survivor (ascending a);
+        //      pairs that need the bytewise path are then taken one at a time by the whole warp
+        for (;;) {
+            const bool need = !found && bits != 0;
+            if (!__any_sync(0xFFFFFFFFu, need)) break;
+            int reason = 0, cd = 0, d = 0, err = 0;
+            uint32_t pa = 0;
+            if (need) {
+                pa = posA0 + a0 + (uint32_t)(__ffs(bits) - 1);
+                bool scored;
+                reason = evaluate_thread(*cx.in, *cx.tb, *cx.pr, cx.ctr, pa, posB, &cd, &d, &err, &scored, &cx.bytes);
+                cx.evals += scored;
+            }
+            uint32_t gm = __ballot_sync(0xFFFFFFFFu, need && reason < 0);
+            while (gm) {
+                const int src = __ffs(gm) - 1;
+                gm &= gm - 1;
+                const uint32_t ga = __shfl_sync(0xFFFFFFFFu, pa, src), gb = __shfl_sync(0xFFFFFFFFu, posB, src);
+                int gcd, gd;
+                const int r = evaluate_warp_bytewise(*cx.in, *cx.tb, *cx.pr, cx.ctr, ga, gb, &gcd, &gd);
+                if ((int)lane == src) { reason = r; cd = gcd; d = gd; }
+            }
+            if (need) {
+                bits &= bits - 1;
+                if (reason <= 0 && ++nrej >= PHASE_A_MAX_REJECTS) found = true;     // give up: see below
+                if (reason > 0) {
+                    found = true;
+                    cx.parent[posB] = pa;
+                    cx.f0_key[posB] = ((unsigned long long)cx.tb->meta[pa].k << 32) | cx.tb->meta[posB].k;
+                    cx.f0_val[posB] = ((unsigned long long)((uint32_t)reason | ((uint32_t)err << 8)) << 32) |
+                                      ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
+                }
+            }
+        }
+        // ---- remaining survivors (b already has its partner): record for phase B
+        if (__any_sync(0xFFFFFFFFu, bits != 0)) {
+            uint32_t cntl = __popc(bits), incl = cntl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+            const uint32_t totalc = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&cx.ctr->n_cand, (unsigned long long)totalc);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cntl);
+            while (bits) {
+                const uint32_t aa = __ffs(bits) - 1;
+                bits &= bits - 1;
+                // a b that gave up has no phase-A edge: its survivors carry the force bit and are all scored
+                if (base < cx.cand_cap) cx.cand[base] = make_uint2((posA0 + a0 + aa) | (nrej >= PHASE_A_MAX_REJECTS ? 0x80000000u : 0u), posB);
+                base++;
+            }
+        }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void row_item(RowCtx &cx, const GroupInfo &g, uint32_t ib, const uint32_t *__restrict__ c3, uint32_t (*sA)[T1_TILE * 2 * T1_WMAX],
+                                         uint64_t *bar, uint32_t &parity) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
+    const bool validB = tid < rowsB;
+    const uint32_t posB = g.start + ib * T1_TILE + tid;
+    uint32_t bH[W], bL[W];
+    {
+        const uint32_t *rb = c3 + g.c3base + (size_t)(ib * T1_TILE + (validB ? tid : 0)) * 2 * W;
+#pragma unroll
+        for (int w = 0; w < W; w++) { bH[w] = rb[w]; bL[w] = rb[W + w]; }
+    }
+    bool found = false;
+    uint32_t nrej = 0;
+    auto issue = [&](uint32_t ia) {
+        const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
+        const uint32_t bytes = (rowsA * 2 * W * 4 + 15) & ~15u;
+        fence_proxy_async();
+        mbar_expect_tx(&bar[ia & 1], bytes);
+        tma_load_1d(sA[ia & 1], c3 + g.c3base + (size_t)ia * T1_TILE * 2 * W, bytes, &bar[ia & 1]);
+    };
+    if (tid == 0) issue(0);
+    for (uint32_t ia = 0; ia <= ib; ia++) {
+        if (tid == 0 && ia + 1 <= ib) issue(ia + 1);       // buffer (ia+1)&1 was released by the barrier ending iteration ia-1
+        mbar_wait(&bar[ia & 1], (parity >> (ia & 1)) & 1u);
+        parity ^= 1u << (ia & 1);
+        const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
+        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, found, nrej);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(T1_TILE) k_join_rows(DevIn in, DevTables tb, DevParams pr, const GroupInfo *__restrict__ groups,
+                                                       DevCounters *ctr, uint2 *cand, unsigned long long cand_cap, uint32_t *parent,
+                                                       unsigned long long *f0_key, unsigned long long *f0_val, uint32_t stride, uint32_t phase) {
+    __shared__ __align__(128) uint32_t sA[2][T1_TILE * 2 * T1_WMAX];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t s_item;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    __syncthreads();
+    uint32_t parity = 0;                       // bit i = phase of bar[i]
+    RowCtx cx;
+    cx.in = &in; cx.tb = &tb; cx.pr = &pr; cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap;
+    cx.parent = parent; cx.f0_key = f0_key; cx.f0_val = f0_val; cx.evals = 0; cx.bytes = 0;
+    const uint32_t ngroups = (uint32_t)ctr->n_groups;
+    const unsigned long long nwork = ctr->n_work;
+    for (;;) {
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&ctr->work_next, 1ull);
+        __syncthreads();
+        const unsigned long long item = (unsigned long long)s_item * stride + phase;
+        __syncthreads();
+        if (item >= nwork) break;
+        uint32_t lo = 0, hi = ngroups;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (groups[mid].work_off <= item) lo = mid; else hi = mid; }
+        const GroupInfo g = groups[lo];
+        const uint32_t ib = g.tiles - 1 - (uint32_t)(item - g.work_off);      // longest rows of a group first
+        switch (g.W) {
+            case 1: row_item<1>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            case 2: row_item<2>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            case 3: row_item<3>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            case 4: row_item<4>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            case 5: row_item<5>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            case 6: row_item<6>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            case 7: row_item<7>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            default: row_item<8>(cx, g, ib, tb.c3, sA, bar, parity); break;
+        }
+    }
+    // per-thread tallies -> one atomic per warp
+    unsigned long long ev = cx.evals, by = cx.bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o); by += __shfl_xor_sync(0xFFFFFFFFu, by, o); }
+    if ((tid & 31) == 0 && ev) { atomicAdd(&ctr->pairs_tier2, ev); atomicAdd(&ctr->t2_alg_bytes, by); }
 }

@@ -52,10 +52,14 @@ class EquivRel:
 class JoinResult:
     def __init__(self, edges, class_of, stats):
         self.edges = edges                      # structured array, raw_joins order
-        self.raw_joins = [(int(a), int(b)) for a, b in zip(edges["k1"], edges["k2"])]
         self.eq = EquivRel(class_of)
         self.class_of = class_of
         self.stats = stats
+
+    @property
+    def raw_joins(self):
+        """Vec<(i32,i32)> of the reference: the emitted (k1,k2) in order."""
+        return [(int(a), int(b)) for a, b in zip(self.edges["k1"], self.edges["k2"])]
 
 
 def _edges_np(ptr, n, dtype, ctype):

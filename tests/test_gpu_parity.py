@@ -99,8 +99,9 @@ def test_empty_and_degenerate_inputs():
     assert len(g.edges) == 0 and list(g.class_of) == [0]
     # ragged: every entry in its own bucket
     bs = pack.bucket_starts()
-    g = join_exacts(pack.subset(bs[:-1]))
-    oe, oc, _ = O.join_exacts(pack.subset(bs[:-1]).struct)
+    sub = pack.subset(bs[:-1])              # keep the owner alive: .struct points into its arrays
+    g = join_exacts(sub)
+    oe, oc, _ = O.join_exacts(sub.struct)
     assert_same_join(g, oe, oc, what="singletons")
 
 
