@@ -90,7 +90,7 @@ class EjoinStats(C.Structure):
 
 class EjoinResult(C.Structure):
     _fields_ = [("n_edges", C.c_uint64), ("edges", C.POINTER(EjoinEdge)), ("class_of", u32p),
-                ("n_info", C.c_uint32), ("n_classes", C.c_uint32), ("stats", EjoinStats)]
+                ("n_info", C.c_uint32), ("n_classes", C.c_uint32), ("owner", C.c_void_p), ("stats", EjoinStats)]
 
 
 class EjoinRawEdge(C.Structure):

@@ -94,6 +94,9 @@ struct ejoin_handle {
     uint64_t launches = 0;
     // pinned staging for results
     void *pin = nullptr; size_t pin_cap = 0;
+    // host replay scratch (kept across runs; only touched entries are reset)
+    std::vector<uint32_t> uf_parent, cnt_tmp;
+    std::vector<size_t> forest_tmp;
 };
 
 namespace {
@@ -449,6 +452,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // prune keys/vals in+out
         sz.take(cub_bytes + 256);
         sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1));                   // payload staging (taken later)
+        sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)h->din.n_exact + 64);                              // union-find labels, first entry per exact
         CK(h->work.buf.ensure(sz.off + 4096));
         h->work.reset();
         Arena &A = h->work;
@@ -581,74 +585,120 @@ struct UF {
 
 // Ordered replay over the accepted edges sorted by (k1,k2): join_core's skip-if-same-class
 // (A.3/A.8), the two-cell rule (A.6) and the emit (A.7).  Returns the emitted (k1,k2).
-void replay(const ejoin_pack_t *pk, const ejoin_params_t &pr, const unsigned long long *keys, const unsigned long long *vals, size_t ne,
+// Work is O(#edges): the union-find lives in the handle and only the touched entries are reset.
+void replay(ejoin_handle *h, const ejoin_pack_t *pk, const unsigned long long *keys, const unsigned long long *vals, size_t ne,
             std::vector<uint2> &final_pairs) {
-    UF uf(pk->n_info);
-    std::vector<size_t> forest;
-    forest.reserve(std::min<size_t>(ne, pk->n_info));
-    for (size_t i = 0; i < ne; i++) {
-        uint32_t k1 = (uint32_t)(keys[i] >> 32), k2 = (uint32_t)keys[i];
-        if (uf.join(k1, k2)) forest.push_back(i);
+    std::vector<uint32_t> &p = h->uf_parent;
+    if (p.size() < pk->n_info) {
+        size_t old = p.size();
+        p.resize(pk->n_info);
+        for (size_t i = old; i < p.size(); i++) p[i] = (uint32_t)i;
     }
-    std::vector<uint32_t> size(pk->n_info, 0);
-    for (uint32_t k = 0; k < pk->n_info; k++) size[uf.find(k)]++;
+    auto find = [&](uint32_t a) {
+        uint32_t r = a;
+        while (p[r] != r) r = p[r];
+        while (p[a] != r) { uint32_t nx = p[a]; p[a] = r; a = nx; }
+        return r;
+    };
+    std::vector<size_t> &forest = h->forest_tmp;
+    forest.clear();
+    for (size_t i = 0; i < ne; i++) {
+        uint32_t a = find((uint32_t)(keys[i] >> 32)), b = find((uint32_t)keys[i]);
+        if (a == b) continue;
+        if (a < b) p[b] = a; else p[a] = b;
+        forest.push_back(i);
+    }
+    // orbit size = forest edges of the orbit + 1; count edges per root (roots are touched entries)
+    std::vector<uint32_t> &cnt = h->cnt_tmp;
+    if (cnt.size() < pk->n_info) cnt.resize(pk->n_info, 0);
+    for (size_t i : forest) cnt[find((uint32_t)(keys[i] >> 32))]++;
+    final_pairs.clear();
+    final_pairs.reserve(forest.size());
     for (size_t i : forest) {
         uint32_t k1 = (uint32_t)(keys[i] >> 32), k2 = (uint32_t)keys[i];
-        if (size[uf.find(k1)] == 2) {
+        if (cnt[find(k1)] == 1) {                          // an orbit with exactly two entries
             uint32_t cells = pk->ncells[pk->exact_id[k1]] + pk->ncells[pk->exact_id[k2]];
             uint32_t cd = (uint32_t)(vals[i] & 0xFFFF), d = (uint32_t)((vals[i] >> 16) & 0xFFFF);
-            if (cells == 2 && !pr.easy && !(cd <= d)) continue;     // help1.rs:349-353
+            if (cells == 2 && !h->params.easy && !(cd <= d)) continue;     // help1.rs:349-353
         }
         final_pairs.push_back(make_uint2(k1, k2));
     }
+    // reset what was touched
+    for (size_t i : forest) { uint32_t k1 = (uint32_t)(keys[i] >> 32), k2 = (uint32_t)keys[i]; cnt[find(k1)] = 0; }
+    for (size_t i : forest) { uint32_t k1 = (uint32_t)(keys[i] >> 32), k2 = (uint32_t)keys[i]; p[k1] = k1; p[k2] = k2; }
 }
 
-// finish_join (A.7): partition over all info entries from the emitted edges plus the
-// same-exact-subclonotype links; labels are min members.
-void finish_partition(const ejoin_pack_t *pk, const ejoin_edge_t *edges, size_t ne, ejoin_result_t *out) {
+// finish_join on the host (used by ejoin_partition and when the handle does not hold the whole input)
+void host_partition(const ejoin_pack_t *pk, const uint32_t *k1, const uint32_t *k2, size_t ne, uint32_t *class_of, uint32_t *n_classes) {
     const uint32_t n = pk->n_info;
     UF uf(n);
-    for (size_t i = 0; i < ne; i++) uf.join(edges[i].k1, edges[i].k2);
+    for (size_t i = 0; i < ne; i++) uf.join(k1[i], k2[i]);
     std::vector<int64_t> first(pk->n_exact, -1);
     for (uint32_t k = 0; k < n; k++) {
         uint32_t x = pk->exact_id[k];
         if (x >= pk->n_exact) continue;
         if (first[x] < 0) first[x] = k; else uf.join((uint32_t)first[x], k);
     }
-    out->class_of = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
-    out->n_info = n;
     uint32_t ncls = 0;
-    for (uint32_t k = 0; k < n; k++) { out->class_of[k] = uf.find(k); ncls += out->class_of[k] == k; }
-    out->n_classes = ncls;
+    for (uint32_t k = 0; k < n; k++) { class_of[k] = uf.find(k); ncls += class_of[k] == k; }
+    if (n_classes) *n_classes = ncls;
 }
 
-// payload of the emitted edges on the device (k_payload), into out->edges
-int payload(ejoin_handle *h, int is_bcr, const std::vector<uint2> &pairs, ejoin_result_t *out) {
+// Emitted edges -> full PotentialJoin records (k_payload) and, when the handle holds the whole
+// input, the finish_join partition by the GPU union-find; both land in the handle's pinned
+// result buffer.
+int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2> &pairs, size_t pin_used, ejoin_result_t *out) {
     const size_t ne = pairs.size();
-    out->n_edges = ne;
-    out->edges = (ejoin_edge_t *)malloc(sizeof(ejoin_edge_t) * (ne ? ne : 1));
-    if (!ne) return 0;
-    const DevParams pr = dev_params(h->params, is_bcr);
-    // reuse the candidate region of the work arena (its contents are dead by now)
+    const uint32_t n = h->n;
+    const bool whole = h->k_base == 0 && h->n == pk->n_info;
+    const DevParams pr = dev_params(h->params, (int)pk->is_bcr);
+    char *pin = (char *)h->pin;
+    size_t off = (pin_used + 255) & ~(size_t)255;
+    ejoin_edge_t *h_edges = (ejoin_edge_t *)(pin + off);
+    off += sizeof(ejoin_edge_t) * (ne ? ne : 1);
+    off = (off + 255) & ~(size_t)255;
+    uint32_t *h_labels = (uint32_t *)(pin + off);
+    off += sizeof(uint32_t) * (size_t)(n ? n : 1);
+    if (off > h->pin_cap) return fail(h, EJOIN_E_NOMEM, "pinned result buffer too small");
+    out->n_edges = ne; out->edges = h_edges; out->owner = h;
+    out->class_of = nullptr; out->n_info = 0; out->n_classes = 0;
+    if (n == 0) return 0;                                  // nothing uploaded: empty result
     Arena &A = h->work;
     const size_t save = A.off;
-    uint2 *d_pairs = A.take<uint2>(ne);
-    ejoin_edge_t *d_out = A.take<ejoin_edge_t>(ne);
-    if (A.off > A.buf.cap) {
-        A.off = save;
-        return fail(h, EJOIN_E_NOMEM, "work arena too small for the payload");
+    uint2 *d_pairs = A.take<uint2>(ne ? ne : 1);
+    ejoin_edge_t *d_out = A.take<ejoin_edge_t>(ne ? ne : 1);
+    uint32_t *d_label = A.take<uint32_t>(n ? n : 1);
+    uint32_t *d_first = A.take<uint32_t>(pk->n_exact ? pk->n_exact : 1);
+    if (A.off > A.buf.cap) { A.off = save; return fail(h, EJOIN_E_NOMEM, "work arena too small for the epilogue"); }
+    DevCounters *ctr = (DevCounters *)h->d_counters.p;
+    const double t_dev0 = now_ms();
+    if (ne) {
+        CK(cudaMemcpyAsync(d_pairs, pairs.data(), ne * sizeof(uint2), cudaMemcpyHostToDevice, h->st));
+        DevTables tbs;
+        tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
+        tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
+        k_payload<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)ne, h->k_base, d_out);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_edges, d_out, ne * sizeof(ejoin_edge_t), cudaMemcpyDeviceToHost, h->st));
     }
-    CK(cudaMemcpyAsync(d_pairs, pairs.data(), ne * sizeof(uint2), cudaMemcpyHostToDevice, h->st));
-    DevTables tbs;
-    tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
-    tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
-    k_payload<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, (DevCounters *)h->d_counters.p, h->k_to_s, d_pairs, (uint32_t)ne, h->k_base, d_out);
-    h->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out->edges, d_out, ne * sizeof(ejoin_edge_t), cudaMemcpyDeviceToHost, h->st));
+    if (whole && n) {
+        const unsigned nbx = (std::max(n, pk->n_exact) + 255) / 256, nbn = (std::max<uint32_t>(n, (uint32_t)ne) + 255) / 256;
+        CK(cudaMemsetAsync(&ctr->n_classes, 0, sizeof(unsigned long long), h->st));
+        k_uf_init<<<nbx, 256, 0, h->st>>>(d_label, n, d_first, pk->n_exact);
+        k_uf_first<<<(n + 255) / 256, 256, 0, h->st>>>(h->din.exact_id, n, pk->n_exact, d_first);
+        k_uf_union<<<nbn, 256, 0, h->st>>>(d_label, d_pairs, (uint32_t)ne, h->k_base, h->din.exact_id, n, pk->n_exact, d_first);
+        k_uf_flatten<<<(n + 255) / 256, 256, 0, h->st>>>(d_label, n, ctr);
+        h->launches += 4;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_labels, d_label, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaMemcpyAsync(&h->counters.n_classes, &ctr->n_classes, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
+    }
     CK(cudaStreamSynchronize(h->st));
+    if (getenv("EJOIN_DEBUG")) fprintf(stderr, "[ejoin] epilogue: %zu edges, device part %.3f ms\n", ne, now_ms() - t_dev0);
     A.off = save;
-    h->stats.d2h_bytes += ne * sizeof(ejoin_edge_t);
+    if (whole) { out->class_of = h_labels; out->n_info = n; out->n_classes = (uint32_t)h->counters.n_classes; }
+    h->stats.d2h_bytes += ne * sizeof(ejoin_edge_t) + (whole ? (size_t)n * 4 : 0);
     return 0;
 }
 
@@ -673,13 +723,13 @@ extern "C" int ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats) {
 }
 
 static int finish_common(ejoin_handle *h, const ejoin_pack_t *pk, const unsigned long long *keys, const unsigned long long *vals, size_t nk,
-                         ejoin_result_t *out) {
+                         size_t pin_used, ejoin_result_t *out) {
     double t0 = now_ms();
     std::vector<uint2> fin;
-    replay(pk, h->params, keys, vals, nk, fin);
-    int rc = payload(h, (int)pk->is_bcr, fin, out);
+    replay(h, pk, keys, vals, nk, fin);
+    if (getenv("EJOIN_DEBUG")) fprintf(stderr, "[ejoin] replay: %zu sorted edges -> %zu emitted, %.3f ms\n", nk, fin.size(), now_ms() - t0);
+    int rc = emit_result(h, pk, fin, pin_used, out);
     if (rc) return rc;
-    finish_partition(pk, out->edges, out->n_edges, out);
     h->stats.ms_host_post = now_ms() - t0;
     return 0;
 }
@@ -699,7 +749,7 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     if (rc) return rc;
     const double t2 = now_ms();
     const size_t nk = (size_t)h->counters.n_kept;
-    rc = ensure_pin(h, 16 * nk + 64);
+    rc = ensure_pin(h, 16 * nk + sizeof(ejoin_edge_t) * (nk + 1) + 4 * ((size_t)h->n + 1) + 1024);
     if (rc) return rc;
     unsigned long long *hk = (unsigned long long *)h->pin, *hv = hk + nk;
     if (nk) {
@@ -709,7 +759,7 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     }
     h->stats.d2h_bytes = 16 * nk + sizeof(DevCounters);
     const double t3 = now_ms();
-    rc = finish_common(h, pk, hk, hv, nk, out);
+    rc = finish_common(h, pk, hk, hv, nk, 16 * nk, out);
     if (rc) return rc;
     const double t4 = now_ms();
     fill_stats(h, &out->stats);
@@ -721,7 +771,7 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
 
 extern "C" void ejoin_result_free(ejoin_result_t *r) {
     if (!r) return;
-    free(r->edges); free(r->class_of);
+    if (!r->owner) { free(r->edges); free(r->class_of); }     // owner != NULL: the handle's pinned buffer
     memset(r, 0, sizeof(*r));
 }
 
@@ -826,10 +876,12 @@ extern "C" int ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pk, const ejo
     }
     std::sort(kv.begin(), kv.end());
     kv.erase(std::unique(kv.begin(), kv.end(), [](auto &a, auto &b) { return a.first == b.first; }), kv.end());
-    std::vector<unsigned long long> keys(kv.size()), vals(kv.size());
-    for (size_t i = 0; i < kv.size(); i++) { keys[i] = kv[i].first; vals[i] = kv[i].second; }
-    // payload works in the handle's local index space
-    int rc = finish_common(h, pk, keys.data(), vals.data(), keys.size(), out);
+    const size_t nk = kv.size();
+    int rc = ensure_pin(h, 16 * nk + sizeof(ejoin_edge_t) * (nk + 1) + 4 * ((size_t)h->n + 1) + 1024);
+    if (rc) return rc;
+    unsigned long long *keys = (unsigned long long *)h->pin, *vals = keys + nk;
+    for (size_t i = 0; i < nk; i++) { keys[i] = kv[i].first; vals[i] = kv[i].second; }
+    rc = finish_common(h, pk, keys, vals, nk, 16 * nk, out);
     if (rc) return rc;
     fill_stats(h, &out->stats);
     out->stats.ms_host_post = h->stats.ms_host_post;
@@ -838,20 +890,7 @@ extern "C" int ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pk, const ejo
 
 extern "C" int ejoin_partition(const ejoin_pack_t *pk, const uint32_t *k1, const uint32_t *k2, uint64_t ne, uint32_t *class_of, uint32_t *n_classes) {
     if (!pk || !class_of || (ne && (!k1 || !k2))) return EJOIN_E_ARG;
-    const uint32_t n = pk->n_info;
-    UF uf(n);
-    for (uint64_t i = 0; i < ne; i++) {
-        if (k1[i] >= n || k2[i] >= n) return EJOIN_E_ARG;
-        uf.join(k1[i], k2[i]);
-    }
-    std::vector<int64_t> first(pk->n_exact, -1);
-    for (uint32_t k = 0; k < n; k++) {
-        uint32_t x = pk->exact_id[k];
-        if (x >= pk->n_exact) continue;
-        if (first[x] < 0) first[x] = k; else uf.join((uint32_t)first[x], k);
-    }
-    uint32_t ncls = 0;
-    for (uint32_t k = 0; k < n; k++) { class_of[k] = uf.find(k); ncls += class_of[k] == k; }
-    if (n_classes) *n_classes = ncls;
+    for (uint64_t i = 0; i < ne; i++) if (k1[i] >= pk->n_info || k2[i] >= pk->n_info) return EJOIN_E_ARG;
+    host_partition(pk, k1, k2, ne, class_of, n_classes);
     return EJOIN_OK;
 }

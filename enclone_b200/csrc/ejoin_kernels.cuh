@@ -908,3 +908,54 @@ __global__ void __launch_bounds__(T1_TILE) k_join_rows(DevIn in, DevTables tb, D
     for (int o = 16; o > 0; o >>= 1) { ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o); by += __shfl_xor_sync(0xFFFFFFFFu, by, o); }
     if ((tid & 31) == 0 && ev) { atomicAdd(&ctr->pairs_tier2, ev); atomicAdd(&ctr->t2_alg_bytes, by); }
 }
+
+// ---------------------------------------------------------------------------------------------
+// EqClass: GPU union-find for finish_join (App. A.7).  Roots are always hooked under the smaller
+// index with a CAS, so the root of a class is its smallest member — the label the host side turns
+// back into an EquivRel.  Loads bypass L1 (the forest is being rewritten by other CTAs).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t uf_find(uint32_t *p, uint32_t x) {
+    for (;;) {
+        uint32_t px = __ldcg(&p[x]);
+        if (px == x) return x;
+        uint32_t gp = __ldcg(&p[px]);
+        if (gp != px) p[x] = gp;         // path halving; a stale value is still an ancestor
+        x = px;
+    }
+}
+__device__ __forceinline__ void uf_union(uint32_t *p, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = uf_find(p, a); b = uf_find(p, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }
+        if (atomicCAS(&p[a], a, b) == a) return;
+    }
+}
+__global__ void k_uf_init(uint32_t *label, uint32_t n, uint32_t *first, uint32_t n_exact) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) label[i] = i;
+    if (i < n_exact) first[i] = 0xFFFFFFFFu;
+}
+__global__ void k_uf_first(const uint32_t *exact_id, uint32_t n, uint32_t n_exact, uint32_t *first) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { uint32_t x = exact_id[k]; if (x < n_exact) atomicMin(&first[x], k); }
+}
+// join the emitted edges, then the info entries that share an exact subclonotype (PREHISTORY:14747)
+__global__ void k_uf_union(uint32_t *label, const uint2 *pairs, uint32_t npairs, uint32_t k_base, const uint32_t *exact_id, uint32_t n,
+                           uint32_t n_exact, const uint32_t *first) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npairs) uf_union(label, pairs[i].x - k_base, pairs[i].y - k_base);
+    if (i < n) {
+        uint32_t x = exact_id[i];
+        if (x < n_exact) { uint32_t f = first[x]; if (f != i) uf_union(label, f, i); }
+    }
+}
+__global__ void __launch_bounds__(256) k_uf_flatten(uint32_t *label, uint32_t n, DevCounters *ctr) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long isroot = 0;
+    if (i < n) { uint32_t r = uf_find(label, i); isroot = r == i; __stcg(&label[i], r); }
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    unsigned long long s = BR(tmp).Sum(isroot);
+    if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_classes, s);
+}

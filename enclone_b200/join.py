@@ -62,10 +62,12 @@ class JoinResult:
         return [(int(a), int(b)) for a, b in zip(self.edges["k1"], self.edges["k2"])]
 
 
-def _edges_np(ptr, n, dtype, ctype):
+def _edges_np(ptr, n, dtype, ctype, copy=True):
     if n == 0:
         return np.zeros(0, dtype)
-    return np.frombuffer(C.string_at(ptr, n * C.sizeof(ctype)), dtype=dtype).copy()
+    addr = C.cast(ptr, C.c_void_p).value
+    view = np.frombuffer((ctype * n).from_address(addr), dtype=dtype)      # zero-copy view of library memory
+    return view.copy() if copy else view
 
 
 class Joiner:
@@ -98,17 +100,23 @@ class Joiner:
         if rc != 0:
             raise _lib.EjoinError(rc, self.L.ejoin_last_error(self.h).decode())
 
-    def _result(self, res):
-        edges = _edges_np(res.edges, res.n_edges, EDGE_DTYPE, EjoinEdge)
-        cls = np.ctypeslib.as_array(res.class_of, shape=(res.n_info,)).copy() if res.n_info else np.zeros(0, np.uint32)
+    def _result(self, res, copy=True):
+        """copy=False returns views into the handle's pinned result buffer: valid until the next
+        run/finish on this Joiner (one live result per handle, include/enclone_join.h)."""
+        edges = _edges_np(res.edges, res.n_edges, EDGE_DTYPE, EjoinEdge, copy)
+        if res.n_info and res.class_of:
+            cls = np.ctypeslib.as_array(res.class_of, shape=(res.n_info,))
+            cls = cls.copy() if copy else cls
+        else:
+            cls = np.zeros(0, np.uint32)
         stats = res.stats.as_dict()
         self.L.ejoin_result_free(C.byref(res))
         return JoinResult(edges, cls, stats)
 
-    def run(self, pack_struct):
+    def run(self, pack_struct, copy=True):
         res = EjoinResult()
         self._check(self.L.ejoin_run(self.h, C.byref(pack_struct), C.byref(res)))
-        return self._result(res)
+        return self._result(res, copy)
 
     def upload(self, pack_struct):
         self._check(self.L.ejoin_upload(self.h, C.byref(pack_struct)))

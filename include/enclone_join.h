@@ -160,9 +160,11 @@ typedef struct ejoin_stats {
 typedef struct ejoin_result {
     uint64_t      n_edges;
     ejoin_edge_t *edges;         /* raw_joins, in the reference's emit order       */
-    uint32_t     *class_of;      /* [n_info] EquivRel partition as min-member labels (finish_join) */
+    uint32_t     *class_of;      /* [n_info] EquivRel partition as min-member labels (finish_join); NULL when n_info == 0 */
     uint32_t      n_info;
     uint32_t      n_classes;
+    void         *owner;         /* non-NULL: edges/class_of live in that handle's pinned result buffer and stay valid
+                                    until its next ejoin_run*/ /*ejoin_finish or ejoin_destroy (one live result per handle) */
     ejoin_stats_t stats;
 } ejoin_result_t;
 

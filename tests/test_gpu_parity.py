@@ -139,6 +139,9 @@ def test_sharded_run_equals_single():
         edges = np.concatenate([f.edges for f in finals])
         order = np.lexsort((edges["k2"], edges["k1"]))
         assert np.array_equal(edges[order], single.edges)
+        from enclone_b200.dist import partition
+        cls, ncls = partition(pack.struct, edges["k1"], edges["k2"])
+        assert np.array_equal(cls, single.class_of) and ncls == len(np.unique(single.class_of))
 
 
 def test_stride_mode_giant_bucket():
