@@ -445,10 +445,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // head_pos, bucket_start
         sz.take(8 * (size_t)n + 8); sz.take(4 * (size_t)n + 4); sz.take(64);                                // uniq, counts, num_runs
         sz.take(sizeof(GroupInfo) * ((size_t)n + 1));
-        sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // t2sizes, t2off
+        sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                             // t2sizes, t2off, gid
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
-        sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);                        // cand, generic, acc
+        sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);        // cand, todo, generic, acc
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // prune keys/vals in+out
         sz.take(cub_bytes + 256);
         sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1));                   // payload staging (taken later)
@@ -462,13 +462,13 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         unsigned long long *uniq = A.take<unsigned long long>((size_t)n + 1);
         uint32_t *counts = A.take<uint32_t>((size_t)n + 1), *num_runs = A.take<uint32_t>(16);
         GroupInfo *groups = A.take<GroupInfo>((size_t)n + 1);
-        uint32_t *t2sizes = A.take<uint32_t>(n), *t2off = A.take<uint32_t>(n);
+        uint32_t *t2sizes = A.take<uint32_t>(n), *t2off = A.take<uint32_t>(n), *gid = A.take<uint32_t>(n);
         EntryMeta *meta = A.take<EntryMeta>(n);
         uint32_t *c3 = A.take<uint32_t>(c3_words);
         uint4 *t2 = A.take<uint4>(t2_units);
         uint32_t *k_to_s = A.take<uint32_t>(n), *parent = A.take<uint32_t>(n);
         unsigned long long *f0_key = A.take<unsigned long long>(n), *f0_val = A.take<unsigned long long>(n);
-        uint2 *cand = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
+        uint2 *cand = A.take<uint2>(cap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
         ejoin_raw_edge_t *acc = A.take<ejoin_raw_edge_t>(cap);
         unsigned long long *pk_in = A.take<unsigned long long>(cap), *pv_in = A.take<unsigned long long>(cap);
         unsigned long long *pk_out = A.take<unsigned long long>(cap), *pv_out = A.take<unsigned long long>(cap);
@@ -496,13 +496,19 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         tb = cub_bytes;
         cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
         k_group_scan<<<1, 1024, 0, st>>>(uniq, counts, num_runs, groups, (const uint16_t *)h->d_cdmax.p, ctr);
+        k_sorted_heads<<<nb256, 256, 0, st>>>(keys_out, n, t2sizes);          // t2sizes doubles as the flag buffer
+        tb = cub_bytes;
+        cub::DeviceScan::InclusiveSum(cub_tmp, tb, t2sizes, gid, (int)n, st);
+        h->launches += 1;
         k_t2_sizes<<<nb256, 256, 0, st>>>(h->din, perm, ctr, t2sizes);
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t2sizes, t2off, (int)n, st);
         h->launches += 2;                           // own kernels only; CUB's sort/RLE/scan launches are not counted
         CK(cudaEventRecord(h->ev[1], st));
-        k_pack<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, perm, groups, t2off, ctr, meta, c3, t2, k_to_s, pr.ref_v_trim,
-                                                                        pr.ref_j_trim);
+        k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, pr.ref_v_trim, pr.ref_j_trim);
+        k_pack_c3<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, meta, ctr, c3);
+        k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2);
+        h->launches += 2;
         k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, n);
         h->launches += 2;
         CK(cudaEventRecord(h->ev[2], st));
@@ -516,11 +522,12 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_join_rows<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(h->din, tbs, pr, groups, ctr, cand, cap, parent, f0_key, f0_val, stride, phase);
         CK(cudaEventRecord(h->ev[3], st));
         for (int it = 0; it < 10; it++) k_root_jump<<<nb256, 256, 0, st>>>(parent, n);      // 4 hops each: covers chains up to 4^10
-        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, cand, cap, generic_q, acc, parent, 0);
+        k_phaseb_filter<<<h->sm_count * 8, 256, 0, st>>>(cand, cap, parent, ctr, todo);
+        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0);
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0);
         CK(cudaEventRecord(h->ev[4], st));
         k_collect<<<h->sm_count * 8, 256, 0, st>>>(f0_key, f0_val, n, acc, ctr, cap, pk_in, pv_in);
-        h->launches += 14;
+        h->launches += 15;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

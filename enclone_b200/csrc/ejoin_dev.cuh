@@ -60,7 +60,7 @@ struct GroupInfo {           // one comparison group = one run of equal sort key
 
 struct DevCounters {         // device-resident scalars (one struct, copied back once)
     unsigned long long n_valid, n_groups, n_work, c3_words, pairs_compared, pairs_candidate, n_buckets;
-    unsigned long long n_cand, n_generic, n_generic_q, n_accept, n_kept, pairs_tier2;
+    unsigned long long n_cand, n_todo, n_generic, n_generic_q, n_accept, n_kept, pairs_tier2;
     unsigned long long work_next;   // dynamic tile scheduler
     unsigned long long t1_alg_bytes, t2_alg_bytes, t2_units, n_classes;
     unsigned int err;

@@ -4,6 +4,12 @@
 
 #include "ejoin_dev.cuh"
 
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
 struct MaxOp {
     template <typename T> __host__ __device__ __forceinline__ T operator()(const T &a, const T &b) const { return a > b ? a : b; }
 };
@@ -38,8 +44,9 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
         if (valid) {
             key = ((unsigned long long)l0 << 48) | ((unsigned long long)l1 << 32) | ((unsigned long long)c0 << 16) | c1;
             uint32_t L = l0 + l1, cc = (c0 << 8) | c1;
-            atomicOr(&presL[L >> 5], 1u << (L & 31));
-            atomicOr(&presC[cc >> 5], 1u << (cc & 31));
+            // test before set: after the first hit per value these are plain cached loads, not serialized atomics
+            if (!(presL[L >> 5] & (1u << (L & 31)))) atomicOr(&presL[L >> 5], 1u << (L & 31));
+            if (!(presC[cc >> 5] & (1u << (cc & 31)))) atomicOr(&presC[cc >> 5], 1u << (cc & 31));
         }
         keys[k] = key;
         vals[k] = k;
@@ -126,6 +133,13 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *u
     }
 }
 
+// head flag of the sorted keys (1 where a new comparison group starts); its inclusive sum - 1 is
+// the group id of the entry (RLE run index)
+__global__ void k_sorted_heads(const unsigned long long *skeys, uint32_t n, uint32_t *flag) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) flag[s] = (s == 0 || skeys[s] != skeys[s - 1]) ? 1u : 0u;
+}
+
 // per sorted entry: t2 row size in 16-byte units = 3 * (ceil(len0/128) + ceil(len1/128))
 __global__ void __launch_bounds__(256) k_t2_sizes(DevIn in, const uint32_t *perm, DevCounters *ctr, uint32_t *sizes) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,104 +158,191 @@ __global__ void __launch_bounds__(256) k_t2_sizes(DevIn in, const uint32_t *perm
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3  pack: one warp per sorted entry.  Builds the c3 row, the t2 rows and the meta record
-// straight from the caller's ASCII bytes (CloneInfo.tigs / cdr3s / vs / js).
+// K3  pack: builds the c3 rows, the t2 rows and the meta records straight from the caller's
+// ASCII bytes (CloneInfo.tigs / cdr3s / vs / js), in three kernels:
+//   k_meta     one thread per entry: ids, lengths, window bounds, flags            -> meta
+//   k_pack_c3  one thread per 32-base word of the concatenated CDR3s               -> c3 rows
+//   k_pack_t2  one warp per entry, one LANE per 32-base plane word: 32 bases are read with three
+//              16-byte loads per sequence and reduced in registers with SWAR byte tricks
+//              (no cross-lane traffic); H/L/M words go straight to the 128-bit rows       -> t2 rows
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack(DevIn in, const uint32_t *perm, const GroupInfo *groups, const uint32_t *t2off,
-                                              DevCounters *ctr, EntryMeta *meta, uint32_t *c3, uint4 *t2, uint32_t *k_to_s,
-                                              int ref_v_trim, int ref_j_trim) {
+__device__ __forceinline__ uint32_t low_bytes(int nbytes) {       // 0xFF in the low nbytes (clamped to 0..4) bytes
+    nbytes = max(0, min(4, nbytes));
+    return (uint32_t)~(~0ull << (8 * nbytes));
+}
+__device__ __forceinline__ uint32_t low_bits(int nbits) {         // low nbits (clamped to 0..32) bits set
+    nbits = max(0, min(32, nbits));
+    return (uint32_t)~(~0ull << nbits);
+}
+__device__ __forceinline__ uint32_t nibble_of(uint32_t y) {       // bit 0 of byte i -> bit i
+    return ((y & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+}
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t d) {   // bit 0 of each byte = (byte != 0)
+    return ((d | ((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) >> 7) & 0x01010101u;
+}
+__device__ __forceinline__ uint32_t not_acgt(uint32_t x) {        // nonzero iff some byte is not one of A,C,G,T
+    // rebuild the byte each 2-bit code (b>>1)&3 stands for with one PRMT and compare
+    const uint32_t y = (x >> 1) & 0x03030303u;
+    const uint32_t t = y | (y >> 4);
+    const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);      // four code nibbles
+    return __byte_perm(0x47544341u /* 'A','C','T','G' for codes 0,1,2,3 */, 0u, sel) ^ x;
+}
+// 32 bytes starting at an arbitrary address, from three aligned 16-byte loads (the arenas carry
+// 64 bytes of slack).  out[i] holds bytes 4i..4i+3.
+__device__ __forceinline__ void load32u(const uint8_t *p, uint32_t (&out)[8]) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint4 *q = (const uint4 *)(a & ~(uintptr_t)15);
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+    const uint32_t w[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+    const uint32_t sh = 8u * (uint32_t)(a & 3);
+    switch ((a >> 2) & 3) {
+        case 0:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
+            break;
+        case 1:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i + 1], w[i + 2], sh);
+            break;
+        case 2:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i + 2], w[i + 3], sh);
+            break;
+        default:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i + 3], w[i + 4], sh);
+            break;
+    }
+}
+// plane words of 32 bytes: code = (byte >> 1) & 3, i.e. A,C,G,T -> 0,1,3,2 (any injective code
+// works: only equality is ever used); H = bit 1 of the code, L = bit 0.
+__device__ __forceinline__ void planes32(const uint32_t (&x)[8], uint32_t &H, uint32_t &L) {
+    H = 0; L = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { H |= nibble_of(x[i] >> 2) << (4 * i); L |= nibble_of(x[i] >> 1) << (4 * i); }
+}
+__device__ __forceinline__ uint32_t neq32(const uint32_t (&x)[8], const uint32_t (&r)[8]) {   // bit i = (byte i differs)
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) m |= ((nonzero_bytes(x[i] ^ r[i]) * 0x01020408u) >> 24 & 0xFu) << (4 * i);
+    return m;
+}
+
+__global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ gid_incl,
+                                              const GroupInfo *__restrict__ groups, const uint32_t *__restrict__ t2off, DevCounters *ctr,
+                                              EntryMeta *__restrict__ meta, uint32_t *__restrict__ k_to_s, int ref_v_trim, int ref_j_trim) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= (uint32_t)ctr->n_valid) return;
+    const uint32_t k = perm[s];
+    const GroupInfo g = groups[gid_incl[s] - 1];
+    EntryMeta m;
+    memset(&m, 0, sizeof(m));
+    const uint32_t e = in.exact_id[k];
+    m.k = k; m.t2off = t2off[s]; m.c3off = g.c3base + (s - g.start) * 2 * g.W;
+    m.donor_lo = in.donor_lo[e]; m.donor_hi = in.donor_hi[e];
+    uint32_t flags = 0;
+    for (int c = 0; c < 2; c++) {
+        const int n = in.len[c][k];
+        const uint32_t vi = in.vs_seq[c][k], ji = in.js_seq[c][k];
+        const bool bad = vi >= in.n_refseq || ji >= in.n_refseq;
+        if (bad) atomicOr(&ctr->err, ERR_BAD_REFSEQ);
+        const int vl = bad ? 0 : (int)in.refseq_len[vi], jl = bad ? 0 : (int)in.refseq_len[ji];
+        int vend = max(0, min(n, vl - ref_v_trim));
+        const int jw = jl - ref_j_trim;                  // J window length
+        int jstart = jw > 0 ? max(0, n - jw) : n;
+        if (jstart < vend) flags |= (FLAG_GENERIC0 << c);  // overlapping windows: counted separately -> bytewise path
+        if (in.has_del[c][k]) flags |= (FLAG_GENERIC0 << c);
+        m.vref[c] = in.v_ref_id[c][k]; m.jref[c] = in.j_ref_id[c][k]; m.dref[c] = in.dref_id[c][k];
+        m.vs[c] = vi; m.js[c] = ji; m.vname[c] = in.vname_id[c][k];
+        m.len[c] = (uint16_t)n; m.cs[c] = in.cdr3_start[c][k]; m.cl[c] = in.cdr3_len[c][k];
+        m.vend[c] = (uint16_t)vend; m.jstart[c] = (uint16_t)jstart;
+    }
+    m.c_light = in.c_ref_id_light[k];
+    m.hcomp = in.hcomp[k]; m.fr1 = in.fr1[k]; m.cdr1 = in.cdr1[k]; m.fr2 = in.fr2[k]; m.cdr2 = in.cdr2[k]; m.fr3 = in.fr3[k];
+    m.flags = (uint16_t)flags;
+    meta[s] = m;
+    k_to_s[k] = s;
+}
+
+// one thread per (entry, c3 word); 8 threads per entry, W of them active
+__global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__restrict__ meta, DevCounters *ctr, uint32_t *__restrict__ c3) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = t >> 3, w = t & 7;
+    if (s >= (uint32_t)ctr->n_valid) return;
+    const EntryMeta &m = meta[s];
+    const int cl0 = m.cl[0], total = cl0 + m.cl[1];
+    const int W = max(1, (total + 31) / 32);
+    if ((int)w >= W) return;
+    const uint32_t k = m.k;
+    const uint8_t *q0 = in.cdr3_arena + in.cdr3_off[0][k], *q1 = in.cdr3_arena + in.cdr3_off[1][k];
+    uint32_t H = 0, L = 0, bad = 0;
+    for (int i = 0; i < 32; i++) {
+        const int p = (int)w * 32 + i;
+        if (p >= total) break;
+        const int code = base_code(p < cl0 ? q0[p] : q1[p - cl0]);
+        if (code < 0) bad = 1;
+        else { H |= (uint32_t)((code >> 1) & 1) << i; L |= (uint32_t)(code & 1) << i; }
+    }
+    if (bad) atomicOr(&ctr->err, ERR_CDR3_BAD_CHAR);
+    c3[m.c3off + w] = H;
+    c3[m.c3off + W + w] = L;
+}
+
+__global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nvalid = (uint32_t)ctr->n_valid;
-    if (s >= nvalid) return;
-    const uint32_t k = perm[s];
-    // group of s: binary search on group starts
-    uint32_t lo = 0, hi = (uint32_t)ctr->n_groups;
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (groups[mid].start <= s) lo = mid; else hi = mid; }
-    const GroupInfo g = groups[lo];
-    const uint32_t W = g.W;
-    const uint32_t c3off = g.c3base + (s - g.start) * 2 * W;
-    // ---- c3 row: CDR3 of chain 0 then chain 1, as two bit planes ----
-    const uint32_t cl0 = in.cdr3_len[0][k], cl1 = in.cdr3_len[1][k];
-    const uint8_t *q0 = in.cdr3_arena + in.cdr3_off[0][k], *q1 = in.cdr3_arena + in.cdr3_off[1][k];
-    for (uint32_t w = 0; w < W; w++) {
-        uint32_t p = w * 32 + lane;
-        int code = 0;
-        if (p < cl0 + cl1) {
-            code = base_code(p < cl0 ? q0[p] : q1[p - cl0]);
-            if (code < 0) { atomicOr(&ctr->err, ERR_CDR3_BAD_CHAR); code = 0; }
-        }
-        uint32_t H = __ballot_sync(0xFFFFFFFFu, code & 2), L = __ballot_sync(0xFFFFFFFFu, code & 1);
-        if (lane == 0) { c3[c3off + w] = H; c3[c3off + W + w] = L; }
-    }
-    // ---- t2 rows ----
-    uint32_t unit = t2off[s];
-    uint32_t mcount[2] = { 0, 0 };
-    uint32_t flags = 0;
-    uint16_t vend_[2], jstart_[2];
-    for (int c = 0; c < 2; c++) {
-        const uint32_t n = in.len[c][k];
-        const uint8_t *t = in.tig_arena + in.tig_off[c][k];
-        const uint32_t vi = in.vs_seq[c][k], ji = in.js_seq[c][k];
-        bool bad = vi >= in.n_refseq || ji >= in.n_refseq;
-        if (bad) { atomicOr(&ctr->err, ERR_BAD_REFSEQ); }
-        const uint8_t *v = bad ? t : in.refseq_arena + in.refseq_off[vi];
-        const uint8_t *j = bad ? t : in.refseq_arena + in.refseq_off[ji];
-        const int vl = bad ? 0 : (int)in.refseq_len[vi], jl = bad ? 0 : (int)in.refseq_len[ji];
-        int vend = vl - ref_v_trim;
-        if (vend > (int)n) vend = (int)n;
-        if (vend < 0) vend = 0;
-        int jw = jl - ref_j_trim;                 // J window length
-        int jstart = jw > 0 ? (int)n - jw : (int)n;
-        if (jstart < 0) jstart = 0;
-        if (jstart < vend) flags |= (FLAG_GENERIC0 << c);   // overlapping windows: count each separately -> bytewise path
-        if (in.has_del[c][k]) flags |= (FLAG_GENERIC0 << c);
-        vend_[c] = (uint16_t)vend; jstart_[c] = (uint16_t)jstart;
-        const uint32_t nblk = (n + 127) / 128;
-        for (uint32_t b = 0; b < nblk; b++) {
-            uint32_t Hw = 0, Lw = 0, Mw = 0;      // lane w (<4) keeps word w of this block
-            for (uint32_t w = 0; w < 4; w++) {
-                uint32_t p = b * 128 + w * 32 + lane;
-                int code = 0, mut = 0, weird = 0;
-                if (p < n) {
-                    uint8_t ch = t[p];
-                    code = base_code(ch);
-                    if (code < 0) { weird = 1; code = 0; }
-                    if ((int)p < vend) mut = ch != v[p];
-                    else if ((int)p >= jstart) mut = ch != j[jl - ((int)n - (int)p)];
-                }
-                uint32_t H = __ballot_sync(0xFFFFFFFFu, code & 2), L = __ballot_sync(0xFFFFFFFFu, code & 1);
-                uint32_t M = __ballot_sync(0xFFFFFFFFu, mut);
-                if (__any_sync(0xFFFFFFFFu, weird)) flags |= (FLAG_GENERIC0 << c);
-                if (lane == w) { Hw = H; Lw = L; Mw = M; }
-                mcount[c] += __popc(M);
+    if (s >= (uint32_t)ctr->n_valid) return;
+    const EntryMeta &m = meta[s];
+    const uint32_t k = m.k;
+    const int n0 = m.len[0], n1 = m.len[1];
+    const int nw0 = 4 * ((n0 + 127) / 128), nw = nw0 + 4 * ((n1 + 127) / 128);
+    uint32_t *rows = (uint32_t *)(t2 + m.t2off);
+    int mcount0 = 0, mcount1 = 0;
+    uint32_t weird0 = 0, weird1 = 0;
+    for (int w = (int)lane; w < nw; w += 32) {
+        const int c = w >= nw0;
+        const int wl = c ? w - nw0 : w;                       // word index inside the chain
+        const int n = c ? n1 : n0;
+        const int p0 = wl * 32;
+        uint32_t H = 0, L = 0, M = 0;
+        if (p0 < n) {
+            const uint8_t *t = in.tig_arena + in.tig_off[c][k];
+            uint32_t x[8];
+            load32u(t + p0, x);
+            const int nb = n - p0;                            // valid bytes in this word (>= 1)
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] &= low_bytes(nb - 4 * i);
+            uint32_t wd = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) wd |= not_acgt(x[i]) & low_bytes(nb - 4 * i);
+            if (c) weird1 |= wd; else weird0 |= wd;
+            planes32(x, H, L);
+            const uint32_t valid = low_bits(nb);
+            H &= valid; L &= valid;
+            const int vend = m.vend[c], jstart = m.jstart[c];
+            const uint32_t inV = low_bits(vend - p0) & valid, inJ = valid & ~low_bits(jstart - p0);
+            if (inV) {
+                uint32_t r[8];
+                load32u(in.refseq_arena + in.refseq_off[m.vs[c]] + p0, r);
+                M |= neq32(x, r) & inV;
             }
-            // lanes 0..3 hold the four words of each plane: assemble 128-bit rows
-            uint4 rh, rl, rm;
-            rh.x = __shfl_sync(0xFFFFFFFFu, Hw, 0); rh.y = __shfl_sync(0xFFFFFFFFu, Hw, 1); rh.z = __shfl_sync(0xFFFFFFFFu, Hw, 2); rh.w = __shfl_sync(0xFFFFFFFFu, Hw, 3);
-            rl.x = __shfl_sync(0xFFFFFFFFu, Lw, 0); rl.y = __shfl_sync(0xFFFFFFFFu, Lw, 1); rl.z = __shfl_sync(0xFFFFFFFFu, Lw, 2); rl.w = __shfl_sync(0xFFFFFFFFu, Lw, 3);
-            rm.x = __shfl_sync(0xFFFFFFFFu, Mw, 0); rm.y = __shfl_sync(0xFFFFFFFFu, Mw, 1); rm.z = __shfl_sync(0xFFFFFFFFu, Mw, 2); rm.w = __shfl_sync(0xFFFFFFFFu, Mw, 3);
-            if (lane == 0) { t2[unit] = rh; t2[unit + 1] = rl; t2[unit + 2] = rm; }
-            unit += 3;
+            if (inJ) {
+                const uint32_t ji = m.js[c];
+                uint32_t r[8];
+                load32u(in.refseq_arena + in.refseq_off[ji] + (p0 - (n - (int)in.refseq_len[ji])), r);
+                M |= neq32(x, r) & inJ;
+            }
+            if (c) mcount1 += __popc(M); else mcount0 += __popc(M);
         }
+        const int o = (w >> 2) * 12 + (w & 3);
+        rows[o] = H; rows[o + 4] = L; rows[o + 8] = M;
     }
+    mcount0 = warp_sum_i(mcount0); mcount1 = warp_sum_i(mcount1);
+    const bool g0 = __any_sync(0xFFFFFFFFu, weird0 != 0), g1 = __any_sync(0xFFFFFFFFu, weird1 != 0);
     if (lane == 0) {
-        EntryMeta m;
-        memset(&m, 0, sizeof(m));
-        const uint32_t e = in.exact_id[k];
-        m.k = k; m.t2off = t2off[s]; m.c3off = c3off;
-        m.donor_lo = in.donor_lo[e]; m.donor_hi = in.donor_hi[e];
-        for (int c = 0; c < 2; c++) {
-            m.vref[c] = in.v_ref_id[c][k]; m.jref[c] = in.j_ref_id[c][k]; m.dref[c] = in.dref_id[c][k];
-            m.vs[c] = in.vs_seq[c][k]; m.js[c] = in.js_seq[c][k]; m.vname[c] = in.vname_id[c][k];
-            m.len[c] = in.len[c][k]; m.cs[c] = in.cdr3_start[c][k]; m.cl[c] = in.cdr3_len[c][k];
-            m.m[c] = (uint16_t)mcount[c]; m.vend[c] = vend_[c]; m.jstart[c] = jstart_[c];
-        }
-        m.c_light = in.c_ref_id_light[k];
-        m.hcomp = in.hcomp[k]; m.fr1 = in.fr1[k]; m.cdr1 = in.cdr1[k]; m.fr2 = in.fr2[k]; m.cdr2 = in.cdr2[k]; m.fr3 = in.fr3[k];
-        m.flags = (uint16_t)flags;
-        meta[s] = m;
-        k_to_s[k] = s;
+        EntryMeta *mm = &meta[s];
+        mm->m[0] = (uint16_t)mcount0; mm->m[1] = (uint16_t)mcount1;
+        if (g0 || g1) mm->flags = (uint16_t)(mm->flags | (g0 ? FLAG_GENERIC0 : 0u) | (g1 ? FLAG_GENERIC1 : 0u));
     }
 }
 
@@ -446,40 +547,60 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5  tier 2, phase B: one thread per recorded survivor; scored only when its endpoints lie in
-// different phase-A trees.
+// K5  tier 2, phase B.  k_phaseb_filter: one thread per recorded survivor; keeps (compacted) those
+// that must be scored: endpoints in different phase-A trees, or the force bit.  k_tier2: one thread
+// per kept pair, full evaluation (dense, so warps stay converged).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *cand,
-                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, const uint32_t *root,
-                                               uint32_t k_base) {
-    uint32_t *minnbr = nullptr;
+__global__ void __launch_bounds__(256) k_phaseb_filter(const uint2 *__restrict__ cand, unsigned long long cand_cap, const uint32_t *__restrict__ root,
+                                                       DevCounters *ctr, uint2 *__restrict__ todo) {
     unsigned long long ncand = ctr->n_cand;
     if (ncand > cand_cap) ncand = cand_cap;
-    unsigned long long my_pairs = 0, my_bytes = 0;      // per-thread tallies, one atomic per warp at the end
+    const uint32_t lane = threadIdx.x & 31;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((ncand + 31) & ~31ull);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        bool keep = false;
+        uint2 c = make_uint2(0, 0);
+        if (i < ncand) {
+            c = cand[i];
+            const bool force = c.x >> 31;
+            c.x &= 0x7FFFFFFFu;
+            // a survivor whose endpoints already sit in one phase-A tree cannot be a forest edge
+            // (DESIGN.md §lazy): never scored
+            keep = force || root[c.x] != root[c.y];
+        }
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
+        if (!mask) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->n_todo, (unsigned long long)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(mask & ((1u << lane) - 1u));
+        if (keep) todo[base] = c;                            // todo has the capacity of cand
+    }
+}
+
+__global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
+                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t k_base) {
+    uint32_t *minnbr = nullptr;
+    unsigned long long ntodo = ctr->n_todo;
+    if (ntodo > cand_cap) ntodo = cand_cap;
+    unsigned long long my_pairs = 0, my_bytes = 0;      // per-thread tallies, one atomic per warp at the end
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((ntodo + 31) & ~31ull);
          i += (unsigned long long)gridDim.x * blockDim.x) {
         bool accepted = false;
         uint32_t k1 = 0, k2 = 0;
         int cd = 0, d = 0, reason = 0, err = 0;
-        if (i < ncand) {
-            uint2 c = cand[i];
-            const bool force = c.x >> 31;
-            c.x &= 0x7FFFFFFFu;
-            // a survivor whose endpoints already sit in one phase-A tree cannot be a forest edge
-            // (DESIGN.md §lazy): skip it unscored
-            if (force || root[c.x] != root[c.y]) {
-                bool scored;
-                reason = evaluate_thread(in, tb, pr, ctr, c.x, c.y, &cd, &d, &err, &scored, &my_bytes);
-                my_pairs += scored;
-                if (reason < 0) {
-                    unsigned long long q = atomicAdd(&ctr->n_generic_q, 1ull);
-                    if (q < cand_cap) generic_q[q] = c;            // c.x < c.y positions: already k1 < k2
-                    reason = 0;
-                }
-                accepted = reason != 0;
-                k1 = tb.meta[c.x].k; k2 = tb.meta[c.y].k;
-                if (k1 > k2) { uint32_t t = k1; k1 = k2; k2 = t; }
+        if (i < ntodo) {
+            const uint2 c = todo[i];
+            bool scored;
+            reason = evaluate_thread(in, tb, pr, ctr, c.x, c.y, &cd, &d, &err, &scored, &my_bytes);
+            my_pairs += scored;
+            if (reason < 0) {
+                unsigned long long q = atomicAdd(&ctr->n_generic_q, 1ull);
+                if (q < cand_cap) generic_q[q] = c;            // c.x < c.y positions: already k1 < k2
+                reason = 0;
             }
+            accepted = reason != 0;
+            k1 = tb.meta[c.x].k; k2 = tb.meta[c.y].k;
+            if (k1 > k2) { uint32_t t = k1; k1 = k2; k2 = t; }
         }
         emit_raw(pr, ctr, acc, cand_cap, minnbr, k1 + k_base, k2 + k_base, cd, d, reason, err, accepted);
     }
@@ -757,14 +878,16 @@ struct RowCtx {
 template <int W>
 __device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
                                           const uint32_t (&bH)[W], const uint32_t (&bL)[W], bool validB, uint32_t posA0, uint32_t posB,
-                                          bool &found, uint32_t &nrej) {
+                                          bool &found, uint32_t &nrej, uint32_t &my_parent) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
+    if (!__any_sync(0xFFFFFFFFu, validB)) return;          // a warp beyond the end of a short B tile
     for (uint32_t a0 = 0; a0 < rowsA; a0 += 32) {
         // on the diagonal tile only a < b counts: a warp whose b's all precede this block is done
         if (diag && a0 > (tid | 31u)) break;
         uint32_t bits = 0;
+        const uint32_t na_loop = min(32u, rowsA - a0);
 #pragma unroll 4
-        for (uint32_t aa = 0; aa < 32; aa++) {
+        for (uint32_t aa = 0; aa < na_loop; aa++) {
             const uint32_t *ra = sA + (a0 + aa) * 2 * W;
             uint32_t cnt = 0;
 #pragma unroll
@@ -806,6 +929,7 @@ __device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict
                 if (reason <= 0 && ++nrej >= PHASE_A_MAX_REJECTS) found = true;     // give up: see below
                 if (reason > 0) {
                     found = true;
+                    my_parent = pa;
                     cx.parent[posB] = pa;
                     cx.f0_key[posB] = ((unsigned long long)cx.tb->meta[pa].k << 32) | cx.tb->meta[posB].k;
                     cx.f0_val[posB] = ((unsigned long long)((uint32_t)reason | ((uint32_t)err << 8)) << 32) |
@@ -813,7 +937,17 @@ __device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict
                 }
             }
         }
-        // ---- remaining survivors (b already has its partner): record for phase B
+        // ---- remaining survivors (b already has its partner): record for phase B, except those that
+        //      visibly hang off the same phase-A parent as b (same tree: phase B would skip them anyway;
+        //      a stale read of parent[] only makes us keep a pair)
+        if (__any_sync(0xFFFFFFFFu, bits != 0 && nrej < PHASE_A_MAX_REJECTS)) {
+            // one coalesced read of the block's 32 parents, then a register transpose by shuffles
+            const uint32_t par_blk = (a0 + lane < rowsA) ? __ldcg(&cx.parent[posA0 + a0 + lane]) : 0xFFFFFFFEu;
+            uint32_t same = 0;
+#pragma unroll
+            for (int aa = 0; aa < 32; aa++) same |= (__shfl_sync(0xFFFFFFFFu, par_blk, aa) == my_parent ? 1u : 0u) << aa;
+            if (nrej < PHASE_A_MAX_REJECTS) bits &= ~same;
+        }
         if (__any_sync(0xFFFFFFFFu, bits != 0)) {
             uint32_t cntl = __popc(bits), incl = cntl;
 #pragma unroll
@@ -847,7 +981,7 @@ __device__ __forceinline__ void row_item(RowCtx &cx, const GroupInfo &g, uint32_
         for (int w = 0; w < W; w++) { bH[w] = rb[w]; bL[w] = rb[W + w]; }
     }
     bool found = false;
-    uint32_t nrej = 0;
+    uint32_t nrej = 0, my_parent = 0xFFFFFFFFu;
     auto issue = [&](uint32_t ia) {
         const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
         const uint32_t bytes = (rowsA * 2 * W * 4 + 15) & ~15u;
@@ -861,7 +995,7 @@ __device__ __forceinline__ void row_item(RowCtx &cx, const GroupInfo &g, uint32_
         mbar_wait(&bar[ia & 1], (parity >> (ia & 1)) & 1u);
         parity ^= 1u << (ia & 1);
         const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
-        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, found, nrej);
+        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, found, nrej, my_parent);
         __syncthreads();
     }
 }
