@@ -78,6 +78,7 @@ struct ejoin_handle {
     uint64_t tig_bytes = 0;
     uint64_t h2d_bytes = 0;
     bool uploaded = false;
+    bool device_final = false;  // the last pipeline run produced the final emitted edge list on the device
     // tables (cached across runs)
     DevBuf d_counters, d_presL, d_presC, d_p1ptrs, d_multinfo, d_multpool, d_cdmax, d_p1scratch, d_Ls, d_tabptrs;
     std::vector<double *> p1_host_ptrs;            // [8192] device pointers (host copy)
@@ -118,7 +119,7 @@ DevParams dev_params(const ejoin_params_t &p, int is_bcr) {
     d.auto_share = p.auto_share; d.comp_filt = p.comp_filt; d.comp_filt_bound = p.comp_filt_bound;
     d.max_cdr3_diffs = p.max_cdr3_diffs; d.cdr3_mult = p.cdr3_mult; d.max_degradation = p.max_degradation;
     d.max_diffs = p.max_diffs; d.max_diffs_tcr = p.max_diffs_tcr; d.ref_v_trim = p.ref_v_trim; d.ref_j_trim = p.ref_j_trim;
-    d.old_light = p.old_light; d.mix_donors = p.mix_donors; d.is_bcr = is_bcr;
+    d.old_light = p.old_light; d.mix_donors = p.mix_donors; d.is_bcr = is_bcr; d.easy = p.easy;
     return d;
 }
 
@@ -449,7 +450,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);        // cand, todo, generic, acc
-        sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // prune keys/vals in+out
+        sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
+        sz.take(8 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                   // Boruvka: best, ends, component sizes
         sz.take(cub_bytes + 256);
         sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1));                   // payload staging (taken later)
         sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)h->din.n_exact + 64);                              // union-find labels, first entry per exact
@@ -472,6 +474,9 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         ejoin_raw_edge_t *acc = A.take<ejoin_raw_edge_t>(cap);
         unsigned long long *pk_in = A.take<unsigned long long>(cap), *pv_in = A.take<unsigned long long>(cap);
         unsigned long long *pk_out = A.take<unsigned long long>(cap), *pv_out = A.take<unsigned long long>(cap);
+        unsigned long long *best = A.take<unsigned long long>(n);
+        uint2 *ends = A.take<uint2>(cap);
+        uint32_t *comp_size = A.take<uint32_t>(n);
         void *cub_tmp = A.take<char>(cub_bytes + 256);
         h->meta = meta; h->c3 = c3; h->t2 = t2; h->k_to_s = k_to_s; h->kept_keys = pk_out; h->kept_vals = pv_out;
         DevCounters *ctr = (DevCounters *)h->d_counters.p;
@@ -521,13 +526,32 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (rows_occ < 1) rows_occ = 1;
         k_join_rows<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(h->din, tbs, pr, groups, ctr, cand, cap, parent, f0_key, f0_val, stride, phase);
         CK(cudaEventRecord(h->ev[3], st));
+        // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
+        // accepted partner becomes the tree edge (atomicMin on the parent)
+        k_phaseb_filter<<<h->sm_count * 8, 256, 0, st>>>(cand, cap, parent, ctr, todo, 0);
+        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, parent);
+        k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, parent, 0);
+        k_forced_resolve<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, f0_key, f0_val);
         for (int it = 0; it < 10; it++) k_root_jump<<<nb256, 256, 0, st>>>(parent, n);      // 4 hops each: covers chains up to 4^10
-        k_phaseb_filter<<<h->sm_count * 8, 256, 0, st>>>(cand, cap, parent, ctr, todo);
-        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0);
-        k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0);
+        // round 2: the other recorded survivors, scored only across trees
+        k_round2_begin<<<1, 1, 0, st>>>(ctr);
+        k_forced_prune<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent);
+        k_phaseb_filter<<<h->sm_count * 8, 256, 0, st>>>(cand, cap, parent, ctr, todo, 1);
+        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, nullptr);
+        k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, nullptr, 1);
         CK(cudaEventRecord(h->ev[4], st));
-        k_collect<<<h->sm_count * 8, 256, 0, st>>>(f0_key, f0_val, n, acc, ctr, cap, pk_in, pv_in);
-        h->launches += 15;
+        const bool device_final = stride == 1;      // stride mode: the forest needs every rank's edges -> host replay after the gather
+        h->device_final = device_final;
+        if (device_final) {
+            k_fill_u64<<<nb256, 256, 0, st>>>(best, ~0ull, n);
+            for (int round = 0; round < 5; round++) {
+                k_bor_min<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, best, ends);
+                k_bor_select<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, parent, best, ends);
+                k_bor_reset<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, best, ends);
+            }
+            k_bor_min<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, best, ends);   // leaves bor_active = 1 iff edges still cross
+            h->launches += 17;
+        }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -540,6 +564,26 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             h->cand_cap = std::max(h->counters.n_cand, std::max(h->counters.n_generic_q, (unsigned long long)n + h->counters.n_accept)) + 1024;
             continue;
         }
+        if (device_final) {
+            for (int guard = 0; h->counters.bor_active && guard < 64; guard++) {     // rare: more than 5 rounds needed
+                k_bor_select<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, parent, best, ends);
+                k_bor_reset<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, best, ends);
+                k_bor_min<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, best, ends);
+                h->launches += 3;
+                CK(cudaMemcpyAsync(&h->counters.bor_active, &ctr->bor_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+            CK(cudaMemsetAsync(comp_size, 0, 4 * (size_t)n, st));
+            k_comp_size<<<nb256, 256, 0, st>>>(parent, (uint32_t)h->counters.n_valid, comp_size);
+            k_final_collect<<<h->sm_count * 8, 256, 0, st>>>(h->din, f0_key, f0_val, n, acc, ctr, cap, k_to_s, 0, parent, comp_size, pr.easy, pk_in, pv_in);
+            h->launches += 2;
+        } else {
+            k_collect<<<h->sm_count * 8, 256, 0, st>>>(f0_key, f0_val, n, acc, ctr, cap, pk_in, pv_in);
+            h->launches += 1;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h->counters.n_kept, &ctr->n_kept, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
         const unsigned long long nk = h->counters.n_kept;
         const unsigned long long nsorted = (unsigned long long)n + std::min<unsigned long long>(h->counters.n_accept, cap);
         if (nk) {
@@ -654,8 +698,9 @@ void host_partition(const ejoin_pack_t *pk, const uint32_t *k1, const uint32_t *
 // Emitted edges -> full PotentialJoin records (k_payload) and, when the handle holds the whole
 // input, the finish_join partition by the GPU union-find; both land in the handle's pinned
 // result buffer.
-int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2> &pairs, size_t pin_used, ejoin_result_t *out) {
-    const size_t ne = pairs.size();
+int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2> &pairs, const unsigned long long *d_keys, size_t ne_dev,
+                size_t pin_used, ejoin_result_t *out) {
+    const size_t ne = d_keys ? ne_dev : pairs.size();
     const uint32_t n = h->n;
     const bool whole = h->k_base == 0 && h->n == pk->n_info;
     const DevParams pr = dev_params(h->params, (int)pk->is_bcr);
@@ -680,7 +725,8 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
     DevCounters *ctr = (DevCounters *)h->d_counters.p;
     const double t_dev0 = now_ms();
     if (ne) {
-        CK(cudaMemcpyAsync(d_pairs, pairs.data(), ne * sizeof(uint2), cudaMemcpyHostToDevice, h->st));
+        if (d_keys) k_keys_to_pairs<<<(unsigned)((ne + 255) / 256), 256, 0, h->st>>>(d_keys, (uint32_t)ne, d_pairs);
+        else CK(cudaMemcpyAsync(d_pairs, pairs.data(), ne * sizeof(uint2), cudaMemcpyHostToDevice, h->st));
         DevTables tbs;
         tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
         tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
@@ -735,7 +781,7 @@ static int finish_common(ejoin_handle *h, const ejoin_pack_t *pk, const unsigned
     std::vector<uint2> fin;
     replay(h, pk, keys, vals, nk, fin);
     if (getenv("EJOIN_DEBUG")) fprintf(stderr, "[ejoin] replay: %zu sorted edges -> %zu emitted, %.3f ms\n", nk, fin.size(), now_ms() - t0);
-    int rc = emit_result(h, pk, fin, pin_used, out);
+    int rc = emit_result(h, pk, fin, nullptr, 0, pin_used, out);
     if (rc) return rc;
     h->stats.ms_host_post = now_ms() - t0;
     return 0;
@@ -756,18 +802,15 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     if (rc) return rc;
     const double t2 = now_ms();
     const size_t nk = (size_t)h->counters.n_kept;
-    rc = ensure_pin(h, 16 * nk + sizeof(ejoin_edge_t) * (nk + 1) + 4 * ((size_t)h->n + 1) + 1024);
+    rc = ensure_pin(h, sizeof(ejoin_edge_t) * (nk + 1) + 4 * ((size_t)h->n + 1) + 1024);
     if (rc) return rc;
-    unsigned long long *hk = (unsigned long long *)h->pin, *hv = hk + nk;
-    if (nk) {
-        CK(cudaMemcpyAsync(hk, h->kept_keys, 8 * nk, cudaMemcpyDeviceToHost, h->st));
-        CK(cudaMemcpyAsync(hv, h->kept_vals, 8 * nk, cudaMemcpyDeviceToHost, h->st));
-        CK(cudaStreamSynchronize(h->st));
-    }
-    h->stats.d2h_bytes = 16 * nk + sizeof(DevCounters);
+    h->stats.d2h_bytes = sizeof(DevCounters);
     const double t3 = now_ms();
-    rc = finish_common(h, pk, hk, hv, nk, 16 * nk, out);
-    if (rc) return rc;
+    {   // the sorted keys on the device already are raw_joins: payload + partition, no host replay
+        static const std::vector<uint2> none;
+        rc = emit_result(h, pk, none, h->kept_keys, nk, 0, out);
+        if (rc) return rc;
+    }
     const double t4 = now_ms();
     fill_stats(h, &out->stats);
     out->stats.ms_h2d = t1 - t0; out->stats.ms_d2h = t3 - t2; out->stats.ms_host_post = t4 - t3; out->stats.ms_total = t4 - t0;

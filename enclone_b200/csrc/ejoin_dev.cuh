@@ -61,16 +61,17 @@ struct GroupInfo {           // one comparison group = one run of equal sort key
 struct DevCounters {         // device-resident scalars (one struct, copied back once)
     unsigned long long n_valid, n_groups, n_work, c3_words, pairs_compared, pairs_candidate, n_buckets;
     unsigned long long n_cand, n_todo, n_generic, n_generic_q, n_accept, n_kept, pairs_tier2;
+    unsigned long long n_accept_r1, n_generic_r1, n_todo_r1;
     unsigned long long work_next;   // dynamic tile scheduler
     unsigned long long t1_alg_bytes, t2_alg_bytes, t2_units, n_classes;
     unsigned int err;
-    unsigned int max_k;
+    unsigned int bor_active;
 };
 
 struct DevParams {           // ejoin_params_t plus run constants, by value to kernels
     double max_score, join_cdr3_ident, fwr1_cdr12_delta;
     int auto_share, comp_filt, comp_filt_bound, max_cdr3_diffs, cdr3_mult, max_degradation;
-    int max_diffs, max_diffs_tcr, ref_v_trim, ref_j_trim, old_light, mix_donors, is_bcr;
+    int max_diffs, max_diffs_tcr, ref_v_trim, ref_j_trim, old_light, mix_donors, is_bcr, easy;
 };
 
 struct MultInfo { uint32_t off; uint32_t d1p1; };   // per (cl0,cl1): pool offset, row stride (D1+1); off = ~0 if absent

@@ -10,6 +10,9 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t uf_find(uint32_t *p, uint32_t x);
+__device__ __forceinline__ void uf_union(uint32_t *p, uint32_t a, uint32_t b);
+
 struct MaxOp {
     template <typename T> __host__ __device__ __forceinline__ T operator()(const T &a, const T &b) const { return a > b ? a : b; }
 };
@@ -551,8 +554,10 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
 // that must be scored: endpoints in different phase-A trees, or the force bit.  k_tier2: one thread
 // per kept pair, full evaluation (dense, so warps stay converged).
 // ---------------------------------------------------------------------------------------------
+// mode 0: the survivors of entries that gave up in phase A (force bit) -> all scored (round 1);
+// mode 1: the other recorded survivors whose endpoints lie in different trees (round 2).
 __global__ void __launch_bounds__(256) k_phaseb_filter(const uint2 *__restrict__ cand, unsigned long long cand_cap, const uint32_t *__restrict__ root,
-                                                       DevCounters *ctr, uint2 *__restrict__ todo) {
+                                                       DevCounters *ctr, uint2 *__restrict__ todo, int mode) {
     unsigned long long ncand = ctr->n_cand;
     if (ncand > cand_cap) ncand = cand_cap;
     const uint32_t lane = threadIdx.x & 31;
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(256) k_phaseb_filter(const uint2 *__restrict__
             c.x &= 0x7FFFFFFFu;
             // a survivor whose endpoints already sit in one phase-A tree cannot be a forest edge
             // (DESIGN.md §lazy): never scored
-            keep = force || root[c.x] != root[c.y];
+            keep = mode == 0 ? force : (!force && root[c.x] != root[c.y]);
         }
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
         if (!mask) continue;
@@ -578,7 +583,8 @@ __global__ void __launch_bounds__(256) k_phaseb_filter(const uint2 *__restrict__
 }
 
 __global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
-                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t k_base) {
+                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t k_base,
+                                               uint32_t *parent_min) {
     uint32_t *minnbr = nullptr;
     unsigned long long ntodo = ctr->n_todo;
     if (ntodo > cand_cap) ntodo = cand_cap;
@@ -601,6 +607,8 @@ __global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams
             accepted = reason != 0;
             k1 = tb.meta[c.x].k; k2 = tb.meta[c.y].k;
             if (k1 > k2) { uint32_t t = k1; k1 = k2; k2 = t; }
+            // round 1: the smallest accepted partner of b becomes its phase-A parent after all
+            if (accepted && parent_min) atomicMin(&parent_min[c.y], c.x);
         }
         emit_raw(pr, ctr, acc, cand_cap, minnbr, k1 + k_base, k2 + k_base, cd, d, reason, err, accepted);
     }
@@ -610,6 +618,42 @@ __global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams
         my_bytes += __shfl_xor_sync(0xFFFFFFFFu, my_bytes, o);
     }
     if ((threadIdx.x & 31) == 0 && my_pairs) { atomicAdd(&ctr->pairs_tier2, my_pairs); atomicAdd(&ctr->t2_alg_bytes, my_bytes); }
+}
+
+// After round 1: an accepted edge (a,b) of a gave-up b is b's tree edge iff a is the minimum
+// (parent[b] == a): move it to the phase-A slot.  Runs before the pointer doubling.
+__global__ void k_forced_resolve(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *k_to_s, uint32_t k_base,
+                                 const uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val) {
+    unsigned long long n = ctr->n_accept;
+    if (n > cap) n = cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        ejoin_raw_edge_t e = acc[i];
+        const uint32_t sa = k_to_s[e.k1 - k_base], sb = k_to_s[e.k2 - k_base];
+        if (parent[sb] == sa) {
+            f0_key[sb] = ((unsigned long long)e.k1 << 32) | e.k2;
+            f0_val[sb] = ((unsigned long long)e.flags << 32) | ((unsigned long long)e.d << 16) | e.cd;
+            acc[i].k1 = 0xFFFFFFFFu;                       // dead: now a tree edge
+        }
+    }
+}
+// Between the rounds: remember where round 1 ended and empty the todo list.
+__global__ void k_round2_begin(DevCounters *ctr) {
+    ctr->n_accept_r1 = ctr->n_accept;
+    ctr->n_generic_r1 = ctr->n_generic_q;
+    ctr->n_todo_r1 = ctr->n_todo;
+    ctr->n_todo = 0;
+}
+// After the pointer doubling: the remaining round-1 edges inside one tree are the heaviest edge of
+// a cycle and are dropped.
+__global__ void k_forced_prune(ejoin_raw_edge_t *acc, const DevCounters *ctr, unsigned long long cap, const uint32_t *k_to_s,
+                               uint32_t k_base, const uint32_t *root) {
+    unsigned long long n_round1 = ctr->n_accept_r1;
+    if (n_round1 > cap) n_round1 = cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round1; i += (unsigned long long)gridDim.x * blockDim.x) {
+        ejoin_raw_edge_t e = acc[i];
+        if (e.k1 == 0xFFFFFFFFu) continue;
+        if (root[k_to_s[e.k1 - k_base]] == root[k_to_s[e.k2 - k_base]]) acc[i].k1 = 0xFFFFFFFFu;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -682,12 +726,14 @@ __device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const Entr
 
 // K6  tier 2, bytewise: one warp per queued pair (already past the CDR3 and meta gates).
 __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *generic_q,
-                                                       unsigned long long cap, ejoin_raw_edge_t *acc, uint32_t k_base) {
+                                                       unsigned long long cap, ejoin_raw_edge_t *acc, uint32_t k_base, uint32_t *parent_min,
+                                                       int round2) {
     uint32_t *minnbr = nullptr;
+    const unsigned long long q_begin = round2 ? ctr->n_generic_r1 : 0ull;
     unsigned long long nq = ctr->n_generic_q;
     if (nq > cap) nq = cap;
     const uint32_t lane = threadIdx.x & 31;
-    for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq;
+    for (unsigned long long i = q_begin + (((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < nq;
          i += ((unsigned long long)gridDim.x * blockDim.x) >> 5) {
         const uint2 c = generic_q[i];
         const EntryMeta m1 = tb.meta[c.x], m2 = tb.meta[c.y];      // already ordered k1 < k2
@@ -707,7 +753,10 @@ __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, D
                 err = !(m1.donor_lo == m1.donor_hi && m2.donor_lo == m2.donor_hi && m1.donor_lo == m2.donor_lo);
             reason = decide(pr, tb, m1, m2, pc, ctr, &kk, &d, &p1, &mult, &score);
         }
-        if (lane == 0) emit_raw(pr, ctr, acc, cap, minnbr, m1.k + k_base, m2.k + k_base, pc.cd0 + pc.cd1, d, reason, err, reason != 0);
+        if (lane == 0) {
+            if (reason != 0 && parent_min) atomicMin(&parent_min[c.y], c.x);
+            emit_raw(pr, ctr, acc, cap, minnbr, m1.k + k_base, m2.k + k_base, pc.cd0 + pc.cd1, d, reason, err, reason != 0);
+        }
     }
 }
 
@@ -761,9 +810,10 @@ __global__ void __launch_bounds__(256) k_collect(const unsigned long long *f0_ke
             mine += f0_key[i] != ~0ull;
         } else {
             ejoin_raw_edge_t e = acc[i - n];
-            keys[i] = ((unsigned long long)e.k1 << 32) | e.k2;
+            const bool dead = e.k1 == 0xFFFFFFFFu;
+            keys[i] = dead ? ~0ull : (((unsigned long long)e.k1 << 32) | e.k2);
             vals[i] = ((unsigned long long)e.flags << 32) | ((unsigned long long)e.d << 16) | e.cd;
-            mine++;
+            mine += !dead;
         }
     }
     typedef cub::BlockReduce<unsigned long long, 256> BR;
@@ -1092,4 +1142,110 @@ __global__ void __launch_bounds__(256) k_uf_flatten(uint32_t *label, uint32_t n,
     __shared__ typename BR::TempStorage tmp;
     unsigned long long s = BR(tmp).Sum(isroot);
     if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_classes, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finishing the forest on the device (single GPU / contiguous shards).  The phase-A trees are
+// certified forest edges; the accepted cross-tree edges from phase B are reduced to the forest
+// edges among them by Boruvka rounds over the contracted trees: every component takes the
+// lightest (smallest (k1,k2)) edge leaving it — such an edge is in the unique minimum spanning
+// forest (cut property) — and the components are merged; repeat until no edge leaves a component.
+// `parent` (after the pointer doubling every entry points at its tree root) is the union-find.
+// ---------------------------------------------------------------------------------------------
+#define ACC_DEAD 0xFFFFFFFFu
+#define ACC_SELECTED 0x40000000u     // in ejoin_raw_edge_t.flags
+
+__global__ void k_fill_u64(unsigned long long *p, unsigned long long v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_bor_min(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *k_to_s, uint32_t k_base,
+                          uint32_t *parent, unsigned long long *best, uint2 *ends) {
+    unsigned long long n = ctr->n_accept;
+    if (n > cap) n = cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const ejoin_raw_edge_t e = acc[i];
+        if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
+        const uint32_t ca = uf_find(parent, k_to_s[e.k1 - k_base]), cb = uf_find(parent, k_to_s[e.k2 - k_base]);
+        if (ca == cb) { acc[i].k1 = ACC_DEAD; continue; }       // both ends in one component: heaviest edge of a cycle
+        const unsigned long long key = ((unsigned long long)e.k1 << 32) | e.k2;
+        atomicMin(&best[ca], key);
+        atomicMin(&best[cb], key);
+        ends[i] = make_uint2(ca, cb);
+        ctr->bor_active = 1;
+    }
+}
+__global__ void k_bor_select(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, uint32_t *parent,
+                             const unsigned long long *best, const uint2 *ends) {
+    unsigned long long n = ctr->n_accept;
+    if (n > cap) n = cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const ejoin_raw_edge_t e = acc[i];
+        if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
+        const uint2 c = ends[i];
+        const unsigned long long key = ((unsigned long long)e.k1 << 32) | e.k2;
+        if (best[c.x] == key || best[c.y] == key) {
+            acc[i].flags = e.flags | ACC_SELECTED;
+            uf_union(parent, c.x, c.y);
+        }
+    }
+}
+// reset `best` only where it was touched
+__global__ void k_bor_reset(const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, unsigned long long *best, const uint2 *ends) {
+    unsigned long long n = ctr->n_accept;
+    if (n > cap) n = cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const ejoin_raw_edge_t e = acc[i];
+        if (e.k1 == ACC_DEAD) continue;
+        const uint2 c = ends[i];
+        best[c.x] = ~0ull; best[c.y] = ~0ull;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->bor_active = 0;
+}
+__global__ void k_comp_size(uint32_t *parent, uint32_t n_valid, uint32_t *size) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_valid) atomicAdd(&size[uf_find(parent, s)], 1u);
+}
+// Final edge list: tree edges + selected cross edges, minus the two-cell rule (help1.rs:349-353):
+// an orbit of exactly two entries whose exact subclonotypes total two cells keeps its join only if
+// EASY or cd <= d.
+__global__ void __launch_bounds__(256) k_final_collect(DevIn in, const unsigned long long *f0_key, const unsigned long long *f0_val, uint32_t n,
+                                                       const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap,
+                                                       const uint32_t *k_to_s, uint32_t k_base, uint32_t *parent, const uint32_t *size, int easy,
+                                                       unsigned long long *keys, unsigned long long *vals) {
+    unsigned long long nacc = ctr->n_accept;
+    if (nacc > cap) nacc = cap;
+    const unsigned long long total = (unsigned long long)n + nacc;
+    unsigned long long mine = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (i >= cap) break;
+        unsigned long long key = ~0ull, val = 0;
+        if (i < n) { key = f0_key[i]; val = f0_val[i]; }
+        else {
+            const ejoin_raw_edge_t e = acc[i - n];
+            if (e.k1 != ACC_DEAD && (e.flags & ACC_SELECTED)) {
+                key = ((unsigned long long)e.k1 << 32) | e.k2;
+                val = ((unsigned long long)(e.flags & ~ACC_SELECTED) << 32) | ((unsigned long long)e.d << 16) | e.cd;
+            }
+        }
+        if (key != ~0ull) {
+            const uint32_t k1 = (uint32_t)(key >> 32) - k_base, k2 = (uint32_t)key - k_base;
+            if (size[uf_find(parent, k_to_s[k1])] == 2) {
+                const uint32_t cells = in.ncells[in.exact_id[k1]] + in.ncells[in.exact_id[k2]];
+                const uint32_t cd = (uint32_t)(val & 0xFFFF), d = (uint32_t)((val >> 16) & 0xFFFF);
+                if (cells == 2 && !easy && !(cd <= d)) key = ~0ull;
+            }
+        }
+        keys[i] = key; vals[i] = val;
+        mine += key != ~0ull;
+    }
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    unsigned long long s = BR(tmp).Sum(mine);
+    if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_kept, s);
+}
+__global__ void k_keys_to_pairs(const unsigned long long *keys, uint32_t ne, uint2 *pairs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ne) pairs[i] = make_uint2((uint32_t)(keys[i] >> 32), (uint32_t)keys[i]);
 }
