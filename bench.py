@@ -207,7 +207,7 @@ def main():
             return j.run(sp.struct, copy=False)     # views into the library's pinned result buffer
         from enclone_b200.dist import sharded_join
         pairs, cls, st, fin = sharded_join(j, sp.struct, rank, world, device=dev)   # includes the NCCL all-gather of edges
-        fin.stats.update({k: v for k, v in st.items() if k in ("h2d_bytes", "ms_h2d", "d2h_bytes")})
+        fin.stats.update(st)
         fin.edges = pairs
         return fin
 

@@ -11,7 +11,7 @@ SO_PATH = os.path.join(_HERE, "libenclone_join.so")
 # every symbol include/enclone_join.h declares
 EXPORTS = [
     "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
-    "ejoin_plan_shards", "ejoin_run_shard", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_run_resident",
+    "ejoin_plan_shards", "ejoin_run_shard", "ejoin_run_shard_final", "ejoin_partition_gpu", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_run_resident",
     "ejoin_host_alloc", "ejoin_host_free", "ejoin_host_register", "ejoin_host_unregister", "ejoin_p1", "ejoin_partition",
 ]
 
@@ -48,6 +48,12 @@ def load():
     L.ejoin_run_shard.argtypes = [H, C.POINTER(EjoinPack), C.c_int, C.c_int, C.POINTER(C.POINTER(EjoinRawEdge)),
                                   C.POINTER(C.c_uint64), C.POINTER(EjoinStats)]
     L.ejoin_run_shard.restype = C.c_int
+    L.ejoin_run_shard_final.argtypes = [H, C.POINTER(EjoinPack), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(EjoinResult),
+                                        C.POINTER(C.POINTER(EjoinRawEdge)), C.POINTER(C.c_uint64), C.POINTER(EjoinStats)]
+    L.ejoin_run_shard_final.restype = C.c_int
+    L.ejoin_partition_gpu.argtypes = [H, C.POINTER(EjoinPack), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint64,
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.ejoin_partition_gpu.restype = C.c_int
     L.ejoin_raw_free.argtypes = [C.POINTER(EjoinRawEdge)]
     L.ejoin_finish.argtypes = [H, C.POINTER(EjoinPack), C.POINTER(EjoinRawEdge), C.c_uint64, C.POINTER(EjoinResult)]
     L.ejoin_finish.restype = C.c_int

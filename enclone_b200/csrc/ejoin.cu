@@ -80,6 +80,7 @@ struct ejoin_handle {
     bool uploaded = false;
     bool device_final = false;  // the last pipeline run produced the final emitted edge list on the device
     // tables (cached across runs)
+    DevBuf d_part;              // ejoin_partition_gpu scratch
     DevBuf d_counters, d_presL, d_presC, d_p1ptrs, d_multinfo, d_multpool, d_cdmax, d_p1scratch, d_Ls, d_tabptrs;
     std::vector<double *> p1_host_ptrs;            // [8192] device pointers (host copy)
     std::vector<MultInfo> multinfo_host;           // [65536]
@@ -226,7 +227,7 @@ extern "C" void ejoin_destroy(ejoin_handle_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
-    h->in_arena.buf.release(); h->work.buf.release();
+    h->in_arena.buf.release(); h->work.buf.release(); h->d_part.release();
     for (DevBuf *b : { &h->d_counters, &h->d_presL, &h->d_presC, &h->d_p1ptrs, &h->d_multinfo, &h->d_multpool, &h->d_cdmax, &h->d_p1scratch,
                        &h->d_Ls, &h->d_tabptrs })
         b->release();
@@ -725,7 +726,7 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
     DevCounters *ctr = (DevCounters *)h->d_counters.p;
     const double t_dev0 = now_ms();
     if (ne) {
-        if (d_keys) k_keys_to_pairs<<<(unsigned)((ne + 255) / 256), 256, 0, h->st>>>(d_keys, (uint32_t)ne, d_pairs);
+        if (d_keys) k_keys_to_pairs<<<(unsigned)((ne + 255) / 256), 256, 0, h->st>>>(d_keys, (uint32_t)ne, h->k_base, d_pairs);
         else CK(cudaMemcpyAsync(d_pairs, pairs.data(), ne * sizeof(uint2), cudaMemcpyHostToDevice, h->st));
         DevTables tbs;
         tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
@@ -855,10 +856,10 @@ extern "C" int ejoin_plan_shards(const ejoin_pack_t *pk, int world, uint32_t *ow
     return 0;
 }
 
-extern "C" int ejoin_run_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int rank, int world, ejoin_raw_edge_t **edges, uint64_t *n_edges,
-                               ejoin_stats_t *stats) {
-    if (!h || !pk || !edges || !n_edges || rank < 0 || rank >= world) return EJOIN_E_ARG;
-    *edges = nullptr; *n_edges = 0;
+static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int world, int want_final, int *mode_out, ejoin_result_t *final,
+                          ejoin_raw_edge_t **edges, uint64_t *n_edges, ejoin_stats_t *stats) {
+    if (edges) *edges = nullptr;
+    if (n_edges) *n_edges = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     h->launches = 0;
     const double t0 = now_ms();
@@ -867,10 +868,11 @@ extern "C" int ejoin_run_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int ra
     std::vector<uint32_t> owner(nb + 1), bstart(nb + 2);
     ejoin_plan_shards(pk, world, owner.data(), bstart.data(), nb, &nb);
     // giant-bucket case: if one bucket holds most of the work, every rank takes all entries and
-    // an interleaved share of the tier-1 tiles instead (stride mode)
+    // an interleaved share of the tile rows instead (stride mode)
     double total = 0, biggest = 0;
     for (uint32_t b = 0; b < nb; b++) { double m = bstart[b + 1] - bstart[b]; double c = m * (m - 1) / 2; total += c; biggest = std::max(biggest, c); }
     const bool stride_mode = world > 1 && biggest > 1.25 * total / world;
+    if (mode_out) *mode_out = stride_mode ? 1 : 0;
     uint32_t lo = 0, hi = pk->n_info;
     if (!stride_mode && world > 1) {
         lo = hi = 0;
@@ -887,28 +889,54 @@ extern "C" int ejoin_run_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int ra
     if (rc) return rc;
     const double t2 = now_ms();
     const size_t nk = (size_t)h->counters.n_kept;
-    rc = ensure_pin(h, 16 * nk + 64);
-    if (rc) return rc;
-    unsigned long long *hk = (unsigned long long *)h->pin, *hv = hk + nk;
-    if (nk) {
-        CK(cudaMemcpyAsync(hk, h->kept_keys, 8 * nk, cudaMemcpyDeviceToHost, h->st));
-        CK(cudaMemcpyAsync(hv, h->kept_vals, 8 * nk, cudaMemcpyDeviceToHost, h->st));
-        CK(cudaStreamSynchronize(h->st));
+    size_t d2h = sizeof(DevCounters);
+    if (want_final && !stride_mode) {
+        // the shard's buckets are complete on this device: emitted joins with payload, no host replay
+        rc = ensure_pin(h, sizeof(ejoin_edge_t) * (nk + 1) + 4 * ((size_t)h->n + 1) + 1024);
+        if (rc) return rc;
+        static const std::vector<uint2> none;
+        rc = emit_result(h, pk, none, h->kept_keys, nk, 0, final);
+        if (rc) return rc;
+        d2h += h->stats.d2h_bytes;
+    } else {
+        rc = ensure_pin(h, 16 * nk + 64);
+        if (rc) return rc;
+        unsigned long long *hk = (unsigned long long *)h->pin, *hv = hk + nk;
+        if (nk) {
+            CK(cudaMemcpyAsync(hk, h->kept_keys, 8 * nk, cudaMemcpyDeviceToHost, h->st));
+            CK(cudaMemcpyAsync(hv, h->kept_vals, 8 * nk, cudaMemcpyDeviceToHost, h->st));
+            CK(cudaStreamSynchronize(h->st));
+        }
+        ejoin_raw_edge_t *e = (ejoin_raw_edge_t *)malloc(sizeof(ejoin_raw_edge_t) * (nk ? nk : 1));
+        for (size_t i = 0; i < nk; i++) {
+            e[i].k1 = (uint32_t)(hk[i] >> 32) + lo; e[i].k2 = (uint32_t)hk[i] + lo;
+            e[i].cd = (uint16_t)(hv[i] & 0xFFFF); e[i].d = (uint16_t)((hv[i] >> 16) & 0xFFFF); e[i].flags = (uint32_t)(hv[i] >> 32);
+        }
+        if (edges) *edges = e; else free(e);
+        if (n_edges) *n_edges = nk;
+        d2h += 16 * nk;
     }
-    ejoin_raw_edge_t *e = (ejoin_raw_edge_t *)malloc(sizeof(ejoin_raw_edge_t) * (nk ? nk : 1));
-    for (size_t i = 0; i < nk; i++) {
-        e[i].k1 = (uint32_t)(hk[i] >> 32) + lo; e[i].k2 = (uint32_t)hk[i] + lo;
-        e[i].cd = (uint16_t)(hv[i] & 0xFFFF); e[i].d = (uint16_t)((hv[i] >> 16) & 0xFFFF); e[i].flags = (uint32_t)(hv[i] >> 32);
-    }
-    *edges = e; *n_edges = nk;
     const double t3 = now_ms();
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         fill_stats(h, stats);
-        stats->ms_h2d = t1 - t0; stats->ms_d2h = t3 - t2; stats->ms_total = t3 - t0; stats->d2h_bytes = 16 * nk + sizeof(DevCounters);
+        stats->ms_h2d = t1 - t0; stats->ms_d2h = 0; stats->ms_host_post = t3 - t2; stats->ms_total = t3 - t0; stats->d2h_bytes = d2h;
         stats->gpu_launches = h->launches;
     }
     return 0;
+}
+
+extern "C" int ejoin_run_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int rank, int world, ejoin_raw_edge_t **edges, uint64_t *n_edges,
+                               ejoin_stats_t *stats) {
+    if (!h || !pk || !edges || !n_edges || rank < 0 || rank >= world) return EJOIN_E_ARG;
+    return run_shard_core(h, pk, rank, world, 0, nullptr, nullptr, edges, n_edges, stats);
+}
+
+extern "C" int ejoin_run_shard_final(ejoin_handle_t *h, const ejoin_pack_t *pk, int rank, int world, int *mode, ejoin_result_t *final,
+                                     ejoin_raw_edge_t **raw, uint64_t *n_raw, ejoin_stats_t *stats) {
+    if (!h || !pk || !mode || !final || !raw || !n_raw || rank < 0 || rank >= world) return EJOIN_E_ARG;
+    memset(final, 0, sizeof(*final));
+    return run_shard_core(h, pk, rank, world, 1, mode, final, raw, n_raw, stats);
 }
 
 extern "C" void ejoin_raw_free(ejoin_raw_edge_t *e) { free(e); }
@@ -942,5 +970,42 @@ extern "C" int ejoin_partition(const ejoin_pack_t *pk, const uint32_t *k1, const
     if (!pk || !class_of || (ne && (!k1 || !k2))) return EJOIN_E_ARG;
     for (uint64_t i = 0; i < ne; i++) if (k1[i] >= pk->n_info || k2[i] >= pk->n_info) return EJOIN_E_ARG;
     host_partition(pk, k1, k2, ne, class_of, n_classes);
+    return EJOIN_OK;
+}
+
+extern "C" int ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pk, const uint32_t *k1, const uint32_t *k2, uint64_t ne, uint32_t *class_of,
+                                   uint32_t *n_classes) {
+    if (!h || !pk || !class_of || (ne && (!k1 || !k2))) return EJOIN_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const uint32_t n = pk->n_info, nx = pk->n_exact;
+    if (n == 0) { if (n_classes) *n_classes = 0; return EJOIN_OK; }
+    // its own small buffer: the work arena may hold a resident shard
+    CK(h->d_part.ensure(4 * (size_t)n * 2 + 4 * (size_t)std::max(1u, nx) + 8 * (ne + 1) + 1024));
+    char *base = (char *)h->d_part.p;
+    uint32_t *d_exact = (uint32_t *)base; base += 4 * (size_t)n;
+    uint32_t *d_label = (uint32_t *)base; base += 4 * (size_t)n;
+    uint32_t *d_first = (uint32_t *)base; base += 4 * (size_t)std::max(1u, nx);
+    base = (char *)(((uintptr_t)base + 15) & ~(uintptr_t)15);
+    uint2 *d_pairs = (uint2 *)base;
+    int rc = ensure_pin(h, 8 * (ne + 1) + 4 * (size_t)n + 1024);
+    if (rc) return rc;
+    uint2 *hp = (uint2 *)h->pin;
+    for (uint64_t i = 0; i < ne; i++) { if (k1[i] >= n || k2[i] >= n) return fail(h, EJOIN_E_ARG, "edge endpoint out of range"); hp[i] = make_uint2(k1[i], k2[i]); }
+    uint32_t *hl = (uint32_t *)((char *)h->pin + ((8 * (ne + 1) + 255) & ~(size_t)255));
+    DevCounters *ctr = (DevCounters *)h->d_counters.p;
+    CK(cudaMemcpyAsync(d_exact, pk->exact_id, 4 * (size_t)n, cudaMemcpyHostToDevice, h->st));
+    if (ne) CK(cudaMemcpyAsync(d_pairs, hp, 8 * ne, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemsetAsync(&ctr->n_classes, 0, sizeof(unsigned long long), h->st));
+    k_uf_init<<<(std::max(n, nx) + 255) / 256, 256, 0, h->st>>>(d_label, n, d_first, nx);
+    k_uf_first<<<(n + 255) / 256, 256, 0, h->st>>>(d_exact, n, nx, d_first);
+    k_uf_union<<<(std::max<uint32_t>(n, (uint32_t)ne) + 255) / 256, 256, 0, h->st>>>(d_label, d_pairs, (uint32_t)ne, 0, d_exact, n, nx, d_first);
+    k_uf_flatten<<<(n + 255) / 256, 256, 0, h->st>>>(d_label, n, ctr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hl, d_label, 4 * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+    unsigned long long ncls = 0;
+    CK(cudaMemcpyAsync(&ncls, &ctr->n_classes, sizeof(ncls), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    memcpy(class_of, hl, 4 * (size_t)n);
+    if (n_classes) *n_classes = (uint32_t)ncls;
     return EJOIN_OK;
 }

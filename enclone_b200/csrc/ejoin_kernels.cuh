@@ -1245,7 +1245,7 @@ __global__ void __launch_bounds__(256) k_final_collect(DevIn in, const unsigned 
     unsigned long long s = BR(tmp).Sum(mine);
     if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_kept, s);
 }
-__global__ void k_keys_to_pairs(const unsigned long long *keys, uint32_t ne, uint2 *pairs) {
+__global__ void k_keys_to_pairs(const unsigned long long *keys, uint32_t ne, uint32_t k_base, uint2 *pairs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ne) pairs[i] = make_uint2((uint32_t)(keys[i] >> 32), (uint32_t)keys[i]);
+    if (i < ne) pairs[i] = make_uint2((uint32_t)(keys[i] >> 32) + k_base, (uint32_t)keys[i] + k_base);   // local -> info indices
 }

@@ -75,12 +75,37 @@ def merge_rank_edges(pack_struct, my_pairs, device=None, group=None):
     return allp, cls, ncls
 
 
-def sharded_join(joiner, pack_struct, rank, world, device=None, group=None):
-    """The whole join stage on `world` GPUs.  Returns (raw_joins [m,2] for the whole input,
-    class_of, this rank's shard stats, this rank's JoinResult)."""
+def all_gather_pairs(pairs, device=None, group=None):
+    """All-gather of per-rank (k1,k2) uint32 lists as one byte tensor per rank (two collectives:
+    sizes, then the padded payload)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    t = torch.from_numpy(pairs.view(np.uint8).reshape(-1))
+    if device is not None:
+        t = t.to(device, non_blocking=True)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = torch.zeros(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = sizes.cpu().tolist()
+    mx = max(max(sizes), 8)
+    buf = torch.zeros(mx, dtype=torch.uint8, device=t.device)
+    buf[:t.numel()] = t
+    out = torch.empty(world * mx, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    host = out.cpu().numpy()
+    parts = [host[r * mx:r * mx + s].view(np.uint32).reshape(-1, 2) for r, s in enumerate(sizes)]
+    return np.concatenate(parts) if parts else np.zeros((0, 2), np.uint32)
+
+
+def sharded_join(joiner, pack_struct, rank, world, device=None, group=None, gpu_partition=True):
+    """The whole join stage on `world` GPUs, one call per rank.  Returns (raw_joins [m,2] for the
+    whole input in the reference's order, class_of, this rank's shard stats, this rank's JoinResult)."""
     from ._abi import RAW_EDGE_DTYPE
-    raw, st = joiner.run_shard(pack_struct, rank, world)
-    if stride_mode(pack_struct, world):
+    mode, fin, raw, st = joiner.run_shard_final(pack_struct, rank, world, copy=False)
+    if mode == 1:
+        # a giant bucket is shared between ranks: gather the accepted edges, replay once
         rows = np.stack([raw["k1"], raw["k2"], raw["cd"].astype(np.uint32) | (raw["d"].astype(np.uint32) << 16), raw["flags"]], axis=1) \
             if len(raw) else np.zeros((0, 4), np.uint32)
         allrows = all_gather_rows(rows, device=device, group=group)
@@ -91,7 +116,11 @@ def sharded_join(joiner, pack_struct, rank, world, device=None, group=None):
         fin = joiner.finish(pack_struct, allraw)
         pairs = np.stack([fin.edges["k1"], fin.edges["k2"]], axis=1) if len(fin.edges) else np.zeros((0, 2), np.uint32)
         return pairs, fin.class_of, st, fin
-    fin = joiner.finish(pack_struct, raw)
+    # contiguous bucket ranges: ranks are in bucket order, so concatenating in rank order IS raw_joins order
     mine = np.stack([fin.edges["k1"], fin.edges["k2"]], axis=1) if len(fin.edges) else np.zeros((0, 2), np.uint32)
-    allp, cls, _ = merge_rank_edges(pack_struct, mine, device=device, group=group)
+    allp = all_gather_pairs(mine, device=device, group=group)
+    if gpu_partition:
+        cls, _ = joiner.partition(pack_struct, allp[:, 0], allp[:, 1])
+    else:
+        cls, _ = partition(pack_struct, allp[:, 0], allp[:, 1])
     return allp, cls, st, fin

@@ -133,6 +133,30 @@ class Joiner:
         self.L.ejoin_raw_free(ep)
         return raw, st.as_dict()
 
+    def run_shard_final(self, pack_struct, rank, world, copy=True):
+        """One call per rank.  Returns (mode, JoinResult or None, raw edges or None, stats): mode 0 =
+        contiguous bucket ranges (the result holds this rank's emitted joins), mode 1 = stride mode
+        (raw accepted edges for the gather + finish)."""
+        mode, res, ep, n, st = C.c_int(), EjoinResult(), C.POINTER(EjoinRawEdge)(), C.c_uint64(), EjoinStats()
+        self._check(self.L.ejoin_run_shard_final(self.h, C.byref(pack_struct), rank, world, C.byref(mode), C.byref(res), C.byref(ep),
+                                                 C.byref(n), C.byref(st)))
+        if mode.value == 0:
+            return 0, self._result(res, copy), None, st.as_dict()
+        raw = _edges_np(ep, n.value, RAW_EDGE_DTYPE, EjoinRawEdge)
+        self.L.ejoin_raw_free(ep)
+        return 1, None, raw, st.as_dict()
+
+    def partition(self, pack_struct, k1, k2):
+        """finish_join on this handle's GPU (ejoin_partition_gpu): min-member labels over all info entries."""
+        k1 = np.ascontiguousarray(k1, dtype=np.uint32)
+        k2 = np.ascontiguousarray(k2, dtype=np.uint32)
+        cls = np.zeros(max(int(pack_struct.n_info), 1), np.uint32)
+        ncls = C.c_uint32()
+        p = C.POINTER(C.c_uint32)
+        self._check(self.L.ejoin_partition_gpu(self.h, C.byref(pack_struct), k1.ctypes.data_as(p), k2.ctypes.data_as(p), len(k1),
+                                               cls.ctypes.data_as(p), C.byref(ncls)))
+        return cls[:int(pack_struct.n_info)], int(ncls.value)
+
     def finish(self, pack_struct, raw_edges):
         raw = np.ascontiguousarray(raw_edges, dtype=RAW_EDGE_DTYPE)
         res = EjoinResult()

@@ -200,6 +200,12 @@ int  ejoin_plan_shards(const ejoin_pack_t *pack, int world_size, uint32_t *bucke
 int  ejoin_run_shard(ejoin_handle_t *h, const ejoin_pack_t *pack, int rank, int world_size,
                      ejoin_raw_edge_t **edges, uint64_t *n_edges, ejoin_stats_t *stats);
 void ejoin_raw_free(ejoin_raw_edge_t *edges);
+/* Same decomposition, one call per rank.  *mode = 0 (contiguous bucket ranges: the rank's buckets are
+ * independent of the others, so `final` receives their emitted joins with full payload, class_of NULL,
+ * and no raw edges are returned) or 1 (stride mode, a giant bucket is shared: `raw` receives the
+ * accepted edges for the gather + ejoin_finish, `final` stays empty). */
+int  ejoin_run_shard_final(ejoin_handle_t *h, const ejoin_pack_t *pack, int rank, int world_size, int *mode,
+                           ejoin_result_t *final, ejoin_raw_edge_t **raw, uint64_t *n_raw, ejoin_stats_t *stats);
 int  ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pack, const ejoin_raw_edge_t *edges,
                   uint64_t n_edges, ejoin_result_t *out);
 
@@ -208,6 +214,10 @@ int  ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pack, const ejoin_raw_e
  * the gather; needs no GPU and no handle. */
 int  ejoin_partition(const ejoin_pack_t *pack, const uint32_t *k1, const uint32_t *k2, uint64_t n_edges,
                      uint32_t *class_of /* [n_info] */, uint32_t *n_classes);
+
+/* The same on the handle's GPU (uploads exact_id and the edge list: ~9 bytes per info entry). */
+int  ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pack, const uint32_t *k1, const uint32_t *k2, uint64_t n_edges,
+                         uint32_t *class_of /* [n_info] */, uint32_t *n_classes);
 
 /* Device-resident variant used to time the device side alone: upload once, then
  * ejoin_run_resident() repeats pack+score+compact+union-find on the resident input. */

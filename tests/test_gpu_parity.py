@@ -144,6 +144,25 @@ def test_sharded_run_equals_single():
         assert np.array_equal(cls, single.class_of) and ncls == len(np.unique(single.class_of))
 
 
+def test_shard_final_and_gpu_partition():
+    pack, _ = synth.generate(n_cells=12000, n_donors=2, seed=31)
+    single = join_exacts(pack)
+    world = 3
+    parts = []
+    for rank in range(world):
+        j = Joiner(default_params())
+        mode, fin, raw, st = j.run_shard_final(pack.struct, rank, world)
+        assert mode == 0 and raw is None
+        parts.append(fin.edges)
+        j.close()
+    edges = np.concatenate(parts)                     # rank order == bucket order == raw_joins order
+    assert np.array_equal(edges, single.edges)
+    j = Joiner(default_params())
+    cls, ncls = j.partition(pack.struct, edges["k1"], edges["k2"])
+    assert np.array_equal(cls, single.class_of) and ncls == len(np.unique(single.class_of))
+    j.close()
+
+
 def test_stride_mode_giant_bucket():
     pack, _ = synth.generate_config("C4", 0.01)
     single = join_exacts(pack)
