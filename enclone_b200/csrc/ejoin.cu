@@ -65,8 +65,13 @@ struct ejoin_handle {
     int device = 0;
     ejoin_params_t params;
     std::string err;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;
     cudaEvent_t ev[8] = {};
+    // overlapped upload: small arrays first, then the tig arena in chunks, each with an event
+    cudaEvent_t ev_copy0 = nullptr, ev_small = nullptr, ev_chunk[8] = {};
+    int n_chunks = 0;
+    uint64_t chunk_end[8] = {};     // arena byte offset (caller coordinates) up to which chunk i has landed
+    bool copy_pending = false;
     int is_bcr = 1;
     int tables_is_bcr = -1;
     int sm_count = 148;
@@ -208,7 +213,11 @@ extern "C" int ejoin_create(ejoin_handle_t **out, const ejoin_params_t *p, int d
     CK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
     for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    CK(cudaEventCreate(&h->ev_copy0)); CK(cudaEventCreate(&h->ev_small));
+    for (auto &e : h->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventDestroy(h->ev_chunk[7])); CK(cudaEventCreate(&h->ev_chunk[7]));
     CK(h->d_counters.ensure(sizeof(DevCounters)));
     CK(h->d_presL.ensure(8192 / 8));
     CK(h->d_presC.ensure(65536 / 8));
@@ -234,6 +243,10 @@ extern "C" void ejoin_destroy(ejoin_handle_t *h) {
     for (auto &t : h->p1_tables) t.release();
     if (h->pin) cudaFreeHost(h->pin);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : h->ev_chunk) if (e) cudaEventDestroy(e);
+    if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
+    if (h->ev_small) cudaEventDestroy(h->ev_small);
+    if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -293,7 +306,7 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     sz.take(4 * n1); for (int i = 0; i < 6; i++) sz.take(2 * n1);
     for (int i = 0; i < 4; i++) sz.take(4 * (size_t)std::max(1u, pk->n_exact));
     sz.take(8 * (size_t)std::max(1u, pk->n_refseq)); sz.take(4 * (size_t)std::max(1u, pk->n_refseq));
-    sz.take(thi - tlo + 64); sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64);
+    sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 256);
     CK(h->in_arena.buf.ensure(sz.off + 4096));
     h->in_arena.reset();
     Arena &A = h->in_arena;
@@ -307,8 +320,11 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
         dst = p;
         if (!count) return cudaSuccess;
         bytes += count * sizeof(T);
-        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->st);
+        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->st_copy);
     };
+    // the copy stream must not run ahead of the previous run's kernels that still read the old input
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaEventRecord(h->ev_copy0, h->st_copy));
     CK(up(d.exact_id, pk->exact_id + lo, n));
     for (int c = 0; c < 2; c++) {
         CK(up(d.len[c], pk->len[c] + lo, n));
@@ -333,9 +349,27 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     CK(up(d.nchains, pk->nchains, pk->n_exact)); CK(up(d.ncells, pk->ncells, pk->n_exact));
     CK(up(d.donor_lo, pk->donor_lo, pk->n_exact)); CK(up(d.donor_hi, pk->donor_hi, pk->n_exact));
     CK(up(d.refseq_off, pk->refseq_off, pk->n_refseq)); CK(up(d.refseq_len, pk->refseq_len, pk->n_refseq));
-    CK(up(d.tig_arena, pk->tig_arena + tlo, thi - tlo));
     CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
     CK(up(d.refseq_arena, pk->refseq_arena, pk->refseq_arena_bytes));
+    CK(cudaEventRecord(h->ev_small, h->st_copy));       // everything but the V..J bytes: keys / sort / groups / meta / c3 can start
+    {
+        // the V..J arena (3/4 of the bytes) goes up in chunks; k_pack_t2 packs each chunk's entries as it lands
+        const uint64_t tb = thi - tlo;
+        uint8_t *dst = A.take<uint8_t>(tb + 64);
+        d.tig_arena = dst;
+        const int nch = tb >= (32ull << 20) ? 8 : 1;
+        h->n_chunks = nch;
+        uint64_t done = 0;
+        for (int i = 0; i < nch; i++) {
+            uint64_t end = i == nch - 1 ? tb : ((tb * (uint64_t)(i + 1) / nch) & ~(uint64_t)4095);
+            if (end > done) CK(cudaMemcpyAsync(dst + done, pk->tig_arena + tlo + done, end - done, cudaMemcpyHostToDevice, h->st_copy));
+            done = end;
+            h->chunk_end[i] = tlo + end;
+            CK(cudaEventRecord(h->ev_chunk[i == nch - 1 ? 7 : i], h->st_copy));
+        }
+        bytes += tb;
+        h->copy_pending = true;
+    }
     // the offsets index the original arenas: rebase the device pointers instead of the offsets
     d.tig_arena -= tlo; d.cdr3_arena -= clo;
     h->n = n; h->k_base = lo; h->tig_bytes = thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
@@ -484,6 +518,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         const unsigned nb256 = (n + 255) / 256;
         cudaStream_t st = h->st;
 
+        if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));
         CK(cudaEventRecord(h->ev[0], st));
         CK(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), st));
         CK(cudaMemsetAsync(h->d_presL.p, 0, 8192 / 8, st));
@@ -513,7 +548,18 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         CK(cudaEventRecord(h->ev[1], st));
         k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, pr.ref_v_trim, pr.ref_j_trim);
         k_pack_c3<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, meta, ctr, c3);
-        k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2);
+        if (h->copy_pending) {
+            // pack each chunk's entries as its bytes land (an entry belongs to the chunk that completes it)
+            uint64_t prev = 0;
+            for (int i = 0; i < h->n_chunks; i++) {
+                CK(cudaStreamWaitEvent(st, h->ev_chunk[i == h->n_chunks - 1 ? 7 : i], 0));
+                k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, prev, h->chunk_end[i]);
+                prev = h->chunk_end[i];
+            }
+            h->launches += h->n_chunks - 1;
+        } else {
+            k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, 0ull, ~0ull);
+        }
         h->launches += 2;
         k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, n);
         h->launches += 2;
@@ -602,6 +648,12 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cudaEventElapsedTime(&tot, h->ev[0], h->ev[5]);
         h->stats.ms_device = tot;
         h->stats.ms_kernel_other = tot - h->stats.ms_kernel_pack - h->stats.ms_kernel_tier1 - h->stats.ms_kernel_tier2;
+        if (h->copy_pending) {
+            float up = 0;
+            cudaEventElapsedTime(&up, h->ev_copy0, h->ev_chunk[7]);
+            h->stats.ms_h2d = up;                 // H2D on the copy stream, overlapped with the stages before the join
+            h->copy_pending = false;
+        }
         return 0;
     }
     return fail(h, EJOIN_E_NOMEM, "candidate buffer kept overflowing");
@@ -762,7 +814,8 @@ extern "C" int ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pk) {
     if (!h) return EJOIN_E_ARG;
     int rc = upload_range(h, pk, 0, pk ? pk->n_info : 0);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(h->st));
+    CK(cudaStreamSynchronize(h->st_copy));
+    h->copy_pending = false;
     h->is_bcr = (int)pk->is_bcr;
     return 0;
 }
@@ -797,8 +850,7 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     int rc = upload_range(h, pk, 0, pk ? pk->n_info : 0);
     if (rc) return rc;
     h->is_bcr = (int)pk->is_bcr;
-    CK(cudaStreamSynchronize(h->st));
-    const double t1 = now_ms();
+    const double t1 = now_ms();                 // copies are in flight on the copy stream; the pipeline waits on their events
     rc = device_pipeline(h, (int)pk->is_bcr, 1, 0);
     if (rc) return rc;
     const double t2 = now_ms();
@@ -814,7 +866,8 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     }
     const double t4 = now_ms();
     fill_stats(h, &out->stats);
-    out->stats.ms_h2d = t1 - t0; out->stats.ms_d2h = t3 - t2; out->stats.ms_host_post = t4 - t3; out->stats.ms_total = t4 - t0;
+    (void)t1;
+    out->stats.ms_h2d = h->stats.ms_h2d; out->stats.ms_d2h = t3 - t2; out->stats.ms_host_post = t4 - t3; out->stats.ms_total = t4 - t0;
     out->stats.d2h_bytes = h->stats.d2h_bytes;
     out->stats.gpu_launches = h->launches;
     return 0;
@@ -883,7 +936,6 @@ static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int
     int rc = upload_range(h, pk, lo, hi);
     if (rc) return rc;
     h->is_bcr = (int)pk->is_bcr;
-    CK(cudaStreamSynchronize(h->st));
     const double t1 = now_ms();
     rc = device_pipeline(h, (int)pk->is_bcr, stride_mode ? (uint32_t)world : 1u, stride_mode ? (uint32_t)rank : 0u);
     if (rc) return rc;
@@ -920,7 +972,8 @@ static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         fill_stats(h, stats);
-        stats->ms_h2d = t1 - t0; stats->ms_d2h = 0; stats->ms_host_post = t3 - t2; stats->ms_total = t3 - t0; stats->d2h_bytes = d2h;
+        (void)t1;
+        stats->ms_h2d = h->stats.ms_h2d; stats->ms_d2h = 0; stats->ms_host_post = t3 - t2; stats->ms_total = t3 - t0; stats->d2h_bytes = d2h;
         stats->gpu_launches = h->launches;
     }
     return 0;

@@ -291,13 +291,21 @@ __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__re
     c3[m.c3off + W + w] = L;
 }
 
-__global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2) {
+// [wm_lo, wm_hi): only the entries whose last V..J byte lies in this range of the caller's arena are
+// packed by this launch (the arena is uploaded in chunks; see upload_range).
+__global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
+                                                 unsigned long long wm_lo, unsigned long long wm_hi) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= (uint32_t)ctr->n_valid) return;
     const EntryMeta &m = meta[s];
     const uint32_t k = m.k;
     const int n0 = m.len[0], n1 = m.len[1];
+    {
+        const unsigned long long e0 = in.tig_off[0][k] + (unsigned long long)n0, e1 = in.tig_off[1][k] + (unsigned long long)n1;
+        const unsigned long long last = e0 > e1 ? e0 : e1;
+        if (!(last > wm_lo && last <= wm_hi)) return;
+    }
     const int nw0 = 4 * ((n0 + 127) / 128), nw = nw0 + 4 * ((n1 + 127) / 128);
     uint32_t *rows = (uint32_t *)(t2 + m.t2off);
     int mcount0 = 0, mcount1 = 0;
