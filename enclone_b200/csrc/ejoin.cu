@@ -489,7 +489,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(8 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                   // Boruvka: best, ends, component sizes
         sz.take(cub_bytes + 256);
         sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1));                   // payload staging (taken later)
-        sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)h->din.n_exact + 64);                              // union-find labels, first entry per exact
+        sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)h->din.n_exact + 64);   // union-find labels (in, out), first entry per exact
         CK(h->work.buf.ensure(sz.off + 4096));
         h->work.reset();
         Arena &A = h->work;
@@ -772,7 +772,7 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
     const size_t save = A.off;
     uint2 *d_pairs = A.take<uint2>(ne ? ne : 1);
     ejoin_edge_t *d_out = A.take<ejoin_edge_t>(ne ? ne : 1);
-    uint32_t *d_label = A.take<uint32_t>(n ? n : 1);
+    uint32_t *d_label = A.take<uint32_t>(n ? n : 1), *d_label_out = A.take<uint32_t>(n ? n : 1);
     uint32_t *d_first = A.take<uint32_t>(pk->n_exact ? pk->n_exact : 1);
     if (A.off > A.buf.cap) { A.off = save; return fail(h, EJOIN_E_NOMEM, "work arena too small for the epilogue"); }
     DevCounters *ctr = (DevCounters *)h->d_counters.p;
@@ -794,10 +794,10 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
         k_uf_init<<<nbx, 256, 0, h->st>>>(d_label, n, d_first, pk->n_exact);
         k_uf_first<<<(n + 255) / 256, 256, 0, h->st>>>(h->din.exact_id, n, pk->n_exact, d_first);
         k_uf_union<<<nbn, 256, 0, h->st>>>(d_label, d_pairs, (uint32_t)ne, h->k_base, h->din.exact_id, n, pk->n_exact, d_first);
-        k_uf_flatten<<<(n + 255) / 256, 256, 0, h->st>>>(d_label, n, ctr);
+        k_uf_flatten<<<(n + 255) / 256, 256, 0, h->st>>>(d_label, n, ctr, d_label_out);
         h->launches += 4;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h_labels, d_label, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaMemcpyAsync(h_labels, d_label_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
         CK(cudaMemcpyAsync(&h->counters.n_classes, &ctr->n_classes, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
     }
     CK(cudaStreamSynchronize(h->st));
@@ -1033,10 +1033,11 @@ extern "C" int ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pk, co
     const uint32_t n = pk->n_info, nx = pk->n_exact;
     if (n == 0) { if (n_classes) *n_classes = 0; return EJOIN_OK; }
     // its own small buffer: the work arena may hold a resident shard
-    CK(h->d_part.ensure(4 * (size_t)n * 2 + 4 * (size_t)std::max(1u, nx) + 8 * (ne + 1) + 1024));
+    CK(h->d_part.ensure(4 * (size_t)n * 3 + 4 * (size_t)std::max(1u, nx) + 8 * (ne + 1) + 1024));
     char *base = (char *)h->d_part.p;
     uint32_t *d_exact = (uint32_t *)base; base += 4 * (size_t)n;
     uint32_t *d_label = (uint32_t *)base; base += 4 * (size_t)n;
+    uint32_t *d_label_out = (uint32_t *)base; base += 4 * (size_t)n;
     uint32_t *d_first = (uint32_t *)base; base += 4 * (size_t)std::max(1u, nx);
     base = (char *)(((uintptr_t)base + 15) & ~(uintptr_t)15);
     uint2 *d_pairs = (uint2 *)base;
@@ -1052,9 +1053,9 @@ extern "C" int ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pk, co
     k_uf_init<<<(std::max(n, nx) + 255) / 256, 256, 0, h->st>>>(d_label, n, d_first, nx);
     k_uf_first<<<(n + 255) / 256, 256, 0, h->st>>>(d_exact, n, nx, d_first);
     k_uf_union<<<(std::max<uint32_t>(n, (uint32_t)ne) + 255) / 256, 256, 0, h->st>>>(d_label, d_pairs, (uint32_t)ne, 0, d_exact, n, nx, d_first);
-    k_uf_flatten<<<(n + 255) / 256, 256, 0, h->st>>>(d_label, n, ctr);
+    k_uf_flatten<<<(n + 255) / 256, 256, 0, h->st>>>(d_label, n, ctr, d_label_out);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(hl, d_label, 4 * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(hl, d_label_out, 4 * (size_t)n, cudaMemcpyDeviceToHost, h->st));
     unsigned long long ncls = 0;
     CK(cudaMemcpyAsync(&ncls, &ctr->n_classes, sizeof(ncls), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));

@@ -1142,10 +1142,12 @@ __global__ void k_uf_union(uint32_t *label, const uint2 *pairs, uint32_t npairs,
         if (x < n_exact) { uint32_t f = first[x]; if (f != i) uf_union(label, f, i); }
     }
 }
-__global__ void __launch_bounds__(256) k_uf_flatten(uint32_t *label, uint32_t n, DevCounters *ctr) {
+// Final labels go to a SEPARATE array: other threads are still path-halving through `label`, and a
+// halving store (an ancestor, not necessarily the root) must not overwrite a final label.
+__global__ void __launch_bounds__(256) k_uf_flatten(uint32_t *label, uint32_t n, DevCounters *ctr, uint32_t *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long isroot = 0;
-    if (i < n) { uint32_t r = uf_find(label, i); isroot = r == i; __stcg(&label[i], r); }
+    if (i < n) { uint32_t r = uf_find(label, i); isroot = r == i; out[i] = r; }
     typedef cub::BlockReduce<unsigned long long, 256> BR;
     __shared__ typename BR::TempStorage tmp;
     unsigned long long s = BR(tmp).Sum(isroot);

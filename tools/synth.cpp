@@ -417,7 +417,7 @@ extern "C" int esynth_generate(const esynth_cfg_t *cfgp, ejoin_pack_t **out, uin
                         mb.nch = 1;
                     }
                 }
-                cells += mb.ncells;
+                cells += giant ? 1 : mb.ncells;         // the giant-bucket config counts exact subclonotypes, not cells
                 members.push_back(std::move(mb));
             }
             family_id++;
