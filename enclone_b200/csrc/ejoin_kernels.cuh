@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restri
     k_to_s[k] = s;
 }
 
-// one thread per (entry, c3 word); 8 threads per entry, W of them active
+// one thread per (entry, c3 word); 8 threads per entry, W of them active.  The 32 bases of a word
+// come from chain 0's CDR3, chain 1's, or both (the word that straddles the boundary).
 __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__restrict__ meta, DevCounters *ctr, uint32_t *__restrict__ c3) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t s = t >> 3, w = t & 7;
@@ -277,18 +278,32 @@ __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__re
     const int W = max(1, (total + 31) / 32);
     if ((int)w >= W) return;
     const uint32_t k = m.k;
-    const uint8_t *q0 = in.cdr3_arena + in.cdr3_off[0][k], *q1 = in.cdr3_arena + in.cdr3_off[1][k];
-    uint32_t H = 0, L = 0, bad = 0;
-    for (int i = 0; i < 32; i++) {
-        const int p = (int)w * 32 + i;
-        if (p >= total) break;
-        const int code = base_code(p < cl0 ? q0[p] : q1[p - cl0]);
-        if (code < 0) bad = 1;
-        else { H |= (uint32_t)((code >> 1) & 1) << i; L |= (uint32_t)(code & 1) << i; }
+    const int p0 = 32 * (int)w;
+    const int nb = total - p0;                                 // valid bytes in this word
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = 0;
+    if (p0 < cl0) {
+        uint32_t a[8];
+        load32u(in.cdr3_arena + in.cdr3_off[0][k] + p0, a);
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = a[i] & low_bytes(cl0 - p0 - 4 * i);
     }
+    if (p0 + 32 > cl0 && nb > 0) {
+        uint32_t b[8];
+        load32u(in.cdr3_arena + in.cdr3_off[1][k] + (p0 - cl0), b);      // may start a few bytes before the string: masked below
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] |= b[i] & ~low_bytes(cl0 - p0 - 4 * i);
+    }
+    uint32_t bad = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x[i] &= low_bytes(nb - 4 * i); bad |= not_acgt(x[i]) & low_bytes(nb - 4 * i); }
     if (bad) atomicOr(&ctr->err, ERR_CDR3_BAD_CHAR);
-    c3[m.c3off + w] = H;
-    c3[m.c3off + W + w] = L;
+    uint32_t H, L;
+    planes32(x, H, L);
+    const uint32_t valid = low_bits(nb);
+    c3[m.c3off + w] = H & valid;
+    c3[m.c3off + W + w] = L & valid;
 }
 
 // [wm_lo, wm_hi): only the entries whose last V..J byte lies in this range of the caller's arena are
@@ -926,6 +941,9 @@ __device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTab
 // scored in parallel.  Exactness is unaffected: only pairs of b's WITH a phase-A edge are ever
 // skipped.
 #define PHASE_A_MAX_REJECTS 6u
+#ifndef ROWS_MIN_BLOCKS
+#define ROWS_MIN_BLOCKS 6
+#endif
 struct RowCtx {
     const DevIn *in; const DevTables *tb; const DevParams *pr; DevCounters *ctr;
     uint2 *cand; unsigned long long cand_cap;
@@ -1058,7 +1076,7 @@ __device__ __forceinline__ void row_item(RowCtx &cx, const GroupInfo &g, uint32_
     }
 }
 
-__global__ void __launch_bounds__(T1_TILE) k_join_rows(DevIn in, DevTables tb, DevParams pr, const GroupInfo *__restrict__ groups,
+__global__ void __launch_bounds__(T1_TILE, ROWS_MIN_BLOCKS) k_join_rows(DevIn in, DevTables tb, DevParams pr, const GroupInfo *__restrict__ groups,
                                                        DevCounters *ctr, uint2 *cand, unsigned long long cand_cap, uint32_t *parent,
                                                        unsigned long long *f0_key, unsigned long long *f0_val, uint32_t stride, uint32_t phase) {
     __shared__ __align__(128) uint32_t sA[2][T1_TILE * 2 * T1_WMAX];
