@@ -205,6 +205,7 @@ extern "C" int ejoin_create(ejoin_handle_t **out, const ejoin_params_t *p, int d
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return EJOIN_E_NOGPU; }
     ejoin_handle *h = new ejoin_handle();
     h->device = device; h->params = *p;
+    if (const char *cc = getenv("EJOIN_CAND_CAP")) h->cand_cap = strtoull(cc, nullptr, 10);   // tests: force the overflow-and-retry path
     *out = h;                                    // so the caller can read last_error on failure
     if (p->old_mult) return fail(h, EJOIN_E_UNSUPPORTED, "OLD_MULT is not supported by the GPU path");
     if (p->auto_share > P1_DCAP) return fail(h, EJOIN_E_UNSUPPORTED, "AUTO_SHARES above the p1 table depth");

@@ -110,3 +110,11 @@ def test_oracle_two_cell_rule_and_skip_semantics():
     # raw_joins are sorted by (k1,k2)
     key = e_strict["k1"].astype(np.int64) << 32 | e_strict["k2"]
     assert (np.diff(key) > 0).all()
+
+
+def test_rust_ffi_crate_declares_the_same_symbols():
+    """rust/enclone_join_ffi (written, not compilable here) must bind exactly the header's entry points."""
+    import re
+    rs = open(os.path.join(ROOT, "rust", "enclone_join_ffi", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (ejoin_[a-z0-9_]+)\(", rs))
+    assert bound == set(_lib.EXPORTS), bound ^ set(_lib.EXPORTS)

@@ -204,3 +204,43 @@ def test_full_size_configs_against_oracle(name, scale):
     assert g.stats["pairs_candidate"] == ost["pairs_candidate"]
     # the GPU compares every pair of a comparison group; the oracle only those join_core did not skip
     assert g.stats["pairs_compared"] >= ost["pairs_same_cdr3_len"]
+
+
+def test_candidate_buffer_overflow_retry(monkeypatch):
+    """A deliberately tiny candidate buffer: the pipeline notices the overflow (the counts stay exact),
+    re-sizes and re-runs; the result is unchanged."""
+    pack, _ = synth.generate(n_cells=6000, n_donors=2, seed=41)
+    ref = join_exacts(pack)
+    monkeypatch.setenv("EJOIN_CAND_CAP", "64")
+    got = join_exacts(pack)
+    assert np.array_equal(ref.edges, got.edges) and np.array_equal(ref.class_of, got.class_of)
+
+
+def test_unsupported_inputs_fail_loudly():
+    from enclone_b200._lib import EjoinError
+    pack, _ = synth.generate(n_cells=500, seed=42)
+    # OLD_MULT is refused at handle creation
+    with pytest.raises(EjoinError) as ei:
+        Joiner(default_params(old_mult=1))
+    assert ei.value.code == -4
+    # a CDR3 with a character outside ACGT
+    a = {k: (list(v) if isinstance(v, list) else v) for k, v in pack.arrays.items()}
+    arena = a["cdr3_arena"].copy()
+    arena[int(a["cdr3_off"][0][3])] = ord("N")
+    a["cdr3_arena"] = arena
+    bad = JoinPack(a, is_bcr=True)
+    with pytest.raises(EjoinError) as ei:
+        join_exacts(bad)
+    assert ei.value.code == -4 and "ACGT" in str(ei.value)
+    # a germline index outside the table
+    a = {k: (list(v) if isinstance(v, list) else v) for k, v in pack.arrays.items()}
+    vs = a["vs_seq"][0].copy(); vs[5] = 10 ** 6; a["vs_seq"] = [vs, a["vs_seq"][1]]
+    with pytest.raises(EjoinError) as ei:
+        join_exacts(JoinPack(a, is_bcr=True))
+    assert ei.value.code == -1
+    # abi version mismatch
+    good = JoinPack({k: v for k, v in pack.arrays.items()}, is_bcr=True)
+    good.struct.abi_version = 99
+    with pytest.raises(EjoinError) as ei:
+        join_exacts(good)
+    assert ei.value.code == -1
