@@ -243,13 +243,11 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_s, dev_s = float(tt[0]), float(tt[1])
-    # pairs of the whole job (all ranks): from the bucket scan of the full input
-    if world == 1:
-        pairs_total = int(e2e_stats["pairs_candidate"])
-    else:
-        cnt = torch.tensor([int(st["pairs_candidate"])], device=dev, dtype=torch.int64)
-        dist.all_reduce(cnt)
-        pairs_total = int(cnt[0])
+    # pairs of the whole job (all ranks): sum over the lens buckets of the full input of n_b (n_b - 1) / 2
+    from enclone_b200.join import plan_shards
+    _, bstart = plan_shards(sp.struct, 1)
+    m = np.diff(bstart.astype(np.int64))
+    pairs_total = int((m * (m - 1) // 2).sum())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -83,6 +83,7 @@ struct ejoin_handle {
     uint64_t tig_bytes = 0;
     uint64_t h2d_bytes = 0;
     bool uploaded = false;
+    uint32_t last_stride = 1, last_phase = 0;   // tile-row share of the last run_shard (stride mode), reused by run_resident
     bool device_final = false;  // the last pipeline run produced the final emitted edge list on the device
     // tables (cached across runs)
     DevBuf d_part;              // ejoin_partition_gpu scratch
@@ -489,7 +490,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
         sz.take(8 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                   // Boruvka: best, ends, component sizes
         sz.take(cub_bytes + 256);
-        sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1));                   // payload staging (taken later)
+        sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1)); sz.take(4 * (size_t)n + 64);   // payload staging (taken later)
         sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)h->din.n_exact + 64);   // union-find labels (in, out), first entry per exact
         CK(h->work.buf.ensure(sz.off + 4096));
         h->work.reset();
@@ -773,6 +774,7 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
     const size_t save = A.off;
     uint2 *d_pairs = A.take<uint2>(ne ? ne : 1);
     ejoin_edge_t *d_out = A.take<ejoin_edge_t>(ne ? ne : 1);
+    uint32_t *d_slow = A.take<uint32_t>(ne ? ne : 1);
     uint32_t *d_label = A.take<uint32_t>(n ? n : 1), *d_label_out = A.take<uint32_t>(n ? n : 1);
     uint32_t *d_first = A.take<uint32_t>(pk->n_exact ? pk->n_exact : 1);
     if (A.off > A.buf.cap) { A.off = save; return fail(h, EJOIN_E_NOMEM, "work arena too small for the epilogue"); }
@@ -784,8 +786,10 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
         DevTables tbs;
         tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
         tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
-        k_payload<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)ne, h->k_base, d_out);
-        h->launches++;
+        CK(cudaMemsetAsync(&ctr->n_payload_slow, 0, sizeof(unsigned int), h->st));
+        k_payload_fast<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)ne, h->k_base, d_out, d_slow);
+        k_payload<<<h->sm_count * 4, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, d_slow, h->k_base, d_out);
+        h->launches += 2;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_edges, d_out, ne * sizeof(ejoin_edge_t), cudaMemcpyDeviceToHost, h->st));
     }
@@ -817,6 +821,7 @@ extern "C" int ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pk) {
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->st_copy));
     h->copy_pending = false;
+    h->last_stride = 1; h->last_phase = 0;
     h->is_bcr = (int)pk->is_bcr;
     return 0;
 }
@@ -824,7 +829,7 @@ extern "C" int ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pk) {
 extern "C" int ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats) {
     if (!h) return EJOIN_E_ARG;
     h->launches = 0;
-    int rc = device_pipeline(h, h->is_bcr, 1, 0);
+    int rc = device_pipeline(h, h->is_bcr, h->last_stride, h->last_phase);
     if (rc) return rc;
     if (stats) { memset(stats, 0, sizeof(*stats)); fill_stats(h, stats); }
     return 0;
@@ -852,6 +857,7 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     if (rc) return rc;
     h->is_bcr = (int)pk->is_bcr;
     const double t1 = now_ms();                 // copies are in flight on the copy stream; the pipeline waits on their events
+    h->last_stride = 1; h->last_phase = 0;
     rc = device_pipeline(h, (int)pk->is_bcr, 1, 0);
     if (rc) return rc;
     const double t2 = now_ms();
@@ -938,7 +944,8 @@ static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int
     if (rc) return rc;
     h->is_bcr = (int)pk->is_bcr;
     const double t1 = now_ms();
-    rc = device_pipeline(h, (int)pk->is_bcr, stride_mode ? (uint32_t)world : 1u, stride_mode ? (uint32_t)rank : 0u);
+    h->last_stride = stride_mode ? (uint32_t)world : 1u; h->last_phase = stride_mode ? (uint32_t)rank : 0u;
+    rc = device_pipeline(h, (int)pk->is_bcr, h->last_stride, h->last_phase);
     if (rc) return rc;
     const double t2 = now_ms();
     const size_t nk = (size_t)h->counters.n_kept;

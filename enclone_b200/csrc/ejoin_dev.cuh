@@ -66,6 +66,8 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned long long t1_alg_bytes, t2_alg_bytes, t2_units, n_classes;
     unsigned int err;
     unsigned int bor_active;
+    unsigned int n_payload_slow;
+    unsigned int pad0;
 };
 
 struct DevParams {           // ejoin_params_t plus run constants, by value to kernels

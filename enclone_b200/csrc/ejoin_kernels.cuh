@@ -783,11 +783,99 @@ __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, D
     }
 }
 
-// K7  payload: the full PotentialJoin record of each emitted edge, one warp per edge.
+// K7  payload: the full PotentialJoin record of each emitted edge.
+//   k_payload_fast  one thread per edge, bit-parallel over the t2 rows (same germline, no flags);
+//                   the edges it cannot represent are listed for
+//   k_payload       one warp per listed edge, bytewise from the ASCII bytes.
+__device__ __forceinline__ void write_edge(ejoin_edge_t *out, uint32_t k1, uint32_t k2, const PairCounts &pc, const EntryMeta &m1, int kk, int d,
+                                           int err, int reason, double p1, double mult, double score) {
+    ejoin_edge_t e;
+    memset(&e, 0, sizeof(e));
+    e.k1 = k1; e.k2 = k2;
+    for (int u = 0; u < pc.nrefs; u++) {
+        e.shares[u] = pc.shares[u]; e.indeps[u] = pc.indeps[u];
+        for (int q = 0; q < 4; q++) e.shares_details[u][q] = (uint16_t)pc.det[u][q];
+    }
+    e.nrefs = (uint16_t)pc.nrefs; e.cd = (uint16_t)(pc.cd0 + pc.cd1); e.cd_chain[0] = (uint16_t)pc.cd0; e.cd_chain[1] = (uint16_t)pc.cd1;
+    e.diffs = (uint32_t)pc.diffs; e.k = (uint16_t)kk; e.d = (uint16_t)d;
+    e.n = 3u * ((uint32_t)m1.len[0] + (uint32_t)m1.len[1]);
+    e.err = (uint8_t)err; e.accept_reason = (uint8_t)reason;
+    e.p1 = p1; e.mult = mult; e.score = score;
+    *out = e;
+}
+
+__global__ void __launch_bounds__(128) k_payload_fast(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *k_to_s,
+                                                      const uint2 *pairs, uint32_t npairs, uint32_t k_base, ejoin_edge_t *out, uint32_t *slow_list) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const uint2 kk2 = pairs[i];
+        const EntryMeta &m1 = tb.meta[k_to_s[kk2.x - k_base]], &m2 = tb.meta[k_to_s[kk2.y - k_base]];
+        const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] ||
+                             m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
+        if (generic) { slow_list[atomicAdd(&ctr->n_payload_slow, 1u)] = i; continue; }
+        PairCounts pc;
+        memset(&pc, 0, sizeof(pc));
+        pc.nrefs = 1;
+        for (int c = 0; c < 2; c++)
+            if (m1.vref[c] != m2.vref[c] || m1.dref[c] != m2.dref[c] || m1.jref[c] != m2.jref[c]) pc.nrefs = 2;
+        // CDR3 differences per chain
+        const uint32_t cl0 = m1.cl[0], total = cl0 + m1.cl[1], W = max(1u, (total + 31) / 32);
+        int cdt = 0, cd0 = 0;
+        for (uint32_t w = 0; w < W; w++) {
+            const uint32_t D = (tb.c3[m1.c3off + w] ^ tb.c3[m2.c3off + w]) | (tb.c3[m1.c3off + W + w] ^ tb.c3[m2.c3off + W + w]);
+            cdt += __popc(D);
+            cd0 += __popc(D & range_mask((int)w, 0, (int)cl0));
+        }
+        pc.cd0 = cd0; pc.cd1 = cdt - cd0;
+        int f1 = 0, c1 = 0, f2 = 0, c2_ = 0, f3 = 0;
+        const bool reg = pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3);
+        const uint32_t *w1 = (const uint32_t *)(tb.t2 + m1.t2off), *w2 = (const uint32_t *)(tb.t2 + m2.t2off);
+        int diffs = 0, dfw = 0, d12 = 0, io = 0, det[4] = { 0, 0, 0, 0 }, blk0 = 0;
+        for (int c = 0; c < 2; c++) {
+            const int nw = ((int)m1.len[c] + 127) / 128 * 4;
+            const int vend = m1.vend[c];                    // same germline and length => same windows for both entries
+            const int a1 = m1.cs[c], a2 = m2.cs[c], cl = m1.cl[c];
+            for (int w = 0; w < nw; w++) {
+                const int o = (blk0 + (w >> 2)) * 12 + (w & 3);
+                const uint32_t D = (w1[o] ^ w2[o]) | (w1[o + 4] ^ w2[o + 4]);
+                const uint32_t M1 = w1[o + 8], M2 = w2[o + 8];
+                const uint32_t S = M1 & M2 & ~D;
+                diffs += __popc(D);
+                const uint32_t inV = range_mask(w, 0, vend);                 // share in the V window, else in the J window
+                det[2 * c] += __popc(S & inV);
+                det[2 * c + 1] += __popc(S & ~inV);
+                const uint32_t R = range_mask(w, a1, a1 + cl) | range_mask(w, a2, a2 + cl);
+                io += __popc(M1 & D & ~R) + __popc(M2 & D & ~R);
+                if (reg && c == 0) {
+                    dfw += __popc(D & range_mask(w, f1, c1));
+                    d12 += __popc(D & (range_mask(w, c1, f2) | range_mask(w, c2_, f3)));
+                }
+            }
+            blk0 += nw / 4;
+        }
+        const int shares = det[0] + det[1] + det[2] + det[3];
+        const int mm = (int)m1.m[0] + (int)m1.m[1] + (int)m2.m[0] + (int)m2.m[1];
+        pc.diffs = diffs;
+        for (int u = 0; u < 2; u++) {
+            pc.shares[u] = shares; pc.indeps[u] = mm - 2 * shares; pc.indeps_out[u] = io;
+            for (int q = 0; q < 4; q++) pc.det[u][q] = det[q];
+        }
+        pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
+        if (reg) { pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_); }
+        int kk = 0, d = 0, err = 0;
+        double p1 = 0, mult = 0, score = 0;
+        if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
+            err = !(m1.donor_lo == m1.donor_hi && m2.donor_lo == m2.donor_hi && m1.donor_lo == m2.donor_lo);
+        const int reason = decide(pr, tb, m1, m2, pc, ctr, &kk, &d, &p1, &mult, &score);
+        write_edge(&out[i], kk2.x, kk2.y, pc, m1, kk, d, err, reason, p1, mult, score);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *k_to_s,
-                                                 const uint2 *pairs, uint32_t npairs, uint32_t k_base, ejoin_edge_t *out) {
+                                                 const uint2 *pairs, const uint32_t *slow_list, uint32_t k_base, ejoin_edge_t *out) {
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < npairs; i += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t nslow = ctr->n_payload_slow;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < nslow; j += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t i = slow_list[j];
         const uint2 kk2 = pairs[i];
         const EntryMeta m1 = tb.meta[k_to_s[kk2.x - k_base]], m2 = tb.meta[k_to_s[kk2.y - k_base]];
         PairCounts pc;
@@ -797,21 +885,7 @@ __global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevPara
         if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
             err = !(m1.donor_lo == m1.donor_hi && m2.donor_lo == m2.donor_hi && m1.donor_lo == m2.donor_lo);
         int reason = decide(pr, tb, m1, m2, pc, ctr, &kk, &d, &p1, &mult, &score);
-        if (lane == 0) {
-            ejoin_edge_t e;
-            memset(&e, 0, sizeof(e));
-            e.k1 = kk2.x; e.k2 = kk2.y;
-            for (int u = 0; u < pc.nrefs; u++) {
-                e.shares[u] = pc.shares[u]; e.indeps[u] = pc.indeps[u];
-                for (int q = 0; q < 4; q++) e.shares_details[u][q] = (uint16_t)pc.det[u][q];
-            }
-            e.nrefs = (uint16_t)pc.nrefs; e.cd = (uint16_t)(pc.cd0 + pc.cd1); e.cd_chain[0] = (uint16_t)pc.cd0; e.cd_chain[1] = (uint16_t)pc.cd1;
-            e.diffs = (uint32_t)pc.diffs; e.k = (uint16_t)kk; e.d = (uint16_t)d;
-            e.n = 3u * ((uint32_t)m1.len[0] + (uint32_t)m1.len[1]);
-            e.err = (uint8_t)err; e.accept_reason = (uint8_t)reason;
-            e.p1 = p1; e.mult = mult; e.score = score;
-            out[i] = e;
-        }
+        if (lane == 0) write_edge(&out[i], kk2.x, kk2.y, pc, m1, kk, d, err, reason, p1, mult, score);
     }
 }
 

@@ -675,3 +675,38 @@ int oracle_accept_graph(const ejoin_pack_t *pk, const ejoin_params_t *pr, uint32
 void oracle_prepare(int kmax) { sr_ensure(kmax < 64 ? 64 : kmax); }
 void oracle_result_free(ejoin_result_t *r) { free(r->edges); free(r->class_of); memset(r, 0, sizeof(*r)); }
 void oracle_free(void *p) { free(p); }
+
+/* Statistic for design work: how many info entries have at least one partner in their bucket that
+ * passes the chain-count, CDR3-length and CDR3-identity gates (i.e. would reach the full scoring).
+ * Single-threaded scan of every pair; not part of the join. */
+uint64_t oracle_count_entries_with_cdr3_partner(const ejoin_pack_t *pk, const ejoin_params_t *pr) {
+    uint32_t nb;
+    uint32_t *bs = oracle_bucket_scan(pk, &nb);
+    uint8_t *hit = (uint8_t *)calloc(pk->n_info ? pk->n_info : 1, 1);
+    for (uint32_t b = 0; b < nb; b++)
+        for (uint32_t k1 = bs[b]; k1 < bs[b + 1]; k1++) {
+            if (pk->len[1][k1] == 0) continue;
+            uint32_t e1 = pk->exact_id[k1];
+            if (pk->nchains[e1] < 2 || pk->nchains[e1] > 3) continue;
+            const int n0 = pk->cdr3_len[0][k1], n1 = pk->cdr3_len[1][k1];
+            for (uint32_t k2 = k1 + 1; k2 < bs[b + 1]; k2++) {
+                if (hit[k1] && hit[k2]) continue;
+                if (pk->cdr3_len[0][k2] != n0 || pk->cdr3_len[1][k2] != n1) continue;
+                uint32_t e2 = pk->exact_id[k2];
+                if (pk->nchains[e2] < 2 || pk->nchains[e2] > 3) continue;
+                int cd = 0;
+                const uint8_t *a = cdr3(pk, 0, k1), *c = cdr3(pk, 0, k2);
+                for (int p = 0; p < n0; p++) cd += a[p] != c[p];
+                a = cdr3(pk, 1, k1); c = cdr3(pk, 1, k2);
+                for (int p = 0; p < n1; p++) cd += a[p] != c[p];
+                if (!pk->is_bcr && cd > 0) continue;
+                if (cd > pr->max_cdr3_diffs) continue;
+                if (100.0 * (1.0 - (double)cd / (double)(n0 + n1)) < pr->join_cdr3_ident) continue;
+                hit[k1] = hit[k2] = 1;
+            }
+        }
+    uint64_t n = 0;
+    for (uint32_t k = 0; k < pk->n_info; k++) n += hit[k];
+    free(hit); free(bs);
+    return n;
+}
