@@ -93,7 +93,8 @@ struct ejoin_handle {
     std::vector<double> multpool_host;
     std::vector<uint16_t> cdmax_host;
     std::vector<DevBuf> p1_tables;
-    unsigned long long cand_cap = 0;
+    unsigned long long cand_cap = 0;    // survivor list (tier-1 survivors beyond the phase-A slots)
+    unsigned long long edge_cap = 0;    // to-be-scored lists, accepted edges, sort arrays
     // work pointers of the last pipeline run
     EntryMeta *meta = nullptr; uint32_t *c3 = nullptr; uint4 *t2 = nullptr; uint32_t *k_to_s = nullptr;
     unsigned long long *kept_keys = nullptr, *kept_vals = nullptr;
@@ -206,7 +207,7 @@ extern "C" int ejoin_create(ejoin_handle_t **out, const ejoin_params_t *p, int d
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return EJOIN_E_NOGPU; }
     ejoin_handle *h = new ejoin_handle();
     h->device = device; h->params = *p;
-    if (const char *cc = getenv("EJOIN_CAND_CAP")) h->cand_cap = strtoull(cc, nullptr, 10);   // tests: force the overflow-and-retry path
+    if (const char *cc = getenv("EJOIN_CAND_CAP")) h->cand_cap = h->edge_cap = strtoull(cc, nullptr, 10);   // tests: force the overflow-and-retry path
     *out = h;                                    // so the caller can read last_error on failure
     if (p->old_mult) return fail(h, EJOIN_E_UNSUPPORTED, "OLD_MULT is not supported by the GPU path");
     if (p->auto_share > P1_DCAP) return fail(h, EJOIN_E_UNSUPPORTED, "AUTO_SHARES above the p1 table depth");
@@ -459,10 +460,12 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     const DevParams pr = dev_params(h->params, is_bcr);
     memset(&h->counters, 0, sizeof(h->counters));
     h->stats.ms_kernel_pack = h->stats.ms_kernel_tier1 = h->stats.ms_kernel_tier2 = h->stats.ms_kernel_other = 0;
-    if (h->cand_cap == 0) h->cand_cap = std::max<unsigned long long>(1ull << 20, 16ull * n);
+    if (h->cand_cap == 0) h->cand_cap = std::max<unsigned long long>(1ull << 20, 48ull * n);
+    if (h->edge_cap == 0) h->edge_cap = std::max<unsigned long long>(1ull << 20, 4ull * n);
     if (n == 0) return 0;
-    for (int attempt = 0; attempt < 4; attempt++) {
-        const unsigned long long cap = h->cand_cap;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        const unsigned long long ccap = h->cand_cap;
+        const unsigned long long cap = std::max<unsigned long long>(h->edge_cap, (unsigned long long)n + 1024);
         // ---- size and carve the work arena ----
         size_t cub_bytes = 0, tmpb = 0;
         const size_t nsort = (size_t)std::max<unsigned long long>(n, cap);
@@ -486,7 +489,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                             // t2sizes, t2off, gid
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
-        sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);        // cand, todo, generic, acc
+        sz.take(8 * ccap); sz.take(8 * ccap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
+        sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
         sz.take(8 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                   // Boruvka: best, ends, component sizes
         sz.take(cub_bytes + 256);
@@ -507,7 +511,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint4 *t2 = A.take<uint4>(t2_units);
         uint32_t *k_to_s = A.take<uint32_t>(n), *parent = A.take<uint32_t>(n);
         unsigned long long *f0_key = A.take<unsigned long long>(n), *f0_val = A.take<unsigned long long>(n);
-        uint2 *cand = A.take<uint2>(cap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
+        uint2 *cand = A.take<uint2>(ccap), *rest = A.take<uint2>(ccap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
+        uint32_t *firstk = A.take<uint32_t>((size_t)n * PHASE_A_K), *surv_cnt = A.take<uint32_t>(n);
+        uint8_t *needed = A.take<uint8_t>(n), *force = A.take<uint8_t>(n);
+        uint2 *pending = A.take<uint2>(n);
         ejoin_raw_edge_t *acc = A.take<ejoin_raw_edge_t>(cap);
         unsigned long long *pk_in = A.take<unsigned long long>(cap), *pv_in = A.take<unsigned long long>(cap);
         unsigned long long *pk_out = A.take<unsigned long long>(cap), *pv_out = A.take<unsigned long long>(cap);
@@ -550,34 +557,38 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         CK(cudaEventRecord(h->ev[1], st));
         k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, pr.ref_v_trim, pr.ref_j_trim);
         k_pack_c3<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, meta, ctr, c3);
+        // stride mode: the gathered edges of the other ranks need this rank's rows too -> pack every entry
+        k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, surv_cnt, needed, force, n, stride > 1 ? 1 : 0);
+        CK(cudaEventRecord(h->ev[2], st));
+        // tier 1: needs only the c3 rows, so it runs while the V..J arena is still on its way
+        int rows_occ = 8;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_occ, k_sweep, T1_TILE, 0);
+        if (rows_occ < 1) rows_occ = 1;
+        k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, cand, ccap, firstk, surv_cnt, needed, stride, phase);
+        CK(cudaEventRecord(h->ev[3], st));
         if (h->copy_pending) {
-            // pack each chunk's entries as its bytes land (an entry belongs to the chunk that completes it)
+            // pack each chunk's (needed) entries as its bytes land (an entry belongs to the chunk that completes it)
             uint64_t prev = 0;
             for (int i = 0; i < h->n_chunks; i++) {
                 CK(cudaStreamWaitEvent(st, h->ev_chunk[i == h->n_chunks - 1 ? 7 : i], 0));
-                k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, prev, h->chunk_end[i]);
+                k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, prev, h->chunk_end[i]);
                 prev = h->chunk_end[i];
             }
             h->launches += h->n_chunks - 1;
         } else {
-            k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, 0ull, ~0ull);
+            k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, 0ull, ~0ull);
         }
-        h->launches += 2;
-        k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, n);
-        h->launches += 2;
-        CK(cudaEventRecord(h->ev[2], st));
+        CK(cudaEventRecord(h->ev[6], st));
         DevTables tbs;
         tbs.meta = meta; tbs.c3 = c3; tbs.t2 = t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
         tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p;
         tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
-        int rows_occ = 4;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_occ, k_join_rows, T1_TILE, 0);
-        if (rows_occ < 1) rows_occ = 1;
-        k_join_rows<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(h->din, tbs, pr, groups, ctr, cand, cap, parent, f0_key, f0_val, stride, phase);
-        CK(cudaEventRecord(h->ev[3], st));
+        k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, firstk, surv_cnt, force, parent, f0_key, f0_val, cand, ccap, pending);
+        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, firstk, surv_cnt, force, parent, f0_key, f0_val, cand, ccap, pending);
+        h->launches += 8;
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
-        k_phaseb_filter<<<h->sm_count * 8, 256, 0, st>>>(cand, cap, parent, ctr, todo, 0);
+        k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, ccap);
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, parent);
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, parent, 0);
         k_forced_resolve<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, f0_key, f0_val);
@@ -585,7 +596,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         // round 2: the other recorded survivors, scored only across trees
         k_round2_begin<<<1, 1, 0, st>>>(ctr);
         k_forced_prune<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent);
-        k_phaseb_filter<<<h->sm_count * 8, 256, 0, st>>>(cand, cap, parent, ctr, todo, 1);
+        k_phaseb_cross<<<h->sm_count * 8, 256, 0, st>>>(rest, ccap, parent, ctr, todo, cap);
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, nullptr);
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, nullptr, 1);
         CK(cudaEventRecord(h->ev[4], st));
@@ -608,10 +619,15 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (h->counters.err & ERR_CDR3_BAD_CHAR) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 contains a character outside ACGT");
         if (h->counters.err & ERR_BAD_REFSEQ) return fail(h, EJOIN_E_ARG, "vs_seq/js_seq index outside the germline table");
         if (h->counters.err & ERR_K_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "a pair has 1024 or more mutations (p1 table width)");
-        if (h->counters.n_cand > cap || h->counters.n_generic_q > cap || (unsigned long long)n + h->counters.n_accept > cap) {
-            // candidate buffer too small: the counts are exact, so one retry suffices
-            h->cand_cap = std::max(h->counters.n_cand, std::max(h->counters.n_generic_q, (unsigned long long)n + h->counters.n_accept)) + 1024;
-            continue;
+        {
+            // a buffer was too small: the counters keep counting past the capacity, so they tell the size to retry with
+            // (a list that overflowed may have starved the lists behind it, hence the loop)
+            const DevCounters &k = h->counters;
+            const unsigned long long need_e = std::max(std::max(k.n_todo, k.n_todo_r1), std::max(k.n_generic_q, (unsigned long long)n + k.n_accept));
+            bool retry = false;
+            if (k.n_cand > ccap) { h->cand_cap = k.n_cand + k.n_cand / 8 + 1024; retry = true; }
+            if (need_e > cap) { h->edge_cap = need_e + need_e / 4 + 1024; retry = true; }
+            if (retry) continue;
         }
         if (device_final) {
             for (int guard = 0; h->counters.bor_active && guard < 64; guard++) {     // rare: more than 5 rounds needed
@@ -643,9 +659,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         CK(cudaEventRecord(h->ev[5], st));
         CK(cudaStreamSynchronize(st));
         float ms;
-        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->stats.ms_kernel_pack = ms;
-        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->stats.ms_kernel_tier1 = ms;
-        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->stats.ms_kernel_tier2 = ms;
+        float ms2;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); cudaEventElapsedTime(&ms2, h->ev[3], h->ev[6]); h->stats.ms_kernel_pack = ms + ms2;   // meta + c3, then t2 rows
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->stats.ms_kernel_tier1 = ms;                                                        // the sweep
+        cudaEventElapsedTime(&ms, h->ev[6], h->ev[4]); h->stats.ms_kernel_tier2 = ms;                                                        // phase A + phase B
         float tot;
         cudaEventElapsedTime(&tot, h->ev[0], h->ev[5]);
         h->stats.ms_device = tot;

@@ -61,13 +61,13 @@ struct GroupInfo {           // one comparison group = one run of equal sort key
 struct DevCounters {         // device-resident scalars (one struct, copied back once)
     unsigned long long n_valid, n_groups, n_work, c3_words, pairs_compared, pairs_candidate, n_buckets;
     unsigned long long n_cand, n_todo, n_generic, n_generic_q, n_accept, n_kept, pairs_tier2;
-    unsigned long long n_accept_r1, n_generic_r1, n_todo_r1;
+    unsigned long long n_accept_r1, n_generic_r1, n_todo_r1, n_rest;
     unsigned long long work_next;   // dynamic tile scheduler
     unsigned long long t1_alg_bytes, t2_alg_bytes, t2_units, n_classes;
     unsigned int err;
     unsigned int bor_active;
     unsigned int n_payload_slow;
-    unsigned int pad0;
+    unsigned int n_pending;
 };
 
 struct DevParams {           // ejoin_params_t plus run constants, by value to kernels

@@ -309,10 +309,11 @@ __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__re
 // [wm_lo, wm_hi): only the entries whose last V..J byte lies in this range of the caller's arena are
 // packed by this launch (the arena is uploaded in chunks; see upload_range).
 __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
-                                                 unsigned long long wm_lo, unsigned long long wm_hi) {
+                                                 const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= (uint32_t)ctr->n_valid) return;
+    if (!needed[s]) return;                       // no CDR3-compatible partner: its rows are never read
     const EntryMeta &m = meta[s];
     const uint32_t k = m.k;
     const int n0 = m.len[0], n1 = m.len[1];
@@ -577,31 +578,58 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
 // that must be scored: endpoints in different phase-A trees, or the force bit.  k_tier2: one thread
 // per kept pair, full evaluation (dense, so warps stay converged).
 // ---------------------------------------------------------------------------------------------
-// mode 0: the survivors of entries that gave up in phase A (force bit) -> all scored (round 1);
-// mode 1: the other recorded survivors whose endpoints lie in different trees (round 2).
-__global__ void __launch_bounds__(256) k_phaseb_filter(const uint2 *__restrict__ cand, unsigned long long cand_cap, const uint32_t *__restrict__ root,
-                                                       DevCounters *ctr, uint2 *__restrict__ todo, int mode) {
+// Pass 1 over the recorded survivors: the survivors of entries that gave up in phase A (force) go to
+// `todo` (all scored in round 1); the others are kept, compacted, in `rest` unless they visibly hang
+// off the same phase-A parent (same tree: never a forest edge).  Pass 2 (after round 1 and the pointer
+// doubling) keeps from `rest` the pairs whose endpoints lie in different trees.
+__global__ void __launch_bounds__(256) k_phaseb_split(const uint2 *__restrict__ cand, unsigned long long cand_cap, const uint32_t *__restrict__ parent,
+                                                      const uint8_t *__restrict__ force_b, DevCounters *ctr, uint2 *__restrict__ todo,
+                                                      unsigned long long todo_cap, uint2 *__restrict__ rest, unsigned long long rest_cap) {
     unsigned long long ncand = ctr->n_cand;
     if (ncand > cand_cap) ncand = cand_cap;
     const uint32_t lane = threadIdx.x & 31;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((ncand + 31) & ~31ull);
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        bool keep = false;
+        bool k1 = false, k2 = false;
         uint2 c = make_uint2(0, 0);
         if (i < ncand) {
             c = cand[i];
-            const bool force = c.x >> 31;
+            const bool fbit = c.x >> 31;
             c.x &= 0x7FFFFFFFu;
-            // a survivor whose endpoints already sit in one phase-A tree cannot be a forest edge
-            // (DESIGN.md §lazy): never scored
-            keep = mode == 0 ? force : (!force && root[c.x] != root[c.y]);
+            if (fbit || force_b[c.y]) k1 = true;
+            else k2 = parent[c.x] != parent[c.y] && parent[c.y] != c.x;
         }
+        const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, k1), m2 = __ballot_sync(0xFFFFFFFFu, k2);
+        if (m1) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->n_todo, (unsigned long long)__popc(m1));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(m1 & ((1u << lane) - 1u));
+            if (k1 && base < todo_cap) todo[base] = c;
+        }
+        if (m2) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->n_rest, (unsigned long long)__popc(m2));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(m2 & ((1u << lane) - 1u));
+            if (k2 && base < rest_cap) rest[base] = c;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_phaseb_cross(const uint2 *__restrict__ rest, unsigned long long rest_cap, const uint32_t *__restrict__ root,
+                                                      DevCounters *ctr, uint2 *__restrict__ todo, unsigned long long todo_cap) {
+    unsigned long long n = ctr->n_rest;
+    if (n > rest_cap) n = rest_cap;
+    const uint32_t lane = threadIdx.x & 31;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ull);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        bool keep = false;
+        uint2 c = make_uint2(0, 0);
+        if (i < n) { c = rest[i]; keep = root[c.x] != root[c.y]; }
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
         if (!mask) continue;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctr->n_todo, (unsigned long long)__popc(mask));
         base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(mask & ((1u << lane) - 1u));
-        if (keep) todo[base] = c;                            // todo has the capacity of cand
+        if (keep && base < todo_cap) todo[base] = c;
     }
 }
 
@@ -691,8 +719,11 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
-__device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
-    const uint32_t lane = threadIdx.x & 31;
+// WARP = true: the 32 lanes of a warp split the positions and reduce with shuffles; WARP = false: one thread does it all.
+template <bool WARP>
+__device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
+    const uint32_t lane = WARP ? (threadIdx.x & 31) : 0u;
+    constexpr int STEP = WARP ? 32 : 1;
     const uint32_t k1 = m1.k, k2 = m2.k;
     int nrefs = 1;
     for (int c = 0; c < 2; c++)
@@ -703,9 +734,9 @@ __device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const Entr
     for (int c = 0; c < 2; c++) {
         const int n = m1.len[c];
         const uint8_t *t1 = in.tig_arena + in.tig_off[c][k1], *t2 = in.tig_arena + in.tig_off[c][k2];
-        for (int p = lane; p < n; p += 32) diffs += t1[p] != t2[p];
+        for (int p = lane; p < n; p += STEP) diffs += t1[p] != t2[p];
         const uint8_t *q1 = in.cdr3_arena + in.cdr3_off[c][k1], *q2 = in.cdr3_arena + in.cdr3_off[c][k2];
-        for (int p = lane; p < (int)m1.cl[c]; p += 32) cdc[c] += q1[p] != q2[p];
+        for (int p = lane; p < (int)m1.cl[c]; p += STEP) cdc[c] += q1[p] != q2[p];
         const int a1 = m1.cs[c], a2 = m2.cs[c], cl = m1.cl[c];
         for (int u = 0; u < nrefs; u++) {
             const EntryMeta &mu = u == 0 ? m1 : m2;
@@ -713,7 +744,7 @@ __device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const Entr
             const int vl = (int)in.refseq_len[mu.vs[c]], jl = (int)in.refseq_len[mu.js[c]];
             int vend = vl - pr.ref_v_trim;
             if (vend > n) vend = n;
-            for (int p = lane; p < vend; p += 32) {
+            for (int p = lane; p < vend; p += STEP) {
                 const uint8_t r = v[p];
                 const int out = !((p >= a1 && p < a1 + cl) || (p >= a2 && p < a2 + cl));
                 if (t1[p] == t2[p]) { if (t1[p] != r) { sh[u]++; det[u][2 * c]++; } }
@@ -722,7 +753,7 @@ __device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const Entr
             int jstart = n - (jl - pr.ref_j_trim);
             if (jstart < 0) jstart = 0;
             if (jl - pr.ref_j_trim > 0)
-                for (int p = jstart + lane; p < n; p += 32) {
+                for (int p = jstart + lane; p < n; p += STEP) {
                     const uint8_t r = j[jl - (n - p)];
                     const int out = !((p >= a1 && p < a1 + cl) || (p >= a2 && p < a2 + cl));
                     if (t1[p] == t2[p]) { if (t1[p] != r) { sh[u]++; det[u][2 * c + 1]++; } }
@@ -730,21 +761,43 @@ __device__ void bytewise_counts(const DevIn &in, const DevParams &pr, const Entr
                 }
         }
     }
-    pc.diffs = warp_sum(diffs); pc.cd0 = warp_sum(cdc[0]); pc.cd1 = warp_sum(cdc[1]);
+    auto red = [](int v) { return WARP ? warp_sum(v) : v; };
+    pc.diffs = red(diffs); pc.cd0 = red(cdc[0]); pc.cd1 = red(cdc[1]);
     for (int u = 0; u < 2; u++) {
-        pc.shares[u] = warp_sum(sh[u]); pc.indeps[u] = warp_sum(in_[u]); pc.indeps_out[u] = warp_sum(io[u]);
-        for (int q = 0; q < 4; q++) pc.det[u][q] = warp_sum(det[u][q]);
+        pc.shares[u] = red(sh[u]); pc.indeps[u] = red(in_[u]); pc.indeps_out[u] = red(io[u]);
+        for (int q = 0; q < 4; q++) pc.det[u][q] = red(det[u][q]);
     }
     pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
     int f1, c1, f2, c2, f3;
     if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2, &f3)) {
         const uint8_t *t1 = in.tig_arena + in.tig_off[0][k1], *t2 = in.tig_arena + in.tig_off[0][k2];
         int dfw = 0, d12 = 0;
-        for (int p = f1 + lane; p < c1; p += 32) dfw += t1[p] != t2[p];
-        for (int p = c1 + lane; p < f2; p += 32) d12 += t1[p] != t2[p];
-        for (int p = c2 + lane; p < f3; p += 32) d12 += t1[p] != t2[p];
-        pc.dfw = warp_sum(dfw); pc.dc12 = warp_sum(d12); pc.lfw = c1 - f1; pc.l12 = (f2 - c1) + (f3 - c2);
+        for (int p = f1 + lane; p < c1; p += STEP) dfw += t1[p] != t2[p];
+        for (int p = c1 + lane; p < f2; p += STEP) d12 += t1[p] != t2[p];
+        for (int p = c2 + lane; p < f3; p += STEP) d12 += t1[p] != t2[p];
+        pc.dfw = red(dfw); pc.dc12 = red(d12); pc.lfw = c1 - f1; pc.l12 = (f2 - c1) + (f3 - c2);
     }
+}
+
+__device__ __forceinline__ void bytewise_counts(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
+    bytewise_counts_t<true>(in, pr, m1, m2, pc);
+}
+// One thread scores a pair bytewise (phase A, for the rare pairs evaluate_thread() sends back with -1;
+// the pair is already past the CDR3 and meta gates).  sa < sb positions of one group.
+__device__ __noinline__ int evaluate_thread_bytewise(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa,
+                                                     uint32_t sb, int *cd_out, int *d_out) {
+    const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
+    PairCounts pc;
+    bytewise_counts_t<false>(in, pr, m1, m2, pc);
+    atomicAdd(&ctr->n_generic, 1ull);
+    *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
+    if (!pr.is_bcr || pr.max_diffs < 1000000) {
+        int cap = pr.max_diffs;
+        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
+        if (pc.diffs > cap) return 0;
+    }
+    int kk; double p1, mult, score;
+    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
 }
 
 // K6  tier 2, bytewise: one warp per queued pair (already past the CDR3 and meta gates).
@@ -919,9 +972,10 @@ __global__ void __launch_bounds__(256) k_collect(const unsigned long long *f0_ke
     if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_kept, s);
 }
 
-__global__ void k_init_rows(uint32_t *parent, unsigned long long *f0_key, uint32_t n) {
+__global__ void k_init_rows(uint32_t *parent, unsigned long long *f0_key, uint32_t *cnt, uint8_t *needed, uint8_t *force, uint32_t n,
+                            uint8_t needed_init) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { parent[i] = i; f0_key[i] = ~0ull; }
+    if (i < n) { parent[i] = i; f0_key[i] = ~0ull; cnt[i] = 0; needed[i] = needed_init; force[i] = 0; }
 }
 
 // pointer doubling over the phase-A parent pointers (parent[s] < s or == s)
@@ -976,59 +1030,29 @@ __global__ void __launch_bounds__(P1_DCAP) k_p1_tables(const uint32_t *Ls, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-cooperative bytewise evaluation of one pair that evaluate_thread() sent back (-1): every
-// lane calls it with the same (sa < sb); the pair is already past the CDR3 and meta gates.
-// ---------------------------------------------------------------------------------------------
-__device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa, uint32_t sb,
-                                      int *cd_out, int *d_out) {
-    const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
-    PairCounts pc;
-    bytewise_counts(in, pr, m1, m2, pc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->n_generic, 1ull);
-    *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
-    if (!pr.is_bcr || pr.max_diffs < 1000000) {
-        int cap = pr.max_diffs;
-        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
-        if (pc.diffs > cap) return 0;
-    }
-    int kk; double p1, mult, score;
-    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K4  join rows: tier 1 (CDR3 XOR/popcount of all pairs of a comparison group) fused with the
-// lazy phase A of tier 2.
+// K4  sweep: tier 1 — CDR3 XOR/popcount of all pairs of a comparison group against the group's cd cap.
 //
-// Work item = one tile row (group g, B tile ib): the CTA's 128 threads each own one entry b of
-// the B tile (its c3 row in registers) and sweep the A tiles ia = 0..ib in ascending order; A
-// tiles are staged in shared memory with 1-D bulk TMA copies, double buffered on two mbarriers.
-// Inside a group sorted position order == info order, so thread b meets its CDR3 survivors a < b
-// in ascending info order.  Until b has an accepted partner, each survivor is fully scored by the
-// whole warp (evaluate_warp); the first accepted a is b's smallest accepted smaller neighbour,
-// i.e. the edge (a,b) of the lexicographically-first spanning forest that join_core's
-// skip-if-same-class scan would keep.  Later survivors of b are only recorded:
-// phase B (k_tier2) scores them iff their endpoints ended in different phase-A trees.
+// Work item = one tile row (group g, B tile ib): the CTA's 128 threads each own one entry b of the B
+// tile (its c3 row in registers) and sweep the A tiles ia = 0..ib in ascending order; A tiles are
+// staged in shared memory with 1-D bulk TMA copies, double buffered on two mbarriers.  Inside a group
+// sorted position order == info order, so thread b meets its CDR3 survivors a < b in ascending info
+// order: the first PHASE_A_K of them go to b's slot array (phase A scores them in that order), the
+// rest to the global survivor list (phase B).  Every entry that appears in a survivor pair is flagged
+// `needed`: only those get their V..J rows packed (about half of a repertoire never needs them).
 // ---------------------------------------------------------------------------------------------
-// A b whose first PHASE_A_MAX_REJECTS scored survivors are all rejected stops scoring inline (one
-// thread scoring thousands of rejected pairs in sequence would stall its whole CTA): it keeps no
-// phase-A edge and hands ALL its remaining survivors to phase B with a force bit, where they are
-// scored in parallel.  Exactness is unaffected: only pairs of b's WITH a phase-A edge are ever
-// skipped.
-#define PHASE_A_MAX_REJECTS 6u
-#ifndef ROWS_MIN_BLOCKS
-#define ROWS_MIN_BLOCKS 6
-#endif
-struct RowCtx {
-    const DevIn *in; const DevTables *tb; const DevParams *pr; DevCounters *ctr;
+#define PHASE_A_K 6u
+struct SweepCtx {
+    DevCounters *ctr;
     uint2 *cand; unsigned long long cand_cap;
-    uint32_t *parent; unsigned long long *f0_key, *f0_val;
-    unsigned long long evals, bytes;
+    uint32_t *firstk;      // [n][PHASE_A_K] a positions
+    uint32_t *cnt;         // [n] survivors of b
+    uint8_t *needed;       // [n]
 };
 
 template <int W>
-__device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
+__device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
                                           const uint32_t (&bH)[W], const uint32_t (&bL)[W], bool validB, uint32_t posA0, uint32_t posB,
-                                          bool &found, uint32_t &nrej, uint32_t &my_parent) {
+                                          uint32_t &mycnt) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (!__any_sync(0xFFFFFFFFu, validB)) return;          // a warp beyond the end of a short B tile
     for (uint32_t a0 = 0; a0 < rowsA; a0 += 32) {
@@ -1044,60 +1068,22 @@ __device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict
             for (int w = 0; w < W; w++) cnt += __popc((bH[w] ^ ra[w]) | (bL[w] ^ ra[W + w]));
             bits |= (cnt <= cdmax ? 1u : 0u) << aa;
         }
-        const uint32_t na = rowsA - a0;
-        if (na < 32) bits &= (1u << na) - 1u;
         if (!validB) bits = 0;
         if (diag) {                                  // keep a < b  <=>  a0 + aa < tid
             if (tid <= a0) bits = 0;
             else if (tid - a0 < 32) bits &= (1u << (tid - a0)) - 1u;
         }
-        if (!__any_sync(0xFFFFFFFFu, bits != 0)) continue;
-        // ---- phase A: every lane without a partner scores its own next survivor (ascending a);
-        //      pairs that need the bytewise path are then taken one at a time by the whole warp
-        for (;;) {
-            const bool need = !found && bits != 0;
-            if (!__any_sync(0xFFFFFFFFu, need)) break;
-            int reason = 0, cd = 0, d = 0, err = 0;
-            uint32_t pa = 0;
-            if (need) {
-                pa = posA0 + a0 + (uint32_t)(__ffs(bits) - 1);
-                bool scored;
-                reason = evaluate_thread(*cx.in, *cx.tb, *cx.pr, cx.ctr, pa, posB, &cd, &d, &err, &scored, &cx.bytes);
-                cx.evals += scored;
-            }
-            uint32_t gm = __ballot_sync(0xFFFFFFFFu, need && reason < 0);
-            while (gm) {
-                const int src = __ffs(gm) - 1;
-                gm &= gm - 1;
-                const uint32_t ga = __shfl_sync(0xFFFFFFFFu, pa, src), gb = __shfl_sync(0xFFFFFFFFu, posB, src);
-                int gcd, gd;
-                const int r = evaluate_warp_bytewise(*cx.in, *cx.tb, *cx.pr, cx.ctr, ga, gb, &gcd, &gd);
-                if ((int)lane == src) { reason = r; cd = gcd; d = gd; }
-            }
-            if (need) {
-                bits &= bits - 1;
-                if (reason <= 0 && ++nrej >= PHASE_A_MAX_REJECTS) found = true;     // give up: see below
-                if (reason > 0) {
-                    found = true;
-                    my_parent = pa;
-                    cx.parent[posB] = pa;
-                    cx.f0_key[posB] = ((unsigned long long)cx.tb->meta[pa].k << 32) | cx.tb->meta[posB].k;
-                    cx.f0_val[posB] = ((unsigned long long)((uint32_t)reason | ((uint32_t)err << 8)) << 32) |
-                                      ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
-                }
-            }
+        const uint32_t col = __reduce_or_sync(0xFFFFFFFFu, bits);      // a's with a survivor partner in this warp
+        if (!col) continue;
+        if ((col >> lane) & 1u) cx.needed[posA0 + a0 + lane] = 1;
+        // the first PHASE_A_K survivors of b, in ascending a, go to its slot array
+        while (bits && mycnt < PHASE_A_K) {
+            const uint32_t aa = __ffs(bits) - 1;
+            bits &= bits - 1;
+            cx.firstk[(size_t)posB * PHASE_A_K + mycnt] = posA0 + a0 + aa;
+            mycnt++;
         }
-        // ---- remaining survivors (b already has its partner): record for phase B, except those that
-        //      visibly hang off the same phase-A parent as b (same tree: phase B would skip them anyway;
-        //      a stale read of parent[] only makes us keep a pair)
-        if (__any_sync(0xFFFFFFFFu, bits != 0 && nrej < PHASE_A_MAX_REJECTS)) {
-            // one coalesced read of the block's 32 parents, then a register transpose by shuffles
-            const uint32_t par_blk = (a0 + lane < rowsA) ? __ldcg(&cx.parent[posA0 + a0 + lane]) : 0xFFFFFFFEu;
-            uint32_t same = 0;
-#pragma unroll
-            for (int aa = 0; aa < 32; aa++) same |= (__shfl_sync(0xFFFFFFFFu, par_blk, aa) == my_parent ? 1u : 0u) << aa;
-            if (nrej < PHASE_A_MAX_REJECTS) bits &= ~same;
-        }
+        // the rest: the global survivor list
         if (__any_sync(0xFFFFFFFFu, bits != 0)) {
             uint32_t cntl = __popc(bits), incl = cntl;
 #pragma unroll
@@ -1106,11 +1092,11 @@ __device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&cx.ctr->n_cand, (unsigned long long)totalc);
             base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cntl);
+            mycnt += cntl;
             while (bits) {
                 const uint32_t aa = __ffs(bits) - 1;
                 bits &= bits - 1;
-                // a b that gave up has no phase-A edge: its survivors carry the force bit and are all scored
-                if (base < cx.cand_cap) cx.cand[base] = make_uint2((posA0 + a0 + aa) | (nrej >= PHASE_A_MAX_REJECTS ? 0x80000000u : 0u), posB);
+                if (base < cx.cand_cap) cx.cand[base] = make_uint2(posA0 + a0 + aa, posB);
                 base++;
             }
         }
@@ -1118,7 +1104,7 @@ __device__ __forceinline__ void row_sweep(RowCtx &cx, const uint32_t *__restrict
 }
 
 template <int W>
-__device__ __forceinline__ void row_item(RowCtx &cx, const GroupInfo &g, uint32_t ib, const uint32_t *__restrict__ c3, uint32_t (*sA)[T1_TILE * 2 * T1_WMAX],
+__device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint32_t ib, const uint32_t *__restrict__ c3, uint32_t (*sA)[T1_TILE * 2 * T1_WMAX],
                                          uint64_t *bar, uint32_t &parity) {
     const uint32_t tid = threadIdx.x;
     const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
@@ -1130,8 +1116,7 @@ __device__ __forceinline__ void row_item(RowCtx &cx, const GroupInfo &g, uint32_
 #pragma unroll
         for (int w = 0; w < W; w++) { bH[w] = rb[w]; bL[w] = rb[W + w]; }
     }
-    bool found = false;
-    uint32_t nrej = 0, my_parent = 0xFFFFFFFFu;
+    uint32_t mycnt = 0;
     auto issue = [&](uint32_t ia) {
         const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
         const uint32_t bytes = (rowsA * 2 * W * 4 + 15) & ~15u;
@@ -1145,14 +1130,15 @@ __device__ __forceinline__ void row_item(RowCtx &cx, const GroupInfo &g, uint32_
         mbar_wait(&bar[ia & 1], (parity >> (ia & 1)) & 1u);
         parity ^= 1u << (ia & 1);
         const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
-        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, found, nrej, my_parent);
+        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, mycnt);
         __syncthreads();
     }
+    if (validB && mycnt) { cx.cnt[posB] = mycnt; cx.needed[posB] = 1; }
 }
 
-__global__ void __launch_bounds__(T1_TILE, ROWS_MIN_BLOCKS) k_join_rows(DevIn in, DevTables tb, DevParams pr, const GroupInfo *__restrict__ groups,
-                                                       DevCounters *ctr, uint2 *cand, unsigned long long cand_cap, uint32_t *parent,
-                                                       unsigned long long *f0_key, unsigned long long *f0_val, uint32_t stride, uint32_t phase) {
+__global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ c3, const GroupInfo *__restrict__ groups, DevCounters *ctr,
+                                                   uint2 *cand, unsigned long long cand_cap, uint32_t *firstk, uint32_t *cnt, uint8_t *needed,
+                                                   uint32_t stride, uint32_t phase) {
     __shared__ __align__(128) uint32_t sA[2][T1_TILE * 2 * T1_WMAX];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t s_item;
@@ -1160,9 +1146,8 @@ __global__ void __launch_bounds__(T1_TILE, ROWS_MIN_BLOCKS) k_join_rows(DevIn in
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
     __syncthreads();
     uint32_t parity = 0;                       // bit i = phase of bar[i]
-    RowCtx cx;
-    cx.in = &in; cx.tb = &tb; cx.pr = &pr; cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap;
-    cx.parent = parent; cx.f0_key = f0_key; cx.f0_val = f0_val; cx.evals = 0; cx.bytes = 0;
+    SweepCtx cx;
+    cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap; cx.firstk = firstk; cx.cnt = cnt; cx.needed = needed;
     const uint32_t ngroups = (uint32_t)ctr->n_groups;
     const unsigned long long nwork = ctr->n_work;
     for (;;) {
@@ -1176,21 +1161,138 @@ __global__ void __launch_bounds__(T1_TILE, ROWS_MIN_BLOCKS) k_join_rows(DevIn in
         const GroupInfo g = groups[lo];
         const uint32_t ib = g.tiles - 1 - (uint32_t)(item - g.work_off);      // longest rows of a group first
         switch (g.W) {
-            case 1: row_item<1>(cx, g, ib, tb.c3, sA, bar, parity); break;
-            case 2: row_item<2>(cx, g, ib, tb.c3, sA, bar, parity); break;
-            case 3: row_item<3>(cx, g, ib, tb.c3, sA, bar, parity); break;
-            case 4: row_item<4>(cx, g, ib, tb.c3, sA, bar, parity); break;
-            case 5: row_item<5>(cx, g, ib, tb.c3, sA, bar, parity); break;
-            case 6: row_item<6>(cx, g, ib, tb.c3, sA, bar, parity); break;
-            case 7: row_item<7>(cx, g, ib, tb.c3, sA, bar, parity); break;
-            default: row_item<8>(cx, g, ib, tb.c3, sA, bar, parity); break;
+            case 1: row_item<1>(cx, g, ib, c3, sA, bar, parity); break;
+            case 2: row_item<2>(cx, g, ib, c3, sA, bar, parity); break;
+            case 3: row_item<3>(cx, g, ib, c3, sA, bar, parity); break;
+            case 4: row_item<4>(cx, g, ib, c3, sA, bar, parity); break;
+            case 5: row_item<5>(cx, g, ib, c3, sA, bar, parity); break;
+            case 6: row_item<6>(cx, g, ib, c3, sA, bar, parity); break;
+            case 7: row_item<7>(cx, g, ib, c3, sA, bar, parity); break;
+            default: row_item<8>(cx, g, ib, c3, sA, bar, parity); break;
         }
     }
-    // per-thread tallies -> one atomic per warp
-    unsigned long long ev = cx.evals, by = cx.bytes;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A (lazy exact scoring): one thread per entry b.  b fully scores its first
+// survivors in ascending a until one is accepted: that a = m(b) is b's smallest accepted smaller
+// neighbour, and (m(b), b) is an edge of the lexicographically-first spanning forest that join_core's
+// skip-if-same-class scan would keep.  Survivors after m(b) are only recorded for phase B.  A b whose
+// PHASE_A_K slots are all rejected is marked `force`:
+// all its remaining survivors are scored in phase B round 1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_phase_a(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *__restrict__ firstk,
+                                                 const uint32_t *__restrict__ cnt, uint8_t *force, uint32_t *parent, unsigned long long *f0_key,
+                                                 unsigned long long *f0_val, uint2 *cand, unsigned long long cand_cap, uint2 *pending) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long evals = 0, bytes = 0;
+    if (s < (uint32_t)ctr->n_valid) {
+        const uint32_t c = cnt[s];
+        if (c) {
+            const uint32_t nfirst = min(c, PHASE_A_K);
+            bool found = false, forced = false, pended = false;
+            uint32_t next = nfirst;                     // first slot not consumed by phase A
+            for (uint32_t i = 0; i < nfirst; i++) {
+                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
+                int cd, d, err;
+                bool scored;
+                int r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
+                evals += scored;
+                if (r < 0) {                       // has_del / different germlines: rare; a whole warp continues this b (k_phase_a_pending)
+                    const uint32_t q = atomicAdd(&ctr->n_pending, 1u);
+                    pending[q] = make_uint2(s, i);
+                    pended = true;
+                    break;
+                }
+                if (r > 0) {
+                    found = true; next = i + 1;
+                    parent[s] = a;
+                    f0_key[s] = ((unsigned long long)tb.meta[a].k << 32) | tb.meta[s].k;
+                    f0_val[s] = ((unsigned long long)((uint32_t)r | ((uint32_t)err << 8)) << 32) | ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
+                    break;
+                }
+            }
+            if (pended) next = nfirst;                                   // the continuation kernel owns the rest of this b
+            if (!found && !forced && !pended && c > PHASE_A_K) forced = true;       // all slots rejected and more survivors exist
+            if (forced) force[s] = 1;
+            // slots not consumed: the survivors after m(b) (recorded for phase B)
+            for (uint32_t i = next; i < nfirst; i++) {
+                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
+                if (found && parent[a] == parent[s]) continue;           // hangs off the same parent: same tree, phase B would skip it
+                const unsigned long long q = atomicAdd(&ctr->n_cand, 1ull);
+                if (q < cand_cap) cand[q] = make_uint2(a | (forced ? 0x80000000u : 0u), s);
+            }
+        }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o); by += __shfl_xor_sync(0xFFFFFFFFu, by, o); }
-    if ((tid & 31) == 0 && ev) { atomicAdd(&ctr->pairs_tier2, ev); atomicAdd(&ctr->t2_alg_bytes, by); }
+    for (int o = 16; o > 0; o >>= 1) { evals += __shfl_xor_sync(0xFFFFFFFFu, evals, o); bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, o); }
+    if ((threadIdx.x & 31) == 0 && evals) { atomicAdd(&ctr->pairs_tier2, evals); atomicAdd(&ctr->t2_alg_bytes, bytes); }
+}
+
+// Continuation of phase A for the entries that met a pair needing the bytewise path: one warp per
+// entry, same rules; the bytewise pairs are scored by the whole warp, the others by lane 0.
+__device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa, uint32_t sb,
+                                                   int *cd_out, int *d_out) {
+    const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
+    PairCounts pc;
+    bytewise_counts_t<true>(in, pr, m1, m2, pc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->n_generic, 1ull);
+    *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
+    if (!pr.is_bcr || pr.max_diffs < 1000000) {
+        int cap = pr.max_diffs;
+        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
+        if (pc.diffs > cap) return 0;
+    }
+    int kk; double p1, mult, score;
+    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
+}
+
+__global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *__restrict__ firstk,
+                                                         const uint32_t *__restrict__ cnt, uint8_t *force, uint32_t *parent,
+                                                         unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
+                                                         unsigned long long cand_cap, const uint2 *pending) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t np = ctr->n_pending;
+    unsigned long long evals = 0, bytes = 0;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < np; j += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t s = pending[j].x, start = pending[j].y;
+        const uint32_t c = cnt[s], nfirst = min(c, PHASE_A_K);
+        bool found = false;
+        uint32_t next = nfirst;
+        for (uint32_t i = start; i < nfirst; i++) {
+            const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
+            int r = 0, cd = 0, d = 0, err = 0;
+            if (lane == 0) {
+                bool scored;
+                r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
+                if (i > start) evals += scored;                      // slot `start` was already counted by k_phase_a
+            }
+            r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
+            cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
+            if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
+            if (r > 0) {
+                found = true; next = i + 1;
+                if (lane == 0) {
+                    parent[s] = a;
+                    f0_key[s] = ((unsigned long long)tb.meta[a].k << 32) | tb.meta[s].k;
+                    f0_val[s] = ((unsigned long long)((uint32_t)r | ((uint32_t)err << 8)) << 32) | ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
+                }
+                break;
+            }
+        }
+        if (lane == 0) {
+            if (!found && c > PHASE_A_K) force[s] = 1;
+            for (uint32_t i = next; i < nfirst; i++) {
+                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
+                const unsigned long long q = atomicAdd(&ctr->n_cand, 1ull);
+                if (q < cand_cap) cand[q] = make_uint2(a, s);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { evals += __shfl_xor_sync(0xFFFFFFFFu, evals, o); bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, o); }
+    if (lane == 0 && evals) { atomicAdd(&ctr->pairs_tier2, evals); atomicAdd(&ctr->t2_alg_bytes, bytes); }
 }
 
 // ---------------------------------------------------------------------------------------------
