@@ -10,6 +10,7 @@ import numpy as np
 EJOIN_ABI_VERSION = 1
 EJOIN_NONE = 0xFFFFFFFF
 EJOIN_NONE16 = 0xFFFF
+EJOIN_F_TIGS_IN_PLACE = 1
 
 u8p, u16p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64))
 
@@ -17,7 +18,7 @@ u8p, u16p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint3
 class EjoinPack(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32), ("n_info", C.c_uint32), ("n_exact", C.c_uint32),
-        ("n_refseq", C.c_uint32), ("is_bcr", C.c_uint32), ("reserved0", C.c_uint32),
+        ("n_refseq", C.c_uint32), ("is_bcr", C.c_uint32), ("flags", C.c_uint32),
         ("exact_id", u32p),
         ("len", u16p * 2), ("tig_off", u64p * 2), ("tig_arena", u8p), ("tig_arena_bytes", C.c_uint64),
         ("has_del", u8p * 2), ("cdr3_len", u16p * 2), ("cdr3_off", u64p * 2), ("cdr3_arena", u8p),

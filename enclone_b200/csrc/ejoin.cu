@@ -72,6 +72,7 @@ struct ejoin_handle {
     int n_chunks = 0;
     uint64_t chunk_end[8] = {};     // arena byte offset (caller coordinates) up to which chunk i has landed
     bool copy_pending = false;
+    bool tigs_in_place = false;    // zero-copy: din.tig_arena aliases the caller's pinned arena
     int is_bcr = 1;
     int tables_is_bcr = -1;
     int sm_count = 148;
@@ -284,7 +285,7 @@ int check_pack(ejoin_handle *h, const ejoin_pack_t *pk) {
 }
 
 // H2D of the entries [lo,hi) (whole arrays for the per-exact and germline tables).
-int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t hi) {
+int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t hi, bool allow_in_place = true) {
     int rc = check_pack(h, pk);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
@@ -302,6 +303,18 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
             }
         if (n == 0) { tlo = thi = clo = chi = 0; }
     }
+    // zero-copy: the caller's arena is pinned, device-readable and padded (EJOIN_F_TIGS_IN_PLACE): k_pack_t2 and
+    // the bytewise path read it in place, and only the needed entries ever cross PCIe
+    bool in_place = false;
+    const uint8_t *in_place_ptr = nullptr;
+    if (allow_in_place && (pk->flags & EJOIN_F_TIGS_IN_PLACE) && thi > tlo && !getenv("EJOIN_NO_ZERO_COPY")) {
+        cudaPointerAttributes a0, a1;
+        if (cudaPointerGetAttributes(&a0, pk->tig_arena + tlo) == cudaSuccess && cudaPointerGetAttributes(&a1, pk->tig_arena + thi - 1) == cudaSuccess &&
+            a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost && a0.devicePointer) {
+            in_place_ptr = (const uint8_t *)a0.devicePointer;     // device alias of pk->tig_arena + tlo
+            in_place = true;
+        } else cudaGetLastError();
+    }
     Sizer sz;
     const size_t n1 = n ? n : 1;
     sz.take(4 * n1);                                   // exact_id
@@ -309,7 +322,7 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     sz.take(4 * n1); for (int i = 0; i < 6; i++) sz.take(2 * n1);
     for (int i = 0; i < 4; i++) sz.take(4 * (size_t)std::max(1u, pk->n_exact));
     sz.take(8 * (size_t)std::max(1u, pk->n_refseq)); sz.take(4 * (size_t)std::max(1u, pk->n_refseq));
-    sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 256);
+    sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 512);
     CK(h->in_arena.buf.ensure(sz.off + 4096));
     h->in_arena.reset();
     Arena &A = h->in_arena;
@@ -355,11 +368,19 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
     CK(up(d.refseq_arena, pk->refseq_arena, pk->refseq_arena_bytes));
     CK(cudaEventRecord(h->ev_small, h->st_copy));       // everything but the V..J bytes: keys / sort / groups / meta / c3 can start
-    {
+    h->tigs_in_place = in_place;
+    if (in_place) {
+        // device mirror with the same 16-byte phase as the host arena (k_pack_t2 copies chunk for chunk)
+        uint8_t *mir = A.take<uint8_t>(thi - tlo + 64 + 256);
+        mir += ((uintptr_t)in_place_ptr & 15);
+        d.tig_src = in_place_ptr; d.tig_copy = mir; d.tig_arena = mir;
+        h->n_chunks = 0;
+        h->copy_pending = true;                                   // still wait for ev_small
+    } else {
         // the V..J arena (3/4 of the bytes) goes up in chunks; k_pack_t2 packs each chunk's entries as it lands
         const uint64_t tb = thi - tlo;
         uint8_t *dst = A.take<uint8_t>(tb + 64);
-        d.tig_arena = dst;
+        d.tig_arena = dst; d.tig_src = dst; d.tig_copy = nullptr;
         const int nch = tb >= (32ull << 20) ? 8 : 1;
         h->n_chunks = nch;
         uint64_t done = 0;
@@ -374,7 +395,8 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
         h->copy_pending = true;
     }
     // the offsets index the original arenas: rebase the device pointers instead of the offsets
-    d.tig_arena -= tlo; d.cdr3_arena -= clo;
+    d.tig_arena -= tlo; d.tig_src -= tlo; if (d.tig_copy) d.tig_copy -= tlo;
+    d.cdr3_arena -= clo;
     h->n = n; h->k_base = lo; h->tig_bytes = thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
     return 0;
 }
@@ -566,7 +588,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (rows_occ < 1) rows_occ = 1;
         k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, cand, ccap, firstk, surv_cnt, needed, stride, phase);
         CK(cudaEventRecord(h->ev[3], st));
-        if (h->copy_pending) {
+        if (h->copy_pending && h->n_chunks > 0) {
             // pack each chunk's (needed) entries as its bytes land (an entry belongs to the chunk that completes it)
             uint64_t prev = 0;
             for (int i = 0; i < h->n_chunks; i++) {
@@ -669,7 +691,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         h->stats.ms_kernel_other = tot - h->stats.ms_kernel_pack - h->stats.ms_kernel_tier1 - h->stats.ms_kernel_tier2;
         if (h->copy_pending) {
             float up = 0;
-            cudaEventElapsedTime(&up, h->ev_copy0, h->ev_chunk[7]);
+            cudaEventElapsedTime(&up, h->ev_copy0, h->n_chunks > 0 ? h->ev_chunk[7] : h->ev_small);
             h->stats.ms_h2d = up;                 // H2D on the copy stream, overlapped with the stages before the join
             h->copy_pending = false;
         }
@@ -683,6 +705,7 @@ void fill_stats(ejoin_handle *h, ejoin_stats_t *s) {
     s->n_buckets = c.n_buckets; s->n_groups = c.n_groups; s->pairs_candidate = c.pairs_candidate; s->pairs_compared = c.pairs_compared;
     s->pairs_tier2 = c.pairs_tier2; s->pairs_accepted = c.n_accept; s->pairs_generic = c.n_generic; s->edges_after_prune = c.n_kept;
     s->gpu_launches = h->launches; s->h2d_bytes = h->h2d_bytes;
+    if (h->tigs_in_place) { unsigned long long ib = 0; for (int i = 0; i < 32; i++) ib += c.inplace_bytes[i]; s->h2d_bytes += ib; }   // bytes k_pack_t2 pulled over PCIe
     s->alg_bytes_tier1 = c.t1_alg_bytes; s->alg_bytes_tier2 = c.t2_alg_bytes;
     s->alg_bytes_pack = h->tig_bytes + c.n_valid * sizeof(EntryMeta) + c.c3_words * 4 + c.t2_units * 16;
     s->ms_kernel_pack = h->stats.ms_kernel_pack; s->ms_kernel_tier1 = h->stats.ms_kernel_tier1; s->ms_kernel_tier2 = h->stats.ms_kernel_tier2;
@@ -834,7 +857,7 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
 
 extern "C" int ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pk) {
     if (!h) return EJOIN_E_ARG;
-    int rc = upload_range(h, pk, 0, pk ? pk->n_info : 0);
+    int rc = upload_range(h, pk, 0, pk ? pk->n_info : 0, /*allow_in_place=*/false);   // resident means resident
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->st_copy));
     h->copy_pending = false;

@@ -63,6 +63,7 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned long long n_cand, n_todo, n_generic, n_generic_q, n_accept, n_kept, pairs_tier2;
     unsigned long long n_accept_r1, n_generic_r1, n_todo_r1, n_rest;
     unsigned long long work_next;   // dynamic tile scheduler
+    unsigned long long inplace_bytes[32];   // V..J bytes staged by k_pack_t2 (spread over 32 slots to keep the atomics apart)
     unsigned long long t1_alg_bytes, t2_alg_bytes, t2_units, n_classes;
     unsigned int err;
     unsigned int bor_active;
@@ -84,7 +85,9 @@ struct DevIn {
     const uint32_t *exact_id;
     const uint16_t *len[2];
     const uint64_t *tig_off[2];
-    const uint8_t *tig_arena;
+    const uint8_t *tig_arena;       // V..J bytes as the scoring kernels read them (device memory)
+    const uint8_t *tig_src;         // where k_pack_t2 reads them: == tig_arena, or the caller's pinned arena (zero-copy)
+    uint8_t *tig_copy;              // zero-copy only: k_pack_t2 mirrors the needed entries' bytes here (== tig_arena)
     const uint8_t *has_del[2];
     const uint16_t *cdr3_len[2];
     const uint64_t *cdr3_off[2];

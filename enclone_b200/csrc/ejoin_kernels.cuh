@@ -306,11 +306,42 @@ __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__re
     c3[m.c3off + W + w] = L & valid;
 }
 
+// 32 bytes at byte offset `off` of a shared-memory staging buffer (16-byte aligned base)
+__device__ __forceinline__ void load32s(const uint8_t *buf, uint32_t off, uint32_t (&out)[8]) {
+    const uint4 *q = (const uint4 *)(buf + (off & ~15u));
+    const uint4 v0 = q[0], v1 = q[1], v2 = q[2];
+    const uint32_t w[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+    const uint32_t sh = 8u * (off & 3);
+    switch ((off >> 2) & 3) {
+        case 0:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
+            break;
+        case 1:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i + 1], w[i + 2], sh);
+            break;
+        case 2:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i + 2], w[i + 3], sh);
+            break;
+        default:
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(w[i + 3], w[i + 4], sh);
+            break;
+    }
+}
+
 // [wm_lo, wm_hi): only the entries whose last V..J byte lies in this range of the caller's arena are
-// packed by this launch (the arena is uploaded in chunks; see upload_range).
+// packed by this launch (the arena is uploaded in chunks; see upload_range).  Each warp first copies
+// its entry's bytes into shared memory with non-overlapping aligned 16-byte loads — in zero-copy mode
+// in.tig_arena is the caller's pinned host buffer and these loads are the only PCIe traffic for the
+// V..J bytes, issued for needed entries only — and then every lane reduces its 32-base word from there.
+#define PACK_STAGE 544          // per chain: 512 bytes + alignment slack + the 48-byte window overrun
 __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
                                                  const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi) {
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint8_t stage[8][2][PACK_STAGE];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= (uint32_t)ctr->n_valid) return;
     if (!needed[s]) return;                       // no CDR3-compatible partner: its rows are never read
@@ -322,6 +353,28 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
         const unsigned long long last = e0 > e1 ? e0 : e1;
         if (!(last > wm_lo && last <= wm_hi)) return;
     }
+    // ---- stage both chains (chains longer than 512 bases are read in place)
+    uint32_t soff[2];
+    bool staged[2];
+    for (int c = 0; c < 2; c++) {
+        const int n = c ? n1 : n0;
+        const uint8_t *t = in.tig_src + in.tig_off[c][k];
+        const uintptr_t a = (uintptr_t)t;
+        soff[c] = (uint32_t)(a & 15);
+        staged[c] = n <= 512;
+        const int nchunks = ((int)soff[c] + n + 15) / 16;              // <= 33 when staged
+        const uint4 *src = (const uint4 *)(a & ~(uintptr_t)15);
+        // the mirror has the same 16-byte phase as the source, so chunk i lands at the same arena offset
+        uint4 *mir = in.tig_copy ? (uint4 *)(((uintptr_t)(in.tig_copy + in.tig_off[c][k])) & ~(uintptr_t)15) : nullptr;
+        if (staged[c]) {
+            uint4 *dst = (uint4 *)stage[wib][c];
+            for (int i = (int)lane; i < nchunks; i += 32) { const uint4 v = src[i]; dst[i] = v; if (mir) mir[i] = v; }
+        } else if (mir) {
+            for (int i = (int)lane; i < nchunks; i += 32) mir[i] = src[i];
+        }
+        if (lane == 0 && in.tig_copy) atomicAdd(&ctr->inplace_bytes[blockIdx.x & 31], 16ull * nchunks);
+    }
+    __syncwarp();
     const int nw0 = 4 * ((n0 + 127) / 128), nw = nw0 + 4 * ((n1 + 127) / 128);
     uint32_t *rows = (uint32_t *)(t2 + m.t2off);
     int mcount0 = 0, mcount1 = 0;
@@ -333,9 +386,9 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
         const int p0 = wl * 32;
         uint32_t H = 0, L = 0, M = 0;
         if (p0 < n) {
-            const uint8_t *t = in.tig_arena + in.tig_off[c][k];
             uint32_t x[8];
-            load32u(t + p0, x);
+            if (staged[c]) load32s(stage[wib][c], soff[c] + (uint32_t)p0, x);
+            else load32u(in.tig_src + in.tig_off[c][k] + p0, x);
             const int nb = n - p0;                            // valid bytes in this word (>= 1)
 #pragma unroll
             for (int i = 0; i < 8; i++) x[i] &= low_bytes(nb - 4 * i);

@@ -69,10 +69,21 @@ class SynthPack:
         return JoinPack.from_struct(self.struct)
 
 
-def generate(n_cells=10000, n_donors=1, is_bcr=True, mode=0, seed=20261019, copy=True, **kw):
+def pinned_allocator():
+    """(alloc, dealloc) function addresses of the CUDA library's pinned allocator: arenas generated with
+    them are page-locked, padded and flagged EJOIN_F_TIGS_IN_PLACE (the library reads them in place)."""
+    from . import _lib
+    L = _lib.load()
+    return dict(alloc=C.cast(L.ejoin_host_alloc, C.c_void_p).value, dealloc=C.cast(L.ejoin_host_free, C.c_void_p).value)
+
+
+def generate(n_cells=10000, n_donors=1, is_bcr=True, mode=0, seed=20261019, copy=True, pinned=False, **kw):
     """Generate a repertoire.  copy=True returns a numpy-backed JoinPack (+ truth family ids);
-    copy=False returns a SynthPack viewing the generator's own buffers (for big inputs)."""
+    copy=False returns a SynthPack viewing the generator's own buffers (for big inputs);
+    pinned=True (with copy=False) puts the arenas in pinned host memory."""
     lib = _load()
+    if pinned:
+        kw = dict(kw, **pinned_allocator())
     cfg = SynthCfg()
     lib.esynth_cfg_default(C.byref(cfg))
     cfg.seed, cfg.n_cells, cfg.n_donors, cfg.is_bcr, cfg.mode = seed, n_cells, n_donors, int(is_bcr), mode
@@ -104,7 +115,7 @@ CONFIGS = {
 }
 
 
-def generate_config(name, scale=1.0, copy=True):
+def generate_config(name, scale=1.0, copy=True, pinned=False):
     cfg = dict(CONFIGS[name])
     cfg["n_cells"] = max(16, int(cfg["n_cells"] * scale))
-    return generate(copy=copy, **cfg)
+    return generate(copy=copy, pinned=pinned, **cfg)

@@ -30,6 +30,11 @@ extern "C" {
 #define EJOIN_ABI_VERSION 1
 #define EJOIN_NONE 0xFFFFFFFFu   /* Option::None for u32 ids                      */
 #define EJOIN_NONE16 0xFFFFu     /* Option::None for u16 region bounds            */
+/* ejoin_pack_t.flags: tig_arena is pinned host memory the device can read (ejoin_host_alloc /
+ * ejoin_host_register), padded with >= 64 readable bytes after tig_arena_bytes: the library then
+ * reads the V..J bytes IN PLACE over PCIe, and only for the entries that have a CDR3-compatible
+ * partner (about half of a repertoire), instead of uploading the whole arena. */
+#define EJOIN_F_TIGS_IN_PLACE 1u
 
 /* error codes */
 #define EJOIN_OK 0
@@ -54,7 +59,7 @@ typedef struct ejoin_pack {
     uint32_t n_exact;            /* exact_clonotypes.len()                        */
     uint32_t n_refseq;           /* entries in the germline sequence table        */
     uint32_t is_bcr;             /* join_exacts(is_bcr, ..)                       */
-    uint32_t reserved0;
+    uint32_t flags;              /* EJOIN_F_*                                     */
 
     /* ---- per info entry ---- */
     const uint32_t *exact_id;    /* [n_info] CloneInfo.clonotype_id               */

@@ -9,10 +9,11 @@ use std::os::raw::{c_char, c_int, c_void};
 pub const EJOIN_ABI_VERSION: u32 = 1;
 pub const EJOIN_NONE: u32 = 0xFFFF_FFFF;
 pub const EJOIN_NONE16: u16 = 0xFFFF;
+pub const EJOIN_F_TIGS_IN_PLACE: u32 = 1;
 
 #[repr(C)]
 pub struct ejoin_pack_t {
-    pub abi_version: u32, pub n_info: u32, pub n_exact: u32, pub n_refseq: u32, pub is_bcr: u32, pub reserved0: u32,
+    pub abi_version: u32, pub n_info: u32, pub n_exact: u32, pub n_refseq: u32, pub is_bcr: u32, pub flags: u32,
     pub exact_id: *const u32,
     pub len: [*const u16; 2], pub tig_off: [*const u64; 2], pub tig_arena: *const u8, pub tig_arena_bytes: u64,
     pub has_del: [*const u8; 2], pub cdr3_len: [*const u16; 2], pub cdr3_off: [*const u64; 2], pub cdr3_arena: *const u8,

@@ -244,3 +244,24 @@ def test_unsupported_inputs_fail_loudly():
     with pytest.raises(EjoinError) as ei:
         join_exacts(good)
     assert ei.value.code == -1
+
+
+def test_zero_copy_in_place_arena(monkeypatch):
+    """Pinned, padded arenas flagged EJOIN_F_TIGS_IN_PLACE are read in place (only the needed entries
+    cross PCIe); the result must equal the uploaded-arena path and the oracle."""
+    import os
+    sp, _ = synth.generate(n_cells=60000, n_donors=3, seed=77, copy=False, pinned=True)
+    assert sp.struct.flags & 1
+    params = default_params()
+    j = Joiner(params)
+    g = j.run(sp.struct)
+    moved_in_place = g.stats["h2d_bytes"]
+    j.close()
+    oe, oc, _ = O.join_exacts(sp.struct, params, threads=os.cpu_count() or 1)
+    assert_same_join(g, oe, oc, what="zero-copy")
+    monkeypatch.setenv("EJOIN_NO_ZERO_COPY", "1")
+    j = Joiner(params)
+    g2 = j.run(sp.struct)
+    j.close()
+    assert np.array_equal(g.edges, g2.edges) and np.array_equal(g.class_of, g2.class_of)
+    assert moved_in_place < g2.stats["h2d_bytes"]          # fewer bytes crossed PCIe

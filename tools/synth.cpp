@@ -569,6 +569,8 @@ extern "C" int esynth_generate(const esynth_cfg_t *cfgp, ejoin_pack_t **out, uin
     ejoin_pack_t &pk = P->pk;
     memset(&pk, 0, sizeof(pk));
     pk.abi_version = EJOIN_ABI_VERSION; pk.n_info = n; pk.n_exact = nx; pk.n_refseq = nr; pk.is_bcr = cfg.is_bcr;
+    // arenas from a caller-supplied (pinned) allocator carry 64 bytes of padding: they may be read in place
+    pk.flags = cfg.alloc ? EJOIN_F_TIGS_IN_PLACE : 0;
     pk.exact_id = P->exact_id.data();
     for (int c = 0; c < 2; c++) {
         pk.len[c] = P->len[c].data(); pk.tig_off[c] = P->tig_off[c].data(); pk.has_del[c] = P->has_del[c].data();
