@@ -68,7 +68,7 @@ struct ejoin_handle {
     cudaStream_t st = nullptr, st_copy = nullptr;
     cudaEvent_t ev[8] = {};
     // overlapped upload: small arrays first, then the tig arena in chunks, each with an event
-    cudaEvent_t ev_copy0 = nullptr, ev_small = nullptr, ev_chunk[8] = {};
+    cudaEvent_t ev_copy0 = nullptr, ev_early = nullptr, ev_small = nullptr, ev_chunk[8] = {};
     int n_chunks = 0;
     uint64_t chunk_end[8] = {};     // arena byte offset (caller coordinates) up to which chunk i has landed
     bool copy_pending = false;
@@ -219,7 +219,7 @@ extern "C" int ejoin_create(ejoin_handle_t **out, const ejoin_params_t *p, int d
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
     for (auto &e : h->ev) CK(cudaEventCreate(&e));
-    CK(cudaEventCreate(&h->ev_copy0)); CK(cudaEventCreate(&h->ev_small));
+    CK(cudaEventCreate(&h->ev_copy0)); CK(cudaEventCreate(&h->ev_small)); CK(cudaEventCreate(&h->ev_early));
     for (auto &e : h->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventDestroy(h->ev_chunk[7])); CK(cudaEventCreate(&h->ev_chunk[7]));
     CK(h->d_counters.ensure(sizeof(DevCounters)));
@@ -250,6 +250,7 @@ extern "C" void ejoin_destroy(ejoin_handle_t *h) {
     for (auto &e : h->ev_chunk) if (e) cudaEventDestroy(e);
     if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
     if (h->ev_small) cudaEventDestroy(h->ev_small);
+    if (h->ev_early) cudaEventDestroy(h->ev_early);
     if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
@@ -341,13 +342,20 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     // the copy stream must not run ahead of the previous run's kernels that still read the old input
     CK(cudaStreamSynchronize(h->st));
     CK(cudaEventRecord(h->ev_copy0, h->st_copy));
+    // early set: what the keys, the sort, the c3 rows and the sweep read
     CK(up(d.exact_id, pk->exact_id + lo, n));
+    CK(up(d.nchains, pk->nchains, pk->n_exact));
     for (int c = 0; c < 2; c++) {
         CK(up(d.len[c], pk->len[c] + lo, n));
-        CK(up(d.tig_off[c], pk->tig_off[c] + lo, n));
-        CK(up(d.has_del[c], pk->has_del[c] + lo, n));
         CK(up(d.cdr3_len[c], pk->cdr3_len[c] + lo, n));
         CK(up(d.cdr3_off[c], pk->cdr3_off[c] + lo, n));
+    }
+    CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
+    CK(cudaEventRecord(h->ev_early, h->st_copy));
+    // late set: what k_meta and the scoring read; goes up while the sweep runs
+    for (int c = 0; c < 2; c++) {
+        CK(up(d.tig_off[c], pk->tig_off[c] + lo, n));
+        CK(up(d.has_del[c], pk->has_del[c] + lo, n));
         CK(up(d.cdr3_start[c], pk->cdr3_start[c] + lo, n));
         CK(up(d.v_ref_id[c], pk->v_ref_id[c] + lo, n));
         CK(up(d.j_ref_id[c], pk->j_ref_id[c] + lo, n));
@@ -362,10 +370,9 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     CK(up(d.hcomp, pk->hcomp + lo, n));
     CK(up(d.fr1, pk->fr1_start + lo, n)); CK(up(d.cdr1, pk->cdr1_start + lo, n)); CK(up(d.fr2, pk->fr2_start + lo, n));
     CK(up(d.cdr2, pk->cdr2_start + lo, n)); CK(up(d.fr3, pk->fr3_start + lo, n));
-    CK(up(d.nchains, pk->nchains, pk->n_exact)); CK(up(d.ncells, pk->ncells, pk->n_exact));
+    CK(up(d.ncells, pk->ncells, pk->n_exact));
     CK(up(d.donor_lo, pk->donor_lo, pk->n_exact)); CK(up(d.donor_hi, pk->donor_hi, pk->n_exact));
     CK(up(d.refseq_off, pk->refseq_off, pk->n_refseq)); CK(up(d.refseq_len, pk->refseq_len, pk->n_refseq));
-    CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
     CK(up(d.refseq_arena, pk->refseq_arena, pk->refseq_arena_bytes));
     CK(cudaEventRecord(h->ev_small, h->st_copy));       // everything but the V..J bytes: keys / sort / groups / meta / c3 can start
     h->tigs_in_place = in_place;
@@ -549,7 +556,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         const unsigned nb256 = (n + 255) / 256;
         cudaStream_t st = h->st;
 
-        if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));
+        if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_early, 0));
         CK(cudaEventRecord(h->ev[0], st));
         CK(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), st));
         CK(cudaMemsetAsync(h->d_presL.p, 0, 8192 / 8, st));
@@ -577,8 +584,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t2sizes, t2off, (int)n, st);
         h->launches += 2;                           // own kernels only; CUB's sort/RLE/scan launches are not counted
         CK(cudaEventRecord(h->ev[1], st));
-        k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, pr.ref_v_trim, pr.ref_j_trim);
-        k_pack_c3<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, meta, ctr, c3);
+        k_pack_c3<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, perm, gid, groups, ctr, c3);
         // stride mode: the gathered edges of the other ranks need this rank's rows too -> pack every entry
         k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, surv_cnt, needed, force, n, stride > 1 ? 1 : 0);
         CK(cudaEventRecord(h->ev[2], st));
@@ -588,6 +594,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (rows_occ < 1) rows_occ = 1;
         k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, cand, ccap, firstk, surv_cnt, needed, stride, phase);
         CK(cudaEventRecord(h->ev[3], st));
+        if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)
+        k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, needed, pr.ref_v_trim, pr.ref_j_trim);
         if (h->copy_pending && h->n_chunks > 0) {
             // pack each chunk's (needed) entries as its bytes land (an entry belongs to the chunk that completes it)
             uint64_t prev = 0;

@@ -233,9 +233,11 @@ __device__ __forceinline__ uint32_t neq32(const uint32_t (&x)[8], const uint32_t
 
 __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ gid_incl,
                                               const GroupInfo *__restrict__ groups, const uint32_t *__restrict__ t2off, DevCounters *ctr,
-                                              EntryMeta *__restrict__ meta, uint32_t *__restrict__ k_to_s, int ref_v_trim, int ref_j_trim) {
+                                              EntryMeta *__restrict__ meta, uint32_t *__restrict__ k_to_s, const uint8_t *__restrict__ needed,
+                                              int ref_v_trim, int ref_j_trim) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (uint32_t)ctr->n_valid) return;
+    if (!needed[s]) return;                       // never scored: no record needed
     const uint32_t k = perm[s];
     const GroupInfo g = groups[gid_incl[s] - 1];
     EntryMeta m;
@@ -268,16 +270,19 @@ __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restri
 }
 
 // one thread per (entry, c3 word); 8 threads per entry, W of them active.  The 32 bases of a word
-// come from chain 0's CDR3, chain 1's, or both (the word that straddles the boundary).
-__global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__restrict__ meta, DevCounters *ctr, uint32_t *__restrict__ c3) {
+// come from chain 0's CDR3, chain 1's, or both (the word that straddles the boundary).  Reads only the
+// early-uploaded arrays (CDR3 strings and lengths), so it runs before the rest of the input has landed.
+__global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ gid_incl,
+                                                 const GroupInfo *__restrict__ groups, DevCounters *ctr, uint32_t *__restrict__ c3) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t s = t >> 3, w = t & 7;
     if (s >= (uint32_t)ctr->n_valid) return;
-    const EntryMeta &m = meta[s];
-    const int cl0 = m.cl[0], total = cl0 + m.cl[1];
-    const int W = max(1, (total + 31) / 32);
+    const uint32_t k = perm[s];
+    const GroupInfo g = groups[gid_incl[s] - 1];
+    const int cl0 = in.cdr3_len[0][k], total = cl0 + in.cdr3_len[1][k];
+    const int W = g.W;
     if ((int)w >= W) return;
-    const uint32_t k = m.k;
+    const uint32_t c3off = g.c3base + (s - g.start) * 2 * W;
     const int p0 = 32 * (int)w;
     const int nb = total - p0;                                 // valid bytes in this word
     uint32_t x[8];
@@ -302,8 +307,8 @@ __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const EntryMeta *__re
     uint32_t H, L;
     planes32(x, H, L);
     const uint32_t valid = low_bits(nb);
-    c3[m.c3off + w] = H & valid;
-    c3[m.c3off + W + w] = L & valid;
+    c3[c3off + w] = H & valid;
+    c3[c3off + W + w] = L & valid;
 }
 
 // 32 bytes at byte offset `off` of a shared-memory staging buffer (16-byte aligned base)
