@@ -237,8 +237,11 @@ __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restri
                                               int ref_v_trim, int ref_j_trim) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (uint32_t)ctr->n_valid) return;
-    if (!needed[s]) return;                       // never scored: no record needed
     const uint32_t k = perm[s];
+    // input validation for every entry, scored or not
+    if (in.vs_seq[0][k] >= in.n_refseq || in.js_seq[0][k] >= in.n_refseq || in.vs_seq[1][k] >= in.n_refseq || in.js_seq[1][k] >= in.n_refseq)
+        atomicOr(&ctr->err, ERR_BAD_REFSEQ);
+    if (!needed[s]) return;                       // never scored: no record needed
     const GroupInfo g = groups[gid_incl[s] - 1];
     EntryMeta m;
     memset(&m, 0, sizeof(m));
