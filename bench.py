@@ -223,7 +223,8 @@ def main():
     # ---------------- value: inputs resident in HBM ----------------
     if world == 1:
         j.upload(sp.struct)
-    # (N > 1: run_shard left this rank's shard resident)
+    else:
+        j.upload_shard(sp.struct, rank, world)        # this rank's bucket range, resident in HBM
     for _ in range(W):
         st = j.run_resident()
     barrier()

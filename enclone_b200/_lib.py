@@ -11,7 +11,7 @@ SO_PATH = os.path.join(_HERE, "libenclone_join.so")
 # every symbol include/enclone_join.h declares
 EXPORTS = [
     "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
-    "ejoin_plan_shards", "ejoin_run_shard", "ejoin_run_shard_final", "ejoin_partition_gpu", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_run_resident",
+    "ejoin_plan_shards", "ejoin_run_shard", "ejoin_run_shard_final", "ejoin_partition_gpu", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_upload_shard", "ejoin_run_resident",
     "ejoin_host_alloc", "ejoin_host_free", "ejoin_host_register", "ejoin_host_unregister", "ejoin_p1", "ejoin_partition",
 ]
 
@@ -59,6 +59,8 @@ def load():
     L.ejoin_finish.restype = C.c_int
     L.ejoin_upload.argtypes = [H, C.POINTER(EjoinPack)]
     L.ejoin_upload.restype = C.c_int
+    L.ejoin_upload_shard.argtypes = [H, C.POINTER(EjoinPack), C.c_int, C.c_int]
+    L.ejoin_upload_shard.restype = C.c_int
     L.ejoin_run_resident.argtypes = [H, C.POINTER(EjoinStats)]
     L.ejoin_run_resident.restype = C.c_int
     L.ejoin_host_alloc.argtypes = [C.c_size_t]

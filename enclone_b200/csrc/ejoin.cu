@@ -874,6 +874,21 @@ extern "C" int ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pk) {
     return 0;
 }
 
+static bool shard_range(const ejoin_pack_t *pk, int rank, int world, uint32_t *lo_out, uint32_t *hi_out);
+
+extern "C" int ejoin_upload_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int rank, int world) {
+    if (!h || !pk || rank < 0 || rank >= world) return EJOIN_E_ARG;
+    uint32_t lo, hi;
+    const bool stride_mode = shard_range(pk, rank, world, &lo, &hi);
+    int rc = upload_range(h, pk, lo, hi, /*allow_in_place=*/false);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->st_copy));
+    h->copy_pending = false;
+    h->last_stride = stride_mode ? (uint32_t)world : 1u; h->last_phase = stride_mode ? (uint32_t)rank : 0u;
+    h->is_bcr = (int)pk->is_bcr;
+    return 0;
+}
+
 extern "C" int ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats) {
     if (!h) return EJOIN_E_ARG;
     h->launches = 0;
@@ -937,31 +952,61 @@ extern "C" void ejoin_result_free(ejoin_result_t *r) {
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU decomposition: contiguous, cost-balanced bucket ranges.
 // ---------------------------------------------------------------------------------------------
-extern "C" int ejoin_plan_shards(const ejoin_pack_t *pk, int world, uint32_t *owner, uint32_t *bstart, uint32_t cap, uint32_t *nb_out) {
-    if (!pk || world < 1 || !nb_out) return EJOIN_E_ARG;
-    std::vector<uint32_t> bs;
+// bucket starts (runs of equal lens) and their contiguous, cost-balanced owners; one pass over the lens arrays
+static void plan_buckets(const ejoin_pack_t *pk, int world, std::vector<uint32_t> &bs, std::vector<uint32_t> &owner) {
+    bs.clear();
+    const uint16_t *l0 = pk->len[0], *l1 = pk->len[1];
     for (uint32_t k = 0; k < pk->n_info; k++)
-        if (k == 0 || pk->len[0][k] != pk->len[0][k - 1] || pk->len[1][k] != pk->len[1][k - 1]) bs.push_back(k);
+        if (k == 0 || l0[k] != l0[k - 1] || l1[k] != l1[k - 1]) bs.push_back(k);
     const uint32_t nb = (uint32_t)bs.size();
     bs.push_back(pk->n_info);
-    *nb_out = nb;
-    if (!owner || !bstart) return 0;
-    if (cap < nb) return EJOIN_E_ARG;
+    owner.assign(nb, 0);
     // cost = candidate pairs + a linear term for packing; contiguous split at equal prefix cost
-    std::vector<double> cost(nb);
     double total = 0;
-    for (uint32_t b = 0; b < nb; b++) { double m = bs[b + 1] - bs[b]; cost[b] = m * (m - 1) / 2 + 64.0 * m; total += cost[b]; }
+    for (uint32_t b = 0; b < nb; b++) { double m = bs[b + 1] - bs[b]; total += m * (m - 1) / 2 + 64.0 * m; }
     double acc = 0;
     int r = 0;
     for (uint32_t b = 0; b < nb; b++) {
+        const double m = bs[b + 1] - bs[b], cost = m * (m - 1) / 2 + 64.0 * m;
         // move to the next rank when this bucket's midpoint passes the rank's boundary
-        while (r < world - 1 && acc + cost[b] / 2 > total * (r + 1) / world) r++;
+        while (r < world - 1 && acc + cost / 2 > total * (r + 1) / world) r++;
         owner[b] = (uint32_t)r;
-        acc += cost[b];
-        bstart[b] = bs[b];
+        acc += cost;
     }
-    bstart[nb] = pk->n_info;
+}
+
+extern "C" int ejoin_plan_shards(const ejoin_pack_t *pk, int world, uint32_t *owner, uint32_t *bstart, uint32_t cap, uint32_t *nb_out) {
+    if (!pk || world < 1 || !nb_out) return EJOIN_E_ARG;
+    std::vector<uint32_t> bs, own;
+    plan_buckets(pk, world, bs, own);
+    const uint32_t nb = (uint32_t)own.size();
+    *nb_out = nb;
+    if (!owner || !bstart) return 0;
+    if (cap < nb) return EJOIN_E_ARG;
+    memcpy(owner, own.data(), sizeof(uint32_t) * nb);
+    memcpy(bstart, bs.data(), sizeof(uint32_t) * (nb + 1));
     return 0;
+}
+
+// this rank's share: a contiguous entry range [lo,hi), or (stride mode) everything and every world-th tile row
+static bool shard_range(const ejoin_pack_t *pk, int rank, int world, uint32_t *lo_out, uint32_t *hi_out) {
+    std::vector<uint32_t> owner, bstart;
+    plan_buckets(pk, world, bstart, owner);
+    const uint32_t nb = (uint32_t)owner.size();
+    // giant-bucket case: if one bucket holds most of the work, every rank takes all entries and
+    // an interleaved share of the tile rows instead (stride mode)
+    double total = 0, biggest = 0;
+    for (uint32_t b = 0; b < nb; b++) { double m = bstart[b + 1] - bstart[b]; double c = m * (m - 1) / 2; total += c; biggest = std::max(biggest, c); }
+    const bool stride_mode = world > 1 && biggest > 1.25 * total / world;
+    uint32_t lo = 0, hi = pk->n_info;
+    if (!stride_mode && world > 1) {
+        lo = hi = 0;
+        bool any = false;
+        for (uint32_t b = 0; b < nb; b++)
+            if ((int)owner[b] == rank) { if (!any) { lo = bstart[b]; any = true; } hi = bstart[b + 1]; }
+    }
+    *lo_out = lo; *hi_out = hi;
+    return stride_mode;
 }
 
 static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int world, int want_final, int *mode_out, ejoin_result_t *final,
@@ -971,23 +1016,9 @@ static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int
     memset(&h->stats, 0, sizeof(h->stats));
     h->launches = 0;
     const double t0 = now_ms();
-    uint32_t nb = 0;
-    ejoin_plan_shards(pk, world, nullptr, nullptr, 0, &nb);
-    std::vector<uint32_t> owner(nb + 1), bstart(nb + 2);
-    ejoin_plan_shards(pk, world, owner.data(), bstart.data(), nb, &nb);
-    // giant-bucket case: if one bucket holds most of the work, every rank takes all entries and
-    // an interleaved share of the tile rows instead (stride mode)
-    double total = 0, biggest = 0;
-    for (uint32_t b = 0; b < nb; b++) { double m = bstart[b + 1] - bstart[b]; double c = m * (m - 1) / 2; total += c; biggest = std::max(biggest, c); }
-    const bool stride_mode = world > 1 && biggest > 1.25 * total / world;
+    uint32_t lo, hi;
+    const bool stride_mode = shard_range(pk, rank, world, &lo, &hi);
     if (mode_out) *mode_out = stride_mode ? 1 : 0;
-    uint32_t lo = 0, hi = pk->n_info;
-    if (!stride_mode && world > 1) {
-        lo = hi = 0;
-        bool any = false;
-        for (uint32_t b = 0; b < nb; b++)
-            if ((int)owner[b] == rank) { if (!any) { lo = bstart[b]; any = true; } hi = bstart[b + 1]; }
-    }
     int rc = upload_range(h, pk, lo, hi);
     if (rc) return rc;
     h->is_bcr = (int)pk->is_bcr;

@@ -121,6 +121,9 @@ class Joiner:
     def upload(self, pack_struct):
         self._check(self.L.ejoin_upload(self.h, C.byref(pack_struct)))
 
+    def upload_shard(self, pack_struct, rank, world):
+        self._check(self.L.ejoin_upload_shard(self.h, C.byref(pack_struct), rank, world))
+
     def run_resident(self):
         st = EjoinStats()
         self._check(self.L.ejoin_run_resident(self.h, C.byref(st)))

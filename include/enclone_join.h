@@ -227,6 +227,7 @@ int  ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pack, const uint
 /* Device-resident variant used to time the device side alone: upload once, then
  * ejoin_run_resident() repeats pack+score+compact+union-find on the resident input. */
 int  ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pack);
+int  ejoin_upload_shard(ejoin_handle_t *h, const ejoin_pack_t *pack, int rank, int world_size);   /* this rank's share, as ejoin_run_shard* would take it */
 int  ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats);
 
 /* Pinned host memory for the caller's flat buffers (so H2D runs at link speed). */

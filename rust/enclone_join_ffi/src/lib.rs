@@ -82,6 +82,7 @@ extern "C" {
     pub fn ejoin_partition_gpu(h: *mut c_void, pack: *const ejoin_pack_t, k1: *const u32, k2: *const u32, n: u64, class_of: *mut u32,
                                n_classes: *mut u32) -> c_int;
     pub fn ejoin_upload(h: *mut c_void, pack: *const ejoin_pack_t) -> c_int;
+    pub fn ejoin_upload_shard(h: *mut c_void, pack: *const ejoin_pack_t, rank: c_int, world: c_int) -> c_int;
     pub fn ejoin_run_resident(h: *mut c_void, stats: *mut ejoin_stats_t) -> c_int;
     pub fn ejoin_host_alloc(bytes: usize) -> *mut c_void;
     pub fn ejoin_host_free(p: *mut c_void);
