@@ -67,6 +67,11 @@ struct ejoin_handle {
     std::string err;
     cudaStream_t st = nullptr, st_copy = nullptr;
     cudaEvent_t ev[8] = {};
+    // EJOIN_DEBUG: per-kernel marks (events created on first use) printed after each pipeline run
+    bool debug = false;
+    std::vector<cudaEvent_t> mark_ev;
+    std::vector<const char *> mark_name;
+    size_t n_marks = 0;
     // overlapped upload: small arrays first, then the tig arena in chunks, each with an event
     cudaEvent_t ev_copy0 = nullptr, ev_early = nullptr, ev_small = nullptr, ev_chunk[8] = {};
     int n_chunks = 0;
@@ -480,6 +485,24 @@ int prepare_tables(ejoin_handle *h, int is_bcr) {
     return 0;
 }
 
+static void mark(ejoin_handle *h, const char *name) {
+    if (!h->debug) return;
+    if (h->n_marks == h->mark_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); h->mark_ev.push_back(e); h->mark_name.push_back(name); }
+    h->mark_name[h->n_marks] = name;
+    cudaEventRecord(h->mark_ev[h->n_marks++], h->st);
+}
+static void print_marks(ejoin_handle *h) {
+    if (!h->debug || h->n_marks < 2) return;
+    const DevCounters &k = h->counters;
+    fprintf(stderr, "[ejoin] n=%u cand=%llu rest=%llu todo_r1=%llu todo_r2=%llu accept_r1=%llu accept=%llu pending=%u generic=%llu tier2_pairs=%llu kept=%llu\n", h->n,
+            k.n_cand, k.n_rest, k.n_todo_r1, k.n_todo, k.n_accept_r1, k.n_accept, k.n_pending, k.n_generic, k.pairs_tier2, k.n_kept);
+    for (size_t i = 1; i < h->n_marks; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->mark_ev[i - 1], h->mark_ev[i]);
+        fprintf(stderr, "[ejoin]   %-28s %8.3f ms\n", h->mark_name[i], ms);
+    }
+}
+
 // The device pipeline on the resident input: keys -> sort -> groups -> pack -> tier 1 ->
 // tier 2 -> prune -> sort of the kept edges.  Ends with the counters on the host.
 int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase) {
@@ -557,7 +580,9 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cudaStream_t st = h->st;
 
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_early, 0));
+        h->debug = getenv("EJOIN_DEBUG") != nullptr; h->n_marks = 0;
         CK(cudaEventRecord(h->ev[0], st));
+        mark(h, "start");
         CK(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), st));
         CK(cudaMemsetAsync(h->d_presL.p, 0, 8192 / 8, st));
         CK(cudaMemsetAsync(h->d_presC.p, 0, 65536 / 8, st));
@@ -570,11 +595,14 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         int rc = prepare_tables(h, is_bcr);         // one sync; cached after the first run
         if (rc) return rc;
         const DevCounters first = h->counters;
+        mark(h, "keys (+tables first run)");
         tb = cub_bytes;
         cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys, keys_out, vals, perm, (int)n, 0, 64, st);
+        mark(h, "sort entries");
         tb = cub_bytes;
         cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
         k_group_scan<<<1, 1024, 0, st>>>(uniq, counts, num_runs, groups, (const uint16_t *)h->d_cdmax.p, ctr);
+        mark(h, "rle + k_group_scan");
         k_sorted_heads<<<nb256, 256, 0, st>>>(keys_out, n, t2sizes);          // t2sizes doubles as the flag buffer
         tb = cub_bytes;
         cub::DeviceScan::InclusiveSum(cub_tmp, tb, t2sizes, gid, (int)n, st);
@@ -584,18 +612,22 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t2sizes, t2off, (int)n, st);
         h->launches += 2;                           // own kernels only; CUB's sort/RLE/scan launches are not counted
         CK(cudaEventRecord(h->ev[1], st));
+        mark(h, "heads/scans/t2 sizes");
         k_pack_c3<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, perm, gid, groups, ctr, c3);
         // stride mode: the gathered edges of the other ranks need this rank's rows too -> pack every entry
         k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, surv_cnt, needed, force, n, stride > 1 ? 1 : 0);
         CK(cudaEventRecord(h->ev[2], st));
+        mark(h, "k_pack_c3 + k_init_rows");
         // tier 1: needs only the c3 rows, so it runs while the V..J arena is still on its way
         int rows_occ = 8;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_occ, k_sweep, T1_TILE, 0);
         if (rows_occ < 1) rows_occ = 1;
         k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, cand, ccap, firstk, surv_cnt, needed, stride, phase);
         CK(cudaEventRecord(h->ev[3], st));
+        mark(h, "k_sweep");
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)
         k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, needed, pr.ref_v_trim, pr.ref_j_trim);
+        mark(h, "k_meta");
         if (h->copy_pending && h->n_chunks > 0) {
             // pack each chunk's (needed) entries as its bytes land (an entry belongs to the chunk that completes it)
             uint64_t prev = 0;
@@ -609,27 +641,37 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, 0ull, ~0ull);
         }
         CK(cudaEventRecord(h->ev[6], st));
+        mark(h, "k_pack_t2");
         DevTables tbs;
         tbs.meta = meta; tbs.c3 = c3; tbs.t2 = t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
         tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p;
         tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
         k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, firstk, surv_cnt, force, parent, f0_key, f0_val, cand, ccap, pending);
+        mark(h, "k_phase_a");
         k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, firstk, surv_cnt, force, parent, f0_key, f0_val, cand, ccap, pending);
+        mark(h, "k_phase_a_pending");
         h->launches += 8;
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
         k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, ccap);
+        mark(h, "k_phaseb_split");
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, parent);
+        mark(h, "k_tier2 r1");
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, parent, 0);
+        mark(h, "k_tier2_generic r1");
         k_forced_resolve<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, f0_key, f0_val);
         for (int it = 0; it < 10; it++) k_root_jump<<<nb256, 256, 0, st>>>(parent, n);      // 4 hops each: covers chains up to 4^10
+        mark(h, "resolve + root jumps");
         // round 2: the other recorded survivors, scored only across trees
         k_round2_begin<<<1, 1, 0, st>>>(ctr);
         k_forced_prune<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent);
         k_phaseb_cross<<<h->sm_count * 8, 256, 0, st>>>(rest, ccap, parent, ctr, todo, cap);
+        mark(h, "round2 begin/prune/cross");
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, nullptr);
+        mark(h, "k_tier2 r2");
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, nullptr, 1);
         CK(cudaEventRecord(h->ev[4], st));
+        mark(h, "k_tier2_generic r2");
         const bool device_final = stride == 1;      // stride mode: the forest needs every rank's edges -> host replay after the gather
         h->device_final = device_final;
         if (device_final) {
@@ -644,6 +686,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        mark(h, "boruvka");
         CK(cudaStreamSynchronize(st));
         h->counters.pairs_candidate = first.pairs_candidate; h->counters.n_buckets = first.n_buckets;
         if (h->counters.err & ERR_CDR3_BAD_CHAR) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 contains a character outside ACGT");
@@ -678,6 +721,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h->counters.n_kept, &ctr->n_kept, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        mark(h, "comp size + collect");
         CK(cudaStreamSynchronize(st));
         const unsigned long long nk = h->counters.n_kept;
         const unsigned long long nsorted = (unsigned long long)n + std::min<unsigned long long>(h->counters.n_accept, cap);
@@ -687,7 +731,9 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nsorted, 0, 64, st);
         }
         CK(cudaEventRecord(h->ev[5], st));
+        mark(h, "sort edges");
         CK(cudaStreamSynchronize(st));
+        print_marks(h);
         float ms;
         float ms2;
         cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); cudaEventElapsedTime(&ms2, h->ev[3], h->ev[6]); h->stats.ms_kernel_pack = ms + ms2;   // meta + c3, then t2 rows

@@ -643,54 +643,89 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
 // `todo` (all scored in round 1); the others are kept, compacted, in `rest` unless they visibly hang
 // off the same phase-A parent (same tree: never a forest edge).  Pass 2 (after round 1 and the pointer
 // doubling) keeps from `rest` the pairs whose endpoints lie in different trees.
+// Block-level compaction for the list filters below: every thread brings up to SPLIT_ITEMS flagged items for each of
+// two output lists; one atomicAdd per list and block tile reserves the slots (a per-warp atomic on one counter was the
+// whole cost of these kernels: ~1M same-address atomics per launch).
+#define SPLIT_ITEMS 4
+struct SplitSmem { uint32_t w1[8], w2[8]; unsigned long long base1, base2; };
+__device__ __forceinline__ void block_reserve2(SplitSmem &sm, uint32_t c1, uint32_t c2, unsigned long long *ctr1, unsigned long long *ctr2,
+                                               unsigned long long &o1, unsigned long long &o2) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t i1 = c1, i2 = c2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v1 = __shfl_up_sync(0xFFFFFFFFu, i1, o), v2 = __shfl_up_sync(0xFFFFFFFFu, i2, o);
+        if (lane >= (uint32_t)o) { i1 += v1; i2 += v2; }
+    }
+    if (lane == 31) { sm.w1[warp] = i1; sm.w2[warp] = i2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t1 = 0, t2 = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t a = sm.w1[w], b = sm.w2[w]; sm.w1[w] = t1; sm.w2[w] = t2; t1 += a; t2 += b; }
+        sm.base1 = t1 ? atomicAdd(ctr1, (unsigned long long)t1) : 0ull;
+        sm.base2 = (t2 && ctr2) ? atomicAdd(ctr2, (unsigned long long)t2) : 0ull;
+    }
+    __syncthreads();
+    o1 = sm.base1 + sm.w1[warp] + (i1 - c1);
+    o2 = sm.base2 + sm.w2[warp] + (i2 - c2);
+    __syncthreads();                                  // sm is reused by the next tile
+}
+
 __global__ void __launch_bounds__(256) k_phaseb_split(const uint2 *__restrict__ cand, unsigned long long cand_cap, const uint32_t *__restrict__ parent,
                                                       const uint8_t *__restrict__ force_b, DevCounters *ctr, uint2 *__restrict__ todo,
                                                       unsigned long long todo_cap, uint2 *__restrict__ rest, unsigned long long rest_cap) {
+    __shared__ SplitSmem sm;
     unsigned long long ncand = ctr->n_cand;
     if (ncand > cand_cap) ncand = cand_cap;
-    const uint32_t lane = threadIdx.x & 31;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((ncand + 31) & ~31ull);
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        bool k1 = false, k2 = false;
-        uint2 c = make_uint2(0, 0);
-        if (i < ncand) {
-            c = cand[i];
-            const bool fbit = c.x >> 31;
-            c.x &= 0x7FFFFFFFu;
-            if (fbit || force_b[c.y]) k1 = true;
-            else k2 = parent[c.x] != parent[c.y] && parent[c.y] != c.x;
+    const unsigned long long tile = 256ull * SPLIT_ITEMS;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < ncand; t0 += (unsigned long long)gridDim.x * tile) {
+        uint2 c[SPLIT_ITEMS];
+        uint32_t k1 = 0, k2 = 0;                      // bit j: item j goes to todo / rest
+#pragma unroll
+        for (int j = 0; j < SPLIT_ITEMS; j++) {
+            const unsigned long long i = t0 + (unsigned long long)j * 256 + threadIdx.x;
+            c[j] = make_uint2(0, 0);
+            if (i < ncand) {
+                c[j] = cand[i];
+                const bool fbit = c[j].x >> 31;
+                c[j].x &= 0x7FFFFFFFu;
+                if (fbit || force_b[c[j].y]) k1 |= 1u << j;
+                else {
+                    const uint32_t pa = parent[c[j].x], pb = parent[c[j].y];
+                    if (pa != pb && pb != c[j].x) k2 |= 1u << j;
+                }
+            }
         }
-        const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, k1), m2 = __ballot_sync(0xFFFFFFFFu, k2);
-        if (m1) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->n_todo, (unsigned long long)__popc(m1));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(m1 & ((1u << lane) - 1u));
-            if (k1 && base < todo_cap) todo[base] = c;
-        }
-        if (m2) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->n_rest, (unsigned long long)__popc(m2));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(m2 & ((1u << lane) - 1u));
-            if (k2 && base < rest_cap) rest[base] = c;
+        unsigned long long o1, o2;
+        block_reserve2(sm, __popc(k1), __popc(k2), &ctr->n_todo, &ctr->n_rest, o1, o2);
+#pragma unroll
+        for (int j = 0; j < SPLIT_ITEMS; j++) {
+            if ((k1 >> j) & 1u) { if (o1 < todo_cap) todo[o1] = c[j]; o1++; }
+            if ((k2 >> j) & 1u) { if (o2 < rest_cap) rest[o2] = c[j]; o2++; }
         }
     }
 }
 __global__ void __launch_bounds__(256) k_phaseb_cross(const uint2 *__restrict__ rest, unsigned long long rest_cap, const uint32_t *__restrict__ root,
                                                       DevCounters *ctr, uint2 *__restrict__ todo, unsigned long long todo_cap) {
+    __shared__ SplitSmem sm;
     unsigned long long n = ctr->n_rest;
     if (n > rest_cap) n = rest_cap;
-    const uint32_t lane = threadIdx.x & 31;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ull);
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        bool keep = false;
-        uint2 c = make_uint2(0, 0);
-        if (i < n) { c = rest[i]; keep = root[c.x] != root[c.y]; }
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
-        if (!mask) continue;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->n_todo, (unsigned long long)__popc(mask));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0) + __popc(mask & ((1u << lane) - 1u));
-        if (keep && base < todo_cap) todo[base] = c;
+    const unsigned long long tile = 256ull * SPLIT_ITEMS;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < n; t0 += (unsigned long long)gridDim.x * tile) {
+        uint2 c[SPLIT_ITEMS];
+        uint32_t k1 = 0;
+#pragma unroll
+        for (int j = 0; j < SPLIT_ITEMS; j++) {
+            const unsigned long long i = t0 + (unsigned long long)j * 256 + threadIdx.x;
+            c[j] = make_uint2(0, 0);
+            if (i < n) { c[j] = rest[i]; if (root[c[j].x] != root[c[j].y]) k1 |= 1u << j; }
+        }
+        unsigned long long o1, o2;
+        block_reserve2(sm, __popc(k1), 0, &ctr->n_todo, nullptr, o1, o2);
+#pragma unroll
+        for (int j = 0; j < SPLIT_ITEMS; j++)
+            if ((k1 >> j) & 1u) { if (o1 < todo_cap) todo[o1] = c[j]; o1++; }
     }
 }
 
@@ -1110,10 +1145,25 @@ struct SweepCtx {
     uint8_t *needed;       // [n]
 };
 
+#define SWEEP_STAGE 256u       // survivor pairs staged per warp
+__device__ __forceinline__ void sweep_flush(SweepCtx &cx, uint2 *stage, uint32_t &fill) {
+    const uint32_t lane = threadIdx.x & 31;
+    __syncwarp();
+    if (fill) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&cx.ctr->n_cand, (unsigned long long)fill);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t i = lane; i < fill; i += 32)
+            if (base + i < cx.cand_cap) cx.cand[base + i] = stage[i];
+    }
+    __syncwarp();
+    fill = 0;
+}
+
 template <int W>
 __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
                                           const uint32_t (&bH)[W], const uint32_t (&bL)[W], bool validB, uint32_t posA0, uint32_t posB,
-                                          uint32_t &mycnt) {
+                                          uint32_t &mycnt, uint2 *stage, uint32_t &fill) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (!__any_sync(0xFFFFFFFFu, validB)) return;          // a warp beyond the end of a short B tile
     for (uint32_t a0 = 0; a0 < rowsA; a0 += 32) {
@@ -1144,21 +1194,33 @@ __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restri
             cx.firstk[(size_t)posB * PHASE_A_K + mycnt] = posA0 + a0 + aa;
             mycnt++;
         }
-        // the rest: the global survivor list
+        // the rest: the global survivor list, through the warp's staging buffer (one atomic per SWEEP_STAGE pairs
+        // and coalesced stores, instead of one same-address atomic per 32x32 block)
         if (__any_sync(0xFFFFFFFFu, bits != 0)) {
             uint32_t cntl = __popc(bits), incl = cntl;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
             const uint32_t totalc = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&cx.ctr->n_cand, (unsigned long long)totalc);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cntl);
             mycnt += cntl;
-            while (bits) {
-                const uint32_t aa = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (base < cx.cand_cap) cx.cand[base] = make_uint2(posA0 + a0 + aa, posB);
-                base++;
+            if (totalc > SWEEP_STAGE) {               // a dense block: straight to the list
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&cx.ctr->n_cand, (unsigned long long)totalc);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cntl);
+                while (bits) {
+                    const uint32_t aa = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (base < cx.cand_cap) cx.cand[base] = make_uint2(posA0 + a0 + aa, posB);
+                    base++;
+                }
+            } else {
+                if (fill + totalc > SWEEP_STAGE) sweep_flush(cx, stage, fill);
+                uint32_t o = fill + (incl - cntl);
+                while (bits) {
+                    const uint32_t aa = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    stage[o++] = make_uint2(posA0 + a0 + aa, posB);
+                }
+                fill += totalc;
             }
         }
     }
@@ -1166,7 +1228,7 @@ __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restri
 
 template <int W>
 __device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint32_t ib, const uint32_t *__restrict__ c3, uint32_t (*sA)[T1_TILE * 2 * T1_WMAX],
-                                         uint64_t *bar, uint32_t &parity) {
+                                         uint64_t *bar, uint32_t &parity, uint2 *stage, uint32_t &fill) {
     const uint32_t tid = threadIdx.x;
     const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
     const bool validB = tid < rowsB;
@@ -1191,7 +1253,7 @@ __device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint3
         mbar_wait(&bar[ia & 1], (parity >> (ia & 1)) & 1u);
         parity ^= 1u << (ia & 1);
         const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
-        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, mycnt);
+        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, mycnt, stage, fill);
         __syncthreads();
     }
     if (validB && mycnt) { cx.cnt[posB] = mycnt; cx.needed[posB] = 1; }
@@ -1203,7 +1265,10 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ 
     __shared__ __align__(128) uint32_t sA[2][T1_TILE * 2 * T1_WMAX];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t s_item;
+    __shared__ uint2 s_stage[T1_TILE / 32][SWEEP_STAGE];
     const uint32_t tid = threadIdx.x;
+    uint2 *stage = s_stage[tid >> 5];
+    uint32_t fill = 0;                         // pairs in this warp's staging buffer (warp-uniform)
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
     __syncthreads();
     uint32_t parity = 0;                       // bit i = phase of bar[i]
@@ -1222,16 +1287,17 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ 
         const GroupInfo g = groups[lo];
         const uint32_t ib = g.tiles - 1 - (uint32_t)(item - g.work_off);      // longest rows of a group first
         switch (g.W) {
-            case 1: row_item<1>(cx, g, ib, c3, sA, bar, parity); break;
-            case 2: row_item<2>(cx, g, ib, c3, sA, bar, parity); break;
-            case 3: row_item<3>(cx, g, ib, c3, sA, bar, parity); break;
-            case 4: row_item<4>(cx, g, ib, c3, sA, bar, parity); break;
-            case 5: row_item<5>(cx, g, ib, c3, sA, bar, parity); break;
-            case 6: row_item<6>(cx, g, ib, c3, sA, bar, parity); break;
-            case 7: row_item<7>(cx, g, ib, c3, sA, bar, parity); break;
-            default: row_item<8>(cx, g, ib, c3, sA, bar, parity); break;
+            case 1: row_item<1>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            case 2: row_item<2>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            case 3: row_item<3>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            case 4: row_item<4>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            case 5: row_item<5>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            case 6: row_item<6>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            case 7: row_item<7>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            default: row_item<8>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
         }
     }
+    sweep_flush(cx, stage, fill);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1247,6 +1313,8 @@ __global__ void __launch_bounds__(128) k_phase_a(DevIn in, DevTables tb, DevPara
                                                  unsigned long long *f0_val, uint2 *cand, unsigned long long cand_cap, uint2 *pending) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long evals = 0, bytes = 0;
+    uint32_t emit = 0;                  // slots of s that go to the survivor list
+    bool emit_forced = false;
     if (s < (uint32_t)ctr->n_valid) {
         const uint32_t c = cnt[s];
         if (c) {
@@ -1280,8 +1348,28 @@ __global__ void __launch_bounds__(128) k_phase_a(DevIn in, DevTables tb, DevPara
             for (uint32_t i = next; i < nfirst; i++) {
                 const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
                 if (found && parent[a] == parent[s]) continue;           // hangs off the same parent: same tree, phase B would skip it
-                const unsigned long long q = atomicAdd(&ctr->n_cand, 1ull);
-                if (q < cand_cap) cand[q] = make_uint2(a | (forced ? 0x80000000u : 0u), s);
+                emit |= 1u << i;
+            }
+            emit_forced = forced;
+        }
+    }
+    {
+        // one reservation per warp for the recorded survivors
+        const uint32_t lane = threadIdx.x & 31;
+        uint32_t cntl = __popc(emit), incl = cntl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        const uint32_t totalc = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (totalc) {
+            unsigned long long q = 0;
+            if (lane == 0) q = atomicAdd(&ctr->n_cand, (unsigned long long)totalc);
+            q = __shfl_sync(0xFFFFFFFFu, q, 0) + (incl - cntl);
+            while (emit) {
+                const uint32_t i = __ffs(emit) - 1;
+                emit &= emit - 1;
+                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
+                if (q < cand_cap) cand[q] = make_uint2(a | (emit_forced ? 0x80000000u : 0u), s);
+                q++;
             }
         }
     }
