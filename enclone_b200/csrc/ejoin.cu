@@ -99,6 +99,7 @@ struct ejoin_handle {
     std::vector<double> multpool_host;
     std::vector<uint16_t> cdmax_host;
     std::vector<DevBuf> p1_tables;
+    unsigned long long xrow_cap = 0;
     unsigned long long cand_cap = 0;    // survivor list (tier-1 survivors beyond the phase-A slots)
     unsigned long long edge_cap = 0;    // to-be-scored lists, accepted edges, sort arrays
     // work pointers of the last pipeline run
@@ -514,9 +515,11 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     h->stats.ms_kernel_pack = h->stats.ms_kernel_tier1 = h->stats.ms_kernel_tier2 = h->stats.ms_kernel_other = 0;
     if (h->cand_cap == 0) h->cand_cap = std::max<unsigned long long>(1ull << 20, 48ull * n);
     if (h->edge_cap == 0) h->edge_cap = std::max<unsigned long long>(1ull << 20, 4ull * n);
+    if (h->xrow_cap == 0) h->xrow_cap = 1024 + n / T1_TILE;
     if (n == 0) return 0;
     for (int attempt = 0; attempt < 6; attempt++) {
         const unsigned long long ccap = h->cand_cap;
+        const unsigned long long xcap = h->xrow_cap;
         const unsigned long long cap = std::max<unsigned long long>(h->edge_cap, (unsigned long long)n + 1024);
         // ---- size and carve the work arena ----
         size_t cub_bytes = 0, tmpb = 0;
@@ -543,6 +546,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
         sz.take(8 * ccap); sz.take(8 * ccap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
         sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending
+        sz.take((size_t)n + 1024); sz.take(8 * ((size_t)n + 1024));                                           // work items: cost class, sorted list (items <= n)
+        sz.take(4 * (size_t)xcap * PHASE_A_K * T1_TILE); sz.take(4 * (size_t)xcap * T1_TILE);                   // extra slot rows (segments q >= 1)
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
         sz.take(8 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                   // Boruvka: best, ends, component sizes
         sz.take(cub_bytes + 256);
@@ -567,6 +572,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint32_t *firstk = A.take<uint32_t>((size_t)n * PHASE_A_K), *surv_cnt = A.take<uint32_t>(n);
         uint8_t *needed = A.take<uint8_t>(n), *force = A.take<uint8_t>(n);
         uint2 *pending = A.take<uint2>(n);
+        const uint32_t item_cap = n + 1024;
+        uint8_t *item_cls = A.take<uint8_t>(item_cap);
+        uint2 *order = A.take<uint2>(item_cap);
+        uint32_t *xk = A.take<uint32_t>((size_t)xcap * PHASE_A_K * T1_TILE), *xcnt = A.take<uint32_t>((size_t)xcap * T1_TILE);
         ejoin_raw_edge_t *acc = A.take<ejoin_raw_edge_t>(cap);
         unsigned long long *pk_in = A.take<unsigned long long>(cap), *pv_in = A.take<unsigned long long>(cap);
         unsigned long long *pk_out = A.take<unsigned long long>(cap), *pv_out = A.take<unsigned long long>(cap);
@@ -601,8 +610,12 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         mark(h, "sort entries");
         tb = cub_bytes;
         cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
-        k_group_scan<<<1, 1024, 0, st>>>(uniq, counts, num_runs, groups, (const uint16_t *)h->d_cdmax.p, ctr);
+        k_group_scan<<<1, 512, 0, st>>>(uniq, counts, num_runs, groups, (const uint16_t *)h->d_cdmax.p, ctr);
         mark(h, "rle + k_group_scan");
+        k_item_hist<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, item_cap, stride, phase);
+        k_item_scatter<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, order, item_cap, stride, phase);
+        h->launches += 2;
+        mark(h, "work items by cost");
         k_sorted_heads<<<nb256, 256, 0, st>>>(keys_out, n, t2sizes);          // t2sizes doubles as the flag buffer
         tb = cub_bytes;
         cub::DeviceScan::InclusiveSum(cub_tmp, tb, t2sizes, gid, (int)n, st);
@@ -622,7 +635,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         int rows_occ = 8;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_occ, k_sweep, T1_TILE, 0);
         if (rows_occ < 1) rows_occ = 1;
-        k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, cand, ccap, firstk, surv_cnt, needed, stride, phase);
+        k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, order, cand, ccap, firstk, surv_cnt, xk, xcnt, xcap, needed);
         CK(cudaEventRecord(h->ev[3], st));
         mark(h, "k_sweep");
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)
@@ -646,9 +659,11 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         tbs.meta = meta; tbs.c3 = c3; tbs.t2 = t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
         tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p;
         tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
-        k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, firstk, surv_cnt, force, parent, f0_key, f0_val, cand, ccap, pending);
+        SlotView sv;
+        sv.firstk = firstk; sv.cnt = surv_cnt; sv.xk = xk; sv.xcnt = xcnt; sv.gid_incl = gid; sv.groups = groups; sv.stride = stride; sv.phase = phase;
+        k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
         mark(h, "k_phase_a");
-        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, firstk, surv_cnt, force, parent, f0_key, f0_val, cand, ccap, pending);
+        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
         mark(h, "k_phase_a_pending");
         h->launches += 8;
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
@@ -700,6 +715,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             bool retry = false;
             if (k.n_cand > ccap) { h->cand_cap = k.n_cand + k.n_cand / 8 + 1024; retry = true; }
             if (need_e > cap) { h->edge_cap = need_e + need_e / 4 + 1024; retry = true; }
+            if (k.n_xrows > xcap) { h->xrow_cap = k.n_xrows + 64; retry = true; }
             if (retry) continue;
         }
         if (device_final) {

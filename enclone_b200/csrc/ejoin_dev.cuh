@@ -47,16 +47,31 @@ struct __align__(16) EntryMeta {
 };
 static_assert(sizeof(EntryMeta) == 128, "EntryMeta must be 128 bytes");
 
+// Tier-1 work decomposition.  A group of T tiles (of T1_TILE entries) is a lower-triangular T x T array
+// of tile pairs.  Row ib (its B tile) meets the A tiles 0..ib; the row is cut into segments of `seg`
+// A tiles, so that no work item is longer than `seg` tile steps (a row of a 4,000-entry group would
+// otherwise run 30+ steps on one CTA while the rest of the GPU idles).  Work items are enumerated
+// segment-major: segment q holds the rows ib = T-1 .. q*seg, i.e. T - q*seg items;
+//   item_index(q, ib) = q*T - seg*q*(q-1)/2 + (T-1-ib),       items(T) = Q*T - seg*Q*(Q-1)/2,  Q = ceil(T/seg).
+// Segment 0 of a row keeps its first survivors in the per-entry slot array; segments q >= 1 use an
+// "extra row" of slots, numbered xoff + item_index - T.
+#define SEG_MIN 8u           // A tiles per segment (small groups); large groups: ceil(T / SEG_QMAX)
+#define SEG_QMAX 32u         // at most this many segments per row
 struct GroupInfo {           // one comparison group = one run of equal sort keys
     uint32_t start;          // first sorted position
     uint32_t n;              // entries
     uint32_t c3base;         // u32 word offset of the group's c3 rows
     uint32_t work_off;       // first tier-1 work item
+    uint32_t xoff;           // first extra slot row
     uint16_t W;              // words per plane
     uint16_t cdmax;          // largest cd that passes the CDR3 gates
     uint16_t tiles;
-    uint16_t pad;
+    uint16_t seg;            // A tiles per segment
+    uint32_t pad;
 };
+static_assert(sizeof(GroupInfo) == 32, "GroupInfo is 32 bytes");
+__host__ __device__ __forceinline__ uint32_t seg_of_tiles(uint32_t T) { uint32_t s = (T + SEG_QMAX - 1) / SEG_QMAX; return s < SEG_MIN ? SEG_MIN : s; }
+__host__ __device__ __forceinline__ uint32_t seg_item_off(uint32_t T, uint32_t S, uint32_t q) { return q * T - S * (q * (q - 1) / 2); }
 
 struct DevCounters {         // device-resident scalars (one struct, copied back once)
     unsigned long long n_valid, n_groups, n_work, c3_words, pairs_compared, pairs_candidate, n_buckets;
@@ -69,6 +84,9 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned int bor_active;
     unsigned int n_payload_slow;
     unsigned int n_pending;
+    unsigned long long n_xrows;      // extra slot rows asked for by the group table
+    unsigned long long n_items;      // tier-1 work items of this rank (after the cost sort)
+    unsigned int cls_count[64], cls_cursor[64];   // counting sort of the work items by cost class
 };
 
 struct DevParams {           // ejoin_params_t plus run constants, by value to kernels

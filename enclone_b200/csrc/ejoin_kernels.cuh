@@ -64,75 +64,143 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
     if (threadIdx.x == 0) { atomicAdd(&ctr->pairs_candidate, s); atomicAdd(&ctr->n_buckets, h); }
 }
 
-// K2  group table from the run-length encoded sorted keys (single block).
-__global__ void __launch_bounds__(1024) k_group_scan(const unsigned long long *uniq, const uint32_t *counts, const uint32_t *num_runs,
-                                                     GroupInfo *groups, const uint16_t *cdmax_tab, DevCounters *ctr) {
-    typedef cub::BlockScan<unsigned long long, 1024> BS;
+// K2  group table from the run-length encoded sorted keys.  One block: every thread owns a contiguous
+// chunk of runs, sums its chunk, the block scans the 512 chunk sums, and a second pass over the
+// chunk writes the GroupInfo records with the running prefix.
+struct GroupVals { unsigned long long v[6]; uint32_t W, cdm, T; bool valid; };   // entries, work items, c3 words, pairs, tier-1 bytes, extra slot rows
+__device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned long long n, const uint16_t *__restrict__ cdmax_tab) {
+    GroupVals o;
+#pragma unroll
+    for (int f = 0; f < 6; f++) o.v[f] = 0;
+    o.W = 0; o.cdm = 0xFFFF; o.T = 0; o.valid = key != ~0ull;
+    if (!o.valid) return o;
+    const uint32_t total = (uint32_t)((key >> 16) & 0xFFFF) + (uint32_t)(key & 0xFFFF);
+    uint32_t W = (total + 31) / 32;
+    if (W == 0) W = 1;
+    const uint32_t cdm = cdmax_tab[total];
+    const uint32_t T = (uint32_t)((n + T1_TILE - 1) / T1_TILE);
+    o.W = W; o.cdm = cdm; o.T = T;
+    o.v[0] = n;
+    if (n >= 2 && cdm != 0xFFFF) {
+        const uint32_t S = seg_of_tiles(T), Q = (T + S - 1) / S;
+        const unsigned long long items = seg_item_off(T, S, Q);       // = Q*T - S*Q*(Q-1)/2
+        o.v[1] = items;
+        o.v[3] = n * (n - 1) / 2;
+        o.v[4] = o.v[3] * 16ull * W;
+        o.v[5] = items - T;
+    }
+    o.v[2] = (n * 2 * W + 3) & ~3ull;
+    return o;
+}
+__global__ void __launch_bounds__(512) k_group_scan(const unsigned long long *__restrict__ uniq, const uint32_t *__restrict__ counts,
+                                                     const uint32_t *num_runs, GroupInfo *groups, const uint16_t *__restrict__ cdmax_tab,
+                                                     DevCounters *ctr) {
+    typedef cub::BlockScan<unsigned long long, 512> BS;
     __shared__ typename BS::TempStorage tmp;
-    __shared__ unsigned long long carry[5];
-    if (threadIdx.x == 0) carry[0] = carry[1] = carry[2] = carry[3] = carry[4] = 0;
-    __syncthreads();
     const uint32_t nr = *num_runs;
+    const uint32_t chunk = (nr + 511) / 512;
+    const uint32_t r0 = min(nr, threadIdx.x * chunk), r1 = min(nr, r0 + chunk);
+    unsigned long long sum[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long ngroups = 0;
-    for (uint32_t base = 0; base < nr; base += 1024) {
-        uint32_t r = base + threadIdx.x;
-        unsigned long long n = 0, work = 0, c3w = 0, pairs = 0;
-        uint32_t W = 0, tiles = 0, cdm = 0xFFFF;
-        bool valid = false;
-        if (r < nr) {
-            unsigned long long key = uniq[r];
-            if (key != ~0ull) {
-                valid = true;
-                n = counts[r];
-                uint32_t total = (uint32_t)((key >> 16) & 0xFFFF) + (uint32_t)(key & 0xFFFF);
-                W = (total + 31) / 32;
-                if (W == 0) W = 1;
-                cdm = cdmax_tab[total];
-                tiles = (uint32_t)((n + T1_TILE - 1) / T1_TILE);
-                if (n >= 2 && cdm != 0xFFFF) { work = tiles; pairs = n * (n - 1) / 2; }   // one work item per tile row
-                c3w = (n * 2 * W + 3) & ~3ull;
-            }
-        }
-        unsigned long long sn, sw, sc, agg;
-        BS(tmp).ExclusiveSum(n, sn, agg);
-        __syncthreads();
-        unsigned long long aggn = agg;
-        BS(tmp).ExclusiveSum(work, sw, agg);
-        __syncthreads();
-        unsigned long long aggw = agg;
-        BS(tmp).ExclusiveSum(c3w, sc, agg);
-        __syncthreads();
-        unsigned long long aggc = agg;
-        unsigned long long t1b = pairs * 16ull * W, aggb;
-        BS(tmp).ExclusiveSum(pairs, pairs, agg);   // only the aggregates are used
-        __syncthreads();
-        BS(tmp).ExclusiveSum(t1b, t1b, aggb);
-        __syncthreads();
-        if (valid) {
-            GroupInfo g;
-            g.start = (uint32_t)(carry[0] + sn);
-            g.n = (uint32_t)n;
-            g.c3base = (uint32_t)(carry[2] + sc);
-            g.work_off = (uint32_t)(carry[1] + sw);
-            g.W = (uint16_t)W; g.cdmax = (uint16_t)cdm; g.tiles = (uint16_t)tiles; g.pad = 0;
-            groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
-            if (r + 1 > ngroups) ngroups = r + 1;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { carry[0] += aggn; carry[1] += aggw; carry[2] += aggc; carry[3] += agg; carry[4] += aggb; }
+    for (uint32_t r = r0; r < r1; r++) {
+        const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
+#pragma unroll
+        for (int f = 0; f < 6; f++) sum[f] += gv.v[f];
+    }
+    unsigned long long pre[6], agg[6];
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        BS(tmp).ExclusiveSum(sum[f], pre[f], agg[f]);
         __syncthreads();
     }
+    for (uint32_t r = r0; r < r1; r++) {
+        const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
+        if (gv.valid) {
+            GroupInfo g;
+            g.start = (uint32_t)pre[0];
+            g.n = counts[r];
+            g.c3base = (uint32_t)pre[2];
+            g.work_off = (uint32_t)pre[1];
+            g.xoff = (uint32_t)pre[5];
+            g.W = (uint16_t)gv.W; g.cdmax = (uint16_t)gv.cdm; g.tiles = (uint16_t)gv.T; g.seg = (uint16_t)seg_of_tiles(gv.T); g.pad = 0;
+            groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
+            ngroups = r + 1;
+        }
+#pragma unroll
+        for (int f = 0; f < 6; f++) pre[f] += gv.v[f];
+    }
     // number of groups = number of valid runs
-    typedef cub::BlockReduce<unsigned long long, 1024> BR;
+    typedef cub::BlockReduce<unsigned long long, 512> BR;
     __shared__ typename BR::TempStorage tmp2;
     unsigned long long ng = BR(tmp2).Reduce(ngroups, MaxOp());
     if (threadIdx.x == 0) {
         ctr->n_groups = ng;
-        ctr->n_valid = carry[0];
-        ctr->n_work = carry[1];
-        ctr->c3_words = carry[2];
-        ctr->pairs_compared = carry[3];
-        ctr->t1_alg_bytes = carry[4];
+        ctr->n_valid = agg[0];
+        ctr->n_work = agg[1];
+        ctr->c3_words = agg[2];
+        ctr->pairs_compared = agg[3];
+        ctr->t1_alg_bytes = agg[4];
+        ctr->n_xrows = agg[5];
+    }
+}
+
+// Work items sorted by cost, longest first (counting sort over 64 cost classes): the sweep's CTAs take
+// items from one atomic counter, and with the long items in front the tail of the kernel is made of
+// the short ones.  In stride mode (a giant bucket shared by several ranks) only the rows this rank
+// owns enter the list: row r of the global numbering belongs to rank r % stride.
+__device__ __forceinline__ bool item_decode(const GroupInfo *__restrict__ groups, uint32_t ngroups, unsigned long long item, uint32_t stride,
+                                            uint32_t phase, uint32_t *g_out, uint32_t *q_out, uint32_t *ib_out, uint32_t *cls_out) {
+    uint32_t lo = 0, hi = ngroups;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (groups[mid].work_off <= item) lo = mid; else hi = mid; }
+    const GroupInfo g = groups[lo];
+    const uint32_t T = g.tiles, S = g.seg;
+    uint32_t rem = (uint32_t)(item - g.work_off), q = 0;
+    while (rem >= T - q * S) { rem -= T - q * S; q++; }
+    const uint32_t ib = T - 1 - rem;
+    *g_out = lo; *q_out = q; *ib_out = ib;
+    if (stride > 1 && (g.work_off + (T - 1 - ib)) % stride != phase) return false;
+    // cost ~ half tile steps (the diagonal tile counts half) x rows in the B tile x words per row
+    const uint32_t hi_t = min((q + 1) * S - 1, ib);
+    const uint32_t half = 2 * (hi_t - q * S + 1) - (hi_t == ib ? 1u : 0u);
+    const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
+    const uint32_t cost = (half * g.W * ((rowsB + 31) >> 5) + 7) >> 3;          // 16 half steps x W=3 x 4 warps -> 24
+    *cls_out = min(cost, 63u);
+    return true;
+}
+__global__ void __launch_bounds__(256) k_item_hist(const GroupInfo *__restrict__ groups, DevCounters *ctr, uint8_t *__restrict__ item_cls,
+                                                   uint32_t item_cap, uint32_t stride, uint32_t phase) {
+    __shared__ uint32_t hist[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t ngroups = (uint32_t)ctr->n_groups;
+    const unsigned long long nwork = min(ctr->n_work, (unsigned long long)item_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t g, q, ib, cls;
+        const bool own = item_decode(groups, ngroups, i, stride, phase, &g, &q, &ib, &cls);
+        item_cls[i] = own ? (uint8_t)cls : (uint8_t)255;
+        if (own) atomicAdd(&hist[cls], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && hist[threadIdx.x]) atomicAdd(&ctr->cls_count[threadIdx.x], hist[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_item_scatter(const GroupInfo *__restrict__ groups, DevCounters *ctr, const uint8_t *__restrict__ item_cls,
+                                                      uint2 *__restrict__ order, uint32_t item_cap, uint32_t stride, uint32_t phase) {
+    __shared__ uint32_t base[64];
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int cl = 63; cl >= 0; cl--) { base[cl] = run; run += ctr->cls_count[cl]; }
+        if (blockIdx.x == 0) ctr->n_items = run;
+    }
+    __syncthreads();
+    const uint32_t ngroups = (uint32_t)ctr->n_groups;
+    const unsigned long long nwork = min(ctr->n_work, (unsigned long long)item_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t cl = item_cls[i];
+        if (cl == 255) continue;
+        uint32_t g, q, ib, cls;
+        item_decode(groups, ngroups, i, stride, phase, &g, &q, &ib, &cls);
+        const uint32_t pos = base[cl] + atomicAdd(&ctr->cls_cursor[cl], 1u);
+        order[pos] = make_uint2(g, (q << 16) | ib);
     }
 }
 
@@ -549,19 +617,50 @@ __device__ __forceinline__ void emit_raw(const DevParams &pr, DevCounters *ctr, 
 // (0 = reject) or -1 when the pair needs the bytewise path (has_del / non-ACGT / overlapping
 // windows / different germlines); *scored is set when the pair got past the cheap gates.
 // ---------------------------------------------------------------------------------------------
+// CDR3 differences of a pair from its two c3 rows, all 4W words in flight at once
+template <int W>
+__device__ __forceinline__ void cdr3_counts_w(const uint32_t *__restrict__ c3, uint32_t o1, uint32_t o2, int cl0, int *cd0, int *cdt) {
+    uint32_t a[2 * W], b[2 * W];
+#pragma unroll
+    for (int i = 0; i < 2 * W; i++) { a[i] = __ldg(c3 + o1 + i); b[i] = __ldg(c3 + o2 + i); }
+    int t = 0, t0 = 0;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        const uint32_t D = (a[w] ^ b[w]) | (a[W + w] ^ b[W + w]);
+        t += __popc(D);
+        t0 += __popc(D & range_mask(w, 0, cl0));
+    }
+    *cd0 = t0; *cdt = t;
+}
+union MetaRegs { EntryMeta m; uint4 q[8]; __device__ MetaRegs() {} };
+
 __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa,
                                                uint32_t sb, int *cd_out, int *d_out, int *err_out, bool *scored, unsigned long long *bytes) {
-    const EntryMeta *pa = &tb.meta[sa], *pb = &tb.meta[sb];
-    if (pa->k > pb->k) { const EntryMeta *t = pa; pa = pb; pb = t; }
-    const EntryMeta &m1 = *pa, &m2 = *pb;
+    // Inside a comparison group sorted position order == info order (stable sort of ascending k), so the
+    // entry at the smaller position is k1: no need to look at the records to order the pair.
+    if (sa > sb) { const uint32_t t = sa; sa = sb; sb = t; }
+    MetaRegs u1, u2;                      // both 128-byte records with 16 loads in flight, then everything from registers
+    {
+        const uint4 *q1 = (const uint4 *)&tb.meta[sa], *q2 = (const uint4 *)&tb.meta[sb];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { u1.q[i] = __ldg(q1 + i); u2.q[i] = __ldg(q2 + i); }
+    }
+    const EntryMeta &m1 = u1.m, &m2 = u2.m;
     *scored = false; *d_out = 0; *err_out = 0;
     // CDR3 differences per chain from the c3 rows
     const uint32_t cl0 = m1.cl[0], total = cl0 + m1.cl[1], W = max(1u, (total + 31) / 32);
     int cd0 = 0, cdt = 0;
-    for (uint32_t w = 0; w < W; w++) {
-        uint32_t D = (tb.c3[m1.c3off + w] ^ tb.c3[m2.c3off + w]) | (tb.c3[m1.c3off + W + w] ^ tb.c3[m2.c3off + W + w]);
-        cdt += __popc(D);
-        cd0 += __popc(D & range_mask((int)w, 0, (int)cl0));
+    switch (W) {
+        case 1: cdr3_counts_w<1>(tb.c3, m1.c3off, m2.c3off, (int)cl0, &cd0, &cdt); break;
+        case 2: cdr3_counts_w<2>(tb.c3, m1.c3off, m2.c3off, (int)cl0, &cd0, &cdt); break;
+        case 3: cdr3_counts_w<3>(tb.c3, m1.c3off, m2.c3off, (int)cl0, &cd0, &cdt); break;
+        case 4: cdr3_counts_w<4>(tb.c3, m1.c3off, m2.c3off, (int)cl0, &cd0, &cdt); break;
+        default:
+            for (uint32_t w = 0; w < W; w++) {
+                uint32_t D = (tb.c3[m1.c3off + w] ^ tb.c3[m2.c3off + w]) | (tb.c3[m1.c3off + W + w] ^ tb.c3[m2.c3off + W + w]);
+                cdt += __popc(D);
+                cd0 += __popc(D & range_mask((int)w, 0, (int)cl0));
+            }
     }
     const int cd = cdt, cd1 = cdt - cd0;
     *cd_out = cd;
@@ -569,7 +668,7 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
     if (cdm == 0xFFFF || (uint32_t)cd > cdm) return 0;          // CDR3 gates (A.4-d), same table as tier 1
     if (!meta_gates(pr, in, m1, m2, cd, err_out)) return 0;
     *scored = true;
-    const uint32_t nblk = ((uint32_t)m1.len[0] + 127) / 128 + ((uint32_t)m1.len[1] + 127) / 128;
+    const uint32_t nb0 = ((uint32_t)m1.len[0] + 127) / 128, nblk = nb0 + ((uint32_t)m1.len[1] + 127) / 128;
     *bytes += 2ull * (48ull * nblk + 128ull);
     const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] ||
                          m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
@@ -578,58 +677,54 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
     pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1;
     for (int c2 = 0; c2 < 2; c2++)
         if (m1.vref[c2] != m2.vref[c2] || m1.dref[c2] != m2.dref[c2] || m1.jref[c2] != m2.jref[c2]) pc.nrefs = 2;
-    int diffs = 0, shares = 0;
+    // One pass over the t2 rows does all the counting: total differences and shared mutations (every block),
+    // FWR1 vs CDR1+CDR2 differences on the heavy chain (A.4-m, blocks of chain 0 that meet [f1,f3)), and the
+    // non-shared mutations outside the CDR3s (A.4-n, only when cd >= CDR3_MULT).
+    int f1 = 0, c1 = 0, f2 = 0, c2_ = 0, f3 = 0;
+    const bool do_reg = pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3);
+    const int wlo = do_reg ? (f1 >> 5) : (1 << 30), whi = do_reg ? ((f3 - 1) >> 5) : -1;
+    const bool do_io = cd >= pr.cdr3_mult;
+    int diffs = 0, shares = 0, dfw = 0, d12 = 0, io = 0;
     const uint4 *r1 = tb.t2 + m1.t2off, *r2 = tb.t2 + m2.t2off;
+#pragma unroll 2
     for (uint32_t b = 0; b < nblk; b++) {
-        uint4 h1 = r1[3 * b], l1 = r1[3 * b + 1], x1 = r1[3 * b + 2];
-        uint4 h2 = r2[3 * b], l2 = r2[3 * b + 1], x2 = r2[3 * b + 2];
-        uint32_t D0 = (h1.x ^ h2.x) | (l1.x ^ l2.x), D1 = (h1.y ^ h2.y) | (l1.y ^ l2.y);
-        uint32_t D2 = (h1.z ^ h2.z) | (l1.z ^ l2.z), D3 = (h1.w ^ h2.w) | (l1.w ^ l2.w);
-        diffs += __popc(D0) + __popc(D1) + __popc(D2) + __popc(D3);
-        shares += __popc(x1.x & x2.x & ~D0) + __popc(x1.y & x2.y & ~D1) + __popc(x1.z & x2.z & ~D2) + __popc(x1.w & x2.w & ~D3);
+        const uint4 h1 = __ldg(r1 + 3 * b), l1 = __ldg(r1 + 3 * b + 1), x1 = __ldg(r1 + 3 * b + 2);
+        const uint4 h2 = __ldg(r2 + 3 * b), l2 = __ldg(r2 + 3 * b + 1), x2 = __ldg(r2 + 3 * b + 2);
+        const uint32_t D[4] = { (h1.x ^ h2.x) | (l1.x ^ l2.x), (h1.y ^ h2.y) | (l1.y ^ l2.y), (h1.z ^ h2.z) | (l1.z ^ l2.z), (h1.w ^ h2.w) | (l1.w ^ l2.w) };
+        const uint32_t X1[4] = { x1.x, x1.y, x1.z, x1.w }, X2[4] = { x2.x, x2.y, x2.z, x2.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) { diffs += __popc(D[q]); shares += __popc(X1[q] & X2[q] & ~D[q]); }
+        const bool ch1 = b >= nb0;
+        const int wl0 = 4 * (int)(b - (ch1 ? nb0 : 0u));          // word index inside the chain
+        if (!ch1 && wl0 + 3 >= wlo && wl0 <= whi) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                dfw += __popc(D[q] & range_mask(wl0 + q, f1, c1));
+                d12 += __popc(D[q] & (range_mask(wl0 + q, c1, f2) | range_mask(wl0 + q, c2_, f3)));
+            }
+        }
+        if (do_io) {
+            const int a1 = ch1 ? m1.cs[1] : m1.cs[0], a2 = ch1 ? m2.cs[1] : m2.cs[0], cl = ch1 ? m1.cl[1] : m1.cl[0];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t R = range_mask(wl0 + q, a1, a1 + cl) | range_mask(wl0 + q, a2, a2 + cl);
+                io += __popc(X1[q] & D[q] & ~R) + __popc(X2[q] & D[q] & ~R);
+            }
+        }
     }
     const int mm = (int)m1.m[0] + (int)m1.m[1] + (int)m2.m[0] + (int)m2.m[1];
     pc.diffs = diffs;
     pc.shares[0] = pc.shares[1] = shares;
     pc.indeps[0] = pc.indeps[1] = mm - 2 * shares;
-    pc.indeps_out[0] = pc.indeps_out[1] = 1 << 20;    // filled below only when the CDR3_MULT rule can bite
+    pc.indeps_out[0] = pc.indeps_out[1] = do_io ? io : (1 << 20);    // only looked at when the CDR3_MULT rule can bite
     // total-difference cap (A.4-c)
     if (!pr.is_bcr || pr.max_diffs < 1000000) {
         int cap = pr.max_diffs;
         if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
         if (diffs > cap) return 0;
     }
-    // FWR1 vs CDR1+CDR2 on the heavy chain (A.4-m)
     pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
-    int f1, c1, f2, c2_, f3;
-    if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3)) {
-        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
-        int dfw = 0, d12 = 0;
-        for (int w = f1 >> 5; w <= (f3 - 1) >> 5; w++) {
-            const int blk = w >> 2, q = w & 3;
-            uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
-            dfw += __popc(D & range_mask(w, f1, c1));
-            d12 += __popc(D & (range_mask(w, c1, f2) | range_mask(w, c2_, f3)));
-        }
-        pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_);
-    }
-    // non-shared mutations outside the CDR3s (A.4-n), only when cd >= CDR3_MULT
-    if (cd >= pr.cdr3_mult) {
-        const uint32_t *w1 = (const uint32_t *)r1, *w2 = (const uint32_t *)r2;
-        int io = 0, blk0 = 0;
-        for (int c2 = 0; c2 < 2; c2++) {
-            const int nw = ((int)m1.len[c2] + 127) / 128 * 4;
-            const int a1 = m1.cs[c2], a2 = m2.cs[c2], cl = m1.cl[c2];
-            for (int w = 0; w < nw; w++) {
-                const int blk = blk0 + (w >> 2), q = w & 3;
-                uint32_t D = (w1[blk * 12 + q] ^ w2[blk * 12 + q]) | (w1[blk * 12 + 4 + q] ^ w2[blk * 12 + 4 + q]);
-                uint32_t R = range_mask(w, a1, a1 + cl) | range_mask(w, a2, a2 + cl);
-                io += __popc(w1[blk * 12 + 8 + q] & D & ~R) + __popc(w2[blk * 12 + 8 + q] & D & ~R);
-            }
-            blk0 += nw / 4;
-        }
-        pc.indeps_out[0] = pc.indeps_out[1] = io;
-    }
+    if (do_reg) { pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_); }
     int kk; double p1, mult, score;
     return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
 }
@@ -729,7 +824,7 @@ __global__ void __launch_bounds__(256) k_phaseb_cross(const uint2 *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(128) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
+__global__ void __launch_bounds__(128, 6) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
                                                unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t k_base,
                                                uint32_t *parent_min) {
     uint32_t *minnbr = nullptr;
@@ -1140,8 +1235,11 @@ __global__ void __launch_bounds__(P1_DCAP) k_p1_tables(const uint32_t *Ls, doubl
 struct SweepCtx {
     DevCounters *ctr;
     uint2 *cand; unsigned long long cand_cap;
-    uint32_t *firstk;      // [n][PHASE_A_K] a positions
-    uint32_t *cnt;         // [n] survivors of b
+    uint32_t *firstk;      // [n][PHASE_A_K] a positions: segment 0 of every row
+    uint32_t *cnt;         // [n] survivors of b in segment 0
+    uint32_t *xk;          // [xrow][PHASE_A_K][T1_TILE] a positions: segments q >= 1
+    uint32_t *xcnt;        // [xrow][T1_TILE]
+    unsigned long long xcap;
     uint8_t *needed;       // [n]
 };
 
@@ -1163,7 +1261,7 @@ __device__ __forceinline__ void sweep_flush(SweepCtx &cx, uint2 *stage, uint32_t
 template <int W>
 __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
                                           const uint32_t (&bH)[W], const uint32_t (&bL)[W], bool validB, uint32_t posA0, uint32_t posB,
-                                          uint32_t &mycnt, uint2 *stage, uint32_t &fill) {
+                                          uint32_t &mycnt, uint2 *stage, uint32_t &fill, uint32_t *slot, uint32_t slot_stride) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (!__any_sync(0xFFFFFFFFu, validB)) return;          // a warp beyond the end of a short B tile
     for (uint32_t a0 = 0; a0 < rowsA; a0 += 32) {
@@ -1191,7 +1289,7 @@ __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restri
         while (bits && mycnt < PHASE_A_K) {
             const uint32_t aa = __ffs(bits) - 1;
             bits &= bits - 1;
-            cx.firstk[(size_t)posB * PHASE_A_K + mycnt] = posA0 + a0 + aa;
+            slot[(size_t)mycnt * slot_stride] = posA0 + a0 + aa;
             mycnt++;
         }
         // the rest: the global survivor list, through the warp's staging buffer (one atomic per SWEEP_STAGE pairs
@@ -1227,12 +1325,22 @@ __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restri
 }
 
 template <int W>
-__device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint32_t ib, const uint32_t *__restrict__ c3, uint32_t (*sA)[T1_TILE * 2 * T1_WMAX],
-                                         uint64_t *bar, uint32_t &parity, uint2 *stage, uint32_t &fill) {
+__device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint32_t ib, uint32_t q, const uint32_t *__restrict__ c3,
+                                         uint32_t (*sA)[T1_TILE * 2 * T1_WMAX], uint64_t *bar, uint32_t &parity, uint2 *stage, uint32_t &fill) {
     const uint32_t tid = threadIdx.x;
     const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
     const bool validB = tid < rowsB;
     const uint32_t posB = g.start + ib * T1_TILE + tid;
+    const uint32_t S = g.seg, ia_lo = q * S, ia_hi = min(ia_lo + S - 1, ib);
+    // where this segment's first survivors go
+    uint32_t *slot = cx.firstk + (size_t)posB * PHASE_A_K, slot_stride = 1;
+    unsigned long long xrow = 0;
+    bool slots_ok = true;
+    if (q) {
+        xrow = (unsigned long long)g.xoff + seg_item_off(g.tiles, S, q) + (g.tiles - 1 - ib) - g.tiles;
+        slots_ok = xrow < cx.xcap;                       // too small: the host sees n_xrows > cap and retries
+        slot = cx.xk + (size_t)(slots_ok ? xrow : 0) * PHASE_A_K * T1_TILE + tid; slot_stride = T1_TILE;
+    }
     uint32_t bH[W], bL[W];
     {
         const uint32_t *rb = c3 + g.c3base + (size_t)(ib * T1_TILE + (validB ? tid : 0)) * 2 * W;
@@ -1241,27 +1349,32 @@ __device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint3
     }
     uint32_t mycnt = 0;
     auto issue = [&](uint32_t ia) {
+        const uint32_t b = (ia - ia_lo) & 1;
         const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
         const uint32_t bytes = (rowsA * 2 * W * 4 + 15) & ~15u;
         fence_proxy_async();
-        mbar_expect_tx(&bar[ia & 1], bytes);
-        tma_load_1d(sA[ia & 1], c3 + g.c3base + (size_t)ia * T1_TILE * 2 * W, bytes, &bar[ia & 1]);
+        mbar_expect_tx(&bar[b], bytes);
+        tma_load_1d(sA[b], c3 + g.c3base + (size_t)ia * T1_TILE * 2 * W, bytes, &bar[b]);
     };
-    if (tid == 0) issue(0);
-    for (uint32_t ia = 0; ia <= ib; ia++) {
-        if (tid == 0 && ia + 1 <= ib) issue(ia + 1);       // buffer (ia+1)&1 was released by the barrier ending iteration ia-1
-        mbar_wait(&bar[ia & 1], (parity >> (ia & 1)) & 1u);
-        parity ^= 1u << (ia & 1);
+    if (tid == 0) issue(ia_lo);
+    for (uint32_t ia = ia_lo; ia <= ia_hi; ia++) {
+        const uint32_t b = (ia - ia_lo) & 1;
+        if (tid == 0 && ia + 1 <= ia_hi) issue(ia + 1);    // the other buffer was released by the barrier ending the previous step
+        mbar_wait(&bar[b], (parity >> b) & 1u);
+        parity ^= 1u << b;
         const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
-        row_sweep<W>(cx, sA[ia & 1], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, mycnt, stage, fill);
+        if (slots_ok)
+            row_sweep<W>(cx, sA[b], rowsA, ia == ib, g.cdmax, bH, bL, validB, g.start + ia * T1_TILE, posB, mycnt, stage, fill, slot, slot_stride);
         __syncthreads();
     }
-    if (validB && mycnt) { cx.cnt[posB] = mycnt; cx.needed[posB] = 1; }
+    if (q == 0) { if (validB && mycnt) cx.cnt[posB] = mycnt; }
+    else if (slots_ok) cx.xcnt[(size_t)xrow * T1_TILE + tid] = validB ? mycnt : 0u;
+    if (validB && mycnt) cx.needed[posB] = 1;
 }
 
 __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ c3, const GroupInfo *__restrict__ groups, DevCounters *ctr,
-                                                   uint2 *cand, unsigned long long cand_cap, uint32_t *firstk, uint32_t *cnt, uint8_t *needed,
-                                                   uint32_t stride, uint32_t phase) {
+                                                   const uint2 *__restrict__ order, uint2 *cand, unsigned long long cand_cap, uint32_t *firstk,
+                                                   uint32_t *cnt, uint32_t *xk, uint32_t *xcnt, unsigned long long xcap, uint8_t *needed) {
     __shared__ __align__(128) uint32_t sA[2][T1_TILE * 2 * T1_WMAX];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t s_item;
@@ -1273,28 +1386,27 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ 
     __syncthreads();
     uint32_t parity = 0;                       // bit i = phase of bar[i]
     SweepCtx cx;
-    cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap; cx.firstk = firstk; cx.cnt = cnt; cx.needed = needed;
-    const uint32_t ngroups = (uint32_t)ctr->n_groups;
-    const unsigned long long nwork = ctr->n_work;
+    cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap; cx.firstk = firstk; cx.cnt = cnt; cx.xk = xk; cx.xcnt = xcnt; cx.xcap = xcap;
+    cx.needed = needed;
+    const unsigned long long nitems = ctr->n_items;
     for (;;) {
         if (tid == 0) s_item = (uint32_t)atomicAdd(&ctr->work_next, 1ull);
         __syncthreads();
-        const unsigned long long item = (unsigned long long)s_item * stride + phase;
+        const unsigned long long w = s_item;
         __syncthreads();
-        if (item >= nwork) break;
-        uint32_t lo = 0, hi = ngroups;
-        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (groups[mid].work_off <= item) lo = mid; else hi = mid; }
-        const GroupInfo g = groups[lo];
-        const uint32_t ib = g.tiles - 1 - (uint32_t)(item - g.work_off);      // longest rows of a group first
+        if (w >= nitems) break;
+        const uint2 it = order[w];             // longest items first (k_item_scatter)
+        const GroupInfo g = groups[it.x];
+        const uint32_t q = it.y >> 16, ib = it.y & 0xFFFFu;
         switch (g.W) {
-            case 1: row_item<1>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
-            case 2: row_item<2>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
-            case 3: row_item<3>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
-            case 4: row_item<4>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
-            case 5: row_item<5>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
-            case 6: row_item<6>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
-            case 7: row_item<7>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
-            default: row_item<8>(cx, g, ib, c3, sA, bar, parity, stage, fill); break;
+            case 1: row_item<1>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
+            case 2: row_item<2>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
+            case 3: row_item<3>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
+            case 4: row_item<4>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
+            case 5: row_item<5>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
+            case 6: row_item<6>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
+            case 7: row_item<7>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
+            default: row_item<8>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
         }
     }
     sweep_flush(cx, stage, fill);
@@ -1308,68 +1420,133 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ 
 // PHASE_A_K slots are all rejected is marked `force`:
 // all its remaining survivors are scored in phase B round 1.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_phase_a(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *__restrict__ firstk,
-                                                 const uint32_t *__restrict__ cnt, uint8_t *force, uint32_t *parent, unsigned long long *f0_key,
-                                                 unsigned long long *f0_val, uint2 *cand, unsigned long long cand_cap, uint2 *pending) {
+// The slots of entry s (sorted position): segment 0 in firstk/cnt, segments q >= 1 in the extra rows.
+struct SlotView {
+    const uint32_t *firstk, *cnt, *xk, *xcnt;
+    const uint32_t *gid_incl;
+    const GroupInfo *groups;
+    uint32_t stride, phase;
+};
+struct RowSlots {
+    uint32_t s, t, nseg;
+    unsigned long long xbase;      // extra row of segment q = xbase + seg_item_off(T, S, q)
+    uint32_t T, S;
+    bool owned;
+    __device__ __forceinline__ void init(const SlotView &sv, uint32_t s_) {
+        s = s_;
+        const GroupInfo g = sv.groups[sv.gid_incl[s] - 1];
+        const uint32_t rel = s - g.start, ib = rel / T1_TILE;
+        t = rel % T1_TILE; T = g.tiles; S = g.seg;
+        nseg = ib / S + 1;
+        xbase = (unsigned long long)g.xoff + (T - 1 - ib) - T;
+        owned = g.n >= 2 && g.cdmax != 0xFFFF &&                                              // a group without work has no slots at all
+                !(sv.stride > 1 && (g.work_off + (T - 1 - ib)) % sv.stride != sv.phase);     // same rule as item_decode
+    }
+    __device__ __forceinline__ uint32_t count(const SlotView &sv, uint32_t q) const {
+        return q == 0 ? sv.cnt[s] : sv.xcnt[(size_t)(xbase + seg_item_off(T, S, q)) * T1_TILE + t];
+    }
+    __device__ __forceinline__ uint32_t slot(const SlotView &sv, uint32_t q, uint32_t i) const {
+        return q == 0 ? sv.firstk[(size_t)s * PHASE_A_K + i] : sv.xk[((size_t)(xbase + seg_item_off(T, S, q)) * PHASE_A_K + i) * T1_TILE + t];
+    }
+};
+
+// Outcome of one entry's walk over its slots (ascending a: segment by segment, slot by slot).
+struct WalkOut {
+    uint32_t emit0;        // segment-0 slots that go to the survivor list (bit i)
+    uint32_t xe_start;     // every slot of the segments q >= 1 with linear index q*K+i >= xe_start goes to the list
+    uint32_t n_emit_x;     // how many those are
+    bool forced;           // the listed slots carry the forced flag
+};
+
+__global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
+                                                 uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
+                                                 unsigned long long cand_cap, uint2 *pending) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long evals = 0, bytes = 0;
-    uint32_t emit = 0;                  // slots of s that go to the survivor list
-    bool emit_forced = false;
+    WalkOut wo;
+    wo.emit0 = 0; wo.xe_start = 0xFFFFFFFFu; wo.n_emit_x = 0; wo.forced = false;
+    RowSlots rs;
+    rs.nseg = 0; rs.owned = false;
     if (s < (uint32_t)ctr->n_valid) {
-        const uint32_t c = cnt[s];
-        if (c) {
-            const uint32_t nfirst = min(c, PHASE_A_K);
+        rs.init(sv, s);
+        if (rs.owned) {
             bool found = false, forced = false, pended = false;
-            uint32_t next = nfirst;                     // first slot not consumed by phase A
-            for (uint32_t i = 0; i < nfirst; i++) {
-                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
-                int cd, d, err;
-                bool scored;
-                int r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
-                evals += scored;
-                if (r < 0) {                       // has_del / different germlines: rare; a whole warp continues this b (k_phase_a_pending)
-                    const uint32_t q = atomicAdd(&ctr->n_pending, 1u);
-                    pending[q] = make_uint2(s, i);
-                    pended = true;
-                    break;
+            uint32_t rejects = 0;
+            for (uint32_t q = 0; q < rs.nseg && !pended; q++) {
+                const uint32_t cq = rs.count(sv, q), nq = min(cq, PHASE_A_K);
+                uint32_t i = 0;
+                if (!found && !forced) {
+                    for (; i < nq; i++) {
+                        const uint32_t a = rs.slot(sv, q, i);
+                        int cd, d, err;
+                        bool scored;
+                        const int r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
+                        evals += scored;
+                        if (r < 0) {                   // has_del / different germlines: rare; a whole warp continues this b (k_phase_a_pending)
+                            const uint32_t pq = atomicAdd(&ctr->n_pending, 1u);
+                            pending[pq] = make_uint2(s, q * PHASE_A_K + i);
+                            pended = true;
+                            break;
+                        }
+                        if (r > 0) {
+                            found = true;
+                            parent[s] = a;
+                            f0_key[s] = ((unsigned long long)tb.meta[a].k << 32) | tb.meta[s].k;
+                            f0_val[s] = ((unsigned long long)((uint32_t)r | ((uint32_t)err << 8)) << 32) | ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
+                            i++;
+                            break;
+                        }
+                        rejects++;
+                        if (rejects >= PHASE_A_K && (i + 1 < nq || cq > PHASE_A_K || q + 1 < rs.nseg)) { forced = true; i++; break; }
+                    }
+                    if (pended) break;
+                    if (!found && !forced && cq > PHASE_A_K) forced = true;     // this segment's listed survivors come before the next segment's slots
                 }
-                if (r > 0) {
-                    found = true; next = i + 1;
-                    parent[s] = a;
-                    f0_key[s] = ((unsigned long long)tb.meta[a].k << 32) | tb.meta[s].k;
-                    f0_val[s] = ((unsigned long long)((uint32_t)r | ((uint32_t)err << 8)) << 32) | ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
-                    break;
+                // slots i..nq-1 of this segment were not scored: they are recorded for phase B
+                if (q == 0) {
+                    for (; i < nq; i++) {
+                        if (found && parent[rs.slot(sv, 0, i)] == parent[s]) continue;     // hangs off the same parent: same tree, phase B would skip it
+                        wo.emit0 |= 1u << i;
+                    }
+                } else if (i < nq) {
+                    wo.xe_start = min(wo.xe_start, q * PHASE_A_K + i);
+                    wo.n_emit_x += nq - i;
                 }
             }
-            if (pended) next = nfirst;                                   // the continuation kernel owns the rest of this b
-            if (!found && !forced && !pended && c > PHASE_A_K) forced = true;       // all slots rejected and more survivors exist
             if (forced) force[s] = 1;
-            // slots not consumed: the survivors after m(b) (recorded for phase B)
-            for (uint32_t i = next; i < nfirst; i++) {
-                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
-                if (found && parent[a] == parent[s]) continue;           // hangs off the same parent: same tree, phase B would skip it
-                emit |= 1u << i;
-            }
-            emit_forced = forced;
+            wo.forced = forced;
+            if (pended) { wo.emit0 = 0; wo.xe_start = 0xFFFFFFFFu; wo.n_emit_x = 0; }       // the continuation kernel owns this b
         }
     }
     {
         // one reservation per warp for the recorded survivors
         const uint32_t lane = threadIdx.x & 31;
-        uint32_t cntl = __popc(emit), incl = cntl;
+        const uint32_t cntl = __popc(wo.emit0) + wo.n_emit_x;
+        uint32_t incl = cntl;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
         const uint32_t totalc = __shfl_sync(0xFFFFFFFFu, incl, 31);
         if (totalc) {
-            unsigned long long q = 0;
-            if (lane == 0) q = atomicAdd(&ctr->n_cand, (unsigned long long)totalc);
-            q = __shfl_sync(0xFFFFFFFFu, q, 0) + (incl - cntl);
-            while (emit) {
-                const uint32_t i = __ffs(emit) - 1;
-                emit &= emit - 1;
-                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
-                if (q < cand_cap) cand[q] = make_uint2(a | (emit_forced ? 0x80000000u : 0u), s);
-                q++;
+            unsigned long long w = 0;
+            if (lane == 0) w = atomicAdd(&ctr->n_cand, (unsigned long long)totalc);
+            w = __shfl_sync(0xFFFFFFFFu, w, 0) + (incl - cntl);
+            const uint32_t fl = wo.forced ? 0x80000000u : 0u;
+            uint32_t e = wo.emit0;
+            while (e) {
+                const uint32_t i = __ffs(e) - 1;
+                e &= e - 1;
+                if (w < cand_cap) cand[w] = make_uint2(rs.slot(sv, 0, i) | fl, s);
+                w++;
+            }
+            if (wo.n_emit_x) {
+                for (uint32_t q = max(1u, wo.xe_start / PHASE_A_K); q < rs.nseg; q++) {
+                    const uint32_t nq = min(rs.count(sv, q), PHASE_A_K);
+                    for (uint32_t i = 0; i < nq; i++) {
+                        if (q * PHASE_A_K + i < wo.xe_start) continue;
+                        if (w < cand_cap) cand[w] = make_uint2(rs.slot(sv, q, i) | fl, s);
+                        w++;
+                    }
+                }
             }
         }
     }
@@ -1396,47 +1573,58 @@ __device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTab
     return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
 }
 
-__global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *__restrict__ firstk,
-                                                         const uint32_t *__restrict__ cnt, uint8_t *force, uint32_t *parent,
-                                                         unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
+__global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
+                                                         uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
                                                          unsigned long long cand_cap, const uint2 *pending) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t np = ctr->n_pending;
     unsigned long long evals = 0, bytes = 0;
     for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < np; j += (gridDim.x * blockDim.x) >> 5) {
-        const uint32_t s = pending[j].x, start = pending[j].y;
-        const uint32_t c = cnt[s], nfirst = min(c, PHASE_A_K);
-        bool found = false;
-        uint32_t next = nfirst;
-        for (uint32_t i = start; i < nfirst; i++) {
-            const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
-            int r = 0, cd = 0, d = 0, err = 0;
-            if (lane == 0) {
-                bool scored;
-                r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
-                if (i > start) evals += scored;                      // slot `start` was already counted by k_phase_a
-            }
-            r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
-            cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
-            if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
-            if (r > 0) {
-                found = true; next = i + 1;
-                if (lane == 0) {
-                    parent[s] = a;
-                    f0_key[s] = ((unsigned long long)tb.meta[a].k << 32) | tb.meta[s].k;
-                    f0_val[s] = ((unsigned long long)((uint32_t)r | ((uint32_t)err << 8)) << 32) | ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
+        const uint32_t s = pending[j].x, start = pending[j].y;       // slots before `start` were scored (and rejected) by k_phase_a
+        RowSlots rs;
+        rs.init(sv, s);
+        bool found = false, forced = false;
+        uint32_t rejects = 0;
+        for (uint32_t q = 0; q < rs.nseg; q++) {
+            const uint32_t cq = rs.count(sv, q), nq = min(cq, PHASE_A_K);
+            uint32_t i = 0;
+            if (!found && !forced) {
+                for (; i < nq; i++) {
+                    const uint32_t li = q * PHASE_A_K + i;
+                    if (li < start) { rejects++; continue; }
+                    const uint32_t a = rs.slot(sv, q, i);
+                    int r = 0, cd = 0, d = 0, err = 0;
+                    if (lane == 0) {
+                        bool scored;
+                        r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
+                        if (li > start) evals += scored;                      // slot `start` was already counted by k_phase_a
+                    }
+                    r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
+                    cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
+                    if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
+                    if (r > 0) {
+                        found = true;
+                        if (lane == 0) {
+                            parent[s] = a;
+                            f0_key[s] = ((unsigned long long)tb.meta[a].k << 32) | tb.meta[s].k;
+                            f0_val[s] = ((unsigned long long)((uint32_t)r | ((uint32_t)err << 8)) << 32) | ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
+                        }
+                        i++;
+                        break;
+                    }
+                    rejects++;
+                    if (rejects >= PHASE_A_K && li >= start && (i + 1 < nq || cq > PHASE_A_K || q + 1 < rs.nseg)) { forced = true; i++; break; }
                 }
-                break;
+                if (!found && !forced && cq > PHASE_A_K) forced = true;
+            }
+            if (lane == 0) {
+                for (; i < nq; i++) {
+                    const unsigned long long w = atomicAdd(&ctr->n_cand, 1ull);
+                    if (w < cand_cap) cand[w] = make_uint2(rs.slot(sv, q, i) | (forced ? 0x80000000u : 0u), s);
+                }
             }
         }
-        if (lane == 0) {
-            if (!found && c > PHASE_A_K) force[s] = 1;
-            for (uint32_t i = next; i < nfirst; i++) {
-                const uint32_t a = firstk[(size_t)s * PHASE_A_K + i];
-                const unsigned long long q = atomicAdd(&ctr->n_cand, 1ull);
-                if (q < cand_cap) cand[q] = make_uint2(a, s);
-            }
-        }
+        if (lane == 0 && forced) force[s] = 1;
         __syncwarp();
     }
 #pragma unroll
