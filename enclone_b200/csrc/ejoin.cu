@@ -626,7 +626,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         h->launches += 2;                           // own kernels only; CUB's sort/RLE/scan launches are not counted
         CK(cudaEventRecord(h->ev[1], st));
         mark(h, "heads/scans/t2 sizes");
-        k_pack_c3<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, perm, gid, groups, ctr, c3);
+        k_pack_c3<<<(unsigned)(((size_t)n * 4 + 255) / 256), 256, 0, st>>>(h->din, perm, gid, groups, ctr, c3);
         // stride mode: the gathered edges of the other ranks need this rank's rows too -> pack every entry
         k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, surv_cnt, needed, force, n, stride > 1 ? 1 : 0);
         CK(cudaEventRecord(h->ev[2], st));

@@ -340,20 +340,20 @@ __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restri
     k_to_s[k] = s;
 }
 
-// one thread per (entry, c3 word); 8 threads per entry, W of them active.  The 32 bases of a word
+// 4 threads per entry, thread j packs the c3 words j, j+4 (W <= 4 for CDR3 pairs up to 128 nt: 3 of 4 lanes busy).  The 32 bases of a word
 // come from chain 0's CDR3, chain 1's, or both (the word that straddles the boundary).  Reads only the
 // early-uploaded arrays (CDR3 strings and lengths), so it runs before the rest of the input has landed.
 __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ gid_incl,
                                                  const GroupInfo *__restrict__ groups, DevCounters *ctr, uint32_t *__restrict__ c3) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t s = t >> 3, w = t & 7;
+    const uint32_t s = t >> 2;
     if (s >= (uint32_t)ctr->n_valid) return;
     const uint32_t k = perm[s];
     const GroupInfo g = groups[gid_incl[s] - 1];
     const int cl0 = in.cdr3_len[0][k], total = cl0 + in.cdr3_len[1][k];
     const int W = g.W;
-    if ((int)w >= W) return;
     const uint32_t c3off = g.c3base + (s - g.start) * 2 * W;
+    for (uint32_t w = t & 3; (int)w < W; w += 4) {
     const int p0 = 32 * (int)w;
     const int nb = total - p0;                                 // valid bytes in this word
     uint32_t x[8];
@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const uint32_t *__res
     const uint32_t valid = low_bits(nb);
     c3[c3off + w] = H & valid;
     c3[c3off + W + w] = L & valid;
+    }
 }
 
 // 32 bytes at byte offset `off` of a shared-memory staging buffer (16-byte aligned base)
