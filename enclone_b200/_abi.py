@@ -83,7 +83,8 @@ class EjoinStats(C.Structure):
         "alg_bytes_tier1", "alg_bytes_tier2", "alg_bytes_pack")] + [
         (n, C.c_double) for n in (
             "ms_h2d", "ms_device", "ms_d2h", "ms_host_post", "ms_total",
-            "ms_kernel_tier1", "ms_kernel_tier2", "ms_kernel_pack", "ms_kernel_other")]
+            "ms_kernel_tier1", "ms_kernel_tier2", "ms_kernel_pack", "ms_kernel_other")] + [
+        ("alg_bytes_pack_t2", C.c_uint64), ("ms_kernel_pack_t2", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

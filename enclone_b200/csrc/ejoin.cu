@@ -534,6 +534,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cub_bytes = std::max(cub_bytes, tmpb);
         cub::DeviceScan::ExclusiveSum(nullptr, tmpb, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
         cub_bytes = std::max(cub_bytes, tmpb);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpb, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n);
+        cub_bytes = std::max(cub_bytes, tmpb);
         const size_t t2_units = 3 * ((size_t)(h->tig_bytes / 128) + 2 * (size_t)n) + 16;
         const size_t c3_words = (size_t)n * 2 * T1_WMAX + 4 * (size_t)n + 64;
         Sizer sz;
@@ -541,6 +543,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                                                     // head_pos, bucket_start
         sz.take(8 * (size_t)n + 8); sz.take(4 * (size_t)n + 4); sz.take(64);                                // uniq, counts, num_runs
         sz.take(sizeof(GroupInfo) * ((size_t)n + 1));
+        sz.take(8 * (size_t)n); sz.take(8 * (size_t)n); sz.take(4 * (size_t)n);                             // group-table scans
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                             // t2sizes, t2off, gid
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
@@ -562,6 +565,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         unsigned long long *uniq = A.take<unsigned long long>((size_t)n + 1);
         uint32_t *counts = A.take<uint32_t>((size_t)n + 1), *num_runs = A.take<uint32_t>(16);
         GroupInfo *groups = A.take<GroupInfo>((size_t)n + 1);
+        unsigned long long *sumA = A.take<unsigned long long>(n), *sumB = A.take<unsigned long long>(n);
+        uint32_t *sumC = A.take<uint32_t>(n);
         uint32_t *t2sizes = A.take<uint32_t>(n), *t2off = A.take<uint32_t>(n), *gid = A.take<uint32_t>(n);
         EntryMeta *meta = A.take<EntryMeta>(n);
         uint32_t *c3 = A.take<uint32_t>(c3_words);
@@ -610,8 +615,16 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         mark(h, "sort entries");
         tb = cub_bytes;
         cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
-        k_group_scan<<<1, 512, 0, st>>>(uniq, counts, num_runs, groups, (const uint16_t *)h->d_cdmax.p, ctr);
-        mark(h, "rle + k_group_scan");
+        k_group_vals<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, n, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, ctr);
+        tb = cub_bytes;
+        cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumA, sumA, (int)n, st);
+        tb = cub_bytes;
+        cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumB, sumB, (int)n, st);
+        tb = cub_bytes;
+        cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumC, sumC, (int)n, st);
+        k_group_build<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, groups, ctr);
+        h->launches += 1;
+        mark(h, "rle + group table");
         k_item_hist<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, item_cap, stride, phase);
         k_item_scatter<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, order, item_cap, stride, phase);
         h->launches += 2;
@@ -640,6 +653,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         mark(h, "k_sweep");
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)
         k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, needed, pr.ref_v_trim, pr.ref_j_trim);
+        CK(cudaEventRecord(h->ev[7], st));
         mark(h, "k_meta");
         if (h->copy_pending && h->n_chunks > 0) {
             // pack each chunk's (needed) entries as its bytes land (an entry belongs to the chunk that completes it)
@@ -753,6 +767,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         float ms;
         float ms2;
         cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); cudaEventElapsedTime(&ms2, h->ev[3], h->ev[6]); h->stats.ms_kernel_pack = ms + ms2;   // meta + c3, then t2 rows
+        cudaEventElapsedTime(&ms, h->ev[7], h->ev[6]); h->stats.ms_kernel_pack_t2 = ms;
         cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->stats.ms_kernel_tier1 = ms;                                                        // the sweep
         cudaEventElapsedTime(&ms, h->ev[6], h->ev[4]); h->stats.ms_kernel_tier2 = ms;                                                        // phase A + phase B
         float tot;
@@ -777,6 +792,8 @@ void fill_stats(ejoin_handle *h, ejoin_stats_t *s) {
     s->gpu_launches = h->launches; s->h2d_bytes = h->h2d_bytes;
     if (h->tigs_in_place) { unsigned long long ib = 0; for (int i = 0; i < 32; i++) ib += c.inplace_bytes[i]; s->h2d_bytes += ib; }   // bytes k_pack_t2 pulled over PCIe
     s->alg_bytes_tier1 = c.t1_alg_bytes; s->alg_bytes_tier2 = c.t2_alg_bytes;
+    { unsigned long long pb = 0; for (int i = 0; i < 32; i++) pb += c.pack_bytes[i]; s->alg_bytes_pack_t2 = pb; }
+    s->ms_kernel_pack_t2 = h->stats.ms_kernel_pack_t2;
     s->alg_bytes_pack = h->tig_bytes + c.n_valid * sizeof(EntryMeta) + c.c3_words * 4 + c.t2_units * 16;
     s->ms_kernel_pack = h->stats.ms_kernel_pack; s->ms_kernel_tier1 = h->stats.ms_kernel_tier1; s->ms_kernel_tier2 = h->stats.ms_kernel_tier2;
     s->ms_kernel_other = h->stats.ms_kernel_other; s->ms_device = h->stats.ms_device;

@@ -64,9 +64,7 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
     if (threadIdx.x == 0) { atomicAdd(&ctr->pairs_candidate, s); atomicAdd(&ctr->n_buckets, h); }
 }
 
-// K2  group table from the run-length encoded sorted keys.  One block: every thread owns a contiguous
-// chunk of runs, sums its chunk, the block scans the 512 chunk sums, and a second pass over the
-// chunk writes the GroupInfo records with the running prefix.
+// K2  group table from the run-length encoded sorted keys.
 struct GroupVals { unsigned long long v[6]; uint32_t W, cdm, T; bool valid; };   // entries, work items, c3 words, pairs, tier-1 bytes, extra slot rows
 __device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned long long n, const uint16_t *__restrict__ cdmax_tab) {
     GroupVals o;
@@ -92,55 +90,64 @@ __device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned
     o.v[2] = (n * 2 * W + 3) & ~3ull;
     return o;
 }
-__global__ void __launch_bounds__(512) k_group_scan(const unsigned long long *__restrict__ uniq, const uint32_t *__restrict__ counts,
-                                                     const uint32_t *num_runs, GroupInfo *groups, const uint16_t *__restrict__ cdmax_tab,
-                                                     DevCounters *ctr) {
-    typedef cub::BlockScan<unsigned long long, 512> BS;
-    __shared__ typename BS::TempStorage tmp;
+// Three kernels around three device-wide exclusive sums (CUB decoupled look-back): the number of runs is only known on
+// the device, so the scans run over n slots (runs <= n) with zeros behind the last run.
+//   sumA = entries | work items << 32   (both totals < 2^32),   sumB = c3 words,   sumC = extra slot rows
+__global__ void __launch_bounds__(256) k_group_vals(const unsigned long long *__restrict__ uniq, const uint32_t *__restrict__ counts,
+                                                    const uint32_t *num_runs, uint32_t n, const uint16_t *__restrict__ cdmax_tab,
+                                                    unsigned long long *__restrict__ sumA, unsigned long long *__restrict__ sumB,
+                                                    uint32_t *__restrict__ sumC, DevCounters *ctr) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nr = *num_runs;
-    const uint32_t chunk = (nr + 511) / 512;
-    const uint32_t r0 = min(nr, threadIdx.x * chunk), r1 = min(nr, r0 + chunk);
-    unsigned long long sum[6] = {0, 0, 0, 0, 0, 0};
-    unsigned long long ngroups = 0;
-    for (uint32_t r = r0; r < r1; r++) {
-        const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
-#pragma unroll
-        for (int f = 0; f < 6; f++) sum[f] += gv.v[f];
-    }
-    unsigned long long pre[6], agg[6];
-#pragma unroll
-    for (int f = 0; f < 6; f++) {
-        BS(tmp).ExclusiveSum(sum[f], pre[f], agg[f]);
-        __syncthreads();
-    }
-    for (uint32_t r = r0; r < r1; r++) {
-        const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
-        if (gv.valid) {
-            GroupInfo g;
-            g.start = (uint32_t)pre[0];
-            g.n = counts[r];
-            g.c3base = (uint32_t)pre[2];
-            g.work_off = (uint32_t)pre[1];
-            g.xoff = (uint32_t)pre[5];
-            g.W = (uint16_t)gv.W; g.cdmax = (uint16_t)gv.cdm; g.tiles = (uint16_t)gv.T; g.seg = (uint16_t)seg_of_tiles(gv.T); g.pad = 0;
-            groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
-            ngroups = r + 1;
+    unsigned long long pairs = 0, t1b = 0, ng = 0;
+    if (r < n) {
+        unsigned long long a = 0, b = 0;
+        uint32_t x = 0;
+        if (r < nr) {
+            const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
+            a = gv.v[0] | (gv.v[1] << 32); b = gv.v[2]; x = (uint32_t)gv.v[5];
+            pairs = gv.v[3]; t1b = gv.v[4];
+            if (gv.valid) ng = r + 1;
         }
-#pragma unroll
-        for (int f = 0; f < 6; f++) pre[f] += gv.v[f];
+        sumA[r] = a; sumB[r] = b; sumC[r] = x;
     }
-    // number of groups = number of valid runs
-    typedef cub::BlockReduce<unsigned long long, 512> BR;
-    __shared__ typename BR::TempStorage tmp2;
-    unsigned long long ng = BR(tmp2).Reduce(ngroups, MaxOp());
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    pairs = BR(tmp).Sum(pairs);
+    __syncthreads();
+    t1b = BR(tmp).Sum(t1b);
+    __syncthreads();
+    ng = BR(tmp).Reduce(ng, MaxOp());
     if (threadIdx.x == 0) {
-        ctr->n_groups = ng;
-        ctr->n_valid = agg[0];
-        ctr->n_work = agg[1];
-        ctr->c3_words = agg[2];
-        ctr->pairs_compared = agg[3];
-        ctr->t1_alg_bytes = agg[4];
-        ctr->n_xrows = agg[5];
+        if (pairs) { atomicAdd(&ctr->pairs_compared, pairs); atomicAdd(&ctr->t1_alg_bytes, t1b); }
+        if (ng) atomicMax(&ctr->n_groups, ng);         // number of groups = number of valid runs (they precede the ~0 run)
+    }
+}
+__global__ void __launch_bounds__(256) k_group_build(const unsigned long long *__restrict__ uniq, const uint32_t *__restrict__ counts,
+                                                     const uint32_t *num_runs, const uint16_t *__restrict__ cdmax_tab,
+                                                     const unsigned long long *__restrict__ sumA, const unsigned long long *__restrict__ sumB,
+                                                     const uint32_t *__restrict__ sumC, GroupInfo *__restrict__ groups, DevCounters *ctr) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nr = *num_runs;
+    if (r >= nr) return;
+    const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
+    const unsigned long long a = sumA[r], b = sumB[r];
+    const uint32_t x = sumC[r];
+    if (gv.valid) {
+        GroupInfo g;
+        g.start = (uint32_t)(a & 0xFFFFFFFFull);
+        g.n = counts[r];
+        g.c3base = (uint32_t)b;
+        g.work_off = (uint32_t)(a >> 32);
+        g.xoff = x;
+        g.W = (uint16_t)gv.W; g.cdmax = (uint16_t)gv.cdm; g.tiles = (uint16_t)gv.T; g.seg = (uint16_t)seg_of_tiles(gv.T); g.pad = 0;
+        groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
+    }
+    if (r == nr - 1) {               // totals = exclusive prefix of the last run + its own values
+        ctr->n_valid = (a & 0xFFFFFFFFull) + gv.v[0];
+        ctr->n_work = (a >> 32) + gv.v[1];
+        ctr->c3_words = b + gv.v[2];
+        ctr->n_xrows = (unsigned long long)x + gv.v[5];
     }
 }
 
@@ -454,6 +461,7 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
     __syncwarp();
     const int nw0 = 4 * ((n0 + 127) / 128), nw = nw0 + 4 * ((n1 + 127) / 128);
     uint32_t *rows = (uint32_t *)(t2 + m.t2off);
+    if (lane == 0) atomicAdd(&ctr->pack_bytes[blockIdx.x & 31], (unsigned long long)(n0 + n1) + 12ull * nw);     // ASCII in, three plane words out per 32 bases
     int mcount0 = 0, mcount1 = 0;
     uint32_t weird0 = 0, weird1 = 0;
     for (int w = (int)lane; w < nw; w += 32) {

@@ -160,6 +160,8 @@ typedef struct ejoin_stats {
     uint64_t alg_bytes_pack;     /* ASCII bytes read + packed rows and meta written by the pack kernel */
     double   ms_h2d, ms_device, ms_d2h, ms_host_post, ms_total; /* wall, host clock */
     double   ms_kernel_tier1, ms_kernel_tier2, ms_kernel_pack, ms_kernel_other; /* CUDA events */
+    uint64_t alg_bytes_pack_t2;  /* k_pack_t2 alone: V..J bytes read + t2 row bytes written, needed entries only */
+    double   ms_kernel_pack_t2;  /* k_pack_t2 alone (CUDA events); with a chunked or in-place upload it includes the wait for the bytes */
 } ejoin_stats_t;
 
 typedef struct ejoin_result {
