@@ -1309,15 +1309,22 @@ __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restri
             for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
             const uint32_t totalc = __shfl_sync(0xFFFFFFFFu, incl, 31);
             mycnt += cntl;
-            if (totalc > SWEEP_STAGE) {               // a dense block: straight to the list
+            if (totalc > SWEEP_STAGE) {
+                // a dense block (a clonal family meeting itself): straight to the list, one a at a time, so that the
+                // lanes holding a survivor of that a store to consecutive slots (b-major runs of 32 would make
+                // every store instruction touch 32 sectors)
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&cx.ctr->n_cand, (unsigned long long)totalc);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cntl);
-                while (bits) {
-                    const uint32_t aa = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    if (base < cx.cand_cap) cx.cand[base] = make_uint2(posA0 + a0 + aa, posB);
-                    base++;
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                uint32_t cols = __reduce_or_sync(0xFFFFFFFFu, bits);
+                while (cols) {
+                    const uint32_t aa = __ffs(cols) - 1;
+                    cols &= cols - 1;
+                    const bool mine = (bits >> aa) & 1u;
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+                    const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
+                    if (mine && o < cx.cand_cap) cx.cand[o] = make_uint2(posA0 + a0 + aa, posB);
+                    base += __popc(m);
                 }
             } else {
                 if (fill + totalc > SWEEP_STAGE) sweep_flush(cx, stage, fill);
