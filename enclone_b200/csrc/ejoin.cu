@@ -100,6 +100,7 @@ struct ejoin_handle {
     std::vector<uint16_t> cdmax_host;
     std::vector<DevBuf> p1_tables;
     unsigned long long xrow_cap = 0;
+    std::vector<uint32_t> ref_plane_off;   // host copy of DevIn::ref_plane_off (kept alive for the async upload)
     unsigned long long cand_cap = 0;    // survivor list (tier-1 survivors beyond the phase-A slots)
     unsigned long long edge_cap = 0;    // to-be-scored lists, accepted edges, sort arrays
     // work pointers of the last pipeline run
@@ -330,6 +331,7 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     for (int i = 0; i < 4; i++) sz.take(4 * (size_t)std::max(1u, pk->n_exact));
     sz.take(8 * (size_t)std::max(1u, pk->n_refseq)); sz.take(4 * (size_t)std::max(1u, pk->n_refseq));
     sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 512);
+    sz.take(4 * (size_t)std::max(1u, pk->n_refseq)); sz.take(12 * ((size_t)pk->refseq_arena_bytes / 32 + 3 * (size_t)pk->n_refseq + 8));   // germline planes
     CK(h->in_arena.buf.ensure(sz.off + 4096));
     h->in_arena.reset();
     Arena &A = h->in_arena;
@@ -380,6 +382,16 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     CK(up(d.donor_lo, pk->donor_lo, pk->n_exact)); CK(up(d.donor_hi, pk->donor_hi, pk->n_exact));
     CK(up(d.refseq_off, pk->refseq_off, pk->n_refseq)); CK(up(d.refseq_len, pk->refseq_len, pk->n_refseq));
     CK(up(d.refseq_arena, pk->refseq_arena, pk->refseq_arena_bytes));
+    {
+        // germline bit planes: offsets from the host's lengths; the planes themselves are built by k_pack_ref
+        h->ref_plane_off.resize(pk->n_refseq ? pk->n_refseq : 1);
+        uint32_t words = 0;
+        for (uint32_t i = 0; i < pk->n_refseq; i++) { h->ref_plane_off[i] = words + 1; words += (pk->refseq_len[i] + 31) / 32 + 2; }
+        d.ref_plane_words = words + 2;
+        CK(up(d.ref_plane_off, h->ref_plane_off.data(), pk->n_refseq));
+        d.ref_planes = A.take<uint32_t>(3 * (size_t)d.ref_plane_words);
+        CK(cudaMemsetAsync(d.ref_planes, 0, 12 * (size_t)d.ref_plane_words, h->st_copy));
+    }
     CK(cudaEventRecord(h->ev_small, h->st_copy));       // everything but the V..J bytes: keys / sort / groups / meta / c3 can start
     h->tigs_in_place = in_place;
     if (in_place) {
@@ -653,6 +665,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         mark(h, "k_sweep");
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)
         k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, needed, pr.ref_v_trim, pr.ref_j_trim);
+        k_pack_ref<<<std::max(1u, h->din.n_refseq), 32, 0, st>>>(h->din);
+        h->launches += 1;
         CK(cudaEventRecord(h->ev[7], st));
         mark(h, "k_meta");
         if (h->copy_pending && h->n_chunks > 0) {
@@ -660,12 +674,12 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             uint64_t prev = 0;
             for (int i = 0; i < h->n_chunks; i++) {
                 CK(cudaStreamWaitEvent(st, h->ev_chunk[i == h->n_chunks - 1 ? 7 : i], 0));
-                k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, prev, h->chunk_end[i]);
+                k_pack_t2<<<(unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, prev, h->chunk_end[i]);
                 prev = h->chunk_end[i];
             }
             h->launches += h->n_chunks - 1;
         } else {
-            k_pack_t2<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, 0ull, ~0ull);
+            k_pack_t2<<<(unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, 0ull, ~0ull);
         }
         CK(cudaEventRecord(h->ev[6], st));
         mark(h, "k_pack_t2");

@@ -119,6 +119,11 @@ struct DevIn {
     const uint64_t *refseq_off;
     const uint32_t *refseq_len;
     const uint8_t *refseq_arena;
+    // germline bit planes (k_pack_ref): per sequence ceil(len/32) words + one zero word before and after;
+    // plane p of word w of sequence i = ref_planes[p * ref_plane_words + ref_plane_off[i] + w], p = H, L, N (not ACGT)
+    const uint32_t *ref_plane_off;
+    uint32_t *ref_planes;
+    uint32_t ref_plane_words;
 };
 
 // Everything tier 2 needs

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) k_t2_sizes(DevIn in, const uint32_t *perm
 // ASCII bytes (CloneInfo.tigs / cdr3s / vs / js), in three kernels:
 //   k_meta     one thread per entry: ids, lengths, window bounds, flags            -> meta
 //   k_pack_c3  one thread per 32-base word of the concatenated CDR3s               -> c3 rows
-//   k_pack_t2  one warp per entry, one LANE per 32-base plane word: 32 bases are read with three
+//   k_pack_t2  one half warp per entry, one LANE per 32-base plane word: 32 bases are read with three
 //              16-byte loads per sequence and reduced in registers with SWAR byte tricks
 //              (no cross-lane traffic); H/L/M words go straight to the 128-bit rows       -> t2 rows
 // ---------------------------------------------------------------------------------------------
@@ -416,6 +416,32 @@ __device__ __forceinline__ void load32s(const uint8_t *buf, uint32_t off, uint32
     }
 }
 
+// Germline table -> bit planes H, L (the 2-bit code) and N (byte is not one of ACGT), one block per sequence.
+__global__ void __launch_bounds__(32) k_pack_ref(DevIn in) {
+    const uint32_t i = blockIdx.x;
+    if (i >= in.n_refseq) return;
+    const int len = (int)in.refseq_len[i];
+    const uint8_t *src = in.refseq_arena + in.refseq_off[i];
+    const uint32_t TW = in.ref_plane_words, o = in.ref_plane_off[i];
+    for (int w = (int)threadIdx.x; w * 32 < len; w += 32) {
+        const int nb = len - 32 * w;
+        uint32_t x[8];
+        load32u(src + 32 * w, x);
+        uint32_t N = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            x[q] &= low_bytes(nb - 4 * q);
+            N |= ((nonzero_bytes(not_acgt(x[q]) & low_bytes(nb - 4 * q)) * 0x01020408u) >> 24 & 0xFu) << (4 * q);
+        }
+        uint32_t H, L;
+        planes32(x, H, L);
+        const uint32_t valid = low_bits(nb);
+        in.ref_planes[o + w] = H & valid;
+        in.ref_planes[TW + o + w] = L & valid;
+        in.ref_planes[2 * TW + o + w] = N & valid;
+    }
+}
+
 // [wm_lo, wm_hi): only the entries whose last V..J byte lies in this range of the caller's arena are
 // packed by this launch (the arena is uploaded in chunks; see upload_range).  Each warp first copies
 // its entry's bytes into shared memory with non-overlapping aligned 16-byte loads — in zero-copy mode
@@ -424,9 +450,12 @@ __device__ __forceinline__ void load32s(const uint8_t *buf, uint32_t off, uint32
 #define PACK_STAGE 544          // per chain: 512 bytes + alignment slack + the 48-byte window overrun
 __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
                                                  const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi) {
-    __shared__ __align__(16) uint8_t stage[8][2][PACK_STAGE];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // one HALF warp per entry: a 2 x 350-base entry has 44 plane words = 3 passes of 16 lanes (92 % of the lane slots;
+    // a whole warp needed 2 passes of 32 = 69 %)
+    __shared__ __align__(16) uint8_t stage[16][2][PACK_STAGE];
+    const uint32_t lane = threadIdx.x & 15, wib = threadIdx.x >> 4;
+    const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);          // the lanes of this half warp
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     if (s >= (uint32_t)ctr->n_valid) return;
     if (!needed[s]) return;                       // no CDR3-compatible partner: its rows are never read
     const EntryMeta &m = meta[s];
@@ -452,19 +481,19 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
         uint4 *mir = in.tig_copy ? (uint4 *)(((uintptr_t)(in.tig_copy + in.tig_off[c][k])) & ~(uintptr_t)15) : nullptr;
         if (staged[c]) {
             uint4 *dst = (uint4 *)stage[wib][c];
-            for (int i = (int)lane; i < nchunks; i += 32) { const uint4 v = src[i]; dst[i] = v; if (mir) mir[i] = v; }
+            for (int i = (int)lane; i < nchunks; i += 16) { const uint4 v = src[i]; dst[i] = v; if (mir) mir[i] = v; }
         } else if (mir) {
-            for (int i = (int)lane; i < nchunks; i += 32) mir[i] = src[i];
+            for (int i = (int)lane; i < nchunks; i += 16) mir[i] = src[i];
         }
         if (lane == 0 && in.tig_copy) atomicAdd(&ctr->inplace_bytes[blockIdx.x & 31], 16ull * nchunks);
     }
-    __syncwarp();
+    __syncwarp(hmask);
     const int nw0 = 4 * ((n0 + 127) / 128), nw = nw0 + 4 * ((n1 + 127) / 128);
     uint32_t *rows = (uint32_t *)(t2 + m.t2off);
     if (lane == 0) atomicAdd(&ctr->pack_bytes[blockIdx.x & 31], (unsigned long long)(n0 + n1) + 12ull * nw);     // ASCII in, three plane words out per 32 bases
     int mcount0 = 0, mcount1 = 0;
     uint32_t weird0 = 0, weird1 = 0;
-    for (int w = (int)lane; w < nw; w += 32) {
+    for (int w = (int)lane; w < nw; w += 16) {
         const int c = w >= nw0;
         const int wl = c ? w - nw0 : w;                       // word index inside the chain
         const int n = c ? n1 : n0;
@@ -486,24 +515,32 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
             H &= valid; L &= valid;
             const int vend = m.vend[c], jstart = m.jstart[c];
             const uint32_t inV = low_bits(vend - p0) & valid, inJ = valid & ~low_bits(jstart - p0);
-            if (inV) {
-                uint32_t r[8];
-                load32u(in.refseq_arena + in.refseq_off[m.vs[c]] + p0, r);
-                M |= neq32(x, r) & inV;
+            // mutation mask from the germline's own bit planes (k_pack_ref): an ACGT base differs from the germline
+            // byte iff the 2-bit codes differ or the germline byte is not ACGT (entries with non-ACGT bases of their
+            // own are flagged for the bytewise path and never read their M plane)
+            const uint32_t TW = in.ref_plane_words;
+            if (inV) {                                        // germline position = p: same word, same alignment
+                const uint32_t o = in.ref_plane_off[m.vs[c]] + (uint32_t)wl;
+                M |= ((H ^ in.ref_planes[o]) | (L ^ in.ref_planes[TW + o]) | in.ref_planes[2 * TW + o]) & inV;
             }
-            if (inJ) {
+            if (inJ) {                                        // germline position = p - (n - |j|): any bit offset
                 const uint32_t ji = m.js[c];
-                uint32_t r[8];
-                load32u(in.refseq_arena + in.refseq_off[ji] + (p0 - (n - (int)in.refseq_len[ji])), r);
-                M |= neq32(x, r) & inJ;
+                const int off = p0 - (n - (int)in.refseq_len[ji]);        // >= -31 for a word that meets the J window
+                const int wi = off >> 5;                                  // >= -1: the zero word in front
+                const uint32_t bo = (uint32_t)off & 31u;
+                const uint32_t *g = in.ref_planes + in.ref_plane_off[ji] + wi;
+                const uint32_t gH = __funnelshift_r(g[0], g[1], bo), gL = __funnelshift_r(g[TW], g[TW + 1], bo);
+                const uint32_t gN = __funnelshift_r(g[2 * TW], g[2 * TW + 1], bo);
+                M |= ((H ^ gH) | (L ^ gL) | gN) & inJ;
             }
             if (c) mcount1 += __popc(M); else mcount0 += __popc(M);
         }
         const int o = (w >> 2) * 12 + (w & 3);
         rows[o] = H; rows[o + 4] = L; rows[o + 8] = M;
     }
-    mcount0 = warp_sum_i(mcount0); mcount1 = warp_sum_i(mcount1);
-    const bool g0 = __any_sync(0xFFFFFFFFu, weird0 != 0), g1 = __any_sync(0xFFFFFFFFu, weird1 != 0);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { mcount0 += __shfl_xor_sync(hmask, mcount0, o); mcount1 += __shfl_xor_sync(hmask, mcount1, o); }
+    const bool g0 = __any_sync(hmask, weird0 != 0), g1 = __any_sync(hmask, weird1 != 0);
     if (lane == 0) {
         EntryMeta *mm = &meta[s];
         mm->m[0] = (uint16_t)mcount0; mm->m[1] = (uint16_t)mcount1;
@@ -602,7 +639,7 @@ __device__ __forceinline__ bool region_bounds(const EntryMeta &a, const EntryMet
 }
 
 __device__ __forceinline__ void emit_raw(const DevParams &pr, DevCounters *ctr, ejoin_raw_edge_t *acc, unsigned long long cap,
-                                         uint32_t *minnbr, uint32_t k1, uint32_t k2, int cd, int d, int reason, int err, bool accepted) {
+                                         uint32_t k1, uint32_t k2, int cd, int d, int reason, int err, bool accepted) {
     // warp-aggregated append
     const uint32_t lane = threadIdx.x & 31;
     uint32_t mask = __ballot_sync(__activemask(), accepted);
@@ -617,7 +654,6 @@ __device__ __forceinline__ void emit_raw(const DevParams &pr, DevCounters *ctr, 
         e.flags = (uint32_t)reason | ((uint32_t)err << 8);
         acc[base] = e;
     }
-    (void)minnbr;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -739,14 +775,12 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5  tier 2, phase B.  k_phaseb_filter: one thread per recorded survivor; keeps (compacted) those
-// that must be scored: endpoints in different phase-A trees, or the force bit.  k_tier2: one thread
-// per kept pair, full evaluation (dense, so warps stay converged).
+// K5  tier 2, phase B.  k_phaseb_split (pass 1 over the recorded survivors): the survivors of entries
+// that gave up in phase A (force) go to `todo` (all scored in round 1); the others are kept, compacted,
+// in `rest` unless they visibly hang off the same phase-A parent (same tree: never a forest edge).
+// k_phaseb_cross (pass 2, after round 1 and the pointer doubling) keeps from `rest` the pairs whose
+// endpoints lie in different trees.  k_tier2: one thread per kept pair, full evaluation.
 // ---------------------------------------------------------------------------------------------
-// Pass 1 over the recorded survivors: the survivors of entries that gave up in phase A (force) go to
-// `todo` (all scored in round 1); the others are kept, compacted, in `rest` unless they visibly hang
-// off the same phase-A parent (same tree: never a forest edge).  Pass 2 (after round 1 and the pointer
-// doubling) keeps from `rest` the pairs whose endpoints lie in different trees.
 // Block-level compaction for the list filters below: every thread brings up to SPLIT_ITEMS flagged items for each of
 // two output lists; one atomicAdd per list and block tile reserves the slots (a per-warp atomic on one counter was the
 // whole cost of these kernels: ~1M same-address atomics per launch).
@@ -836,7 +870,6 @@ __global__ void __launch_bounds__(256) k_phaseb_cross(const uint2 *__restrict__ 
 __global__ void __launch_bounds__(128, 6) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
                                                unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t k_base,
                                                uint32_t *parent_min) {
-    uint32_t *minnbr = nullptr;
     unsigned long long ntodo = ctr->n_todo;
     if (ntodo > cand_cap) ntodo = cand_cap;
     unsigned long long my_pairs = 0, my_bytes = 0;      // per-thread tallies, one atomic per warp at the end
@@ -861,7 +894,7 @@ __global__ void __launch_bounds__(128, 6) k_tier2(DevIn in, DevTables tb, DevPar
             // round 1: the smallest accepted partner of b becomes its phase-A parent after all
             if (accepted && parent_min) atomicMin(&parent_min[c.y], c.x);
         }
-        emit_raw(pr, ctr, acc, cand_cap, minnbr, k1 + k_base, k2 + k_base, cd, d, reason, err, accepted);
+        emit_raw(pr, ctr, acc, cand_cap, k1 + k_base, k2 + k_base, cd, d, reason, err, accepted);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -982,29 +1015,10 @@ __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const En
 __device__ __forceinline__ void bytewise_counts(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
     bytewise_counts_t<true>(in, pr, m1, m2, pc);
 }
-// One thread scores a pair bytewise (phase A, for the rare pairs evaluate_thread() sends back with -1;
-// the pair is already past the CDR3 and meta gates).  sa < sb positions of one group.
-__device__ __noinline__ int evaluate_thread_bytewise(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa,
-                                                     uint32_t sb, int *cd_out, int *d_out) {
-    const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
-    PairCounts pc;
-    bytewise_counts_t<false>(in, pr, m1, m2, pc);
-    atomicAdd(&ctr->n_generic, 1ull);
-    *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
-    if (!pr.is_bcr || pr.max_diffs < 1000000) {
-        int cap = pr.max_diffs;
-        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
-        if (pc.diffs > cap) return 0;
-    }
-    int kk; double p1, mult, score;
-    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
-}
-
 // K6  tier 2, bytewise: one warp per queued pair (already past the CDR3 and meta gates).
 __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *generic_q,
                                                        unsigned long long cap, ejoin_raw_edge_t *acc, uint32_t k_base, uint32_t *parent_min,
                                                        int round2) {
-    uint32_t *minnbr = nullptr;
     const unsigned long long q_begin = round2 ? ctr->n_generic_r1 : 0ull;
     unsigned long long nq = ctr->n_generic_q;
     if (nq > cap) nq = cap;
@@ -1031,7 +1045,7 @@ __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, D
         }
         if (lane == 0) {
             if (reason != 0 && parent_min) atomicMin(&parent_min[c.y], c.x);
-            emit_raw(pr, ctr, acc, cap, minnbr, m1.k + k_base, m2.k + k_base, pc.cd0 + pc.cd1, d, reason, err, reason != 0);
+            emit_raw(pr, ctr, acc, cap, m1.k + k_base, m2.k + k_base, pc.cd0 + pc.cd1, d, reason, err, reason != 0);
         }
     }
 }
@@ -1188,10 +1202,6 @@ __global__ void k_root_jump(uint32_t *parent, uint32_t n) {
     parent[i] = p;
 }
 
-__global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 
 // ---------------------------------------------------------------------------------------------
 // p1 tables: one block per n (= 3 * L), see dd.cuh.  Phase 1: T_j(k) into scratch;

@@ -180,6 +180,41 @@ def test_stride_mode_giant_bucket():
         j.close()
 
 
+def test_stride_mode_segmented_rows_three_ranks():
+    """A 10,000-entry bucket: rows of up to 79 tiles are cut into 10 segments (extra slot rows, capacity
+    retry) and dealt to three ranks row by row; the gathered edges must replay to the single-GPU join."""
+    pack, _ = synth.generate_config("C4", 0.05)
+    single = join_exacts(pack)
+    oe, oc, _ = O.join_exacts(pack.struct)
+    assert_same_join(single, oe, oc, what="C4x0.05 single")
+    world = 3
+    raws, js = [], []
+    for rank in range(world):
+        j = Joiner(default_params())
+        raw, st = j.run_shard(pack.struct, rank, world)
+        raws.append(raw)
+        js.append(j)
+    fin = js[0].finish(pack.struct, np.concatenate(raws))
+    assert np.array_equal(fin.edges, single.edges) and np.array_equal(fin.class_of, single.class_of)
+    for j in js:
+        j.close()
+
+
+def test_upload_shard_resident_matches_shard_run():
+    pack, _ = synth.generate(n_cells=12000, n_donors=2, seed=31)
+    world = 3
+    total = 0
+    for rank in range(world):
+        j = Joiner(default_params())
+        mode, fin, raw, st = j.run_shard_final(pack.struct, rank, world)
+        j.upload_shard(pack.struct, rank, world)
+        s = j.run_resident()
+        assert s["pairs_accepted"] == st["pairs_accepted"] and s["edges_after_prune"] == len(fin.edges)
+        total += len(fin.edges)
+        j.close()
+    assert total == len(join_exacts(pack).edges)
+
+
 @pytest.mark.parametrize("name,scale", [("C3", 1.0), ("C5", 1.0), ("C4", 0.1), ("C2", 1.0)])
 def test_full_size_configs_against_oracle(name, scale):
     """BASELINE.json's configurations at (or near) full size: bit-exact edges, per-edge integers and
