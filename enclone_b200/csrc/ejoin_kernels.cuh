@@ -952,11 +952,58 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
-// WARP = true: the 32 lanes of a warp split the positions and reduce with shuffles; WARP = false: one thread does it all.
+// 16 bytes starting at an arbitrary address, from two aligned 16-byte loads (every arena carries >= 64 bytes of
+// slack behind its last byte).  out[i] holds bytes 4i..4i+3.
+__device__ __forceinline__ void load16u(const uint8_t *p, uint32_t (&out)[4]) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint4 *q = (const uint4 *)(a & ~(uintptr_t)15);
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
+    const uint32_t w[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+    const uint32_t sh = 8u * (uint32_t)(a & 3);
+    switch ((a >> 2) & 3) {
+        case 0:
+#pragma unroll
+            for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
+            break;
+        case 1:
+#pragma unroll
+            for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(w[i + 1], w[i + 2], sh);
+            break;
+        case 2:
+#pragma unroll
+            for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(w[i + 2], w[i + 3], sh);
+            break;
+        default:
+#pragma unroll
+            for (int i = 0; i < 3; i++) out[i] = __funnelshift_r(w[i + 3], w[i + 4], sh);
+            out[3] = __funnelshift_r(w[6], w[7], sh);
+            break;
+    }
+}
+// bit i = (byte i of a differs from byte i of b), i < 16
+__device__ __forceinline__ uint32_t neq16(const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) m |= ((nonzero_bytes(a[i] ^ b[i]) * 0x01020408u) >> 24 & 0xFu) << (4 * i);
+    return m;
+}
+// bits i < 16 with lo <= p0 + i < hi
+__device__ __forceinline__ uint32_t range16(int p0, int lo, int hi) {
+    int a = lo - p0, b = hi - p0;
+    a = a < 0 ? 0 : a;
+    b = b > 16 ? 16 : b;
+    if (b <= a) return 0u;
+    return ((1u << b) - 1u) & ~((1u << a) - 1u);
+}
+
+// The 32 lanes of a warp take 16 consecutive positions each (one pass covers 512 bases): the bytes of both entries and
+// of the germlines are fetched with 16-byte loads, compared as 16-bit masks, and every count of join_one's loops is a
+// popcount of mask products.  The first version walked the sequences one byte per lane and pass (diffs, V window, J
+// window, per germline set): ~60 dependent load rounds per pair, against 3 here.
 template <bool WARP>
 __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
-    const uint32_t lane = WARP ? (threadIdx.x & 31) : 0u;
-    constexpr int STEP = WARP ? 32 : 1;
+    static_assert(WARP, "warp-cooperative only");
+    const int lane = (int)(threadIdx.x & 31);
     const uint32_t k1 = m1.k, k2 = m2.k;
     int nrefs = 1;
     for (int c = 0; c < 2; c++)
@@ -964,52 +1011,76 @@ __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const En
     pc.nrefs = nrefs;
     int diffs = 0, cdc[2] = { 0, 0 };
     int sh[2] = { 0, 0 }, in_[2] = { 0, 0 }, io[2] = { 0, 0 }, det[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+    int dfw = 0, d12 = 0;
+    int f1 = 0, c1 = 0, f2 = 0, c2 = 0, f3 = 0;
+    const bool reg = pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2, &f3);
     for (int c = 0; c < 2; c++) {
         const int n = m1.len[c];
         const uint8_t *t1 = in.tig_arena + in.tig_off[c][k1], *t2 = in.tig_arena + in.tig_off[c][k2];
-        for (int p = lane; p < n; p += STEP) diffs += t1[p] != t2[p];
-        const uint8_t *q1 = in.cdr3_arena + in.cdr3_off[c][k1], *q2 = in.cdr3_arena + in.cdr3_off[c][k2];
-        for (int p = lane; p < (int)m1.cl[c]; p += STEP) cdc[c] += q1[p] != q2[p];
         const int a1 = m1.cs[c], a2 = m2.cs[c], cl = m1.cl[c];
-        for (int u = 0; u < nrefs; u++) {
-            const EntryMeta &mu = u == 0 ? m1 : m2;
-            const uint8_t *v = in.refseq_arena + in.refseq_off[mu.vs[c]], *j = in.refseq_arena + in.refseq_off[mu.js[c]];
-            const int vl = (int)in.refseq_len[mu.vs[c]], jl = (int)in.refseq_len[mu.js[c]];
-            int vend = vl - pr.ref_v_trim;
-            if (vend > n) vend = n;
-            for (int p = lane; p < vend; p += STEP) {
-                const uint8_t r = v[p];
-                const int out = !((p >= a1 && p < a1 + cl) || (p >= a2 && p < a2 + cl));
-                if (t1[p] == t2[p]) { if (t1[p] != r) { sh[u]++; det[u][2 * c]++; } }
-                else { int q = (t1[p] != r) + (t2[p] != r); in_[u] += q; if (out) io[u] += q; }
+        {   // CDR3 strings (cl <= 255: one pass)
+            const uint8_t *q1 = in.cdr3_arena + in.cdr3_off[c][k1], *q2 = in.cdr3_arena + in.cdr3_off[c][k2];
+            const int p0 = 16 * lane;
+            if (p0 < cl) {
+                uint32_t x[4], y[4];
+                load16u(q1 + p0, x); load16u(q2 + p0, y);
+                cdc[c] += __popc(neq16(x, y) & range16(p0, 0, cl));
             }
-            int jstart = n - (jl - pr.ref_j_trim);
-            if (jstart < 0) jstart = 0;
-            if (jl - pr.ref_j_trim > 0)
-                for (int p = jstart + lane; p < n; p += STEP) {
-                    const uint8_t r = j[jl - (n - p)];
-                    const int out = !((p >= a1 && p < a1 + cl) || (p >= a2 && p < a2 + cl));
-                    if (t1[p] == t2[p]) { if (t1[p] != r) { sh[u]++; det[u][2 * c + 1]++; } }
-                    else { int q = (t1[p] != r) + (t2[p] != r); in_[u] += q; if (out) io[u] += q; }
+        }
+        for (int p0 = 16 * lane; p0 < n; p0 += 512) {
+            uint32_t x[4], y[4];
+            load16u(t1 + p0, x); load16u(t2 + p0, y);
+            const uint32_t valid = range16(p0, 0, n);
+            const uint32_t D = neq16(x, y) & valid, S = ~D & valid;          // positions where the entries differ / agree
+            const uint32_t out = valid & ~(range16(p0, a1, a1 + cl) | range16(p0, a2, a2 + cl));
+            diffs += __popc(D);
+            if (reg && c == 0) { dfw += __popc(D & range16(p0, f1, c1)); d12 += __popc(D & (range16(p0, c1, f2) | range16(p0, c2, f3))); }
+            for (int u = 0; u < nrefs; u++) {
+                const EntryMeta &mu = u == 0 ? m1 : m2;
+                const uint32_t vi = mu.vs[c], ji = mu.js[c];
+                const int vl = (int)in.refseq_len[vi], jl = (int)in.refseq_len[ji];
+                const uint32_t inV = range16(p0, 0, min(vl - pr.ref_v_trim, n));
+                if (inV) {
+                    uint32_t r[4];
+                    load16u(in.refseq_arena + in.refseq_off[vi] + p0, r);
+                    const uint32_t A = neq16(x, r) & inV, B = neq16(y, r) & inV;
+                    const int s_ = __popc(S & A);
+                    sh[u] += s_; det[u][2 * c] += s_;
+                    in_[u] += __popc(D & A) + __popc(D & B);
+                    io[u] += __popc(D & A & out) + __popc(D & B & out);
                 }
+                const int jw = jl - pr.ref_j_trim;
+                const uint32_t inJ = jw > 0 ? range16(p0, max(0, n - jw), n) : 0u;
+                if (inJ) {
+                    const int g0 = p0 - (n - jl);                 // germline index of position p0
+                    const uint8_t *jp = in.refseq_arena + in.refseq_off[ji];
+                    uint32_t r[4];
+                    if (g0 >= 0) load16u(jp + g0, r);
+                    else {                                        // the chunk starts before the germline does: byte by byte
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            uint32_t wv = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; b++) { const int g = g0 + 4 * i + b; if (g >= 0 && g < jl) wv |= (uint32_t)jp[g] << (8 * b); }
+                            r[i] = wv;
+                        }
+                    }
+                    const uint32_t A = neq16(x, r) & inJ, B = neq16(y, r) & inJ;
+                    const int s_ = __popc(S & A);
+                    sh[u] += s_; det[u][2 * c + 1] += s_;
+                    in_[u] += __popc(D & A) + __popc(D & B);
+                    io[u] += __popc(D & A & out) + __popc(D & B & out);
+                }
+            }
         }
     }
-    auto red = [](int v) { return WARP ? warp_sum(v) : v; };
-    pc.diffs = red(diffs); pc.cd0 = red(cdc[0]); pc.cd1 = red(cdc[1]);
+    pc.diffs = warp_sum(diffs); pc.cd0 = warp_sum(cdc[0]); pc.cd1 = warp_sum(cdc[1]);
     for (int u = 0; u < 2; u++) {
-        pc.shares[u] = red(sh[u]); pc.indeps[u] = red(in_[u]); pc.indeps_out[u] = red(io[u]);
-        for (int q = 0; q < 4; q++) pc.det[u][q] = red(det[u][q]);
+        pc.shares[u] = warp_sum(sh[u]); pc.indeps[u] = warp_sum(in_[u]); pc.indeps_out[u] = warp_sum(io[u]);
+        for (int q = 0; q < 4; q++) pc.det[u][q] = warp_sum(det[u][q]);
     }
     pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
-    int f1, c1, f2, c2, f3;
-    if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2, &f3)) {
-        const uint8_t *t1 = in.tig_arena + in.tig_off[0][k1], *t2 = in.tig_arena + in.tig_off[0][k2];
-        int dfw = 0, d12 = 0;
-        for (int p = f1 + lane; p < c1; p += STEP) dfw += t1[p] != t2[p];
-        for (int p = c1 + lane; p < f2; p += STEP) d12 += t1[p] != t2[p];
-        for (int p = c2 + lane; p < f3; p += STEP) d12 += t1[p] != t2[p];
-        pc.dfw = red(dfw); pc.dc12 = red(d12); pc.lfw = c1 - f1; pc.l12 = (f2 - c1) + (f3 - c2);
-    }
+    if (reg) { pc.dfw = warp_sum(dfw); pc.dc12 = warp_sum(d12); pc.lfw = c1 - f1; pc.l12 = (f2 - c1) + (f3 - c2); }
 }
 
 __device__ __forceinline__ void bytewise_counts(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
