@@ -623,7 +623,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         const DevCounters first = h->counters;
         mark(h, "keys (+tables first run)");
         tb = cub_bytes;
-        cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys, keys_out, vals, perm, (int)n, 0, 64, st);
+        cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys, keys_out, vals, perm, (int)n, 0, ENTRY_KEY_BITS, st);
         mark(h, "sort entries");
         tb = cub_bytes;
         cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
@@ -768,11 +768,12 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         mark(h, "comp size + collect");
         CK(cudaStreamSynchronize(st));
         const unsigned long long nk = h->counters.n_kept;
-        const unsigned long long nsorted = (unsigned long long)n + std::min<unsigned long long>(h->counters.n_accept, cap);
         if (nk) {
-            // the empty phase-A slots carry the key ~0 and sort to the end: the first n_kept are the edges
+            // keys are (k1 << 32 | k2) with k < n: only the bits that can differ are sorted
+            int kb = 1;
+            while (kb < 32 && (1ull << kb) < (unsigned long long)n + h->k_base) kb++;
             tb = cub_bytes;
-            cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nsorted, 0, 64, st);
+            cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nk, 0, 32 + kb, st);
         }
         CK(cudaEventRecord(h->ev[5], st));
         mark(h, "sort edges");

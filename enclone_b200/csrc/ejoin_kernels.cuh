@@ -45,7 +45,7 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
             else if (l0 + l1 >= 8192) { atomicOr(&ctr->err, ERR_LEN_TOO_LARGE); valid = false; }
         }
         if (valid) {
-            key = ((unsigned long long)l0 << 48) | ((unsigned long long)l1 << 32) | ((unsigned long long)c0 << 16) | c1;
+            key = ((unsigned long long)l0 << 29) | ((unsigned long long)l1 << 16) | ((unsigned long long)c0 << 8) | c1;   // 13|13|8|8 bits: ENTRY_KEY_BITS
             uint32_t L = l0 + l1, cc = (c0 << 8) | c1;
             // test before set: after the first hit per value these are plain cached loads, not serialized atomics
             if (!(presL[L >> 5] & (1u << (L & 31)))) atomicOr(&presL[L >> 5], 1u << (L & 31));
@@ -72,7 +72,7 @@ __device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned
     for (int f = 0; f < 6; f++) o.v[f] = 0;
     o.W = 0; o.cdm = 0xFFFF; o.T = 0; o.valid = key != ~0ull;
     if (!o.valid) return o;
-    const uint32_t total = (uint32_t)((key >> 16) & 0xFFFF) + (uint32_t)(key & 0xFFFF);
+    const uint32_t total = (uint32_t)((key >> 8) & 0xFF) + (uint32_t)(key & 0xFF);
     uint32_t W = (total + 31) / 32;
     if (W == 0) W = 1;
     const uint32_t cdm = cdmax_tab[total];
@@ -1234,27 +1234,26 @@ __global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevPara
 __global__ void __launch_bounds__(256) k_collect(const unsigned long long *f0_key, const unsigned long long *f0_val, uint32_t n,
                                                  const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap,
                                                  unsigned long long *keys, unsigned long long *vals) {
+    // compacted: the sort that follows then handles the live edges only (n_kept of them)
+    __shared__ SplitSmem sm;
     unsigned long long nacc = ctr->n_accept;
     if (nacc > cap) nacc = cap;
     const unsigned long long total = (unsigned long long)n + nacc;
-    unsigned long long mine = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
-        if (i >= cap) break;
-        if (i < n) {
-            keys[i] = f0_key[i]; vals[i] = f0_val[i];
-            mine += f0_key[i] != ~0ull;
-        } else {
-            ejoin_raw_edge_t e = acc[i - n];
-            const bool dead = e.k1 == 0xFFFFFFFFu;
-            keys[i] = dead ? ~0ull : (((unsigned long long)e.k1 << 32) | e.k2);
-            vals[i] = ((unsigned long long)e.flags << 32) | ((unsigned long long)e.d << 16) | e.cd;
-            mine += !dead;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x; t0 < total; t0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = t0 + threadIdx.x;
+        unsigned long long key = ~0ull, val = 0;
+        if (i < n) { key = f0_key[i]; val = f0_val[i]; }
+        else if (i < total) {
+            const ejoin_raw_edge_t e = acc[i - n];
+            if (e.k1 != 0xFFFFFFFFu) {
+                key = ((unsigned long long)e.k1 << 32) | e.k2;
+                val = ((unsigned long long)e.flags << 32) | ((unsigned long long)e.d << 16) | e.cd;
+            }
         }
+        unsigned long long o1, o2;
+        block_reserve2(sm, key != ~0ull ? 1u : 0u, 0u, &ctr->n_kept, nullptr, o1, o2);
+        if (key != ~0ull && o1 < cap) { keys[o1] = key; vals[o1] = val; }
     }
-    typedef cub::BlockReduce<unsigned long long, 256> BR;
-    __shared__ typename BR::TempStorage tmp;
-    unsigned long long s = BR(tmp).Sum(mine);
-    if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_kept, s);
 }
 
 __global__ void k_init_rows(uint32_t *parent, unsigned long long *f0_key, uint32_t *cnt, uint8_t *needed, uint8_t *force, uint32_t n,
@@ -1852,15 +1851,16 @@ __global__ void __launch_bounds__(256) k_final_collect(DevIn in, const unsigned 
                                                        const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap,
                                                        const uint32_t *k_to_s, uint32_t k_base, uint32_t *parent, const uint32_t *size, int easy,
                                                        unsigned long long *keys, unsigned long long *vals) {
+    // compacted: the sort that follows then handles the emitted joins only (n_kept of them)
+    __shared__ SplitSmem sm;
     unsigned long long nacc = ctr->n_accept;
     if (nacc > cap) nacc = cap;
     const unsigned long long total = (unsigned long long)n + nacc;
-    unsigned long long mine = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
-        if (i >= cap) break;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x; t0 < total; t0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = t0 + threadIdx.x;
         unsigned long long key = ~0ull, val = 0;
         if (i < n) { key = f0_key[i]; val = f0_val[i]; }
-        else {
+        else if (i < total) {
             const ejoin_raw_edge_t e = acc[i - n];
             if (e.k1 != ACC_DEAD && (e.flags & ACC_SELECTED)) {
                 key = ((unsigned long long)e.k1 << 32) | e.k2;
@@ -1875,13 +1875,10 @@ __global__ void __launch_bounds__(256) k_final_collect(DevIn in, const unsigned 
                 if (cells == 2 && !easy && !(cd <= d)) key = ~0ull;
             }
         }
-        keys[i] = key; vals[i] = val;
-        mine += key != ~0ull;
+        unsigned long long o1, o2;
+        block_reserve2(sm, key != ~0ull ? 1u : 0u, 0u, &ctr->n_kept, nullptr, o1, o2);
+        if (key != ~0ull && o1 < cap) { keys[o1] = key; vals[o1] = val; }
     }
-    typedef cub::BlockReduce<unsigned long long, 256> BR;
-    __shared__ typename BR::TempStorage tmp;
-    unsigned long long s = BR(tmp).Sum(mine);
-    if (threadIdx.x == 0 && s) atomicAdd(&ctr->n_kept, s);
 }
 __global__ void k_keys_to_pairs(const unsigned long long *keys, uint32_t ne, uint32_t k_base, uint2 *pairs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
