@@ -273,7 +273,7 @@ def main():
     except Exception:
         pass
     notes = {"k_pack_t2": "streams the needed entries' ASCII V..J bytes once and writes their bit-plane rows; ALU-bound on the byte-to-plane "
-                          "SWAR arithmetic (ncu: ALU pipe 61%, DRAM 13%), not yet at the HBM roofline (profiles/README.md)",
+                          "SWAR arithmetic (ncu: ALU pipe 55%, issue 49%, DRAM 17%), not at the HBM roofline (profiles/README.md)",
              "k_sweep": "all-pairs CDR3 XOR/popcount on rows staged in shared memory by TMA: each row is read once from HBM and reused "
                         "~n_group times on chip, so achieved/peak is an equivalent streaming rate, not an HBM utilisation; the kernel "
                         "is bound by the popcount (XU) pipe and issue slots (profiles/README.md)"}
