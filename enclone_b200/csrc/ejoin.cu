@@ -735,6 +735,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (h->counters.err & ERR_CDR3_BAD_CHAR) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 contains a character outside ACGT");
         if (h->counters.err & ERR_BAD_REFSEQ) return fail(h, EJOIN_E_ARG, "vs_seq/js_seq index outside the germline table");
         if (h->counters.err & ERR_K_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "a pair has 1024 or more mutations (p1 table width)");
+        if (h->counters.err & ERR_GROUP_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "more than 8.3 M entries share all four lengths (one comparison group)");
         {
             // a buffer was too small: the counters keep counting past the capacity, so they tell the size to retry with
             // (a list that overflowed may have starved the lists behind it, hence the loop)

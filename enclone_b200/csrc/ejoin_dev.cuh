@@ -29,6 +29,7 @@
 #define ERR_BAD_REFSEQ 4u
 #define ERR_K_TOO_LARGE 8u
 #define ERR_LEN_TOO_LARGE 16u
+#define ERR_GROUP_TOO_LARGE 32u   // a comparison group of more than 65535 tiles (8.3 M entries with equal lengths)
 
 struct __align__(16) EntryMeta {
     uint32_t k;              // info index

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) k_group_vals(const unsigned long long *__
             a = gv.v[0] | (gv.v[1] << 32); b = gv.v[2]; x = (uint32_t)gv.v[5];
             pairs = gv.v[3]; t1b = gv.v[4];
             if (gv.valid) ng = r + 1;
+            if (gv.T > 65535u) atomicOr(&ctr->err, ERR_GROUP_TOO_LARGE);      // GroupInfo::tiles is 16 bits
         }
         sumA[r] = a; sumB[r] = b; sumC[r] = x;
     }

@@ -118,3 +118,17 @@ def test_rust_ffi_crate_declares_the_same_symbols():
     rs = open(os.path.join(ROOT, "rust", "enclone_join_ffi", "src", "lib.rs")).read()
     bound = set(re.findall(r"pub fn (ejoin_[a-z0-9_]+)\(", rs))
     assert bound == set(_lib.EXPORTS), bound ^ set(_lib.EXPORTS)
+
+
+def test_tier1_work_decomposition_arithmetic(tmp_path):
+    """tests/seg_enum_test.cu (host code only, built with nvcc): the (segment, row) enumeration of
+    ejoin_dev.cuh is a bijection, item_decode()'s loop inverts it, segments respect their length cap."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "seg_enum_test")
+    subprocess.check_call(["nvcc", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(root, "tests", "seg_enum_test.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
