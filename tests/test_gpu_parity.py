@@ -180,6 +180,46 @@ def test_stride_mode_giant_bucket():
         j.close()
 
 
+def test_ambiguous_bases_in_reads_and_germlines():
+    """'N' and lower-case bytes: in the V..J reads (outside the CDR3s) they send the entry to the bytewise path;
+    in the germline table they count as a difference from every read base (the N plane of k_pack_ref)."""
+    pack, _ = synth.generate(n_cells=6000, n_donors=2, seed=77)
+    rng = np.random.default_rng(5)
+    a = pack.arrays
+    n = pack.n_info
+    arena = a["tig_arena"]
+    for k in rng.choice(n, size=n // 40, replace=False):
+        for c in range(2):
+            ln, cs, cl = int(a["len"][c][k]), int(a["cdr3_start"][c][k]), int(a["cdr3_len"][c][k])
+            if ln < 60:
+                continue
+            pos = int(rng.integers(0, ln))
+            if cs <= pos < cs + cl:                       # CDR3 characters must stay ACGT (documented limit)
+                continue
+            arena[int(a["tig_off"][c][k]) + pos] = ord("N") if rng.random() < 0.7 else ord("a")
+    ref = a["refseq_arena"]
+    for i in rng.choice(len(a["refseq_len"]), size=max(1, len(a["refseq_len"]) // 5), replace=False):
+        ln = int(a["refseq_len"][i])
+        for pos in rng.integers(0, ln, size=3):
+            b = ref[int(a["refseq_off"][i]) + int(pos)]
+            ref[int(a["refseq_off"][i]) + int(pos)] = ord("N") if rng.random() < 0.5 else (b | 0x20)   # lower case: same 2-bit code, different byte
+    g, oe, oc, _ = _run_both(pack)
+    assert_same_join(g, oe, oc, what="ambiguous bases")
+    assert g.stats["pairs_generic"] > 0
+
+
+def test_narrow_trims_make_windows_overlap():
+    """REF_V_TRIM / REF_J_TRIM of 2: the V and J windows of short light chains overlap, positions in the overlap are
+    counted against both germlines (bytewise path), everything else shifts its window ends."""
+    pack, _ = synth.generate(n_cells=6000, n_donors=2, seed=78)
+    base = join_exacts(pack)
+    g, oe, oc, _ = _run_both(pack, ref_v_trim=2, ref_j_trim=2)
+    assert_same_join(g, oe, oc, what="trims 2/2")
+    g0, oe0, oc0, _ = _run_both(pack, ref_v_trim=0, ref_j_trim=0)
+    assert_same_join(g0, oe0, oc0, what="trims 0/0")
+    assert g0.stats["pairs_generic"] >= base.stats["pairs_generic"]
+
+
 def test_stride_mode_segmented_rows_three_ranks():
     """A 10,000-entry bucket: rows of up to 79 tiles are cut into 10 segments (extra slot rows, capacity
     retry) and dealt to three ranks row by row; the gathered edges must replay to the single-GPU join."""
