@@ -560,26 +560,24 @@ struct PairCounts {
     int dfw, lfw, dc12, l12;     // FWR1 / CDR1+CDR2 region counts; lfw == 0 when the gate is skipped
 };
 
-__device__ __forceinline__ double p1_lookup(const DevTables &tb, int L, int k, int d, DevCounters *ctr) {
-    if (d <= 0) return 1.0;
-    if (d >= P1_DCAP) return 0.0;        // below the reference's double-double noise floor
-    if (k >= P1_KCAP) { atomicOr(&ctr->err, ERR_K_TOO_LARGE); return 1.0; }
-    const double *tab = tb.p1tab[L];
-    return tab[d * P1_KCAP + k];
-}
-
-// returns accept_reason (0 = reject); fills k, d, p1, mult, score
-__device__ __forceinline__ int decide(const DevParams &pr, const DevTables &tb, const EntryMeta &m1, const EntryMeta &m2,
-                                      const PairCounts &pc, DevCounters *ctr, int *kout, int *dout, double *p1o, double *multo,
-                                      double *scoreo) {
+// The decision in two steps, so that callers can count the FWR1 / CDR1+CDR2 differences only for pairs that got past
+// the score: decide_score -> accept_reason (0 = reject) with k, d, p1, mult, score; decide_gates -> the two vetoes
+// that follow it (A.4 m, n).  `p1tab_L` = tb.p1tab[len0+len1], `mi2` = tb.multinfo[cl0<<8|cl1]: the callers fetch them
+// early, together with the meta records.
+__device__ __forceinline__ int decide_score(const DevParams &pr, const DevTables &tb, const EntryMeta &m1, const EntryMeta &m2,
+                                            const PairCounts &pc, DevCounters *ctr, const double *p1tab_L, const MultInfo mi2, int *kout,
+                                            int *dout, int *mo_out, double *p1o, double *multo, double *scoreo) {
     const int cd = pc.cd0 + pc.cd1;
     if (pc.nrefs == 2) { int df = pc.shares[0] - pc.shares[1]; if (df < 0) df = -df; if (df > pr.max_degradation) return 0; }
     int d = pc.shares[0], mi = pc.indeps[0], mo = pc.indeps_out[0];
     if (pc.nrefs == 2) { d = min(d, pc.shares[1]); mi = min(mi, pc.indeps[1]); mo = min(mo, pc.indeps_out[1]); }
     const int k = mi + 2 * d;
-    const int L = (int)m1.len[0] + (int)m1.len[1];
-    const double p1 = p1_lookup(tb, L, k, d, ctr);
-    const MultInfo mi2 = tb.multinfo[((uint32_t)m1.cl[0] << 8) | m1.cl[1]];
+    double p1 = 1.0;
+    if (d >= P1_DCAP) p1 = 0.0;          // below the reference's double-double noise floor
+    else if (d > 0) {
+        if (k >= P1_KCAP) atomicOr(&ctr->err, ERR_K_TOO_LARGE);
+        else p1 = p1tab_L[d * P1_KCAP + k];
+    }
     const double mult = tb.multpool[mi2.off + (uint32_t)pc.cd0 * mi2.d1p1 + (uint32_t)pc.cd1];
     const double score = __dmul_rn(p1, mult);
     int reason = 0;
@@ -589,18 +587,27 @@ __device__ __forceinline__ int decide(const DevParams &pr, const DevTables &tb, 
         int hc = min((int)m1.hcomp, (int)m2.hcomp);
         if (hc - cd >= pr.comp_filt && pc.diffs - cd <= pr.comp_filt_bound) reason |= 4;
     }
-    if (!reason) return 0;
+    *kout = k; *dout = d; *mo_out = mo; *p1o = p1; *multo = mult; *scoreo = score;
+    return reason;
+}
+__device__ __forceinline__ bool decide_gates(const DevParams &pr, const PairCounts &pc, int mo) {
     if (pr.is_bcr && pc.lfw > 0) {
         const double ifw = __dmul_rn(100.0, __dsub_rn(1.0, __ddiv_rn((double)pc.dfw, (double)pc.lfw)));
         const double i12 = __dmul_rn(100.0, __dsub_rn(1.0, __ddiv_rn((double)pc.dc12, (double)pc.l12)));
-        if (__dsub_rn(ifw, i12) >= pr.fwr1_cdr12_delta) return 0;
+        if (__dsub_rn(ifw, i12) >= pr.fwr1_cdr12_delta) return false;
     }
-    {
-        int x = mo > 1 ? mo : 1;
-        if (cd >= pr.cdr3_mult * x) return 0;
-    }
-    *kout = k; *dout = d; *p1o = p1; *multo = mult; *scoreo = score;
-    return reason;
+    const int x = mo > 1 ? mo : 1;
+    return !(pc.cd0 + pc.cd1 >= pr.cdr3_mult * x);
+}
+// returns accept_reason (0 = reject); fills k, d, p1, mult, score
+__device__ __forceinline__ int decide(const DevParams &pr, const DevTables &tb, const EntryMeta &m1, const EntryMeta &m2,
+                                      const PairCounts &pc, DevCounters *ctr, int *kout, int *dout, double *p1o, double *multo,
+                                      double *scoreo) {
+    int mo = 0;
+    const int reason = decide_score(pr, tb, m1, m2, pc, ctr, tb.p1tab[(int)m1.len[0] + (int)m1.len[1]],
+                                    tb.multinfo[((uint32_t)m1.cl[0] << 8) | m1.cl[1]], kout, dout, &mo, p1o, multo, scoreo);
+    if (!reason) return 0;
+    return decide_gates(pr, pc, mo) ? reason : 0;
 }
 
 // cheap gates that need only the meta records (App. A.4 e-g); returns 0 = reject, 1 = pass; *err = cross-donor
@@ -693,6 +700,9 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
     }
     const EntryMeta &m1 = u1.m, &m2 = u2.m;
     *scored = false; *d_out = 0; *err_out = 0;
+    // table handles of this pair's (n, CDR3 lengths): fetched now, used by the score at the very end
+    const double *p1tab_L = tb.p1tab[(int)m1.len[0] + (int)m1.len[1]];
+    const MultInfo mi2 = tb.multinfo[((uint32_t)m1.cl[0] << 8) | m1.cl[1]];
     // CDR3 differences per chain from the c3 rows
     const uint32_t cl0 = m1.cl[0], total = cl0 + m1.cl[1], W = max(1u, (total + 31) / 32);
     int cd0 = 0, cdt = 0;
@@ -723,14 +733,12 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
     pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1;
     for (int c2 = 0; c2 < 2; c2++)
         if (m1.vref[c2] != m2.vref[c2] || m1.dref[c2] != m2.dref[c2] || m1.jref[c2] != m2.jref[c2]) pc.nrefs = 2;
-    // One pass over the t2 rows does all the counting: total differences and shared mutations (every block),
-    // FWR1 vs CDR1+CDR2 differences on the heavy chain (A.4-m, blocks of chain 0 that meet [f1,f3)), and the
-    // non-shared mutations outside the CDR3s (A.4-n, only when cd >= CDR3_MULT).
-    int f1 = 0, c1 = 0, f2 = 0, c2_ = 0, f3 = 0;
-    const bool do_reg = pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3);
-    const int wlo = do_reg ? (f1 >> 5) : (1 << 30), whi = do_reg ? ((f3 - 1) >> 5) : -1;
+    // One pass over the t2 rows counts total differences, shared mutations and, when cd >= CDR3_MULT, the non-shared
+    // mutations outside the CDR3s (A.4-n).  The FWR1 vs CDR1+CDR2 differences of the heavy chain (A.4-m) only veto
+    // pairs that got past the score (one in seven in phase B), so they are counted afterwards, for those pairs, from
+    // the few blocks that meet [f1,f3) — by then in L1.
     const bool do_io = cd >= pr.cdr3_mult;
-    int diffs = 0, shares = 0, dfw = 0, d12 = 0, io = 0;
+    int diffs = 0, shares = 0, io = 0;
     const uint4 *r1 = tb.t2 + m1.t2off, *r2 = tb.t2 + m2.t2off;
 #pragma unroll 2
     for (uint32_t b = 0; b < nblk; b++) {
@@ -742,13 +750,6 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
         for (int q = 0; q < 4; q++) { diffs += __popc(D[q]); shares += __popc(X1[q] & X2[q] & ~D[q]); }
         const bool ch1 = b >= nb0;
         const int wl0 = 4 * (int)(b - (ch1 ? nb0 : 0u));          // word index inside the chain
-        if (!ch1 && wl0 + 3 >= wlo && wl0 <= whi) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                dfw += __popc(D[q] & range_mask(wl0 + q, f1, c1));
-                d12 += __popc(D[q] & (range_mask(wl0 + q, c1, f2) | range_mask(wl0 + q, c2_, f3)));
-            }
-        }
         if (do_io) {
             const int a1 = ch1 ? m1.cs[1] : m1.cs[0], a2 = ch1 ? m2.cs[1] : m2.cs[0], cl = ch1 ? m1.cl[1] : m1.cl[0];
 #pragma unroll
@@ -769,10 +770,25 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
         if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
         if (diffs > cap) return 0;
     }
+    int kk, mo; double p1, mult, score;
+    const int reason = decide_score(pr, tb, m1, m2, pc, ctr, p1tab_L, mi2, &kk, d_out, &mo, &p1, &mult, &score);
+    if (!reason) return 0;
     pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
-    if (do_reg) { pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_); }
-    int kk; double p1, mult, score;
-    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
+    int f1 = 0, c1 = 0, f2 = 0, c2_ = 0, f3 = 0;
+    if (pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3)) {
+        int dfw = 0, d12 = 0;
+        for (int b = f1 >> 7; b <= (f3 - 1) >> 7; b++) {             // f3 <= len0: blocks of chain 0
+            const uint4 h1 = __ldg(r1 + 3 * b), l1 = __ldg(r1 + 3 * b + 1), h2 = __ldg(r2 + 3 * b), l2 = __ldg(r2 + 3 * b + 1);
+            const uint32_t D[4] = { (h1.x ^ h2.x) | (l1.x ^ l2.x), (h1.y ^ h2.y) | (l1.y ^ l2.y), (h1.z ^ h2.z) | (l1.z ^ l2.z), (h1.w ^ h2.w) | (l1.w ^ l2.w) };
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                dfw += __popc(D[q] & range_mask(4 * b + q, f1, c1));
+                d12 += __popc(D[q] & (range_mask(4 * b + q, c1, f2) | range_mask(4 * b + q, c2_, f3)));
+            }
+        }
+        pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_);
+    }
+    return decide_gates(pr, pc, mo) ? reason : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
