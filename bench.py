@@ -288,6 +288,15 @@ def main():
                 "algorithmic_bytes_all": {"k_sweep": int(st["alg_bytes_tier1"]), "k_pack_t2": int(st["alg_bytes_pack_t2"]),
                                           "scoring kernels": int(st["alg_bytes_tier2"])},
                 "device_ms_per_step": ms.get("ms_device")}
+    # supplementary: k_sweep against the pipe that bounds it.  One POPC per 32-base word and pair (alg_bytes_tier1 / 16);
+    # 16 POPC lanes per SM and clock (the rate at which the kernel saturates on the giant-bucket workload C4: 90 %).
+    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    sweep_ms = kern["k_sweep"][0]
+    popc = st["alg_bytes_tier1"] / 16.0
+    xu_peak = 148 * 16 * sm_clock
+    roofline["popcount_pipe"] = {"kernel": "k_sweep", "achieved": popc / (sweep_ms * 1e-3) if sweep_ms > 0 else 0.0, "peak": xu_peak,
+                                 "unit": "POPC/s", "frac": (popc / (sweep_ms * 1e-3) / xu_peak) if sweep_ms > 0 else None,
+                                 "note": "pair compares only; the survivor bookkeeping (ffs) shares the pipe: ncu reports it 73% busy at C3"}
     config.update({"n_info": sp.n_info, "candidate_pairs": pairs_total, "pairs_compared_tier1": int(st["pairs_compared"]),
                    "pairs_tier2": int(st["pairs_tier2"]), "pairs_accepted": int(st["pairs_accepted"]), "joins_emitted": int(len(res.edges)),
                    "l2": "inputs (%.0f MB resident) exceed the 126 MB L2; no flush" % (e2e_stats["h2d_bytes"] / 1e6),
