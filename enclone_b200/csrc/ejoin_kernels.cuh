@@ -725,10 +725,22 @@ __device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb
     if (!meta_gates(pr, in, m1, m2, cd, err_out)) return 0;
     *scored = true;
     const uint32_t nb0 = ((uint32_t)m1.len[0] + 127) / 128, nblk = nb0 + ((uint32_t)m1.len[1] + 127) / 128;
-    *bytes += 2ull * (48ull * nblk + 128ull);
     const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] ||
                          m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
-    if (generic) return -1;
+    if (generic) { *bytes += 2ull * (48ull * nblk + 128ull); return -1; }
+    {
+        // No shared mutation is possible when one of the entries has none (shares <= each entry's own count of germline
+        // differences inside the windows): then d = 0, p1 = 1 and the score is the CDR3 multiplier alone.  If that
+        // exceeds MAX_SCORE, AUTO_SHARES cannot fire (d = 0) and the junction-complexity exception is out of reach
+        // (hcomp - cd < COMP_FILT), join_one rejects the pair whatever the rest of the sequences say: no t2 row is read.
+        // (Naive cells with similar CDR3s: most of the rejected pairs of a repertoire.)
+        const int mt1 = (int)m1.m[0] + (int)m1.m[1], mt2 = (int)m2.m[0] + (int)m2.m[1];
+        if (min(mt1, mt2) == 0 && pr.auto_share > 0 && min((int)m1.hcomp, (int)m2.hcomp) - cd < pr.comp_filt) {
+            const double mult0 = tb.multpool[mi2.off + (uint32_t)cd0 * mi2.d1p1 + (uint32_t)cd1];
+            if (__dmul_rn(1.0, mult0) > pr.max_score) { *bytes += 256ull; return 0; }
+        }
+    }
+    *bytes += 2ull * (48ull * nblk + 128ull);
     PairCounts pc;
     pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1;
     for (int c2 = 0; c2 < 2; c2++)
