@@ -73,6 +73,35 @@ def test_parameter_variants(over):
     assert_same_join(g, oe, oc, max_score=over.get("max_score", 100000.0), what=str(over))
 
 
+@pytest.mark.parametrize("case", range(10))
+def test_randomized_repertoires_and_parameters(case):
+    """Random repertoire shapes (size, donors, BCR/TCR, naive / public / indel / multi-chain fractions, family size
+    law) under random parameter settings: bit-exact against the oracle every time."""
+    rng = np.random.default_rng(1000 + case)
+    is_bcr = case % 3 != 2                                       # cases 2, 5, 8: TCR rules
+    gen = dict(n_cells=int(rng.integers(1500, 20000)), n_donors=int(rng.integers(1, 5)), is_bcr=is_bcr, seed=int(rng.integers(1, 1 << 30)),
+               frac_naive=float(rng.uniform(0.1, 0.8)), frac_public=float(rng.uniform(0.0, 0.15)), frac_indel=float(rng.uniform(0.0, 0.08)),
+               frac_3chain=float(rng.uniform(0.0, 0.08)), frac_1chain=float(rng.uniform(0.0, 0.1)), family_alpha=float(rng.uniform(1.2, 2.5)))
+    if rng.random() < 0.3:
+        gen["max_family"] = int(rng.integers(200, 3000))         # a few very large families: multi-segment tile rows
+    over = {}
+    if rng.random() < 0.5: over["mix_donors"] = 1
+    if rng.random() < 0.3: over["max_score"] = float(10.0 ** rng.uniform(0, 7))
+    if rng.random() < 0.3: over["auto_share"] = int(rng.integers(3, 40))
+    if rng.random() < 0.3: over["join_cdr3_ident"] = float(rng.uniform(70, 100))
+    if rng.random() < 0.3: over["max_cdr3_diffs"] = int(rng.integers(0, 12))
+    if rng.random() < 0.3: over["cdr3_mult"] = int(rng.integers(1, 8))
+    if rng.random() < 0.3: over["comp_filt"] = int(rng.integers(0, 20))
+    if rng.random() < 0.3: over["max_degradation"] = int(rng.integers(0, 5))
+    if rng.random() < 0.2: over["easy"] = 1
+    if rng.random() < 0.2: over["fwr1_cdr12_delta"] = float(rng.uniform(0, 40))
+    if rng.random() < 0.2: over["max_diffs"] = int(rng.integers(5, 120))
+    pack, _ = synth.generate(**gen)
+    g, oe, oc, ost = _run_both(pack, **over)
+    assert_same_join(g, oe, oc, max_score=over.get("max_score", 100000.0), what=f"case {case}: {gen} {over}")
+    assert g.stats["pairs_candidate"] == ost["pairs_candidate"]
+
+
 def test_accept_graph_is_a_superset_forest():
     """The GPU scores ALL pairs; its emitted edges must be the lexicographically-first spanning
     forest of the oracle's full accept graph."""
