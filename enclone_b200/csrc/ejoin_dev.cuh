@@ -85,6 +85,7 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned long long t1_alg_bytes, t2_alg_bytes, t2_units, n_classes;
     unsigned int err;
     unsigned int bor_active;
+    unsigned int bor_done;           // a k_bor_min pass found no edge between two components: the later rounds return at once
     unsigned int n_payload_slow;
     unsigned int n_pending;
     unsigned long long n_xrows;      // extra slot rows asked for by the group table

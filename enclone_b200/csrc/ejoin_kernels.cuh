@@ -1828,6 +1828,7 @@ __global__ void k_fill_u64(unsigned long long *p, unsigned long long v, size_t n
 
 __global__ void k_bor_min(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *k_to_s, uint32_t k_base,
                           uint32_t *parent, unsigned long long *best, uint2 *ends) {
+    if (ctr->bor_done) return;                        // an earlier pass found the forest complete
     unsigned long long n = ctr->n_accept;
     if (n > cap) n = cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -1844,6 +1845,11 @@ __global__ void k_bor_min(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long
 }
 __global__ void k_bor_select(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, uint32_t *parent,
                              const unsigned long long *best, const uint2 *ends) {
+    if (ctr->bor_done) return;
+    if (!ctr->bor_active) {                           // the k_bor_min pass before this one found nothing left to merge
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctr->bor_done = 1;      // read by the NEXT kernels only (this one tests bor_active)
+        return;
+    }
     unsigned long long n = ctr->n_accept;
     if (n > cap) n = cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -1859,6 +1865,7 @@ __global__ void k_bor_select(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned l
 }
 // reset `best` only where it was touched
 __global__ void k_bor_reset(const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, unsigned long long *best, const uint2 *ends) {
+    if (ctr->bor_done) return;
     unsigned long long n = ctr->n_accept;
     if (n > cap) n = cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
