@@ -4,11 +4,6 @@
 
 #include "ejoin_dev.cuh"
 
-__device__ __forceinline__ int warp_sum_i(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
 
 __device__ __forceinline__ uint32_t uf_find(uint32_t *p, uint32_t x);
 __device__ __forceinline__ void uf_union(uint32_t *p, uint32_t a, uint32_t b);
@@ -299,12 +294,6 @@ __device__ __forceinline__ void planes32(const uint32_t (&x)[8], uint32_t &H, ui
     H = 0; L = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) { H |= nibble_of(x[i] >> 2) << (4 * i); L |= nibble_of(x[i] >> 1) << (4 * i); }
-}
-__device__ __forceinline__ uint32_t neq32(const uint32_t (&x)[8], const uint32_t (&r)[8]) {   // bit i = (byte i differs)
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) m |= ((nonzero_bytes(x[i] ^ r[i]) * 0x01020408u) >> 24 & 0xFu) << (4 * i);
-    return m;
 }
 
 __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ gid_incl,
