@@ -676,7 +676,7 @@ __device__ __forceinline__ void cdr3_counts_w(const uint32_t *__restrict__ c3, u
 }
 union MetaRegs { EntryMeta m; uint4 q[8]; __device__ MetaRegs() {} };
 
-__device__ __noinline__ int evaluate_thread(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa,
+__device__ __forceinline__ int evaluate_thread(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa,
                                                uint32_t sb, int *cd_out, int *d_out, int *err_out, bool *scored, unsigned long long *bytes) {
     // Inside a comparison group sorted position order == info order (stable sort of ascending k), so the
     // entry at the smaller position is k1: no need to look at the records to order the pair.
