@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(256) k_phaseb_cross(const uint2 *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(128, 6) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
+__global__ void __launch_bounds__(128, 5) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
                                                unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t k_base,
                                                uint32_t *parent_min) {
     unsigned long long ntodo = ctr->n_todo;
@@ -1032,6 +1032,7 @@ __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const En
     int dfw = 0, d12 = 0;
     int f1 = 0, c1 = 0, f2 = 0, c2 = 0, f3 = 0;
     const bool reg = pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2, &f3);
+#pragma unroll
     for (int c = 0; c < 2; c++) {
         const int n = m1.len[c];
         const uint8_t *t1 = in.tig_arena + in.tig_off[c][k1], *t2 = in.tig_arena + in.tig_off[c][k2];
