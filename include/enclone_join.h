@@ -192,13 +192,15 @@ int  ejoin_create(ejoin_handle_t **h, const ejoin_params_t *p, int device);
 void ejoin_destroy(ejoin_handle_t *h);
 const char *ejoin_last_error(const ejoin_handle_t *h);
 
-/* The whole join stage on one GPU: H2D, pack, score, compact, union-find, D2H,
- * ordered replay.  Equivalent of join_exacts + finish_join. */
+/* The whole join stage on one GPU: upload (overlapped with the first kernels), pack, score, the spanning
+ * forest + two-cell rule + ordered raw_joins on the device, per-edge payload, union-find, D2H into the
+ * handle's pinned result buffer.  Equivalent of join_exacts + finish_join.  `out` points into that buffer:
+ * valid until the next call on the handle. */
 int  ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pack, ejoin_result_t *out);
 void ejoin_result_free(ejoin_result_t *r);
 
 /* Multi-GPU decomposition (one process per GPU):
- *   every rank: ejoin_plan_shards() -> which buckets this rank owns (size-aware LPT),
+ *   every rank: ejoin_plan_shards() -> which buckets this rank owns (contiguous, cost-balanced ranges),
  *               ejoin_run_shard()   -> accepted raw edges for those buckets (global info ids),
  *   all-gather the raw edges (NCCL; done by the host framework),
  *   then       ejoin_finish()       -> ordered replay, per-edge payload, partition. */
