@@ -635,7 +635,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumC, sumC, (int)n, st);
         k_group_build<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, groups, ctr);
-        h->launches += 1;
+        h->launches += 2;                           // k_group_vals, k_group_build (own kernels only: CUB's sort / RLE / scan passes are never counted)
         mark(h, "rle + group table");
         k_item_hist<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, item_cap, stride, phase);
         k_item_scatter<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, order, item_cap, stride, phase);
@@ -648,7 +648,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_t2_sizes<<<nb256, 256, 0, st>>>(h->din, perm, ctr, t2sizes);
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t2sizes, t2off, (int)n, st);
-        h->launches += 2;                           // own kernels only; CUB's sort/RLE/scan launches are not counted
+        h->launches += 1;                           // k_t2_sizes
         CK(cudaEventRecord(h->ev[1], st));
         mark(h, "heads/scans/t2 sizes");
         k_pack_c3<<<(unsigned)(((size_t)n * 4 + 255) / 256), 256, 0, st>>>(h->din, perm, gid, groups, ctr, c3);
@@ -693,7 +693,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         mark(h, "k_phase_a");
         k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
         mark(h, "k_phase_a_pending");
-        h->launches += 8;
+        h->launches += 7;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
         k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, ccap);
@@ -713,6 +713,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, nullptr);
         mark(h, "k_tier2 r2");
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, nullptr, 1);
+        h->launches += 19;                          // phase B: split, 2 x (k_tier2, k_tier2_generic), resolve, 10 root jumps, round-2 begin, prune, cross
         CK(cudaEventRecord(h->ev[4], st));
         mark(h, "k_tier2_generic r2");
         const bool device_final = stride == 1;      // stride mode: the forest needs every rank's edges -> host replay after the gather
@@ -932,7 +933,7 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
         CK(cudaMemsetAsync(&ctr->n_payload_slow, 0, sizeof(unsigned int), h->st));
         k_payload_fast<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)ne, h->k_base, d_out, d_slow);
         k_payload<<<h->sm_count * 4, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, d_slow, h->k_base, d_out);
-        h->launches += 2;
+        h->launches += d_keys ? 3 : 2;               // (k_keys_to_pairs,) k_payload_fast, k_payload
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_edges, d_out, ne * sizeof(ejoin_edge_t), cudaMemcpyDeviceToHost, h->st));
     }
