@@ -114,7 +114,7 @@ def make_workload(name, scale, pinned):
     return sp, gen_s, (L, registered)
 
 
-def cpu_baseline(sp, params, target_s=12.0, steps=1, warmup=0):
+def cpu_baseline(sp, params, target_s=12.0, steps=1, warmup=0, best=False):
     """The CPU restatement of the reference join (oracle/), all host threads, on a bounded
     representative sample: every stride-th lens bucket.  Returns (pairs/s, info)."""
     import oracle_lib as O
@@ -135,10 +135,11 @@ def cpu_baseline(sp, params, target_s=12.0, steps=1, warmup=0):
         if it >= warmup:
             times.append(dt)
         pairs = st["pairs_candidate"]
-    sec = sum(times) / len(times)
+    sec = min(times) if best else sum(times) / len(times)     # best-of: the box's host cores are shared, a pass can be disturbed
     info = {"cores": threads, "kind": "port",
             "sample": f"every {stride}-th lens bucket of the workload ({st['n_buckets']} buckets scanned, {pairs} candidate pairs, "
-                      f"{st['pairs_evaluated']} evaluated after skip-if-joined, {sec:.2f} s per pass)",
+                      f"{st['pairs_evaluated']} evaluated after skip-if-joined, {sec:.2f} s per pass"
+                      + (f", best of {len(times)} passes)" if best and len(times) > 1 else ")"),
             "pairs": pairs, "seconds": sec, "stride": stride}
     return pairs / sec, info
 
@@ -312,7 +313,7 @@ def main():
                                      if k2 in e2e_stats}},
             "gpu_launches": int(st["gpu_launches"]) * K, "roofline": roofline}
     if not args.no_cpu_baseline:
-        val, info = cpu_baseline(sp, params)
+        val, info = cpu_baseline(sp, params, steps=2, best=True)
         line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
     print(json.dumps(line))
     j.close()
