@@ -40,7 +40,7 @@ class EjoinParams(C.Structure):
         ("comp_filt_bound", C.c_int32), ("max_cdr3_diffs", C.c_int32), ("cdr3_mult", C.c_int32),
         ("max_degradation", C.c_int32), ("max_diffs", C.c_int32), ("max_diffs_tcr", C.c_int32),
         ("ref_v_trim", C.c_int32), ("ref_j_trim", C.c_int32), ("easy", C.c_int32), ("old_light", C.c_int32),
-        ("old_mult", C.c_int32), ("mix_donors", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("old_mult", C.c_int32), ("mix_donors", C.c_int32), ("degradation_mode", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 

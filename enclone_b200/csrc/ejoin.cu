@@ -111,6 +111,7 @@ struct ejoin_handle {
     uint64_t launches = 0;
     // pinned staging for results
     void *pin = nullptr; size_t pin_cap = 0;
+    void *pin2 = nullptr; size_t pin2_cap = 0;   // ejoin_partition_gpu staging (h->pin may hold a live result)
     // host replay scratch (kept across runs; only touched entries are reset)
     std::vector<uint32_t> uf_parent, cnt_tmp;
     std::vector<size_t> forest_tmp;
@@ -135,7 +136,7 @@ DevParams dev_params(const ejoin_params_t &p, int is_bcr) {
     d.auto_share = p.auto_share; d.comp_filt = p.comp_filt; d.comp_filt_bound = p.comp_filt_bound;
     d.max_cdr3_diffs = p.max_cdr3_diffs; d.cdr3_mult = p.cdr3_mult; d.max_degradation = p.max_degradation;
     d.max_diffs = p.max_diffs; d.max_diffs_tcr = p.max_diffs_tcr; d.ref_v_trim = p.ref_v_trim; d.ref_j_trim = p.ref_j_trim;
-    d.old_light = p.old_light; d.mix_donors = p.mix_donors; d.is_bcr = is_bcr; d.easy = p.easy;
+    d.old_light = p.old_light; d.mix_donors = p.mix_donors; d.is_bcr = is_bcr; d.easy = p.easy; d.degradation_mode = p.degradation_mode;
     return d;
 }
 
@@ -253,6 +254,7 @@ extern "C" void ejoin_destroy(ejoin_handle_t *h) {
         b->release();
     for (auto &t : h->p1_tables) t.release();
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->pin2) cudaFreeHost(h->pin2);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->ev_chunk) if (e) cudaEventDestroy(e);
     if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
@@ -284,11 +286,38 @@ extern "C" int ejoin_host_unregister(void *p) {
 
 namespace {
 
+// every array the library dereferences, given the counts (the header promises EJOIN_E_ARG, not a crash)
+const char *pack_null_field(const ejoin_pack_t *pk) {
+    if (pk->n_info) {
+        if (!pk->exact_id) return "exact_id";
+        if (!pk->c_ref_id_light) return "c_ref_id_light";
+        if (!pk->hcomp) return "hcomp";
+        if (!pk->fr1_start || !pk->cdr1_start || !pk->fr2_start || !pk->cdr2_start || !pk->fr3_start) return "region starts";
+        if (!pk->tig_arena) return "tig_arena";
+        if (!pk->cdr3_arena) return "cdr3_arena";
+        for (int c = 0; c < 2; c++) {
+            if (!pk->len[c]) return "len";
+            if (!pk->tig_off[c]) return "tig_off";
+            if (!pk->has_del[c]) return "has_del";
+            if (!pk->cdr3_len[c]) return "cdr3_len";
+            if (!pk->cdr3_off[c]) return "cdr3_off";
+            if (!pk->cdr3_start[c]) return "cdr3_start";
+            if (!pk->v_ref_id[c] || !pk->j_ref_id[c] || !pk->dref_id[c]) return "v_ref_id/j_ref_id/dref_id";
+            if (!pk->vs_seq[c] || !pk->js_seq[c] || !pk->vuni_seq[c] || !pk->utr_seq[c]) return "vs_seq/js_seq/vuni_seq/utr_seq";
+            if (!pk->vname_id[c]) return "vname_id";
+        }
+        if (!pk->n_exact) return "n_exact is 0 with n_info > 0";
+    }
+    if (pk->n_exact && (!pk->nchains || !pk->ncells || !pk->donor_lo || !pk->donor_hi)) return "nchains/ncells/donor_lo/donor_hi";
+    if (pk->n_refseq && (!pk->refseq_off || !pk->refseq_len || !pk->refseq_arena)) return "refseq_off/refseq_len/refseq_arena";
+    return nullptr;
+}
+
 int check_pack(ejoin_handle *h, const ejoin_pack_t *pk) {
     if (!pk) return fail(h, EJOIN_E_ARG, "null pack");
     if (pk->abi_version != EJOIN_ABI_VERSION) return fail(h, EJOIN_E_ARG, "abi_version mismatch");
-    if (pk->n_info && (!pk->exact_id || !pk->len[0] || !pk->len[1] || !pk->tig_arena || !pk->cdr3_arena || !pk->nchains))
-        return fail(h, EJOIN_E_ARG, "null array in pack");
+    const char *bad = pack_null_field(pk);
+    if (bad) return fail(h, EJOIN_E_ARG, std::string("null array in pack: ") + bad);
     return 0;
 }
 
@@ -435,6 +464,7 @@ int prepare_tables(ejoin_handle *h, int is_bcr) {
     CK(cudaStreamSynchronize(h->st));
     if (h->counters.err & ERR_CDR3_TOO_LONG) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 exceeds 255 nt (or 256 nt for both chains)");
     if (h->counters.err & ERR_LEN_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "V..J lengths of one entry sum to 8192 or more");
+    if (h->counters.err & ERR_BAD_EXACT) return fail(h, EJOIN_E_ARG, "exact_id outside [0, n_exact)");
     // p1 tables for new L
     std::vector<uint32_t> newL;
     for (uint32_t L = 0; L < 8192; L++)
@@ -987,6 +1017,8 @@ extern "C" int ejoin_upload_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int
 
 extern "C" int ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats) {
     if (!h) return EJOIN_E_ARG;
+    // an in-place run leaves din.tig_src pointing at the caller's arena, which the caller owns only during that call
+    if (h->uploaded && h->tigs_in_place) return fail(h, EJOIN_E_ARG, "ejoin_run_resident needs ejoin_upload / ejoin_upload_shard first (the last run read the caller's arena in place)");
     h->launches = 0;
     int rc = device_pipeline(h, h->is_bcr, h->last_stride, h->last_phase);
     if (rc) return rc;
@@ -1073,6 +1105,7 @@ static void plan_buckets(const ejoin_pack_t *pk, int world, std::vector<uint32_t
 
 extern "C" int ejoin_plan_shards(const ejoin_pack_t *pk, int world, uint32_t *owner, uint32_t *bstart, uint32_t cap, uint32_t *nb_out) {
     if (!pk || world < 1 || !nb_out) return EJOIN_E_ARG;
+    if (pk->abi_version != EJOIN_ABI_VERSION || (pk->n_info && (!pk->len[0] || !pk->len[1]))) return EJOIN_E_ARG;
     std::vector<uint32_t> bs, own;
     plan_buckets(pk, world, bs, own);
     const uint32_t nb = (uint32_t)own.size();
@@ -1183,6 +1216,18 @@ extern "C" void ejoin_raw_free(ejoin_raw_edge_t *e) { free(e); }
 extern "C" int ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pk, const ejoin_raw_edge_t *edges, uint64_t n_edges, ejoin_result_t *out) {
     if (!h || !pk || !out || (n_edges && !edges)) return EJOIN_E_ARG;
     memset(out, 0, sizeof(*out));
+    {
+        int rc0 = check_pack(h, pk);
+        if (rc0) return rc0;
+        if (!h->uploaded && n_edges) return fail(h, EJOIN_E_ARG, "ejoin_finish: the handle holds no upload");
+        // every endpoint must lie in the range this handle holds ([k_base, k_base + n): everything in stride mode,
+        // the rank's own buckets otherwise): the payload kernels index the resident rows by k - k_base
+        const uint64_t lo = h->k_base, hi = (uint64_t)h->k_base + h->n;
+        for (uint64_t i = 0; i < n_edges; i++)
+            if (edges[i].k1 >= edges[i].k2 || edges[i].k2 >= pk->n_info || edges[i].k1 < lo || edges[i].k2 >= hi)
+                return fail(h, EJOIN_E_ARG, "ejoin_finish: an edge endpoint lies outside the entries this handle holds "
+                                            "(gather-then-finish needs stride mode or a handle holding the whole input)");
+    }
     std::vector<std::pair<unsigned long long, unsigned long long>> kv(n_edges);
     for (uint64_t i = 0; i < n_edges; i++) {
         kv[i].first = ((unsigned long long)edges[i].k1 << 32) | edges[i].k2;
@@ -1224,11 +1269,17 @@ extern "C" int ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pk, co
     uint32_t *d_first = (uint32_t *)base; base += 4 * (size_t)std::max(1u, nx);
     base = (char *)(((uintptr_t)base + 15) & ~(uintptr_t)15);
     uint2 *d_pairs = (uint2 *)base;
-    int rc = ensure_pin(h, 8 * (ne + 1) + 4 * (size_t)n + 1024);
-    if (rc) return rc;
-    uint2 *hp = (uint2 *)h->pin;
+    // its own pinned staging: h->pin may hold a live result (one live result per handle)
+    const size_t need2 = ((8 * (ne + 1) + 255) & ~(size_t)255) + 4 * (size_t)n + 1024;
+    if (need2 > h->pin2_cap) {
+        if (h->pin2) cudaFreeHost(h->pin2);
+        h->pin2 = nullptr; h->pin2_cap = 0;
+        CK(cudaMallocHost(&h->pin2, need2 + need2 / 2));
+        h->pin2_cap = need2 + need2 / 2;
+    }
+    uint2 *hp = (uint2 *)h->pin2;
     for (uint64_t i = 0; i < ne; i++) { if (k1[i] >= n || k2[i] >= n) return fail(h, EJOIN_E_ARG, "edge endpoint out of range"); hp[i] = make_uint2(k1[i], k2[i]); }
-    uint32_t *hl = (uint32_t *)((char *)h->pin + ((8 * (ne + 1) + 255) & ~(size_t)255));
+    uint32_t *hl = (uint32_t *)((char *)h->pin2 + ((8 * (ne + 1) + 255) & ~(size_t)255));
     DevCounters *ctr = (DevCounters *)h->d_counters.p;
     CK(cudaMemcpyAsync(d_exact, pk->exact_id, 4 * (size_t)n, cudaMemcpyHostToDevice, h->st));
     if (ne) CK(cudaMemcpyAsync(d_pairs, hp, 8 * ne, cudaMemcpyHostToDevice, h->st));

@@ -29,6 +29,7 @@
 #define ERR_BAD_REFSEQ 4u
 #define ERR_K_TOO_LARGE 8u
 #define ERR_LEN_TOO_LARGE 16u
+#define ERR_BAD_EXACT 64u         // exact_id[k] >= n_exact
 #define ERR_GROUP_TOO_LARGE 32u   // a comparison group of more than 65535 tiles (8.3 M entries with equal lengths)
 
 struct __align__(16) EntryMeta {
@@ -96,7 +97,7 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
 struct DevParams {           // ejoin_params_t plus run constants, by value to kernels
     double max_score, join_cdr3_ident, fwr1_cdr12_delta;
     int auto_share, comp_filt, comp_filt_bound, max_cdr3_diffs, cdr3_mult, max_degradation;
-    int max_diffs, max_diffs_tcr, ref_v_trim, ref_j_trim, old_light, mix_donors, is_bcr, easy;
+    int max_diffs, max_diffs_tcr, ref_v_trim, ref_j_trim, old_light, mix_donors, is_bcr, easy, degradation_mode;
 };
 
 struct MultInfo { uint32_t off; uint32_t d1p1; };   // per (cl0,cl1): pool offset, row stride (D1+1); off = ~0 if absent

@@ -33,6 +33,7 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
         uint32_t l0 = in.len[0][k], l1 = in.len[1][k], c0 = in.cdr3_len[0][k], c1 = in.cdr3_len[1][k];
         uint32_t e = in.exact_id[k];
         uint32_t nch = e < in.n_exact ? in.nchains[e] : 0;
+        if (e >= in.n_exact) atomicOr(&ctr->err, ERR_BAD_EXACT);
         bool valid = l1 > 0 && nch >= 2 && nch <= 3;
         unsigned long long key = ~0ull;
         if (valid) {
@@ -547,6 +548,7 @@ struct PairCounts {
     int det[2][4];
     int nrefs;
     int dfw, lfw, dc12, l12;     // FWR1 / CDR1+CDR2 region counts; lfw == 0 when the gate is skipped
+    int refdiff;                 // positions at which the two entries' assigned references differ (nrefs == 2; help1.rs:345-348)
 };
 
 // The decision in two steps, so that callers can count the FWR1 / CDR1+CDR2 differences only for pairs that got past
@@ -557,7 +559,10 @@ __device__ __forceinline__ int decide_score(const DevParams &pr, const DevTables
                                             const PairCounts &pc, DevCounters *ctr, const double *p1tab_L, const MultInfo mi2, int *kout,
                                             int *dout, int *mo_out, double *p1o, double *multo, double *scoreo) {
     const int cd = pc.cd0 + pc.cd1;
-    if (pc.nrefs == 2) { int df = pc.shares[0] - pc.shares[1]; if (df < 0) df = -df; if (df > pr.max_degradation) return 0; }
+    if (pc.nrefs == 2) {            // MAX_DEGRADATION, both readings (include/enclone_join.h: degradation_mode)
+        if (pr.degradation_mode == 1) { int df = pc.shares[0] - pc.shares[1]; if (df < 0) df = -df; if (df > pr.max_degradation) return 0; }
+        else if (pc.refdiff > pr.max_degradation) return 0;
+    }
     int d = pc.shares[0], mi = pc.indeps[0], mo = pc.indeps_out[0];
     if (pc.nrefs == 2) { d = min(d, pc.shares[1]); mi = min(mi, pc.indeps[1]); mo = min(mo, pc.indeps_out[1]); }
     const int k = mi + 2 * d;
@@ -731,7 +736,7 @@ __device__ __forceinline__ int evaluate_thread(const DevIn &in, const DevTables 
     }
     *bytes += 2ull * (48ull * nblk + 128ull);
     PairCounts pc;
-    pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1;
+    pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1; pc.refdiff = 0;      // same germline sequences on this path
     for (int c2 = 0; c2 < 2; c2++)
         if (m1.vref[c2] != m2.vref[c2] || m1.dref[c2] != m2.dref[c2] || m1.jref[c2] != m2.jref[c2]) pc.nrefs = 2;
     // One pass over the t2 rows counts total differences, shared mutations and, when cd >= CDR3_MULT, the non-shared
@@ -1093,6 +1098,21 @@ __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const En
             }
         }
     }
+    int refdiff = 0;
+    if (nrefs == 2 && pr.degradation_mode != 1) {
+        // V references left-aligned, J references right-aligned; unmatched positions of the longer one count as differing
+        for (int c = 0; c < 2; c++) {
+            for (int vj = 0; vj < 2; vj++) {
+                const uint32_t i1 = vj ? m1.js[c] : m1.vs[c], i2 = vj ? m2.js[c] : m2.vs[c];
+                if (i1 == i2) continue;
+                const int l1 = (int)in.refseq_len[i1], l2 = (int)in.refseq_len[i2], mn = min(l1, l2);
+                const uint8_t *a = in.refseq_arena + in.refseq_off[i1] + (vj ? l1 - mn : 0), *b = in.refseq_arena + in.refseq_off[i2] + (vj ? l2 - mn : 0);
+                for (int p = lane; p < mn; p += 32) refdiff += (a[p] != b[p]);
+                if (lane == 0) refdiff += abs(l1 - l2);
+            }
+        }
+    }
+    pc.refdiff = warp_sum(refdiff);
     pc.diffs = warp_sum(diffs); pc.cd0 = warp_sum(cdc[0]); pc.cd1 = warp_sum(cdc[1]);
     for (int u = 0; u < 2; u++) {
         pc.shares[u] = warp_sum(sh[u]); pc.indeps[u] = warp_sum(in_[u]); pc.indeps_out[u] = warp_sum(io[u]);

@@ -123,7 +123,11 @@ typedef struct ejoin_params {
     int32_t old_light;           /* OLD_LIGHT                                      */
     int32_t old_mult;            /* OLD_MULT (unsupported on the GPU: EJOIN_E_UNSUPPORTED) */
     int32_t mix_donors;          /* MIX_DONORS (clono_filt_opt_def.donor)          */
-    int32_t reserved[5];
+    int32_t degradation_mode;    /* how MAX_DEGRADATION is read (help1.rs:345-348):
+                                  * 0 = the documented rule: the references assigned to the two entries may differ in at most
+                                  *     MAX_DEGRADATION positions (V left-aligned, J right-aligned, both chains summed);
+                                  * 1 = |shares[0] - shares[1]| <= MAX_DEGRADATION (recollection of the upstream code) */
+    int32_t reserved[4];
 } ejoin_params_t;
 
 /* One emitted join = one PotentialJoin that survived. */

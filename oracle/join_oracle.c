@@ -242,6 +242,32 @@ int oracle_fwr1_cdr12_counts(const ejoin_pack_t *pk, uint32_t k1, uint32_t k2, i
     return 1;
 }
 
+/* Number of positions at which the germline sequences assigned to k1 and k2 differ
+ * (help1.rs:345-348, literal reading): V references compared left-aligned, J references
+ * right-aligned, unmatched tail / head positions of the longer one count as differing. */
+int oracle_ref_positions_differing(const ejoin_pack_t *pk, uint32_t k1, uint32_t k2) {
+    int tot = 0;
+    for (int c = 0; c < 2; c++) {
+        const uint32_t v1 = pk->vs_seq[c][k1], v2 = pk->vs_seq[c][k2];
+        if (v1 != v2) {
+            const int l1 = (int)pk->refseq_len[v1], l2 = (int)pk->refseq_len[v2];
+            const int m = l1 < l2 ? l1 : l2;
+            const uint8_t *a = refseq(pk, v1), *b = refseq(pk, v2);
+            for (int p = 0; p < m; p++) tot += (a[p] != b[p]);
+            tot += (l1 > l2 ? l1 - l2 : l2 - l1);
+        }
+        const uint32_t j1 = pk->js_seq[c][k1], j2 = pk->js_seq[c][k2];
+        if (j1 != j2) {
+            const int l1 = (int)pk->refseq_len[j1], l2 = (int)pk->refseq_len[j2];
+            const int m = l1 < l2 ? l1 : l2;
+            const uint8_t *a = refseq(pk, j1) + (l1 - m), *b = refseq(pk, j2) + (l2 - m);
+            for (int p = 0; p < m; p++) tot += (a[p] != b[p]);
+            tot += (l1 > l2 ? l1 - l2 : l2 - l1);
+        }
+    }
+    return tot;
+}
+
 /* join_one: the pairwise test.  SURVEY Appendix A.4; help1.rs:270-363.
  * Pure predicate of (k1,k2); fills *e on accept (and the count fields on every call that
  * reaches them).  Gate order is cheap-first; the order only affects logging in the
@@ -369,9 +395,21 @@ int oracle_join_one(const ejoin_pack_t *pk, const ejoin_params_t *pr, uint32_t k
                 }
         }
     }
-    /*    different references allowed only when they barely change the count
-     *    (MAX_DEGRADATION, help1.rs:345-348) [RECALL: |shares0 - shares1|] */
-    if (nrefs == 2 && abs(shares[0] - shares[1]) > pr->max_degradation) return 0;
+    /*    MAX_DEGRADATION (help1.rs:345-348): "We do not join two clonotypes which were assigned
+     *    different reference sequences unless those reference sequences differ by at most 2
+     *    positions."  degradation_mode 0 (default) implements that sentence literally [DOC]:
+     *    the number of positions at which the two entries' V references (left-aligned, as the
+     *    V window indexes them) and J references (right-aligned, as the J window indexes them)
+     *    differ, a length difference counting one per unmatched position, summed over both
+     *    chains.  degradation_mode 1 is the builder's recollection of the upstream code
+     *    [RECALL]: |shares[0] - shares[1]| > MAX_DEGRADATION.  SURVEY App. C-6. */
+    if (nrefs == 2) {
+        if (pr->degradation_mode == 1) {
+            if (abs(shares[0] - shares[1]) > pr->max_degradation) return 0;
+        } else {
+            if (oracle_ref_positions_differing(pk, k1, k2) > pr->max_degradation) return 0;
+        }
+    }
     int d = shares[0], mi = indeps[0], mo = indeps_out[0];
     if (nrefs == 2) {
         if (shares[1] < d) d = shares[1];
@@ -464,15 +502,143 @@ static void ev_push(evec_t *x, const ejoin_edge_t *e) {
     x->v[x->n++] = *e;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Tile-parallel join_core for ONE large bucket (test infrastructure for the 200,000-entry
+ * configuration, where the sequential scan below would take hours on one core).
+ * join_one is a pure predicate of (k1,k2), so `pot` = the replay of
+ * join_core's skip-if-same-class rule over the FULL accept set in (k1,k2) order.  Rows k1 are
+ * scored by worker threads; a pair is handed to oracle_join_one only when it passes a packed
+ * restatement of join_one's own first gates (b: CDR3 lengths equal; d: TCR cd = 0,
+ * cd <= MAX_CDR3_DIFFS, CDR3 identity >= JOIN_CDR3_IDENT with the same double expression) --
+ * pairs it drops are pairs oracle_join_one returns 0 for.  tests/test_oracle_kat.py checks that
+ * this mode and the sequential scan give identical edges on the same buckets.
+ * ---------------------------------------------------------------------------------------- */
+static uint32_t g_parallel_bucket_min = 0xFFFFFFFFu;     /* off unless a test asks for it */
+static int g_parallel_threads = 1;
+void oracle_set_parallel_bucket(uint32_t min_entries, int threads) {
+    g_parallel_bucket_min = min_entries ? min_entries : 0xFFFFFFFFu;
+    g_parallel_threads = threads < 1 ? 1 : threads;
+}
+
+typedef struct {
+    const ejoin_pack_t *pk; const ejoin_params_t *pr;
+    uint32_t i, j;
+    const uint64_t *packed;      /* [nb][pw] 2-bit CDR3s (both chains concatenated), NULL = no prefilter */
+    const uint8_t *packable;     /* [nb] CDR3s are ACGT only */
+    uint32_t pw;
+    _Atomic uint32_t *next_row;
+    evec_t acc;
+    ostats_t st;
+} prow_t;
+
+static int cdr3_prefilter_pass(const prow_t *w, uint32_t k1, uint32_t k2) {
+    const ejoin_pack_t *pk = w->pk; const ejoin_params_t *pr = w->pr;
+    if (pk->cdr3_len[0][k1] != pk->cdr3_len[0][k2] || pk->cdr3_len[1][k1] != pk->cdr3_len[1][k2]) return 0;
+    if (!w->packed || !w->packable[k1 - w->i] || !w->packable[k2 - w->i]) return 1;
+    const uint64_t *a = w->packed + (size_t)(k1 - w->i) * w->pw, *b = w->packed + (size_t)(k2 - w->i) * w->pw;
+    int cd = 0;
+    for (uint32_t q = 0; q < w->pw; q++) {
+        const uint64_t z = a[q] ^ b[q];
+        cd += __builtin_popcountll((z | (z >> 1)) & 0x5555555555555555ull);
+    }
+    if (!pk->is_bcr && cd > 0) return 0;
+    if (cd > pr->max_cdr3_diffs) return 0;
+    const int tot = pk->cdr3_len[0][k1] + pk->cdr3_len[1][k1];
+    const double ident = 100.0 * (1.0 - (double)cd / (double)tot);
+    if (ident < pr->join_cdr3_ident) return 0;
+    return 1;
+}
+
+static void *prow_main(void *arg) {
+    prow_t *w = (prow_t *)arg;
+    ejoin_edge_t e;
+    for (;;) {
+        const uint32_t r0 = atomic_fetch_add(w->next_row, 64);
+        if (r0 >= w->j - w->i) break;
+        const uint32_t r1 = r0 + 64 < w->j - w->i ? r0 + 64 : w->j - w->i;
+        for (uint32_t k1 = w->i + r0; k1 < w->i + r1; k1++)
+            for (uint32_t k2 = k1 + 1; k2 < w->j; k2++) {
+                if (!cdr3_prefilter_pass(w, k1, k2)) continue;
+                w->st.pairs_evaluated++;
+                if (oracle_join_one(w->pk, w->pr, k1, k2, &e, &w->st)) ev_push(&w->acc, &e);
+            }
+    }
+    return NULL;
+}
+
+static int edge_cmp(const void *a, const void *b) {
+    const ejoin_edge_t *x = (const ejoin_edge_t *)a, *y = (const ejoin_edge_t *)b;
+    if (x->k1 != y->k1) return x->k1 < y->k1 ? -1 : 1;
+    if (x->k2 != y->k2) return x->k2 < y->k2 ? -1 : 1;
+    return 0;
+}
+
+/* fills `pot` with join_core's result for the bucket [i,j) */
+static void join_core_parallel(const ejoin_pack_t *pk, const ejoin_params_t *pr, uint32_t i, uint32_t j, evec_t *pot, ostats_t *st) {
+    const uint32_t nb = j - i;
+    uint32_t maxlen = 0;
+    for (uint32_t k = i; k < j; k++) { uint32_t t = (uint32_t)pk->cdr3_len[0][k] + pk->cdr3_len[1][k]; if (t > maxlen) maxlen = t; }
+    const uint32_t pw = (maxlen + 31) / 32 ? (maxlen + 31) / 32 : 1;
+    uint64_t *packed = (uint64_t *)calloc((size_t)nb * pw, sizeof(uint64_t));
+    uint8_t *packable = (uint8_t *)malloc(nb);
+    for (uint32_t k = i; k < j; k++) {
+        uint64_t *row = packed + (size_t)(k - i) * pw;
+        uint32_t pos = 0; int ok = 1;
+        for (int c = 0; c < 2; c++) {
+            const uint8_t *q = cdr3(pk, c, k);
+            for (uint32_t p = 0; p < pk->cdr3_len[c][k]; p++, pos++) {
+                uint64_t code;
+                switch (q[p]) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break; default: code = 0; ok = 0; }
+                row[pos >> 5] |= code << (2 * (pos & 31));
+            }
+        }
+        packable[k - i] = (uint8_t)ok;
+    }
+    const int T = g_parallel_threads;
+    prow_t *ws = (prow_t *)calloc((size_t)T, sizeof(prow_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
+    _Atomic uint32_t next_row = 0;
+    for (int t = 0; t < T; t++) {
+        ws[t].pk = pk; ws[t].pr = pr; ws[t].i = i; ws[t].j = j; ws[t].packed = packed; ws[t].packable = packable; ws[t].pw = pw;
+        ws[t].next_row = &next_row;
+    }
+    if (T == 1) prow_main(&ws[0]);
+    else {
+        for (int t = 0; t < T; t++) pthread_create(&th[t], NULL, prow_main, &ws[t]);
+        for (int t = 0; t < T; t++) pthread_join(th[t], NULL);
+    }
+    evec_t all = { 0, 0, 0 };
+    for (int t = 0; t < T; t++) {
+        for (size_t q = 0; q < ws[t].acc.n; q++) ev_push(&all, &ws[t].acc.v[q]);
+        free(ws[t].acc.v);
+        st->pairs_evaluated += ws[t].st.pairs_evaluated; st->pairs_same_cdr3_len += ws[t].st.pairs_same_cdr3_len;
+        st->pairs_tier2 += ws[t].st.pairs_tier2; st->pairs_accepted += ws[t].st.pairs_accepted;
+    }
+    if (all.n) qsort(all.v, all.n, sizeof(ejoin_edge_t), edge_cmp);
+    /* the replay: exactly join_core's rule, applied to the accepted pairs in scan order */
+    equiv_t eq;
+    eq_init(&eq, (int32_t)nb);
+    for (size_t q = 0; q < all.n; q++) {
+        const int32_t a = (int32_t)(all.v[q].k1 - i), b = (int32_t)(all.v[q].k2 - i);
+        if (eq_class_id(&eq, a) == eq_class_id(&eq, b)) continue;
+        eq_join(&eq, a, b);
+        ev_push(pot, &all.v[q]);
+    }
+    eq_free(&eq);
+    free(all.v); free(ws); free(th); free(packed); free(packable);
+}
+
 static void bucket_join(const ejoin_pack_t *pk, const ejoin_params_t *pr, uint32_t i, uint32_t j,
                         evec_t *out, ostats_t *st) {
     const int32_t nb = (int32_t)(j - i);
     st->pairs_candidate += (uint64_t)nb * (uint64_t)(nb - 1) / 2;
     if (nb < 2) return;
     evec_t pot = { 0, 0, 0 };
+    equiv_t eq;
+    if ((uint32_t)nb >= g_parallel_bucket_min) join_core_parallel(pk, pr, i, j, &pot, st);
+    else {
     /* join_core: upper-triangle loop, skipping pairs already in one class
      * (pages/heuristics.html.src:30-32; idiom grouper.rs:406-412) */
-    equiv_t eq;
     eq_init(&eq, nb);
     ejoin_edge_t e;
     for (uint32_t k1 = i; k1 < j; k1++)
@@ -485,6 +651,7 @@ static void bucket_join(const ejoin_pack_t *pk, const ejoin_params_t *pr, uint32
             }
         }
     eq_free(&eq);
+    }
     /* two-cell rule, applied in two passes (help1.rs:349-353; PREHISTORY:14607) */
     int32_t *size = (int32_t *)malloc(sizeof(int32_t) * (size_t)nb);
     for (int pass = 0; pass < 2; pass++) {

@@ -32,7 +32,7 @@ pub struct ejoin_params_t {
     pub max_score: f64, pub mult_pow: f64, pub join_cdr3_ident: f64, pub fwr1_cdr12_delta: f64,
     pub cdr3_normal_len: i32, pub auto_share: i32, pub comp_filt: i32, pub comp_filt_bound: i32, pub max_cdr3_diffs: i32,
     pub cdr3_mult: i32, pub max_degradation: i32, pub max_diffs: i32, pub max_diffs_tcr: i32, pub ref_v_trim: i32, pub ref_j_trim: i32,
-    pub easy: i32, pub old_light: i32, pub old_mult: i32, pub mix_donors: i32, pub reserved: [i32; 5],
+    pub easy: i32, pub old_light: i32, pub old_mult: i32, pub mix_donors: i32, pub degradation_mode: i32, pub reserved: [i32; 4],
 }
 
 #[repr(C)]

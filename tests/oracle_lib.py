@@ -48,6 +48,9 @@ def lib():
         L.oracle_result_free.argtypes = [C.POINTER(EjoinResult)]
         L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_prepare.argtypes = [C.c_int]
+        L.oracle_set_parallel_bucket.argtypes = [C.c_uint32, C.c_int]
+        L.oracle_ref_positions_differing.argtypes = [C.POINTER(EjoinPack), C.c_uint32, C.c_uint32]
+        L.oracle_ref_positions_differing.restype = C.c_int
         _lib = L
     return _lib
 
@@ -90,6 +93,16 @@ def join_exacts(pack_struct, params=None, threads=1, bucket_lo=0, bucket_hi=0xFF
     stats = {n: getattr(st, n) for n, _ in st._fields_}
     L.oracle_result_free(C.byref(res))
     return edges, cls, stats
+
+
+def set_parallel_bucket(min_entries, threads):
+    """Buckets with at least `min_entries` entries are scored by `threads` workers row by row and
+    replayed in scan order (join_oracle.c, join_core_parallel); 0 switches the mode off."""
+    lib().oracle_set_parallel_bucket(min_entries, threads)
+
+
+def ref_positions_differing(pack_struct, k1, k2):
+    return lib().oracle_ref_positions_differing(C.byref(pack_struct), k1, k2)
 
 
 def accept_graph(pack_struct, params, i, j):

@@ -66,7 +66,8 @@ def test_giant_bucket_small():
 
 @pytest.mark.parametrize("over", [dict(mix_donors=1), dict(easy=1), dict(max_score=1.0), dict(auto_share=1000000 if False else 100),
                                   dict(join_cdr3_ident=0.0, max_cdr3_diffs=15), dict(max_diffs=55), dict(old_light=1),
-                                  dict(cdr3_mult=100), dict(comp_filt=1000000), dict(max_degradation=0), dict(ref_v_trim=0, ref_j_trim=0)])
+                                  dict(cdr3_mult=100), dict(comp_filt=1000000), dict(max_degradation=0), dict(ref_v_trim=0, ref_j_trim=0),
+                                  dict(degradation_mode=1), dict(degradation_mode=1, max_degradation=0), dict(max_degradation=1), dict(max_degradation=40)])
 def test_parameter_variants(over):
     pack, _ = synth.generate(n_cells=6000, n_donors=3, seed=11)
     g, oe, oc, _ = _run_both(pack, **over)
@@ -93,6 +94,7 @@ def test_randomized_repertoires_and_parameters(case):
     if rng.random() < 0.3: over["cdr3_mult"] = int(rng.integers(1, 8))
     if rng.random() < 0.3: over["comp_filt"] = int(rng.integers(0, 20))
     if rng.random() < 0.3: over["max_degradation"] = int(rng.integers(0, 5))
+    if rng.random() < 0.4: over["degradation_mode"] = 1
     if rng.random() < 0.2: over["easy"] = 1
     if rng.random() < 0.2: over["fwr1_cdr12_delta"] = float(rng.uniform(0, 40))
     if rng.random() < 0.2: over["max_diffs"] = int(rng.integers(5, 120))
@@ -284,13 +286,15 @@ def test_upload_shard_resident_matches_shard_run():
     assert total == len(join_exacts(pack).edges)
 
 
-@pytest.mark.parametrize("name,scale", [("C3", 1.0), ("C5", 1.0), ("C4", 0.1), ("C2", 1.0)])
-def test_full_size_configs_against_oracle(name, scale):
-    """BASELINE.json's configurations at (or near) full size: bit-exact edges, per-edge integers and
-    partition against the multithreaded CPU oracle, plus size-independent properties."""
+@pytest.mark.parametrize("name,scale,over", [("C3", 1.0, {}), ("C3", 1.0, dict(mix_donors=1)), ("C5", 1.0, {}), ("C4", 0.1, {}), ("C4", 1.0, {}),
+                                             ("C2", 1.0, {})])
+def test_full_size_configs_against_oracle(name, scale, over):
+    """BASELINE.json's configurations at full size: bit-exact edges, per-edge integers and partition against the
+    multithreaded CPU oracle, plus size-independent properties.  The 200,000-entry bucket of C4 is scored by the
+    oracle's row-parallel mode (tests/test_oracle_kat.py checks that mode against the sequential scan)."""
     import os
     sp, _ = synth.generate_config(name, scale, copy=False)
-    params = default_params()
+    params = default_params(**over)
     j = Joiner(params)
     g = j.run(sp.struct)
     g2 = j.run(sp.struct)                                    # idempotent on a warm handle
@@ -303,11 +307,18 @@ def test_full_size_configs_against_oracle(name, scale):
     assert (g.class_of[g.edges["k1"]] == g.class_of[g.edges["k2"]]).all()
     assert (g.class_of <= np.arange(len(g.class_of))).all()  # labels are min members
     assert (g.class_of[g.class_of] == g.class_of).all()
-    oe, oc, ost = O.join_exacts(sp.struct, params, threads=os.cpu_count() or 1)
-    assert_same_join(g, oe, oc, what=f"{name} x{scale}")
+    if name == "C4" and scale >= 0.5:
+        O.set_parallel_bucket(50000, os.cpu_count() or 1)
+    try:
+        oe, oc, ost = O.join_exacts(sp.struct, params, threads=os.cpu_count() or 1)
+    finally:
+        O.set_parallel_bucket(0, 1)
+    assert_same_join(g, oe, oc, what=f"{name} x{scale} {over}")
     assert g.stats["pairs_candidate"] == ost["pairs_candidate"]
     # the GPU compares every pair of a comparison group; the oracle only those join_core did not skip
     assert g.stats["pairs_compared"] >= ost["pairs_same_cdr3_len"]
+    if over.get("mix_donors"):
+        assert g.edges["err"].sum() > 0            # cross-donor joins are kept and flagged (JOIN ERROR)
 
 
 def test_candidate_buffer_overflow_retry(monkeypatch):
@@ -369,3 +380,55 @@ def test_zero_copy_in_place_arena(monkeypatch):
     j.close()
     assert np.array_equal(g.edges, g2.edges) and np.array_equal(g.class_of, g2.class_of)
     assert moved_in_place < g2.stats["h2d_bytes"]          # fewer bytes crossed PCIe
+
+
+def test_finish_rejects_edges_outside_the_resident_range():
+    """ejoin_finish on a handle that holds one contiguous shard must refuse gathered edges of other shards
+    (EJOIN_E_ARG), not index its resident rows out of bounds."""
+    from enclone_b200._lib import EjoinError
+    from enclone_b200._abi import RAW_EDGE_DTYPE
+    pack, _ = synth.generate(n_cells=12000, n_donors=2, seed=31)
+    j0, j1 = Joiner(default_params()), Joiner(default_params())
+    raw0, _ = j0.run_shard(pack.struct, 0, 2)
+    raw1, _ = j1.run_shard(pack.struct, 1, 2)
+    assert len(raw0) and len(raw1)
+    fin = j0.finish(pack.struct, raw0)                       # its own edges: fine
+    assert len(fin.edges) > 0
+    with pytest.raises(EjoinError) as ei:
+        j0.finish(pack.struct, np.concatenate([raw0, raw1]))
+    assert ei.value.code == -1 and "outside" in str(ei.value)
+    bad = np.zeros(1, RAW_EDGE_DTYPE)
+    bad["k1"], bad["k2"] = 5, 5                              # k1 >= k2
+    with pytest.raises(EjoinError):
+        j0.finish(pack.struct, bad)
+    j0.close(); j1.close()
+
+
+def test_resident_run_after_in_place_run_is_refused():
+    from enclone_b200._lib import EjoinError
+    sp, _ = synth.generate(n_cells=20000, n_donors=2, seed=78, copy=False, pinned=True)
+    j = Joiner(default_params())
+    j.run(sp.struct)
+    with pytest.raises(EjoinError) as ei:
+        j.run_resident()
+    assert ei.value.code == -1
+    j.upload(sp.struct)
+    assert j.run_resident()["pairs_candidate"] > 0
+    j.close()
+
+
+def test_null_pack_arrays_are_an_argument_error():
+    from enclone_b200._lib import EjoinError
+    import ctypes as C
+    pack, _ = synth.generate(n_cells=500, seed=42)
+    for field in ("hcomp", "ncells", "refseq_len", "c_ref_id_light"):
+        good = JoinPack({k: v for k, v in pack.arrays.items()}, is_bcr=True)
+        setattr(good.struct, field, C.cast(None, type(getattr(good.struct, field))))
+        with pytest.raises(EjoinError) as ei:
+            join_exacts(good)
+        assert ei.value.code == -1 and "null array" in str(ei.value)
+    a = {k: (list(v) if isinstance(v, list) else v) for k, v in pack.arrays.items()}
+    ex = a["exact_id"].copy(); ex[7] = 10 ** 7; a["exact_id"] = ex
+    with pytest.raises(EjoinError) as ei:
+        join_exacts(JoinPack(a, is_bcr=True))
+    assert ei.value.code == -1 and "exact_id" in str(ei.value)
