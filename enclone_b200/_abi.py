@@ -7,12 +7,24 @@ import ctypes as C
 
 import numpy as np
 
-EJOIN_ABI_VERSION = 1
+EJOIN_ABI_VERSION = 2
 EJOIN_NONE = 0xFFFFFFFF
 EJOIN_NONE16 = 0xFFFF
 EJOIN_F_TIGS_IN_PLACE = 1
+EJOIN_F_TIGS_2BIT = 2
+EJOIN_F_ENTRY_RECS = 4
 
 u8p, u16p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64))
+
+
+class EjoinEntryRec(C.Structure):
+    _fields_ = [("tig_off", C.c_uint32 * 2), ("cdr3_start", C.c_uint16 * 2)] + [
+        (n, C.c_uint16 * 2) for n in ("v_ref_id", "j_ref_id", "dref_id", "vs_seq", "js_seq", "vname_id", "vuni_seq", "utr_seq")] + [
+        (n, C.c_uint16) for n in ("c_ref_id_light", "hcomp", "fr1_start", "cdr1_start", "fr2_start", "cdr2_start", "fr3_start")] + [
+        ("has_del", C.c_uint8 * 2), ("pad", C.c_uint8 * 4)]
+
+
+assert C.sizeof(EjoinEntryRec) == 64
 
 
 class EjoinPack(C.Structure):
@@ -29,6 +41,7 @@ class EjoinPack(C.Structure):
         ("fr1_start", u16p), ("cdr1_start", u16p), ("fr2_start", u16p), ("cdr2_start", u16p), ("fr3_start", u16p),
         ("nchains", u32p), ("ncells", u32p), ("donor_lo", u32p), ("donor_hi", u32p),
         ("refseq_off", u64p), ("refseq_len", u32p), ("refseq_arena", u8p), ("refseq_arena_bytes", C.c_uint64),
+        ("tig2_arena", u64p), ("tig2_arena_words", C.c_uint64), ("entry_rec", C.POINTER(EjoinEntryRec)),
     ]
 
 

@@ -13,6 +13,7 @@ EXPORTS = [
     "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
     "ejoin_plan_shards", "ejoin_run_shard", "ejoin_run_shard_final", "ejoin_partition_gpu", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_upload_shard", "ejoin_run_resident",
     "ejoin_host_alloc", "ejoin_host_free", "ejoin_host_register", "ejoin_host_unregister", "ejoin_p1", "ejoin_partition",
+    "ejoin_pack_compact", "ejoin_pack_compact_free",
 ]
 
 _lib = None
@@ -73,6 +74,9 @@ def load():
     L.ejoin_partition.argtypes = [C.POINTER(EjoinPack), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint64,
                                   C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.ejoin_partition.restype = C.c_int
+    L.ejoin_pack_compact.argtypes = [C.POINTER(EjoinPack), C.c_int, C.POINTER(C.POINTER(EjoinPack))]
+    L.ejoin_pack_compact.restype = C.c_int
+    L.ejoin_pack_compact_free.argtypes = [C.POINTER(EjoinPack)]
     L.ejoin_p1.argtypes = [C.c_uint32] * 3
     L.ejoin_p1.restype = C.c_double
     _lib = L

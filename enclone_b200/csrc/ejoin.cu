@@ -78,6 +78,9 @@ struct ejoin_handle {
     uint64_t chunk_end[8] = {};     // arena byte offset (caller coordinates) up to which chunk i has landed
     bool copy_pending = false;
     bool tigs_in_place = false;    // zero-copy: din.tig_arena aliases the caller's pinned arena
+    bool recs_pending = false;     // EJOIN_F_ENTRY_RECS: k_unpack_recs still has to run on this upload
+    const ejoin_entry_rec_t *d_rec = nullptr;
+    RecOut rec_out;
     int is_bcr = 1;
     int tables_is_bcr = -1;
     int sm_count = 148;
@@ -289,22 +292,30 @@ namespace {
 // every array the library dereferences, given the counts (the header promises EJOIN_E_ARG, not a crash)
 const char *pack_null_field(const ejoin_pack_t *pk) {
     if (pk->n_info) {
+        const bool recs = pk->flags & EJOIN_F_ENTRY_RECS;
         if (!pk->exact_id) return "exact_id";
-        if (!pk->c_ref_id_light) return "c_ref_id_light";
-        if (!pk->hcomp) return "hcomp";
-        if (!pk->fr1_start || !pk->cdr1_start || !pk->fr2_start || !pk->cdr2_start || !pk->fr3_start) return "region starts";
-        if (!pk->tig_arena) return "tig_arena";
+        if (recs && !pk->entry_rec) return "entry_rec";
+        if ((pk->flags & EJOIN_F_TIGS_2BIT) && !pk->tig2_arena && pk->tig2_arena_words) return "tig2_arena";
+        if (!(pk->flags & EJOIN_F_TIGS_2BIT) && !pk->tig_arena) return "tig_arena";
+        if (pk->tig_arena_bytes && !pk->tig_arena) return "tig_arena";
         if (!pk->cdr3_arena) return "cdr3_arena";
         for (int c = 0; c < 2; c++) {
             if (!pk->len[c]) return "len";
-            if (!pk->tig_off[c]) return "tig_off";
-            if (!pk->has_del[c]) return "has_del";
             if (!pk->cdr3_len[c]) return "cdr3_len";
             if (!pk->cdr3_off[c]) return "cdr3_off";
-            if (!pk->cdr3_start[c]) return "cdr3_start";
-            if (!pk->v_ref_id[c] || !pk->j_ref_id[c] || !pk->dref_id[c]) return "v_ref_id/j_ref_id/dref_id";
-            if (!pk->vs_seq[c] || !pk->js_seq[c] || !pk->vuni_seq[c] || !pk->utr_seq[c]) return "vs_seq/js_seq/vuni_seq/utr_seq";
-            if (!pk->vname_id[c]) return "vname_id";
+        }
+        if (!recs) {
+            if (!pk->c_ref_id_light) return "c_ref_id_light";
+            if (!pk->hcomp) return "hcomp";
+            if (!pk->fr1_start || !pk->cdr1_start || !pk->fr2_start || !pk->cdr2_start || !pk->fr3_start) return "region starts";
+            for (int c = 0; c < 2; c++) {
+                if (!pk->tig_off[c]) return "tig_off";
+                if (!pk->has_del[c]) return "has_del";
+                if (!pk->cdr3_start[c]) return "cdr3_start";
+                if (!pk->v_ref_id[c] || !pk->j_ref_id[c] || !pk->dref_id[c]) return "v_ref_id/j_ref_id/dref_id";
+                if (!pk->vs_seq[c] || !pk->js_seq[c] || !pk->vuni_seq[c] || !pk->utr_seq[c]) return "vs_seq/js_seq/vuni_seq/utr_seq";
+                if (!pk->vname_id[c]) return "vname_id";
+            }
         }
         if (!pk->n_exact) return "n_exact is 0 with n_info > 0";
     }
@@ -327,30 +338,42 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     const uint32_t n = hi - lo;
-    // arena slices actually referenced by [lo,hi)
-    uint64_t tlo = 0, thi = pk->tig_arena_bytes, clo = 0, chi = pk->cdr3_arena_bytes;
+    const bool two_bit = pk->flags & EJOIN_F_TIGS_2BIT, recs = pk->flags & EJOIN_F_ENTRY_RECS;
+    auto tig_off_of = [&](int c, uint32_t k) -> uint64_t { return recs ? (uint64_t)pk->entry_rec[k].tig_off[c] : pk->tig_off[c][k]; };
+    auto has_del_of = [&](int c, uint32_t k) -> bool { return recs ? pk->entry_rec[k].has_del[c] != 0 : pk->has_del[c][k] != 0; };
+    // arena slices actually referenced by [lo,hi): ASCII bytes [tlo,thi), 2-bit words [wlo,whi), CDR3 bytes [clo,chi).
+    // In 2-bit mode the ASCII arena only holds the few chains with a deletion marker: it goes up whole.
+    uint64_t tlo = 0, thi = pk->tig_arena_bytes, clo = 0, chi = pk->cdr3_arena_bytes, wlo = 0, whi = two_bit ? pk->tig2_arena_words : 0;
     if (lo != 0 || hi != pk->n_info) {
-        tlo = ~0ull; thi = 0; clo = ~0ull; chi = 0;
+        if (!two_bit) { tlo = ~0ull; thi = 0; }
+        clo = ~0ull; chi = 0; wlo = ~0ull; whi = 0;
         for (uint32_t k = lo; k < hi; k++)
             for (int c = 0; c < 2; c++) {
-                uint64_t o = pk->tig_off[c][k], e = o + pk->len[c][k];
-                tlo = std::min(tlo, o); thi = std::max(thi, e);
+                uint64_t o = tig_off_of(c, k), e;
+                if (two_bit && !has_del_of(c, k)) { e = o + (pk->len[c][k] + 31) / 32; wlo = std::min(wlo, o); whi = std::max(whi, e); }
+                else if (!two_bit) { e = o + pk->len[c][k]; tlo = std::min(tlo, o); thi = std::max(thi, e); }
                 o = pk->cdr3_off[c][k]; e = o + pk->cdr3_len[c][k];
                 clo = std::min(clo, o); chi = std::max(chi, e);
             }
-        if (n == 0) { tlo = thi = clo = chi = 0; }
+        if (n == 0) { clo = chi = 0; if (!two_bit) tlo = thi = 0; }
+        if (whi <= wlo) wlo = whi = 0;
+        if (thi < tlo) tlo = thi = 0;
     }
-    // zero-copy: the caller's arena is pinned, device-readable and padded (EJOIN_F_TIGS_IN_PLACE): k_pack_t2 and
-    // the bytewise path read it in place, and only the needed entries ever cross PCIe
+    // zero-copy: the caller's arena is pinned, device-readable and padded (EJOIN_F_TIGS_IN_PLACE): k_pack_t2 (and, for
+    // ASCII, the bytewise path through the mirror) reads it in place, and only the needed entries ever cross PCIe
     bool in_place = false;
     const uint8_t *in_place_ptr = nullptr;
-    if (allow_in_place && (pk->flags & EJOIN_F_TIGS_IN_PLACE) && thi > tlo && !getenv("EJOIN_NO_ZERO_COPY")) {
-        cudaPointerAttributes a0, a1;
-        if (cudaPointerGetAttributes(&a0, pk->tig_arena + tlo) == cudaSuccess && cudaPointerGetAttributes(&a1, pk->tig_arena + thi - 1) == cudaSuccess &&
-            a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost && a0.devicePointer) {
-            in_place_ptr = (const uint8_t *)a0.devicePointer;     // device alias of pk->tig_arena + tlo
-            in_place = true;
-        } else cudaGetLastError();
+    {
+        const uint8_t *a_lo = two_bit ? (const uint8_t *)(pk->tig2_arena + wlo) : pk->tig_arena + tlo;
+        const uint8_t *a_hi = two_bit ? (const uint8_t *)(pk->tig2_arena + whi) - 1 : pk->tig_arena + thi - 1;
+        if (allow_in_place && (pk->flags & EJOIN_F_TIGS_IN_PLACE) && a_hi > a_lo && !getenv("EJOIN_NO_ZERO_COPY")) {
+            cudaPointerAttributes a0, a1;
+            if (cudaPointerGetAttributes(&a0, a_lo) == cudaSuccess && cudaPointerGetAttributes(&a1, a_hi) == cudaSuccess &&
+                a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost && a0.devicePointer) {
+                in_place_ptr = (const uint8_t *)a0.devicePointer;     // device alias of the first referenced byte / word
+                in_place = true;
+            } else cudaGetLastError();
+        }
     }
     Sizer sz;
     const size_t n1 = n ? n : 1;
@@ -360,6 +383,7 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     for (int i = 0; i < 4; i++) sz.take(4 * (size_t)std::max(1u, pk->n_exact));
     sz.take(8 * (size_t)std::max(1u, pk->n_refseq)); sz.take(4 * (size_t)std::max(1u, pk->n_refseq));
     sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 512);
+    sz.take(8 * (whi - wlo) + 256); sz.take(sizeof(ejoin_entry_rec_t) * n1);
     sz.take(4 * (size_t)std::max(1u, pk->n_refseq)); sz.take(12 * ((size_t)pk->refseq_arena_bytes / 32 + 3 * (size_t)pk->n_refseq + 8));   // germline planes
     CK(h->in_arena.buf.ensure(sz.off + 4096));
     h->in_arena.reset();
@@ -390,23 +414,45 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
     CK(cudaEventRecord(h->ev_early, h->st_copy));
     // late set: what k_meta and the scoring read; goes up while the sweep runs
-    for (int c = 0; c < 2; c++) {
-        CK(up(d.tig_off[c], pk->tig_off[c] + lo, n));
-        CK(up(d.has_del[c], pk->has_del[c] + lo, n));
-        CK(up(d.cdr3_start[c], pk->cdr3_start[c] + lo, n));
-        CK(up(d.v_ref_id[c], pk->v_ref_id[c] + lo, n));
-        CK(up(d.j_ref_id[c], pk->j_ref_id[c] + lo, n));
-        CK(up(d.dref_id[c], pk->dref_id[c] + lo, n));
-        CK(up(d.vs_seq[c], pk->vs_seq[c] + lo, n));
-        CK(up(d.js_seq[c], pk->js_seq[c] + lo, n));
-        CK(up(d.vname_id[c], pk->vname_id[c] + lo, n));
-        CK(up(d.vuni_seq[c], pk->vuni_seq[c] + lo, n));
-        CK(up(d.utr_seq[c], pk->utr_seq[c] + lo, n));
+    h->recs_pending = false;
+    if (recs) {
+        // one 64-byte record per entry crosses PCIe; k_unpack_recs (first thing after the wait for the late set) widens it
+        // into the parallel arrays the kernels read
+        const ejoin_entry_rec_t *d_rec = nullptr;
+        CK(up(d_rec, pk->entry_rec + lo, n));
+        RecOut &o = h->rec_out;
+        auto carve = [&](auto *&dev_const, auto *&dev_mut) {
+            using T = std::remove_pointer_t<std::remove_reference_t<decltype(dev_mut)>>;
+            dev_mut = A.take<T>(n1); dev_const = dev_mut;
+        };
+        for (int c = 0; c < 2; c++) {
+            carve(d.tig_off[c], o.tig_off[c]); carve(d.has_del[c], o.has_del[c]); carve(d.cdr3_start[c], o.cdr3_start[c]);
+            carve(d.v_ref_id[c], o.v_ref_id[c]); carve(d.j_ref_id[c], o.j_ref_id[c]); carve(d.dref_id[c], o.dref_id[c]);
+            carve(d.vs_seq[c], o.vs_seq[c]); carve(d.js_seq[c], o.js_seq[c]); carve(d.vname_id[c], o.vname_id[c]);
+            carve(d.vuni_seq[c], o.vuni_seq[c]); carve(d.utr_seq[c], o.utr_seq[c]);
+        }
+        carve(d.c_ref_id_light, o.c_ref_id_light); carve(d.hcomp, o.hcomp);
+        carve(d.fr1, o.fr1); carve(d.cdr1, o.cdr1); carve(d.fr2, o.fr2); carve(d.cdr2, o.cdr2); carve(d.fr3, o.fr3);
+        h->d_rec = d_rec; h->recs_pending = true;
+    } else {
+        for (int c = 0; c < 2; c++) {
+            CK(up(d.tig_off[c], pk->tig_off[c] + lo, n));
+            CK(up(d.has_del[c], pk->has_del[c] + lo, n));
+            CK(up(d.cdr3_start[c], pk->cdr3_start[c] + lo, n));
+            CK(up(d.v_ref_id[c], pk->v_ref_id[c] + lo, n));
+            CK(up(d.j_ref_id[c], pk->j_ref_id[c] + lo, n));
+            CK(up(d.dref_id[c], pk->dref_id[c] + lo, n));
+            CK(up(d.vs_seq[c], pk->vs_seq[c] + lo, n));
+            CK(up(d.js_seq[c], pk->js_seq[c] + lo, n));
+            CK(up(d.vname_id[c], pk->vname_id[c] + lo, n));
+            CK(up(d.vuni_seq[c], pk->vuni_seq[c] + lo, n));
+            CK(up(d.utr_seq[c], pk->utr_seq[c] + lo, n));
+        }
+        CK(up(d.c_ref_id_light, pk->c_ref_id_light + lo, n));
+        CK(up(d.hcomp, pk->hcomp + lo, n));
+        CK(up(d.fr1, pk->fr1_start + lo, n)); CK(up(d.cdr1, pk->cdr1_start + lo, n)); CK(up(d.fr2, pk->fr2_start + lo, n));
+        CK(up(d.cdr2, pk->cdr2_start + lo, n)); CK(up(d.fr3, pk->fr3_start + lo, n));
     }
-    CK(up(d.c_ref_id_light, pk->c_ref_id_light + lo, n));
-    CK(up(d.hcomp, pk->hcomp + lo, n));
-    CK(up(d.fr1, pk->fr1_start + lo, n)); CK(up(d.cdr1, pk->cdr1_start + lo, n)); CK(up(d.fr2, pk->fr2_start + lo, n));
-    CK(up(d.cdr2, pk->cdr2_start + lo, n)); CK(up(d.fr3, pk->fr3_start + lo, n));
     CK(up(d.ncells, pk->ncells, pk->n_exact));
     CK(up(d.donor_lo, pk->donor_lo, pk->n_exact)); CK(up(d.donor_hi, pk->donor_hi, pk->n_exact));
     CK(up(d.refseq_off, pk->refseq_off, pk->n_refseq)); CK(up(d.refseq_len, pk->refseq_len, pk->n_refseq));
@@ -423,7 +469,24 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     }
     CK(cudaEventRecord(h->ev_small, h->st_copy));       // everything but the V..J bytes: keys / sort / groups / meta / c3 can start
     h->tigs_in_place = in_place;
-    if (in_place) {
+    if (two_bit) {
+        // ASCII chains (deletion marker / non-ACGT): the small arena goes up whole, with the late set
+        uint8_t *dst = A.take<uint8_t>(thi - tlo + 64);
+        if (thi > tlo) { CK(cudaMemcpyAsync(dst, pk->tig_arena + tlo, thi - tlo, cudaMemcpyHostToDevice, h->st_copy)); bytes += thi - tlo; }
+        d.tig_arena = dst; d.tig_src = dst; d.tig_copy = nullptr;
+        CK(cudaEventRecord(h->ev_small, h->st_copy));
+        if (in_place) {
+            d.tig2_src = (const uint64_t *)in_place_ptr;                 // k_pack_t2 pulls the needed entries' words over PCIe
+            h->n_chunks = 0;
+        } else {
+            uint64_t *w = A.take<uint64_t>(whi - wlo + 8);
+            if (whi > wlo) { CK(cudaMemcpyAsync(w, pk->tig2_arena + wlo, 8 * (whi - wlo), cudaMemcpyHostToDevice, h->st_copy)); bytes += 8 * (whi - wlo); }
+            d.tig2_src = w;
+            h->n_chunks = 1; h->chunk_end[0] = ~0ull;
+            CK(cudaEventRecord(h->ev_chunk[7], h->st_copy));
+        }
+        h->copy_pending = true;
+    } else if (in_place) {
         // device mirror with the same 16-byte phase as the host arena (k_pack_t2 copies chunk for chunk)
         uint8_t *mir = A.take<uint8_t>(thi - tlo + 64 + 256);
         mir += ((uintptr_t)in_place_ptr & 15);
@@ -450,8 +513,9 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     }
     // the offsets index the original arenas: rebase the device pointers instead of the offsets
     d.tig_arena -= tlo; d.tig_src -= tlo; if (d.tig_copy) d.tig_copy -= tlo;
+    if (d.tig2_src) d.tig2_src -= wlo;
     d.cdr3_arena -= clo;
-    h->n = n; h->k_base = lo; h->tig_bytes = thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
+    h->n = n; h->k_base = lo; h->tig_bytes = two_bit ? 32 * (whi - wlo) + (thi - tlo) : thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
     return 0;
 }
 
@@ -694,6 +758,11 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         CK(cudaEventRecord(h->ev[3], st));
         mark(h, "k_sweep");
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)
+        if (h->recs_pending) {
+            k_unpack_recs<<<nb256, 256, 0, st>>>(h->d_rec, n, h->rec_out);
+            h->launches += 1;
+            h->recs_pending = false;               // the parallel arrays stay valid for later resident runs
+        }
         k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, needed, pr.ref_v_trim, pr.ref_j_trim);
         k_pack_ref<<<std::max(1u, h->din.n_refseq), 32, 0, st>>>(h->din);
         h->launches += 1;
@@ -1296,4 +1365,145 @@ extern "C" int ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pk, co
     memcpy(class_of, hl, 4 * (size_t)n);
     if (n_classes) *n_classes = (uint32_t)ncls;
     return EJOIN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ejoin_pack_compact: ASCII / parallel-array pack -> compact pack (2-bit V..J bases in the DnaString
+// layout, one 64-byte record per entry), in pinned host memory.  Host code only; a caller that holds
+// CloneInfo.tigsp writes this form directly.
+// ---------------------------------------------------------------------------------------------
+#include <thread>
+namespace {
+struct CompactOwner {
+    ejoin_pack_t pk;                       // first member: the pointer handed to the caller
+    uint64_t *tig2 = nullptr; ejoin_entry_rec_t *rec = nullptr; uint8_t *ascii = nullptr;
+    bool pinned = true;
+};
+// pinned when a CUDA device is there; plain aligned memory otherwise (the conversion itself is host code and is tested
+// on machines without a GPU; the join entry points still refuse to run there)
+void *compact_alloc(CompactOwner *o, size_t bytes) {
+    void *p = nullptr;
+    if (o->pinned) {
+        if (cudaMallocHost(&p, bytes) == cudaSuccess) return p;
+        cudaGetLastError();
+        if (o->tig2 || o->rec || o->ascii) return nullptr;       // do not mix the two kinds
+        o->pinned = false;
+    }
+    if (posix_memalign(&p, 4096, (bytes + 4095) & ~(size_t)4095) != 0) return nullptr;
+    return p;
+}
+struct Code256 { uint8_t t[256]; Code256() { memset(t, 0xFF, 256); t['A'] = 0; t['C'] = 1; t['G'] = 2; t['T'] = 3; } };
+const Code256 g_code;
+
+template <typename F> void parallel_ranges(uint32_t n, int threads, F f) {
+    threads = std::max(1, std::min(threads, (int)((n + 4095) / 4096)));
+    if (threads == 1) { f(0u, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        const uint32_t a = (uint32_t)((uint64_t)n * t / threads), b = (uint32_t)((uint64_t)n * (t + 1) / threads);
+        th.emplace_back([=] { f(a, b); });
+    }
+    for (auto &x : th) x.join();
+}
+}  // namespace
+
+extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pack_t **out) {
+    if (!in || !out) return EJOIN_E_ARG;
+    *out = nullptr;
+    if (in->abi_version != EJOIN_ABI_VERSION || (in->flags & (EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS))) return EJOIN_E_ARG;
+    if (pack_null_field(in)) return EJOIN_E_ARG;
+    const uint32_t n = in->n_info;
+    if (threads < 1) threads = 1;
+    // pass 1: which chains stay ASCII (deletion marker or a byte outside ACGT), sizes
+    std::vector<uint8_t> asc[2];
+    for (int c = 0; c < 2; c++) asc[c].assign(n, 0);
+    bool id_overflow = false;
+    parallel_ranges(n, threads, [&](uint32_t a, uint32_t b) {
+        bool ov = false;
+        for (uint32_t k = a; k < b; k++)
+            for (int c = 0; c < 2; c++) {
+                bool x = in->has_del[c][k] != 0;
+                if (!x) {
+                    const uint8_t *p = in->tig_arena + in->tig_off[c][k];
+                    uint8_t bad = 0;
+                    for (uint32_t i = 0, L = in->len[c][k]; i < L; i++) bad |= g_code.t[p[i]];
+                    x = (bad & 0x80) != 0;
+                }
+                asc[c][k] = x;
+                auto big = [](uint32_t v) { return v != EJOIN_NONE && v >= 0xFFFFu; };
+                ov |= big(in->v_ref_id[c][k]) || big(in->j_ref_id[c][k]) || big(in->dref_id[c][k]) || big(in->vs_seq[c][k]) || big(in->js_seq[c][k]) ||
+                      big(in->vname_id[c][k]) || big(in->vuni_seq[c][k]) || big(in->utr_seq[c][k]) || (c == 0 && big(in->c_ref_id_light[k]));
+            }
+        if (ov) id_overflow = true;
+    });
+    if (id_overflow) return EJOIN_E_UNSUPPORTED;
+    std::vector<uint64_t> woff[2], aoff[2];
+    for (int c = 0; c < 2; c++) { woff[c].assign(n, 0); aoff[c].assign(n, 0); }
+    uint64_t words = 0, abytes = 0;
+    for (uint32_t k = 0; k < n; k++)
+        for (int c = 0; c < 2; c++) {
+            if (asc[c][k]) { aoff[c][k] = abytes; abytes += in->len[c][k]; }
+            else { woff[c][k] = words; words += (in->len[c][k] + 31) / 32; }
+        }
+    if (words >= 0xFFFFFFFFull || abytes >= 0xFFFFFFFFull) return EJOIN_E_UNSUPPORTED;
+    CompactOwner *o = new CompactOwner();
+    o->pk = *in;
+    o->tig2 = (uint64_t *)compact_alloc(o, 8 * (words + 16));
+    if (o->tig2) o->rec = (ejoin_entry_rec_t *)compact_alloc(o, sizeof(ejoin_entry_rec_t) * ((size_t)n + 1));
+    if (o->rec) o->ascii = (uint8_t *)compact_alloc(o, abytes + 128);
+    if (!o->tig2 || !o->rec || !o->ascii) { ejoin_pack_compact_free(&o->pk); return EJOIN_E_NOMEM; }
+    memset(o->tig2 + words, 0, 8 * 16);
+    memset(o->ascii + abytes, 0, 128);
+    parallel_ranges(n, threads, [&](uint32_t a, uint32_t b) {
+        for (uint32_t k = a; k < b; k++) {
+            ejoin_entry_rec_t r;
+            memset(&r, 0, sizeof(r));
+            auto n16 = [](uint32_t v) { return v == EJOIN_NONE ? (uint16_t)0xFFFF : (uint16_t)v; };
+            for (int c = 0; c < 2; c++) {
+                const uint8_t *p = in->tig_arena + in->tig_off[c][k];
+                const uint32_t L = in->len[c][k];
+                if (asc[c][k]) {
+                    memcpy(o->ascii + aoff[c][k], p, L);
+                    r.tig_off[c] = (uint32_t)aoff[c][k]; r.has_del[c] = 1;
+                } else {
+                    uint64_t *w = o->tig2 + woff[c][k];
+                    for (uint32_t i0 = 0; i0 < L; i0 += 32) {
+                        uint64_t x = 0;
+                        const uint32_t m = std::min(32u, L - i0);
+                        for (uint32_t i = 0; i < m; i++) x |= (uint64_t)g_code.t[p[i0 + i]] << (62 - 2 * i);
+                        w[i0 >> 5] = x;
+                    }
+                    r.tig_off[c] = (uint32_t)woff[c][k]; r.has_del[c] = 0;
+                }
+                r.cdr3_start[c] = in->cdr3_start[c][k];
+                r.v_ref_id[c] = n16(in->v_ref_id[c][k]); r.j_ref_id[c] = n16(in->j_ref_id[c][k]); r.dref_id[c] = n16(in->dref_id[c][k]);
+                r.vs_seq[c] = n16(in->vs_seq[c][k]); r.js_seq[c] = n16(in->js_seq[c][k]); r.vname_id[c] = n16(in->vname_id[c][k]);
+                r.vuni_seq[c] = n16(in->vuni_seq[c][k]); r.utr_seq[c] = n16(in->utr_seq[c][k]);
+            }
+            r.c_ref_id_light = n16(in->c_ref_id_light[k]); r.hcomp = in->hcomp[k];
+            r.fr1_start = in->fr1_start[k]; r.cdr1_start = in->cdr1_start[k]; r.fr2_start = in->fr2_start[k];
+            r.cdr2_start = in->cdr2_start[k]; r.fr3_start = in->fr3_start[k];
+            o->rec[k] = r;
+        }
+    });
+    ejoin_pack_t &pk = o->pk;
+    pk.flags = (in->flags & ~EJOIN_F_TIGS_IN_PLACE) | EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS | (o->pinned ? EJOIN_F_TIGS_IN_PLACE : 0u);
+    pk.tig2_arena = o->tig2; pk.tig2_arena_words = words; pk.entry_rec = o->rec;
+    pk.tig_arena = o->ascii; pk.tig_arena_bytes = abytes;
+    for (int c = 0; c < 2; c++) {
+        pk.tig_off[c] = nullptr; pk.has_del[c] = nullptr; pk.cdr3_start[c] = nullptr; pk.v_ref_id[c] = nullptr; pk.j_ref_id[c] = nullptr;
+        pk.dref_id[c] = nullptr; pk.vs_seq[c] = nullptr; pk.js_seq[c] = nullptr; pk.vname_id[c] = nullptr; pk.vuni_seq[c] = nullptr; pk.utr_seq[c] = nullptr;
+    }
+    pk.c_ref_id_light = nullptr; pk.hcomp = nullptr;
+    pk.fr1_start = pk.cdr1_start = pk.fr2_start = pk.cdr2_start = pk.fr3_start = nullptr;
+    *out = &o->pk;
+    return EJOIN_OK;
+}
+
+extern "C" void ejoin_pack_compact_free(ejoin_pack_t *p) {
+    if (!p) return;
+    CompactOwner *o = reinterpret_cast<CompactOwner *>(p);
+    for (void *q : { (void *)o->tig2, (void *)o->rec, (void *)o->ascii })
+        if (q) { if (o->pinned) cudaFreeHost(q); else free(q); }
+    delete o;
 }

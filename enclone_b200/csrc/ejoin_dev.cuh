@@ -111,6 +111,10 @@ struct DevIn {
     const uint8_t *tig_arena;       // V..J bytes as the scoring kernels read them (device memory)
     const uint8_t *tig_src;         // where k_pack_t2 reads them: == tig_arena, or the caller's pinned arena (zero-copy)
     uint8_t *tig_copy;              // zero-copy only: k_pack_t2 mirrors the needed entries' bytes here (== tig_arena)
+    // EJOIN_F_TIGS_2BIT: chains without a deletion marker come 2 bits per base (CloneInfo.tigsp layout); tig_off of such a
+    // chain is a word offset into tig2_src (device copy, or the caller's pinned arena read in place); tig_arena / tig_off
+    // keep their ASCII meaning for the chains with has_del != 0.  nullptr = every chain is ASCII.
+    const uint64_t *tig2_src;
     const uint8_t *has_del[2];
     const uint16_t *cdr3_len[2];
     const uint64_t *cdr3_off[2];

@@ -438,6 +438,63 @@ __global__ void __launch_bounds__(32) k_pack_ref(DevIn in) {
 // its entry's bytes into shared memory with non-overlapping aligned 16-byte loads — in zero-copy mode
 // in.tig_arena is the caller's pinned host buffer and these loads are the only PCIe traffic for the
 // V..J bytes, issued for needed entries only — and then every lane reduces its 32-base word from there.
+// 32 bases of a DnaString word (base i at bits 63-2i, 62-2i; A,C,G,T = 0..3) -> the plane words of this library:
+// bit i of H / L = high / low bit of the code (byte >> 1) & 3 that the ASCII path uses (A,C,G,T -> 0,1,3,2 = g ^ (g >> 1)).
+__device__ __forceinline__ uint32_t even_bits16(uint32_t v) {      // bits 0,2,4,.. of v -> bits 0..15
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+    v = (v | (v >> 4)) & 0x00FF00FFu;
+    return (v | (v >> 8)) & 0xFFFFu;
+}
+__device__ __forceinline__ void planes_of_2bit(unsigned long long x, uint32_t &H, uint32_t &L) {
+    // after the bit reversal base i sits at bits 2i (code bit 1) and 2i+1 (code bit 0)
+    const unsigned long long r = __brevll(x);
+    const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+    const uint32_t b1 = even_bits16(lo) | (even_bits16(hi) << 16), b0 = even_bits16(lo >> 1) | (even_bits16(hi >> 1) << 16);
+    H = b1; L = b1 ^ b0;
+}
+// 16 consecutive bases of a chain as ASCII bytes, rebuilt from its H / L plane words (positions p0..p0+15, p0 % 16 == 0)
+__device__ __forceinline__ void bytes_of_planes16(uint32_t H, uint32_t L, int half, uint32_t (&out)[4]) {
+    const uint32_t h = (H >> (16 * half)) & 0xFFFFu, l = (L >> (16 * half)) & 0xFFFFu;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t hn = (h >> (4 * i)) & 0xFu, ln = (l >> (4 * i)) & 0xFu;
+        // selector nibble j = 2 * hbit_j + lbit_j
+        const uint32_t sh = (hn & 1u) | ((hn & 2u) << 3) | ((hn & 4u) << 6) | ((hn & 8u) << 9);
+        const uint32_t sl = (ln & 1u) | ((ln & 2u) << 3) | ((ln & 4u) << 6) | ((ln & 8u) << 9);
+        out[i] = __byte_perm(0x47544341u /* codes 0,1,2,3 -> 'A','C','T','G' */, 0u, (sh << 1) | sl);
+    }
+}
+
+// EJOIN_F_ENTRY_RECS: one 64-byte record per entry -> the parallel arrays the kernels read (device to device, ~40 us at
+// 1.27 M entries); 0xFFFF widens to EJOIN_NONE.
+struct RecOut {
+    uint64_t *tig_off[2]; uint8_t *has_del[2]; uint16_t *cdr3_start[2];
+    uint32_t *v_ref_id[2], *j_ref_id[2], *dref_id[2], *vs_seq[2], *js_seq[2], *vname_id[2], *vuni_seq[2], *utr_seq[2];
+    uint32_t *c_ref_id_light; uint16_t *hcomp, *fr1, *cdr1, *fr2, *cdr2, *fr3;
+};
+__device__ __forceinline__ uint32_t widen16(uint16_t v) { return v == 0xFFFFu ? EJOIN_NONE : (uint32_t)v; }
+__global__ void __launch_bounds__(256) k_unpack_recs(const ejoin_entry_rec_t *__restrict__ rec, uint32_t n, RecOut o) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    union { ejoin_entry_rec_t r; uint4 q[4]; } u;
+    const uint4 *src = (const uint4 *)(rec + k);
+#pragma unroll
+    for (int i = 0; i < 4; i++) u.q[i] = __ldg(src + i);
+    const ejoin_entry_rec_t &r = u.r;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        o.tig_off[c][k] = (unsigned long long)r.tig_off[c];
+        o.has_del[c][k] = r.has_del[c]; o.cdr3_start[c][k] = r.cdr3_start[c];
+        o.v_ref_id[c][k] = widen16(r.v_ref_id[c]); o.j_ref_id[c][k] = widen16(r.j_ref_id[c]); o.dref_id[c][k] = widen16(r.dref_id[c]);
+        o.vs_seq[c][k] = widen16(r.vs_seq[c]); o.js_seq[c][k] = widen16(r.js_seq[c]); o.vname_id[c][k] = widen16(r.vname_id[c]);
+        o.vuni_seq[c][k] = widen16(r.vuni_seq[c]); o.utr_seq[c][k] = widen16(r.utr_seq[c]);
+    }
+    o.c_ref_id_light[k] = widen16(r.c_ref_id_light); o.hcomp[k] = r.hcomp;
+    o.fr1[k] = r.fr1_start; o.cdr1[k] = r.cdr1_start; o.fr2[k] = r.fr2_start; o.cdr2[k] = r.cdr2_start; o.fr3[k] = r.fr3_start;
+}
+
 #define PACK_STAGE 544          // per chain: 512 bytes + alignment slack + the 48-byte window overrun
 __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
                                                  const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi) {
@@ -452,15 +509,18 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
     const EntryMeta &m = meta[s];
     const uint32_t k = m.k;
     const int n0 = m.len[0], n1 = m.len[1];
-    {
+    // which chains come as ASCII bytes (all of them unless the pack is EJOIN_F_TIGS_2BIT; then only those with has_del)
+    const bool asc[2] = { in.tig2_src == nullptr || in.has_del[0][k] != 0, in.tig2_src == nullptr || in.has_del[1][k] != 0 };
+    if (in.tig2_src == nullptr) {
         const unsigned long long e0 = in.tig_off[0][k] + (unsigned long long)n0, e1 = in.tig_off[1][k] + (unsigned long long)n1;
         const unsigned long long last = e0 > e1 ? e0 : e1;
         if (!(last > wm_lo && last <= wm_hi)) return;
     }
-    // ---- stage both chains (chains longer than 512 bases are read in place)
-    uint32_t soff[2];
-    bool staged[2];
+    // ---- stage the ASCII chains (chains longer than 512 bases are read in place)
+    uint32_t soff[2] = { 0, 0 };
+    bool staged[2] = { false, false };
     for (int c = 0; c < 2; c++) {
+        if (!asc[c]) continue;
         const int n = c ? n1 : n0;
         const uint8_t *t = in.tig_src + in.tig_off[c][k];
         const uintptr_t a = (uintptr_t)t;
@@ -481,7 +541,12 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
     __syncwarp(hmask);
     const int nw0 = 4 * ((n0 + 127) / 128), nw = nw0 + 4 * ((n1 + 127) / 128);
     uint32_t *rows = (uint32_t *)(t2 + m.t2off);
-    if (lane == 0) atomicAdd(&ctr->pack_bytes[blockIdx.x & 31], (unsigned long long)(n0 + n1) + 12ull * nw);     // ASCII in, three plane words out per 32 bases
+    if (lane == 0) {
+        // bytes in (ASCII: one per base; 2-bit: one u64 word per 32 bases), three plane words out per 32 bases
+        const unsigned long long bin0 = asc[0] ? (unsigned long long)n0 : 8ull * ((n0 + 31) / 32), bin1 = asc[1] ? (unsigned long long)n1 : 8ull * ((n1 + 31) / 32);
+        atomicAdd(&ctr->pack_bytes[blockIdx.x & 31], bin0 + bin1 + 12ull * nw);
+        if (in.tig2_src) atomicAdd(&ctr->inplace_bytes[blockIdx.x & 31], (asc[0] ? 0ull : bin0) + (asc[1] ? 0ull : bin1));
+    }
     int mcount0 = 0, mcount1 = 0;
     uint32_t weird0 = 0, weird1 = 0;
     for (int w = (int)lane; w < nw; w += 16) {
@@ -491,17 +556,23 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
         const int p0 = wl * 32;
         uint32_t H = 0, L = 0, M = 0;
         if (p0 < n) {
-            uint32_t x[8];
-            if (staged[c]) load32s(stage[wib][c], soff[c] + (uint32_t)p0, x);
-            else load32u(in.tig_src + in.tig_off[c][k] + p0, x);
-            const int nb = n - p0;                            // valid bytes in this word (>= 1)
+            const int nb = n - p0;                            // valid bases in this word (>= 1)
+            if (asc[c]) {
+                uint32_t x[8];
+                if (staged[c]) load32s(stage[wib][c], soff[c] + (uint32_t)p0, x);
+                else load32u(in.tig_src + in.tig_off[c][k] + p0, x);
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] &= low_bytes(nb - 4 * i);
-            uint32_t wd = 0;
+                for (int i = 0; i < 8; i++) x[i] &= low_bytes(nb - 4 * i);
+                uint32_t wd = 0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) wd |= not_acgt(x[i]) & low_bytes(nb - 4 * i);
-            if (c) weird1 |= wd; else weird0 |= wd;
-            planes32(x, H, L);
+                for (int i = 0; i < 8; i++) wd |= not_acgt(x[i]) & low_bytes(nb - 4 * i);
+                if (c) weird1 |= wd; else weird0 |= wd;
+                planes32(x, H, L);
+            } else {
+                // one DnaString word = these 32 bases; the half warp's loads are consecutive 8-byte words (in zero-copy
+                // mode this is the PCIe traffic of the V..J bases: 1/4 of the ASCII bytes, needed entries only)
+                planes_of_2bit(__ldg(in.tig2_src + in.tig_off[c][k] + wl), H, L);
+            }
             const uint32_t valid = low_bits(nb);
             H &= valid; L &= valid;
             const int vend = m.vend[c], jstart = m.jstart[c];
@@ -1024,7 +1095,7 @@ __device__ __forceinline__ uint32_t range16(int p0, int lo, int hi) {
 // popcount of mask products.  The first version walked the sequences one byte per lane and pass (diffs, V window, J
 // window, per germline set): ~60 dependent load rounds per pair, against 3 here.
 template <bool WARP>
-__device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
+__device__ void bytewise_counts_t(const DevIn &in, const uint4 *__restrict__ t2rows, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
     static_assert(WARP, "warp-cooperative only");
     const int lane = (int)(threadIdx.x & 31);
     const uint32_t k1 = m1.k, k2 = m2.k;
@@ -1040,7 +1111,11 @@ __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const En
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         const int n = m1.len[c];
-        const uint8_t *t1 = in.tig_arena + in.tig_off[c][k1], *t2 = in.tig_arena + in.tig_off[c][k2];
+        // the bytes of a 2-bit chain are rebuilt from its plane words in the t2 rows
+        const bool asc1 = in.tig2_src == nullptr || in.has_del[c][k1] != 0, asc2 = in.tig2_src == nullptr || in.has_del[c][k2] != 0;
+        const uint8_t *t1 = in.tig_arena + (asc1 ? in.tig_off[c][k1] : 0ull), *t2 = in.tig_arena + (asc2 ? in.tig_off[c][k2] : 0ull);
+        const uint32_t blk0 = c ? ((uint32_t)m1.len[0] + 127) / 128 : 0u;
+        const uint32_t *w1 = (const uint32_t *)(t2rows + m1.t2off) + 12 * blk0, *w2 = (const uint32_t *)(t2rows + m2.t2off) + 12 * blk0;
         const int a1 = m1.cs[c], a2 = m2.cs[c], cl = m1.cl[c];
         {   // CDR3 strings (cl <= 255: one pass)
             const uint8_t *q1 = in.cdr3_arena + in.cdr3_off[c][k1], *q2 = in.cdr3_arena + in.cdr3_off[c][k2];
@@ -1053,7 +1128,11 @@ __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const En
         }
         for (int p0 = 16 * lane; p0 < n; p0 += 512) {
             uint32_t x[4], y[4];
-            load16u(t1 + p0, x); load16u(t2 + p0, y);
+            {
+                const int o = (p0 >> 7) * 12 + ((p0 >> 5) & 3), half = (p0 >> 4) & 1;
+                if (asc1) load16u(t1 + p0, x); else bytes_of_planes16(__ldg(w1 + o), __ldg(w1 + o + 4), half, x);
+                if (asc2) load16u(t2 + p0, y); else bytes_of_planes16(__ldg(w2 + o), __ldg(w2 + o + 4), half, y);
+            }
             const uint32_t valid = range16(p0, 0, n);
             const uint32_t D = neq16(x, y) & valid, S = ~D & valid;          // positions where the entries differ / agree
             const uint32_t out = valid & ~(range16(p0, a1, a1 + cl) | range16(p0, a2, a2 + cl));
@@ -1122,8 +1201,8 @@ __device__ void bytewise_counts_t(const DevIn &in, const DevParams &pr, const En
     if (reg) { pc.dfw = warp_sum(dfw); pc.dc12 = warp_sum(d12); pc.lfw = c1 - f1; pc.l12 = (f2 - c1) + (f3 - c2); }
 }
 
-__device__ __forceinline__ void bytewise_counts(const DevIn &in, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
-    bytewise_counts_t<true>(in, pr, m1, m2, pc);
+__device__ __forceinline__ void bytewise_counts(const DevIn &in, const uint4 *t2rows, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
+    bytewise_counts_t<true>(in, t2rows, pr, m1, m2, pc);
 }
 // K6  tier 2, bytewise: one warp per queued pair (already past the CDR3 and meta gates).
 __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *generic_q,
@@ -1138,7 +1217,7 @@ __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, D
         const uint2 c = generic_q[i];
         const EntryMeta m1 = tb.meta[c.x], m2 = tb.meta[c.y];      // already ordered k1 < k2
         PairCounts pc;
-        bytewise_counts(in, pr, m1, m2, pc);
+        bytewise_counts(in, tb.t2, pr, m1, m2, pc);
         if (lane == 0) atomicAdd(&ctr->n_generic, 1ull);
         bool ok = true;
         if (!pr.is_bcr || pr.max_diffs < 1000000) {
@@ -1256,7 +1335,7 @@ __global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevPara
         const uint2 kk2 = pairs[i];
         const EntryMeta m1 = tb.meta[k_to_s[kk2.x - k_base]], m2 = tb.meta[k_to_s[kk2.y - k_base]];
         PairCounts pc;
-        bytewise_counts(in, pr, m1, m2, pc);
+        bytewise_counts(in, tb.t2, pr, m1, m2, pc);
         int kk = 0, d = 0, err = 0;
         double p1 = 0, mult = 0, score = 0;
         if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
@@ -1696,7 +1775,7 @@ __device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTab
                                                    int *cd_out, int *d_out) {
     const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
     PairCounts pc;
-    bytewise_counts_t<true>(in, pr, m1, m2, pc);
+    bytewise_counts_t<true>(in, tb.t2, pr, m1, m2, pc);
     if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->n_generic, 1ull);
     *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
     if (!pr.is_bcr || pr.max_diffs < 1000000) {

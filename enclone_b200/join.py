@@ -177,6 +177,39 @@ def join_exacts(pack, params=None, device=0):
         j.close()
 
 
+class CompactPack:
+    """The compact form of a pack (ejoin_pack_compact): V..J bases 2 bits per base in the layout of CloneInfo.tigsp,
+    one 64-byte record per entry, pinned arenas read in place.  `.struct` is the C ejoin_pack_t; the source pack
+    must stay alive (unchanged arrays are shared)."""
+
+    def __init__(self, src, threads=None):
+        import os
+        self.L = _lib.load()
+        self._src = src                                # keeps the shared arrays alive
+        st = src.struct if hasattr(src, "struct") else src
+        pp = C.POINTER(_lib.EjoinPack)()
+        rc = self.L.ejoin_pack_compact(C.byref(st), threads or (os.cpu_count() or 1), C.byref(pp))
+        if rc != 0:
+            raise _lib.EjoinError(rc, "ejoin_pack_compact")
+        self._pp = pp
+        self.struct = pp.contents
+
+    @property
+    def n_info(self):
+        return int(self.struct.n_info)
+
+    def close(self):
+        if getattr(self, "_pp", None):
+            self.L.ejoin_pack_compact_free(self._pp)
+            self._pp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def plan_shards(pack_struct, world):
     L = _lib.load()
     nb = C.c_uint32()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define EJOIN_ABI_VERSION 1
+#define EJOIN_ABI_VERSION 2
 #define EJOIN_NONE 0xFFFFFFFFu   /* Option::None for u32 ids                      */
 #define EJOIN_NONE16 0xFFFFu     /* Option::None for u16 region bounds            */
 /* ejoin_pack_t.flags: tig_arena is pinned host memory the device can read (ejoin_host_alloc /
@@ -35,6 +35,20 @@ extern "C" {
  * reads the V..J bytes IN PLACE over PCIe, and only for the entries that have a CDR3-compatible
  * partner (about half of a repertoire), instead of uploading the whole arena. */
 #define EJOIN_F_TIGS_IN_PLACE 1u
+/* The V..J bases of every chain WITHOUT a deletion marker are given 2 bits per base in tig2_arena, in the layout the
+ * reference already holds them in (CloneInfo.tigsp: debruijn 0.3.4 DnaString, Cargo.lock:527-530 — 32 bases per u64,
+ * base i of a chain in word i >> 5 at bits 63-2(i&31) (high) and 62-2(i&31) (low), A,C,G,T = 0,1,2,3; every chain
+ * starts on a word boundary) — the same split join_one makes: ndiffs on tigsp when !has_del, bytes otherwise.
+ * tig_off[c][k] (or entry_rec[k].tig_off[c]) is then a WORD offset into tig2_arena for those chains; chains with
+ * has_del[c][k] != 0 (deletion marker '-', or any byte outside ACGT) stay ASCII: tig_off is a byte offset into
+ * tig_arena, which needs to hold only those chains.  With EJOIN_F_TIGS_IN_PLACE the in-place reads go to tig2_arena. */
+#define EJOIN_F_TIGS_2BIT 2u
+/* The per-entry fields that only the scoring reads are given as one 64-byte record per entry (entry_rec) instead of
+ * 22 parallel arrays (which may then be NULL): 4.5x fewer bytes per entry and one cache line per entry.
+ * Requires every id / germline index to be < 65535. */
+#define EJOIN_F_ENTRY_RECS 4u
+/* cdr3_off may be NULL: the CDR3 strings lie back to back in cdr3_arena in entry order (chain 0 then chain 1). */
+#define EJOIN_F_CDR3_DENSE 8u
 
 /* error codes */
 #define EJOIN_OK 0
@@ -53,6 +67,18 @@ extern "C" {
  * (CloneInfo.lens.len() == 1) has len[1][k] == 0 and is never joined
  * (enclone_help/src/help1.rs:270-276).
  * ------------------------------------------------------------------------- */
+/* One info entry's "late" fields (EJOIN_F_ENTRY_RECS): same meaning as the arrays of the same name below;
+ * 0xFFFF stands for None (EJOIN_NONE / EJOIN_NONE16). */
+typedef struct ejoin_entry_rec {
+    uint32_t tig_off[2];         /* word offset into tig2_arena (2-bit chain) or byte offset into tig_arena (ASCII chain) */
+    uint16_t cdr3_start[2];
+    uint16_t v_ref_id[2], j_ref_id[2], dref_id[2], vs_seq[2], js_seq[2], vname_id[2], vuni_seq[2], utr_seq[2];
+    uint16_t c_ref_id_light, hcomp;
+    uint16_t fr1_start, cdr1_start, fr2_start, cdr2_start, fr3_start;
+    uint8_t  has_del[2];
+    uint8_t  pad[4];
+} ejoin_entry_rec_t;             /* 64 bytes */
+
 typedef struct ejoin_pack {
     uint32_t abi_version;        /* EJOIN_ABI_VERSION                             */
     uint32_t n_info;             /* info.len()                                    */
@@ -98,6 +124,11 @@ typedef struct ejoin_pack {
     const uint32_t *refseq_len;  /* [n_refseq]                                    */
     const uint8_t  *refseq_arena;
     uint64_t        refseq_arena_bytes;
+
+    /* ---- compact forms (ABI 2; see EJOIN_F_TIGS_2BIT / EJOIN_F_ENTRY_RECS) ---- */
+    const uint64_t *tig2_arena;  /* 2-bit V..J bases (CloneInfo.tigsp), >= 8 readable words of slack behind the last one */
+    uint64_t        tig2_arena_words;
+    const ejoin_entry_rec_t *entry_rec; /* [n_info] */
 } ejoin_pack_t;
 
 /* Join parameters: EncloneControl.{join_alg_opt, heur, clono_filt_opt_def} as
@@ -237,6 +268,13 @@ int  ejoin_partition_gpu(ejoin_handle_t *h, const ejoin_pack_t *pack, const uint
 int  ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pack);
 int  ejoin_upload_shard(ejoin_handle_t *h, const ejoin_pack_t *pack, int rank, int world_size);   /* this rank's share, as ejoin_run_shard* would take it */
 int  ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats);
+
+/* Host-side conversion of an ASCII / parallel-array pack into the compact form (EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS |
+ * EJOIN_F_CDR3_DENSE | EJOIN_F_TIGS_IN_PLACE): what a caller that holds CloneInfo.tigsp would build directly.  The arenas
+ * of the new pack are pinned (ejoin_host_alloc); arrays that do not change are shared with `in`, which must outlive it.
+ * Fails with EJOIN_E_UNSUPPORTED when an id does not fit 16 bits.  Needs no handle. */
+int  ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pack_t **out);
+void ejoin_pack_compact_free(ejoin_pack_t *p);
 
 /* Pinned host memory for the caller's flat buffers (so H2D runs at link speed). */
 void *ejoin_host_alloc(size_t bytes);

@@ -1,4 +1,4 @@
-//! Raw bindings to `libenclone_join.so` (include/enclone_join.h, ABI version 1).
+//! Raw bindings to `libenclone_join.so` (include/enclone_join.h, ABI version 2).
 //! NOT COMPILED HERE: the build image has no Rust toolchain.  Field order and types mirror the C
 //! header one for one; `tests/test_cpu.py::test_library_exports_every_declared_symbol` keeps the
 //! header and the library's export list in step, and the same layouts are exercised through ctypes
@@ -6,10 +6,23 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const EJOIN_ABI_VERSION: u32 = 1;
+pub const EJOIN_ABI_VERSION: u32 = 2;
 pub const EJOIN_NONE: u32 = 0xFFFF_FFFF;
 pub const EJOIN_NONE16: u16 = 0xFFFF;
 pub const EJOIN_F_TIGS_IN_PLACE: u32 = 1;
+pub const EJOIN_F_TIGS_2BIT: u32 = 2;
+pub const EJOIN_F_ENTRY_RECS: u32 = 4;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct ejoin_entry_rec_t {
+    pub tig_off: [u32; 2], pub cdr3_start: [u16; 2],
+    pub v_ref_id: [u16; 2], pub j_ref_id: [u16; 2], pub dref_id: [u16; 2], pub vs_seq: [u16; 2], pub js_seq: [u16; 2],
+    pub vname_id: [u16; 2], pub vuni_seq: [u16; 2], pub utr_seq: [u16; 2],
+    pub c_ref_id_light: u16, pub hcomp: u16,
+    pub fr1_start: u16, pub cdr1_start: u16, pub fr2_start: u16, pub cdr2_start: u16, pub fr3_start: u16,
+    pub has_del: [u8; 2], pub pad: [u8; 4],
+}
 
 #[repr(C)]
 pub struct ejoin_pack_t {
@@ -24,6 +37,7 @@ pub struct ejoin_pack_t {
     pub fr1_start: *const u16, pub cdr1_start: *const u16, pub fr2_start: *const u16, pub cdr2_start: *const u16, pub fr3_start: *const u16,
     pub nchains: *const u32, pub ncells: *const u32, pub donor_lo: *const u32, pub donor_hi: *const u32,
     pub refseq_off: *const u64, pub refseq_len: *const u32, pub refseq_arena: *const u8, pub refseq_arena_bytes: u64,
+    pub tig2_arena: *const u64, pub tig2_arena_words: u64, pub entry_rec: *const ejoin_entry_rec_t,
 }
 
 #[repr(C)]
@@ -89,6 +103,8 @@ extern "C" {
     pub fn ejoin_host_free(p: *mut c_void);
     pub fn ejoin_host_register(p: *mut c_void, bytes: usize) -> c_int;
     pub fn ejoin_host_unregister(p: *mut c_void) -> c_int;
+    pub fn ejoin_pack_compact(input: *const ejoin_pack_t, threads: c_int, out: *mut *mut ejoin_pack_t) -> c_int;
+    pub fn ejoin_pack_compact_free(p: *mut ejoin_pack_t);
     pub fn ejoin_p1(k: u32, d: u32, n: u32) -> f64;
 }
 // The safe wrapper `join_exacts(..) -> EquivRel` with `Flat::pack` is sketched in INTEGRATION.md §1-§3;

@@ -132,3 +132,46 @@ def test_tier1_work_decomposition_arithmetic(tmp_path):
     subprocess.check_call(["nvcc", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(root, "tests", "seg_enum_test.cu")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+def test_pack_compact_round_trip():
+    """ejoin_pack_compact (host code): the 2-bit words decode back to the ASCII bases in the DnaString layout
+    (base i of a chain in word i >> 5, bits 63-2(i&31), 62-2(i&31); A,C,G,T = 0..3), chains with a deletion marker or
+    a non-ACGT byte stay ASCII, and every record field equals the parallel array it replaces."""
+    from enclone_b200.join import CompactPack
+    pack, _ = synth.generate(n_cells=3000, n_donors=2, seed=5, frac_indel=0.05)
+    a = pack.arrays
+    arena = a["tig_arena"]
+    rng = np.random.default_rng(1)
+    for k in rng.choice(pack.n_info, size=40, replace=False):          # a few non-ACGT bytes outside the CDR3s
+        c = int(rng.integers(0, 2))
+        cs, cl = int(a["cdr3_start"][c][k]), int(a["cdr3_len"][c][k])
+        pos = int(rng.integers(0, max(1, cs)))
+        arena[int(a["tig_off"][c][k]) + pos] = ord("N")
+    cp = CompactPack(pack, threads=3)
+    st = cp.struct
+    assert st.flags & 2 and st.flags & 4 and st.n_info == pack.n_info
+    words = np.ctypeslib.as_array(st.tig2_arena, shape=(int(st.tig2_arena_words),))
+    asc = np.ctypeslib.as_array(st.tig_arena, shape=(max(1, int(st.tig_arena_bytes)),))
+    n_ascii = 0
+    for k in range(0, pack.n_info, 7):
+        r = st.entry_rec[k]
+        for c in range(2):
+            ln = int(a["len"][c][k])
+            src = pack.tig(c, k)
+            plain = not a["has_del"][c][k] and all(ch in b"ACGT" for ch in src)
+            assert bool(r.has_del[c]) == (not plain)
+            if plain:
+                w = words[r.tig_off[c]: r.tig_off[c] + (ln + 31) // 32]
+                got = bytes(b"ACGT"[(int(w[i >> 5]) >> (62 - 2 * (i & 31))) & 3] for i in range(ln))
+            else:
+                n_ascii += 1
+                got = asc[r.tig_off[c]: r.tig_off[c] + ln].tobytes()
+            assert got == src
+            assert r.cdr3_start[c] == int(a["cdr3_start"][c][k])
+            for f in ("v_ref_id", "j_ref_id", "vs_seq", "js_seq", "vname_id", "vuni_seq", "dref_id", "utr_seq"):
+                v = int(a[f][c][k])
+                assert getattr(r, f)[c] == (0xFFFF if v == 0xFFFFFFFF else v), f
+        assert r.hcomp == int(a["hcomp"][k]) and r.fr3_start == int(a["fr3_start"][k])
+    assert n_ascii > 0
+    cp.close()

@@ -432,3 +432,99 @@ def test_null_pack_arrays_are_an_argument_error():
     with pytest.raises(EjoinError) as ei:
         join_exacts(JoinPack(a, is_bcr=True))
     assert ei.value.code == -1 and "exact_id" in str(ei.value)
+
+
+# ---- compact input (EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS): the form a caller holding CloneInfo.tigsp passes ----
+def _compact_vs_everything(pack, what, **over):
+    from enclone_b200.join import CompactPack
+    params = default_params(**over)
+    cp = CompactPack(pack)
+    j = Joiner(params)
+    g = j.run(cp.struct)                                   # 2-bit words read in place over PCIe, 64-byte records
+    a = j.run(pack.struct if hasattr(pack, "struct") else pack)      # the ASCII / parallel-array form on the same handle
+    j.close()
+    assert np.array_equal(g.edges, a.edges) and np.array_equal(g.class_of, a.class_of), f"{what}: compact != ascii"
+    oe, oc, _ = O.join_exacts(pack.struct, params, threads=8)
+    assert_same_join(g, oe, oc, max_score=over.get("max_score", 100000.0), what=what)
+    cp.close()
+    return g, a
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 0.3), ("C3", 0.03), ("C5", 0.05), ("C4", 0.03)])
+def test_compact_input_matches_ascii_and_oracle(name, scale):
+    pack, _ = synth.generate_config(name, scale)
+    g, a = _compact_vs_everything(pack, f"compact {name}")
+    assert g.stats["h2d_bytes"] < 0.6 * a.stats["h2d_bytes"]
+
+
+def test_compact_input_bytewise_paths():
+    """Pairs the bit planes cannot represent are scored from bytes rebuilt out of the plane words (2-bit chains) or read
+    from the small ASCII arena (chains with a deletion marker / non-ACGT byte): indels, N bases, overlapping windows,
+    different germlines under both MAX_DEGRADATION readings."""
+    pack, _ = synth.generate(n_cells=9000, n_donors=3, seed=91, frac_indel=0.06, frac_public=0.1)
+    a = pack.arrays
+    rng = np.random.default_rng(9)
+    arena = a["tig_arena"]
+    for k in rng.choice(pack.n_info, size=pack.n_info // 30, replace=False):
+        c = int(rng.integers(0, 2))
+        ln, cs, cl = int(a["len"][c][k]), int(a["cdr3_start"][c][k]), int(a["cdr3_len"][c][k])
+        pos = int(rng.integers(0, ln))
+        if not (cs <= pos < cs + cl):
+            arena[int(a["tig_off"][c][k]) + pos] = ord("N")
+    g, _ = _compact_vs_everything(pack, "compact generic", mix_donors=1)
+    assert g.stats["pairs_generic"] > 0
+    _compact_vs_everything(pack, "compact trims", ref_v_trim=2, ref_j_trim=2)
+    _compact_vs_everything(pack, "compact degradation 1", degradation_mode=1, max_degradation=1, mix_donors=1)
+    _compact_vs_everything(pack, "compact degradation 0", max_degradation=1, mix_donors=1)
+
+
+def test_compact_input_sharded_and_uploaded(monkeypatch):
+    from enclone_b200.join import CompactPack
+    pack, _ = synth.generate(n_cells=15000, n_donors=2, seed=33, frac_indel=0.03)
+    cp = CompactPack(pack)
+    single = join_exacts(pack)
+    world = 3
+    parts = []
+    for rank in range(world):
+        j = Joiner(default_params())
+        mode, fin, raw, st = j.run_shard_final(cp.struct, rank, world)
+        assert mode == 0
+        parts.append(fin.edges)
+        j.upload_shard(cp.struct, rank, world)               # resident form of the same shard
+        s = j.run_resident()
+        assert s["edges_after_prune"] == len(fin.edges)
+        j.close()
+    assert np.array_equal(np.concatenate(parts), single.edges)
+    # stride mode on a giant bucket
+    big, _ = synth.generate_config("C4", 0.02)
+    cb = CompactPack(big)
+    ref = join_exacts(big)
+    raws, js = [], []
+    for rank in range(2):
+        j = Joiner(default_params())
+        raw, st = j.run_shard(cb.struct, rank, 2)
+        raws.append(raw); js.append(j)
+    fin = js[0].finish(cb.struct, np.concatenate(raws))
+    assert np.array_equal(fin.edges, ref.edges) and np.array_equal(fin.class_of, ref.class_of)
+    for j in js:
+        j.close()
+    # no zero-copy: the 2-bit arena is uploaded
+    monkeypatch.setenv("EJOIN_NO_ZERO_COPY", "1")
+    g2 = join_exacts(cp)
+    assert np.array_equal(g2.edges, single.edges) and np.array_equal(g2.class_of, single.class_of)
+    cp.close(); cb.close()
+
+
+def test_compact_full_size_c3():
+    import os
+    from enclone_b200.join import CompactPack
+    sp, _ = synth.generate_config("C3", 1.0, copy=False)
+    cp = CompactPack(sp)
+    params = default_params()
+    j = Joiner(params)
+    g = j.run(cp.struct)
+    j.close()
+    oe, oc, _ = O.join_exacts(sp.struct, params, threads=os.cpu_count() or 1)
+    assert_same_join(g, oe, oc, what="compact C3")
+    assert g.stats["h2d_bytes"] <= 350e6
+    cp.close()
