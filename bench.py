@@ -5,8 +5,11 @@ One "step" = one pass of the join stage over the workload.
   value : device-resident step (inputs already in HBM): keys -> sort -> groups -> pack ->
           tier 1 -> tier 2 -> prune -> sort of kept edges, wall clock around K steps.
   e2e   : the same workload through the C-ABI call ejoin_run() with HOST buffers: H2D of
-          the flat JoinPack, the device pipeline, D2H of the edges, ordered replay, payload
-          and partition — the call a user of the library makes.
+          the flat JoinPack (compact form: V..J bases 2 bits per base as the reference holds
+          them in CloneInfo.tigsp, one 64-byte record per entry), the device pipeline (forest,
+          two-cell rule, payload, union-find all on the device), D2H of edges and labels —
+          the call a user of the library makes.  e2e_variants adds the ASCII / parallel-array
+          form of the same input, e2e_cold a fresh process (context, tables, first call).
   pairs : candidate pairs = sum over lens buckets of n_b (n_b - 1) / 2.
 Workload: BASELINE.json configs[2] (the ~1.6M-cell pooled BCR run the metric's target
 sentence names), which fits one GPU; N > 1 shards its buckets over the ranks (strong scaling).
@@ -193,6 +196,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     sp, gen_s, pin = make_workload(args.workload, args.scale, pinned=True)
+    from enclone_b200.join import CompactPack
+    t0 = time.perf_counter()
+    cp = CompactPack(sp)                       # what a caller holding CloneInfo.tigsp passes (ejoin_pack_compact, host threads)
+    compact_s = time.perf_counter() - t0
     j = Joiner(params, device=local_rank)
 
     def barrier():
@@ -201,13 +208,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- e2e: host buffers -> result, through the C ABI ----------------
-    def e2e_step():
+    def e2e_step(pack_struct=None):
+        pack_struct = pack_struct if pack_struct is not None else cp.struct
         if world == 1:
-            return j.run(sp.struct, copy=False)     # views into the library's pinned result buffer
+            return j.run(pack_struct, copy=False)     # views into the library's pinned result buffer
         from enclone_b200.dist import sharded_join
-        pairs, cls, st, fin = sharded_join(j, sp.struct, rank, world, device=dev)   # includes the NCCL all-gather of edges
+        pairs, cls, st, fin = sharded_join(j, pack_struct, rank, world, device=dev)   # includes the NCCL gather of edges
         fin.stats.update(st)
         fin.edges = pairs
+        fin.class_of = cls
         return fin
 
     for _ in range(W):
@@ -221,11 +230,39 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_stats = res.stats
+    n_joins = len(res.edges)
+    # parity of the sharded result: rank 0 repeats the join on its one GPU and compares raw_joins and the partition
+    parity_ok = None
+    if world > 1:
+        ok = 1
+        if rank == 0:
+            pairs_n = np.array(res.edges, copy=True)
+            cls_n = np.array(res.class_of, copy=True)
+            j1 = Joiner(params, device=local_rank)
+            one = j1.run(cp.struct)
+            ok = int(np.array_equal(np.stack([one.edges["k1"], one.edges["k2"]], axis=1), pairs_n.reshape(-1, 2)) and
+                     np.array_equal(one.class_of, cls_n))
+            j1.close()
+        okt = torch.tensor([ok], device=dev)
+        dist.broadcast(okt, 0)
+        parity_ok = bool(int(okt[0]))
+    # the same input in its ASCII / parallel-array form (ABI 1 layout), for comparison
+    e2e_ascii_s = None
+    if world == 1:
+        for _ in range(2):
+            e2e_step(sp.struct)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            ra = e2e_step(sp.struct)
+        barrier()
+        e2e_ascii_s = time.perf_counter() - t0
+        ascii_h2d = int(ra.stats["h2d_bytes"])
     # ---------------- value: inputs resident in HBM ----------------
     if world == 1:
-        j.upload(sp.struct)
+        j.upload(cp.struct)
     else:
-        j.upload_shard(sp.struct, rank, world)        # this rank's bucket range, resident in HBM
+        j.upload_shard(cp.struct, rank, world)        # this rank's bucket range, resident in HBM
     for _ in range(W):
         st = j.run_resident()
     barrier()
@@ -298,12 +335,14 @@ def main():
     roofline["popcount_pipe"] = {"kernel": "k_sweep", "achieved": popc / (sweep_ms * 1e-3) if sweep_ms > 0 else 0.0, "peak": xu_peak,
                                  "unit": "POPC/s", "frac": (popc / (sweep_ms * 1e-3) / xu_peak) if sweep_ms > 0 else None,
                                  "note": "pair compares only; the survivor bookkeeping (ffs) shares the pipe: ncu reports it 73% busy at C3"}
-    config.update({"n_info": sp.n_info, "candidate_pairs": pairs_total, "pairs_compared_tier1": int(st["pairs_compared"]),
-                   "pairs_tier2": int(st["pairs_tier2"]), "pairs_accepted": int(st["pairs_accepted"]), "joins_emitted": int(len(res.edges)),
-                   "l2": "inputs (%.0f MB resident) exceed the 126 MB L2; no flush" % (e2e_stats["h2d_bytes"] / 1e6),
-                   "host_buffers": "pinned (ejoin_host_alloc / ejoin_host_register); V..J arena flagged EJOIN_F_TIGS_IN_PLACE: read in place "
-                                   "over PCIe for the entries that need it, h2d_bytes_per_step counts those bytes", "generate_s": round(gen_s, 2),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, contiguous cost-balanced bucket ranges, NCCL all-gather of edges"})
+    config.update({"n_info": sp.n_info})
+    workload_stats = {"candidate_pairs": pairs_total, "pairs_compared_tier1": int(st["pairs_compared"]),
+                      "pairs_tier2": int(st["pairs_tier2"]), "pairs_accepted": int(st["pairs_accepted"]), "joins_emitted": int(n_joins),
+                      "l2": "inputs (%.0f MB resident) exceed the 126 MB L2; no flush" % (e2e_stats["h2d_bytes"] / 1e6),
+                      "host_buffers": "pinned; compact pack (EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS | EJOIN_F_TIGS_IN_PLACE): the 2-bit V..J "
+                                      "words are read in place over PCIe for the entries that need them, h2d_bytes_per_step counts those bytes",
+                      "generate_s": round(gen_s, 2), "pack_compact_s": round(compact_s, 3), "pack_compact_threads": os.cpu_count(),
+                      "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, cost-balanced bucket ranges, edges gathered to rank 0 over NCCL"}
     line = {"metric": "join pairs scored/sec", "value": pairs_total * K / dev_s, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 popcount + f64 score", "data": "synthetic", "config": config, "clocks": clocks,
@@ -311,7 +350,13 @@ def main():
                     "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
                     "breakdown_ms": {k2: round(e2e_stats[k2], 3) for k2 in ("ms_h2d", "ms_device", "ms_d2h", "ms_host_post", "ms_total")
                                      if k2 in e2e_stats}},
-            "gpu_launches": int(st["gpu_launches"]) * K, "roofline": roofline}
+            "gpu_launches": int(st["gpu_launches"]) * K, "roofline": roofline, "workload_stats": workload_stats,
+            "pairs_compared_per_s": int(st["pairs_compared"]) * K / dev_s}
+    if parity_ok is not None:
+        line["parity_ok"] = parity_ok
+    if e2e_ascii_s is not None:
+        line["e2e_variants"] = {"ascii_parallel_arrays": {"ms_per_step": e2e_ascii_s / K * 1e3, "value": pairs_total * K / e2e_ascii_s,
+                                                          "h2d_bytes_per_step": ascii_h2d}}
     if not args.no_cpu_baseline:
         val, info = cpu_baseline(sp, params, steps=2, best=True)
         line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
