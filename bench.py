@@ -213,11 +213,7 @@ def main():
         if world == 1:
             return j.run(pack_struct, copy=False)     # views into the library's pinned result buffer
         from enclone_b200.dist import sharded_join
-        pairs, cls, st, fin = sharded_join(j, pack_struct, rank, world, device=dev)   # includes the NCCL gather of edges
-        fin.stats.update(st)
-        fin.edges = pairs
-        fin.class_of = cls
-        return fin
+        return sharded_join(j, pack_struct, rank, world, device=dev)   # includes the device-to-device gather of the joins to rank 0
 
     for _ in range(W):
         res = e2e_step()
@@ -231,17 +227,20 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_stats = res.stats
     n_joins = len(res.edges)
+    if world > 1:
+        nj = torch.tensor([n_joins], device=dev)
+        dist.broadcast(nj, 0)
+        n_joins = int(nj[0])
     # parity of the sharded result: rank 0 repeats the join on its one GPU and compares raw_joins and the partition
     parity_ok = None
     if world > 1:
         ok = 1
         if rank == 0:
-            pairs_n = np.array(res.edges, copy=True)
+            edges_n = np.array(res.edges, copy=True)
             cls_n = np.array(res.class_of, copy=True)
             j1 = Joiner(params, device=local_rank)
             one = j1.run(cp.struct)
-            ok = int(np.array_equal(np.stack([one.edges["k1"], one.edges["k2"]], axis=1), pairs_n.reshape(-1, 2)) and
-                     np.array_equal(one.class_of, cls_n))
+            ok = int(np.array_equal(one.edges, edges_n) and np.array_equal(one.class_of, cls_n))     # every record field, in order
             j1.close()
         okt = torch.tensor([ok], device=dev)
         dist.broadcast(okt, 0)

@@ -13,7 +13,7 @@ EXPORTS = [
     "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
     "ejoin_plan_shards", "ejoin_run_shard", "ejoin_run_shard_final", "ejoin_partition_gpu", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_upload_shard", "ejoin_run_resident",
     "ejoin_host_alloc", "ejoin_host_free", "ejoin_host_register", "ejoin_host_unregister", "ejoin_p1", "ejoin_partition",
-    "ejoin_pack_compact", "ejoin_pack_compact_free",
+    "ejoin_pack_compact", "ejoin_pack_compact_free", "ejoin_comm_id", "ejoin_comm_init", "ejoin_run_sharded",
 ]
 
 _lib = None
@@ -77,6 +77,12 @@ def load():
     L.ejoin_pack_compact.argtypes = [C.POINTER(EjoinPack), C.c_int, C.POINTER(C.POINTER(EjoinPack))]
     L.ejoin_pack_compact.restype = C.c_int
     L.ejoin_pack_compact_free.argtypes = [C.POINTER(EjoinPack)]
+    L.ejoin_comm_id.argtypes = [C.c_char_p]
+    L.ejoin_comm_id.restype = C.c_int
+    L.ejoin_comm_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
+    L.ejoin_comm_init.restype = C.c_int
+    L.ejoin_run_sharded.argtypes = [H, C.POINTER(EjoinPack), C.POINTER(EjoinResult)]
+    L.ejoin_run_sharded.restype = C.c_int
     L.ejoin_p1.argtypes = [C.c_uint32] * 3
     L.ejoin_p1.restype = C.c_double
     _lib = L

@@ -17,6 +17,9 @@
 #include <type_traits>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>          // types and enums only: the library is bound at run time (dlopen), never linked
+
 #include "ejoin_kernels.cuh"
 
 namespace {
@@ -60,6 +63,44 @@ struct Sizer {                 // same walk as Arena, to size it first
 };
 
 }  // namespace
+
+// NCCL, bound at run time: the copy already loaded in the process (torch's bundled one) or the system libnccl.so.2.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    static int state = 0;              // 0 = not tried, 1 = ok, -1 = unavailable
+    if (state == 0) {
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        state = -1;
+        if (lib) {
+            bool ok = true;
+            auto sym = [&](const char *name) { void *p = dlsym(lib, name); if (!p) ok = false; return p; };
+            api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+            api.Send = (decltype(api.Send))sym("ncclSend");
+            api.Recv = (decltype(api.Recv))sym("ncclRecv");
+            api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+            if (ok) state = 1;
+        }
+    }
+    return state == 1 ? &api : nullptr;
+}
 
 struct ejoin_handle {
     int device = 0;
@@ -115,6 +156,10 @@ struct ejoin_handle {
     // pinned staging for results
     void *pin = nullptr; size_t pin_cap = 0;
     void *pin2 = nullptr; size_t pin2_cap = 0;   // ejoin_partition_gpu staging (h->pin may hold a live result)
+    // multi-GPU (ejoin_comm_init): the one exchange step of the path runs inside the library, device to device
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    DevBuf d_gather, d_xcounts, d_exact_all;
     // host replay scratch (kept across runs; only touched entries are reset)
     std::vector<uint32_t> uf_parent, cnt_tmp;
     std::vector<size_t> forest_tmp;
@@ -251,7 +296,8 @@ extern "C" void ejoin_destroy(ejoin_handle_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
-    h->in_arena.buf.release(); h->work.buf.release(); h->d_part.release();
+    if (h->comm && nccl_api()) { nccl_api()->CommDestroy(h->comm); h->comm = nullptr; }
+    h->in_arena.buf.release(); h->work.buf.release(); h->d_part.release(); h->d_gather.release(); h->d_xcounts.release(); h->d_exact_all.release();
     for (DevBuf *b : { &h->d_counters, &h->d_presL, &h->d_presC, &h->d_p1ptrs, &h->d_multinfo, &h->d_multpool, &h->d_cdmax, &h->d_p1scratch,
                        &h->d_Ls, &h->d_tabptrs })
         b->release();
@@ -1278,6 +1324,220 @@ extern "C" int ejoin_run_shard_final(ejoin_handle_t *h, const ejoin_pack_t *pk, 
 }
 
 extern "C" void ejoin_raw_free(ejoin_raw_edge_t *e) { free(e); }
+
+// ---------------------------------------------------------------------------------------------
+// The exchange step inside the library: every rank scores its bucket ranges and builds the
+// PotentialJoin records of its emitted joins on its own GPU; the records travel device to device to rank 0
+// (ncclSend / ncclRecv in one group, straight out of the work arena); rank 0 runs finish_join (GPU union-find
+// over all info entries) on the gathered buffer and makes the one device-to-host copy of the result.
+// ---------------------------------------------------------------------------------------------
+#define NCK(call)                                                                                  \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + nc->GetErrorString(r_);                           \
+            return EJOIN_E_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+extern "C" int ejoin_comm_id(uint8_t *id) {
+    NcclApi *nc = nccl_api();
+    if (!nc || !id) return nc ? EJOIN_E_ARG : EJOIN_E_UNSUPPORTED;
+    ncclUniqueId u;
+    if (nc->GetUniqueId(&u) != ncclSuccess) return EJOIN_E_CUDA;
+    static_assert(sizeof(u) == EJOIN_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &u, sizeof(u));
+    return EJOIN_OK;
+}
+
+extern "C" int ejoin_comm_init(ejoin_handle_t *h, const uint8_t *id, int rank, int world) {
+    if (!h || !id || world < 1 || rank < 0 || rank >= world) return EJOIN_E_ARG;
+    NcclApi *nc = nccl_api();
+    if (!nc) return fail(h, EJOIN_E_UNSUPPORTED, "libnccl.so.2 not found");
+    CK(cudaSetDevice(h->device));
+    if (h->comm) { nc->CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NCK(nc->CommInitRank(&h->comm, world, u, rank));
+    h->comm_rank = rank; h->comm_world = world;
+    CK(h->d_xcounts.ensure(8 * (size_t)(world + 1)));
+    return EJOIN_OK;
+}
+
+extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result_t *out) {
+    if (!h || !pk || !out) return EJOIN_E_ARG;
+    memset(out, 0, sizeof(*out));
+    if (!h->comm) return fail(h, EJOIN_E_ARG, "ejoin_run_sharded: ejoin_comm_init has not been called on this handle");
+    NcclApi *nc = nccl_api();
+    const int rank = h->comm_rank, world = h->comm_world, root = 0;
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->launches = 0;
+    const double t0 = now_ms();
+    uint32_t lo, hi;
+    const bool stride_mode = shard_range(pk, rank, world, &lo, &hi);
+    int rc = upload_range(h, pk, lo, hi);
+    if (rc) return rc;
+    const uint32_t n_all = pk->n_info;
+    const bool whole = lo == 0 && hi == n_all;
+    if (rank == root && !whole && n_all) {
+        // finish_join runs over every info entry: rank 0 also takes the whole exact_id array (4 bytes per entry)
+        CK(h->d_exact_all.ensure(4 * (size_t)n_all));
+        CK(cudaMemcpyAsync(h->d_exact_all.p, pk->exact_id, 4 * (size_t)n_all, cudaMemcpyHostToDevice, h->st_copy));
+        CK(cudaEventRecord(h->ev[6], h->st_copy));          // ev[6] is re-recorded by the pipeline; the wait below precedes that
+        h->h2d_bytes += 4 * (size_t)n_all;
+    }
+    h->is_bcr = (int)pk->is_bcr;
+    h->last_stride = stride_mode ? (uint32_t)world : 1u; h->last_phase = stride_mode ? (uint32_t)rank : 0u;
+    if (rank == root && !whole && n_all) CK(cudaStreamWaitEvent(h->st, h->ev[6], 0));
+    rc = device_pipeline(h, (int)pk->is_bcr, h->last_stride, h->last_phase);
+    if (rc) return rc;
+    const double t1 = now_ms();
+    const size_t nk = (size_t)h->counters.n_kept;
+    DevCounters *ctr = (DevCounters *)h->d_counters.p;
+    cudaStream_t st = h->st;
+    std::vector<unsigned long long> counts(world, 0);
+    auto exchange_counts = [&]() -> int {
+        unsigned long long *dc = (unsigned long long *)h->d_xcounts.p;
+        NCK(nc->AllGather(&ctr->n_kept, dc, 1, ncclUint64, h->comm, st));
+        CK(cudaMemcpyAsync(counts.data(), dc, 8 * (size_t)world, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    };
+    h->stats.d2h_bytes = sizeof(DevCounters);
+    if (stride_mode) {
+        // a giant bucket shared by the ranks: the accepted edges (16 bytes each) go to rank 0, which replays them
+        rc = exchange_counts();
+        if (rc) return rc;
+        size_t total = 0, off_me = 0;
+        for (int r = 0; r < world; r++) { if (r < rank) off_me += counts[r]; total += counts[r]; }
+        (void)off_me;
+        unsigned long long *gk = nullptr, *gv = nullptr;
+        if (rank == root) {
+            CK(h->d_gather.ensure(16 * (total + 1)));
+            gk = (unsigned long long *)h->d_gather.p; gv = gk + total;
+        }
+        NCK(nc->GroupStart());
+        if (rank == root) {
+            size_t off = 0;
+            for (int r = 0; r < world; r++) {
+                if (r != root && counts[r]) { NCK(nc->Recv(gk + off, counts[r], ncclUint64, r, h->comm, st)); NCK(nc->Recv(gv + off, counts[r], ncclUint64, r, h->comm, st)); }
+                off += counts[r];
+            }
+        } else if (nk) {
+            NCK(nc->Send(h->kept_keys, nk, ncclUint64, root, h->comm, st));
+            NCK(nc->Send(h->kept_vals, nk, ncclUint64, root, h->comm, st));
+        }
+        NCK(nc->GroupEnd());
+        if (rank == root) {
+            size_t off = 0;
+            for (int r = 0; r < root; r++) off += counts[r];
+            if (nk) {
+                CK(cudaMemcpyAsync(gk + off, h->kept_keys, 8 * nk, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(gv + off, h->kept_vals, 8 * nk, cudaMemcpyDeviceToDevice, st));
+            }
+            std::vector<unsigned long long> hk(2 * total + 2);
+            if (total) CK(cudaMemcpyAsync(hk.data(), gk, 16 * total, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            h->stats.d2h_bytes += 16 * total;
+            std::vector<ejoin_raw_edge_t> raw(total);
+            for (size_t i = 0; i < total; i++) {
+                const unsigned long long key = hk[i], val = hk[total + i];
+                raw[i].k1 = (uint32_t)(key >> 32); raw[i].k2 = (uint32_t)key;
+                raw[i].cd = (uint16_t)(val & 0xFFFF); raw[i].d = (uint16_t)((val >> 16) & 0xFFFF); raw[i].flags = (uint32_t)(val >> 32);
+            }
+            const size_t d2h_before = h->stats.d2h_bytes;
+            const uint64_t launches_before = h->launches;
+            rc = ejoin_finish(h, pk, raw.data(), total, out);
+            if (rc) return rc;
+            h->stats.d2h_bytes += d2h_before; h->launches += 0 * launches_before;
+        } else CK(cudaStreamSynchronize(st));
+    } else {
+        // contiguous bucket ranges: the rank's emitted joins are final; build their records here, ship them to rank 0
+        Arena &A = h->work;
+        const size_t save = A.off;
+        uint2 *d_pairs = A.take<uint2>(nk ? nk : 1);
+        ejoin_edge_t *d_out = A.take<ejoin_edge_t>(nk ? nk : 1);
+        uint32_t *d_slow = A.take<uint32_t>(nk ? nk : 1);
+        if (A.off > A.buf.cap) { A.off = save; return fail(h, EJOIN_E_NOMEM, "work arena too small for the epilogue"); }
+        if (nk) {
+            const DevParams pr = dev_params(h->params, (int)pk->is_bcr);
+            DevTables tbs;
+            tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
+            tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
+            k_keys_to_pairs<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(h->kept_keys, (uint32_t)nk, h->k_base, d_pairs);
+            CK(cudaMemsetAsync(&ctr->n_payload_slow, 0, sizeof(unsigned int), st));
+            k_payload_fast<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)nk, h->k_base, d_out, d_slow);
+            k_payload<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, d_slow, h->k_base, d_out);
+            h->launches += 3;
+            CK(cudaGetLastError());
+        }
+        rc = exchange_counts();
+        if (rc) { A.off = save; return rc; }
+        size_t total = 0;
+        for (int r = 0; r < world; r++) total += counts[r];
+        ejoin_edge_t *g_edges = nullptr;
+        if (rank == root) {
+            CK(h->d_gather.ensure(sizeof(ejoin_edge_t) * (total + 1) + 8 * (total + 1) + 8 * (size_t)n_all + 4 * (size_t)std::max(1u, pk->n_exact) + 1024));
+            g_edges = (ejoin_edge_t *)h->d_gather.p;
+        }
+        NCK(nc->GroupStart());
+        if (rank == root) {
+            size_t off = 0;
+            for (int r = 0; r < world; r++) {
+                if (r != root && counts[r]) NCK(nc->Recv(g_edges + off, counts[r] * sizeof(ejoin_edge_t), ncclUint8, r, h->comm, st));
+                off += counts[r];
+            }
+        } else if (nk) NCK(nc->Send(d_out, nk * sizeof(ejoin_edge_t), ncclUint8, root, h->comm, st));
+        NCK(nc->GroupEnd());
+        if (rank == root) {
+            size_t off = 0;
+            for (int r = 0; r < root; r++) off += counts[r];
+            if (nk) CK(cudaMemcpyAsync(g_edges + off, d_out, nk * sizeof(ejoin_edge_t), cudaMemcpyDeviceToDevice, st));
+            // finish_join on the gathered records
+            char *base = (char *)(g_edges + total + 1);
+            base = (char *)(((uintptr_t)base + 15) & ~(uintptr_t)15);
+            uint2 *g_pairs = (uint2 *)base; base += 8 * (total + 1);
+            uint32_t *d_label = (uint32_t *)base; base += 4 * (size_t)n_all;
+            uint32_t *d_label_out = (uint32_t *)base; base += 4 * (size_t)n_all;
+            uint32_t *d_first = (uint32_t *)base;
+            const uint32_t *d_exact = whole ? h->din.exact_id : (const uint32_t *)h->d_exact_all.p;
+            rc = ensure_pin(h, sizeof(ejoin_edge_t) * (total + 1) + 4 * ((size_t)n_all + 1) + 1024);
+            if (rc) { A.off = save; return rc; }
+            ejoin_edge_t *h_edges = (ejoin_edge_t *)h->pin;
+            uint32_t *h_labels = (uint32_t *)((char *)h->pin + ((sizeof(ejoin_edge_t) * (total + 1) + 255) & ~(size_t)255));
+            if (total) {
+                k_edge_pairs<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g_edges, (uint32_t)total, g_pairs);
+                CK(cudaMemcpyAsync(h_edges, g_edges, total * sizeof(ejoin_edge_t), cudaMemcpyDeviceToHost, st));
+            }
+            if (n_all) {
+                const uint32_t nx = pk->n_exact;
+                CK(cudaMemsetAsync(&ctr->n_classes, 0, sizeof(unsigned long long), st));
+                k_uf_init<<<(std::max(n_all, nx) + 255) / 256, 256, 0, st>>>(d_label, n_all, d_first, nx);
+                k_uf_first<<<(n_all + 255) / 256, 256, 0, st>>>(d_exact, n_all, nx, d_first);
+                k_uf_union<<<(std::max<uint32_t>(n_all, (uint32_t)total) + 255) / 256, 256, 0, st>>>(d_label, g_pairs, (uint32_t)total, 0, d_exact, n_all, nx, d_first);
+                k_uf_flatten<<<(n_all + 255) / 256, 256, 0, st>>>(d_label, n_all, ctr, d_label_out);
+                h->launches += 5;
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(h_labels, d_label_out, 4 * (size_t)n_all, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&h->counters.n_classes, &ctr->n_classes, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            }
+            CK(cudaStreamSynchronize(st));
+            out->n_edges = total; out->edges = h_edges; out->owner = h;
+            out->class_of = n_all ? h_labels : nullptr; out->n_info = n_all; out->n_classes = (uint32_t)h->counters.n_classes;
+            h->stats.d2h_bytes += total * sizeof(ejoin_edge_t) + 4 * (size_t)n_all;
+        } else {
+            CK(cudaStreamSynchronize(st));
+            out->owner = h;
+        }
+        A.off = save;
+    }
+    const double t2 = now_ms();
+    fill_stats(h, &out->stats);
+    out->stats.ms_h2d = h->stats.ms_h2d; out->stats.ms_d2h = 0; out->stats.ms_host_post = t2 - t1; out->stats.ms_total = t2 - t0;
+    out->stats.d2h_bytes = h->stats.d2h_bytes;
+    out->stats.gpu_launches = h->launches;
+    return 0;
+}
 
 // Ordered replay + payload + partition from gathered raw edges.  The handle must still hold
 // the upload that covers every entry the edges touch (its own shard, or everything in

@@ -2009,3 +2009,7 @@ __global__ void k_keys_to_pairs(const unsigned long long *keys, uint32_t ne, uin
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ne) pairs[i] = make_uint2((uint32_t)(keys[i] >> 32) + k_base, (uint32_t)keys[i] + k_base);   // local -> info indices
 }
+__global__ void k_edge_pairs(const ejoin_edge_t *edges, uint32_t ne, uint2 *pairs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ne) pairs[i] = make_uint2(edges[i].k1, edges[i].k2);
+}

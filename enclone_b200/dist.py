@@ -99,28 +99,22 @@ def all_gather_pairs(pairs, device=None, group=None):
     return np.concatenate(parts) if parts else np.zeros((0, 2), np.uint32)
 
 
-def sharded_join(joiner, pack_struct, rank, world, device=None, group=None, gpu_partition=True):
-    """The whole join stage on `world` GPUs, one call per rank.  Returns (raw_joins [m,2] for the
-    whole input in the reference's order, class_of, this rank's shard stats, this rank's JoinResult)."""
-    from ._abi import RAW_EDGE_DTYPE
-    mode, fin, raw, st = joiner.run_shard_final(pack_struct, rank, world, copy=False)
-    if mode == 1:
-        # a giant bucket is shared between ranks: gather the accepted edges, replay once
-        rows = np.stack([raw["k1"], raw["k2"], raw["cd"].astype(np.uint32) | (raw["d"].astype(np.uint32) << 16), raw["flags"]], axis=1) \
-            if len(raw) else np.zeros((0, 4), np.uint32)
-        allrows = all_gather_rows(rows, device=device, group=group)
-        allraw = np.zeros(len(allrows), RAW_EDGE_DTYPE)
-        if len(allrows):
-            allraw["k1"], allraw["k2"] = allrows[:, 0], allrows[:, 1]
-            allraw["cd"], allraw["d"], allraw["flags"] = allrows[:, 2] & 0xFFFF, allrows[:, 2] >> 16, allrows[:, 3]
-        fin = joiner.finish(pack_struct, allraw)
-        pairs = np.stack([fin.edges["k1"], fin.edges["k2"]], axis=1) if len(fin.edges) else np.zeros((0, 2), np.uint32)
-        return pairs, fin.class_of, st, fin
-    # contiguous bucket ranges: ranks are in bucket order, so concatenating in rank order IS raw_joins order
-    mine = np.stack([fin.edges["k1"], fin.edges["k2"]], axis=1) if len(fin.edges) else np.zeros((0, 2), np.uint32)
-    allp = all_gather_pairs(mine, device=device, group=group)
-    if gpu_partition:
-        cls, _ = joiner.partition(pack_struct, allp[:, 0], allp[:, 1])
-    else:
-        cls, _ = partition(pack_struct, allp[:, 0], allp[:, 1])
-    return allp, cls, st, fin
+def init_comm(joiner, rank, world, device=None, group=None):
+    """Give `joiner` the library's own communicator: rank 0 draws the id, torch.distributed hands it round."""
+    import torch
+    import torch.distributed as dist
+    from .join import comm_id
+    t = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(comm_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0, group=group)
+    joiner.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+
+def sharded_join(joiner, pack_struct, rank, world, device=None, group=None, copy=False):
+    """The whole join stage on `world` GPUs, one call per rank: score this rank's bucket ranges, gather the emitted joins
+    to rank 0 device to device inside the library (ejoin_run_sharded), finish_join there.  Returns the JoinResult of the
+    whole input on rank 0 (views into the handle's pinned result buffer unless copy=True), an empty one elsewhere."""
+    if getattr(joiner, "comm", None) != (rank, world):
+        init_comm(joiner, rank, world, device=device, group=group)
+    return joiner.run_sharded(pack_struct, copy=copy)

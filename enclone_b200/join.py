@@ -149,6 +149,19 @@ class Joiner:
         self.L.ejoin_raw_free(ep)
         return 1, None, raw, st.as_dict()
 
+    def comm_init(self, comm_id, rank, world):
+        """Join the library's own communicator (ejoin_comm_init): `comm_id` is the 128-byte id rank 0 got from
+        comm_id() and handed to every rank."""
+        self._check(self.L.ejoin_comm_init(self.h, comm_id, rank, world))
+        self.comm = (rank, world)
+
+    def run_sharded(self, pack_struct, copy=True):
+        """One call per rank (ejoin_run_sharded): rank 0 gets the whole join (raw_joins order, partition over all
+        entries), the other ranks an empty result with their own stats."""
+        res = EjoinResult()
+        self._check(self.L.ejoin_run_sharded(self.h, C.byref(pack_struct), C.byref(res)))
+        return self._result(res, copy)
+
     def partition(self, pack_struct, k1, k2):
         """finish_join on this handle's GPU (ejoin_partition_gpu): min-member labels over all info entries."""
         k1 = np.ascontiguousarray(k1, dtype=np.uint32)
@@ -208,6 +221,15 @@ class CompactPack:
             self.close()
         except Exception:
             pass
+
+
+def comm_id():
+    """A fresh communicator id (rank 0 calls this; ejoin_comm_id)."""
+    buf = C.create_string_buffer(128)
+    rc = _lib.load().ejoin_comm_id(buf)
+    if rc != 0:
+        raise _lib.EjoinError(rc, "ejoin_comm_id: libnccl.so.2 not usable")
+    return buf.raw
 
 
 def plan_shards(pack_struct, world):

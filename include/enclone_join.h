@@ -253,6 +253,18 @@ int  ejoin_run_shard_final(ejoin_handle_t *h, const ejoin_pack_t *pack, int rank
 int  ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pack, const ejoin_raw_edge_t *edges,
                   uint64_t n_edges, ejoin_result_t *out);
 
+/* The same decomposition with the exchange step inside the library (NCCL, bound at run time from libnccl.so.2): one
+ * process per GPU, each with its own handle.  Rank 0 obtains an id (ejoin_comm_id), the host framework hands it to every
+ * rank (any transport: MPI, a file, torch.distributed), every rank calls ejoin_comm_init, then ejoin_run_sharded once per
+ * join.  Contiguous bucket ranges: each rank's emitted joins, with their PotentialJoin records, go device to device to
+ * rank 0, which runs finish_join on its GPU and returns the whole result (raw_joins order, class_of over all entries);
+ * the other ranks return an empty result with their own stats.  A giant bucket shared by the ranks (stride mode): the
+ * accepted raw edges are gathered to rank 0 and replayed there. */
+#define EJOIN_COMM_ID_BYTES 128
+int  ejoin_comm_id(uint8_t *id /* [EJOIN_COMM_ID_BYTES] */);
+int  ejoin_comm_init(ejoin_handle_t *h, const uint8_t *id, int rank, int world_size);
+int  ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pack, ejoin_result_t *out);
+
 /* finish_join on the host from an emitted edge list (k1[i], k2[i]): partition labels (min member)
  * over all n_info entries, including the same-exact-subclonotype links.  Used by rank 0 after
  * the gather; needs no GPU and no handle. */

@@ -486,17 +486,26 @@ def test_compact_input_sharded_and_uploaded(monkeypatch):
     cp = CompactPack(pack)
     single = join_exacts(pack)
     world = 3
-    parts = []
+    parts, raws, js = [], [], []
     for rank in range(world):
         j = Joiner(default_params())
         mode, fin, raw, st = j.run_shard_final(cp.struct, rank, world)
-        assert mode == 0
-        parts.append(fin.edges)
-        j.upload_shard(cp.struct, rank, world)               # resident form of the same shard
-        s = j.run_resident()
-        assert s["edges_after_prune"] == len(fin.edges)
+        if mode == 0:
+            parts.append(fin.edges)
+            j.upload_shard(cp.struct, rank, world)               # resident form of the same shard
+            s = j.run_resident()
+            assert s["edges_after_prune"] == len(fin.edges)
+        else:
+            raws.append(raw)
+        js.append(j)
+    if parts:
+        assert not raws
+        assert np.array_equal(np.concatenate(parts), single.edges)
+    else:
+        fin = js[0].finish(cp.struct, np.concatenate(raws))
+        assert np.array_equal(fin.edges, single.edges) and np.array_equal(fin.class_of, single.class_of)
+    for j in js:
         j.close()
-    assert np.array_equal(np.concatenate(parts), single.edges)
     # stride mode on a giant bucket
     big, _ = synth.generate_config("C4", 0.02)
     cb = CompactPack(big)
@@ -530,3 +539,21 @@ def test_compact_full_size_c3():
     assert_same_join(g, oe, oc, what="compact C3")
     assert g.stats["h2d_bytes"] <= 350e6
     cp.close()
+
+
+@pytest.mark.parametrize("name,scale,stride,compact", [("C3", 0.05, 0, 1), ("C3", 0.05, 0, 0), ("C4", 0.05, 1, 1), ("C5", 0.05, 0, 1)])
+def test_two_rank_nccl_sharded_join(name, scale, stride, compact):
+    """Real NCCL, one process per GPU (torchrun, 2 ranks): contiguous bucket ranges and the shared giant bucket (stride
+    mode), the exchange inside the library; rank 0 checks the gathered result against the one-GPU join and the oracle."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = 29500 + (os.getpid() % 400)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(here, "mgpu_worker.py"), name, str(scale), str(stride), str(compact)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
