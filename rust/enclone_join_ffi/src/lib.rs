@@ -105,6 +105,9 @@ extern "C" {
     pub fn ejoin_host_unregister(p: *mut c_void) -> c_int;
     pub fn ejoin_pack_compact(input: *const ejoin_pack_t, threads: c_int, out: *mut *mut ejoin_pack_t) -> c_int;
     pub fn ejoin_pack_compact_free(p: *mut ejoin_pack_t);
+    pub fn ejoin_comm_id(id: *mut u8) -> c_int;
+    pub fn ejoin_comm_init(h: *mut c_void, id: *const u8, rank: c_int, world: c_int) -> c_int;
+    pub fn ejoin_run_sharded(h: *mut c_void, pack: *const ejoin_pack_t, out: *mut ejoin_result_t) -> c_int;
     pub fn ejoin_p1(k: u32, d: u32, n: u32) -> f64;
 }
 // The safe wrapper `join_exacts(..) -> EquivRel` with `Flat::pack` is sketched in INTEGRATION.md §1-§3;
