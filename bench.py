@@ -285,7 +285,9 @@ def main():
     m = np.diff(bstart.astype(np.int64))
     pairs_total = int((m * (m - 1) // 2).sum())
     if rank != 0:
+        j.close()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     ms = {k2: v / K for k2, v in acc.items()}
@@ -359,9 +361,10 @@ def main():
     if not args.no_cpu_baseline:
         val, info = cpu_baseline(sp, params, steps=2, best=True)
         line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     j.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -13,6 +13,7 @@ EJOIN_NONE16 = 0xFFFF
 EJOIN_F_TIGS_IN_PLACE = 1
 EJOIN_F_TIGS_2BIT = 2
 EJOIN_F_ENTRY_RECS = 4
+EJOIN_F_CDR3_2BIT = 8
 
 u8p, u16p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64))
 
@@ -42,6 +43,7 @@ class EjoinPack(C.Structure):
         ("nchains", u32p), ("ncells", u32p), ("donor_lo", u32p), ("donor_hi", u32p),
         ("refseq_off", u64p), ("refseq_len", u32p), ("refseq_arena", u8p), ("refseq_arena_bytes", C.c_uint64),
         ("tig2_arena", u64p), ("tig2_arena_words", C.c_uint64), ("entry_rec", C.POINTER(EjoinEntryRec)),
+        ("cdr3_2bit", u64p), ("cdr3_2bit_words", C.c_uint64), ("cdr3_2bit_off", u32p),
     ]
 
 

@@ -69,6 +69,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *);
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
     ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*CommAbort)(ncclComm_t);          // optional
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
@@ -90,6 +91,7 @@ static NcclApi *nccl_api() {
             api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
             api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+            api.CommAbort = (decltype(api.CommAbort))dlsym(lib, "ncclCommAbort");
             api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
             api.Send = (decltype(api.Send))sym("ncclSend");
             api.Recv = (decltype(api.Recv))sym("ncclRecv");
@@ -296,7 +298,8 @@ extern "C" void ejoin_destroy(ejoin_handle_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
-    if (h->comm && nccl_api()) { nccl_api()->CommDestroy(h->comm); h->comm = nullptr; }
+    // abort, not destroy: tearing a handle down must never wait for the other ranks (they may already be gone)
+    if (h->comm && nccl_api()) { NcclApi *nc = nccl_api(); if (nc->CommAbort) nc->CommAbort(h->comm); else nc->CommDestroy(h->comm); h->comm = nullptr; }
     h->in_arena.buf.release(); h->work.buf.release(); h->d_part.release(); h->d_gather.release(); h->d_xcounts.release(); h->d_exact_all.release();
     for (DevBuf *b : { &h->d_counters, &h->d_presL, &h->d_presC, &h->d_p1ptrs, &h->d_multinfo, &h->d_multpool, &h->d_cdmax, &h->d_p1scratch,
                        &h->d_Ls, &h->d_tabptrs })
@@ -344,11 +347,13 @@ const char *pack_null_field(const ejoin_pack_t *pk) {
         if ((pk->flags & EJOIN_F_TIGS_2BIT) && !pk->tig2_arena && pk->tig2_arena_words) return "tig2_arena";
         if (!(pk->flags & EJOIN_F_TIGS_2BIT) && !pk->tig_arena) return "tig_arena";
         if (pk->tig_arena_bytes && !pk->tig_arena) return "tig_arena";
-        if (!pk->cdr3_arena) return "cdr3_arena";
+        const bool c2 = pk->flags & EJOIN_F_CDR3_2BIT;
+        if (c2 && (!pk->cdr3_2bit_off || (!pk->cdr3_2bit && pk->cdr3_2bit_words))) return "cdr3_2bit / cdr3_2bit_off";
+        if (!c2 && !pk->cdr3_arena) return "cdr3_arena";
         for (int c = 0; c < 2; c++) {
             if (!pk->len[c]) return "len";
             if (!pk->cdr3_len[c]) return "cdr3_len";
-            if (!pk->cdr3_off[c]) return "cdr3_off";
+            if (!c2 && !pk->cdr3_off[c]) return "cdr3_off";
         }
         if (!recs) {
             if (!pk->c_ref_id_light) return "c_ref_id_light";
@@ -384,24 +389,39 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     const uint32_t n = hi - lo;
-    const bool two_bit = pk->flags & EJOIN_F_TIGS_2BIT, recs = pk->flags & EJOIN_F_ENTRY_RECS;
+    const bool two_bit = pk->flags & EJOIN_F_TIGS_2BIT, recs = pk->flags & EJOIN_F_ENTRY_RECS, c2 = pk->flags & EJOIN_F_CDR3_2BIT;
     auto tig_off_of = [&](int c, uint32_t k) -> uint64_t { return recs ? (uint64_t)pk->entry_rec[k].tig_off[c] : pk->tig_off[c][k]; };
     auto has_del_of = [&](int c, uint32_t k) -> bool { return recs ? pk->entry_rec[k].has_del[c] != 0 : pk->has_del[c][k] != 0; };
     // arena slices actually referenced by [lo,hi): ASCII bytes [tlo,thi), 2-bit words [wlo,whi), CDR3 bytes [clo,chi).
     // In 2-bit mode the ASCII arena only holds the few chains with a deletion marker: it goes up whole.
-    uint64_t tlo = 0, thi = pk->tig_arena_bytes, clo = 0, chi = pk->cdr3_arena_bytes, wlo = 0, whi = two_bit ? pk->tig2_arena_words : 0;
-    if (lo != 0 || hi != pk->n_info) {
+    // (with EJOIN_F_CDR3_2BIT, [clo,chi) counts 8-byte words of cdr3_2bit)
+    uint64_t tlo = 0, thi = pk->tig_arena_bytes, clo = 0, chi = c2 ? pk->cdr3_2bit_words : pk->cdr3_arena_bytes, wlo = 0, whi = two_bit ? pk->tig2_arena_words : 0;
+    if ((lo != 0 || hi != pk->n_info) && n > 0) {
+        // A shard's slices are read off its first and last entries: the arenas must be laid out in entry order (offsets
+        // non-decreasing in k, as every packer writes them; include/enclone_join.h).  The kernels check each entry against
+        // the slice (ERR_ARENA_RANGE -> EJOIN_E_ARG) instead of the host walking 10^6 entries per call.
         if (!two_bit) { tlo = ~0ull; thi = 0; }
         clo = ~0ull; chi = 0; wlo = ~0ull; whi = 0;
-        for (uint32_t k = lo; k < hi; k++)
+        auto visit = [&](uint32_t k) {
             for (int c = 0; c < 2; c++) {
                 uint64_t o = tig_off_of(c, k), e;
                 if (two_bit && !has_del_of(c, k)) { e = o + (pk->len[c][k] + 31) / 32; wlo = std::min(wlo, o); whi = std::max(whi, e); }
                 else if (!two_bit) { e = o + pk->len[c][k]; tlo = std::min(tlo, o); thi = std::max(thi, e); }
-                o = pk->cdr3_off[c][k]; e = o + pk->cdr3_len[c][k];
+                if (!c2) { o = pk->cdr3_off[c][k]; e = o + pk->cdr3_len[c][k]; clo = std::min(clo, o); chi = std::max(chi, e); }
+            }
+            if (c2) {
+                const uint64_t o = pk->cdr3_2bit_off[k], e = o + ((uint64_t)pk->cdr3_len[0][k] + pk->cdr3_len[1][k] + 31) / 32;
                 clo = std::min(clo, o); chi = std::max(chi, e);
             }
-        if (n == 0) { clo = chi = 0; if (!two_bit) tlo = thi = 0; }
+        };
+        auto plain2 = [&](uint32_t k) { return two_bit && ((pk->len[0][k] && !has_del_of(0, k)) || (pk->len[1][k] && !has_del_of(1, k))); };
+        uint32_t a = lo, b = hi - 1;
+        visit(a); visit(b);
+        if (two_bit) {          // the first / last entry that has a 2-bit chain (nearly always lo and hi - 1 themselves)
+            while (a < b && !plain2(a)) visit(++a);
+            while (b > a && !plain2(b)) visit(--b);
+        }
+        if (chi < clo) clo = chi = 0;
         if (whi <= wlo) wlo = whi = 0;
         if (thi < tlo) tlo = thi = 0;
     }
@@ -428,7 +448,7 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     sz.take(4 * n1); for (int i = 0; i < 6; i++) sz.take(2 * n1);
     for (int i = 0; i < 4; i++) sz.take(4 * (size_t)std::max(1u, pk->n_exact));
     sz.take(8 * (size_t)std::max(1u, pk->n_refseq)); sz.take(4 * (size_t)std::max(1u, pk->n_refseq));
-    sz.take(chi - clo + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 512);
+    sz.take((c2 ? 8 : 1) * (chi - clo) + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 512);
     sz.take(8 * (whi - wlo) + 256); sz.take(sizeof(ejoin_entry_rec_t) * n1);
     sz.take(4 * (size_t)std::max(1u, pk->n_refseq)); sz.take(12 * ((size_t)pk->refseq_arena_bytes / 32 + 3 * (size_t)pk->n_refseq + 8));   // germline planes
     CK(h->in_arena.buf.ensure(sz.off + 4096));
@@ -455,9 +475,10 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     for (int c = 0; c < 2; c++) {
         CK(up(d.len[c], pk->len[c] + lo, n));
         CK(up(d.cdr3_len[c], pk->cdr3_len[c] + lo, n));
-        CK(up(d.cdr3_off[c], pk->cdr3_off[c] + lo, n));
+        if (!c2) CK(up(d.cdr3_off[c], pk->cdr3_off[c] + lo, n));
     }
-    CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
+    if (c2) { CK(up(d.cdr3_2bit_off, pk->cdr3_2bit_off + lo, n)); CK(up(d.cdr3_2bit, pk->cdr3_2bit + clo, chi - clo)); }
+    else CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
     CK(cudaEventRecord(h->ev_early, h->st_copy));
     // late set: what k_meta and the scoring read; goes up while the sweep runs
     h->recs_pending = false;
@@ -560,7 +581,8 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     // the offsets index the original arenas: rebase the device pointers instead of the offsets
     d.tig_arena -= tlo; d.tig_src -= tlo; if (d.tig_copy) d.tig_copy -= tlo;
     if (d.tig2_src) d.tig2_src -= wlo;
-    d.cdr3_arena -= clo;
+    if (c2) d.cdr3_2bit -= clo; else d.cdr3_arena -= clo;
+    d.tig_lo = tlo; d.tig_hi = thi; d.tig2_lo = wlo; d.tig2_hi = whi; d.cdr3_lo = clo; d.cdr3_hi = chi;
     h->n = n; h->k_base = lo; h->tig_bytes = two_bit ? 32 * (whi - wlo) + (thi - tlo) : thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
     return 0;
 }
@@ -575,6 +597,7 @@ int prepare_tables(ejoin_handle *h, int is_bcr) {
     if (h->counters.err & ERR_CDR3_TOO_LONG) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 exceeds 255 nt (or 256 nt for both chains)");
     if (h->counters.err & ERR_LEN_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "V..J lengths of one entry sum to 8192 or more");
     if (h->counters.err & ERR_BAD_EXACT) return fail(h, EJOIN_E_ARG, "exact_id outside [0, n_exact)");
+    if (h->counters.err & ERR_ARENA_RANGE) return fail(h, EJOIN_E_ARG, "an arena offset lies outside the slice of its shard (arenas must be laid out in entry order) or outside the arena");
     // p1 tables for new L
     std::vector<uint32_t> newL;
     for (uint32_t L = 0; L < 8192; L++)
@@ -880,6 +903,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         h->counters.pairs_candidate = first.pairs_candidate; h->counters.n_buckets = first.n_buckets;
         if (h->counters.err & ERR_CDR3_BAD_CHAR) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 contains a character outside ACGT");
         if (h->counters.err & ERR_BAD_REFSEQ) return fail(h, EJOIN_E_ARG, "vs_seq/js_seq index outside the germline table");
+        if (h->counters.err & ERR_ARENA_RANGE) return fail(h, EJOIN_E_ARG, "an arena offset lies outside the slice of its shard (arenas must be laid out in entry order) or outside the arena");
         if (h->counters.err & ERR_K_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "a pair has 1024 or more mutations (p1 table width)");
         if (h->counters.err & ERR_GROUP_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "more than 8.3 M entries share all four lengths (one comparison group)");
         {
@@ -1199,8 +1223,19 @@ extern "C" void ejoin_result_free(ejoin_result_t *r) {
 static void plan_buckets(const ejoin_pack_t *pk, int world, std::vector<uint32_t> &bs, std::vector<uint32_t> &owner) {
     bs.clear();
     const uint16_t *l0 = pk->len[0], *l1 = pk->len[1];
-    for (uint32_t k = 0; k < pk->n_info; k++)
-        if (k == 0 || l0[k] != l0[k - 1] || l1[k] != l1[k - 1]) bs.push_back(k);
+    // `info` is sorted with lens first (CloneInfo's Ord), so a bucket is found by galloping + bisection from its head instead of a
+    // scan of all entries (a host scan of 1.3 M entries costs a millisecond per call).  Every boundary reported is a true run
+    // boundary (len differs across it) whatever the input, which is all the sharding needs: a rank's range is a union of runs.
+    const uint32_t n_all = pk->n_info;
+    auto same = [&](uint32_t a, uint32_t b) { return l0[a] == l0[b] && l1[a] == l1[b]; };
+    for (uint32_t k = 0; k < n_all;) {
+        bs.push_back(k);
+        uint32_t lo = k, step = 1;
+        while (lo + step < n_all && same(k, lo + step)) { lo += step; step <<= 1; }
+        uint32_t hi = std::min<uint64_t>((uint64_t)lo + step, n_all);      // same(k, lo) holds, hi == n_all or !same(k, hi)
+        while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (same(k, mid)) lo = mid; else hi = mid; }
+        k = hi;
+    }
     const uint32_t nb = (uint32_t)bs.size();
     bs.push_back(pk->n_info);
     owner.assign(nb, 0);
@@ -1355,7 +1390,7 @@ extern "C" int ejoin_comm_init(ejoin_handle_t *h, const uint8_t *id, int rank, i
     NcclApi *nc = nccl_api();
     if (!nc) return fail(h, EJOIN_E_UNSUPPORTED, "libnccl.so.2 not found");
     CK(cudaSetDevice(h->device));
-    if (h->comm) { nc->CommDestroy(h->comm); h->comm = nullptr; }
+    if (h->comm) { if (nc->CommAbort) nc->CommAbort(h->comm); else nc->CommDestroy(h->comm); h->comm = nullptr; }
     ncclUniqueId u;
     memcpy(&u, id, sizeof(u));
     NCK(nc->CommInitRank(&h->comm, world, u, rank));
@@ -1637,6 +1672,7 @@ namespace {
 struct CompactOwner {
     ejoin_pack_t pk;                       // first member: the pointer handed to the caller
     uint64_t *tig2 = nullptr; ejoin_entry_rec_t *rec = nullptr; uint8_t *ascii = nullptr;
+    uint64_t *c3w = nullptr; uint32_t *c3off = nullptr;
     bool pinned = true;
 };
 // pinned when a CUDA device is there; plain aligned memory otherwise (the conversion itself is host code and is tested
@@ -1646,7 +1682,7 @@ void *compact_alloc(CompactOwner *o, size_t bytes) {
     if (o->pinned) {
         if (cudaMallocHost(&p, bytes) == cudaSuccess) return p;
         cudaGetLastError();
-        if (o->tig2 || o->rec || o->ascii) return nullptr;       // do not mix the two kinds
+        if (o->tig2) return nullptr;       // do not mix the two kinds
         o->pinned = false;
     }
     if (posix_memalign(&p, 4096, (bytes + 4095) & ~(size_t)4095) != 0) return nullptr;
@@ -1670,7 +1706,7 @@ template <typename F> void parallel_ranges(uint32_t n, int threads, F f) {
 extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pack_t **out) {
     if (!in || !out) return EJOIN_E_ARG;
     *out = nullptr;
-    if (in->abi_version != EJOIN_ABI_VERSION || (in->flags & (EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS))) return EJOIN_E_ARG;
+    if (in->abi_version != EJOIN_ABI_VERSION || (in->flags & (EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS | EJOIN_F_CDR3_2BIT))) return EJOIN_E_ARG;
     if (pack_null_field(in)) return EJOIN_E_ARG;
     const uint32_t n = in->n_info;
     if (threads < 1) threads = 1;
@@ -1705,13 +1741,20 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
             if (asc[c][k]) { aoff[c][k] = abytes; abytes += in->len[c][k]; }
             else { woff[c][k] = words; words += (in->len[c][k] + 31) / 32; }
         }
-    if (words >= 0xFFFFFFFFull || abytes >= 0xFFFFFFFFull) return EJOIN_E_UNSUPPORTED;
+    std::vector<uint32_t> c3off_v(n ? n : 1);
+    uint64_t c3words = 0;
+    for (uint32_t k = 0; k < n; k++) { c3off_v[k] = (uint32_t)c3words; c3words += ((uint64_t)in->cdr3_len[0][k] + in->cdr3_len[1][k] + 31) / 32; }
+    if (words >= 0xFFFFFFFFull || abytes >= 0xFFFFFFFFull || c3words >= 0xFFFFFFFFull) return EJOIN_E_UNSUPPORTED;
     CompactOwner *o = new CompactOwner();
     o->pk = *in;
     o->tig2 = (uint64_t *)compact_alloc(o, 8 * (words + 16));
     if (o->tig2) o->rec = (ejoin_entry_rec_t *)compact_alloc(o, sizeof(ejoin_entry_rec_t) * ((size_t)n + 1));
     if (o->rec) o->ascii = (uint8_t *)compact_alloc(o, abytes + 128);
-    if (!o->tig2 || !o->rec || !o->ascii) { ejoin_pack_compact_free(&o->pk); return EJOIN_E_NOMEM; }
+    if (o->ascii) o->c3w = (uint64_t *)compact_alloc(o, 8 * (c3words + 16));
+    if (o->c3w) o->c3off = (uint32_t *)compact_alloc(o, 4 * ((size_t)n + 16));
+    if (!o->tig2 || !o->rec || !o->ascii || !o->c3w || !o->c3off) { ejoin_pack_compact_free(&o->pk); return EJOIN_E_NOMEM; }
+    memcpy(o->c3off, c3off_v.data(), 4 * (size_t)n);
+    bool bad_cdr3 = false;
     memset(o->tig2 + words, 0, 8 * 16);
     memset(o->ascii + abytes, 0, 128);
     parallel_ranges(n, threads, [&](uint32_t a, uint32_t b) {
@@ -1740,14 +1783,35 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
                 r.vs_seq[c] = n16(in->vs_seq[c][k]); r.js_seq[c] = n16(in->js_seq[c][k]); r.vname_id[c] = n16(in->vname_id[c][k]);
                 r.vuni_seq[c] = n16(in->vuni_seq[c][k]); r.utr_seq[c] = n16(in->utr_seq[c][k]);
             }
+            {   // both CDR3s concatenated, 2 bits per base, DnaString bit order
+                uint64_t *w = o->c3w + c3off_v[k];
+                const uint32_t cl0 = in->cdr3_len[0][k], tot = cl0 + in->cdr3_len[1][k];
+                const uint8_t *q0 = in->cdr3_arena + in->cdr3_off[0][k], *q1 = in->cdr3_arena + in->cdr3_off[1][k];
+                uint8_t bad = 0;
+                for (uint32_t i0 = 0; i0 < tot; i0 += 32) {
+                    uint64_t x = 0;
+                    const uint32_t m = std::min(32u, tot - i0);
+                    for (uint32_t i = 0; i < m; i++) {
+                        const uint32_t p = i0 + i;
+                        const uint8_t code = g_code.t[p < cl0 ? q0[p] : q1[p - cl0]];
+                        bad |= code;
+                        x |= (uint64_t)(code & 3) << (62 - 2 * i);
+                    }
+                    w[i0 >> 5] = x;
+                }
+                if (bad & 0x80) bad_cdr3 = true;
+            }
             r.c_ref_id_light = n16(in->c_ref_id_light[k]); r.hcomp = in->hcomp[k];
             r.fr1_start = in->fr1_start[k]; r.cdr1_start = in->cdr1_start[k]; r.fr2_start = in->fr2_start[k];
             r.cdr2_start = in->cdr2_start[k]; r.fr3_start = in->fr3_start[k];
             o->rec[k] = r;
         }
     });
+    if (bad_cdr3) { ejoin_pack_compact_free(&o->pk); return EJOIN_E_UNSUPPORTED; }      // a CDR3 character outside ACGT (documented limit)
     ejoin_pack_t &pk = o->pk;
-    pk.flags = (in->flags & ~EJOIN_F_TIGS_IN_PLACE) | EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS | (o->pinned ? EJOIN_F_TIGS_IN_PLACE : 0u);
+    pk.flags = (in->flags & ~EJOIN_F_TIGS_IN_PLACE) | EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS | EJOIN_F_CDR3_2BIT | (o->pinned ? EJOIN_F_TIGS_IN_PLACE : 0u);
+    pk.cdr3_2bit = o->c3w; pk.cdr3_2bit_words = c3words; pk.cdr3_2bit_off = o->c3off;
+    pk.cdr3_arena = nullptr; pk.cdr3_arena_bytes = 0; pk.cdr3_off[0] = pk.cdr3_off[1] = nullptr;
     pk.tig2_arena = o->tig2; pk.tig2_arena_words = words; pk.entry_rec = o->rec;
     pk.tig_arena = o->ascii; pk.tig_arena_bytes = abytes;
     for (int c = 0; c < 2; c++) {
@@ -1763,7 +1827,7 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
 extern "C" void ejoin_pack_compact_free(ejoin_pack_t *p) {
     if (!p) return;
     CompactOwner *o = reinterpret_cast<CompactOwner *>(p);
-    for (void *q : { (void *)o->tig2, (void *)o->rec, (void *)o->ascii })
+    for (void *q : { (void *)o->tig2, (void *)o->rec, (void *)o->ascii, (void *)o->c3w, (void *)o->c3off })
         if (q) { if (o->pinned) cudaFreeHost(q); else free(q); }
     delete o;
 }

@@ -29,6 +29,7 @@
 #define ERR_BAD_REFSEQ 4u
 #define ERR_K_TOO_LARGE 8u
 #define ERR_LEN_TOO_LARGE 16u
+#define ERR_ARENA_RANGE 128u      // an entry's bytes / words lie outside the uploaded slice of their arena
 #define ERR_BAD_EXACT 64u         // exact_id[k] >= n_exact
 #define ERR_GROUP_TOO_LARGE 32u   // a comparison group of more than 65535 tiles (8.3 M entries with equal lengths)
 
@@ -115,6 +116,11 @@ struct DevIn {
     // chain is a word offset into tig2_src (device copy, or the caller's pinned arena read in place); tig_arena / tig_off
     // keep their ASCII meaning for the chains with has_del != 0.  nullptr = every chain is ASCII.
     const uint64_t *tig2_src;
+    // EJOIN_F_CDR3_2BIT: both CDR3s of an entry concatenated, 2 bits per base; nullptr = ASCII strings in cdr3_arena
+    const uint64_t *cdr3_2bit;
+    const uint32_t *cdr3_2bit_off;
+    // uploaded slices (caller coordinates): ASCII V..J bytes, 2-bit V..J words, CDR3 bytes or words
+    unsigned long long tig_lo, tig_hi, tig2_lo, tig2_hi, cdr3_lo, cdr3_hi;
     const uint8_t *has_del[2];
     const uint16_t *cdr3_len[2];
     const uint64_t *cdr3_off[2];

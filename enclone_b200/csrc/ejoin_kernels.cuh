@@ -297,6 +297,35 @@ __device__ __forceinline__ void planes32(const uint32_t (&x)[8], uint32_t &H, ui
     for (int i = 0; i < 8; i++) { H |= nibble_of(x[i] >> 2) << (4 * i); L |= nibble_of(x[i] >> 1) << (4 * i); }
 }
 
+// 32 bases of a DnaString word (base i at bits 63-2i, 62-2i; A,C,G,T = 0..3) -> the plane words of this library:
+// bit i of H / L = high / low bit of the code (byte >> 1) & 3 that the ASCII path uses (A,C,G,T -> 0,1,3,2 = g ^ (g >> 1)).
+__device__ __forceinline__ uint32_t even_bits16(uint32_t v) {      // bits 0,2,4,.. of v -> bits 0..15
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+    v = (v | (v >> 4)) & 0x00FF00FFu;
+    return (v | (v >> 8)) & 0xFFFFu;
+}
+__device__ __forceinline__ void planes_of_2bit(unsigned long long x, uint32_t &H, uint32_t &L) {
+    // after the bit reversal base i sits at bits 2i (code bit 1) and 2i+1 (code bit 0)
+    const unsigned long long r = __brevll(x);
+    const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+    const uint32_t b1 = even_bits16(lo) | (even_bits16(hi) << 16), b0 = even_bits16(lo >> 1) | (even_bits16(hi >> 1) << 16);
+    H = b1; L = b1 ^ b0;
+}
+// 16 consecutive bases of a chain as ASCII bytes, rebuilt from its H / L plane words (positions p0..p0+15, p0 % 16 == 0)
+__device__ __forceinline__ void bytes_of_planes16(uint32_t H, uint32_t L, int half, uint32_t (&out)[4]) {
+    const uint32_t h = (H >> (16 * half)) & 0xFFFFu, l = (L >> (16 * half)) & 0xFFFFu;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t hn = (h >> (4 * i)) & 0xFu, ln = (l >> (4 * i)) & 0xFu;
+        // selector nibble j = 2 * hbit_j + lbit_j
+        const uint32_t sh = (hn & 1u) | ((hn & 2u) << 3) | ((hn & 4u) << 6) | ((hn & 8u) << 9);
+        const uint32_t sl = (ln & 1u) | ((ln & 2u) << 3) | ((ln & 4u) << 6) | ((ln & 8u) << 9);
+        out[i] = __byte_perm(0x47544341u /* codes 0,1,2,3 -> 'A','C','T','G' */, 0u, (sh << 1) | sl);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ gid_incl,
                                               const GroupInfo *__restrict__ groups, const uint32_t *__restrict__ t2off, DevCounters *ctr,
                                               EntryMeta *__restrict__ meta, uint32_t *__restrict__ k_to_s, const uint8_t *__restrict__ needed,
@@ -351,9 +380,26 @@ __global__ void __launch_bounds__(256) k_pack_c3(DevIn in, const uint32_t *__res
     const int cl0 = in.cdr3_len[0][k], total = cl0 + in.cdr3_len[1][k];
     const int W = g.W;
     const uint32_t c3off = g.c3base + (s - g.start) * 2 * W;
+    {   // the entry's CDR3 data must lie inside the uploaded slice
+        bool ok;
+        if (in.cdr3_2bit) { const unsigned long long o = in.cdr3_2bit_off[k]; ok = o >= in.cdr3_lo && o + (unsigned)((total + 31) / 32) <= in.cdr3_hi; }
+        else {
+            const unsigned long long o0 = in.cdr3_off[0][k], o1 = in.cdr3_off[1][k];
+            ok = o0 >= in.cdr3_lo && o0 + (unsigned)cl0 <= in.cdr3_hi && o1 >= in.cdr3_lo && o1 + (unsigned)(total - cl0) <= in.cdr3_hi;
+        }
+        if (!ok) { if ((t & 3) == 0) atomicOr(&ctr->err, ERR_ARENA_RANGE); for (uint32_t w = t & 3; (int)w < W; w += 4) { c3[c3off + w] = 0; c3[c3off + W + w] = 0; } return; }
+    }
     for (uint32_t w = t & 3; (int)w < W; w += 4) {
     const int p0 = 32 * (int)w;
     const int nb = total - p0;                                 // valid bytes in this word
+    if (in.cdr3_2bit) {                                        // the caller's word IS the row word, up to the bit order
+        uint32_t H = 0, L = 0;
+        if (nb > 0) planes_of_2bit(__ldg(in.cdr3_2bit + in.cdr3_2bit_off[k] + w), H, L);
+        const uint32_t valid = low_bits(nb);
+        c3[c3off + w] = H & valid;
+        c3[c3off + W + w] = L & valid;
+        continue;
+    }
     uint32_t x[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) x[i] = 0;
@@ -438,35 +484,6 @@ __global__ void __launch_bounds__(32) k_pack_ref(DevIn in) {
 // its entry's bytes into shared memory with non-overlapping aligned 16-byte loads — in zero-copy mode
 // in.tig_arena is the caller's pinned host buffer and these loads are the only PCIe traffic for the
 // V..J bytes, issued for needed entries only — and then every lane reduces its 32-base word from there.
-// 32 bases of a DnaString word (base i at bits 63-2i, 62-2i; A,C,G,T = 0..3) -> the plane words of this library:
-// bit i of H / L = high / low bit of the code (byte >> 1) & 3 that the ASCII path uses (A,C,G,T -> 0,1,3,2 = g ^ (g >> 1)).
-__device__ __forceinline__ uint32_t even_bits16(uint32_t v) {      // bits 0,2,4,.. of v -> bits 0..15
-    v &= 0x55555555u;
-    v = (v | (v >> 1)) & 0x33333333u;
-    v = (v | (v >> 2)) & 0x0F0F0F0Fu;
-    v = (v | (v >> 4)) & 0x00FF00FFu;
-    return (v | (v >> 8)) & 0xFFFFu;
-}
-__device__ __forceinline__ void planes_of_2bit(unsigned long long x, uint32_t &H, uint32_t &L) {
-    // after the bit reversal base i sits at bits 2i (code bit 1) and 2i+1 (code bit 0)
-    const unsigned long long r = __brevll(x);
-    const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
-    const uint32_t b1 = even_bits16(lo) | (even_bits16(hi) << 16), b0 = even_bits16(lo >> 1) | (even_bits16(hi >> 1) << 16);
-    H = b1; L = b1 ^ b0;
-}
-// 16 consecutive bases of a chain as ASCII bytes, rebuilt from its H / L plane words (positions p0..p0+15, p0 % 16 == 0)
-__device__ __forceinline__ void bytes_of_planes16(uint32_t H, uint32_t L, int half, uint32_t (&out)[4]) {
-    const uint32_t h = (H >> (16 * half)) & 0xFFFFu, l = (L >> (16 * half)) & 0xFFFFu;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t hn = (h >> (4 * i)) & 0xFu, ln = (l >> (4 * i)) & 0xFu;
-        // selector nibble j = 2 * hbit_j + lbit_j
-        const uint32_t sh = (hn & 1u) | ((hn & 2u) << 3) | ((hn & 4u) << 6) | ((hn & 8u) << 9);
-        const uint32_t sl = (ln & 1u) | ((ln & 2u) << 3) | ((ln & 4u) << 6) | ((ln & 8u) << 9);
-        out[i] = __byte_perm(0x47544341u /* codes 0,1,2,3 -> 'A','C','T','G' */, 0u, (sh << 1) | sl);
-    }
-}
-
 // EJOIN_F_ENTRY_RECS: one 64-byte record per entry -> the parallel arrays the kernels read (device to device, ~40 us at
 // 1.27 M entries); 0xFFFF widens to EJOIN_NONE.
 struct RecOut {
@@ -515,6 +532,16 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
         const unsigned long long e0 = in.tig_off[0][k] + (unsigned long long)n0, e1 = in.tig_off[1][k] + (unsigned long long)n1;
         const unsigned long long last = e0 > e1 ? e0 : e1;
         if (!(last > wm_lo && last <= wm_hi)) return;
+    }
+    {   // every chain must lie inside the uploaded slice of its arena
+        bool ok = true;
+        for (int c = 0; c < 2; c++) {
+            const unsigned long long o = in.tig_off[c][k];
+            const unsigned nn = (unsigned)(c ? n1 : n0);
+            if (asc[c]) ok = ok && (nn == 0 || (o >= in.tig_lo && o + nn <= in.tig_hi));
+            else ok = ok && (nn == 0 || (o >= in.tig2_lo && o + (nn + 31) / 32 <= in.tig2_hi));
+        }
+        if (!ok) { if (lane == 0) atomicOr(&ctr->err, ERR_ARENA_RANGE); return; }
     }
     // ---- stage the ASCII chains (chains longer than 512 bases are read in place)
     uint32_t soff[2] = { 0, 0 };
@@ -1095,7 +1122,7 @@ __device__ __forceinline__ uint32_t range16(int p0, int lo, int hi) {
 // popcount of mask products.  The first version walked the sequences one byte per lane and pass (diffs, V window, J
 // window, per germline set): ~60 dependent load rounds per pair, against 3 here.
 template <bool WARP>
-__device__ void bytewise_counts_t(const DevIn &in, const uint4 *__restrict__ t2rows, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
+__device__ void bytewise_counts_t(const DevIn &in, const uint4 *__restrict__ t2rows, const uint32_t *__restrict__ c3rows, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
     static_assert(WARP, "warp-cooperative only");
     const int lane = (int)(threadIdx.x & 31);
     const uint32_t k1 = m1.k, k2 = m2.k;
@@ -1117,13 +1144,13 @@ __device__ void bytewise_counts_t(const DevIn &in, const uint4 *__restrict__ t2r
         const uint32_t blk0 = c ? ((uint32_t)m1.len[0] + 127) / 128 : 0u;
         const uint32_t *w1 = (const uint32_t *)(t2rows + m1.t2off) + 12 * blk0, *w2 = (const uint32_t *)(t2rows + m2.t2off) + 12 * blk0;
         const int a1 = m1.cs[c], a2 = m2.cs[c], cl = m1.cl[c];
-        {   // CDR3 strings (cl <= 255: one pass)
-            const uint8_t *q1 = in.cdr3_arena + in.cdr3_off[c][k1], *q2 = in.cdr3_arena + in.cdr3_off[c][k2];
-            const int p0 = 16 * lane;
-            if (p0 < cl) {
-                uint32_t x[4], y[4];
-                load16u(q1 + p0, x); load16u(q2 + p0, y);
-                cdc[c] += __popc(neq16(x, y) & range16(p0, 0, cl));
+        if (c == 0 && lane < 8) {   // CDR3 differences per chain from the c3 rows (the CDR3s are ACGT only): lane w takes word w
+            const int cl0 = m1.cl[0], total = cl0 + (int)m1.cl[1], W = max(1, (total + 31) / 32);
+            if (lane < W) {
+                const uint32_t D = (__ldg(c3rows + m1.c3off + lane) ^ __ldg(c3rows + m2.c3off + lane)) |
+                                   (__ldg(c3rows + m1.c3off + W + lane) ^ __ldg(c3rows + m2.c3off + W + lane));
+                const int d0 = __popc(D & range_mask(lane, 0, cl0));
+                cdc[0] += d0; cdc[1] += __popc(D) - d0;
             }
         }
         for (int p0 = 16 * lane; p0 < n; p0 += 512) {
@@ -1201,8 +1228,8 @@ __device__ void bytewise_counts_t(const DevIn &in, const uint4 *__restrict__ t2r
     if (reg) { pc.dfw = warp_sum(dfw); pc.dc12 = warp_sum(d12); pc.lfw = c1 - f1; pc.l12 = (f2 - c1) + (f3 - c2); }
 }
 
-__device__ __forceinline__ void bytewise_counts(const DevIn &in, const uint4 *t2rows, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
-    bytewise_counts_t<true>(in, t2rows, pr, m1, m2, pc);
+__device__ __forceinline__ void bytewise_counts(const DevIn &in, const uint4 *t2rows, const uint32_t *c3rows, const DevParams &pr, const EntryMeta &m1, const EntryMeta &m2, PairCounts &pc) {
+    bytewise_counts_t<true>(in, t2rows, c3rows, pr, m1, m2, pc);
 }
 // K6  tier 2, bytewise: one warp per queued pair (already past the CDR3 and meta gates).
 __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *generic_q,
@@ -1217,7 +1244,7 @@ __global__ void __launch_bounds__(128) k_tier2_generic(DevIn in, DevTables tb, D
         const uint2 c = generic_q[i];
         const EntryMeta m1 = tb.meta[c.x], m2 = tb.meta[c.y];      // already ordered k1 < k2
         PairCounts pc;
-        bytewise_counts(in, tb.t2, pr, m1, m2, pc);
+        bytewise_counts(in, tb.t2, tb.c3, pr, m1, m2, pc);
         if (lane == 0) atomicAdd(&ctr->n_generic, 1ull);
         bool ok = true;
         if (!pr.is_bcr || pr.max_diffs < 1000000) {
@@ -1335,7 +1362,7 @@ __global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevPara
         const uint2 kk2 = pairs[i];
         const EntryMeta m1 = tb.meta[k_to_s[kk2.x - k_base]], m2 = tb.meta[k_to_s[kk2.y - k_base]];
         PairCounts pc;
-        bytewise_counts(in, tb.t2, pr, m1, m2, pc);
+        bytewise_counts(in, tb.t2, tb.c3, pr, m1, m2, pc);
         int kk = 0, d = 0, err = 0;
         double p1 = 0, mult = 0, score = 0;
         if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
@@ -1775,7 +1802,7 @@ __device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTab
                                                    int *cd_out, int *d_out) {
     const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
     PairCounts pc;
-    bytewise_counts_t<true>(in, tb.t2, pr, m1, m2, pc);
+    bytewise_counts_t<true>(in, tb.t2, tb.c3, pr, m1, m2, pc);
     if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->n_generic, 1ull);
     *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
     if (!pr.is_bcr || pr.max_diffs < 1000000) {

@@ -47,8 +47,10 @@ extern "C" {
  * 22 parallel arrays (which may then be NULL): 4.5x fewer bytes per entry and one cache line per entry.
  * Requires every id / germline index to be < 65535. */
 #define EJOIN_F_ENTRY_RECS 4u
-/* cdr3_off may be NULL: the CDR3 strings lie back to back in cdr3_arena in entry order (chain 0 then chain 1). */
-#define EJOIN_F_CDR3_DENSE 8u
+/* The CDR3s come 2 bits per base: for entry k the two CDR3 strings concatenated (chain 0 then chain 1, no gap), in the
+ * DnaString bit layout, in ceil((cdr3_len[0][k] + cdr3_len[1][k]) / 32) words starting at cdr3_2bit[cdr3_2bit_off[k]].
+ * cdr3_arena / cdr3_off may then be NULL.  (CDR3 characters outside ACGT are outside the documented limits either way.) */
+#define EJOIN_F_CDR3_2BIT 8u
 
 /* error codes */
 #define EJOIN_OK 0
@@ -66,6 +68,10 @@ extern "C" {
  * (TigData1.left), c = 1 the light/TRA chain.  An entry with one chain
  * (CloneInfo.lens.len() == 1) has len[1][k] == 0 and is never joined
  * (enclone_help/src/help1.rs:270-276).
+ * Arena layout: offsets are free within an arena, except that the sharded entry points (ejoin_run_shard*,
+ * ejoin_upload_shard, ejoin_run_sharded) upload only the slice between a shard's first and last entry, so for those
+ * the arenas must be laid out in entry order (offsets non-decreasing in k — what any packer that walks `info` once
+ * writes).  An entry whose bytes fall outside its slice, or outside the arena, is an EJOIN_E_ARG error.
  * ------------------------------------------------------------------------- */
 /* One info entry's "late" fields (EJOIN_F_ENTRY_RECS): same meaning as the arrays of the same name below;
  * 0xFFFF stands for None (EJOIN_NONE / EJOIN_NONE16). */
@@ -129,6 +135,9 @@ typedef struct ejoin_pack {
     const uint64_t *tig2_arena;  /* 2-bit V..J bases (CloneInfo.tigsp), >= 8 readable words of slack behind the last one */
     uint64_t        tig2_arena_words;
     const ejoin_entry_rec_t *entry_rec; /* [n_info] */
+    const uint64_t *cdr3_2bit;   /* EJOIN_F_CDR3_2BIT */
+    uint64_t        cdr3_2bit_words;
+    const uint32_t *cdr3_2bit_off; /* [n_info] word offset into cdr3_2bit */
 } ejoin_pack_t;
 
 /* Join parameters: EncloneControl.{join_alg_opt, heur, clono_filt_opt_def} as
@@ -282,7 +291,7 @@ int  ejoin_upload_shard(ejoin_handle_t *h, const ejoin_pack_t *pack, int rank, i
 int  ejoin_run_resident(ejoin_handle_t *h, ejoin_stats_t *stats);
 
 /* Host-side conversion of an ASCII / parallel-array pack into the compact form (EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS |
- * EJOIN_F_CDR3_DENSE | EJOIN_F_TIGS_IN_PLACE): what a caller that holds CloneInfo.tigsp would build directly.  The arenas
+ * EJOIN_F_CDR3_2BIT | EJOIN_F_TIGS_IN_PLACE): what a caller that holds CloneInfo.tigsp would build directly.  The arenas
  * of the new pack are pinned (ejoin_host_alloc); arrays that do not change are shared with `in`, which must outlive it.
  * Fails with EJOIN_E_UNSUPPORTED when an id does not fit 16 bits.  Needs no handle. */
 int  ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pack_t **out);

@@ -12,6 +12,7 @@ pub const EJOIN_NONE16: u16 = 0xFFFF;
 pub const EJOIN_F_TIGS_IN_PLACE: u32 = 1;
 pub const EJOIN_F_TIGS_2BIT: u32 = 2;
 pub const EJOIN_F_ENTRY_RECS: u32 = 4;
+pub const EJOIN_F_CDR3_2BIT: u32 = 8;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -38,6 +39,7 @@ pub struct ejoin_pack_t {
     pub nchains: *const u32, pub ncells: *const u32, pub donor_lo: *const u32, pub donor_hi: *const u32,
     pub refseq_off: *const u64, pub refseq_len: *const u32, pub refseq_arena: *const u8, pub refseq_arena_bytes: u64,
     pub tig2_arena: *const u64, pub tig2_arena_words: u64, pub entry_rec: *const ejoin_entry_rec_t,
+    pub cdr3_2bit: *const u64, pub cdr3_2bit_words: u64, pub cdr3_2bit_off: *const u32,
 }
 
 #[repr(C)]
