@@ -19,14 +19,15 @@ class EquivRel:
     class_id, orbit_reps, orbit — built from the partition labels the library returns."""
 
     def __init__(self, class_of):
-        self._cls = np.asarray(class_of, dtype=np.int64)
-        self._orbits = None
+        self._cls = class_of                     # the library's labels (min member of each class); nothing is copied or
+        self._orbits = None                      # converted until a caller asks for orbits
 
     def class_id(self, a):
         return int(self._cls[a])
 
     def _build(self):
         if self._orbits is None:
+            self._cls = np.asarray(self._cls, dtype=np.int64)
             order = np.argsort(self._cls, kind="stable")
             reps, starts = np.unique(self._cls[order], return_index=True)
             self._reps = reps

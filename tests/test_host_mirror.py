@@ -15,7 +15,8 @@ BIN = os.path.join(ROOT, "tests", "host_mirror_test")
 def _build():
     src = os.path.join(ROOT, "tests", "host_mirror_test.cpp")
     lib = os.path.join(ROOT, "enclone_b200")
-    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(lib, "host", "join_exacts.hpp"))):
+    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(lib, "host", "join_exacts.hpp")),
+                                                                  os.path.getmtime(os.path.join(ROOT, "include", "enclone_join.h")), os.path.getmtime(os.path.join(lib, "libenclone_join.so"))):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", BIN, src, "-L" + lib, "-lenclone_join", "-Wl,-rpath," + lib])
     return BIN
 
