@@ -91,6 +91,11 @@ EDGE_DTYPE = np.dtype([
 assert EDGE_DTYPE.itemsize == C.sizeof(EjoinEdge), (EDGE_DTYPE.itemsize, C.sizeof(EjoinEdge))
 
 
+class EjoinLogNames(C.Structure):
+    _fields_ = [("index", C.c_int32)] + [(n, C.c_char_p) for n in ("id1", "id2", "vsegs1", "vsegs2", "dataset1", "dataset2", "cdr3_aa1", "cdr3_aa2",
+                                                                   "bcs1", "bcs2")]
+
+
 class EjoinStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_buckets", "n_groups", "pairs_candidate", "pairs_compared", "pairs_tier2", "pairs_accepted",

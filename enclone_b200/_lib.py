@@ -3,7 +3,7 @@ missing or no CUDA device is usable, calls raise."""
 import ctypes as C
 import os
 
-from ._abi import EjoinEdge, EjoinPack, EjoinParams, EjoinRawEdge, EjoinResult, EjoinStats
+from ._abi import EjoinEdge, EjoinLogNames, EjoinPack, EjoinParams, EjoinRawEdge, EjoinResult, EjoinStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libenclone_join.so")
@@ -13,7 +13,7 @@ EXPORTS = [
     "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
     "ejoin_plan_shards", "ejoin_run_shard", "ejoin_run_shard_final", "ejoin_partition_gpu", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_upload_shard", "ejoin_run_resident",
     "ejoin_host_alloc", "ejoin_host_free", "ejoin_host_register", "ejoin_host_unregister", "ejoin_p1", "ejoin_partition",
-    "ejoin_pack_compact", "ejoin_pack_compact_free", "ejoin_comm_id", "ejoin_comm_init", "ejoin_run_sharded",
+    "ejoin_pack_compact", "ejoin_pack_compact_free", "ejoin_comm_id", "ejoin_comm_init", "ejoin_run_sharded", "ejoin_format_join_log",
 ]
 
 _lib = None
@@ -83,6 +83,9 @@ def load():
     L.ejoin_comm_init.restype = C.c_int
     L.ejoin_run_sharded.argtypes = [H, C.POINTER(EjoinPack), C.POINTER(EjoinResult)]
     L.ejoin_run_sharded.restype = C.c_int
+    L.ejoin_format_join_log.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.POINTER(EjoinEdge), C.POINTER(EjoinLogNames), C.c_char_p,
+                                        C.c_size_t, C.POINTER(C.c_size_t)]
+    L.ejoin_format_join_log.restype = C.c_int
     L.ejoin_p1.argtypes = [C.c_uint32] * 3
     L.ejoin_p1.restype = C.c_double
     _lib = L

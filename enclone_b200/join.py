@@ -224,6 +224,28 @@ class CompactPack:
             pass
 
 
+def format_join_log(pack_struct, params, edge, **names):
+    """JoinInfo.log of one emitted join (ejoin_format_join_log): `edge` is an EjoinEdge or one row of JoinResult.edges;
+    names: index, id1, id2, vsegs1, vsegs2, dataset1, dataset2, cdr3_aa1, cdr3_aa2, bcs1, bcs2."""
+    from ._abi import EjoinLogNames
+    L = _lib.load()
+    if not isinstance(edge, EjoinEdge):
+        e = EjoinEdge.from_buffer_copy(np.asarray(edge).tobytes())
+    else:
+        e = edge
+    nm = EjoinLogNames()
+    nm.index = int(names.get("index", 0))
+    for k in ("id1", "id2", "vsegs1", "vsegs2", "dataset1", "dataset2", "cdr3_aa1", "cdr3_aa2", "bcs1", "bcs2"):
+        setattr(nm, k, str(names.get(k, "")).encode())
+    n = C.c_size_t()
+    rc = L.ejoin_format_join_log(C.byref(pack_struct), C.byref(params), C.byref(e), C.byref(nm), None, 0, C.byref(n))
+    if rc != 0:
+        raise _lib.EjoinError(rc, "ejoin_format_join_log")
+    buf = C.create_string_buffer(n.value + 1)
+    L.ejoin_format_join_log(C.byref(pack_struct), C.byref(params), C.byref(e), C.byref(nm), buf, n.value + 1, C.byref(n))
+    return buf.value.decode("utf-8")
+
+
 def comm_id():
     """A fresh communicator id (rank 0 calls this; ejoin_comm_id)."""
     buf = C.create_string_buffer(128)

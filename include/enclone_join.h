@@ -304,6 +304,22 @@ void  ejoin_host_free(void *p);
 int   ejoin_host_register(void *p, size_t bytes);
 int   ejoin_host_unregister(void *p);
 
+/* JoinInfo.log of one emitted join (enclone_tail/src/group.rs:70-74,434-441): the text block enclone prints under
+ * PRINT_JOINS-style options, rebuilt from the edge record and the caller's inputs; golden:
+ * enclone_exec/testx/inputs/outputs/enclone_test256_output:29-70, reproduced byte for byte by tests/test_join_log.py.
+ * share_pos_v / share_pos_j are recomputed on the host for that one edge.  `names` carries the strings only the caller
+ * has.  Writes at most cap-1 bytes + NUL; *len = full length.  Host code: needs no GPU and no handle. */
+typedef struct ejoin_log_names {
+    int32_t index;               /* "[0] = ..."                                                  */
+    const char *id1, *id2;       /* "<dataset>.clono<exact id>" of the two entries               */
+    const char *vsegs1, *vsegs2; /* "107=ENST00000632630, 219=ENST00000632910"                   */
+    const char *dataset1, *dataset2; /* "flaky8b = flaky8b"                                      */
+    const char *cdr3_aa1, *cdr3_aa2; /* "IGK:CMQSTHWPTWTF;IGH:CAFDFW"                            */
+    const char *bcs1, *bcs2;     /* barcodes, comma separated                                    */
+} ejoin_log_names_t;
+int  ejoin_format_join_log(const ejoin_pack_t *pack, const ejoin_params_t *params, const ejoin_edge_t *edge,
+                           const ejoin_log_names_t *names, char *buf, size_t cap, size_t *len);
+
 /* The probability table entry the device uses: P(at most k-d distinct values in k
  * draws with replacement from n) — exposed so tests can pin it to the known-answer
  * vector (enclone_exec/testx/inputs/outputs/enclone_test256_output:55-56). */

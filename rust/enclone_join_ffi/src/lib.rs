@@ -77,6 +77,13 @@ pub struct ejoin_result_t {
 }
 
 #[repr(C)]
+pub struct ejoin_log_names_t {
+    pub index: i32, pub id1: *const c_char, pub id2: *const c_char, pub vsegs1: *const c_char, pub vsegs2: *const c_char,
+    pub dataset1: *const c_char, pub dataset2: *const c_char, pub cdr3_aa1: *const c_char, pub cdr3_aa2: *const c_char,
+    pub bcs1: *const c_char, pub bcs2: *const c_char,
+}
+
+#[repr(C)]
 #[derive(Clone, Copy)]
 pub struct ejoin_raw_edge_t { pub k1: u32, pub k2: u32, pub cd: u16, pub d: u16, pub flags: u32 }
 
@@ -110,6 +117,8 @@ extern "C" {
     pub fn ejoin_comm_id(id: *mut u8) -> c_int;
     pub fn ejoin_comm_init(h: *mut c_void, id: *const u8, rank: c_int, world: c_int) -> c_int;
     pub fn ejoin_run_sharded(h: *mut c_void, pack: *const ejoin_pack_t, out: *mut ejoin_result_t) -> c_int;
+    pub fn ejoin_format_join_log(pack: *const ejoin_pack_t, params: *const ejoin_params_t, edge: *const ejoin_edge_t, names: *const ejoin_log_names_t,
+                                 buf: *mut c_char, cap: usize, len: *mut usize) -> c_int;
     pub fn ejoin_p1(k: u32, d: u32, n: u32) -> f64;
 }
 // The safe wrapper `join_exacts(..) -> EquivRel` with `Flat::pack` is sketched in INTEGRATION.md §1-§3;

@@ -120,6 +120,11 @@ def main():
     out = dict(source="enclone_test256_output + flaky8a/flaky8b all_contig_annotations.json",
                k1=c1, k2=c2, germline=germ, regions=regions, expected=exp)
     json.dump(out, open(os.path.join(HERE, "kat256.json"), "w"), indent=1)
+    # the join's log block, verbatim (ANSI stripped): "JOIN ERROR" .. last line of "difference pattern for chain 2"
+    lines = gold.split("\n")
+    i0 = lines.index("JOIN ERROR")
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith("chain 1, tig 1"))
+    open(os.path.join(HERE, "kat256_join_log.txt"), "w").write("\n".join(lines[i0:i1]) + "\n")
     print("wrote kat256.json; n =", 3 * (len(c1["heavy"]["seq"]) + len(c1["light"]["seq"])))
 
 
