@@ -157,20 +157,34 @@ template <typename F> void parallel_for(uint32_t n, int threads, F f) {      // 
 struct Flat {
     ejoin_pack_t pk;
     bool pinned = false;
-    std::vector<void *> owned;
     std::vector<uint32_t> exact_id, nchains, ncells, dlo, dhi, c3off, ref_len;
     std::vector<uint16_t> len[2], cdr3_len[2];
     std::vector<uint64_t> ref_off;
     std::string ref_arena;
-    ~Flat() { for (void *p : owned) { if (pinned) ejoin_host_free(p); else free(p); } }
+    // Pinned buffers are expensive to create (cudaMallocHost: ~0.6 ms per MB) and cheap to keep: they go back to a
+    // process-wide pool instead of the driver, so only the first join of a process pays for them.
+    struct Pool { std::vector<std::pair<void *, size_t>> free_list; ~Pool() { for (auto &b : free_list) ejoin_host_free(b.first); } };
+    static Pool &pool() { static Pool p; return p; }
+    std::vector<std::pair<void *, size_t>> owned_sz;
+    ~Flat() {
+        for (auto &b : owned_sz) { if (pinned) pool().free_list.push_back(b); else free(b.first); }
+    }
     void *alloc(size_t bytes) {
-        void *p = pinned ? ejoin_host_alloc(bytes) : nullptr;
+        void *p = nullptr;
+        size_t got = bytes;
+        if (pinned) {
+            auto &fl = pool().free_list;
+            size_t best = fl.size();
+            for (size_t i = 0; i < fl.size(); i++) if (fl[i].second >= bytes && (best == fl.size() || fl[i].second < fl[best].second)) best = i;
+            if (best < fl.size()) { p = fl[best].first; got = fl[best].second; fl.erase(fl.begin() + best); }
+            else p = ejoin_host_alloc(bytes);
+        }
         if (!p) {
-            if (pinned && !owned.empty()) throw std::runtime_error("pinned allocation failed");
+            if (pinned && !owned_sz.empty()) throw std::runtime_error("pinned allocation failed");
             pinned = false;
             if (posix_memalign(&p, 4096, (bytes + 4095) & ~(size_t)4095) != 0) throw std::bad_alloc();
         }
-        owned.push_back(p);
+        owned_sz.emplace_back(p, got);
         return p;
     }
 };
@@ -230,27 +244,46 @@ inline void pack(Flat &F, bool is_bcr, const RefData &refdata, const std::vector
     uint64_t *c3w = (uint64_t *)F.alloc(8 * (total.c3words + 16));
     memset(tig2 + total.words, 0, 128); memset(ascii + total.abytes, 0, 128); memset(c3w + total.c3words, 0, 128);
     // ---- pass 2 (parallel): arenas and records; germline strings and V names interned per thread
-    struct Local { std::vector<std::string_view> seqs; std::unordered_map<std::string_view, uint32_t> seq_index;
-                   std::vector<std::string> names; std::unordered_map<std::string, uint32_t> name_index; bool bad_cdr3 = false, big_id = false; };
+    // Germline strings are interned by content (every CloneInfo owns its own copy of vs / js), but found through a cheap
+    // key — length and 24 sampled bytes — and confirmed with one memcmp, instead of hashing ~1.4 KB of text per entry;
+    // refdata.refs / refdata.name are interned by index.
+    struct Local { std::vector<std::string_view> seqs; std::unordered_map<uint64_t, std::vector<uint32_t>> seq_index;
+                   std::vector<std::string> names; std::unordered_map<std::string, uint32_t> name_index;
+                   std::vector<int32_t> ref_cache, name_cache; bool bad_cdr3 = false, big_id = false; };
     std::vector<Local> loc(T);
     parallel_for(n, T, [&](int t, uint32_t a, uint32_t b) {
         Local &L = loc[t];
+        L.ref_cache.assign(refdata.refs.size(), -1); L.name_cache.assign(refdata.name.size(), -1);
         auto intern = [&](const std::string &s) -> uint32_t {
-            std::string_view v(s);
-            auto it = L.seq_index.find(v);
-            if (it != L.seq_index.end()) return it->second;
+            const std::string_view v(s);
+            uint64_t key = v.size() * 0x9E3779B97F4A7C15ull;
+            if (v.size() >= 8) {
+                uint64_t x0, x1, x2;
+                memcpy(&x0, v.data(), 8); memcpy(&x1, v.data() + v.size() / 2 - 4, 8); memcpy(&x2, v.data() + v.size() - 8, 8);
+                key ^= x0 * 0xBF58476D1CE4E5B9ull ^ (x1 * 0x94D049BB133111EBull + (x2 << 7));
+            }
+            auto &cand = L.seq_index[key];
+            for (uint32_t id : cand) if (L.seqs[id] == v) return id;
             const uint32_t id = (uint32_t)L.seqs.size();
-            L.seqs.push_back(v); L.seq_index.emplace(v, id);
+            L.seqs.push_back(v); cand.push_back(id);
             return id;
         };
+        auto intern_ref = [&](size_t ref_id) -> uint32_t {
+            int32_t &slot = L.ref_cache.at(ref_id);
+            if (slot < 0) slot = (int32_t)intern(refdata.refs[ref_id]);
+            return (uint32_t)slot;
+        };
         auto vname = [&](size_t v_ref_id) -> uint32_t {
-            std::string s = refdata.name.at(v_ref_id);
+            int32_t &slot = L.name_cache.at(v_ref_id);
+            if (slot >= 0) return (uint32_t)slot;
+            std::string s = refdata.name[v_ref_id];
             const auto p = s.find('*');
             if (p != std::string::npos) s.resize(p);
             auto it = L.name_index.find(s);
-            if (it != L.name_index.end()) return it->second;
-            const uint32_t id = (uint32_t)L.names.size();
-            L.names.push_back(s); L.name_index.emplace(s, id);
+            uint32_t id;
+            if (it != L.name_index.end()) id = it->second;
+            else { id = (uint32_t)L.names.size(); L.names.push_back(s); L.name_index.emplace(s, id); }
+            slot = (int32_t)id;
             return id;
         };
         auto id16 = [&](int64_t v) -> uint16_t { if (v < 0) return 0xFFFF; if (v >= 0xFFFF) L.big_id = true; return (uint16_t)v; };
@@ -291,8 +324,8 @@ inline void pack(Flat &F, bool is_bcr, const RefData &refdata, const std::vector
                 r.cdr3_start[c] = (uint16_t)td.cdr3_start;
                 r.v_ref_id[c] = id16((int64_t)ci.vsids[c]); r.j_ref_id[c] = id16((int64_t)ci.jsids[c]); r.dref_id[c] = id16(ci.dref[c]);
                 r.vs_seq[c] = (uint16_t)intern(ci.vs[c]); r.js_seq[c] = (uint16_t)intern(ci.js[c]);       // thread-local ids, remapped below
-                r.vname_id[c] = (uint16_t)vname(ci.vsids[c]); r.vuni_seq[c] = (uint16_t)intern(refdata.refs.at(ci.vsids[c]));
-                r.utr_seq[c] = td.u_ref_id < 0 ? (uint16_t)0xFFFF : (uint16_t)intern(refdata.refs.at((size_t)td.u_ref_id));
+                r.vname_id[c] = (uint16_t)vname(ci.vsids[c]); r.vuni_seq[c] = (uint16_t)intern_ref(ci.vsids[c]);
+                r.utr_seq[c] = td.u_ref_id < 0 ? (uint16_t)0xFFFF : (uint16_t)intern_ref((size_t)td.u_ref_id);
                 if (c == 0) {
                     r.hcomp = (uint16_t)td.jun.hcomp; r.fr1_start = opt16(td.fr1_start); r.cdr1_start = opt16(td.cdr1_start);
                     r.fr2_start = opt16(td.fr2_start); r.cdr2_start = opt16(td.cdr2_start); r.fr3_start = opt16(td.fr3_start);

@@ -541,7 +541,7 @@ def test_compact_full_size_c3():
     cp.close()
 
 
-@pytest.mark.parametrize("name,scale,stride,compact", [("C3", 0.05, 0, 1), ("C3", 0.05, 0, 0), ("C4", 0.05, 1, 1), ("C5", 0.05, 0, 1)])
+@pytest.mark.parametrize("name,scale,stride,compact", [("C3", 0.2, 0, 1), ("C3", 0.2, 0, 0), ("C4", 0.05, 1, 1), ("C3", 0.05, 1, 0), ("C5", 0.05, 0, 1)])
 def test_two_rank_nccl_sharded_join(name, scale, stride, compact):
     """Real NCCL, one process per GPU (torchrun, 2 ranks): contiguous bucket ranges and the shared giant bucket (stride
     mode), the exchange inside the library; rank 0 checks the gathered result against the one-GPU join and the oracle."""
