@@ -127,11 +127,13 @@ struct ejoin_handle {
     int is_bcr = 1;
     int tables_is_bcr = -1;
     int sm_count = 148;
+    int bor_grid = 0;          // cooperative grid of k_boruvka
     // resident input + work buffers
     Arena in_arena, work;
     DevIn din;
     uint32_t n = 0;            // entries uploaded
     uint32_t k_base = 0;       // info index of uploaded entry 0
+    RangeTab rt;               // the uploaded entry ranges: local index <-> info index
     uint64_t tig_bytes = 0;
     uint64_t h2d_bytes = 0;
     bool uploaded = false;
@@ -383,47 +385,72 @@ int check_pack(ejoin_handle *h, const ejoin_pack_t *pk) {
     return 0;
 }
 
-// H2D of the entries [lo,hi) (whole arrays for the per-exact and germline tables).
-int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t hi, bool allow_in_place = true) {
+// H2D of this rank's entries: one or several ascending entry ranges [lo,hi) (whole arrays for the per-exact and germline
+// tables).  Per-entry arrays are concatenated (local index = position in that concatenation, h->rt maps it back to the info
+// index); the arenas keep the caller's offsets: a device buffer spans from the first to the last referenced byte and only
+// the owned slices are copied into it.
+typedef std::vector<std::pair<uint32_t, uint32_t>> Ranges;
+int upload_ranges(ejoin_handle *h, const ejoin_pack_t *pk, const Ranges &rg_in, bool allow_in_place = true) {
     int rc = check_pack(h, pk);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
-    const uint32_t n = hi - lo;
+    Ranges rg;
+    for (auto &r : rg_in) if (r.second > r.first) rg.push_back(r);
+    if (rg.size() > EJOIN_MAX_RANGES) return fail(h, EJOIN_E_ARG, "too many entry ranges");
+    uint32_t n = 0;
+    RangeTab &rt = h->rt;
+    memset(&rt, 0, sizeof(rt));
+    for (auto &r : rg) { rt.lo[rt.n] = r.first; rt.base[rt.n] = n; rt.n++; n += r.second - r.first; }
+    const bool everything = rg.size() == 1 && rg[0].first == 0 && rg[0].second == pk->n_info;
     const bool two_bit = pk->flags & EJOIN_F_TIGS_2BIT, recs = pk->flags & EJOIN_F_ENTRY_RECS, c2 = pk->flags & EJOIN_F_CDR3_2BIT;
     auto tig_off_of = [&](int c, uint32_t k) -> uint64_t { return recs ? (uint64_t)pk->entry_rec[k].tig_off[c] : pk->tig_off[c][k]; };
     auto has_del_of = [&](int c, uint32_t k) -> bool { return recs ? pk->entry_rec[k].has_del[c] != 0 : pk->has_del[c][k] != 0; };
-    // arena slices actually referenced by [lo,hi): ASCII bytes [tlo,thi), 2-bit words [wlo,whi), CDR3 bytes [clo,chi).
-    // In 2-bit mode the ASCII arena only holds the few chains with a deletion marker: it goes up whole.
-    // (with EJOIN_F_CDR3_2BIT, [clo,chi) counts 8-byte words of cdr3_2bit)
+    // arena slices referenced by each range: ASCII bytes [tlo,thi), 2-bit words [wlo,whi), CDR3 bytes or words [clo,chi);
+    // the unsuffixed variables are the spans over all ranges.  In 2-bit mode the ASCII arena only holds the few chains
+    // with a deletion marker: it goes up whole.
+    struct Slice { uint64_t tlo, thi, clo, chi, wlo, whi; };
+    std::vector<Slice> sl(rg.size());
     uint64_t tlo = 0, thi = pk->tig_arena_bytes, clo = 0, chi = c2 ? pk->cdr3_2bit_words : pk->cdr3_arena_bytes, wlo = 0, whi = two_bit ? pk->tig2_arena_words : 0;
-    if ((lo != 0 || hi != pk->n_info) && n > 0) {
-        // A shard's slices are read off its first and last entries: the arenas must be laid out in entry order (offsets
+    if (everything) sl[0] = Slice{ tlo, thi, clo, chi, wlo, whi };
+    else if (n == 0) { clo = chi = wlo = whi = 0; if (!two_bit) tlo = thi = 0; }
+    else {
+        // A range's slices are read off its first and last entries: the arenas must be laid out in entry order (offsets
         // non-decreasing in k, as every packer writes them; include/enclone_join.h).  The kernels check each entry against
-        // the slice (ERR_ARENA_RANGE -> EJOIN_E_ARG) instead of the host walking 10^6 entries per call.
-        if (!two_bit) { tlo = ~0ull; thi = 0; }
-        clo = ~0ull; chi = 0; wlo = ~0ull; whi = 0;
-        auto visit = [&](uint32_t k) {
-            for (int c = 0; c < 2; c++) {
-                uint64_t o = tig_off_of(c, k), e;
-                if (two_bit && !has_del_of(c, k)) { e = o + (pk->len[c][k] + 31) / 32; wlo = std::min(wlo, o); whi = std::max(whi, e); }
-                else if (!two_bit) { e = o + pk->len[c][k]; tlo = std::min(tlo, o); thi = std::max(thi, e); }
-                if (!c2) { o = pk->cdr3_off[c][k]; e = o + pk->cdr3_len[c][k]; clo = std::min(clo, o); chi = std::max(chi, e); }
+        // the span (ERR_ARENA_RANGE -> EJOIN_E_ARG) instead of the host walking 10^6 entries per call.
+        for (size_t ri = 0; ri < rg.size(); ri++) {
+            Slice x{ ~0ull, 0, ~0ull, 0, ~0ull, 0 };
+            auto visit = [&](uint32_t k) {
+                for (int c = 0; c < 2; c++) {
+                    uint64_t o = tig_off_of(c, k), e;
+                    if (two_bit && !has_del_of(c, k)) { e = o + (pk->len[c][k] + 31) / 32; x.wlo = std::min(x.wlo, o); x.whi = std::max(x.whi, e); }
+                    else if (!two_bit) { e = o + pk->len[c][k]; x.tlo = std::min(x.tlo, o); x.thi = std::max(x.thi, e); }
+                    if (!c2) { o = pk->cdr3_off[c][k]; e = o + pk->cdr3_len[c][k]; x.clo = std::min(x.clo, o); x.chi = std::max(x.chi, e); }
+                }
+                if (c2) {
+                    const uint64_t o = pk->cdr3_2bit_off[k], e = o + ((uint64_t)pk->cdr3_len[0][k] + pk->cdr3_len[1][k] + 31) / 32;
+                    x.clo = std::min(x.clo, o); x.chi = std::max(x.chi, e);
+                }
+            };
+            auto plain2 = [&](uint32_t k) { return two_bit && ((pk->len[0][k] && !has_del_of(0, k)) || (pk->len[1][k] && !has_del_of(1, k))); };
+            uint32_t a = rg[ri].first, b = rg[ri].second - 1;
+            visit(a); visit(b);
+            if (two_bit) {          // the first / last entry that has a 2-bit chain (nearly always the end entries themselves)
+                while (a < b && !plain2(a)) visit(++a);
+                while (b > a && !plain2(b)) visit(--b);
             }
-            if (c2) {
-                const uint64_t o = pk->cdr3_2bit_off[k], e = o + ((uint64_t)pk->cdr3_len[0][k] + pk->cdr3_len[1][k] + 31) / 32;
-                clo = std::min(clo, o); chi = std::max(chi, e);
-            }
-        };
-        auto plain2 = [&](uint32_t k) { return two_bit && ((pk->len[0][k] && !has_del_of(0, k)) || (pk->len[1][k] && !has_del_of(1, k))); };
-        uint32_t a = lo, b = hi - 1;
-        visit(a); visit(b);
-        if (two_bit) {          // the first / last entry that has a 2-bit chain (nearly always lo and hi - 1 themselves)
-            while (a < b && !plain2(a)) visit(++a);
-            while (b > a && !plain2(b)) visit(--b);
+            if (x.chi < x.clo) x.clo = x.chi = 0;
+            if (x.whi <= x.wlo) x.wlo = x.whi = 0;
+            if (x.thi < x.tlo) x.tlo = x.thi = 0;
+            if (two_bit) { x.tlo = 0; x.thi = pk->tig_arena_bytes; }
+            sl[ri] = x;
         }
-        if (chi < clo) clo = chi = 0;
-        if (whi <= wlo) wlo = whi = 0;
-        if (thi < tlo) tlo = thi = 0;
+        auto span = [&](uint64_t Slice::*lo_m, uint64_t Slice::*hi_m, uint64_t &lo_o, uint64_t &hi_o) {
+            lo_o = ~0ull; hi_o = 0;
+            for (auto &x : sl) if (x.*hi_m > x.*lo_m) { lo_o = std::min(lo_o, x.*lo_m); hi_o = std::max(hi_o, x.*hi_m); }
+            if (hi_o <= lo_o) lo_o = hi_o = 0;
+        };
+        span(&Slice::clo, &Slice::chi, clo, chi); span(&Slice::wlo, &Slice::whi, wlo, whi);
+        if (!two_bit) span(&Slice::tlo, &Slice::thi, tlo, thi);
     }
     // zero-copy: the caller's arena is pinned, device-readable and padded (EJOIN_F_TIGS_IN_PLACE): k_pack_t2 (and, for
     // ASCII, the bytewise path through the mirror) reads it in place, and only the needed entries ever cross PCIe
@@ -466,19 +493,48 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
         bytes += count * sizeof(T);
         return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->st_copy);
     };
+    // a per-entry array: the owned ranges, concatenated
+    auto up_e = [&](auto *&dst, const auto *src_all) -> cudaError_t {
+        using T = std::remove_cv_t<std::remove_pointer_t<std::remove_reference_t<decltype(dst)>>>;
+        T *p = A.take<T>(n ? n : 1);
+        dst = p;
+        for (size_t ri = 0; ri < rg.size(); ri++) {
+            const size_t cnt = rg[ri].second - rg[ri].first;
+            bytes += cnt * sizeof(T);
+            cudaError_t e = cudaMemcpyAsync(p + rt.base[ri], src_all + rg[ri].first, cnt * sizeof(T), cudaMemcpyHostToDevice, h->st_copy);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    // an arena: a buffer over the span [lo,hi) (in elements of T), the owned slices copied to their own offsets
+    auto up_arena = [&](auto *&dst, const auto *src_all, uint64_t lo_, uint64_t hi_, uint64_t Slice::*lo_m, uint64_t Slice::*hi_m, size_t slack) -> cudaError_t {
+        using T = std::remove_cv_t<std::remove_pointer_t<std::remove_reference_t<decltype(dst)>>>;
+        T *p = A.take<T>(hi_ - lo_ + slack);
+        dst = p;
+        uint64_t done_hi = 0;
+        for (auto &x : sl) {
+            uint64_t a_ = std::max(x.*lo_m, done_hi), b_ = x.*hi_m;          // slices ascend; never copy an overlap twice
+            if (b_ <= a_) continue;
+            bytes += (b_ - a_) * sizeof(T);
+            cudaError_t e = cudaMemcpyAsync(p + (a_ - lo_), src_all + a_, (b_ - a_) * sizeof(T), cudaMemcpyHostToDevice, h->st_copy);
+            if (e != cudaSuccess) return e;
+            done_hi = b_;
+        }
+        return cudaSuccess;
+    };
     // the copy stream must not run ahead of the previous run's kernels that still read the old input
     CK(cudaStreamSynchronize(h->st));
     CK(cudaEventRecord(h->ev_copy0, h->st_copy));
     // early set: what the keys, the sort, the c3 rows and the sweep read
-    CK(up(d.exact_id, pk->exact_id + lo, n));
+    CK(up_e(d.exact_id, pk->exact_id));
     CK(up(d.nchains, pk->nchains, pk->n_exact));
     for (int c = 0; c < 2; c++) {
-        CK(up(d.len[c], pk->len[c] + lo, n));
-        CK(up(d.cdr3_len[c], pk->cdr3_len[c] + lo, n));
-        if (!c2) CK(up(d.cdr3_off[c], pk->cdr3_off[c] + lo, n));
+        CK(up_e(d.len[c], pk->len[c]));
+        CK(up_e(d.cdr3_len[c], pk->cdr3_len[c]));
+        if (!c2) CK(up_e(d.cdr3_off[c], pk->cdr3_off[c]));
     }
-    if (c2) { CK(up(d.cdr3_2bit_off, pk->cdr3_2bit_off + lo, n)); CK(up(d.cdr3_2bit, pk->cdr3_2bit + clo, chi - clo)); }
-    else CK(up(d.cdr3_arena, pk->cdr3_arena + clo, chi - clo));
+    if (c2) { CK(up_e(d.cdr3_2bit_off, pk->cdr3_2bit_off)); CK(up_arena(d.cdr3_2bit, pk->cdr3_2bit, clo, chi, &Slice::clo, &Slice::chi, 8)); }
+    else CK(up_arena(d.cdr3_arena, pk->cdr3_arena, clo, chi, &Slice::clo, &Slice::chi, 64));
     CK(cudaEventRecord(h->ev_early, h->st_copy));
     // late set: what k_meta and the scoring read; goes up while the sweep runs
     h->recs_pending = false;
@@ -486,7 +542,7 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
         // one 64-byte record per entry crosses PCIe; k_unpack_recs (first thing after the wait for the late set) widens it
         // into the parallel arrays the kernels read
         const ejoin_entry_rec_t *d_rec = nullptr;
-        CK(up(d_rec, pk->entry_rec + lo, n));
+        CK(up_e(d_rec, pk->entry_rec));
         RecOut &o = h->rec_out;
         auto carve = [&](auto *&dev_const, auto *&dev_mut) {
             using T = std::remove_pointer_t<std::remove_reference_t<decltype(dev_mut)>>;
@@ -503,22 +559,22 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
         h->d_rec = d_rec; h->recs_pending = true;
     } else {
         for (int c = 0; c < 2; c++) {
-            CK(up(d.tig_off[c], pk->tig_off[c] + lo, n));
-            CK(up(d.has_del[c], pk->has_del[c] + lo, n));
-            CK(up(d.cdr3_start[c], pk->cdr3_start[c] + lo, n));
-            CK(up(d.v_ref_id[c], pk->v_ref_id[c] + lo, n));
-            CK(up(d.j_ref_id[c], pk->j_ref_id[c] + lo, n));
-            CK(up(d.dref_id[c], pk->dref_id[c] + lo, n));
-            CK(up(d.vs_seq[c], pk->vs_seq[c] + lo, n));
-            CK(up(d.js_seq[c], pk->js_seq[c] + lo, n));
-            CK(up(d.vname_id[c], pk->vname_id[c] + lo, n));
-            CK(up(d.vuni_seq[c], pk->vuni_seq[c] + lo, n));
-            CK(up(d.utr_seq[c], pk->utr_seq[c] + lo, n));
+            CK(up_e(d.tig_off[c], pk->tig_off[c]));
+            CK(up_e(d.has_del[c], pk->has_del[c]));
+            CK(up_e(d.cdr3_start[c], pk->cdr3_start[c]));
+            CK(up_e(d.v_ref_id[c], pk->v_ref_id[c]));
+            CK(up_e(d.j_ref_id[c], pk->j_ref_id[c]));
+            CK(up_e(d.dref_id[c], pk->dref_id[c]));
+            CK(up_e(d.vs_seq[c], pk->vs_seq[c]));
+            CK(up_e(d.js_seq[c], pk->js_seq[c]));
+            CK(up_e(d.vname_id[c], pk->vname_id[c]));
+            CK(up_e(d.vuni_seq[c], pk->vuni_seq[c]));
+            CK(up_e(d.utr_seq[c], pk->utr_seq[c]));
         }
-        CK(up(d.c_ref_id_light, pk->c_ref_id_light + lo, n));
-        CK(up(d.hcomp, pk->hcomp + lo, n));
-        CK(up(d.fr1, pk->fr1_start + lo, n)); CK(up(d.cdr1, pk->cdr1_start + lo, n)); CK(up(d.fr2, pk->fr2_start + lo, n));
-        CK(up(d.cdr2, pk->cdr2_start + lo, n)); CK(up(d.fr3, pk->fr3_start + lo, n));
+        CK(up_e(d.c_ref_id_light, pk->c_ref_id_light));
+        CK(up_e(d.hcomp, pk->hcomp));
+        CK(up_e(d.fr1, pk->fr1_start)); CK(up_e(d.cdr1, pk->cdr1_start)); CK(up_e(d.fr2, pk->fr2_start));
+        CK(up_e(d.cdr2, pk->cdr2_start)); CK(up_e(d.fr3, pk->fr3_start));
     }
     CK(up(d.ncells, pk->ncells, pk->n_exact));
     CK(up(d.donor_lo, pk->donor_lo, pk->n_exact)); CK(up(d.donor_hi, pk->donor_hi, pk->n_exact));
@@ -546,8 +602,8 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
             d.tig2_src = (const uint64_t *)in_place_ptr;                 // k_pack_t2 pulls the needed entries' words over PCIe
             h->n_chunks = 0;
         } else {
-            uint64_t *w = A.take<uint64_t>(whi - wlo + 8);
-            if (whi > wlo) { CK(cudaMemcpyAsync(w, pk->tig2_arena + wlo, 8 * (whi - wlo), cudaMemcpyHostToDevice, h->st_copy)); bytes += 8 * (whi - wlo); }
+            const uint64_t *w = nullptr;
+            CK(up_arena(w, pk->tig2_arena, wlo, whi, &Slice::wlo, &Slice::whi, 8));
             d.tig2_src = w;
             h->n_chunks = 1; h->chunk_end[0] = ~0ull;
             CK(cudaEventRecord(h->ev_chunk[7], h->st_copy));
@@ -565,9 +621,20 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
         const uint64_t tb = thi - tlo;
         uint8_t *dst = A.take<uint8_t>(tb + 64);
         d.tig_arena = dst; d.tig_src = dst; d.tig_copy = nullptr;
-        const int nch = tb >= (32ull << 20) ? 8 : 1;
-        h->n_chunks = nch;
+        const int nch = sl.size() > 1 ? 0 : (tb >= (32ull << 20) ? 8 : 1);
+        h->n_chunks = nch ? nch : 1;
         uint64_t done = 0;
+        if (nch == 0) {          // several slices: each goes to its own offset; k_pack_t2 runs once when all have landed
+            uint64_t done_hi = 0;
+            for (auto &x : sl) {
+                const uint64_t a_ = std::max(x.tlo, done_hi), b_ = x.thi;
+                if (b_ <= a_) continue;
+                CK(cudaMemcpyAsync(dst + (a_ - tlo), pk->tig_arena + a_, b_ - a_, cudaMemcpyHostToDevice, h->st_copy));
+                bytes += b_ - a_; done_hi = b_;
+            }
+            h->chunk_end[0] = ~0ull;
+            CK(cudaEventRecord(h->ev_chunk[7], h->st_copy));
+        }
         for (int i = 0; i < nch; i++) {
             uint64_t end = i == nch - 1 ? tb : ((tb * (uint64_t)(i + 1) / nch) & ~(uint64_t)4095);
             if (end > done) CK(cudaMemcpyAsync(dst + done, pk->tig_arena + tlo + done, end - done, cudaMemcpyHostToDevice, h->st_copy));
@@ -575,7 +642,7 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
             h->chunk_end[i] = tlo + end;
             CK(cudaEventRecord(h->ev_chunk[i == nch - 1 ? 7 : i], h->st_copy));
         }
-        bytes += tb;
+        if (nch) bytes += tb;
         h->copy_pending = true;
     }
     // the offsets index the original arenas: rebase the device pointers instead of the offsets
@@ -583,8 +650,21 @@ int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t 
     if (d.tig2_src) d.tig2_src -= wlo;
     if (c2) d.cdr3_2bit -= clo; else d.cdr3_arena -= clo;
     d.tig_lo = tlo; d.tig_hi = thi; d.tig2_lo = wlo; d.tig2_hi = whi; d.cdr3_lo = clo; d.cdr3_hi = chi;
-    h->n = n; h->k_base = lo; h->tig_bytes = two_bit ? 32 * (whi - wlo) + (thi - tlo) : thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
+    h->n = n; h->k_base = rt.n ? rt.lo[0] : 0; h->tig_bytes = two_bit ? 32 * (whi - wlo) + (thi - tlo) : thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
     return 0;
+}
+
+int upload_range(ejoin_handle *h, const ejoin_pack_t *pk, uint32_t lo, uint32_t hi, bool allow_in_place = true) {
+    return upload_ranges(h, pk, Ranges{ { lo, hi } }, allow_in_place);
+}
+// local index (position in the concatenated ranges) <-> info index
+uint32_t host_to_global(const RangeTab &rt, uint32_t local) { uint32_t r = 0; while (r + 1 < rt.n && rt.base[r + 1] <= local) r++; return rt.lo[r] + (local - rt.base[r]); }
+bool host_to_local(const RangeTab &rt, uint32_t n, uint32_t g, uint32_t *local) {
+    for (uint32_t r = 0; r < rt.n; r++) {
+        const uint32_t cnt = (r + 1 < rt.n ? rt.base[r + 1] : n) - rt.base[r];
+        if (g >= rt.lo[r] && g - rt.lo[r] < cnt) { *local = rt.base[r] + (g - rt.lo[r]); return true; }
+    }
+    return false;
 }
 
 // Prepare p1 / mult / cdmax tables for what this input contains (one small D2H + sync).
@@ -871,7 +951,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, parent, 0);
         mark(h, "k_tier2_generic r1");
         k_forced_resolve<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, f0_key, f0_val);
-        for (int it = 0; it < 10; it++) k_root_jump<<<nb256, 256, 0, st>>>(parent, n);      // 4 hops each: covers chains up to 4^10
+        k_root_all<<<nb256, 256, 0, st>>>(parent, n);
         mark(h, "resolve + root jumps");
         // round 2: the other recorded survivors, scored only across trees
         k_round2_begin<<<1, 1, 0, st>>>(ctr);
@@ -881,20 +961,25 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, nullptr);
         mark(h, "k_tier2 r2");
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, nullptr, 1);
-        h->launches += 19;                          // phase B: split, 2 x (k_tier2, k_tier2_generic), resolve, 10 root jumps, round-2 begin, prune, cross
+        h->launches += 10;                          // phase B: split, 2 x (k_tier2, k_tier2_generic), resolve, roots, round-2 begin, prune, cross
         CK(cudaEventRecord(h->ev[4], st));
         mark(h, "k_tier2_generic r2");
         const bool device_final = stride == 1;      // stride mode: the forest needs every rank's edges -> host replay after the gather
         h->device_final = device_final;
         if (device_final) {
             k_fill_u64<<<nb256, 256, 0, st>>>(best, ~0ull, n);
-            for (int round = 0; round < 5; round++) {
-                k_bor_min<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, best, ends);
-                k_bor_select<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, parent, best, ends);
-                k_bor_reset<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, best, ends);
+            {   // all Boruvka rounds in one cooperative launch (grid = what is resident at once)
+                if (h->bor_grid == 0) {
+                    int occ = 1;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_boruvka, 256, 0);
+                    h->bor_grid = h->sm_count * std::max(1, std::min(occ, 4));
+                }
+                ejoin_raw_edge_t *a_acc = acc; DevCounters *a_ctr = ctr; unsigned long long a_cap = cap; const uint32_t *a_kts = k_to_s;
+                uint32_t *a_par = parent; unsigned long long *a_best = best; uint2 *a_ends = ends;
+                void *args[] = { &a_acc, &a_ctr, &a_cap, &a_kts, &a_par, &a_best, &a_ends };
+                CK(cudaLaunchCooperativeKernel((void *)k_boruvka, dim3(h->bor_grid), dim3(256), args, 0, st));
             }
-            k_bor_min<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, best, ends);   // leaves bor_active = 1 iff edges still cross
-            h->launches += 17;
+            h->launches += 2;
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
@@ -918,14 +1003,6 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             if (retry) continue;
         }
         if (device_final) {
-            for (int guard = 0; h->counters.bor_active && guard < 64; guard++) {     // rare: more than 5 rounds needed
-                k_bor_select<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, parent, best, ends);
-                k_bor_reset<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, best, ends);
-                k_bor_min<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent, best, ends);
-                h->launches += 3;
-                CK(cudaMemcpyAsync(&h->counters.bor_active, &ctr->bor_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-            }
             CK(cudaMemsetAsync(comp_size, 0, 4 * (size_t)n, st));
             k_comp_size<<<nb256, 256, 0, st>>>(parent, (uint32_t)h->counters.n_valid, comp_size);
             k_final_collect<<<h->sm_count * 8, 256, 0, st>>>(h->din, f0_key, f0_val, n, acc, ctr, cap, k_to_s, 0, parent, comp_size, pr.easy, pk_in, pv_in);
@@ -942,7 +1019,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         if (nk) {
             // keys are (k1 << 32 | k2) with k < n: only the bits that can differ are sorted
             int kb = 1;
-            while (kb < 32 && (1ull << kb) < (unsigned long long)n + h->k_base) kb++;
+            while (kb < 32 && (1ull << kb) < (unsigned long long)n) kb++;
             tb = cub_bytes;
             cub::DeviceRadixSort::SortPairs(cub_tmp, tb, pk_in, pk_out, pv_in, pv_out, (int)nk, 0, 32 + kb, st);
         }
@@ -1070,7 +1147,7 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
                 size_t pin_used, ejoin_result_t *out) {
     const size_t ne = d_keys ? ne_dev : pairs.size();
     const uint32_t n = h->n;
-    const bool whole = h->k_base == 0 && h->n == pk->n_info;
+    const bool whole = h->rt.n == 1 && h->rt.lo[0] == 0 && h->n == pk->n_info;
     const DevParams pr = dev_params(h->params, (int)pk->is_bcr);
     char *pin = (char *)h->pin;
     size_t off = (pin_used + 255) & ~(size_t)255;
@@ -1094,14 +1171,14 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
     DevCounters *ctr = (DevCounters *)h->d_counters.p;
     const double t_dev0 = now_ms();
     if (ne) {
-        if (d_keys) k_keys_to_pairs<<<(unsigned)((ne + 255) / 256), 256, 0, h->st>>>(d_keys, (uint32_t)ne, h->k_base, d_pairs);
+        if (d_keys) k_keys_to_pairs<<<(unsigned)((ne + 255) / 256), 256, 0, h->st>>>(d_keys, (uint32_t)ne, h->rt, d_pairs);
         else CK(cudaMemcpyAsync(d_pairs, pairs.data(), ne * sizeof(uint2), cudaMemcpyHostToDevice, h->st));
         DevTables tbs;
         tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
         tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
         CK(cudaMemsetAsync(&ctr->n_payload_slow, 0, sizeof(unsigned int), h->st));
-        k_payload_fast<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)ne, h->k_base, d_out, d_slow);
-        k_payload<<<h->sm_count * 4, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, d_slow, h->k_base, d_out);
+        k_payload_fast<<<h->sm_count * 8, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)ne, h->rt, h->n, d_out, d_slow);
+        k_payload<<<h->sm_count * 4, 128, 0, h->st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, d_slow, h->rt, h->n, d_out);
         h->launches += d_keys ? 3 : 2;               // (k_keys_to_pairs,) k_payload_fast, k_payload
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_edges, d_out, ne * sizeof(ejoin_edge_t), cudaMemcpyDeviceToHost, h->st));
@@ -1111,7 +1188,7 @@ int emit_result(ejoin_handle *h, const ejoin_pack_t *pk, const std::vector<uint2
         CK(cudaMemsetAsync(&ctr->n_classes, 0, sizeof(unsigned long long), h->st));
         k_uf_init<<<nbx, 256, 0, h->st>>>(d_label, n, d_first, pk->n_exact);
         k_uf_first<<<(n + 255) / 256, 256, 0, h->st>>>(h->din.exact_id, n, pk->n_exact, d_first);
-        k_uf_union<<<nbn, 256, 0, h->st>>>(d_label, d_pairs, (uint32_t)ne, h->k_base, h->din.exact_id, n, pk->n_exact, d_first);
+        k_uf_union<<<nbn, 256, 0, h->st>>>(d_label, d_pairs, (uint32_t)ne, 0, h->din.exact_id, n, pk->n_exact, d_first);
         k_uf_flatten<<<(n + 255) / 256, 256, 0, h->st>>>(d_label, n, ctr, d_label_out);
         h->launches += 4;
         CK(cudaGetLastError());
@@ -1139,13 +1216,13 @@ extern "C" int ejoin_upload(ejoin_handle_t *h, const ejoin_pack_t *pk) {
     return 0;
 }
 
-static bool shard_range(const ejoin_pack_t *pk, int rank, int world, uint32_t *lo_out, uint32_t *hi_out);
+static bool shard_plan(const ejoin_pack_t *pk, int rank, int world, Ranges &out);
 
 extern "C" int ejoin_upload_shard(ejoin_handle_t *h, const ejoin_pack_t *pk, int rank, int world) {
     if (!h || !pk || rank < 0 || rank >= world) return EJOIN_E_ARG;
-    uint32_t lo, hi;
-    const bool stride_mode = shard_range(pk, rank, world, &lo, &hi);
-    int rc = upload_range(h, pk, lo, hi, /*allow_in_place=*/false);
+    Ranges rg;
+    const bool stride_mode = shard_plan(pk, rank, world, rg);
+    int rc = upload_ranges(h, pk, rg, /*allow_in_place=*/false);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->st_copy));
     h->copy_pending = false;
@@ -1217,8 +1294,9 @@ extern "C" void ejoin_result_free(ejoin_result_t *r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Multi-GPU decomposition: contiguous, cost-balanced bucket ranges.
+// Multi-GPU decomposition: cost-balanced bucket ranges, dealt to the ranks in turn.
 // ---------------------------------------------------------------------------------------------
+#define SHARD_CHUNKS 4          // bucket ranges per rank
 // bucket starts (runs of equal lens) and their contiguous, cost-balanced owners; one pass over the lens arrays
 static void plan_buckets(const ejoin_pack_t *pk, int world, std::vector<uint32_t> &bs, std::vector<uint32_t> &owner) {
     bs.clear();
@@ -1239,16 +1317,22 @@ static void plan_buckets(const ejoin_pack_t *pk, int world, std::vector<uint32_t
     const uint32_t nb = (uint32_t)bs.size();
     bs.push_back(pk->n_info);
     owner.assign(nb, 0);
-    // cost = candidate pairs + a linear term for packing; contiguous split at equal prefix cost
+    // cost = candidate pairs + a linear term for packing.  The bucket list is cut into world * SHARD_CHUNKS contiguous
+    // chunks of equal prefix cost and the chunks are dealt to the ranks in turn: what the pair count cannot see — how many
+    // CDR3 survivors a bucket sends to the full scoring, which varies tenfold along the length axis (one contiguous eighth
+    // of the 1.6 M-cell repertoire held 55 % of all scored pairs) — is then spread over every rank.
+    int per_rank = SHARD_CHUNKS;
+    if (const char *e = getenv("EJOIN_SHARD_CHUNKS")) per_rank = std::max(1, std::min(EJOIN_MAX_RANGES, atoi(e)));
+    const int chunks = world * per_rank;
     double total = 0;
     for (uint32_t b = 0; b < nb; b++) { double m = bs[b + 1] - bs[b]; total += m * (m - 1) / 2 + 64.0 * m; }
     double acc = 0;
-    int r = 0;
+    int ch = 0;
     for (uint32_t b = 0; b < nb; b++) {
         const double m = bs[b + 1] - bs[b], cost = m * (m - 1) / 2 + 64.0 * m;
-        // move to the next rank when this bucket's midpoint passes the rank's boundary
-        while (r < world - 1 && acc + cost / 2 > total * (r + 1) / world) r++;
-        owner[b] = (uint32_t)r;
+        // move to the next chunk when this bucket's midpoint passes the chunk's boundary
+        while (ch < chunks - 1 && acc + cost / 2 > total * (ch + 1) / chunks) ch++;
+        owner[b] = (uint32_t)(ch % world);
         acc += cost;
     }
 }
@@ -1267,8 +1351,8 @@ extern "C" int ejoin_plan_shards(const ejoin_pack_t *pk, int world, uint32_t *ow
     return 0;
 }
 
-// this rank's share: a contiguous entry range [lo,hi), or (stride mode) everything and every world-th tile row
-static bool shard_range(const ejoin_pack_t *pk, int rank, int world, uint32_t *lo_out, uint32_t *hi_out) {
+// this rank's share: a few ascending entry ranges, or (stride mode) everything and every world-th tile row
+static bool shard_plan(const ejoin_pack_t *pk, int rank, int world, Ranges &out) {
     std::vector<uint32_t> owner, bstart;
     plan_buckets(pk, world, bstart, owner);
     const uint32_t nb = (uint32_t)owner.size();
@@ -1277,14 +1361,13 @@ static bool shard_range(const ejoin_pack_t *pk, int rank, int world, uint32_t *l
     double total = 0, biggest = 0;
     for (uint32_t b = 0; b < nb; b++) { double m = bstart[b + 1] - bstart[b]; double c = m * (m - 1) / 2; total += c; biggest = std::max(biggest, c); }
     const bool stride_mode = world > 1 && biggest > 1.25 * total / world;
-    uint32_t lo = 0, hi = pk->n_info;
-    if (!stride_mode && world > 1) {
-        lo = hi = 0;
-        bool any = false;
-        for (uint32_t b = 0; b < nb; b++)
-            if ((int)owner[b] == rank) { if (!any) { lo = bstart[b]; any = true; } hi = bstart[b + 1]; }
-    }
-    *lo_out = lo; *hi_out = hi;
+    out.clear();
+    if (stride_mode || world <= 1) { out.emplace_back(0u, pk->n_info); return stride_mode; }
+    for (uint32_t b = 0; b < nb; b++)
+        if ((int)owner[b] == rank) {
+            if (!out.empty() && out.back().second == bstart[b]) out.back().second = bstart[b + 1];
+            else out.emplace_back(bstart[b], bstart[b + 1]);
+        }
     return stride_mode;
 }
 
@@ -1295,10 +1378,10 @@ static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int
     memset(&h->stats, 0, sizeof(h->stats));
     h->launches = 0;
     const double t0 = now_ms();
-    uint32_t lo, hi;
-    const bool stride_mode = shard_range(pk, rank, world, &lo, &hi);
+    Ranges rg;
+    const bool stride_mode = shard_plan(pk, rank, world, rg);
     if (mode_out) *mode_out = stride_mode ? 1 : 0;
-    int rc = upload_range(h, pk, lo, hi);
+    int rc = upload_ranges(h, pk, rg);
     if (rc) return rc;
     h->is_bcr = (int)pk->is_bcr;
     const double t1 = now_ms();
@@ -1327,7 +1410,7 @@ static int run_shard_core(ejoin_handle *h, const ejoin_pack_t *pk, int rank, int
         }
         ejoin_raw_edge_t *e = (ejoin_raw_edge_t *)malloc(sizeof(ejoin_raw_edge_t) * (nk ? nk : 1));
         for (size_t i = 0; i < nk; i++) {
-            e[i].k1 = (uint32_t)(hk[i] >> 32) + lo; e[i].k2 = (uint32_t)hk[i] + lo;
+            e[i].k1 = host_to_global(h->rt, (uint32_t)(hk[i] >> 32)); e[i].k2 = host_to_global(h->rt, (uint32_t)hk[i]);
             e[i].cd = (uint16_t)(hv[i] & 0xFFFF); e[i].d = (uint16_t)((hv[i] >> 16) & 0xFFFF); e[i].flags = (uint32_t)(hv[i] >> 32);
         }
         if (edges) *edges = e; else free(e);
@@ -1408,12 +1491,12 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
     memset(&h->stats, 0, sizeof(h->stats));
     h->launches = 0;
     const double t0 = now_ms();
-    uint32_t lo, hi;
-    const bool stride_mode = shard_range(pk, rank, world, &lo, &hi);
-    int rc = upload_range(h, pk, lo, hi);
+    Ranges rg;
+    const bool stride_mode = shard_plan(pk, rank, world, rg);
+    int rc = upload_ranges(h, pk, rg);
     if (rc) return rc;
     const uint32_t n_all = pk->n_info;
-    const bool whole = lo == 0 && hi == n_all;
+    const bool whole = rg.size() == 1 && rg[0].first == 0 && rg[0].second == n_all;
     if (rank == root && !whole && n_all) {
         // finish_join runs over every info entry: rank 0 also takes the whole exact_id array (4 bytes per entry)
         CK(h->d_exact_all.ensure(4 * (size_t)n_all));
@@ -1499,10 +1582,10 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
             DevTables tbs;
             tbs.meta = h->meta; tbs.c3 = h->c3; tbs.t2 = h->t2; tbs.p1tab = (const double *const *)h->d_p1ptrs.p;
             tbs.multinfo = (const MultInfo *)h->d_multinfo.p; tbs.multpool = (const double *)h->d_multpool.p; tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
-            k_keys_to_pairs<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(h->kept_keys, (uint32_t)nk, h->k_base, d_pairs);
+            k_keys_to_pairs<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(h->kept_keys, (uint32_t)nk, h->rt, d_pairs);
             CK(cudaMemsetAsync(&ctr->n_payload_slow, 0, sizeof(unsigned int), st));
-            k_payload_fast<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)nk, h->k_base, d_out, d_slow);
-            k_payload<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, d_slow, h->k_base, d_out);
+            k_payload_fast<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, (uint32_t)nk, h->rt, h->n, d_out, d_slow);
+            k_payload<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, h->k_to_s, d_pairs, d_slow, h->rt, h->n, d_out);
             h->launches += 3;
             CK(cudaGetLastError());
         }
@@ -1510,10 +1593,25 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
         if (rc) { A.off = save; return rc; }
         size_t total = 0;
         for (int r = 0; r < world; r++) total += counts[r];
-        ejoin_edge_t *g_edges = nullptr;
+        ejoin_edge_t *g_edges = nullptr, *g_sorted = nullptr;
+        unsigned long long *sk_in = nullptr, *sk_out = nullptr;
+        uint32_t *si_in = nullptr, *si_out = nullptr;
+        void *g_cub = nullptr;
+        size_t g_cub_bytes = 0;
+        char *g_rest = nullptr;
         if (rank == root) {
-            CK(h->d_gather.ensure(sizeof(ejoin_edge_t) * (total + 1) + 8 * (total + 1) + 8 * (size_t)n_all + 4 * (size_t)std::max(1u, pk->n_exact) + 1024));
-            g_edges = (ejoin_edge_t *)h->d_gather.p;
+            cub::DeviceRadixSort::SortPairs(nullptr, g_cub_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                            (int)std::max<size_t>(total, 1));
+            const size_t te = total + 1;
+            CK(h->d_gather.ensure(2 * sizeof(ejoin_edge_t) * te + 2 * 8 * te + 2 * 4 * te + g_cub_bytes + 8 * te + 8 * (size_t)n_all +
+                                  4 * (size_t)std::max(1u, pk->n_exact) + 4096));
+            char *b = (char *)h->d_gather.p;
+            auto carve = [&](size_t bytes) { char *r = b; b += (bytes + 255) & ~(size_t)255; return r; };
+            g_edges = (ejoin_edge_t *)carve(sizeof(ejoin_edge_t) * te); g_sorted = (ejoin_edge_t *)carve(sizeof(ejoin_edge_t) * te);
+            sk_in = (unsigned long long *)carve(8 * te); sk_out = (unsigned long long *)carve(8 * te);
+            si_in = (uint32_t *)carve(4 * te); si_out = (uint32_t *)carve(4 * te);
+            g_cub = carve(g_cub_bytes);
+            g_rest = b;
         }
         NCK(nc->GroupStart());
         if (rank == root) {
@@ -1528,8 +1626,20 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
             size_t off = 0;
             for (int r = 0; r < root; r++) off += counts[r];
             if (nk) CK(cudaMemcpyAsync(g_edges + off, d_out, nk * sizeof(ejoin_edge_t), cudaMemcpyDeviceToDevice, st));
+            if (total && world > 1) {
+                // every rank's list is in raw_joins order; the ranks' bucket ranges interleave, so one sort by (k1,k2) orders the union
+                int kb = 1;
+                while (kb < 32 && (1ull << kb) < (unsigned long long)n_all) kb++;
+                k_edge_keys<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g_edges, (uint32_t)total, sk_in, si_in);
+                size_t tb = g_cub_bytes;
+                cub::DeviceRadixSort::SortPairs(g_cub, tb, sk_in, sk_out, si_in, si_out, (int)total, 0, 32 + kb, st);
+                const unsigned long long nthreads = (unsigned long long)total * (sizeof(ejoin_edge_t) / 8);
+                k_gather_edges<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(g_edges, si_out, (uint32_t)total, g_sorted);
+                h->launches += 2;
+                g_edges = g_sorted;
+            }
             // finish_join on the gathered records
-            char *base = (char *)(g_edges + total + 1);
+            char *base = g_rest;
             base = (char *)(((uintptr_t)base + 15) & ~(uintptr_t)15);
             uint2 *g_pairs = (uint2 *)base; base += 8 * (total + 1);
             uint32_t *d_label = (uint32_t *)base; base += 4 * (size_t)n_all;
@@ -1586,11 +1696,12 @@ extern "C" int ejoin_finish(ejoin_handle_t *h, const ejoin_pack_t *pk, const ejo
         if (!h->uploaded && n_edges) return fail(h, EJOIN_E_ARG, "ejoin_finish: the handle holds no upload");
         // every endpoint must lie in the range this handle holds ([k_base, k_base + n): everything in stride mode,
         // the rank's own buckets otherwise): the payload kernels index the resident rows by k - k_base
-        const uint64_t lo = h->k_base, hi = (uint64_t)h->k_base + h->n;
-        for (uint64_t i = 0; i < n_edges; i++)
-            if (edges[i].k1 >= edges[i].k2 || edges[i].k2 >= pk->n_info || edges[i].k1 < lo || edges[i].k2 >= hi)
+        for (uint64_t i = 0; i < n_edges; i++) {
+            uint32_t l1, l2;
+            if (edges[i].k1 >= edges[i].k2 || edges[i].k2 >= pk->n_info || !host_to_local(h->rt, h->n, edges[i].k1, &l1) || !host_to_local(h->rt, h->n, edges[i].k2, &l2))
                 return fail(h, EJOIN_E_ARG, "ejoin_finish: an edge endpoint lies outside the entries this handle holds "
                                             "(gather-then-finish needs stride mode or a handle holding the whole input)");
+        }
     }
     std::vector<std::pair<unsigned long long, unsigned long long>> kv(n_edges);
     for (uint64_t i = 0; i < n_edges; i++) {

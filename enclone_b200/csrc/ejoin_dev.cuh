@@ -101,6 +101,24 @@ struct DevParams {           // ejoin_params_t plus run constants, by value to k
     int max_diffs, max_diffs_tcr, ref_v_trim, ref_j_trim, old_light, mix_donors, is_bcr, easy, degradation_mode;
 };
 
+// The entries a handle holds: up to EJOIN_MAX_RANGES ascending ranges of info indices, concatenated.  local index i of
+// range r (base[r] <= i < base[r+1]) is info index lo[r] + (i - base[r]).
+#define EJOIN_MAX_RANGES 16
+struct RangeTab { uint32_t n; uint32_t lo[EJOIN_MAX_RANGES], base[EJOIN_MAX_RANGES]; };
+__host__ __device__ __forceinline__ uint32_t rt_to_global(const RangeTab &rt, uint32_t local) {
+    uint32_t r = 0;
+    while (r + 1 < rt.n && rt.base[r + 1] <= local) r++;
+    return rt.lo[r] + (local - rt.base[r]);
+}
+// info index -> local index (the index must belong to one of the ranges; n = total entries held)
+__host__ __device__ __forceinline__ uint32_t rt_to_local(const RangeTab &rt, uint32_t n, uint32_t g) {
+    for (uint32_t r = 0; r < rt.n; r++) {
+        const uint32_t cnt = (r + 1 < rt.n ? rt.base[r + 1] : n) - rt.base[r];
+        if (g >= rt.lo[r] && g - rt.lo[r] < cnt) return rt.base[r] + (g - rt.lo[r]);
+    }
+    return 0;
+}
+
 struct MultInfo { uint32_t off; uint32_t d1p1; };   // per (cl0,cl1): pool offset, row stride (D1+1); off = ~0 if absent
 
 // Raw input arrays as uploaded (same meaning as ejoin_pack_t)

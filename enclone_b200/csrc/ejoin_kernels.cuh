@@ -1,5 +1,6 @@
 // ejoin_kernels.cuh — the sm_100a kernels of the join path.  See ejoin_dev.cuh for layouts.
 #pragma once
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "ejoin_dev.cuh"
@@ -1288,10 +1289,10 @@ __device__ __forceinline__ void write_edge(ejoin_edge_t *out, uint32_t k1, uint3
 }
 
 __global__ void __launch_bounds__(128) k_payload_fast(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *k_to_s,
-                                                      const uint2 *pairs, uint32_t npairs, uint32_t k_base, ejoin_edge_t *out, uint32_t *slow_list) {
+                                                      const uint2 *pairs, uint32_t npairs, RangeTab rt, uint32_t n_held, ejoin_edge_t *out, uint32_t *slow_list) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
         const uint2 kk2 = pairs[i];
-        const EntryMeta &m1 = tb.meta[k_to_s[kk2.x - k_base]], &m2 = tb.meta[k_to_s[kk2.y - k_base]];
+        const EntryMeta &m1 = tb.meta[k_to_s[rt_to_local(rt, n_held, kk2.x)]], &m2 = tb.meta[k_to_s[rt_to_local(rt, n_held, kk2.y)]];
         const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] ||
                              m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
         if (generic) { slow_list[atomicAdd(&ctr->n_payload_slow, 1u)] = i; continue; }
@@ -1354,13 +1355,13 @@ __global__ void __launch_bounds__(128) k_payload_fast(DevIn in, DevTables tb, De
 }
 
 __global__ void __launch_bounds__(128) k_payload(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint32_t *k_to_s,
-                                                 const uint2 *pairs, const uint32_t *slow_list, uint32_t k_base, ejoin_edge_t *out) {
+                                                 const uint2 *pairs, const uint32_t *slow_list, RangeTab rt, uint32_t n_held, ejoin_edge_t *out) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nslow = ctr->n_payload_slow;
     for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < nslow; j += (gridDim.x * blockDim.x) >> 5) {
         const uint32_t i = slow_list[j];
         const uint2 kk2 = pairs[i];
-        const EntryMeta m1 = tb.meta[k_to_s[kk2.x - k_base]], m2 = tb.meta[k_to_s[kk2.y - k_base]];
+        const EntryMeta m1 = tb.meta[k_to_s[rt_to_local(rt, n_held, kk2.x)]], m2 = tb.meta[k_to_s[rt_to_local(rt, n_held, kk2.y)]];
         PairCounts pc;
         bytewise_counts(in, tb.t2, tb.c3, pr, m1, m2, pc);
         int kk = 0, d = 0, err = 0;
@@ -1407,13 +1408,14 @@ __global__ void k_init_rows(uint32_t *parent, unsigned long long *f0_key, uint32
     if (i < n) { parent[i] = i; f0_key[i] = ~0ull; cnt[i] = 0; needed[i] = needed_init; force[i] = 0; }
 }
 
-// pointer doubling over the phase-A parent pointers (parent[s] < s or == s)
-__global__ void k_root_jump(uint32_t *parent, uint32_t n) {
+// Every entry to its phase-A tree root, in one launch: parent[s] <= s always, roots never move while this runs, and a
+// concurrent store only replaces a pointer by another ancestor, so every walk ends at the root of its tree.  (Ten
+// launches of four hops each used to do this; chains are short — a child hangs off its SMALLEST accepted neighbour.)
+__global__ void k_root_all(uint32_t *parent, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t p = parent[i];
-#pragma unroll 1
-    for (int hop = 0; hop < 4; hop++) { uint32_t q = parent[p]; if (q == p) break; p = q; }
+    uint32_t p = __ldcg(&parent[i]);
+    for (;;) { const uint32_t q = __ldcg(&parent[p]); if (q == p) break; p = q; }
     parent[i] = p;
 }
 
@@ -1942,55 +1944,49 @@ __global__ void k_fill_u64(unsigned long long *p, unsigned long long v, size_t n
     if (i < n) p[i] = v;
 }
 
-__global__ void k_bor_min(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *k_to_s, uint32_t k_base,
-                          uint32_t *parent, unsigned long long *best, uint2 *ends) {
-    if (ctr->bor_done) return;                        // an earlier pass found the forest complete
+// All rounds in ONE cooperative launch, grid-wide barriers between the three steps of a round: (1) every live edge finds its two
+// components and bids for them (64-bit atomicMin of its (k1,k2) key); (2) the winning edges are selected and their components
+// merged; (3) the bids are cleared where they were placed.  Stops when a round finds no edge between two components.
+__global__ void __launch_bounds__(256) k_boruvka(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *k_to_s,
+                                                 uint32_t *parent, unsigned long long *best, uint2 *ends) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     unsigned long long n = ctr->n_accept;
     if (n > cap) n = cap;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const ejoin_raw_edge_t e = acc[i];
-        if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
-        const uint32_t ca = uf_find(parent, k_to_s[e.k1 - k_base]), cb = uf_find(parent, k_to_s[e.k2 - k_base]);
-        if (ca == cb) { acc[i].k1 = ACC_DEAD; continue; }       // both ends in one component: heaviest edge of a cycle
-        const unsigned long long key = ((unsigned long long)e.k1 << 32) | e.k2;
-        atomicMin(&best[ca], key);
-        atomicMin(&best[cb], key);
-        ends[i] = make_uint2(ca, cb);
-        ctr->bor_active = 1;
-    }
-}
-__global__ void k_bor_select(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, uint32_t *parent,
-                             const unsigned long long *best, const uint2 *ends) {
-    if (ctr->bor_done) return;
-    if (!ctr->bor_active) {                           // the k_bor_min pass before this one found nothing left to merge
-        if (blockIdx.x == 0 && threadIdx.x == 0) ctr->bor_done = 1;      // read by the NEXT kernels only (this one tests bor_active)
-        return;
-    }
-    unsigned long long n = ctr->n_accept;
-    if (n > cap) n = cap;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const ejoin_raw_edge_t e = acc[i];
-        if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
-        const uint2 c = ends[i];
-        const unsigned long long key = ((unsigned long long)e.k1 << 32) | e.k2;
-        if (best[c.x] == key || best[c.y] == key) {
-            acc[i].flags = e.flags | ACC_SELECTED;
-            uf_union(parent, c.x, c.y);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned int round = 1; round < 4096; round++) {
+        for (unsigned long long i = first; i < n; i += stride) {
+            const ejoin_raw_edge_t e = acc[i];
+            if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
+            const uint32_t ca = uf_find(parent, k_to_s[e.k1]), cb = uf_find(parent, k_to_s[e.k2]);
+            if (ca == cb) { acc[i].k1 = ACC_DEAD; continue; }       // both ends in one component: heaviest edge of a cycle
+            const unsigned long long key = ((unsigned long long)e.k1 << 32) | e.k2;
+            atomicMin(&best[ca], key);
+            atomicMin(&best[cb], key);
+            ends[i] = make_uint2(ca, cb);
+            *(volatile unsigned int *)&ctr->bor_active = round;
         }
+        grid.sync();
+        if (*(volatile unsigned int *)&ctr->bor_active != round) break;      // nothing left to merge (same answer in every thread)
+        for (unsigned long long i = first; i < n; i += stride) {
+            const ejoin_raw_edge_t e = acc[i];
+            if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
+            const uint2 c = ends[i];
+            const unsigned long long key = ((unsigned long long)e.k1 << 32) | e.k2;
+            if (best[c.x] == key || best[c.y] == key) {
+                acc[i].flags = e.flags | ACC_SELECTED;
+                uf_union(parent, c.x, c.y);
+            }
+        }
+        grid.sync();
+        for (unsigned long long i = first; i < n; i += stride) {
+            const ejoin_raw_edge_t e = acc[i];
+            if (e.k1 == ACC_DEAD) continue;
+            const uint2 c = ends[i];
+            best[c.x] = ~0ull; best[c.y] = ~0ull;
+        }
+        grid.sync();
     }
-}
-// reset `best` only where it was touched
-__global__ void k_bor_reset(const ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, unsigned long long *best, const uint2 *ends) {
-    if (ctr->bor_done) return;
-    unsigned long long n = ctr->n_accept;
-    if (n > cap) n = cap;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const ejoin_raw_edge_t e = acc[i];
-        if (e.k1 == ACC_DEAD) continue;
-        const uint2 c = ends[i];
-        best[c.x] = ~0ull; best[c.y] = ~0ull;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->bor_active = 0;
+    if (first == 0) ctr->bor_active = 0;
 }
 __global__ void k_comp_size(uint32_t *parent, uint32_t n_valid, uint32_t *size) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2032,11 +2028,23 @@ __global__ void __launch_bounds__(256) k_final_collect(DevIn in, const unsigned 
         if (key != ~0ull && o1 < cap) { keys[o1] = key; vals[o1] = val; }
     }
 }
-__global__ void k_keys_to_pairs(const unsigned long long *keys, uint32_t ne, uint32_t k_base, uint2 *pairs) {
+__global__ void k_keys_to_pairs(const unsigned long long *keys, uint32_t ne, RangeTab rt, uint2 *pairs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ne) pairs[i] = make_uint2((uint32_t)(keys[i] >> 32) + k_base, (uint32_t)keys[i] + k_base);   // local -> info indices
+    if (i < ne) pairs[i] = make_uint2(rt_to_global(rt, (uint32_t)(keys[i] >> 32)), rt_to_global(rt, (uint32_t)keys[i]));   // local -> info indices
 }
 __global__ void k_edge_pairs(const ejoin_edge_t *edges, uint32_t ne, uint2 *pairs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ne) pairs[i] = make_uint2(edges[i].k1, edges[i].k2);
+}
+// rank 0 after the gather: the ranks' lists are each in raw_joins order, their union is put in order by one key sort
+__global__ void k_edge_keys(const ejoin_edge_t *edges, uint32_t ne, unsigned long long *keys, uint32_t *idx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ne) { keys[i] = ((unsigned long long)edges[i].k1 << 32) | edges[i].k2; idx[i] = i; }
+}
+__global__ void k_gather_edges(const ejoin_edge_t *src, const uint32_t *idx, uint32_t ne, ejoin_edge_t *dst) {
+    static_assert(sizeof(ejoin_edge_t) % 8 == 0, "ejoin_edge_t is moved as 8-byte words");
+    const uint32_t W = sizeof(ejoin_edge_t) / 8;
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long i = t / W, w = t % W;
+    if (i < ne) ((unsigned long long *)(dst + i))[w] = ((const unsigned long long *)(src + idx[i]))[w];
 }

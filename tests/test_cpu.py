@@ -79,12 +79,18 @@ def test_generator_is_deterministic_and_sorted():
         assert tigs == sorted(tigs)
 
 
-def test_plan_shards_is_contiguous_and_balanced():
+def test_plan_shards_deals_balanced_chunks():
     pack, _ = synth.generate(n_cells=30000, n_donors=2, seed=4)
+    l0, l1 = pack.arrays["len"][0].astype(np.int64), pack.arrays["len"][1].astype(np.int64)
+    true_starts = np.concatenate([[0], np.flatnonzero(np.diff(l0 * 65536 + l1) != 0) + 1, [pack.n_info]])
     for world in (1, 2, 4, 8):
         owner, bstart = plan_shards(pack.struct, world)
         assert len(owner) == len(bstart) - 1 and bstart[0] == 0 and bstart[-1] == pack.n_info
-        assert (np.diff(owner.astype(np.int64)) >= 0).all() and owner.max() <= world - 1
+        assert np.array_equal(bstart, true_starts)                 # the galloping scan finds every run of equal lens
+        assert owner.max() <= world - 1
+        # each rank owns at most SHARD_CHUNKS (4) runs of consecutive buckets, dealt in turn
+        runs = 1 + int((np.diff(owner.astype(np.int64)) != 0).sum())
+        assert runs <= 4 * world
         sz = np.diff(bstart).astype(np.float64)
         cost = sz * (sz - 1) / 2 + 64 * sz
         per = np.bincount(owner, weights=cost, minlength=world)

@@ -26,8 +26,13 @@ def _worker(rank, world, port, out):
     mine = np.flatnonzero(owner == rank)
     edges = np.zeros((0, 2), np.uint32)
     if len(mine):
-        e, _, _ = O.join_exacts(pack.struct, default_params(), bucket_lo=int(mine[0]), bucket_hi=int(mine[-1]) + 1)
-        edges = np.stack([e["k1"], e["k2"]], axis=1).astype(np.uint32)
+        # the rank's buckets come as a few runs of consecutive buckets (chunks dealt in turn, ejoin_plan_shards)
+        cuts = np.flatnonzero(np.diff(mine) != 1) + 1
+        parts = []
+        for run in np.split(mine, cuts):
+            e, _, _ = O.join_exacts(pack.struct, default_params(), bucket_lo=int(run[0]), bucket_hi=int(run[-1]) + 1)
+            parts.append(np.stack([e["k1"], e["k2"]], axis=1).astype(np.uint32))
+        edges = np.concatenate(parts)
     allp, cls, ncls = merge_rank_edges(pack.struct, edges)
     if rank == 0:
         fe, fc, _ = O.join_exacts(pack.struct, default_params())
