@@ -148,6 +148,7 @@ struct ejoin_handle {
     std::vector<uint16_t> cdmax_host;
     std::vector<DevBuf> p1_tables;
     unsigned long long xrow_cap = 0;
+    uint32_t xrow_seg = 0;
     std::vector<uint32_t> ref_plane_off;   // host copy of DevIn::ref_plane_off (kept alive for the async upload)
     unsigned long long cand_cap = 0;    // survivor list (tier-1 survivors beyond the phase-A slots)
     unsigned long long edge_cap = 0;    // to-be-scored lists, accepted edges, sort arrays
@@ -770,7 +771,11 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     h->stats.ms_kernel_pack = h->stats.ms_kernel_tier1 = h->stats.ms_kernel_tier2 = h->stats.ms_kernel_other = 0;
     if (h->cand_cap == 0) h->cand_cap = std::max<unsigned long long>(1ull << 20, 48ull * n);
     if (h->edge_cap == 0) h->edge_cap = std::max<unsigned long long>(1ull << 20, 4ull * n);
-    if (h->xrow_cap == 0) h->xrow_cap = 1024 + n / T1_TILE;
+    // tier-1 segment length: shorter on small inputs (more, smaller work items: a rank's eighth of a join otherwise has fewer
+    // items than the GPU has CTA slots and the sweep's time is the time of its longest item)
+    uint32_t seg_min = n >= 1000000u ? SEG_MIN : (n >= 400000u ? 4u : 2u);
+    if (const char *e = getenv("EJOIN_SEG_MIN")) seg_min = (uint32_t)std::max(1, atoi(e));
+    if (h->xrow_cap == 0 || h->xrow_seg != seg_min) { h->xrow_cap = 1024 + (unsigned long long)(n / T1_TILE) * (16 / std::min(16u, seg_min)); h->xrow_seg = seg_min; }
     if (n == 0) return 0;
     for (int attempt = 0; attempt < 6; attempt++) {
         const unsigned long long ccap = h->cand_cap;
@@ -804,6 +809,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
         sz.take(8 * ccap); sz.take(8 * ccap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
         sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending
+        sz.take(sizeof(PendRes) * ((size_t)n / 8 + 1024) * PEND_SPEC);
         sz.take((size_t)n + 1024); sz.take(8 * ((size_t)n + 1024));                                           // work items: cost class, sorted list (items <= n)
         sz.take(4 * (size_t)xcap * PHASE_A_K * T1_TILE); sz.take(4 * (size_t)xcap * T1_TILE);                   // extra slot rows (segments q >= 1)
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
@@ -832,6 +838,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint32_t *firstk = A.take<uint32_t>((size_t)n * PHASE_A_K), *surv_cnt = A.take<uint32_t>(n);
         uint8_t *needed = A.take<uint8_t>(n), *force = A.take<uint8_t>(n);
         uint2 *pending = A.take<uint2>(n);
+        const uint32_t pend_cap = n / 8 + 1024;
+        PendRes *pend_res = A.take<PendRes>((size_t)pend_cap * PEND_SPEC);
         const uint32_t item_cap = n + 1024;
         uint8_t *item_cls = A.take<uint8_t>(item_cap);
         uint2 *order = A.take<uint2>(item_cap);
@@ -870,14 +878,14 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         mark(h, "sort entries");
         tb = cub_bytes;
         cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
-        k_group_vals<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, n, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, ctr);
+        k_group_vals<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, n, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, ctr, seg_min);
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumA, sumA, (int)n, st);
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumB, sumB, (int)n, st);
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumC, sumC, (int)n, st);
-        k_group_build<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, groups, ctr);
+        k_group_build<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, groups, ctr, seg_min);
         h->launches += 2;                           // k_group_vals, k_group_build (own kernels only: CUB's sort / RLE / scan passes are never counted)
         mark(h, "rle + group table");
         k_item_hist<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, item_cap, stride, phase);
@@ -939,9 +947,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sv.firstk = firstk; sv.cnt = surv_cnt; sv.xk = xk; sv.xcnt = xcnt; sv.gid_incl = gid; sv.groups = groups; sv.stride = stride; sv.phase = phase;
         k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
         mark(h, "k_phase_a");
-        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
+        k_pending_eval<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, pending, pend_res, pend_cap);
+        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending, pend_res, pend_cap);
         mark(h, "k_phase_a_pending");
-        h->launches += 7;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
+        h->launches += 8;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
         k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, ccap);
@@ -972,7 +981,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
                 if (h->bor_grid == 0) {
                     int occ = 1;
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_boruvka, 256, 0);
-                    h->bor_grid = h->sm_count * std::max(1, std::min(occ, 4));
+                    h->bor_grid = occ >= 1 ? h->sm_count : 1;          // one CTA per SM: the grid-wide barriers are the cost, not the edge loop
                 }
                 ejoin_raw_edge_t *a_acc = acc; DevCounters *a_ctr = ctr; unsigned long long a_cap = cap; const uint32_t *a_kts = k_to_s;
                 uint32_t *a_par = parent; unsigned long long *a_best = best; uint2 *a_ends = ends;

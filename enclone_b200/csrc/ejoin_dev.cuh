@@ -59,7 +59,8 @@ static_assert(sizeof(EntryMeta) == 128, "EntryMeta must be 128 bytes");
 //   item_index(q, ib) = q*T - seg*q*(q-1)/2 + (T-1-ib),       items(T) = Q*T - seg*Q*(Q-1)/2,  Q = ceil(T/seg).
 // Segment 0 of a row keeps its first survivors in the per-entry slot array; segments q >= 1 use an
 // "extra row" of slots, numbered xoff + item_index - T.
-#define SEG_MIN 8u           // A tiles per segment (small groups); large groups: ceil(T / SEG_QMAX)
+#define SEG_MIN 8u           // A tiles per segment (small groups) on a big input; large groups: ceil(T / SEG_QMAX).  Small inputs (a
+                             // rank's share of a sharded join) use 4 or 2, so that there are still more work items than CTA slots
 #define SEG_QMAX 32u         // at most this many segments per row
 struct GroupInfo {           // one comparison group = one run of equal sort keys
     uint32_t start;          // first sorted position
@@ -74,7 +75,7 @@ struct GroupInfo {           // one comparison group = one run of equal sort key
     uint32_t pad;
 };
 static_assert(sizeof(GroupInfo) == 32, "GroupInfo is 32 bytes");
-__host__ __device__ __forceinline__ uint32_t seg_of_tiles(uint32_t T) { uint32_t s = (T + SEG_QMAX - 1) / SEG_QMAX; return s < SEG_MIN ? SEG_MIN : s; }
+__host__ __device__ __forceinline__ uint32_t seg_of_tiles(uint32_t T, uint32_t seg_min = SEG_MIN) { uint32_t s = (T + SEG_QMAX - 1) / SEG_QMAX; return s < seg_min ? seg_min : s; }
 __host__ __device__ __forceinline__ uint32_t seg_item_off(uint32_t T, uint32_t S, uint32_t q) { return q * T - S * (q * (q - 1) / 2); }
 
 struct DevCounters {         // device-resident scalars (one struct, copied back once)

@@ -63,7 +63,7 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
 
 // K2  group table from the run-length encoded sorted keys.
 struct GroupVals { unsigned long long v[6]; uint32_t W, cdm, T; bool valid; };   // entries, work items, c3 words, pairs, tier-1 bytes, extra slot rows
-__device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned long long n, const uint16_t *__restrict__ cdmax_tab) {
+__device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned long long n, const uint16_t *__restrict__ cdmax_tab, uint32_t seg_min) {
     GroupVals o;
 #pragma unroll
     for (int f = 0; f < 6; f++) o.v[f] = 0;
@@ -77,7 +77,7 @@ __device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned
     o.W = W; o.cdm = cdm; o.T = T;
     o.v[0] = n;
     if (n >= 2 && cdm != 0xFFFF) {
-        const uint32_t S = seg_of_tiles(T), Q = (T + S - 1) / S;
+        const uint32_t S = seg_of_tiles(T, seg_min), Q = (T + S - 1) / S;
         const unsigned long long items = seg_item_off(T, S, Q);       // = Q*T - S*Q*(Q-1)/2
         o.v[1] = items;
         o.v[3] = n * (n - 1) / 2;
@@ -93,7 +93,7 @@ __device__ __forceinline__ GroupVals group_vals(unsigned long long key, unsigned
 __global__ void __launch_bounds__(256) k_group_vals(const unsigned long long *__restrict__ uniq, const uint32_t *__restrict__ counts,
                                                     const uint32_t *num_runs, uint32_t n, const uint16_t *__restrict__ cdmax_tab,
                                                     unsigned long long *__restrict__ sumA, unsigned long long *__restrict__ sumB,
-                                                    uint32_t *__restrict__ sumC, DevCounters *ctr) {
+                                                    uint32_t *__restrict__ sumC, DevCounters *ctr, uint32_t seg_min) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nr = *num_runs;
     unsigned long long pairs = 0, t1b = 0, ng = 0;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_group_vals(const unsigned long long *__
         unsigned long long a = 0, b = 0;
         uint32_t x = 0;
         if (r < nr) {
-            const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
+            const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab, seg_min);
             a = gv.v[0] | (gv.v[1] << 32); b = gv.v[2]; x = (uint32_t)gv.v[5];
             pairs = gv.v[3]; t1b = gv.v[4];
             if (gv.valid) ng = r + 1;
@@ -124,11 +124,11 @@ __global__ void __launch_bounds__(256) k_group_vals(const unsigned long long *__
 __global__ void __launch_bounds__(256) k_group_build(const unsigned long long *__restrict__ uniq, const uint32_t *__restrict__ counts,
                                                      const uint32_t *num_runs, const uint16_t *__restrict__ cdmax_tab,
                                                      const unsigned long long *__restrict__ sumA, const unsigned long long *__restrict__ sumB,
-                                                     const uint32_t *__restrict__ sumC, GroupInfo *__restrict__ groups, DevCounters *ctr) {
+                                                     const uint32_t *__restrict__ sumC, GroupInfo *__restrict__ groups, DevCounters *ctr, uint32_t seg_min) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nr = *num_runs;
     if (r >= nr) return;
-    const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab);
+    const GroupVals gv = group_vals(uniq[r], counts[r], cdmax_tab, seg_min);
     const unsigned long long a = sumA[r], b = sumB[r];
     const uint32_t x = sumC[r];
     if (gv.valid) {
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_group_build(const unsigned long long *_
         g.c3base = (uint32_t)b;
         g.work_off = (uint32_t)(a >> 32);
         g.xoff = x;
-        g.W = (uint16_t)gv.W; g.cdmax = (uint16_t)gv.cdm; g.tiles = (uint16_t)gv.T; g.seg = (uint16_t)seg_of_tiles(gv.T); g.pad = 0;
+        g.W = (uint16_t)gv.W; g.cdmax = (uint16_t)gv.cdm; g.tiles = (uint16_t)gv.T; g.seg = (uint16_t)seg_of_tiles(gv.T, seg_min); g.pad = 0;
         groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
     }
     if (r == nr - 1) {               // totals = exclusive prefix of the last run + its own values
@@ -1816,9 +1816,47 @@ __device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTab
     return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
 }
 
+// The continuation walks an entry's slots one after the other, and each step is a full evaluation (~20 us of dependent loads):
+// six in a row made this the longest latency chain of a small join.  k_pending_eval therefore scores the next PEND_SPEC slots of
+// every parked entry AT ONCE, one warp per (entry, slot); the walk below then reads those answers instead of computing them.
+// A slot the walk never reaches was scored for nothing: at most PEND_SPEC per parked entry (1 % of the entries).
+#define PEND_SPEC 8u
+struct PendRes { int r, cd, d; uint32_t err_scored; };       // err_scored: bit 0 = err, bit 1 = scored, bit 2 = bytewise path, bit 31 = valid
+__global__ void __launch_bounds__(128) k_pending_eval(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, const uint2 *pending,
+                                                      PendRes *res, uint32_t res_cap) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t np = min(ctr->n_pending, res_cap);
+    unsigned long long bytes = 0;
+    for (unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < (unsigned long long)np * PEND_SPEC;
+         w += ((unsigned long long)gridDim.x * blockDim.x) >> 5) {
+        const uint32_t j = (uint32_t)(w / PEND_SPEC), t = (uint32_t)(w % PEND_SPEC);
+        const uint32_t s = pending[j].x, li = pending[j].y + t;
+        RowSlots rs;
+        rs.init(sv, s);
+        const uint32_t q = li / PHASE_A_K, i = li % PHASE_A_K;
+        PendRes o; o.r = 0; o.cd = 0; o.d = 0; o.err_scored = 0;
+        if (q < rs.nseg && i < min(rs.count(sv, q), PHASE_A_K)) {
+            const uint32_t a = rs.slot(sv, q, i);
+            int r = 0, cd = 0, d = 0, err = 0;
+            bool scored = false;
+            if (lane == 0) r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
+            r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
+            cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
+            uint32_t fl = 0x80000000u | (err ? 1u : 0u) | (__shfl_sync(0xFFFFFFFFu, (int)scored, 0) ? 2u : 0u);
+            if (r < 0) { r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d); fl |= 4u; }
+            o.r = r; o.cd = cd; o.d = d; o.err_scored = fl;
+        }
+        if (lane == 0) res[(size_t)j * PEND_SPEC + t] = o;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, o);
+    if (lane == 0 && bytes) atomicAdd(&ctr->t2_alg_bytes, bytes);
+}
+
 __global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
                                                          uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
-                                                         unsigned long long cand_cap, const uint2 *pending) {
+                                                         unsigned long long cand_cap, const uint2 *pending, const PendRes *res, uint32_t res_cap) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t np = ctr->n_pending;
     unsigned long long evals = 0, bytes = 0;
@@ -1837,14 +1875,20 @@ __global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb,
                     if (li < start) { rejects++; continue; }
                     const uint32_t a = rs.slot(sv, q, i);
                     int r = 0, cd = 0, d = 0, err = 0;
-                    if (lane == 0) {
-                        bool scored;
-                        r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
-                        if (li > start) evals += scored;                      // slot `start` was already counted by k_phase_a
+                    const PendRes *pre = (j < res_cap && li - start < PEND_SPEC) ? &res[(size_t)j * PEND_SPEC + (li - start)] : nullptr;
+                    if (pre && (pre->err_scored & 0x80000000u)) {          // scored ahead of time by k_pending_eval
+                        r = pre->r; cd = pre->cd; d = pre->d; err = (int)(pre->err_scored & 1u);
+                        if (lane == 0 && li > start) evals += (pre->err_scored >> 1) & 1u;
+                    } else {
+                        if (lane == 0) {
+                            bool scored;
+                            r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
+                            if (li > start) evals += scored;                      // slot `start` was already counted by k_phase_a
+                        }
+                        r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
+                        cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
+                        if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
                     }
-                    r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
-                    cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
-                    if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
                     if (r > 0) {
                         found = true;
                         if (lane == 0) {

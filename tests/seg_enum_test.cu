@@ -8,12 +8,13 @@
 
 int main() {
     long checked = 0;
+    for (uint32_t seg_min : { 8u, 4u, 2u, 1u })
     for (uint32_t T = 1; T <= 70000; T = T < 600 ? T + 1 : T + 997) {
         if (T > 65535) break;
-        const uint32_t S = seg_of_tiles(T), Q = (T + S - 1) / S;
+        const uint32_t S = seg_of_tiles(T, seg_min), Q = (T + S - 1) / S;
         const uint32_t items = seg_item_off(T, S, Q);
         if (Q > SEG_QMAX) { printf("T=%u: %u segments\n", T, Q); return 1; }
-        if (T <= SEG_MIN && items != T) { printf("T=%u: small group must have one item per row\n", T); return 1; }
+        if (T <= seg_min && items != T) { printf("T=%u: small group must have one item per row\n", T); return 1; }
         std::vector<unsigned char> seen(items, 0);
         for (uint32_t q = 0; q < Q; q++)
             for (uint32_t ib = q * S; ib < T; ib++) {
