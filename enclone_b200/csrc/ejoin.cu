@@ -773,7 +773,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     if (h->edge_cap == 0) h->edge_cap = std::max<unsigned long long>(1ull << 20, 4ull * n);
     // tier-1 segment length: shorter on small inputs (more, smaller work items: a rank's eighth of a join otherwise has fewer
     // items than the GPU has CTA slots and the sweep's time is the time of its longest item)
-    uint32_t seg_min = n >= 1000000u ? SEG_MIN : (n >= 400000u ? 4u : 2u);
+    uint32_t seg_min = n >= 1000000u ? SEG_MIN : 4u;       // measured on eighths of the 1.6 M-cell join: 8 -> 4 halves the sweep; 2 and 1 cost phase A more than they save
     if (const char *e = getenv("EJOIN_SEG_MIN")) seg_min = (uint32_t)std::max(1, atoi(e));
     if (h->xrow_cap == 0 || h->xrow_seg != seg_min) { h->xrow_cap = 1024 + (unsigned long long)(n / T1_TILE) * (16 / std::min(16u, seg_min)); h->xrow_seg = seg_min; }
     if (n == 0) return 0;
@@ -809,7 +809,6 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
         sz.take(8 * ccap); sz.take(8 * ccap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
         sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending
-        sz.take(sizeof(PendRes) * ((size_t)n / 8 + 1024) * PEND_SPEC);
         sz.take((size_t)n + 1024); sz.take(8 * ((size_t)n + 1024));                                           // work items: cost class, sorted list (items <= n)
         sz.take(4 * (size_t)xcap * PHASE_A_K * T1_TILE); sz.take(4 * (size_t)xcap * T1_TILE);                   // extra slot rows (segments q >= 1)
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
@@ -838,8 +837,6 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint32_t *firstk = A.take<uint32_t>((size_t)n * PHASE_A_K), *surv_cnt = A.take<uint32_t>(n);
         uint8_t *needed = A.take<uint8_t>(n), *force = A.take<uint8_t>(n);
         uint2 *pending = A.take<uint2>(n);
-        const uint32_t pend_cap = n / 8 + 1024;
-        PendRes *pend_res = A.take<PendRes>((size_t)pend_cap * PEND_SPEC);
         const uint32_t item_cap = n + 1024;
         uint8_t *item_cls = A.take<uint8_t>(item_cap);
         uint2 *order = A.take<uint2>(item_cap);
@@ -947,10 +944,9 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sv.firstk = firstk; sv.cnt = surv_cnt; sv.xk = xk; sv.xcnt = xcnt; sv.gid_incl = gid; sv.groups = groups; sv.stride = stride; sv.phase = phase;
         k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
         mark(h, "k_phase_a");
-        k_pending_eval<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, pending, pend_res, pend_cap);
-        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending, pend_res, pend_cap);
+        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
         mark(h, "k_phase_a_pending");
-        h->launches += 8;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
+        h->launches += 7;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
         k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, ccap);

@@ -1816,47 +1816,9 @@ __device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTab
     return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
 }
 
-// The continuation walks an entry's slots one after the other, and each step is a full evaluation (~20 us of dependent loads):
-// six in a row made this the longest latency chain of a small join.  k_pending_eval therefore scores the next PEND_SPEC slots of
-// every parked entry AT ONCE, one warp per (entry, slot); the walk below then reads those answers instead of computing them.
-// A slot the walk never reaches was scored for nothing: at most PEND_SPEC per parked entry (1 % of the entries).
-#define PEND_SPEC 8u
-struct PendRes { int r, cd, d; uint32_t err_scored; };       // err_scored: bit 0 = err, bit 1 = scored, bit 2 = bytewise path, bit 31 = valid
-__global__ void __launch_bounds__(128) k_pending_eval(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, const uint2 *pending,
-                                                      PendRes *res, uint32_t res_cap) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t np = min(ctr->n_pending, res_cap);
-    unsigned long long bytes = 0;
-    for (unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < (unsigned long long)np * PEND_SPEC;
-         w += ((unsigned long long)gridDim.x * blockDim.x) >> 5) {
-        const uint32_t j = (uint32_t)(w / PEND_SPEC), t = (uint32_t)(w % PEND_SPEC);
-        const uint32_t s = pending[j].x, li = pending[j].y + t;
-        RowSlots rs;
-        rs.init(sv, s);
-        const uint32_t q = li / PHASE_A_K, i = li % PHASE_A_K;
-        PendRes o; o.r = 0; o.cd = 0; o.d = 0; o.err_scored = 0;
-        if (q < rs.nseg && i < min(rs.count(sv, q), PHASE_A_K)) {
-            const uint32_t a = rs.slot(sv, q, i);
-            int r = 0, cd = 0, d = 0, err = 0;
-            bool scored = false;
-            if (lane == 0) r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
-            r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
-            cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
-            uint32_t fl = 0x80000000u | (err ? 1u : 0u) | (__shfl_sync(0xFFFFFFFFu, (int)scored, 0) ? 2u : 0u);
-            if (r < 0) { r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d); fl |= 4u; }
-            o.r = r; o.cd = cd; o.d = d; o.err_scored = fl;
-        }
-        if (lane == 0) res[(size_t)j * PEND_SPEC + t] = o;
-        __syncwarp();
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, o);
-    if (lane == 0 && bytes) atomicAdd(&ctr->t2_alg_bytes, bytes);
-}
-
 __global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
                                                          uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
-                                                         unsigned long long cand_cap, const uint2 *pending, const PendRes *res, uint32_t res_cap) {
+                                                         unsigned long long cand_cap, const uint2 *pending) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t np = ctr->n_pending;
     unsigned long long evals = 0, bytes = 0;
@@ -1875,20 +1837,14 @@ __global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb,
                     if (li < start) { rejects++; continue; }
                     const uint32_t a = rs.slot(sv, q, i);
                     int r = 0, cd = 0, d = 0, err = 0;
-                    const PendRes *pre = (j < res_cap && li - start < PEND_SPEC) ? &res[(size_t)j * PEND_SPEC + (li - start)] : nullptr;
-                    if (pre && (pre->err_scored & 0x80000000u)) {          // scored ahead of time by k_pending_eval
-                        r = pre->r; cd = pre->cd; d = pre->d; err = (int)(pre->err_scored & 1u);
-                        if (lane == 0 && li > start) evals += (pre->err_scored >> 1) & 1u;
-                    } else {
-                        if (lane == 0) {
-                            bool scored;
-                            r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
-                            if (li > start) evals += scored;                      // slot `start` was already counted by k_phase_a
-                        }
-                        r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
-                        cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
-                        if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
+                    if (lane == 0) {
+                        bool scored;
+                        r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
+                        if (li > start) evals += scored;                      // slot `start` was already counted by k_phase_a
                     }
+                    r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
+                    cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
+                    if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
                     if (r > 0) {
                         found = true;
                         if (lane == 0) {
