@@ -863,7 +863,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_bucket_heads<<<nb256, 256, 0, st>>>(h->din, head_pos);
         size_t tb = cub_bytes;
         cub::DeviceScan::InclusiveScan(cub_tmp, tb, head_pos, bucket_start, MaxOp(), (int)n, st);
-        k_entry_keys<<<nb256, 256, 0, st>>>(h->din, bucket_start, keys, vals, (uint32_t *)h->d_presL.p, (uint32_t *)h->d_presC.p, ctr);
+        k_entry_keys<<<std::min(nb256, (unsigned)h->sm_count * 4u), 256, 0, st>>>(h->din, bucket_start, keys, vals, (uint32_t *)h->d_presL.p, (uint32_t *)h->d_presC.p, ctr);
         h->launches += 2;
         CK(cudaGetLastError());
         int rc = prepare_tables(h, is_bcr);         // one sync; cached after the first run
@@ -933,6 +933,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             h->launches += h->n_chunks - 1;
         } else {
             k_pack_t2<<<(unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, 0ull, ~0ull);
+        }
+        if (h->din.tig2_src) {       // entries with both chains 2 bits per base (the launches above did the ones with an ASCII chain)
+            k_pack_t2_2bit<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed);
+            h->launches += 1;
         }
         CK(cudaEventRecord(h->ev[6], st));
         mark(h, "k_pack_t2");
@@ -1852,11 +1856,15 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
     std::vector<uint64_t> woff[2], aoff[2];
     for (int c = 0; c < 2; c++) { woff[c].assign(n, 0); aoff[c].assign(n, 0); }
     uint64_t words = 0, abytes = 0;
-    for (uint32_t k = 0; k < n; k++)
+    for (uint32_t k = 0; k < n; k++) {
+        // every entry starts on a 64-byte boundary: SM reads of host memory move whole 64-byte pieces, and an entry read in place
+        // then costs 192 bytes of PCIe traffic instead of up to 256 (measured: 41.7 against 32.6 GB/s of useful bytes)
+        words = (words + 7) & ~7ull;
         for (int c = 0; c < 2; c++) {
             if (asc[c][k]) { aoff[c][k] = abytes; abytes += in->len[c][k]; }
             else { woff[c][k] = words; words += (in->len[c][k] + 31) / 32; }
         }
+    }
     std::vector<uint32_t> c3off_v(n ? n : 1);
     uint64_t c3words = 0;
     for (uint32_t k = 0; k < n; k++) { c3off_v[k] = (uint32_t)c3words; c3words += ((uint64_t)in->cdr3_len[0][k] + in->cdr3_len[1][k] + 31) / 32; }
@@ -1871,7 +1879,7 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
     if (!o->tig2 || !o->rec || !o->ascii || !o->c3w || !o->c3off) { ejoin_pack_compact_free(&o->pk); return EJOIN_E_NOMEM; }
     memcpy(o->c3off, c3off_v.data(), 4 * (size_t)n);
     bool bad_cdr3 = false;
-    memset(o->tig2 + words, 0, 8 * 16);
+    memset(o->tig2, 0, 8 * (words + 16));                 // alignment gaps included
     memset(o->ascii + abytes, 0, 128);
     parallel_ranges(n, threads, [&](uint32_t a, uint32_t b) {
         for (uint32_t k = a; k < b; k++) {

@@ -28,9 +28,10 @@ __global__ void k_bucket_heads(DevIn in, uint32_t *head_pos) {
 // help1.rs:270-276) get the key ~0 and drop out of every comparison group.
 __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned long long *keys, uint32_t *vals,
                              uint32_t *presL, uint32_t *presC, DevCounters *ctr) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-stride: a few hundred blocks, each ending with ONE pair of atomics on the two global tallies (one block per 256
+    // entries meant 10,000 same-address atomics in a row: 0.1 ms at 1.27 M entries, four times the rest of the kernel)
     unsigned long long pairs = 0, heads = 0;
-    if (k < in.n_info) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < in.n_info; k += gridDim.x * blockDim.x) {
         uint32_t l0 = in.len[0][k], l1 = in.len[1][k], c0 = in.cdr3_len[0][k], c1 = in.cdr3_len[1][k];
         uint32_t e = in.exact_id[k];
         uint32_t nch = e < in.n_exact ? in.nchains[e] : 0;
@@ -50,8 +51,8 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
         }
         keys[k] = key;
         vals[k] = k;
-        pairs = k - bucket_start[k];
-        heads = bucket_start[k] == k;
+        pairs += k - bucket_start[k];
+        heads += bucket_start[k] == k;
     }
     typedef cub::BlockReduce<unsigned long long, 256> BR;
     __shared__ typename BR::TempStorage tmp;
@@ -529,6 +530,7 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
     const int n0 = m.len[0], n1 = m.len[1];
     // which chains come as ASCII bytes (all of them unless the pack is EJOIN_F_TIGS_2BIT; then only those with has_del)
     const bool asc[2] = { in.tig2_src == nullptr || in.has_del[0][k] != 0, in.tig2_src == nullptr || in.has_del[1][k] != 0 };
+    if (!asc[0] && !asc[1]) return;               // both chains 2 bits per base: k_pack_t2_2bit packs this entry
     if (in.tig2_src == nullptr) {
         const unsigned long long e0 = in.tig_off[0][k] + (unsigned long long)n0, e1 = in.tig_off[1][k] + (unsigned long long)n1;
         const unsigned long long last = e0 > e1 ? e0 : e1;
@@ -635,6 +637,93 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
         EntryMeta *mm = &meta[s];
         mm->m[0] = (uint16_t)mcount0; mm->m[1] = (uint16_t)mcount1;
         if (g0 || g1) mm->flags = (uint16_t)(mm->flags | (g0 ? FLAG_GENERIC0 : 0u) | (g1 ? FLAG_GENERIC1 : 0u));
+    }
+}
+
+// The same rows for entries whose two chains both come 2 bits per base (EJOIN_F_TIGS_2BIT; nearly all of them): no bytes to
+// convert, so the work is one bit transpose per word and the kernel is organised around its memory traffic instead.
+// EIGHT lanes per entry, one 128-base block per lane: four consecutive 8-byte words in (32 contiguous bytes per lane, the
+// in-place PCIe traffic in zero-copy mode), three 16-byte rows [H x4 | L x4 | M x4] out (48 contiguous bytes per lane, 16-byte
+// stores).  Entries with an ASCII chain are left to k_pack_t2.  Byte tallies: one atomic per CTA.
+__global__ void __launch_bounds__(256) k_pack_t2_2bit(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
+                                                      const uint8_t *__restrict__ needed) {
+    __shared__ unsigned long long s_bytes[2];
+    if (threadIdx.x < 2) s_bytes[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 7;
+    const uint32_t gmask = 0xFFu << (threadIdx.x & 24);          // this entry's eight lanes inside the warp
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    bool live = s < (uint32_t)ctr->n_valid && needed[s];
+    uint32_t k = 0;
+    if (live) { k = meta[s].k; live = in.has_del[0][k] == 0 && in.has_del[1][k] == 0; }
+    if (live) {
+        const EntryMeta &m = meta[s];
+        const int n0 = m.len[0], n1 = m.len[1];
+        const uint32_t nb0 = ((uint32_t)n0 + 127) / 128, nblk = nb0 + ((uint32_t)n1 + 127) / 128;
+        const unsigned long long off0 = in.tig_off[0][k], off1 = in.tig_off[1][k];
+        bool ok = (n0 == 0 || (off0 >= in.tig2_lo && off0 + (unsigned)(n0 + 31) / 32 <= in.tig2_hi)) &&
+                  (n1 == 0 || (off1 >= in.tig2_lo && off1 + (unsigned)(n1 + 31) / 32 <= in.tig2_hi));
+        if (!ok) { if (lane == 0) atomicOr(&ctr->err, ERR_ARENA_RANGE); }
+        else {
+            const uint32_t TW = in.ref_plane_words;
+            int mcount0 = 0, mcount1 = 0;
+            for (uint32_t b = lane; b < nblk; b += 8) {
+                const int c = b >= nb0;
+                const int wl0 = 4 * (int)(b - (c ? nb0 : 0u));          // first word of this block inside the chain
+                const int n = c ? n1 : n0, nwords = (n + 31) / 32;
+                const unsigned long long *src = (const unsigned long long *)in.tig2_src + (c ? off1 : off0) + wl0;
+                unsigned long long x[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) x[q] = wl0 + q < nwords ? __ldg(src + q) : 0ull;      // four loads in flight
+                const int vend = m.vend[c], jstart = m.jstart[c];
+                const uint32_t vo = in.ref_plane_off[m.vs[c]], ji = m.js[c];
+                const int joff0 = 32 * wl0 - (n - (int)in.refseq_len[ji]);
+                const uint32_t *jg = in.ref_planes + in.ref_plane_off[ji];
+                uint32_t H[4], L[4], M[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int p0 = 32 * (wl0 + q), nb = n - p0;
+                    planes_of_2bit(x[q], H[q], L[q]);
+                    const uint32_t valid = low_bits(nb);
+                    H[q] &= valid; L[q] &= valid;
+                    uint32_t mm = 0;
+                    const uint32_t inV = low_bits(vend - p0) & valid, inJ = valid & ~low_bits(jstart - p0);
+                    if (inV) {
+                        const uint32_t o = vo + (uint32_t)(wl0 + q);
+                        mm |= ((H[q] ^ in.ref_planes[o]) | (L[q] ^ in.ref_planes[TW + o]) | in.ref_planes[2 * TW + o]) & inV;
+                    }
+                    if (inJ) {
+                        const int off = joff0 + 32 * q;               // >= -31 for a word that meets the J window
+                        const int wi = off >> 5;
+                        const uint32_t bo = (uint32_t)off & 31u;
+                        const uint32_t *g = jg + wi;
+                        const uint32_t gH = __funnelshift_r(g[0], g[1], bo), gL = __funnelshift_r(g[TW], g[TW + 1], bo);
+                        const uint32_t gN = __funnelshift_r(g[2 * TW], g[2 * TW + 1], bo);
+                        mm |= ((H[q] ^ gH) | (L[q] ^ gL) | gN) & inJ;
+                    }
+                    M[q] = mm;
+                    if (c) mcount1 += __popc(mm); else mcount0 += __popc(mm);
+                }
+                uint4 *rows = t2 + m.t2off + 3 * b;
+                rows[0] = make_uint4(H[0], H[1], H[2], H[3]);
+                rows[1] = make_uint4(L[0], L[1], L[2], L[3]);
+                rows[2] = make_uint4(M[0], M[1], M[2], M[3]);
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) { mcount0 += __shfl_xor_sync(gmask, mcount0, o); mcount1 += __shfl_xor_sync(gmask, mcount1, o); }
+            if (lane == 0) {
+                EntryMeta *mm = &meta[s];
+                mm->m[0] = (uint16_t)mcount0; mm->m[1] = (uint16_t)mcount1;
+                const unsigned long long bin = 8ull * ((n0 + 31) / 32) + 8ull * ((n1 + 31) / 32);
+                atomicAdd(&s_bytes[0], bin + 48ull * nblk);
+                atomicAdd(&s_bytes[1], bin);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bytes[0]) {
+        atomicAdd(&ctr->pack_bytes[blockIdx.x & 31], s_bytes[0]);
+        atomicAdd(&ctr->inplace_bytes[blockIdx.x & 31], s_bytes[1]);
     }
 }
 

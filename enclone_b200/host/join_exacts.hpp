@@ -217,6 +217,7 @@ inline void pack(Flat &F, bool is_bcr, const RefData &refdata, const std::vector
         for (uint32_t k = a; k < b; k++) {
             const CloneInfo &ci = info[k];
             uint32_t c3n = 0;
+            run.words = (run.words + 7) & ~7ull;                    // every entry starts on a 64-byte boundary (in-place reads move 64-byte pieces)
             for (size_t c = 0; c < ci.lens.size() && c < 2; c++) {
                 const uint32_t L = (uint32_t)ci.tigs[c].size();
                 const bool x = write ? asc[c][k] != 0 : chain_ascii(ci, c);
@@ -228,6 +229,7 @@ inline void pack(Flat &F, bool is_bcr, const RefData &refdata, const std::vector
             if (write) F.c3off[k] = (uint32_t)run.c3words;
             run.c3words += (c3n + 31) / 32;
         }
+        run.words = (run.words + 7) & ~7ull;                        // so that the next thread's range starts aligned too
         if (!write) tot[t] = run;
     };
     parallel_for(n, T, [&](int t, uint32_t a, uint32_t b) { sizes(t, a, b, false); });
@@ -242,7 +244,7 @@ inline void pack(Flat &F, bool is_bcr, const RefData &refdata, const std::vector
     ejoin_entry_rec_t *rec = (ejoin_entry_rec_t *)F.alloc(sizeof(ejoin_entry_rec_t) * ((size_t)n + 1));
     uint8_t *ascii = (uint8_t *)F.alloc(total.abytes + 128);
     uint64_t *c3w = (uint64_t *)F.alloc(8 * (total.c3words + 16));
-    memset(tig2 + total.words, 0, 128); memset(ascii + total.abytes, 0, 128); memset(c3w + total.c3words, 0, 128);
+    memset(tig2 + total.words, 0, 128);       // (alignment gaps between entries are never read: every chain has its own offset) memset(ascii + total.abytes, 0, 128); memset(c3w + total.c3words, 0, 128);
     // ---- pass 2 (parallel): arenas and records; germline strings and V names interned per thread
     // Germline strings are interned by content (every CloneInfo owns its own copy of vs / js), but found through a cheap
     // key — length and 24 sampled bytes — and confirmed with one memcmp, instead of hashing ~1.4 KB of text per entry;
