@@ -150,7 +150,8 @@ struct ejoin_handle {
     unsigned long long xrow_cap = 0;
     uint32_t xrow_seg = 0;
     std::vector<uint32_t> ref_plane_off;   // host copy of DevIn::ref_plane_off (kept alive for the async upload)
-    unsigned long long cand_cap = 0;    // survivor list (tier-1 survivors beyond the phase-A slots)
+    unsigned long long cand_cap = 0;    // survivor list (tier-1 survivors beyond the phase-A slots): 16-byte mask records
+    unsigned long long rest_cap = 0;    // survivor pairs kept for round 2
     unsigned long long edge_cap = 0;    // to-be-scored lists, accepted edges, sort arrays
     // work pointers of the last pipeline run
     EntryMeta *meta = nullptr; uint32_t *c3 = nullptr; uint4 *t2 = nullptr; uint32_t *k_to_s = nullptr;
@@ -269,7 +270,7 @@ extern "C" int ejoin_create(ejoin_handle_t **out, const ejoin_params_t *p, int d
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return EJOIN_E_NOGPU; }
     ejoin_handle *h = new ejoin_handle();
     h->device = device; h->params = *p;
-    if (const char *cc = getenv("EJOIN_CAND_CAP")) h->cand_cap = h->edge_cap = strtoull(cc, nullptr, 10);   // tests: force the overflow-and-retry path
+    if (const char *cc = getenv("EJOIN_CAND_CAP")) h->cand_cap = h->rest_cap = h->edge_cap = strtoull(cc, nullptr, 10);   // tests: force the overflow-and-retry path
     *out = h;                                    // so the caller can read last_error on failure
     if (p->old_mult) return fail(h, EJOIN_E_UNSUPPORTED, "OLD_MULT is not supported by the GPU path");
     if (p->auto_share > P1_DCAP) return fail(h, EJOIN_E_UNSUPPORTED, "AUTO_SHARES above the p1 table depth");
@@ -769,7 +770,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     const DevParams pr = dev_params(h->params, is_bcr);
     memset(&h->counters, 0, sizeof(h->counters));
     h->stats.ms_kernel_pack = h->stats.ms_kernel_tier1 = h->stats.ms_kernel_tier2 = h->stats.ms_kernel_other = 0;
-    if (h->cand_cap == 0) h->cand_cap = std::max<unsigned long long>(1ull << 20, 48ull * n);
+    if (h->cand_cap == 0) h->cand_cap = std::max<unsigned long long>(1ull << 20, 12ull * n);
+    if (h->rest_cap == 0) h->rest_cap = std::max<unsigned long long>(1ull << 20, 8ull * n);
     if (h->edge_cap == 0) h->edge_cap = std::max<unsigned long long>(1ull << 20, 4ull * n);
     // tier-1 segment length: shorter on small inputs (more, smaller work items: a rank's eighth of a join otherwise has fewer
     // items than the GPU has CTA slots and the sweep's time is the time of its longest item)
@@ -778,7 +780,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     if (h->xrow_cap == 0 || h->xrow_seg != seg_min) { h->xrow_cap = 1024 + (unsigned long long)(n / T1_TILE) * (16 / std::min(16u, seg_min)); h->xrow_seg = seg_min; }
     if (n == 0) return 0;
     for (int attempt = 0; attempt < 6; attempt++) {
-        const unsigned long long ccap = h->cand_cap;
+        const unsigned long long ccap = h->cand_cap, rcap = h->rest_cap;
         const unsigned long long xcap = h->xrow_cap;
         const unsigned long long cap = std::max<unsigned long long>(h->edge_cap, (unsigned long long)n + 1024);
         // ---- size and carve the work arena ----
@@ -807,8 +809,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                             // t2sizes, t2off, gid
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
-        sz.take(8 * ccap); sz.take(8 * ccap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
-        sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending
+        sz.take(16 * ccap); sz.take(8 * rcap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
+        sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n); sz.take(4 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending, asc list
         sz.take((size_t)n + 1024); sz.take(8 * ((size_t)n + 1024));                                           // work items: cost class, sorted list (items <= n)
         sz.take(4 * (size_t)xcap * PHASE_A_K * T1_TILE); sz.take(4 * (size_t)xcap * T1_TILE);                   // extra slot rows (segments q >= 1)
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
@@ -833,10 +835,12 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint4 *t2 = A.take<uint4>(t2_units);
         uint32_t *k_to_s = A.take<uint32_t>(n), *parent = A.take<uint32_t>(n);
         unsigned long long *f0_key = A.take<unsigned long long>(n), *f0_val = A.take<unsigned long long>(n);
-        uint2 *cand = A.take<uint2>(ccap), *rest = A.take<uint2>(ccap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
+        uint4 *cand = A.take<uint4>(ccap);
+        uint2 *rest = A.take<uint2>(rcap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
         uint32_t *firstk = A.take<uint32_t>((size_t)n * PHASE_A_K), *surv_cnt = A.take<uint32_t>(n);
         uint8_t *needed = A.take<uint8_t>(n), *force = A.take<uint8_t>(n);
         uint2 *pending = A.take<uint2>(n);
+        uint32_t *asc_list = A.take<uint32_t>(n);
         const uint32_t item_cap = n + 1024;
         uint8_t *item_cls = A.take<uint8_t>(item_cap);
         uint2 *order = A.take<uint2>(item_cap);
@@ -917,22 +921,26 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             h->launches += 1;
             h->recs_pending = false;               // the parallel arrays stay valid for later resident runs
         }
-        k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, needed, pr.ref_v_trim, pr.ref_j_trim);
+        k_meta<<<nb256, 256, 0, st>>>(h->din, perm, gid, groups, t2off, ctr, meta, k_to_s, needed, pr.ref_v_trim, pr.ref_j_trim, asc_list);
         k_pack_ref<<<std::max(1u, h->din.n_refseq), 32, 0, st>>>(h->din);
         h->launches += 1;
         CK(cudaEventRecord(h->ev[7], st));
         mark(h, "k_meta");
+        // 2-bit input: k_pack_t2 takes only the entries with an ASCII chain, which k_meta listed (~1 % of them; the other half
+        // warps of the grid leave at once), k_pack_t2_2bit all the others
+        const uint32_t *pack_list = h->din.tig2_src ? asc_list : nullptr;
+        const unsigned pack_blocks = (unsigned)(((size_t)n * 16 + 255) / 256);
         if (h->copy_pending && h->n_chunks > 0) {
             // pack each chunk's (needed) entries as its bytes land (an entry belongs to the chunk that completes it)
             uint64_t prev = 0;
             for (int i = 0; i < h->n_chunks; i++) {
                 CK(cudaStreamWaitEvent(st, h->ev_chunk[i == h->n_chunks - 1 ? 7 : i], 0));
-                k_pack_t2<<<(unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, prev, h->chunk_end[i]);
+                k_pack_t2<<<pack_blocks, 256, 0, st>>>(h->din, ctr, meta, t2, needed, prev, h->chunk_end[i], pack_list);
                 prev = h->chunk_end[i];
             }
             h->launches += h->n_chunks - 1;
         } else {
-            k_pack_t2<<<(unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed, 0ull, ~0ull);
+            k_pack_t2<<<pack_blocks, 256, 0, st>>>(h->din, ctr, meta, t2, needed, 0ull, ~0ull, pack_list);
         }
         if (h->din.tig2_src) {       // entries with both chains 2 bits per base (the launches above did the ones with an ASCII chain)
             k_pack_t2_2bit<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, st>>>(h->din, ctr, meta, t2, needed);
@@ -953,7 +961,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         h->launches += 7;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
-        k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, ccap);
+        k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, rcap);
         mark(h, "k_phaseb_split");
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, parent);
         mark(h, "k_tier2 r1");
@@ -965,7 +973,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         // round 2: the other recorded survivors, scored only across trees
         k_round2_begin<<<1, 1, 0, st>>>(ctr);
         k_forced_prune<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent);
-        k_phaseb_cross<<<h->sm_count * 8, 256, 0, st>>>(rest, ccap, parent, ctr, todo, cap);
+        k_phaseb_cross<<<h->sm_count * 8, 256, 0, st>>>(rest, rcap, parent, ctr, todo, cap);
         mark(h, "round2 begin/prune/cross");
         k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, nullptr);
         mark(h, "k_tier2 r2");
@@ -1007,6 +1015,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             const unsigned long long need_e = std::max(std::max(k.n_todo, k.n_todo_r1), std::max(k.n_generic_q, (unsigned long long)n + k.n_accept));
             bool retry = false;
             if (k.n_cand > ccap) { h->cand_cap = k.n_cand + k.n_cand / 8 + 1024; retry = true; }
+            if (k.n_rest > rcap) { h->rest_cap = k.n_rest + k.n_rest / 8 + 1024; retry = true; }
             if (need_e > cap) { h->edge_cap = need_e + need_e / 4 + 1024; retry = true; }
             if (k.n_xrows > xcap) { h->xrow_cap = k.n_xrows + 64; retry = true; }
             if (retry) continue;

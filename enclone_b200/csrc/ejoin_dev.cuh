@@ -91,6 +91,7 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned int bor_done;           // a k_bor_min pass found no edge between two components: the later rounds return at once
     unsigned int n_payload_slow;
     unsigned int n_pending;
+    unsigned int n_asc;              // 2-bit input: entries with an ASCII chain (k_meta lists them for k_pack_t2)
     unsigned long long n_xrows;      // extra slot rows asked for by the group table
     unsigned long long n_items;      // tier-1 work items of this rank (after the cost sort)
     unsigned int cls_count[64], cls_cursor[64];   // counting sort of the work items by cost class

@@ -331,7 +331,7 @@ __device__ __forceinline__ void bytes_of_planes16(uint32_t H, uint32_t L, int ha
 __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ gid_incl,
                                               const GroupInfo *__restrict__ groups, const uint32_t *__restrict__ t2off, DevCounters *ctr,
                                               EntryMeta *__restrict__ meta, uint32_t *__restrict__ k_to_s, const uint8_t *__restrict__ needed,
-                                              int ref_v_trim, int ref_j_trim) {
+                                              int ref_v_trim, int ref_j_trim, uint32_t *__restrict__ asc_list) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (uint32_t)ctr->n_valid) return;
     const uint32_t k = perm[s];
@@ -367,6 +367,8 @@ __global__ void __launch_bounds__(256) k_meta(DevIn in, const uint32_t *__restri
     m.flags = (uint16_t)flags;
     meta[s] = m;
     k_to_s[k] = s;
+    // 2-bit input: the few entries with an ASCII chain (deletion marker / non-ACGT byte) are listed for k_pack_t2
+    if (in.tig2_src && (in.has_del[0][k] || in.has_del[1][k])) asc_list[atomicAdd(&ctr->n_asc, 1u)] = s;
 }
 
 // 4 threads per entry, thread j packs the c3 words j, j+4 (W <= 4 for CDR3 pairs up to 128 nt: 3 of 4 lanes busy).  The 32 bases of a word
@@ -516,13 +518,18 @@ __global__ void __launch_bounds__(256) k_unpack_recs(const ejoin_entry_rec_t *__
 
 #define PACK_STAGE 544          // per chain: 512 bytes + alignment slack + the 48-byte window overrun
 __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
-                                                 const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi) {
+                                                 const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi,
+                                                 const uint32_t *__restrict__ asc_list) {
     // one HALF warp per entry: a 2 x 350-base entry has 44 plane words = 3 passes of 16 lanes (92 % of the lane slots;
     // a whole warp needed 2 passes of 32 = 69 %)
     __shared__ __align__(16) uint8_t stage[16][2][PACK_STAGE];
     const uint32_t lane = threadIdx.x & 15, wib = threadIdx.x >> 4;
     const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);          // the lanes of this half warp
-    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (asc_list) {                               // 2-bit input: only the listed entries (those with an ASCII chain) are this kernel's
+        if (s >= ctr->n_asc) return;
+        s = asc_list[s];
+    }
     if (s >= (uint32_t)ctr->n_valid) return;
     if (!needed[s]) return;                       // no CDR3-compatible partner: its rows are never read
     const EntryMeta &m = meta[s];
@@ -1021,38 +1028,36 @@ __device__ __forceinline__ void block_reserve2(SplitSmem &sm, uint32_t c1, uint3
     __syncthreads();                                  // sm is reused by the next tile
 }
 
-__global__ void __launch_bounds__(256) k_phaseb_split(const uint2 *__restrict__ cand, unsigned long long cand_cap, const uint32_t *__restrict__ parent,
+__global__ void __launch_bounds__(256) k_phaseb_split(const uint4 *__restrict__ cand, unsigned long long cand_cap, const uint32_t *__restrict__ parent,
                                                       const uint8_t *__restrict__ force_b, DevCounters *ctr, uint2 *__restrict__ todo,
                                                       unsigned long long todo_cap, uint2 *__restrict__ rest, unsigned long long rest_cap) {
     __shared__ SplitSmem sm;
     unsigned long long ncand = ctr->n_cand;
     if (ncand > cand_cap) ncand = cand_cap;
-    const unsigned long long tile = 256ull * SPLIT_ITEMS;
-    for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < ncand; t0 += (unsigned long long)gridDim.x * tile) {
-        uint2 c[SPLIT_ITEMS];
-        uint32_t k1 = 0, k2 = 0;                      // bit j: item j goes to todo / rest
-#pragma unroll
-        for (int j = 0; j < SPLIT_ITEMS; j++) {
-            const unsigned long long i = t0 + (unsigned long long)j * 256 + threadIdx.x;
-            c[j] = make_uint2(0, 0);
-            if (i < ncand) {
-                c[j] = cand[i];
-                const bool fbit = c[j].x >> 31;
-                c[j].x &= 0x7FFFFFFFu;
-                if (fbit || force_b[c[j].y]) k1 |= 1u << j;
-                else {
-                    const uint32_t pa = parent[c[j].x], pb = parent[c[j].y];
-                    if (pa != pb && pb != c[j].x) k2 |= 1u << j;
+    // one record (b, 32 a's as a mask) per thread and tile: the mask splits into the pairs scored in round 1 (b gave up in
+    // phase A) and the pairs kept for round 2 (endpoints not visibly in one phase-A tree)
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * 256ull; t0 < ncand; t0 += (unsigned long long)gridDim.x * 256ull) {
+        const unsigned long long i = t0 + threadIdx.x;
+        uint4 c = make_uint4(0, 0, 0, 0);
+        uint32_t k1 = 0, k2 = 0;                      // masks: bit j -> pair (c.x + j, c.y) goes to todo / rest
+        if (i < ncand) {
+            c = cand[i];
+            if ((c.w & 1u) || force_b[c.y]) k1 = c.z;
+            else {
+                const uint32_t pb = parent[c.y];
+                uint32_t m = c.z;
+                while (m) {
+                    const uint32_t j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t a = c.x + j;
+                    if (parent[a] != pb && pb != a) k2 |= 1u << j;
                 }
             }
         }
         unsigned long long o1, o2;
         block_reserve2(sm, __popc(k1), __popc(k2), &ctr->n_todo, &ctr->n_rest, o1, o2);
-#pragma unroll
-        for (int j = 0; j < SPLIT_ITEMS; j++) {
-            if ((k1 >> j) & 1u) { if (o1 < todo_cap) todo[o1] = c[j]; o1++; }
-            if ((k2 >> j) & 1u) { if (o2 < rest_cap) rest[o2] = c[j]; o2++; }
-        }
+        while (k1) { const uint32_t j = __ffs(k1) - 1; k1 &= k1 - 1; if (o1 < todo_cap) todo[o1] = make_uint2(c.x + j, c.y); o1++; }
+        while (k2) { const uint32_t j = __ffs(k2) - 1; k2 &= k2 - 1; if (o2 < rest_cap) rest[o2] = make_uint2(c.x + j, c.y); o2++; }
     }
 }
 __global__ void __launch_bounds__(256) k_phaseb_cross(const uint2 *__restrict__ rest, unsigned long long rest_cap, const uint32_t *__restrict__ root,
@@ -1557,9 +1562,13 @@ __global__ void __launch_bounds__(P1_DCAP) k_p1_tables(const uint32_t *Ls, doubl
 // `needed`: only those get their V..J rows packed (about half of a repertoire never needs them).
 // ---------------------------------------------------------------------------------------------
 #define PHASE_A_K 6u
+// A record of the survivor list: the survivors of entry b among the 32 entries a = abase .. abase + 31 as a bit mask
+// (x = abase, y = b, z = mask, w = flags: bit 0 = b gave up in phase A and all of these are scored in round 1).  A clonal
+// family meeting itself fills whole masks: 16 bytes then stand for up to 32 pairs (the pair list this replaces was 0.5 GB
+// at the 1.6 M-cell input, written by the sweep and read back by the split).  Phase A records single pairs as mask 1.
 struct SweepCtx {
     DevCounters *ctr;
-    uint2 *cand; unsigned long long cand_cap;
+    uint4 *cand; unsigned long long cand_cap;
     uint32_t *firstk;      // [n][PHASE_A_K] a positions: segment 0 of every row
     uint32_t *cnt;         // [n] survivors of b in segment 0
     uint32_t *xk;          // [xrow][PHASE_A_K][T1_TILE] a positions: segments q >= 1
@@ -1568,8 +1577,8 @@ struct SweepCtx {
     uint8_t *needed;       // [n]
 };
 
-#define SWEEP_STAGE 256u       // survivor pairs staged per warp
-__device__ __forceinline__ void sweep_flush(SweepCtx &cx, uint2 *stage, uint32_t &fill) {
+#define SWEEP_STAGE 96u        // survivor records staged per warp
+__device__ __forceinline__ void sweep_flush(SweepCtx &cx, uint4 *stage, uint32_t &fill) {
     const uint32_t lane = threadIdx.x & 31;
     __syncwarp();
     if (fill) {
@@ -1586,7 +1595,7 @@ __device__ __forceinline__ void sweep_flush(SweepCtx &cx, uint2 *stage, uint32_t
 template <int W>
 __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
                                           const uint32_t (&bH)[W], const uint32_t (&bL)[W], bool validB, uint32_t posA0, uint32_t posB,
-                                          uint32_t &mycnt, uint2 *stage, uint32_t &fill, uint32_t *slot, uint32_t slot_stride) {
+                                          uint32_t &mycnt, uint4 *stage, uint32_t &fill, uint32_t *slot, uint32_t slot_stride) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (!__any_sync(0xFFFFFFFFu, validB)) return;          // a warp beyond the end of a short B tile
     for (uint32_t a0 = 0; a0 < rowsA; a0 += 32) {
@@ -1617,48 +1626,22 @@ __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restri
             slot[(size_t)mycnt * slot_stride] = posA0 + a0 + aa;
             mycnt++;
         }
-        // the rest: the global survivor list, through the warp's staging buffer (one atomic per SWEEP_STAGE pairs
-        // and coalesced stores, instead of one same-address atomic per 32x32 block)
-        if (__any_sync(0xFFFFFFFFu, bits != 0)) {
-            uint32_t cntl = __popc(bits), incl = cntl;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
-            const uint32_t totalc = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            mycnt += cntl;
-            if (totalc > SWEEP_STAGE) {
-                // a dense block (a clonal family meeting itself): straight to the list, one a at a time, so that the
-                // lanes holding a survivor of that a store to consecutive slots (b-major runs of 32 would make
-                // every store instruction touch 32 sectors)
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&cx.ctr->n_cand, (unsigned long long)totalc);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                uint32_t cols = __reduce_or_sync(0xFFFFFFFFu, bits);
-                while (cols) {
-                    const uint32_t aa = __ffs(cols) - 1;
-                    cols &= cols - 1;
-                    const bool mine = (bits >> aa) & 1u;
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
-                    const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
-                    if (mine && o < cx.cand_cap) cx.cand[o] = make_uint2(posA0 + a0 + aa, posB);
-                    base += __popc(m);
-                }
-            } else {
-                if (fill + totalc > SWEEP_STAGE) sweep_flush(cx, stage, fill);
-                uint32_t o = fill + (incl - cntl);
-                while (bits) {
-                    const uint32_t aa = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    stage[o++] = make_uint2(posA0 + a0 + aa, posB);
-                }
-                fill += totalc;
-            }
+        // the rest: one record per (b, block of 32 a's) on the global survivor list, through the warp's staging buffer (one
+        // atomic per SWEEP_STAGE records and coalesced 16-byte stores)
+        const uint32_t have = __ballot_sync(0xFFFFFFFFu, bits != 0);
+        if (have) {
+            mycnt += __popc(bits);
+            const uint32_t totalc = __popc(have);
+            if (fill + totalc > SWEEP_STAGE) sweep_flush(cx, stage, fill);
+            if (bits) stage[fill + __popc(have & ((1u << lane) - 1u))] = make_uint4(posA0 + a0, posB, bits, 0u);
+            fill += totalc;
         }
     }
 }
 
 template <int W>
 __device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint32_t ib, uint32_t q, const uint32_t *__restrict__ c3,
-                                         uint32_t (*sA)[T1_TILE * 2 * T1_WMAX], uint64_t *bar, uint32_t &parity, uint2 *stage, uint32_t &fill) {
+                                         uint32_t (*sA)[T1_TILE * 2 * T1_WMAX], uint64_t *bar, uint32_t &parity, uint4 *stage, uint32_t &fill) {
     const uint32_t tid = threadIdx.x;
     const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
     const bool validB = tid < rowsB;
@@ -1705,14 +1688,14 @@ __device__ __forceinline__ void row_item(SweepCtx &cx, const GroupInfo &g, uint3
 }
 
 __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ c3, const GroupInfo *__restrict__ groups, DevCounters *ctr,
-                                                   const uint2 *__restrict__ order, uint2 *cand, unsigned long long cand_cap, uint32_t *firstk,
+                                                   const uint2 *__restrict__ order, uint4 *cand, unsigned long long cand_cap, uint32_t *firstk,
                                                    uint32_t *cnt, uint32_t *xk, uint32_t *xcnt, unsigned long long xcap, uint8_t *needed) {
     __shared__ __align__(128) uint32_t sA[2][T1_TILE * 2 * T1_WMAX];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t s_item;
-    __shared__ uint2 s_stage[T1_TILE / 32][SWEEP_STAGE];
+    __shared__ uint4 s_stage[T1_TILE / 32][SWEEP_STAGE];
     const uint32_t tid = threadIdx.x;
-    uint2 *stage = s_stage[tid >> 5];
+    uint4 *stage = s_stage[tid >> 5];
     uint32_t fill = 0;                         // pairs in this warp's staging buffer (warp-uniform)
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
     __syncthreads();
@@ -1791,7 +1774,7 @@ struct WalkOut {
 };
 
 __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
-                                                 uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
+                                                 uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint4 *cand,
                                                  unsigned long long cand_cap, uint2 *pending) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long evals = 0, bytes = 0;
@@ -1862,12 +1845,12 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
             unsigned long long w = 0;
             if (lane == 0) w = atomicAdd(&ctr->n_cand, (unsigned long long)totalc);
             w = __shfl_sync(0xFFFFFFFFu, w, 0) + (incl - cntl);
-            const uint32_t fl = wo.forced ? 0x80000000u : 0u;
+            const uint32_t fl = wo.forced ? 1u : 0u;
             uint32_t e = wo.emit0;
             while (e) {
                 const uint32_t i = __ffs(e) - 1;
                 e &= e - 1;
-                if (w < cand_cap) cand[w] = make_uint2(rs.slot(sv, 0, i) | fl, s);
+                if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, 0, i), s, 1u, fl);
                 w++;
             }
             if (wo.n_emit_x) {
@@ -1875,7 +1858,7 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
                     const uint32_t nq = min(rs.count(sv, q), PHASE_A_K);
                     for (uint32_t i = 0; i < nq; i++) {
                         if (q * PHASE_A_K + i < wo.xe_start) continue;
-                        if (w < cand_cap) cand[w] = make_uint2(rs.slot(sv, q, i) | fl, s);
+                        if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, q, i), s, 1u, fl);
                         w++;
                     }
                 }
@@ -1906,7 +1889,7 @@ __device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTab
 }
 
 __global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
-                                                         uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint2 *cand,
+                                                         uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint4 *cand,
                                                          unsigned long long cand_cap, const uint2 *pending) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t np = ctr->n_pending;
@@ -1952,7 +1935,7 @@ __global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb,
             if (lane == 0) {
                 for (; i < nq; i++) {
                     const unsigned long long w = atomicAdd(&ctr->n_cand, 1ull);
-                    if (w < cand_cap) cand[w] = make_uint2(rs.slot(sv, q, i) | (forced ? 0x80000000u : 0u), s);
+                    if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, q, i), s, 1u, forced ? 1u : 0u);
                 }
             }
         }
