@@ -815,7 +815,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(4 * (size_t)n);                             // t2sizes, t2off, gid
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
-        sz.take(16 * ccap); sz.take(8 * rcap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
+        sz.take(16 * ccap); sz.take(8 * rcap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
         sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n); sz.take(4 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending, asc list
         sz.take((size_t)n + 1024); sz.take(8 * ((size_t)n + 1024));                                           // work items: cost class, sorted list (items <= n)
         sz.take(4 * (size_t)xcap * PHASE_A_K * T1_TILE); sz.take(4 * (size_t)xcap * T1_TILE);                   // extra slot rows (segments q >= 1)
@@ -842,7 +842,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint32_t *k_to_s = A.take<uint32_t>(n), *parent = A.take<uint32_t>(n);
         unsigned long long *f0_key = A.take<unsigned long long>(n), *f0_val = A.take<unsigned long long>(n);
         uint4 *cand = A.take<uint4>(ccap);
-        uint2 *rest = A.take<uint2>(rcap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap), *tworef_q = A.take<uint2>(cap);
+        uint2 *rest = A.take<uint2>(rcap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
         uint32_t *firstk = A.take<uint32_t>((size_t)n * PHASE_A_K), *surv_cnt = A.take<uint32_t>(n);
         uint8_t *needed = A.take<uint8_t>(n), *force = A.take<uint8_t>(n);
         uint2 *pending = A.take<uint2>(n);
@@ -969,8 +969,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         // accepted partner becomes the tree edge (atomicMin on the parent)
         k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, rcap);
         mark(h, "k_phaseb_split");
-        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, tworef_q, acc, 0, parent);
-        k_tier2_tworef<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, tworef_q, cap, generic_q, acc, parent, 0);
+        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, parent);
         mark(h, "k_tier2 r1");
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, parent, 0);
         mark(h, "k_tier2_generic r1");
@@ -982,11 +981,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_forced_prune<<<h->sm_count * 4, 256, 0, st>>>(acc, ctr, cap, k_to_s, 0, parent);
         k_phaseb_cross<<<h->sm_count * 8, 256, 0, st>>>(rest, rcap, parent, ctr, todo, cap);
         mark(h, "round2 begin/prune/cross");
-        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, tworef_q, acc, 0, nullptr);
-        k_tier2_tworef<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, tworef_q, cap, generic_q, acc, nullptr, 1);
+        k_tier2<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, todo, cap, generic_q, acc, 0, nullptr);
         mark(h, "k_tier2 r2");
         k_tier2_generic<<<h->sm_count * 8, 128, 0, st>>>(h->din, tbs, pr, ctr, generic_q, cap, acc, 0, nullptr, 1);
-        h->launches += 12;                          // phase B: split, 2 x (k_tier2, k_tier2_tworef, k_tier2_generic), resolve, roots, round-2 begin, prune, cross
+        h->launches += 10;                          // phase B: split, 2 x (k_tier2, k_tier2_generic), resolve, roots, round-2 begin, prune, cross
         CK(cudaEventRecord(h->ev[4], st));
         mark(h, "k_tier2_generic r2");
         const bool device_final = stride == 1;      // stride mode: the forest needs every rank's edges -> host replay after the gather
@@ -1020,7 +1018,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             // a buffer was too small: the counters keep counting past the capacity, so they tell the size to retry with
             // (a list that overflowed may have starved the lists behind it, hence the loop)
             const DevCounters &k = h->counters;
-            const unsigned long long need_e = std::max(std::max(k.n_todo, k.n_todo_r1), std::max(std::max(k.n_generic_q, k.n_tworef_q), (unsigned long long)n + k.n_accept));
+            const unsigned long long need_e = std::max(std::max(k.n_todo, k.n_todo_r1), std::max(k.n_generic_q, (unsigned long long)n + k.n_accept));
             bool retry = false;
             if (k.n_cand > ccap) { h->cand_cap = k.n_cand + k.n_cand / 8 + 1024; retry = true; }
             if (k.n_rest > rcap) { h->rest_cap = k.n_rest + k.n_rest / 8 + 1024; retry = true; }

@@ -82,7 +82,6 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned long long n_valid, n_groups, n_work, c3_words, pairs_compared, pairs_candidate, n_buckets;
     unsigned long long n_cand, n_todo, n_generic, n_generic_q, n_accept, n_kept, pairs_tier2;
     unsigned long long n_accept_r1, n_generic_r1, n_todo_r1, n_rest;
-    unsigned long long n_tworef_q, n_tworef_r1;      // queued pairs whose entries carry different germline sequences (k_tier2_tworef)
     unsigned long long work_next;   // dynamic tile scheduler
     unsigned long long pack_bytes[32];      // V..J bytes read + t2 row bytes written by k_pack_t2 (needed entries only)
     unsigned long long inplace_bytes[32];   // V..J bytes staged by k_pack_t2 (spread over 32 slots to keep the atomics apart)

@@ -888,20 +888,8 @@ __device__ __forceinline__ uint32_t mask_vs_ref(const DevIn &in, const RefSet &r
 // Returns accept_reason (0 = reject), or -1 when a germline holds a non-ACGT byte (reference-vs-reference differences cannot
 // be read off the planes then: the bytewise kernels take the pair).
 __device__ __noinline__ int evaluate_tworef(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa, uint32_t sb,
-                                            int *cd_out, int *d_out) {
+                                            int cd0, int cd1, int *d_out) {
     const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
-    int cd0 = 0, cd1 = 0;
-    {
-        const uint32_t cl0 = m1.cl[0], total = cl0 + m1.cl[1], W = max(1u, (total + 31) / 32);
-        int cdt = 0;
-        for (uint32_t w = 0; w < W; w++) {
-            const uint32_t Dc = (tb.c3[m1.c3off + w] ^ tb.c3[m2.c3off + w]) | (tb.c3[m1.c3off + W + w] ^ tb.c3[m2.c3off + W + w]);
-            cdt += __popc(Dc);
-            cd0 += __popc(Dc & range_mask((int)w, 0, (int)cl0));
-        }
-        cd1 = cdt - cd0;
-    }
-    *cd_out = cd0 + cd1; *d_out = 0;
     PairCounts pc;
     pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1; pc.refdiff = 0;
     for (int c = 0; c < 2; c++)
@@ -1048,7 +1036,7 @@ __device__ __forceinline__ int evaluate_thread(const DevIn &in, const DevTables 
     if (generic) { *bytes += 2ull * (48ull * nblk + 128ull); return -1; }
     if (m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] || m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1]) {
         *bytes += 2ull * (48ull * nblk + 128ull);
-        return -2;        // different germline sequences: k_tier2_tworef (dense, one thread per such pair) or the parked-walk kernel
+        return evaluate_tworef(in, tb, pr, ctr, sa, sb, cd0, cd1, d_out);      // different germline sequences: masks rebuilt from the germline planes
     }
     {
         // No shared mutation is possible when one of the entries has none (shares <= each entry's own count of germline
@@ -1217,7 +1205,7 @@ __global__ void __launch_bounds__(256) k_phaseb_cross(const uint2 *__restrict__ 
 }
 
 __global__ void __launch_bounds__(128, 5) k_tier2(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *todo,
-                                               unsigned long long cand_cap, uint2 *generic_q, uint2 *tworef_q, ejoin_raw_edge_t *acc, uint32_t k_base,
+                                               unsigned long long cand_cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t k_base,
                                                uint32_t *parent_min) {
     unsigned long long ntodo = ctr->n_todo;
     if (ntodo > cand_cap) ntodo = cand_cap;
@@ -1232,13 +1220,9 @@ __global__ void __launch_bounds__(128, 5) k_tier2(DevIn in, DevTables tb, DevPar
             bool scored;
             reason = evaluate_thread(in, tb, pr, ctr, c.x, c.y, &cd, &d, &err, &scored, &my_bytes);
             my_pairs += scored;
-            if (reason == -1) {
+            if (reason < 0) {
                 unsigned long long q = atomicAdd(&ctr->n_generic_q, 1ull);
                 if (q < cand_cap) generic_q[q] = c;            // c.x < c.y positions: already k1 < k2
-                reason = 0;
-            } else if (reason == -2) {
-                unsigned long long q = atomicAdd(&ctr->n_tworef_q, 1ull);
-                if (q < cand_cap) tworef_q[q] = c;
                 reason = 0;
             }
             accepted = reason != 0;
@@ -1255,37 +1239,6 @@ __global__ void __launch_bounds__(128, 5) k_tier2(DevIn in, DevTables tb, DevPar
         my_bytes += __shfl_xor_sync(0xFFFFFFFFu, my_bytes, o);
     }
     if ((threadIdx.x & 31) == 0 && my_pairs) { atomicAdd(&ctr->pairs_tier2, my_pairs); atomicAdd(&ctr->t2_alg_bytes, my_bytes); }
-}
-
-// The queued pairs whose entries carry different germline sequences: one thread per pair, all lanes on the same (long) path —
-// inside k_tier2 or the phase-A walks one such pair would hold its warp's 31 other lanes for the whole evaluation.
-__global__ void __launch_bounds__(128) k_tier2_tworef(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, const uint2 *tworef_q,
-                                                      unsigned long long cap, uint2 *generic_q, ejoin_raw_edge_t *acc, uint32_t *parent_min, int round2) {
-    const unsigned long long q_begin = round2 ? ctr->n_tworef_r1 : 0ull;
-    unsigned long long nq = ctr->n_tworef_q;
-    if (nq > cap) nq = cap;
-    const unsigned long long span = nq > q_begin ? nq - q_begin : 0ull;
-    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < ((span + 31) & ~31ull); t += (unsigned long long)gridDim.x * blockDim.x) {
-        bool accepted = false;
-        uint32_t k1 = 0, k2 = 0;
-        int cd = 0, d = 0, reason = 0, err = 0;
-        if (t < span) {
-            const uint2 c = tworef_q[q_begin + t];
-            reason = evaluate_tworef(in, tb, pr, ctr, c.x, c.y, &cd, &d);
-            if (reason == -1) {                       // a germline with a non-ACGT byte: the bytewise kernel takes it
-                unsigned long long q = atomicAdd(&ctr->n_generic_q, 1ull);
-                if (q < cap) generic_q[q] = c;
-                reason = 0;
-            }
-            const EntryMeta &m1 = tb.meta[c.x], &m2 = tb.meta[c.y];
-            if (m1.donor_lo != EJOIN_NONE && m2.donor_lo != EJOIN_NONE)
-                err = !(m1.donor_lo == m1.donor_hi && m2.donor_lo == m2.donor_hi && m1.donor_lo == m2.donor_lo);
-            accepted = reason != 0;
-            k1 = m1.k; k2 = m2.k;
-            if (accepted && parent_min) atomicMin(&parent_min[c.y], c.x);
-        }
-        emit_raw(pr, ctr, acc, cap, k1, k2, cd, d, reason, err, accepted);
-    }
 }
 
 // After round 1: an accepted edge (a,b) of a gave-up b is b's tree edge iff a is the minimum
@@ -1308,7 +1261,6 @@ __global__ void k_forced_resolve(ejoin_raw_edge_t *acc, DevCounters *ctr, unsign
 __global__ void k_round2_begin(DevCounters *ctr) {
     ctr->n_accept_r1 = ctr->n_accept;
     ctr->n_generic_r1 = ctr->n_generic_q;
-    ctr->n_tworef_r1 = ctr->n_tworef_q;
     ctr->n_todo_r1 = ctr->n_todo;
     ctr->n_todo = 0;
 }
@@ -2083,7 +2035,6 @@ __global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb,
                         r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
                         if (li > start) evals += scored;                      // slot `start` was already counted by k_phase_a
                     }
-                    if (lane == 0 && r == -2) r = evaluate_tworef(in, tb, pr, ctr, min(a, s), max(a, s), &cd, &d);      // -1 again: a germline with non-ACGT bytes
                     r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
                     cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
                     if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
