@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-from-structs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,12 +267,14 @@ def main():
         st = j.run_resident()
     barrier()
     t0 = time.perf_counter()
-    acc = {}
+    acc, stage_acc = {}, {}
     for _ in range(K):
         st = j.run_resident()
         for k2, v in st.items():
             if k2.startswith("ms_"):
                 acc[k2] = acc.get(k2, 0.0) + v
+        for name, v in j.stage_times():                 # CUDA events on the launching stream, between the pipeline stages
+            stage_acc[name] = stage_acc.get(name, 0.0) + v
     barrier()
     dev_s = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -297,45 +300,49 @@ def main():
     except Exception:
         pass
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
-    # Event-timed single kernels (library stats, CUDA events on the launching stream): the sweep and the V..J pack are one
-    # launch each; "tier2" is the group of scoring kernels (phase A, phase B rounds), shown for context only.
-    kern = {"k_sweep": (ms.get("ms_kernel_tier1", 0), st["alg_bytes_tier1"]),
-            "k_pack_t2": (ms.get("ms_kernel_pack_t2", 0), st["alg_bytes_pack_t2"])}
-    dom = max(kern, key=lambda k2: kern[k2][0])
-    dom_ms, dom_bytes = kern[dom]
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # Every pipeline stage is timed live with CUDA events on the launching stream (ejoin_stage_time); the roofline entry is for the
+    # longest single-kernel stage.  k_sweep is bound by the popcount (XU) pipe, the pack and scoring kernels by memory.
+    stages = {k2: v / K for k2, v in stage_acc.items()}
+    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    xu_peak = 148 * 16 * sm_clock                        # POPC lanes per SM and clock x SMs
+    cand = {}
+    if stages.get("k_sweep"):
+        t = stages["k_sweep"] * 1e-3
+        popc = st["alg_bytes_tier1"] / 16.0              # one POPC per 32-base word and compared pair
+        cand["k_sweep"] = {"bound": "xu_popc", "kernel": "k_sweep", "achieved": popc / t, "peak": xu_peak, "unit": "POPC/s", "frac": popc / t / xu_peak,
+                           "algorithmic_popc_per_launch": popc, "kernel_ms": stages["k_sweep"],
+                           "hbm_equivalent": {"achieved": st["alg_bytes_tier1"] / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                                              "note": "2 x 8W bytes per compared pair as if streamed: rows are staged in shared memory by TMA and reused ~n_group "
+                                                      "times on chip, so this exceeds the HBM peak; it only shows HBM is not the binding roof"},
+                           "note": "all-pairs CDR3 XOR/popcount; ncu: XU pipe 75 %, ALU 71 %, issue slots 66 % busy, DRAM 2 % (profiles/r02l_ncu_metrics.json)"}
+    if stages.get("k_pack_t2"):
+        t = stages["k_pack_t2"] * 1e-3
+        cand["k_pack_t2"] = {"bound": "hbm", "kernel": "k_pack_t2_2bit (+ k_pack_t2 for the entries with an ASCII chain)", "achieved": st["alg_bytes_pack_t2"] / t / 1e9,
+                             "peak": peak_hbm, "unit": "GB/s", "frac": st["alg_bytes_pack_t2"] / t / 1e9 / peak_hbm,
+                             "algorithmic_bytes_per_launch": int(st["alg_bytes_pack_t2"]), "kernel_ms": stages["k_pack_t2"],
+                             "note": "2-bit V..J words in (8 B per 32 bases), H/L/M plane rows out (12 B per 32 bases), needed entries only; ncu: issue 36 %, "
+                                     "19 of 32 lanes, DRAM 16 %: bound by the bit transpose and the dependent meta -> offset -> words loads, not by HBM"}
+    dom = max(cand, key=lambda k2: cand[k2]["kernel_ms"]) if cand else None
+    roofline = dict(cand[dom]) if dom else {"bound": "hbm", "achieved": 0.0, "peak": peak_hbm, "unit": "GB/s", "frac": None}
+    roofline["peak_source"] = ("MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)") if roofline["bound"] == "hbm" \
+        else "16 POPC lanes per SM and clock x 148 SMs x the SM clock sampled under load"
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tj.get("workload") == args.workload and args.scale == 1.0 and world == 1:
             traffic = tj.get(dom)
     except Exception:
         pass
-    notes = {"k_pack_t2": "streams the needed entries' ASCII V..J bytes once and writes their bit-plane rows; ALU-bound on the byte-to-plane "
-                          "SWAR arithmetic (ncu: ALU pipe 55%, issue 49%, DRAM 17%), not at the HBM roofline (profiles/README.md)",
-             "k_sweep": "all-pairs CDR3 XOR/popcount on rows staged in shared memory by TMA: each row is read once from HBM and reused "
-                        "~n_group times on chip, so achieved/peak is an equivalent streaming rate, not an HBM utilisation; the kernel "
-                        "is bound by the popcount (XU) pipe and issue slots (profiles/README.md)"}
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_hbm, "unit": "GB/s",
-                "frac": achieved / peak_hbm if peak_hbm else None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_traffic.json" if traffic else None,
-                "note": notes[dom], "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
-                "kernel_ms_all": {"k_sweep": kern["k_sweep"][0], "k_pack_t2": kern["k_pack_t2"][0],
-                                  "k_meta+k_pack_c3+k_pack_t2": ms.get("ms_kernel_pack", 0),
-                                  "scoring kernels (phase A + phase B)": ms.get("ms_kernel_tier2", 0), "other": ms.get("ms_kernel_other", 0)},
-                "algorithmic_bytes_all": {"k_sweep": int(st["alg_bytes_tier1"]), "k_pack_t2": int(st["alg_bytes_pack_t2"]),
-                                          "scoring kernels": int(st["alg_bytes_tier2"])},
-                "device_ms_per_step": ms.get("ms_device")}
-    # supplementary: k_sweep against the pipe that bounds it.  One POPC per 32-base word and pair (alg_bytes_tier1 / 16);
-    # 16 POPC lanes per SM and clock (the rate at which the kernel saturates on the giant-bucket workload C4: 90 %).
-    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
-    sweep_ms = kern["k_sweep"][0]
-    popc = st["alg_bytes_tier1"] / 16.0
-    xu_peak = 148 * 16 * sm_clock
-    roofline["popcount_pipe"] = {"kernel": "k_sweep", "achieved": popc / (sweep_ms * 1e-3) if sweep_ms > 0 else 0.0, "peak": xu_peak,
-                                 "unit": "POPC/s", "frac": (popc / (sweep_ms * 1e-3) / xu_peak) if sweep_ms > 0 else None,
-                                 "note": "pair compares only; the survivor bookkeeping (ffs) shares the pipe: ncu reports it 73% busy at C3"}
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = "ncu --set full capture, profiles/r02_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None
+    roofline["other_kernels"] = {k2: {kk: v for kk, v in c.items() if kk in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")} for k2, c in cand.items() if k2 != dom}
+    roofline["stage_ms"] = {k2: round(v, 4) for k2, v in stages.items()}
+    t2ms = max(ms.get("ms_kernel_tier2", 0), 1e-9)
+    roofline["scoring_group"] = {"kernels": "k_phase_a, k_phase_a_pending, k_phaseb_split, k_tier2 x2, k_tier2_generic x2", "ms": ms.get("ms_kernel_tier2", 0),
+                                 "algorithmic_bytes": int(st["alg_bytes_tier2"]), "achieved_gbs": st["alg_bytes_tier2"] / t2ms / 1e6,
+                                 "frac_of_hbm": st["alg_bytes_tier2"] / t2ms / 1e6 / peak_hbm,
+                                 "note": "latency-bound gathers of cold rows (two 128-byte records + two t2 rows per scored pair)"}
+    roofline["device_ms_per_step"] = ms.get("ms_device")
     config.update({"n_info": sp.n_info})
     workload_stats = {"candidate_pairs": pairs_total, "pairs_compared_tier1": int(st["pairs_compared"]),
                       "pairs_tier2": int(st["pairs_tier2"]), "pairs_accepted": int(st["pairs_accepted"]), "joins_emitted": int(n_joins),
@@ -358,6 +365,26 @@ def main():
     if e2e_ascii_s is not None:
         line["e2e_variants"] = {"ascii_parallel_arrays": {"ms_per_step": e2e_ascii_s / K * 1e3, "value": pairs_total * K / e2e_ascii_s,
                                                           "h2d_bytes_per_step": ascii_h2d}}
+    # the same join from the caller's array-of-struct inputs, and the cold first call of a fresh process (tools/from_structs.cpp)
+    fs = os.path.join(ROOT, "tools", "from_structs")
+    if world == 1 and os.path.exists(fs) and not args.no_from_structs:
+        try:
+            out = subprocess.run([fs, args.workload, str(args.scale), "3", "1"], capture_output=True, text=True, timeout=240)
+            r = json.loads(out.stdout.strip().splitlines()[-1])
+            line["e2e_from_structs"] = {"ms_per_step": r["warm"]["ms_best"], "value": pairs_total / (r["warm"]["ms_best"] * 1e-3), "unit": "pairs/s",
+                                        "breakdown_ms": {"flatten (Vec<CloneInfo> -> compact pack)": r["warm"]["ms_pack"], "ejoin_run": r["warm"]["ms_run"],
+                                                         "raw_joins + EquivRel": r["warm"]["ms_unpack"]},
+                                        "host_threads": r["threads"], "note": "enclone_b200/host/join_exacts.hpp: AoS structs in, raw_joins + EquivRel out; handle "
+                                        "created beforehand; best of 3"}
+            line["e2e_cold"] = {"ms_total": r["cold"]["ms_total"], "breakdown_ms": {"ejoin_create (CUDA context, streams)": r["cold"]["ms_create"],
+                                                                                   "flatten incl. first pinned allocations": r["cold"]["ms_pack"],
+                                                                                   "first ejoin_run (p1 / mult tables, device arenas)": r["cold"]["ms_run"],
+                                                                                   "raw_joins + EquivRel": r["cold"]["ms_unpack"]},
+                                "value": pairs_total / (r["cold"]["ms_total"] * 1e-3), "unit": "pairs/s",
+                                "note": "fresh process, first call: join_exacts runs once per enclone process, so this is the latency a user sees unless the "
+                                        "handle is created at program start (INTEGRATION.md)"}
+        except Exception as e:                       # the tool is optional evidence, never a reason to lose the bench line
+            line["e2e_from_structs"] = {"unavailable": str(e)[:200]}
     if not args.no_cpu_baseline:
         val, info = cpu_baseline(sp, params, steps=2, best=True)
         line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}

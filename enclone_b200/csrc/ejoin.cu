@@ -114,6 +114,7 @@ struct ejoin_handle {
     bool debug = false;
     std::vector<cudaEvent_t> mark_ev;
     std::vector<const char *> mark_name;
+    std::vector<float> mark_ms;            // stage times of the last pipeline run (CUDA events on the launching stream)
     size_t n_marks = 0;
     // overlapped upload: small arrays first, then the tig arena in chunks, each with an event
     cudaEvent_t ev_copy0 = nullptr, ev_early = nullptr, ev_small = nullptr, ev_chunk[8] = {};
@@ -312,6 +313,7 @@ extern "C" void ejoin_destroy(ejoin_handle_t *h) {
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pin2) cudaFreeHost(h->pin2);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : h->mark_ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->ev_chunk) if (e) cudaEventDestroy(e);
     if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
     if (h->ev_small) cudaEventDestroy(h->ev_small);
@@ -746,13 +748,14 @@ int prepare_tables(ejoin_handle *h, int is_bcr) {
     return 0;
 }
 
-static void mark(ejoin_handle *h, const char *name) {
-    if (!h->debug) return;
+static void mark(ejoin_handle *h, const char *name) {      // one event per pipeline stage, always on (a record costs ~1 us of host time)
     if (h->n_marks == h->mark_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); h->mark_ev.push_back(e); h->mark_name.push_back(name); }
     h->mark_name[h->n_marks] = name;
     cudaEventRecord(h->mark_ev[h->n_marks++], h->st);
 }
 static void print_marks(ejoin_handle *h) {
+    h->mark_ms.assign(h->n_marks, 0.0f);
+    for (size_t i = 1; i < h->n_marks; i++) cudaEventElapsedTime(&h->mark_ms[i], h->mark_ev[i - 1], h->mark_ev[i]);
     if (!h->debug || h->n_marks < 2) return;
     const DevCounters &k = h->counters;
     fprintf(stderr, "[ejoin] n=%u cand=%llu rest=%llu todo_r1=%llu todo_r2=%llu accept_r1=%llu accept=%llu pending=%u generic=%llu tier2_pairs=%llu kept=%llu\n", h->n,
@@ -1306,6 +1309,13 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     out->stats.d2h_bytes = h->stats.d2h_bytes;
     out->stats.gpu_launches = h->launches;
     return 0;
+}
+
+extern "C" int ejoin_stage_time(const ejoin_handle_t *h, int index, const char **name, double *ms) {
+    if (!h || index < 0 || (size_t)index + 1 >= h->mark_ms.size() || (size_t)index + 1 >= h->n_marks) return EJOIN_E_ARG;
+    if (name) *name = h->mark_name[index + 1];
+    if (ms) *ms = h->mark_ms[index + 1];
+    return EJOIN_OK;
 }
 
 extern "C" void ejoin_result_free(ejoin_result_t *r) {

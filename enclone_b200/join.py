@@ -150,6 +150,15 @@ class Joiner:
         self.L.ejoin_raw_free(ep)
         return 1, None, raw, st.as_dict()
 
+    def stage_times(self):
+        """[(stage name, device ms)] of the last pipeline run on this handle (ejoin_stage_time: CUDA events)."""
+        out, i = [], 0
+        name, ms = C.c_char_p(), C.c_double()
+        while self.L.ejoin_stage_time(self.h, i, C.byref(name), C.byref(ms)) == 0:
+            out.append((name.value.decode(), ms.value))
+            i += 1
+        return out
+
     def comm_init(self, comm_id, rank, world):
         """Join the library's own communicator (ejoin_comm_init): `comm_id` is the 128-byte id rank 0 got from
         comm_id() and handed to every rank."""

@@ -242,6 +242,10 @@ const char *ejoin_last_error(const ejoin_handle_t *h);
  * valid until the next call on the handle. */
 int  ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pack, ejoin_result_t *out);
 void ejoin_result_free(ejoin_result_t *r);
+/* Device time of stage `index` (0, 1, ...) of the handle's last pipeline run, from CUDA events recorded on the launching
+ * stream between the stages (a stage = one kernel or a short group: "k_sweep", "k_pack_t2", "sort entries", ...).
+ * Returns EJOIN_E_ARG past the last stage. */
+int  ejoin_stage_time(const ejoin_handle_t *h, int index, const char **name, double *ms);
 
 /* Multi-GPU decomposition (one process per GPU):
  *   every rank: ejoin_plan_shards() -> which buckets this rank owns (contiguous, cost-balanced ranges),
