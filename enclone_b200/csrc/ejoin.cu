@@ -482,7 +482,6 @@ int upload_ranges(ejoin_handle *h, const ejoin_pack_t *pk, const Ranges &rg_in, 
     sz.take((c2 ? 8 : 1) * (chi - clo) + 64); sz.take(pk->refseq_arena_bytes + 64); sz.take(thi - tlo + 64 + 512);
     sz.take(8 * (whi - wlo) + 256); sz.take(sizeof(ejoin_entry_rec_t) * n1);
     sz.take(4 * (size_t)std::max(1u, pk->n_refseq)); sz.take(12 * ((size_t)pk->refseq_arena_bytes / 32 + 3 * (size_t)pk->n_refseq + 8));   // germline planes
-    sz.take(4 * (size_t)std::max(1u, pk->n_refseq));
     CK(h->in_arena.buf.ensure(sz.off + 4096));
     h->in_arena.reset();
     Arena &A = h->in_arena;
@@ -594,8 +593,6 @@ int upload_ranges(ejoin_handle *h, const ejoin_pack_t *pk, const Ranges &rg_in, 
         CK(up(d.ref_plane_off, h->ref_plane_off.data(), pk->n_refseq));
         d.ref_planes = A.take<uint32_t>(3 * (size_t)d.ref_plane_words);
         CK(cudaMemsetAsync(d.ref_planes, 0, 12 * (size_t)d.ref_plane_words, h->st_copy));
-        d.ref_has_n = A.take<uint32_t>(pk->n_refseq ? pk->n_refseq : 1);
-        CK(cudaMemsetAsync(d.ref_has_n, 0, 4 * (size_t)(pk->n_refseq ? pk->n_refseq : 1), h->st_copy));
     }
     CK(cudaEventRecord(h->ev_small, h->st_copy));       // everything but the V..J bytes: keys / sort / groups / meta / c3 can start
     h->tigs_in_place = in_place;

@@ -157,7 +157,6 @@ struct DevIn {
     // plane p of word w of sequence i = ref_planes[p * ref_plane_words + ref_plane_off[i] + w], p = H, L, N (not ACGT)
     const uint32_t *ref_plane_off;
     uint32_t *ref_planes;
-    uint32_t *ref_has_n;            // [n_refseq] nonzero: the sequence holds a byte outside ACGT
     uint32_t ref_plane_words;
 };
 

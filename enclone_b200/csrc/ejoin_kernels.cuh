@@ -480,7 +480,6 @@ __global__ void __launch_bounds__(32) k_pack_ref(DevIn in) {
         in.ref_planes[o + w] = H & valid;
         in.ref_planes[TW + o + w] = L & valid;
         in.ref_planes[2 * TW + o + w] = N & valid;
-        if (N & valid) in.ref_has_n[i] = 1u;
     }
 }
 
@@ -855,123 +854,6 @@ __device__ __forceinline__ void emit_raw(const DevParams &pr, DevCounters *ctr, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pairs whose entries were assigned DIFFERENT germline sequences (another allele of the V gene, another donor's
-// reference, a V reference edited for an insertion; 3 % of the scored pairs of a repertoire): join_one counts shares and
-// indeps against the references of k1 and, when the reference ids differ (nrefs = 2), against those of k2 as well.  An
-// entry's M plane only knows its OWN germline, so the mask of the other entry against that germline is rebuilt here, word by
-// word, from the other entry's H / L planes and the germline's bit planes (k_pack_ref) — the same expression k_pack_t2 uses.
-// One thread per pair, no bytes touched.  (These pairs used to go to the warp-per-pair bytewise kernels.)
-// ---------------------------------------------------------------------------------------------
-struct RefSet { uint32_t vo, jo; int vend, jstart, joff; };      // plane offsets of the V / J germline, window ends, J alignment
-__device__ __forceinline__ RefSet ref_set(const DevIn &in, const EntryMeta &m, int c) {
-    RefSet r;
-    r.vo = in.ref_plane_off[m.vs[c]]; r.jo = in.ref_plane_off[m.js[c]];
-    r.vend = m.vend[c]; r.jstart = m.jstart[c];
-    r.joff = (int)m.len[c] - (int)in.refseq_len[m.js[c]];        // tig position of the J germline's first base
-    return r;
-}
-// positions of word w (32 bases from p0) where a read with planes (H, L) differs from the germline set r, inside r's windows
-__device__ __forceinline__ uint32_t mask_vs_ref(const DevIn &in, const RefSet &r, uint32_t H, uint32_t L, int w, uint32_t valid) {
-    const uint32_t TW = in.ref_plane_words;
-    const int p0 = 32 * w;
-    uint32_t mm = 0;
-    const uint32_t inV = low_bits(r.vend - p0) & valid, inJ = valid & ~low_bits(r.jstart - p0);
-    if (inV) { const uint32_t o = r.vo + (uint32_t)w; mm |= ((H ^ in.ref_planes[o]) | (L ^ in.ref_planes[TW + o]) | in.ref_planes[2 * TW + o]) & inV; }
-    if (inJ) {
-        const int off = p0 - r.joff;
-        const uint32_t *g = in.ref_planes + r.jo + (off >> 5);
-        const uint32_t bo = (uint32_t)off & 31u;
-        mm |= ((H ^ __funnelshift_r(g[0], g[1], bo)) | (L ^ __funnelshift_r(g[TW], g[TW + 1], bo)) | __funnelshift_r(g[2 * TW], g[2 * TW + 1], bo)) & inJ;
-    }
-    return mm;
-}
-// Returns accept_reason (0 = reject), or -1 when a germline holds a non-ACGT byte (reference-vs-reference differences cannot
-// be read off the planes then: the bytewise kernels take the pair).
-__device__ __noinline__ int evaluate_tworef(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa, uint32_t sb,
-                                            int cd0, int cd1, int *d_out) {
-    const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
-    PairCounts pc;
-    pc.cd0 = cd0; pc.cd1 = cd1; pc.nrefs = 1; pc.refdiff = 0;
-    for (int c = 0; c < 2; c++)
-        if (m1.vref[c] != m2.vref[c] || m1.dref[c] != m2.dref[c] || m1.jref[c] != m2.jref[c]) pc.nrefs = 2;
-    const bool two = pc.nrefs == 2;
-    const bool want_refdiff = two && pr.degradation_mode != 1;
-    if (want_refdiff)
-        for (int c = 0; c < 2; c++)
-            if (in.ref_has_n[m1.vs[c]] | in.ref_has_n[m2.vs[c]] | in.ref_has_n[m1.js[c]] | in.ref_has_n[m2.js[c]]) return -1;
-    const int cd = cd0 + cd1;
-    const bool do_io = cd >= pr.cdr3_mult;
-    const uint32_t TW = in.ref_plane_words;
-    int diffs = 0, s0 = 0, s1 = 0, pb0 = 0, pa1 = 0, io0 = 0, io1 = 0, refdiff = 0, dfw = 0, d12 = 0;
-    int f1 = 0, c1 = 0, f2 = 0, c2_ = 0, f3 = 0;
-    const bool reg = pr.is_bcr && region_bounds(m1, m2, &f1, &c1, &f2, &c2_, &f3);
-    const uint32_t *w1 = (const uint32_t *)(tb.t2 + m1.t2off), *w2 = (const uint32_t *)(tb.t2 + m2.t2off);
-    int blk0 = 0;
-    for (int c = 0; c < 2; c++) {
-        const int n = m1.len[c], nw = (n + 31) / 32;
-        const RefSet r1 = ref_set(in, m1, c), r2 = ref_set(in, m2, c);
-        const int a1 = m1.cs[c], a2 = m2.cs[c], cl = m1.cl[c];
-        const bool vdiff = m1.vs[c] != m2.vs[c], jdiff = m1.js[c] != m2.js[c];
-        const int vl1 = (int)in.refseq_len[m1.vs[c]], vl2 = (int)in.refseq_len[m2.vs[c]], jl1 = n - r1.joff, jl2 = n - r2.joff;
-        if (want_refdiff) refdiff += (vdiff ? abs(vl1 - vl2) : 0) + (jdiff ? abs(jl1 - jl2) : 0);
-        for (int w = 0; w < nw; w++) {
-            const int o = (blk0 + (w >> 2)) * 12 + (w & 3);
-            const uint32_t H1 = __ldg(w1 + o), L1 = __ldg(w1 + o + 4), X1 = __ldg(w1 + o + 8);
-            const uint32_t H2 = __ldg(w2 + o), L2 = __ldg(w2 + o + 4), X2 = __ldg(w2 + o + 8);
-            const uint32_t valid = low_bits(n - 32 * w);
-            const uint32_t Dm = (H1 ^ H2) | (L1 ^ L2);
-            diffs += __popc(Dm);
-            const uint32_t R = do_io ? (range_mask(w, a1, a1 + cl) | range_mask(w, a2, a2 + cl)) : 0u;
-            // u = 0: the references of k1 (its own M plane; k2 against them rebuilt)
-            const uint32_t Mb0 = (vdiff || jdiff) ? mask_vs_ref(in, r1, H2, L2, w, valid) : X2;
-            s0 += __popc(X1 & Mb0 & ~Dm); pb0 += __popc(Mb0);
-            if (do_io) io0 += __popc(X1 & Dm & ~R) + __popc(Mb0 & Dm & ~R);
-            if (two) {       // u = 1: the references of k2
-                const uint32_t Ma1 = (vdiff || jdiff) ? mask_vs_ref(in, r2, H1, L1, w, valid) : X1;
-                s1 += __popc(Ma1 & X2 & ~Dm); pa1 += __popc(Ma1);
-                if (do_io) io1 += __popc(Ma1 & Dm & ~R) + __popc(X2 & Dm & ~R);
-            }
-            if (reg && c == 0) { dfw += __popc(Dm & range_mask(w, f1, c1)); d12 += __popc(Dm & (range_mask(w, c1, f2) | range_mask(w, c2_, f3))); }
-            if (want_refdiff) {
-                // positions at which the two germlines differ: V left-aligned (same word as the read), J right-aligned (tig coordinates)
-                if (vdiff) {
-                    const uint32_t ov = low_bits(min(vl1, vl2) - 32 * w);
-                    if (ov) refdiff += __popc(((in.ref_planes[r1.vo + w] ^ in.ref_planes[r2.vo + w]) | (in.ref_planes[TW + r1.vo + w] ^ in.ref_planes[TW + r2.vo + w])) & ov);
-                }
-                if (jdiff) {
-                    const uint32_t ov = valid & ~low_bits(max(r1.joff, r2.joff) - 32 * w);       // tig positions covered by both J germlines
-                    if (ov) {
-                        const int o1 = 32 * w - r1.joff, o2 = 32 * w - r2.joff;
-                        const uint32_t *g1 = in.ref_planes + r1.jo + (o1 >> 5), *g2 = in.ref_planes + r2.jo + (o2 >> 5);
-                        const uint32_t b1 = (uint32_t)o1 & 31u, b2 = (uint32_t)o2 & 31u;
-                        const uint32_t hd = __funnelshift_r(g1[0], g1[1], b1) ^ __funnelshift_r(g2[0], g2[1], b2);
-                        const uint32_t ld = __funnelshift_r(g1[TW], g1[TW + 1], b1) ^ __funnelshift_r(g2[TW], g2[TW + 1], b2);
-                        refdiff += __popc((hd | ld) & ov);
-                    }
-                }
-            }
-        }
-        blk0 += (n + 127) / 128;
-    }
-    const int mt1 = (int)m1.m[0] + (int)m1.m[1], mt2 = (int)m2.m[0] + (int)m2.m[1];
-    pc.diffs = diffs; pc.refdiff = refdiff;
-    pc.shares[0] = s0; pc.indeps[0] = mt1 + pb0 - 2 * s0; pc.indeps_out[0] = do_io ? io0 : (1 << 20);
-    pc.shares[1] = two ? s1 : s0; pc.indeps[1] = two ? pa1 + mt2 - 2 * s1 : pc.indeps[0]; pc.indeps_out[1] = two ? (do_io ? io1 : (1 << 20)) : pc.indeps_out[0];
-    if (!pr.is_bcr || pr.max_diffs < 1000000) {
-        int cap = pr.max_diffs;
-        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
-        if (diffs > cap) return 0;
-    }
-    int kk, mo; double p1, mult, score;
-    const int reason = decide_score(pr, tb, m1, m2, pc, ctr, tb.p1tab[(int)m1.len[0] + (int)m1.len[1]], tb.multinfo[((uint32_t)m1.cl[0] << 8) | m1.cl[1]],
-                                    &kk, d_out, &mo, &p1, &mult, &score);
-    if (!reason) return 0;
-    pc.lfw = 0; pc.dfw = pc.dc12 = pc.l12 = 0;
-    if (reg) { pc.dfw = dfw; pc.lfw = c1 - f1; pc.dc12 = d12; pc.l12 = (f2 - c1) + (f3 - c2_); }
-    return decide_gates(pr, pc, mo) ? reason : 0;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Thread-level full evaluation of one pair (positions sa, sb of one comparison group; the entry
 // with the smaller info index is k1).  Bit-parallel over the t2 rows.  Returns accept_reason
 // (0 = reject) or -1 when the pair needs the bytewise path (has_del / non-ACGT / overlapping
@@ -1032,12 +914,9 @@ __device__ __forceinline__ int evaluate_thread(const DevIn &in, const DevTables 
     if (!meta_gates(pr, in, m1, m2, cd, err_out)) return 0;
     *scored = true;
     const uint32_t nb0 = ((uint32_t)m1.len[0] + 127) / 128, nblk = nb0 + ((uint32_t)m1.len[1] + 127) / 128;
-    const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) != 0;
+    const bool generic = ((m1.flags | m2.flags) & (FLAG_GENERIC0 | FLAG_GENERIC1)) || m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] ||
+                         m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1];
     if (generic) { *bytes += 2ull * (48ull * nblk + 128ull); return -1; }
-    if (m1.vs[0] != m2.vs[0] || m1.vs[1] != m2.vs[1] || m1.js[0] != m2.js[0] || m1.js[1] != m2.js[1]) {
-        *bytes += 2ull * (48ull * nblk + 128ull);
-        return evaluate_tworef(in, tb, pr, ctr, sa, sb, cd0, cd1, d_out);      // different germline sequences: masks rebuilt from the germline planes
-    }
     {
         // No shared mutation is possible when one of the entries has none (shares <= each entry's own count of germline
         // differences inside the windows): then d = 0, p1 = 1 and the score is the CDR3 multiplier alone.  If that
