@@ -157,6 +157,7 @@ struct ejoin_handle {
     // work pointers of the last pipeline run
     EntryMeta *meta = nullptr; uint32_t *c3 = nullptr; uint4 *t2 = nullptr; uint32_t *k_to_s = nullptr;
     unsigned long long *kept_keys = nullptr, *kept_vals = nullptr;
+    uint32_t *w_parent = nullptr, *w_comp_size = nullptr; unsigned long long *w_best = nullptr, *w_f0_key = nullptr, *w_f0_val = nullptr;   // forest scratch of the last run
     DevCounters counters;
     ejoin_stats_t stats;
     uint64_t launches = 0;
@@ -856,6 +857,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint32_t *comp_size = A.take<uint32_t>(n);
         void *cub_tmp = A.take<char>(cub_bytes + 256);
         h->meta = meta; h->c3 = c3; h->t2 = t2; h->k_to_s = k_to_s; h->kept_keys = pk_out; h->kept_vals = pv_out;
+        h->w_parent = parent; h->w_best = best; h->w_comp_size = comp_size; h->w_f0_key = f0_key; h->w_f0_val = f0_val;
         DevCounters *ctr = (DevCounters *)h->d_counters.p;
         const unsigned nb256 = (n + 255) / 256;
         cudaStream_t st = h->st;
@@ -1557,10 +1559,22 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
         size_t total = 0, off_me = 0;
         for (int r = 0; r < world; r++) { if (r < rank) off_me += counts[r]; total += counts[r]; }
         (void)off_me;
-        unsigned long long *gk = nullptr, *gv = nullptr;
+        unsigned long long *gk = nullptr, *gv = nullptr, *sk_in = nullptr, *sk_out = nullptr, *sv_in = nullptr, *sv_out = nullptr;
+        void *gacc = nullptr, *g_cub = nullptr;
+        uint2 *gends = nullptr;
+        size_t g_cub_bytes = 0;
         if (rank == root) {
-            CK(h->d_gather.ensure(16 * (total + 1)));
-            gk = (unsigned long long *)h->d_gather.p; gv = gk + total;
+            const size_t te = total + 1;
+            cub::DeviceRadixSort::SortPairs(nullptr, g_cub_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                            (unsigned long long *)nullptr, (int)te);
+            CK(h->d_gather.ensure(6 * 8 * te + sizeof(ejoin_raw_edge_t) * te + 8 * te + g_cub_bytes + 4096));
+            char *b = (char *)h->d_gather.p;
+            auto carve = [&](size_t bytes) { char *r = b; b += (bytes + 255) & ~(size_t)255; return r; };
+            gk = (unsigned long long *)carve(8 * te); gv = (unsigned long long *)carve(8 * te);
+            sk_in = (unsigned long long *)carve(8 * te); sk_out = (unsigned long long *)carve(8 * te);
+            sv_in = (unsigned long long *)carve(8 * te); sv_out = (unsigned long long *)carve(8 * te);
+            gacc = carve(sizeof(ejoin_raw_edge_t) * te); gends = (uint2 *)carve(8 * te);
+            g_cub = carve(g_cub_bytes);
         }
         NCK(nc->GroupStart());
         if (rank == root) {
@@ -1581,21 +1595,44 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
                 CK(cudaMemcpyAsync(gk + off, h->kept_keys, 8 * nk, cudaMemcpyDeviceToDevice, st));
                 CK(cudaMemcpyAsync(gv + off, h->kept_vals, 8 * nk, cudaMemcpyDeviceToDevice, st));
             }
-            std::vector<unsigned long long> hk(2 * total + 2);
-            if (total) CK(cudaMemcpyAsync(hk.data(), gk, 16 * total, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            h->stats.d2h_bytes += 16 * total;
-            std::vector<ejoin_raw_edge_t> raw(total);
-            for (size_t i = 0; i < total; i++) {
-                const unsigned long long key = hk[i], val = hk[total + i];
-                raw[i].k1 = (uint32_t)(key >> 32); raw[i].k2 = (uint32_t)key;
-                raw[i].cd = (uint16_t)(val & 0xFFFF); raw[i].d = (uint16_t)((val >> 16) & 0xFFFF); raw[i].flags = (uint32_t)(val >> 32);
+            // The forest over the gathered edges, on this GPU (every entry is resident here in stride mode): Boruvka from singletons —
+            // the gathered set holds every rank's exact tree edges plus the accepted edges it could not prove redundant, so its
+            // minimum spanning forest under the (k1,k2) order is join_core's `pot` (forest) —, then the two-cell rule,
+            // the sort, the payload and finish_join exactly as on one GPU.  No edge visits the host.
+            const uint32_t n = h->n;
+            const unsigned nb256 = (n + 255) / 256;
+            ejoin_raw_edge_t *acc = (ejoin_raw_edge_t *)gacc;
+            if (total) k_kv_to_acc<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gk, gv, total, acc);
+            k_iota_parent<<<nb256, 256, 0, st>>>(h->w_parent, h->w_f0_key, n);
+            k_set_accept<<<1, 1, 0, st>>>(ctr, total);
+            k_fill_u64<<<nb256, 256, 0, st>>>(h->w_best, ~0ull, n);
+            {
+                if (h->bor_grid == 0) { int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_boruvka, 256, 0); h->bor_grid = occ >= 1 ? h->sm_count : 1; }
+                ejoin_raw_edge_t *a_acc = acc; DevCounters *a_ctr = ctr; unsigned long long a_cap = total; const uint32_t *a_kts = h->k_to_s;
+                uint32_t *a_par = h->w_parent; unsigned long long *a_best = h->w_best; uint2 *a_ends = gends;
+                void *args[] = { &a_acc, &a_ctr, &a_cap, &a_kts, &a_par, &a_best, &a_ends };
+                CK(cudaLaunchCooperativeKernel((void *)k_boruvka, dim3(h->bor_grid), dim3(256), args, 0, st));
             }
-            const size_t d2h_before = h->stats.d2h_bytes;
-            const uint64_t launches_before = h->launches;
-            rc = ejoin_finish(h, pk, raw.data(), total, out);
+            CK(cudaMemsetAsync(h->w_comp_size, 0, 4 * (size_t)n, st));
+            k_comp_size<<<nb256, 256, 0, st>>>(h->w_parent, (uint32_t)h->counters.n_valid, h->w_comp_size);
+            k_final_collect<<<h->sm_count * 8, 256, 0, st>>>(h->din, h->w_f0_key, h->w_f0_val, n, acc, ctr, total, h->k_to_s, 0, h->w_parent, h->w_comp_size,
+                                                             h->params.easy, sk_in, sv_in);
+            h->launches += 7;
+            CK(cudaGetLastError());
+            unsigned long long nfin = 0;
+            CK(cudaMemcpyAsync(&nfin, &ctr->n_kept, sizeof(nfin), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (nfin) {
+                int kb = 1;
+                while (kb < 32 && (1ull << kb) < (unsigned long long)n) kb++;
+                size_t tb = g_cub_bytes;
+                cub::DeviceRadixSort::SortPairs(g_cub, tb, sk_in, sk_out, sv_in, sv_out, (int)nfin, 0, 32 + kb, st);
+            }
+            rc = ensure_pin(h, sizeof(ejoin_edge_t) * (nfin + 1) + 4 * ((size_t)n + 1) + 1024);
             if (rc) return rc;
-            h->stats.d2h_bytes += d2h_before; h->launches += 0 * launches_before;
+            static const std::vector<uint2> none;
+            rc = emit_result(h, pk, none, sk_out, (size_t)nfin, 0, out);
+            if (rc) return rc;
         } else CK(cudaStreamSynchronize(st));
     } else {
         // contiguous bucket ranges: the rank's emitted joins are final; build their records here, ship them to rank 0

@@ -2120,3 +2120,19 @@ __global__ void k_gather_edges(const ejoin_edge_t *src, const uint32_t *idx, uin
     const unsigned long long i = t / W, w = t % W;
     if (i < ne) ((unsigned long long *)(dst + i))[w] = ((const unsigned long long *)(src + idx[i]))[w];
 }
+// Stride mode, rank 0 after the gather: the ranks' accepted edges as (key, val) pairs -> the edge array the forest kernels work on,
+// every entry its own component again.
+__global__ void k_kv_to_acc(const unsigned long long *keys, const unsigned long long *vals, unsigned long long ne, ejoin_raw_edge_t *acc) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne) return;
+    ejoin_raw_edge_t e;
+    e.k1 = (uint32_t)(keys[i] >> 32); e.k2 = (uint32_t)keys[i];
+    e.cd = (uint16_t)(vals[i] & 0xFFFF); e.d = (uint16_t)((vals[i] >> 16) & 0xFFFF);
+    e.flags = (uint32_t)(vals[i] >> 32) & ~ACC_SELECTED;
+    acc[i] = e;
+}
+__global__ void k_iota_parent(uint32_t *parent, unsigned long long *f0_key, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { parent[i] = i; f0_key[i] = ~0ull; }
+}
+__global__ void k_set_accept(DevCounters *ctr, unsigned long long n) { ctr->n_accept = n; ctr->n_kept = 0; ctr->bor_active = 0; }
