@@ -123,6 +123,34 @@ def cpu_baseline(sp, params, target_s=12.0, steps=1, warmup=0, best=False):
     import oracle_lib as O
     threads = os.cpu_count() or 1
     O.lib().oracle_prepare(700)
+    # One giant bucket (configuration C4): the reference gives a bucket to ONE rayon task, which at 2e10 pairs would run for hours, so
+    # the sample is the first rows of that bucket's triangle, scored by all threads (the oracle's row-parallel mode), reported as such.
+    import numpy as np
+    from enclone_b200.join import plan_shards
+    _, bs = plan_shards(sp.struct, 1)
+    sizes = np.diff(bs.astype(np.int64))
+    if len(sizes) and sizes.max() >= 50000 and (sizes.max() * (sizes.max() - 1) // 2) > 0.9 * int((sizes * (sizes - 1) // 2).sum()):
+        nb = int(sizes.max())
+        rows = 256
+        try:
+            O.set_parallel_bucket(50000, threads)
+            while True:
+                O.lib().oracle_set_row_limit(rows)
+                t0 = time.time()
+                O.join_exacts(sp.struct, params, threads=1)
+                dt = time.time() - t0
+                if dt >= 0.5 * target_s or rows >= nb:
+                    break
+                rows = min(nb, int(rows * max(2.0, 0.8 * target_s / max(dt, 1e-3))))
+        finally:
+            O.lib().oracle_set_row_limit(0)
+            O.set_parallel_bucket(0, 1)
+        rows = min(rows, nb)
+        pairs = rows * (nb - 1) - rows * (rows - 1) // 2
+        info = {"cores": threads, "kind": "port", "pairs": pairs, "seconds": dt, "stride": 1,
+                "sample": f"the first {rows} of {nb} rows of the one bucket's pair triangle ({pairs} candidate pairs), scored row-parallel on {threads} threads "
+                          f"in {dt:.2f} s (the reference's own decomposition, one task per bucket, would run this bucket on a single core)"}
+        return pairs / dt, info
     # pilot to size the sample
     stride = 64
     t0 = time.time()
@@ -273,11 +301,17 @@ def main():
         for k2, v in st.items():
             if k2.startswith("ms_"):
                 acc[k2] = acc.get(k2, 0.0) + v
-        for name, v in j.stage_times():                 # CUDA events on the launching stream, between the pipeline stages
-            stage_acc[name] = stage_acc.get(name, 0.0) + v
     barrier()
     dev_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    # the same step again with a CUDA event between the stages (outside the timed region: the events themselves cost time)
+    j.set_stage_timing(True)
+    NS = 5
+    for _ in range(NS):
+        j.run_resident()
+        for name, v in j.stage_times():
+            stage_acc[name] = stage_acc.get(name, 0.0) + v
+    j.set_stage_timing(False)
     tt = torch.tensor([e2e_s, dev_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -302,7 +336,7 @@ def main():
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
     # Every pipeline stage is timed live with CUDA events on the launching stream (ejoin_stage_time); the roofline entry is for the
     # longest single-kernel stage.  k_sweep is bound by the popcount (XU) pipe, the pack and scoring kernels by memory.
-    stages = {k2: v / K for k2, v in stage_acc.items()}
+    stages = {k2: v / NS for k2, v in stage_acc.items()}
     sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
     xu_peak = 148 * 16 * sm_clock                        # POPC lanes per SM and clock x SMs
     cand = {}

@@ -13,7 +13,7 @@ EXPORTS = [
     "ejoin_params_default", "ejoin_create", "ejoin_destroy", "ejoin_last_error", "ejoin_run", "ejoin_result_free",
     "ejoin_plan_shards", "ejoin_run_shard", "ejoin_run_shard_final", "ejoin_partition_gpu", "ejoin_raw_free", "ejoin_finish", "ejoin_upload", "ejoin_upload_shard", "ejoin_run_resident",
     "ejoin_host_alloc", "ejoin_host_free", "ejoin_host_register", "ejoin_host_unregister", "ejoin_p1", "ejoin_partition",
-    "ejoin_pack_compact", "ejoin_pack_compact_free", "ejoin_comm_id", "ejoin_comm_init", "ejoin_run_sharded", "ejoin_format_join_log", "ejoin_stage_time",
+    "ejoin_pack_compact", "ejoin_pack_compact_free", "ejoin_comm_id", "ejoin_comm_init", "ejoin_run_sharded", "ejoin_format_join_log", "ejoin_stage_time", "ejoin_set_stage_timing",
 ]
 
 _lib = None
@@ -86,6 +86,8 @@ def load():
     L.ejoin_format_join_log.argtypes = [C.POINTER(EjoinPack), C.POINTER(EjoinParams), C.POINTER(EjoinEdge), C.POINTER(EjoinLogNames), C.c_char_p,
                                         C.c_size_t, C.POINTER(C.c_size_t)]
     L.ejoin_format_join_log.restype = C.c_int
+    L.ejoin_set_stage_timing.argtypes = [H, C.c_int]
+    L.ejoin_set_stage_timing.restype = C.c_int
     L.ejoin_stage_time.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double)]
     L.ejoin_stage_time.restype = C.c_int
     L.ejoin_p1.argtypes = [C.c_uint32] * 3

@@ -115,6 +115,7 @@ struct ejoin_handle {
     std::vector<cudaEvent_t> mark_ev;
     std::vector<const char *> mark_name;
     std::vector<float> mark_ms;            // stage times of the last pipeline run (CUDA events on the launching stream)
+    bool stage_timing = false;
     size_t n_marks = 0;
     // overlapped upload: small arrays first, then the tig arena in chunks, each with an event
     cudaEvent_t ev_copy0 = nullptr, ev_early = nullptr, ev_small = nullptr, ev_chunk[8] = {};
@@ -746,7 +747,8 @@ int prepare_tables(ejoin_handle *h, int is_bcr) {
     return 0;
 }
 
-static void mark(ejoin_handle *h, const char *name) {      // one event per pipeline stage, always on (a record costs ~1 us of host time)
+static void mark(ejoin_handle *h, const char *name) {      // one event per pipeline stage (ejoin_set_stage_timing / EJOIN_DEBUG): off in timed runs,
+    if (!h->stage_timing && !h->debug) return;              // an event between two kernels keeps the second from starting under the first's tail
     if (h->n_marks == h->mark_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); h->mark_ev.push_back(e); h->mark_name.push_back(name); }
     h->mark_name[h->n_marks] = name;
     cudaEventRecord(h->mark_ev[h->n_marks++], h->st);
@@ -1308,6 +1310,13 @@ extern "C" int ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoin_result
     out->stats.d2h_bytes = h->stats.d2h_bytes;
     out->stats.gpu_launches = h->launches;
     return 0;
+}
+
+extern "C" int ejoin_set_stage_timing(ejoin_handle_t *h, int on) {
+    if (!h) return EJOIN_E_ARG;
+    h->stage_timing = on != 0;
+    if (!on) { h->mark_ms.clear(); h->n_marks = 0; }
+    return EJOIN_OK;
 }
 
 extern "C" int ejoin_stage_time(const ejoin_handle_t *h, int index, const char **name, double *ms) {

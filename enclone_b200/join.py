@@ -150,6 +150,9 @@ class Joiner:
         self.L.ejoin_raw_free(ep)
         return 1, None, raw, st.as_dict()
 
+    def set_stage_timing(self, on=True):
+        self._check(self.L.ejoin_set_stage_timing(self.h, 1 if on else 0))
+
     def stage_times(self):
         """[(stage name, device ms)] of the last pipeline run on this handle (ejoin_stage_time: CUDA events)."""
         out, i = [], 0

@@ -242,9 +242,11 @@ const char *ejoin_last_error(const ejoin_handle_t *h);
  * valid until the next call on the handle. */
 int  ejoin_run(ejoin_handle_t *h, const ejoin_pack_t *pack, ejoin_result_t *out);
 void ejoin_result_free(ejoin_result_t *r);
-/* Device time of stage `index` (0, 1, ...) of the handle's last pipeline run, from CUDA events recorded on the launching
- * stream between the stages (a stage = one kernel or a short group: "k_sweep", "k_pack_t2", "sort entries", ...).
- * Returns EJOIN_E_ARG past the last stage. */
+/* Per-stage device times: after ejoin_set_stage_timing(h, 1) every pipeline run records a CUDA event on the launching
+ * stream between its stages (a stage = one kernel or a short group: "k_sweep", "k_pack_t2", "sort entries", ...), and
+ * ejoin_stage_time returns the time of stage `index` (0, 1, ...) of the last run, EJOIN_E_ARG past the last stage.
+ * Off by default: the events cost a few microseconds per stage. */
+int  ejoin_set_stage_timing(ejoin_handle_t *h, int on);
 int  ejoin_stage_time(const ejoin_handle_t *h, int index, const char **name, double *ms);
 
 /* Multi-GPU decomposition (one process per GPU):

@@ -515,6 +515,8 @@ static void ev_push(evec_t *x, const ejoin_edge_t *e) {
  * ---------------------------------------------------------------------------------------- */
 static uint32_t g_parallel_bucket_min = 0xFFFFFFFFu;     /* off unless a test asks for it */
 static int g_parallel_threads = 1;
+static uint32_t g_parallel_row_limit = 0xFFFFFFFFu;     /* bench only: score just the first rows of the triangle (a bounded timing sample) */
+void oracle_set_row_limit(uint32_t rows) { g_parallel_row_limit = rows ? rows : 0xFFFFFFFFu; }
 void oracle_set_parallel_bucket(uint32_t min_entries, int threads) {
     g_parallel_bucket_min = min_entries ? min_entries : 0xFFFFFFFFu;
     g_parallel_threads = threads < 1 ? 1 : threads;
@@ -554,8 +556,10 @@ static void *prow_main(void *arg) {
     ejoin_edge_t e;
     for (;;) {
         const uint32_t r0 = atomic_fetch_add(w->next_row, 64);
-        if (r0 >= w->j - w->i) break;
-        const uint32_t r1 = r0 + 64 < w->j - w->i ? r0 + 64 : w->j - w->i;
+        uint32_t rows = w->j - w->i;
+        if (g_parallel_row_limit < rows) rows = g_parallel_row_limit;
+        if (r0 >= rows) break;
+        const uint32_t r1 = r0 + 64 < rows ? r0 + 64 : rows;
         for (uint32_t k1 = w->i + r0; k1 < w->i + r1; k1++)
             for (uint32_t k2 = k1 + 1; k2 < w->j; k2++) {
                 if (!cdr3_prefilter_pass(w, k1, k2)) continue;

@@ -119,6 +119,7 @@ extern "C" {
     pub fn ejoin_run_sharded(h: *mut c_void, pack: *const ejoin_pack_t, out: *mut ejoin_result_t) -> c_int;
     pub fn ejoin_format_join_log(pack: *const ejoin_pack_t, params: *const ejoin_params_t, edge: *const ejoin_edge_t, names: *const ejoin_log_names_t,
                                  buf: *mut c_char, cap: usize, len: *mut usize) -> c_int;
+    pub fn ejoin_set_stage_timing(h: *mut c_void, on: c_int) -> c_int;
     pub fn ejoin_stage_time(h: *const c_void, index: c_int, name: *mut *const c_char, ms: *mut f64) -> c_int;
     pub fn ejoin_p1(k: u32, d: u32, n: u32) -> f64;
 }

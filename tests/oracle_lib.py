@@ -49,6 +49,7 @@ def lib():
         L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_prepare.argtypes = [C.c_int]
         L.oracle_set_parallel_bucket.argtypes = [C.c_uint32, C.c_int]
+        L.oracle_set_row_limit.argtypes = [C.c_uint32]
         L.oracle_ref_positions_differing.argtypes = [C.POINTER(EjoinPack), C.c_uint32, C.c_uint32]
         L.oracle_ref_positions_differing.restype = C.c_int
         _lib = L
