@@ -14,6 +14,7 @@ EJOIN_F_TIGS_IN_PLACE = 1
 EJOIN_F_TIGS_2BIT = 2
 EJOIN_F_ENTRY_RECS = 4
 EJOIN_F_CDR3_2BIT = 8
+EJOIN_F_TIGS_PLANES = 16
 
 u8p, u16p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64))
 

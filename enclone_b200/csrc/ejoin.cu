@@ -654,6 +654,7 @@ int upload_ranges(ejoin_handle *h, const ejoin_pack_t *pk, const Ranges &rg_in, 
     // the offsets index the original arenas: rebase the device pointers instead of the offsets
     d.tig_arena -= tlo; d.tig_src -= tlo; if (d.tig_copy) d.tig_copy -= tlo;
     if (d.tig2_src) d.tig2_src -= wlo;
+    d.tig2_planes = (pk->flags & EJOIN_F_TIGS_PLANES) ? 1u : 0u;
     if (c2) d.cdr3_2bit -= clo; else d.cdr3_arena -= clo;
     d.tig_lo = tlo; d.tig_hi = thi; d.tig2_lo = wlo; d.tig2_hi = whi; d.cdr3_lo = clo; d.cdr3_hi = chi;
     h->n = n; h->k_base = rt.n ? rt.lo[0] : 0; h->tig_bytes = two_bit ? 32 * (whi - wlo) + (thi - tlo) : thi - tlo; h->h2d_bytes = bytes; h->uploaded = true;
@@ -1875,6 +1876,16 @@ void *compact_alloc(CompactOwner *o, size_t bytes) {
 }
 struct Code256 { uint8_t t[256]; Code256() { memset(t, 0xFF, 256); t['A'] = 0; t['C'] = 1; t['G'] = 2; t['T'] = 3; } };
 const Code256 g_code;
+// DnaString word -> (high-bit plane << 32) | low-bit plane, base i at bit 31-i of each half (EJOIN_F_TIGS_PLANES)
+inline uint64_t even_bits32(uint64_t v) {          // bits 0,2,4,..,62 of v -> bits 0..31
+    v &= 0x5555555555555555ull;
+    v = (v | (v >> 1)) & 0x3333333333333333ull;
+    v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v >> 4)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v >> 8)) & 0x0000FFFF0000FFFFull;
+    return (v | (v >> 16)) & 0xFFFFFFFFull;
+}
+inline uint64_t planes_of_word(uint64_t w) { return (even_bits32(w >> 1) << 32) | even_bits32(w); }
 
 template <typename F> void parallel_ranges(uint32_t n, int threads, F f) {
     threads = std::max(1, std::min(threads, (int)((n + 4095) / 4096)));
@@ -1895,6 +1906,7 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
     if (pack_null_field(in)) return EJOIN_E_ARG;
     const uint32_t n = in->n_info;
     if (threads < 1) threads = 1;
+    const bool as_planes = getenv("EJOIN_COMPACT_DNASTRING") == nullptr;      // tests: keep the words exactly as a DnaString holds them
     // pass 1: which chains stay ASCII (deletion marker or a byte outside ACGT), sizes
     std::vector<uint8_t> asc[2];
     for (int c = 0; c < 2; c++) asc[c].assign(n, 0);
@@ -1963,7 +1975,7 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
                         uint64_t x = 0;
                         const uint32_t m = std::min(32u, L - i0);
                         for (uint32_t i = 0; i < m; i++) x |= (uint64_t)g_code.t[p[i0 + i]] << (62 - 2 * i);
-                        w[i0 >> 5] = x;
+                        w[i0 >> 5] = as_planes ? planes_of_word(x) : x;
                     }
                     r.tig_off[c] = (uint32_t)woff[c][k]; r.has_del[c] = 0;
                 }
@@ -1998,7 +2010,8 @@ extern "C" int ejoin_pack_compact(const ejoin_pack_t *in, int threads, ejoin_pac
     });
     if (bad_cdr3) { ejoin_pack_compact_free(&o->pk); return EJOIN_E_UNSUPPORTED; }      // a CDR3 character outside ACGT (documented limit)
     ejoin_pack_t &pk = o->pk;
-    pk.flags = (in->flags & ~EJOIN_F_TIGS_IN_PLACE) | EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS | EJOIN_F_CDR3_2BIT | (o->pinned ? EJOIN_F_TIGS_IN_PLACE : 0u);
+    pk.flags = (in->flags & ~EJOIN_F_TIGS_IN_PLACE) | EJOIN_F_TIGS_2BIT | (as_planes ? EJOIN_F_TIGS_PLANES : 0u) | EJOIN_F_ENTRY_RECS | EJOIN_F_CDR3_2BIT |
+               (o->pinned ? EJOIN_F_TIGS_IN_PLACE : 0u);
     pk.cdr3_2bit = o->c3w; pk.cdr3_2bit_words = c3words; pk.cdr3_2bit_off = o->c3off;
     pk.cdr3_arena = nullptr; pk.cdr3_arena_bytes = 0; pk.cdr3_off[0] = pk.cdr3_off[1] = nullptr;
     pk.tig2_arena = o->tig2; pk.tig2_arena_words = words; pk.entry_rec = o->rec;

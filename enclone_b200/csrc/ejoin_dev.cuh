@@ -136,6 +136,7 @@ struct DevIn {
     // chain is a word offset into tig2_src (device copy, or the caller's pinned arena read in place); tig_arena / tig_off
     // keep their ASCII meaning for the chains with has_del != 0.  nullptr = every chain is ASCII.
     const uint64_t *tig2_src;
+    uint32_t tig2_planes;           // EJOIN_F_TIGS_PLANES: the words already hold the two bit planes
     // EJOIN_F_CDR3_2BIT: both CDR3s of an entry concatenated, 2 bits per base; nullptr = ASCII strings in cdr3_arena
     const uint64_t *cdr3_2bit;
     const uint32_t *cdr3_2bit_off;

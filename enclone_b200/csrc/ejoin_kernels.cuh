@@ -608,7 +608,9 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
             } else {
                 // one DnaString word = these 32 bases; the half warp's loads are consecutive 8-byte words (in zero-copy
                 // mode this is the PCIe traffic of the V..J bases: 1/4 of the ASCII bytes, needed entries only)
-                planes_of_2bit(__ldg(in.tig2_src + in.tig_off[c][k] + wl), H, L);
+                const unsigned long long xw = __ldg(in.tig2_src + in.tig_off[c][k] + wl);
+                if (in.tig2_planes) { const uint32_t hi = (uint32_t)(xw >> 32), lo = (uint32_t)xw; H = __brev(hi); L = __brev(hi ^ lo); }
+                else planes_of_2bit(xw, H, L);
             }
             const uint32_t valid = low_bits(nb);
             H &= valid; L &= valid;
@@ -651,13 +653,12 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
 // convert, so the work is one bit transpose per word and the kernel is organised around its memory traffic instead.
 // EIGHT lanes per entry, one 128-base block per lane: four consecutive 8-byte words in (32 contiguous bytes per lane, the
 // in-place PCIe traffic in zero-copy mode), three 16-byte rows [H x4 | L x4 | M x4] out (48 contiguous bytes per lane, 16-byte
-// stores).  Entries with an ASCII chain are left to k_pack_t2.  Byte tallies: one atomic per CTA.
+// stores).  Entries with an ASCII chain are left to k_pack_t2.  Byte tallies: one atomic per warp, no barrier.
 __global__ void __launch_bounds__(256) k_pack_t2_2bit(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
                                                       const uint8_t *__restrict__ needed) {
-    __shared__ unsigned long long s_bytes[2];
-    if (threadIdx.x < 2) s_bytes[threadIdx.x] = 0;
-    __syncthreads();
     const uint32_t lane = threadIdx.x & 7;
+    unsigned long long my_bytes = 0, my_in = 0;          // tallies: lane 0 of each entry, summed per warp at the end (no block barrier:
+                                                         // a barrier made every warp of the CTA wait for its slowest entry)
     const uint32_t gmask = 0xFFu << (threadIdx.x & 24);          // this entry's eight lanes inside the warp
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     bool live = s < (uint32_t)ctr->n_valid && needed[s];
@@ -690,7 +691,8 @@ __global__ void __launch_bounds__(256) k_pack_t2_2bit(DevIn in, DevCounters *ctr
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int p0 = 32 * (wl0 + q), nb = n - p0;
-                    planes_of_2bit(x[q], H[q], L[q]);
+                    if (in.tig2_planes) { const uint32_t hi = (uint32_t)(x[q] >> 32), lo = (uint32_t)x[q]; H[q] = __brev(hi); L[q] = __brev(hi ^ lo); }
+                    else planes_of_2bit(x[q], H[q], L[q]);
                     const uint32_t valid = low_bits(nb);
                     H[q] &= valid; L[q] &= valid;
                     uint32_t mm = 0;
@@ -721,16 +723,18 @@ __global__ void __launch_bounds__(256) k_pack_t2_2bit(DevIn in, DevCounters *ctr
             if (lane == 0) {
                 EntryMeta *mm = &meta[s];
                 mm->m[0] = (uint16_t)mcount0; mm->m[1] = (uint16_t)mcount1;
-                const unsigned long long bin = 8ull * ((n0 + 31) / 32) + 8ull * ((n1 + 31) / 32);
-                atomicAdd(&s_bytes[0], bin + 48ull * nblk);
-                atomicAdd(&s_bytes[1], bin);
+                my_in = 8ull * ((n0 + 31) / 32) + 8ull * ((n1 + 31) / 32);
+                my_bytes = my_in + 48ull * nblk;
             }
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_bytes[0]) {
-        atomicAdd(&ctr->pack_bytes[blockIdx.x & 31], s_bytes[0]);
-        atomicAdd(&ctr->inplace_bytes[blockIdx.x & 31], s_bytes[1]);
+    const uint32_t act = __activemask();
+    my_bytes = __reduce_add_sync(act, (unsigned)my_bytes);      // < 2^32 per warp: four entries of a few KB each
+    my_in = __reduce_add_sync(act, (unsigned)my_in);
+    if ((threadIdx.x & 31) == (__ffs(act) - 1) && my_bytes) {
+        const uint32_t slot = ((blockIdx.x << 3) | (threadIdx.x >> 5)) & 31;
+        atomicAdd(&ctr->pack_bytes[slot], my_bytes);
+        atomicAdd(&ctr->inplace_bytes[slot], my_in);
     }
 }
 

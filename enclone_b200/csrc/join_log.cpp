@@ -37,6 +37,8 @@ std::string chain_bytes(const ejoin_pack_t *pk, int c, uint32_t k) {
     const bool asc = !two_bit || (recs ? pk->entry_rec[k].has_del[c] != 0 : pk->has_del[c][k] != 0);
     std::string s(n, 'A');
     if (asc) memcpy(&s[0], pk->tig_arena + off, n);
+    else if (pk->flags & EJOIN_F_TIGS_PLANES)
+        for (uint32_t i = 0; i < n; i++) { const uint64_t w = pk->tig2_arena[off + (i >> 5)]; s[i] = "ACGT"[(((w >> (63 - (i & 31))) & 1) << 1) | ((w >> (31 - (i & 31))) & 1)]; }
     else for (uint32_t i = 0; i < n; i++) s[i] = "ACGT"[(pk->tig2_arena[off + (i >> 5)] >> (62 - 2 * (i & 31))) & 3];
     return s;
 }

@@ -189,6 +189,19 @@ struct Flat {
     }
 };
 
+#if defined(__BMI2__)
+inline uint64_t planes_of_word(uint64_t w) { return (__builtin_ia32_pext_di(w, 0xAAAAAAAAAAAAAAAAull) << 32) | __builtin_ia32_pext_di(w, 0x5555555555555555ull); }
+#else
+inline uint64_t even_bits32(uint64_t v) {
+    v &= 0x5555555555555555ull;
+    v = (v | (v >> 1)) & 0x3333333333333333ull;
+    v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v >> 4)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v >> 8)) & 0x0000FFFF0000FFFFull;
+    return (v | (v >> 16)) & 0xFFFFFFFFull;
+}
+inline uint64_t planes_of_word(uint64_t w) { return (even_bits32(w >> 1) << 32) | even_bits32(w); }
+#endif
 inline uint8_t code_of(char b) { switch (b) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 0x80; } }
 
 // Flat::pack of INTEGRATION.md §2: (exact_clonotypes, info, refdata) -> compact ejoin_pack_t, on `threads` threads.
@@ -310,10 +323,13 @@ inline void pack(Flat &F, bool is_bcr, const RefData &refdata, const std::vector
                 if (asc[c][k]) { memcpy(ascii + aoff[c][k], tig.data(), Ln); r.tig_off[c] = aoff[c][k]; r.has_del[c] = 1; }
                 else {
                     uint64_t *w = tig2 + woff[c][k];
-                    if (c < ci.tigsp.size() && ci.tigsp[c].len == Ln) memcpy(w, ci.tigsp[c].storage.data(), 8 * (size_t)((Ln + 31) / 32));    // the reference's own packed form
+                    // the reference's own packed form, each word split into its two bit planes (EJOIN_F_TIGS_PLANES: two `pext`s per
+                    // word where BMI2 is there; the GPU would need a 45-instruction transpose for the same)
+                    const size_t nwd = (Ln + 31) / 32;
+                    if (c < ci.tigsp.size() && ci.tigsp[c].len == Ln) for (size_t q = 0; q < nwd; q++) w[q] = planes_of_word(ci.tigsp[c].storage[q]);
                     else {
                         const DnaString d = DnaString::from_acgt_bytes(tig);
-                        memcpy(w, d.storage.data(), 8 * d.storage.size());
+                        for (size_t q = 0; q < nwd; q++) w[q] = planes_of_word(d.storage[q]);
                     }
                     r.tig_off[c] = woff[c][k]; r.has_del[c] = 0;
                 }
@@ -393,7 +409,7 @@ inline void pack(Flat &F, bool is_bcr, const RefData &refdata, const std::vector
     F.ref_arena.append(64, '\0');
     ejoin_pack_t &pk = F.pk;
     pk.abi_version = EJOIN_ABI_VERSION; pk.n_info = n; pk.n_exact = nx; pk.n_refseq = (uint32_t)refs.size(); pk.is_bcr = is_bcr;
-    pk.flags = EJOIN_F_TIGS_2BIT | EJOIN_F_ENTRY_RECS | EJOIN_F_CDR3_2BIT | (F.pinned ? EJOIN_F_TIGS_IN_PLACE : 0u);
+    pk.flags = EJOIN_F_TIGS_2BIT | EJOIN_F_TIGS_PLANES | EJOIN_F_ENTRY_RECS | EJOIN_F_CDR3_2BIT | (F.pinned ? EJOIN_F_TIGS_IN_PLACE : 0u);
     pk.exact_id = F.exact_id.data();
     for (int c = 0; c < 2; c++) { pk.len[c] = F.len[c].data(); pk.cdr3_len[c] = F.cdr3_len[c].data(); }
     pk.tig_arena = ascii; pk.tig_arena_bytes = total.abytes;

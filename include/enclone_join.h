@@ -43,6 +43,11 @@ extern "C" {
  * has_del[c][k] != 0 (deletion marker '-', or any byte outside ACGT) stay ASCII: tig_off is a byte offset into
  * tig_arena, which needs to hold only those chains.  With EJOIN_F_TIGS_IN_PLACE the in-place reads go to tig2_arena. */
 #define EJOIN_F_TIGS_2BIT 2u
+/* With EJOIN_F_TIGS_2BIT: every word of tig2_arena holds its 32 bases as the two bit planes of their 2-bit codes instead of
+ * interleaved: bits 63..32 = the codes' high bits, bits 31..0 = the codes' low bits, base i at bit 31-i of each half — i.e.
+ * (pext(w, 0xAAAAAAAAAAAAAAAA) << 32) | pext(w, 0x5555555555555555) of the DnaString word w.  Same size, same offsets; the GPU has
+ * no pext, the host does it in two instructions per word, and the packing kernel then skips a 45-instruction bit transpose. */
+#define EJOIN_F_TIGS_PLANES 16u
 /* The per-entry fields that only the scoring reads are given as one 64-byte record per entry (entry_rec) instead of
  * 22 parallel arrays (which may then be NULL): 4.5x fewer bytes per entry and one cache line per entry.
  * Requires every id / germline index to be < 65535. */

@@ -13,6 +13,7 @@ pub const EJOIN_F_TIGS_IN_PLACE: u32 = 1;
 pub const EJOIN_F_TIGS_2BIT: u32 = 2;
 pub const EJOIN_F_ENTRY_RECS: u32 = 4;
 pub const EJOIN_F_CDR3_2BIT: u32 = 8;
+pub const EJOIN_F_TIGS_PLANES: u32 = 16;
 
 #[repr(C)]
 #[derive(Clone, Copy)]

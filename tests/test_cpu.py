@@ -154,30 +154,39 @@ def test_pack_compact_round_trip():
         cs, cl = int(a["cdr3_start"][c][k]), int(a["cdr3_len"][c][k])
         pos = int(rng.integers(0, max(1, cs)))
         arena[int(a["tig_off"][c][k]) + pos] = ord("N")
-    cp = CompactPack(pack, threads=3)
-    st = cp.struct
-    assert st.flags & 2 and st.flags & 4 and st.n_info == pack.n_info
-    words = np.ctypeslib.as_array(st.tig2_arena, shape=(int(st.tig2_arena_words),))
-    asc = np.ctypeslib.as_array(st.tig_arena, shape=(max(1, int(st.tig_arena_bytes)),))
-    n_ascii = 0
-    for k in range(0, pack.n_info, 7):
-        r = st.entry_rec[k]
-        for c in range(2):
-            ln = int(a["len"][c][k])
-            src = pack.tig(c, k)
-            plain = not a["has_del"][c][k] and all(ch in b"ACGT" for ch in src)
-            assert bool(r.has_del[c]) == (not plain)
-            if plain:
-                w = words[r.tig_off[c]: r.tig_off[c] + (ln + 31) // 32]
-                got = bytes(b"ACGT"[(int(w[i >> 5]) >> (62 - 2 * (i & 31))) & 3] for i in range(ln))
-            else:
-                n_ascii += 1
-                got = asc[r.tig_off[c]: r.tig_off[c] + ln].tobytes()
-            assert got == src
-            assert r.cdr3_start[c] == int(a["cdr3_start"][c][k])
-            for f in ("v_ref_id", "j_ref_id", "vs_seq", "js_seq", "vname_id", "vuni_seq", "dref_id", "utr_seq"):
-                v = int(a[f][c][k])
-                assert getattr(r, f)[c] == (0xFFFF if v == 0xFFFFFFFF else v), f
-        assert r.hcomp == int(a["hcomp"][k]) and r.fr3_start == int(a["fr3_start"][k])
-    assert n_ascii > 0
-    cp.close()
+    for planes in (True, False):
+        if not planes:
+          os.environ["EJOIN_COMPACT_DNASTRING"] = "1"
+        try:
+          cp = CompactPack(pack, threads=3)
+        finally:
+          os.environ.pop("EJOIN_COMPACT_DNASTRING", None)
+        st = cp.struct
+        assert st.flags & 2 and st.flags & 4 and st.n_info == pack.n_info and bool(st.flags & 16) == planes
+        words = np.ctypeslib.as_array(st.tig2_arena, shape=(int(st.tig2_arena_words),))
+        asc = np.ctypeslib.as_array(st.tig_arena, shape=(max(1, int(st.tig_arena_bytes)),))
+        n_ascii = 0
+        for k in range(0, pack.n_info, 7):
+            r = st.entry_rec[k]
+            for c in range(2):
+                ln = int(a["len"][c][k])
+                src = pack.tig(c, k)
+                plain = not a["has_del"][c][k] and all(ch in b"ACGT" for ch in src)
+                assert bool(r.has_del[c]) == (not plain)
+                if plain:
+                    w = words[r.tig_off[c]: r.tig_off[c] + (ln + 31) // 32]
+                    if planes:          # EJOIN_F_TIGS_PLANES: high-bit plane in bits 63..32, low-bit plane in bits 31..0, base i at bit 31-i
+                        got = bytes(b"ACGT"[(((int(w[i >> 5]) >> (63 - (i & 31))) & 1) << 1) | ((int(w[i >> 5]) >> (31 - (i & 31))) & 1)] for i in range(ln))
+                    else:
+                        got = bytes(b"ACGT"[(int(w[i >> 5]) >> (62 - 2 * (i & 31))) & 3] for i in range(ln))
+                else:
+                    n_ascii += 1
+                    got = asc[r.tig_off[c]: r.tig_off[c] + ln].tobytes()
+                assert got == src
+                assert r.cdr3_start[c] == int(a["cdr3_start"][c][k])
+                for f in ("v_ref_id", "j_ref_id", "vs_seq", "js_seq", "vname_id", "vuni_seq", "dref_id", "utr_seq"):
+                    v = int(a[f][c][k])
+                    assert getattr(r, f)[c] == (0xFFFF if v == 0xFFFFFFFF else v), f
+            assert r.hcomp == int(a["hcomp"][k]) and r.fr3_start == int(a["fr3_start"][k])
+        assert n_ascii > 0
+        cp.close()

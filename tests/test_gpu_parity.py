@@ -559,3 +559,21 @@ def test_two_rank_nccl_sharded_join(name, scale, stride, compact):
            "--master-port", str(port), os.path.join(here, "mgpu_worker.py"), name, str(scale), str(stride), str(compact)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_compact_input_dnastring_words(monkeypatch):
+    """The 2-bit words exactly as a DnaString holds them (interleaved; no EJOIN_F_TIGS_PLANES): the packing kernel transposes them
+    itself.  Same joins as the plane-split form and as the oracle."""
+    from enclone_b200.join import CompactPack
+    pack, _ = synth.generate(n_cells=9000, n_donors=2, seed=92, frac_indel=0.04)
+    monkeypatch.setenv("EJOIN_COMPACT_DNASTRING", "1")
+    cp = CompactPack(pack)
+    monkeypatch.delenv("EJOIN_COMPACT_DNASTRING")
+    assert cp.struct.flags & 2 and not cp.struct.flags & 16
+    cp2 = CompactPack(pack)
+    assert cp2.struct.flags & 16
+    g, g2 = join_exacts(cp), join_exacts(cp2)
+    assert np.array_equal(g.edges, g2.edges) and np.array_equal(g.class_of, g2.class_of)
+    oe, oc, _ = O.join_exacts(pack.struct, default_params(), threads=8)
+    assert_same_join(g, oe, oc, what="compact, DnaString words")
+    cp.close(); cp2.close()
