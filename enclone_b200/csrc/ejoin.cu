@@ -817,7 +817,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(sizeof(EntryMeta) * (size_t)n); sz.take(4 * c3_words); sz.take(16 * t2_units);
         sz.take(4 * (size_t)n); sz.take(4 * (size_t)n); sz.take(8 * (size_t)n); sz.take(8 * (size_t)n);           // k_to_s, parent, f0 key/val
         sz.take(16 * ccap); sz.take(8 * rcap); sz.take(8 * cap); sz.take(8 * cap); sz.take(sizeof(ejoin_raw_edge_t) * cap);       // cand, rest, todo, generic, acc
-        sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(8 * (size_t)n); sz.take(4 * (size_t)n);   // phase-A slots, survivor counts, needed, force, pending, asc list
+        sz.take(4 * (size_t)n * PHASE_A_K); sz.take(4 * (size_t)n); sz.take((size_t)n); sz.take((size_t)n); sz.take(4 * (size_t)n);   // phase-A slots, survivor counts, needed, force, asc list
         sz.take((size_t)n + 1024); sz.take(8 * ((size_t)n + 1024));                                           // work items: cost class, sorted list (items <= n)
         sz.take(4 * (size_t)xcap * PHASE_A_K * T1_TILE); sz.take(4 * (size_t)xcap * T1_TILE);                   // extra slot rows (segments q >= 1)
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
@@ -846,7 +846,6 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint2 *rest = A.take<uint2>(rcap), *todo = A.take<uint2>(cap), *generic_q = A.take<uint2>(cap);
         uint32_t *firstk = A.take<uint32_t>((size_t)n * PHASE_A_K), *surv_cnt = A.take<uint32_t>(n);
         uint8_t *needed = A.take<uint8_t>(n), *force = A.take<uint8_t>(n);
-        uint2 *pending = A.take<uint2>(n);
         uint32_t *asc_list = A.take<uint32_t>(n);
         const uint32_t item_cap = n + 1024;
         uint8_t *item_cls = A.take<uint8_t>(item_cap);
@@ -937,7 +936,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         // 2-bit input: k_pack_t2 takes only the entries with an ASCII chain, which k_meta listed (~1 % of them; the other half
         // warps of the grid leave at once), k_pack_t2_2bit all the others
         const uint32_t *pack_list = h->din.tig2_src ? asc_list : nullptr;
-        const unsigned pack_blocks = (unsigned)(((size_t)n * 16 + 255) / 256);
+        const unsigned pack_blocks = h->din.tig2_src ? (unsigned)h->sm_count * 4u : (unsigned)(((size_t)n * 16 + 255) / 256);
         if (h->copy_pending && h->n_chunks > 0) {
             // pack each chunk's (needed) entries as its bytes land (an entry belongs to the chunk that completes it)
             uint64_t prev = 0;
@@ -962,11 +961,9 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         tbs.cdmax = (const uint16_t *)h->d_cdmax.p;
         SlotView sv;
         sv.firstk = firstk; sv.cnt = surv_cnt; sv.xk = xk; sv.xcnt = xcnt; sv.gid_incl = gid; sv.groups = groups; sv.stride = stride; sv.phase = phase;
-        k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
+        k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap);
         mark(h, "k_phase_a");
-        k_phase_a_pending<<<h->sm_count * 4, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap, pending);
-        mark(h, "k_phase_a_pending");
-        h->launches += 7;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
+        h->launches += 6;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
         k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, rcap);

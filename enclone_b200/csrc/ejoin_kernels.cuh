@@ -517,19 +517,12 @@ __global__ void __launch_bounds__(256) k_unpack_recs(const ejoin_entry_rec_t *__
 }
 
 #define PACK_STAGE 544          // per chain: 512 bytes + alignment slack + the 48-byte window overrun
-__global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
-                                                 const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi,
-                                                 const uint32_t *__restrict__ asc_list) {
-    // one HALF warp per entry: a 2 x 350-base entry has 44 plane words = 3 passes of 16 lanes (92 % of the lane slots;
-    // a whole warp needed 2 passes of 32 = 69 %)
-    __shared__ __align__(16) uint8_t stage[16][2][PACK_STAGE];
+// one HALF warp per entry: a 2 x 350-base entry has 44 plane words = 3 passes of 16 lanes (92 % of the lane slots;
+// a whole warp needed 2 passes of 32 = 69 %)
+__device__ void pack_t2_entry(const DevIn &in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2, const uint8_t *__restrict__ needed,
+                              unsigned long long wm_lo, unsigned long long wm_hi, uint32_t s, uint8_t (*stage)[2][PACK_STAGE]) {
     const uint32_t lane = threadIdx.x & 15, wib = threadIdx.x >> 4;
     const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);          // the lanes of this half warp
-    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    if (asc_list) {                               // 2-bit input: only the listed entries (those with an ASCII chain) are this kernel's
-        if (s >= ctr->n_asc) return;
-        s = asc_list[s];
-    }
     if (s >= (uint32_t)ctr->n_valid) return;
     if (!needed[s]) return;                       // no CDR3-compatible partner: its rows are never read
     const EntryMeta &m = meta[s];
@@ -646,6 +639,20 @@ __global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, Ent
         EntryMeta *mm = &meta[s];
         mm->m[0] = (uint16_t)mcount0; mm->m[1] = (uint16_t)mcount1;
         if (g0 || g1) mm->flags = (uint16_t)(mm->flags | (g0 ? FLAG_GENERIC0 : 0u) | (g1 ? FLAG_GENERIC1 : 0u));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack_t2(DevIn in, DevCounters *ctr, EntryMeta *__restrict__ meta, uint4 *__restrict__ t2,
+                                                 const uint8_t *__restrict__ needed, unsigned long long wm_lo, unsigned long long wm_hi,
+                                                 const uint32_t *__restrict__ asc_list) {
+    __shared__ __align__(16) uint8_t stage[16][2][PACK_STAGE];
+    const uint32_t hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, total = (gridDim.x * blockDim.x) >> 4;
+    if (!asc_list) { pack_t2_entry(in, ctr, meta, t2, needed, wm_lo, wm_hi, hw, stage); return; }
+    // 2-bit input: only the listed entries (those with an ASCII chain, ~1 %) are this kernel's; a small grid walks the list
+    const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
+    for (uint32_t i = hw; i < ctr->n_asc; i += total) {
+        pack_t2_entry(in, ctr, meta, t2, needed, wm_lo, wm_hi, asc_list[i], stage);
+        __syncwarp(hmask);                        // the staging buffer is reused by the next entry
     }
 }
 
@@ -1779,32 +1786,38 @@ struct WalkOut {
 
 __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
                                                  uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint4 *cand,
-                                                 unsigned long long cand_cap, uint2 *pending) {
+                                                 unsigned long long cand_cap) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long evals = 0, bytes = 0;
     WalkOut wo;
     wo.emit0 = 0; wo.xe_start = 0xFFFFFFFFu; wo.n_emit_x = 0; wo.forced = false;
+    uint32_t defer_li = 0xFFFFFFFFu;           // linear slot index of a pair left to round 1 (bytewise path), see below
     RowSlots rs;
     rs.nseg = 0; rs.owned = false;
     if (s < (uint32_t)ctr->n_valid) {
         rs.init(sv, s);
         if (rs.owned) {
-            bool found = false, forced = false, pended = false;
+            bool found = false, forced = false, deferred = false;
             uint32_t rejects = 0;
-            for (uint32_t q = 0; q < rs.nseg && !pended; q++) {
+            for (uint32_t q = 0; q < rs.nseg; q++) {
                 const uint32_t cq = rs.count(sv, q), nq = min(cq, PHASE_A_K);
                 uint32_t i = 0;
-                if (!found && !forced) {
+                if (!found && !forced && !deferred) {
                     for (; i < nq; i++) {
                         const uint32_t a = rs.slot(sv, q, i);
                         int cd, d, err;
                         bool scored;
                         const int r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
                         evals += scored;
-                        if (r < 0) {                   // has_del / different germlines: rare; a whole warp continues this b (k_phase_a_pending)
-                            const uint32_t pq = atomicAdd(&ctr->n_pending, 1u);
-                            pending[pq] = make_uint2(s, q * PHASE_A_K + i);
-                            pended = true;
+                        if (r < 0) {
+                            // A pair for the bytewise path (has_del / non-ACGT / different germlines; 3 % of the pairs).  The walk
+                            // stops here: this one pair goes to round 1 of phase B with the forced flag — every smaller survivor of
+                            // b has been scored and rejected, so if the bytewise kernel accepts it, it IS b's smallest accepted
+                            // neighbour and atomicMin makes it the tree edge (k_forced_resolve) — and the slots behind it are recorded
+                            // like any others.  If it is rejected b stays a singleton tree and round 2 scores what it recorded.
+                            // (Round 1 used to park such walks for a warp-per-entry continuation kernel: 0.35 ms of latency chain.)
+                            deferred = true;
+                            defer_li = q * PHASE_A_K + i;
                             break;
                         }
                         if (r > 0) {
@@ -1818,8 +1831,7 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
                         rejects++;
                         if (rejects >= PHASE_A_K && (i + 1 < nq || cq > PHASE_A_K || q + 1 < rs.nseg)) { forced = true; i++; break; }
                     }
-                    if (pended) break;
-                    if (!found && !forced && cq > PHASE_A_K) forced = true;     // this segment's listed survivors come before the next segment's slots
+                    if (!found && !forced && !deferred && cq > PHASE_A_K) forced = true;     // this segment's listed survivors come before the next segment's slots
                 }
                 // slots i..nq-1 of this segment were not scored: they are recorded for phase B
                 if (q == 0) {
@@ -1834,7 +1846,6 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
             }
             if (forced) force[s] = 1;
             wo.forced = forced;
-            if (pended) { wo.emit0 = 0; wo.xe_start = 0xFFFFFFFFu; wo.n_emit_x = 0; }       // the continuation kernel owns this b
         }
     }
     {
@@ -1854,7 +1865,7 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
             while (e) {
                 const uint32_t i = __ffs(e) - 1;
                 e &= e - 1;
-                if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, 0, i), s, 1u, fl);
+                if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, 0, i), s, 1u, i == defer_li ? 1u : fl);
                 w++;
             }
             if (wo.n_emit_x) {
@@ -1862,7 +1873,7 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
                     const uint32_t nq = min(rs.count(sv, q), PHASE_A_K);
                     for (uint32_t i = 0; i < nq; i++) {
                         if (q * PHASE_A_K + i < wo.xe_start) continue;
-                        if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, q, i), s, 1u, fl);
+                        if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, q, i), s, 1u, q * PHASE_A_K + i == defer_li ? 1u : fl);
                         w++;
                     }
                 }
@@ -1872,83 +1883,6 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { evals += __shfl_xor_sync(0xFFFFFFFFu, evals, o); bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, o); }
     if ((threadIdx.x & 31) == 0 && evals) { atomicAdd(&ctr->pairs_tier2, evals); atomicAdd(&ctr->t2_alg_bytes, bytes); }
-}
-
-// Continuation of phase A for the entries that met a pair needing the bytewise path: one warp per
-// entry, same rules; the bytewise pairs are scored by the whole warp, the others by lane 0.
-__device__ __noinline__ int evaluate_warp_bytewise(const DevIn &in, const DevTables &tb, const DevParams &pr, DevCounters *ctr, uint32_t sa, uint32_t sb,
-                                                   int *cd_out, int *d_out) {
-    const EntryMeta &m1 = tb.meta[sa], &m2 = tb.meta[sb];
-    PairCounts pc;
-    bytewise_counts_t<true>(in, tb.t2, tb.c3, pr, m1, m2, pc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->n_generic, 1ull);
-    *cd_out = pc.cd0 + pc.cd1; *d_out = 0;
-    if (!pr.is_bcr || pr.max_diffs < 1000000) {
-        int cap = pr.max_diffs;
-        if (!pr.is_bcr && pr.max_diffs_tcr < cap) cap = pr.max_diffs_tcr;
-        if (pc.diffs > cap) return 0;
-    }
-    int kk; double p1, mult, score;
-    return decide(pr, tb, m1, m2, pc, ctr, &kk, d_out, &p1, &mult, &score);
-}
-
-__global__ void __launch_bounds__(128) k_phase_a_pending(DevIn in, DevTables tb, DevParams pr, DevCounters *ctr, SlotView sv, uint8_t *force,
-                                                         uint32_t *parent, unsigned long long *f0_key, unsigned long long *f0_val, uint4 *cand,
-                                                         unsigned long long cand_cap, const uint2 *pending) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t np = ctr->n_pending;
-    unsigned long long evals = 0, bytes = 0;
-    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < np; j += (gridDim.x * blockDim.x) >> 5) {
-        const uint32_t s = pending[j].x, start = pending[j].y;       // slots before `start` were scored (and rejected) by k_phase_a
-        RowSlots rs;
-        rs.init(sv, s);
-        bool found = false, forced = false;
-        uint32_t rejects = 0;
-        for (uint32_t q = 0; q < rs.nseg; q++) {
-            const uint32_t cq = rs.count(sv, q), nq = min(cq, PHASE_A_K);
-            uint32_t i = 0;
-            if (!found && !forced) {
-                for (; i < nq; i++) {
-                    const uint32_t li = q * PHASE_A_K + i;
-                    if (li < start) { rejects++; continue; }
-                    const uint32_t a = rs.slot(sv, q, i);
-                    int r = 0, cd = 0, d = 0, err = 0;
-                    if (lane == 0) {
-                        bool scored;
-                        r = evaluate_thread(in, tb, pr, ctr, a, s, &cd, &d, &err, &scored, &bytes);
-                        if (li > start) evals += scored;                      // slot `start` was already counted by k_phase_a
-                    }
-                    r = __shfl_sync(0xFFFFFFFFu, r, 0); err = __shfl_sync(0xFFFFFFFFu, err, 0);
-                    cd = __shfl_sync(0xFFFFFFFFu, cd, 0); d = __shfl_sync(0xFFFFFFFFu, d, 0);
-                    if (r < 0) r = evaluate_warp_bytewise(in, tb, pr, ctr, a, s, &cd, &d);
-                    if (r > 0) {
-                        found = true;
-                        if (lane == 0) {
-                            parent[s] = a;
-                            f0_key[s] = ((unsigned long long)tb.meta[a].k << 32) | tb.meta[s].k;
-                            f0_val[s] = ((unsigned long long)((uint32_t)r | ((uint32_t)err << 8)) << 32) | ((unsigned long long)(uint32_t)min(d, 65535) << 16) | (uint32_t)cd;
-                        }
-                        i++;
-                        break;
-                    }
-                    rejects++;
-                    if (rejects >= PHASE_A_K && li >= start && (i + 1 < nq || cq > PHASE_A_K || q + 1 < rs.nseg)) { forced = true; i++; break; }
-                }
-                if (!found && !forced && cq > PHASE_A_K) forced = true;
-            }
-            if (lane == 0) {
-                for (; i < nq; i++) {
-                    const unsigned long long w = atomicAdd(&ctr->n_cand, 1ull);
-                    if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, q, i), s, 1u, forced ? 1u : 0u);
-                }
-            }
-        }
-        if (lane == 0 && forced) force[s] = 1;
-        __syncwarp();
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { evals += __shfl_xor_sync(0xFFFFFFFFu, evals, o); bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, o); }
-    if (lane == 0 && evals) { atomicAdd(&ctr->pairs_tier2, evals); atomicAdd(&ctr->t2_alg_bytes, bytes); }
 }
 
 // ---------------------------------------------------------------------------------------------
