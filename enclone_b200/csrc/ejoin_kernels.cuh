@@ -1811,10 +1811,11 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
                         evals += scored;
                         if (r < 0) {
                             // A pair for the bytewise path (has_del / non-ACGT / different germlines; 3 % of the pairs).  The walk
-                            // stops here: this one pair goes to round 1 of phase B with the forced flag — every smaller survivor of
-                            // b has been scored and rejected, so if the bytewise kernel accepts it, it IS b's smallest accepted
-                            // neighbour and atomicMin makes it the tree edge (k_forced_resolve) — and the slots behind it are recorded
-                            // like any others.  If it is rejected b stays a singleton tree and round 2 scores what it recorded.
+                            // stops here: this slot and the ones behind it in the same segment go to round 1 of phase B with the
+                            // forced flag — every smaller survivor of b has been scored and rejected, so the smallest of them that
+                            // round 1 accepts IS b's smallest accepted neighbour, and atomicMin makes it the tree edge
+                            // (k_forced_resolve) — and the slots of the later segments are recorded like any others.  If none is
+                            // accepted b stays a singleton tree and round 2 scores what it recorded.
                             // (Round 1 used to park such walks for a warp-per-entry continuation kernel: 0.35 ms of latency chain.)
                             deferred = true;
                             defer_li = q * PHASE_A_K + i;
@@ -1865,7 +1866,7 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
             while (e) {
                 const uint32_t i = __ffs(e) - 1;
                 e &= e - 1;
-                if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, 0, i), s, 1u, i == defer_li ? 1u : fl);
+                if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, 0, i), s, 1u, (i >= defer_li && defer_li < PHASE_A_K) ? 1u : fl);
                 w++;
             }
             if (wo.n_emit_x) {
@@ -1873,7 +1874,7 @@ __global__ void __launch_bounds__(128, 8) k_phase_a(DevIn in, DevTables tb, DevP
                     const uint32_t nq = min(rs.count(sv, q), PHASE_A_K);
                     for (uint32_t i = 0; i < nq; i++) {
                         if (q * PHASE_A_K + i < wo.xe_start) continue;
-                        if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, q, i), s, 1u, q * PHASE_A_K + i == defer_li ? 1u : fl);
+                        if (w < cand_cap) cand[w] = make_uint4(rs.slot(sv, q, i), s, 1u, (q * PHASE_A_K + i >= defer_li && q == defer_li / PHASE_A_K) ? 1u : fl);
                         w++;
                     }
                 }
