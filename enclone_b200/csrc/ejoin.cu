@@ -22,6 +22,8 @@
 
 #include "ejoin_kernels.cuh"
 
+#define P1_CACHE_MAX 512          // p1 tables kept across inputs (1.3 MB each: 0.67 GB)
+
 namespace {
 
 double now_ms() {
@@ -226,6 +228,14 @@ void build_cdmax(ejoin_handle *h, int is_bcr) {
 // mult = MULT_POW ^ (sum_c CDR3_NORMAL_LEN * cd_c / n_c), with the host libm pow, in the
 // oracle's floating-point order (help1.rs:300-306).
 double mult_value(const ejoin_params_t &p, int cd0, int n0, int cd1, int n1) {
+    if (p.old_mult) {
+        // OLD_MULT (pages/cellranger.html.src:142-144): N = sum_{i <= cd} C(3 * cn, i), cn = total CDR3 amino acids; same
+        // floating-point order as the oracle
+        const int cn = (n0 + n1) / 3, cd = cd0 + cd1;
+        double s = 0.0, t = 1.0;
+        for (int i = 0; i <= cd; i++) { s += t; t = t * (double)(3 * cn - i) / (double)(i + 1); }
+        return s;
+    }
     double cdx = 0.0;
     cdx += (double)p.cdr3_normal_len * (double)cd0 / (double)n0;
     cdx += (double)p.cdr3_normal_len * (double)cd1 / (double)n1;
@@ -275,7 +285,6 @@ extern "C" int ejoin_create(ejoin_handle_t **out, const ejoin_params_t *p, int d
     h->device = device; h->params = *p;
     if (const char *cc = getenv("EJOIN_CAND_CAP")) h->cand_cap = h->rest_cap = h->edge_cap = strtoull(cc, nullptr, 10);   // tests: force the overflow-and-retry path
     *out = h;                                    // so the caller can read last_error on failure
-    if (p->old_mult) return fail(h, EJOIN_E_UNSUPPORTED, "OLD_MULT is not supported by the GPU path");
     if (p->auto_share > P1_DCAP) return fail(h, EJOIN_E_UNSUPPORTED, "AUTO_SHARES above the p1 table depth");
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -691,7 +700,7 @@ int prepare_tables(ejoin_handle *h, int is_bcr) {
         if ((presL[L >> 5] >> (L & 31)) & 1u)
             if (!h->p1_host_ptrs[L]) newL.push_back(L);
     const size_t tab_bytes = (size_t)P1_DCAP * P1_KCAP * sizeof(double);
-    const size_t BATCH = 32;
+    const size_t BATCH = 192;          // tables built per launch (one CTA each: a launch is a 1,024-step latency chain whatever its width)
     if (!newL.empty()) {
         CK(h->d_p1scratch.ensure(BATCH * (size_t)P1_KCAP * P1_DCAP * sizeof(dd_t)));
         CK(h->d_Ls.ensure(BATCH * sizeof(uint32_t)));
@@ -713,8 +722,25 @@ int prepare_tables(ejoin_handle *h, int is_bcr) {
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(h->st));          // ptrs / newL staging is reused by the next batch
     }
-    if (!newL.empty())
+    if (!newL.empty()) {
+        // the cache is bounded: past P1_CACHE_MAX tables, those of lengths this input does not contain are dropped (1.3 MB each)
+        if (h->p1_tables.size() > P1_CACHE_MAX) {
+            CK(cudaStreamSynchronize(h->st));
+            std::vector<DevBuf> keep;
+            for (uint32_t L = 0; L < 8192; L++) {
+                if (!h->p1_host_ptrs[L]) continue;
+                const bool present = (presL[L >> 5] >> (L & 31)) & 1u;
+                for (auto &t : h->p1_tables)
+                    if (t.p == (void *)h->p1_host_ptrs[L]) {
+                        if (present) { keep.push_back(t); t.p = nullptr; t.cap = 0; } else { t.release(); h->p1_host_ptrs[L] = nullptr; }
+                        break;
+                    }
+            }
+            h->p1_tables.swap(keep);
+        }
+        h->d_p1scratch.release();                      // the build scratch (2.6 MB per table of the batch) is not kept
         CK(cudaMemcpyAsync(h->d_p1ptrs.p, h->p1_host_ptrs.data(), 8192 * sizeof(double *), cudaMemcpyHostToDevice, h->st));
+    }
     // cd caps (and the mult tables sized by them) depend on is_bcr: rebuild when it changes
     if (h->tables_is_bcr != is_bcr) {
         build_cdmax(h, is_bcr);

@@ -166,7 +166,7 @@ typedef struct ejoin_params {
     int32_t ref_j_trim;          /* 15                                             */
     int32_t easy;                /* EASY                                           */
     int32_t old_light;           /* OLD_LIGHT                                      */
-    int32_t old_mult;            /* OLD_MULT (unsupported on the GPU: EJOIN_E_UNSUPPORTED) */
+    int32_t old_mult;            /* OLD_MULT: N = sum_{i<=cd} C(3 cn, i)              */
     int32_t mix_donors;          /* MIX_DONORS (clono_filt_opt_def.donor)          */
     int32_t degradation_mode;    /* how MAX_DEGRADATION is read (help1.rs:345-348):
                                   * 0 = the documented rule: the references assigned to the two entries may differ in at most

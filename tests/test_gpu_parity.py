@@ -67,7 +67,8 @@ def test_giant_bucket_small():
 @pytest.mark.parametrize("over", [dict(mix_donors=1), dict(easy=1), dict(max_score=1.0), dict(auto_share=1000000 if False else 100),
                                   dict(join_cdr3_ident=0.0, max_cdr3_diffs=15), dict(max_diffs=55), dict(old_light=1),
                                   dict(cdr3_mult=100), dict(comp_filt=1000000), dict(max_degradation=0), dict(ref_v_trim=0, ref_j_trim=0),
-                                  dict(degradation_mode=1), dict(degradation_mode=1, max_degradation=0), dict(max_degradation=1), dict(max_degradation=40)])
+                                  dict(degradation_mode=1), dict(degradation_mode=1, max_degradation=0), dict(max_degradation=1), dict(max_degradation=40),
+                                  dict(old_mult=1), dict(old_mult=1, max_score=1e7)])
 def test_parameter_variants(over):
     pack, _ = synth.generate(n_cells=6000, n_donors=3, seed=11)
     g, oe, oc, _ = _run_both(pack, **over)
@@ -335,9 +336,9 @@ def test_candidate_buffer_overflow_retry(monkeypatch):
 def test_unsupported_inputs_fail_loudly():
     from enclone_b200._lib import EjoinError
     pack, _ = synth.generate(n_cells=500, seed=42)
-    # OLD_MULT is refused at handle creation
+    # AUTO_SHARES beyond the p1 table depth is refused at handle creation
     with pytest.raises(EjoinError) as ei:
-        Joiner(default_params(old_mult=1))
+        Joiner(default_params(auto_share=100000))
     assert ei.value.code == -4
     # a CDR3 with a character outside ACGT
     a = {k: (list(v) if isinstance(v, list) else v) for k, v in pack.arrays.items()}
