@@ -1576,6 +1576,7 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
     const size_t nk = (size_t)h->counters.n_kept;
     DevCounters *ctr = (DevCounters *)h->d_counters.p;
     cudaStream_t st = h->st;
+    if (h->n == 0) CK(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), st));      // a rank without entries ran no pipeline: its device counters are stale
     std::vector<unsigned long long> counts(world, 0);
     auto exchange_counts = [&]() -> int {
         unsigned long long *dc = (unsigned long long *)h->d_xcounts.p;
@@ -1671,10 +1672,13 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
         // contiguous bucket ranges: the rank's emitted joins are final; build their records here, ship them to rank 0
         Arena &A = h->work;
         const size_t save = A.off;
-        uint2 *d_pairs = A.take<uint2>(nk ? nk : 1);
-        ejoin_edge_t *d_out = A.take<ejoin_edge_t>(nk ? nk : 1);
-        uint32_t *d_slow = A.take<uint32_t>(nk ? nk : 1);
-        if (A.off > A.buf.cap) { A.off = save; return fail(h, EJOIN_E_NOMEM, "work arena too small for the epilogue"); }
+        uint2 *d_pairs = nullptr;
+        ejoin_edge_t *d_out = nullptr;
+        uint32_t *d_slow = nullptr;
+        if (nk) {
+            d_pairs = A.take<uint2>(nk); d_out = A.take<ejoin_edge_t>(nk); d_slow = A.take<uint32_t>(nk);
+            if (A.off > A.buf.cap) { A.off = save; return fail(h, EJOIN_E_NOMEM, "work arena too small for the epilogue"); }
+        }
         if (nk) {
             const DevParams pr = dev_params(h->params, (int)pk->is_bcr);
             DevTables tbs;

@@ -43,6 +43,18 @@ def main():
                 assert_same_join(res, oe, oc, what=f"{name} x{scale} on {world} GPUs")
         else:
             assert len(res.edges) == 0
+    # an input without entries: every rank is empty, the exchange still has to line up
+    empty = pack.subset([])
+    res = sharded_join(j, empty.struct, rank, world, device=dev, copy=True)
+    assert len(res.edges) == 0 and len(res.class_of) == 0
+    # and one with a single two-entry bucket (fewer buckets than ranks x chunks: some ranks get nothing)
+    tiny = pack.subset([0, 1])
+    res = sharded_join(j, tiny.struct, rank, world, device=dev, copy=True)
+    if rank == 0:
+        j1 = Joiner(params, device=local)
+        one = j1.run(tiny.struct)
+        j1.close()
+        assert np.array_equal(one.edges, res.edges) and np.array_equal(one.class_of, res.class_of)
     dist.barrier()
     j.close()
     if rank == 0:
