@@ -1,0 +1,433 @@
+// egroup.cu — symmetric clonotype grouping on the GPU (include/enclone_group.h).
+//
+// Replaces the distance passes of enclone_tail::grouper::grouper(), Case 1
+// (/root/reference/enclone_tail/src/grouper.rs:386-758): inside every group, all pairs of clonotypes are tested
+// with a sequence-distance criterion and the accepted pairs are merged in an EquivRel.  The reference walks the pair
+// triangle sequentially, skipping pairs already in one class; the classes are the connected components of the accept
+// graph whatever the order, so here every pair is a thread: bit-parallel Levenshtein (Myers / Hyyro block algorithm,
+// 64 rows of the DP matrix per word, the vertical deltas Pv / Mv in registers or local memory), GPU union-find with
+// compare-and-swap hooking.  Key partitions, the orbit bookkeeping between passes (with the reference's own
+// `ee.orbit(i)` idiom, grouper.rs:441-452) and the final joins (:760-766) are host code in this file.
+// No CPU fallback for the distance passes: without a device egroup_run fails with -3.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/enclone_group.h"
+
+namespace {
+
+thread_local std::string g_err;
+int gfail(int code, const std::string &m) { g_err = m; return code; }
+#define GCK(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) return gfail(-2, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+enum { D_SEQ = 0, D_HF = 1, D_AA = 2, D_CDR3 = 3, D_CDR3AA = 4 };
+
+struct GDev {                      // device copies of the pack's tables
+    const uint32_t *clono_exact_off, *clono_exact, *exact_chain_off;
+    const uint8_t *left;
+    const uint64_t *seq_off; const uint32_t *seq_len, *cdr3_start;
+    const uint64_t *cdr3_aa_off; const uint32_t *cdr3_aa_len;
+    const uint8_t *seq_arena, *aa_arena;
+};
+struct GCounters { unsigned long long pairs_evaluated, chain_compares; unsigned int err; };
+
+#define MAXW 8                     // 64-row blocks per pattern: patterns up to 512 symbols
+#define ERR_TOO_LONG 1u
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t *p, uint32_t x) {
+    for (;;) {
+        const uint32_t px = __ldcg(&p[x]);
+        if (px == x) return x;
+        const uint32_t gp = __ldcg(&p[px]);
+        if (gp != px) p[x] = gp;
+        x = px;
+    }
+}
+__device__ __forceinline__ void uf_union(uint32_t *p, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = uf_find(p, a); b = uf_find(p, b);
+        if (a == b) return;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }
+        if (atomicCAS(&p[a], a, b) == a) return;
+    }
+}
+
+// symbol of a byte: nucleotides ACGT N - -> 0..5 (anything else 6); amino acids and '*' -> byte & 31
+__device__ __forceinline__ uint32_t sym_nt(uint8_t b) {
+    switch (b) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; case 'N': return 4; case '-': return 5; default: return 6; }
+}
+__device__ __forceinline__ uint32_t sym_aa(uint8_t b) { return b & 31u; }
+
+// Levenshtein distance (unit costs, global) of pat[0..m) and txt[0..n), m <= 64 * MAXW: Myers' bit-vector algorithm in
+// Hyyro's block form.  Block b holds rows 64b .. 64b+63 of the DP matrix as vertical deltas (Pv: +1, Mv: -1); a column
+// is processed block by block, the horizontal delta leaving a block (hout) entering the next one (hin); the first block
+// sees +1 (D[0][j] = j).  `score` follows the bottom row of the last block; the rows below the pattern's last one are
+// then walked back with their vertical deltas.
+template <int NSYM, bool AA>
+__device__ uint32_t myers(const uint8_t *pat, uint32_t m, const uint8_t *txt, uint32_t n) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const uint32_t W = (m + 63) / 64;
+    unsigned long long peq[NSYM][MAXW];
+    for (int s = 0; s < NSYM; s++)
+        for (uint32_t b = 0; b < W; b++) peq[s][b] = 0ull;
+    for (uint32_t i = 0; i < m; i++) { const uint32_t s = AA ? sym_aa(pat[i]) : sym_nt(pat[i]); peq[s][i >> 6] |= 1ull << (i & 63); }
+    unsigned long long Pv[MAXW], Mv[MAXW];
+    for (uint32_t b = 0; b < W; b++) { Pv[b] = ~0ull; Mv[b] = 0ull; }
+    int score = (int)(64 * W);
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t s = AA ? sym_aa(txt[j]) : sym_nt(txt[j]);
+        int hin = 1;
+        for (uint32_t b = 0; b < W; b++) {
+            unsigned long long Eq = peq[s][b];
+            const unsigned long long pv = Pv[b], mv = Mv[b];
+            const unsigned long long hneg = hin < 0 ? 1ull : 0ull;
+            const unsigned long long Xv = Eq | mv;
+            Eq |= hneg;
+            const unsigned long long Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+            unsigned long long Ph = mv | ~(Xh | pv), Mh = pv & Xh;
+            int hout = 0;
+            if (Ph >> 63) hout = 1;
+            if (Mh >> 63) hout = -1;
+            Ph <<= 1; Mh <<= 1;
+            Mh |= hneg;
+            if (hin > 0) Ph |= 1ull;
+            Pv[b] = Mh | ~(Xv | Ph);
+            Mv[b] = Ph & Xv;
+            hin = hout;
+        }
+        score += hin;
+    }
+    for (uint32_t r = 64 * W; r-- > m;) {          // rows m .. 64W-1: undo their vertical deltas
+        const unsigned long long bit = 1ull << (r & 63);
+        if (Pv[r >> 6] & bit) score--;
+        if (Mv[r >> 6] & bit) score++;
+    }
+    return (uint32_t)score;
+}
+
+__device__ __forceinline__ uint32_t lev_nt(const uint8_t *a, uint32_t n, const uint8_t *b, uint32_t m) {      // the shorter string is the pattern
+    return n <= m ? myers<7, false>(a, n, b, m) : myers<7, false>(b, m, a, n);
+}
+__device__ __forceinline__ uint32_t lev_aa(const uint8_t *a, uint32_t n, const uint8_t *b, uint32_t m) {
+    return n <= m ? myers<32, true>(a, n, b, m) : myers<32, true>(b, m, a, n);
+}
+
+// amino::nucleotide_to_aminoacid_sequence(dna, 0) (grouper.rs:576-580)
+__device__ uint32_t translate(const uint8_t *dna, uint32_t n, uint8_t *aa) {
+    const char *tab = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
+    uint32_t k = 0;
+    for (uint32_t i = 0; i + 3 <= n; i += 3) {
+        uint32_t idx = 0;
+        bool ok = true;
+        for (int q = 0; q < 3; q++) { const uint32_t c = sym_nt(dna[i + q]); ok = ok && c < 4; idx = idx * 4 + (c & 3); }
+        aa[k++] = ok ? (uint8_t)tab[idx] : (uint8_t)'X';
+    }
+    return k;
+}
+
+// one chain pair against the criterion of pass `kind` (grouper.rs:426-436, 499-512, 576-590, 648-664, 724-735)
+__device__ bool chain_pair_ok(const GDev &d, int kind, double min_r, const double *__restrict__ penalty, uint32_t h1, uint32_t h2, GCounters *ctr) {
+    const uint8_t *s1 = d.seq_arena + d.seq_off[h1], *s2 = d.seq_arena + d.seq_off[h2];
+    const uint32_t n1 = d.seq_len[h1], n2 = d.seq_len[h2];
+    const uint8_t *a1 = d.aa_arena + d.cdr3_aa_off[h1], *a2 = d.aa_arena + d.cdr3_aa_off[h2];
+    const uint32_t m1 = d.cdr3_aa_len[h1], m2 = d.cdr3_aa_len[h2];
+    switch (kind) {
+        case D_SEQ: {
+            if (min(n1, n2) > 64 * MAXW) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
+            const uint32_t dist = lev_nt(s1, n1, s2, n2);
+            const double r1 = __ddiv_rn((double)(dist <= n1 ? n1 - dist : 0u), (double)n1), r2 = __ddiv_rn((double)(dist <= n2 ? n2 - dist : 0u), (double)n2);
+            return r1 >= min_r || r2 >= min_r;
+        }
+        case D_AA: {
+            if (min(n1, n2) / 3 > 64 * MAXW || max(n1, n2) > 3 * 512) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
+            uint8_t t1[512], t2[512];
+            const uint32_t k1 = translate(s1, n1, t1), k2 = translate(s2, n2, t2);
+            const uint32_t dist = lev_aa(t1, k1, t2, k2);
+            const double r1 = __ddiv_rn((double)(dist <= k1 ? k1 - dist : 0u), (double)k1), r2 = __ddiv_rn((double)(dist <= k2 ? k2 - dist : 0u), (double)k2);
+            return r1 >= min_r || r2 >= min_r;
+        }
+        case D_HF: {
+            if (m1 != m2) return false;
+            double err = 0.0;
+            for (uint32_t k = 0; k < m1; k++) {
+                const unsigned x = (unsigned)(a1[k] - 'A'), y = (unsigned)(a2[k] - 'A');
+                err = __dadd_rn(err, penalty[(x < 27 ? x : 26) * 27 + (y < 27 ? y : 26)]);
+            }
+            err = __ddiv_rn(err, (double)m1);
+            return err <= __dsub_rn(1.0, min_r);
+        }
+        case D_CDR3: {
+            const uint32_t l1 = 3 * m1, l2 = 3 * m2;
+            if (min(l1, l2) > 64 * MAXW) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
+            const double d_max_f = __dmul_rn(__dsub_rn(1.0, min_r), (double)min(l1, l2));
+            const uint32_t d_max = (uint32_t)floor(d_max_f);
+            return lev_nt(s1 + d.cdr3_start[h1], l1, s2 + d.cdr3_start[h2], l2) <= d_max;
+        }
+        default: {
+            if (min(m1, m2) > 64 * MAXW) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
+            const double d_max_f = __dmul_rn(__dsub_rn(1.0, min_r), (double)min(m1, m2));
+            const uint32_t d_max = (uint32_t)floor(d_max_f);
+            return lev_aa(a1, m1, a2, m2) <= d_max;
+        }
+    }
+}
+
+// One thread per clonotype pair (i1 < i2) of a group; `members` = all groups concatenated, grp_off / pair_off their
+// member and pair prefix sums.  A pair already in one class is skipped (as the reference does; it cannot change the
+// classes), the others run the loop nest of grouper.rs:406-438.
+__global__ void __launch_bounds__(128) k_group_pairs(GDev d, int kind, int want_left, double min_r, const double *__restrict__ penalty,
+                                                     const uint32_t *__restrict__ members, const uint32_t *__restrict__ grp_off,
+                                                     const unsigned long long *__restrict__ pair_off, uint32_t n_groups, unsigned long long n_pairs,
+                                                     uint32_t *label, GCounters *ctr) {
+    unsigned long long evaluated = 0, compares = 0;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = n_groups;                              // group of pair t
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (pair_off[mid] <= t) lo = mid; else hi = mid; }
+        const unsigned long long r = t - pair_off[lo];
+        // pair r of the triangle, row-major over i2: r = i2 (i2 - 1) / 2 + i1, i1 < i2
+        uint32_t i2 = (uint32_t)((1.0 + sqrt(1.0 + 8.0 * (double)r)) * 0.5);
+        while ((unsigned long long)i2 * (i2 - 1) / 2 > r) i2--;
+        while ((unsigned long long)(i2 + 1) * i2 / 2 <= r) i2++;
+        const uint32_t i1 = (uint32_t)(r - (unsigned long long)i2 * (i2 - 1) / 2);
+        const uint32_t p1 = grp_off[lo] + i1, p2 = grp_off[lo] + i2;
+        if (uf_find(label, p1) == uf_find(label, p2)) continue;
+        evaluated++;
+        const uint32_t g1 = members[p1], g2 = members[p2];
+        bool ok = false;
+        for (uint32_t x1 = d.clono_exact_off[g1]; x1 < d.clono_exact_off[g1 + 1] && !ok; x1++)
+            for (uint32_t x2 = d.clono_exact_off[g2]; x2 < d.clono_exact_off[g2 + 1] && !ok; x2++) {
+                const uint32_t u1 = d.clono_exact[x1], u2 = d.clono_exact[x2];
+                for (uint32_t c1 = d.exact_chain_off[u1]; c1 < d.exact_chain_off[u1 + 1] && !ok; c1++) {
+                    if ((want_left != 0) != (d.left[c1] != 0)) continue;
+                    for (uint32_t c2 = d.exact_chain_off[u2]; c2 < d.exact_chain_off[u2 + 1] && !ok; c2++) {
+                        if ((want_left != 0) != (d.left[c2] != 0)) continue;
+                        compares++;
+                        ok = chain_pair_ok(d, kind, min_r, penalty, c1, c2, ctr);
+                    }
+                }
+            }
+        if (ok) uf_union(label, p1, p2);
+    }
+    for (int o = 16; o > 0; o >>= 1) { evaluated += __shfl_xor_sync(0xFFFFFFFFu, evaluated, o); compares += __shfl_xor_sync(0xFFFFFFFFu, compares, o); }
+    if ((threadIdx.x & 31) == 0 && (evaluated | compares)) { atomicAdd(&ctr->pairs_evaluated, evaluated); atomicAdd(&ctr->chain_compares, compares); }
+}
+__global__ void k_iota(uint32_t *p, uint32_t n) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+__global__ void k_flatten(uint32_t *label, uint32_t n, uint32_t *out) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = uf_find(label, i); }
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef std::vector<std::vector<uint32_t>> Groups;
+
+enum { K_VJ, K_VDJ, K_VH, K_VJH, K_VDJH, K_VJLEN, K_CDR3LEN, K_CDR3HLEN, K_CDR3LLEN };
+
+// the key of clonotype i for a key partition (grouper.rs:64-384); `lonely` = no heavy chain in a *_heavy_refname pass
+std::vector<int64_t> make_key(const egroup_pack_t *pk, int kind, uint32_t i, bool *lonely) {
+    std::vector<int64_t> k;
+    *lonely = false;
+    const uint32_t c0 = pk->col_off[i], c1 = pk->col_off[i + 1];
+    const uint32_t ex0 = pk->clono_exact[pk->clono_exact_off[i]];
+    const uint32_t h0 = pk->exact_chain_off[ex0], h1 = pk->exact_chain_off[ex0 + 1];
+    switch (kind) {
+        case K_VJ: for (uint32_t c = c0; c < c1; c++) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_jname[c]); } break;
+        case K_VDJ: for (uint32_t c = c0; c < c1; c++) { k.push_back(pk->col_vname[c]); if (pk->col_left[c]) k.push_back(pk->col_dname[c]); k.push_back(pk->col_jname[c]); } break;
+        case K_VH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) k.push_back(pk->col_vname[c]); *lonely = k.empty(); break;
+        case K_VJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_jname[c]); } *lonely = k.empty(); break;
+        case K_VDJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_dname[c]); k.push_back(pk->col_jname[c]); } *lonely = k.empty(); break;
+        case K_VJLEN: for (uint32_t h = h0; h < h1; h++) k.push_back(((int64_t)pk->left[h] << 32) | pk->seq_del_len[h]); std::sort(k.begin(), k.end()); break;
+        case K_CDR3LEN: for (uint32_t h = h0; h < h1; h++) k.push_back(((int64_t)pk->left[h] << 32) | pk->cdr3_aa_len[h]); std::sort(k.begin(), k.end()); break;
+        case K_CDR3HLEN: for (uint32_t h = h0; h < h1; h++) if (pk->left[h]) k.push_back(pk->cdr3_aa_len[h]); std::sort(k.begin(), k.end()); break;
+        case K_CDR3LLEN: for (uint32_t h = h0; h < h1; h++) if (!pk->left[h]) k.push_back(pk->cdr3_aa_len[h]); std::sort(k.begin(), k.end()); break;
+    }
+    return k;
+}
+
+void key_pass(const egroup_pack_t *pk, int kind, Groups &G) {
+    Groups out;
+    struct Rec { std::vector<int64_t> key; uint32_t idx; bool lonely; };
+    for (const auto &g : G) {
+        std::vector<Rec> all(g.size());
+        for (size_t t = 0; t < g.size(); t++) { all[t].idx = g[t]; all[t].key = make_key(pk, kind, g[t], &all[t].lonely); }
+        std::sort(all.begin(), all.end(), [](const Rec &a, const Rec &b) { return a.key != b.key ? a.key < b.key : a.idx < b.idx; });
+        for (size_t i = 0; i < all.size();) {
+            size_t j = i + 1;
+            while (j < all.size() && all[j].key == all[i].key) j++;
+            if (all[i].lonely) for (size_t k = i; k < j; k++) out.push_back({ all[k].idx });
+            else { out.emplace_back(); for (size_t k = i; k < j; k++) out.back().push_back(all[k].idx); }
+            i = j;
+        }
+    }
+    G.swap(out);
+}
+
+struct DevMem {
+    std::vector<void *> ptrs;
+    ~DevMem() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> cudaError_t up(const T *&dst, const T *src, size_t count, cudaStream_t st) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T) + 64);
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        dst = (const T *)p;
+        return count ? cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st) : cudaSuccess;
+    }
+    template <typename T> cudaError_t take(T *&dst, size_t count) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T) + 64);
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        dst = (T *)p;
+        return cudaSuccess;
+    }
+};
+
+double now_ms() { using namespace std::chrono; return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+extern "C" const char *egroup_last_error(void) { return g_err.c_str(); }
+
+extern "C" void egroup_opts_default(egroup_opts_t *o) {
+    memset(o, 0, sizeof(*o));
+    o->heavy_pc = o->light_pc = o->cdr3_heavy_pc_hf = o->aa_heavy_pc = o->aa_light_pc = o->cdr3_heavy_pc = o->cdr3_light_pc = o->cdr3_aa_heavy_pc = o->cdr3_aa_light_pc = -1.0;
+}
+
+extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int device, uint32_t *group_of, egroup_stats_t *stats) {
+    if (!pk || !op || (pk->n_clono && !group_of)) return gfail(-1, "null argument");
+    if (pk->abi_version != EGROUP_ABI_VERSION) return gfail(-1, "abi_version mismatch");
+    const uint32_t n = pk->n_clono;
+    if (n && (!pk->clono_exact_off || !pk->clono_exact || !pk->exact_chain_off || !pk->left || !pk->seq_off || !pk->seq_len || !pk->seq_del_len ||
+              !pk->cdr3_start || !pk->cdr3_aa_off || !pk->cdr3_aa_len || !pk->seq_arena || !pk->aa_arena || !pk->col_off))
+        return gfail(-1, "null array in pack");
+    if (op->cdr3_heavy_pc_hf >= 0.0 && !op->hf_matrix) return gfail(-1, "cdr3_heavy_pc_hf without its penalty matrix");
+    const double t0 = now_ms();
+    egroup_stats_t st;
+    memset(&st, 0, sizeof(st));
+    Groups G(1);
+    for (uint32_t i = 0; i < n; i++) G[0].push_back(i);
+    if (n == 0) G.clear();
+    if (op->vj_refname) key_pass(pk, K_VJ, G);
+    if (op->vdj_refname) key_pass(pk, K_VDJ, G);
+    if (op->v_heavy_refname) key_pass(pk, K_VH, G);
+    if (op->vj_heavy_refname) key_pass(pk, K_VJH, G);
+    if (op->vdj_heavy_refname) key_pass(pk, K_VDJH, G);
+    if (op->vj_len) key_pass(pk, K_VJLEN, G);
+    if (op->cdr3_len) key_pass(pk, K_CDR3LEN, G);
+    if (op->cdr3_heavy_len) key_pass(pk, K_CDR3HLEN, G);
+    if (op->cdr3_light_len) key_pass(pk, K_CDR3LLEN, G);
+    const struct { double pc; int kind, left; } passes[] = {
+        { op->heavy_pc, D_SEQ, 1 }, { op->light_pc, D_SEQ, 0 }, { op->cdr3_heavy_pc_hf, D_HF, 1 }, { op->aa_heavy_pc, D_AA, 1 }, { op->aa_light_pc, D_AA, 0 },
+        { op->cdr3_heavy_pc, D_CDR3, 1 }, { op->cdr3_light_pc, D_CDR3, 0 }, { op->cdr3_aa_heavy_pc, D_CDR3AA, 1 }, { op->cdr3_aa_light_pc, D_CDR3AA, 0 } };
+    bool any_dist = false;
+    for (const auto &p : passes) any_dist = any_dist || p.pc >= 0.0;
+    if (any_dist && n) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return gfail(-3, "no usable CUDA device (the distance passes have no CPU fallback)"); }
+        GCK(cudaSetDevice(device));
+        // every byte the nucleotide criteria compare must be one of ACGT, N, - (the symbol map of the bit-parallel kernel)
+        for (uint64_t i = 0; i < pk->seq_arena_bytes; i++) {
+            const uint8_t b = pk->seq_arena[i];
+            if (!(b == 'A' || b == 'C' || b == 'G' || b == 'T' || b == 'N' || b == '-' || b == 0)) return gfail(-4, "a nucleotide sequence holds a byte outside ACGTN-");
+        }
+        cudaStream_t s;
+        GCK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        DevMem M;
+        GDev d;
+        int sm = 148;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+        GCK(M.up(d.clono_exact_off, pk->clono_exact_off, (size_t)n + 1, s));
+        GCK(M.up(d.clono_exact, pk->clono_exact, pk->clono_exact_off[n], s));
+        GCK(M.up(d.exact_chain_off, pk->exact_chain_off, (size_t)pk->n_exact + 1, s));
+        GCK(M.up(d.left, pk->left, pk->n_chain, s));
+        GCK(M.up(d.seq_off, pk->seq_off, pk->n_chain, s)); GCK(M.up(d.seq_len, pk->seq_len, pk->n_chain, s));
+        GCK(M.up(d.cdr3_start, pk->cdr3_start, pk->n_chain, s));
+        GCK(M.up(d.cdr3_aa_off, pk->cdr3_aa_off, pk->n_chain, s)); GCK(M.up(d.cdr3_aa_len, pk->cdr3_aa_len, pk->n_chain, s));
+        GCK(M.up(d.seq_arena, pk->seq_arena, pk->seq_arena_bytes, s)); GCK(M.up(d.aa_arena, pk->aa_arena, pk->aa_arena_bytes, s));
+        double penalty_h[27 * 27];
+        memset(penalty_h, 0, sizeof(penalty_h));
+        if (op->cdr3_heavy_pc_hf >= 0.0) {                                   // grouper.rs:463-472
+            static const char *aa = "ACDEFGHIKLMNPQRSTVWY";
+            for (int i1 = 0; i1 < 20; i1++)
+                for (int i2 = 0; i2 < 20; i2++) penalty_h[(aa[i1] - 'A') * 27 + (aa[i2] - 'A')] = op->hf_matrix[i1 * 20 + i2];
+        }
+        const double *d_penalty = nullptr;
+        GCK(M.up(d_penalty, penalty_h, 27 * 27, s));
+        GCounters *d_ctr = nullptr;
+        GCK(M.take(d_ctr, 1));
+        GCK(cudaMemsetAsync(d_ctr, 0, sizeof(GCounters), s));
+        cudaEvent_t e0, e1;
+        GCK(cudaEventCreate(&e0)); GCK(cudaEventCreate(&e1));
+        GCK(cudaEventRecord(e0, s));
+        for (const auto &p : passes) {
+            if (p.pc < 0.0) continue;
+            // flatten the groups of this pass
+            std::vector<uint32_t> members, grp_off;
+            std::vector<unsigned long long> pair_off;
+            unsigned long long np = 0;
+            for (const auto &g : G) { grp_off.push_back((uint32_t)members.size()); pair_off.push_back(np); members.insert(members.end(), g.begin(), g.end()); np += (unsigned long long)g.size() * (g.size() - 1) / 2; }
+            const uint32_t ng = (uint32_t)G.size(), nm = (uint32_t)members.size();
+            st.pairs_candidate += np;
+            std::vector<uint32_t> lab(nm);
+            if (np) {
+                DevMem P;
+                const uint32_t *d_members = nullptr, *d_grp_off = nullptr;
+                const unsigned long long *d_pair_off = nullptr;
+                uint32_t *d_label = nullptr, *d_flat = nullptr;
+                GCK(P.up(d_members, members.data(), nm, s)); GCK(P.up(d_grp_off, grp_off.data(), ng, s)); GCK(P.up(d_pair_off, pair_off.data(), ng, s));
+                GCK(P.take(d_label, nm)); GCK(P.take(d_flat, nm));
+                k_iota<<<(nm + 255) / 256, 256, 0, s>>>(d_label, nm);
+                const unsigned long long want = (np + 127) / 128;
+                const unsigned blocks = (unsigned)std::min<unsigned long long>(want, (unsigned long long)sm * 16);
+                k_group_pairs<<<blocks, 128, 0, s>>>(d, p.kind, p.left, p.pc / 100.0, d_penalty, d_members, d_grp_off, d_pair_off, ng, np, d_label, d_ctr);
+                k_flatten<<<(nm + 255) / 256, 256, 0, s>>>(d_label, nm, d_flat);
+                st.gpu_launches += 3;
+                GCK(cudaGetLastError());
+                GCK(cudaMemcpyAsync(lab.data(), d_flat, 4 * (size_t)nm, cudaMemcpyDeviceToHost, s));
+                GCK(cudaStreamSynchronize(s));
+            } else for (uint32_t i = 0; i < nm; i++) lab[i] = i;
+            // the orbits of this pass, listed the way the source lists them (grouper.rs:441-452): orbit(i) for i < #orbits
+            Groups out;
+            for (uint32_t gi = 0; gi < ng; gi++) {
+                const uint32_t base = grp_off[gi], m = (uint32_t)G[gi].size();
+                uint32_t nreps = 0;
+                for (uint32_t i = 0; i < m; i++) nreps += lab[base + i] == base + i;          // labels are min members: a rep labels itself
+                for (uint32_t i = 0; i < nreps; i++) {
+                    out.emplace_back();
+                    for (uint32_t j = 0; j < m; j++) if (lab[base + j] == lab[base + i]) out.back().push_back(G[gi][j]);
+                }
+            }
+            G.swap(out);
+        }
+        GCK(cudaEventRecord(e1, s));
+        GCounters hc;
+        GCK(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
+        GCK(cudaStreamSynchronize(s));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        st.ms_device = ms; st.pairs_evaluated = hc.pairs_evaluated; st.chain_compares = hc.chain_compares;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+        if (hc.err & ERR_TOO_LONG) return gfail(-4, "a sequence compared by a distance pass is longer than 512 symbols");
+    }
+    // grouper.rs:760-766: join consecutive members of every group; labels = smallest member
+    std::vector<uint32_t> parent(n);
+    for (uint32_t i = 0; i < n; i++) parent[i] = i;
+    auto find = [&](uint32_t a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
+    for (const auto &g : G)
+        for (size_t i = 0; i + 1 < g.size(); i++) { uint32_t a = find(g[i]), b = find(g[i + 1]); if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } }
+    uint64_t ncls = 0;
+    for (uint32_t i = 0; i < n; i++) { group_of[i] = find(i); ncls += group_of[i] == i; }
+    st.n_groups = ncls;
+    st.ms_total = now_ms() - t0;
+    if (stats) *stats = st;
+    return 0;
+}

@@ -1,0 +1,280 @@
+/* grouper_oracle.c — CPU restatement of enclone's SYMMETRIC clonotype grouping.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Follows /root/reference/enclone_tail/src/grouper.rs:55-766 ("Case 1: symmetric grouping"), whose source IS in the
+ * reference tree, statement by statement:
+ *   :55-62    e = EquivRel(n), one group holding every clonotype
+ *   :64-384   the key partitions: vj_refname, vdj_refname, v_heavy_refname, vj_heavy_refname, vdj_heavy_refname, vj_len,
+ *             cdr3_len, cdr3_heavy_len, cdr3_light_len (sort by key, runs of equal keys become groups; a clonotype without
+ *             a heavy chain is a group of its own in the *_heavy_refname passes, :156-161)
+ *   :386-457  heavy_pc / light_pc: Levenshtein distance over the whole V..J nucleotide sequence
+ *   :459-535  cdr3_heavy_pc_hf: substitution-penalty distance over equal-length heavy CDR3 amino-acid strings
+ *   :537-612  aa_heavy_pc / aa_light_pc: Levenshtein distance over the translated V..J sequences
+ *   :614-687  cdr3_heavy_pc / cdr3_light_pc: Levenshtein distance over the CDR3 nucleotides, bounded by d_max
+ *   :689-758  cdr3_aa_heavy_pc / cdr3_aa_light_pc: the same over the CDR3 amino acids
+ *   :760-766  e.join over consecutive members of every group; the partition of e is the result
+ * Not restated: keeper_group and the ordering of groups by cell count (:762-820, presentation), Case 2 (asymmetric).
+ *
+ * Each distance pass ends with the reference's own idiom (:441-452 and its four copies):
+ *     ee.orbit_reps(&mut reps);  for i in 0..reps.len() { ee.orbit(i as i32, &mut o); ... }
+ * i.e. it lists the orbit of ELEMENT i for i < #orbits, not the orbit of reps[i]: an orbit that contains none of the
+ * elements 0..#orbits-1 is dropped from `groups` (its members stay singletons of `e`), and one that contains several of
+ * them appears several times.  This restatement does what the source does.  The members of an orbit are taken in
+ * ascending order [the crate `equiv` is not in the tree: its internal order of an orbit is unknown; only a later distance
+ * pass applied to the output of an earlier one could tell the difference].
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/enclone_group.h"
+
+/* ---- EquivRel (crate equiv; API as used at grouper.rs:57,408,435,441-452) ---- */
+typedef struct { int32_t *p; int32_t n; } eq_t;
+static void eq_init(eq_t *e, int32_t n) { e->p = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1)); e->n = n; for (int32_t i = 0; i < n; i++) e->p[i] = i; }
+static int32_t eq_class(eq_t *e, int32_t a) { int32_t r = a; while (e->p[r] != r) r = e->p[r]; while (e->p[a] != r) { int32_t nx = e->p[a]; e->p[a] = r; a = nx; } return r; }
+static void eq_join(eq_t *e, int32_t a, int32_t b) { int32_t x = eq_class(e, a), y = eq_class(e, b); if (x == y) return; if (x < y) e->p[y] = x; else e->p[x] = y; }
+
+/* triple_accel::levenshtein: plain edit distance (unit costs) */
+static uint32_t levenshtein(const uint8_t *a, uint32_t n, const uint8_t *b, uint32_t m) {
+    uint32_t *row = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)m + 1));
+    for (uint32_t j = 0; j <= m; j++) row[j] = j;
+    for (uint32_t i = 1; i <= n; i++) {
+        uint32_t prev = row[0];
+        row[0] = i;
+        for (uint32_t j = 1; j <= m; j++) {
+            const uint32_t cur = row[j];
+            uint32_t v = prev + (a[i - 1] != b[j - 1]);
+            if (row[j] + 1 < v) v = row[j] + 1;
+            if (row[j - 1] + 1 < v) v = row[j - 1] + 1;
+            row[j] = v;
+            prev = cur;
+        }
+    }
+    const uint32_t d = row[m];
+    free(row);
+    return d;
+}
+
+/* amino::nucleotide_to_aminoacid_sequence(dna, 0): codons from position 0, the incomplete tail dropped; standard code, '*' = stop */
+static uint32_t translate(const uint8_t *dna, uint32_t n, uint8_t *aa) {
+    static const char *tab = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";   /* index: A,C,G,T = 0,1,2,3 */
+    uint32_t k = 0;
+    for (uint32_t i = 0; i + 3 <= n; i += 3) {
+        int idx = 0, ok = 1;
+        for (int q = 0; q < 3; q++) {
+            int c;
+            switch (dna[i + q]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: c = 0; ok = 0; }
+            idx = idx * 4 + c;
+        }
+        aa[k++] = ok ? (uint8_t)tab[idx] : (uint8_t)'X';
+    }
+    return k;
+}
+
+typedef struct { uint32_t *v; size_t n, cap; } uvec_t;
+static void uv_push(uvec_t *x, uint32_t a) { if (x->n == x->cap) { x->cap = x->cap ? 2 * x->cap : 8; x->v = (uint32_t *)realloc(x->v, sizeof(uint32_t) * x->cap); } x->v[x->n++] = a; }
+typedef struct { uvec_t *g; size_t n, cap; } groups_t;
+static uvec_t *gr_new(groups_t *G) {
+    if (G->n == G->cap) { G->cap = G->cap ? 2 * G->cap : 8; G->g = (uvec_t *)realloc(G->g, sizeof(uvec_t) * G->cap); }
+    uvec_t *x = &G->g[G->n++];
+    x->v = NULL; x->n = x->cap = 0;
+    return x;
+}
+static void gr_free(groups_t *G) { for (size_t i = 0; i < G->n; i++) free(G->g[i].v); free(G->g); G->g = NULL; G->n = G->cap = 0; }
+
+/* ---- key partitions: a key is a short vector of integers; equal keys <=> one group (sorted by (key, index), :79-91) ---- */
+#define KEY_MAX 64
+typedef struct { int64_t k[KEY_MAX]; int len; uint32_t idx; int lonely; } keyrec_t;
+static int key_cmp(const void *a, const void *b) {
+    const keyrec_t *x = (const keyrec_t *)a, *y = (const keyrec_t *)b;
+    const int n = x->len < y->len ? x->len : y->len;
+    for (int i = 0; i < n; i++) if (x->k[i] != y->k[i]) return x->k[i] < y->k[i] ? -1 : 1;
+    if (x->len != y->len) return x->len < y->len ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+static int key_eq(const keyrec_t *x, const keyrec_t *y) { if (x->len != y->len) return 0; for (int i = 0; i < x->len; i++) if (x->k[i] != y->k[i]) return 0; return 1; }
+static int i64_cmp(const void *a, const void *b) { const int64_t x = *(const int64_t *)a, y = *(const int64_t *)b; return x < y ? -1 : (x > y ? 1 : 0); }
+
+enum { K_VJ, K_VDJ, K_VH, K_VJH, K_VDJH, K_VJLEN, K_CDR3LEN, K_CDR3HLEN, K_CDR3LLEN };
+
+static void make_key(const egroup_pack_t *pk, int kind, uint32_t i, keyrec_t *r) {
+    r->len = 0; r->idx = i; r->lonely = 0;
+    const uint32_t c0 = pk->col_off[i], c1 = pk->col_off[i + 1];
+    const uint32_t ex0 = pk->clono_exact[pk->clono_exact_off[i]];                    /* exacts[i][0] */
+    const uint32_t h0 = pk->exact_chain_off[ex0], h1 = pk->exact_chain_off[ex0 + 1];
+#define PUSH(x) do { if (r->len < KEY_MAX) r->k[r->len++] = (int64_t)(x); } while (0)
+    switch (kind) {
+        case K_VJ: for (uint32_t c = c0; c < c1; c++) { PUSH(pk->col_vname[c]); PUSH(pk->col_jname[c]); } break;                                 /* :70-77 */
+        case K_VDJ: for (uint32_t c = c0; c < c1; c++) { PUSH(pk->col_vname[c]); if (pk->col_left[c]) PUSH(pk->col_dname[c]); PUSH(pk->col_jname[c]); } break;  /* :100-118 */
+        case K_VH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) PUSH(pk->col_vname[c]); r->lonely = r->len == 0; break;              /* :141-150,156 */
+        case K_VJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { PUSH(pk->col_vname[c]); PUSH(pk->col_jname[c]); } r->lonely = r->len == 0; break;
+        case K_VDJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { PUSH(pk->col_vname[c]); PUSH(pk->col_dname[c]); PUSH(pk->col_jname[c]); } r->lonely = r->len == 0; break;
+        case K_VJLEN: {                                                                                                                           /* :262-290: (left, seq_del.len()) sorted */
+            for (uint32_t h = h0; h < h1; h++) PUSH(((int64_t)pk->left[h] << 32) | pk->seq_del_len[h]);
+            qsort(r->k, (size_t)r->len, sizeof(int64_t), i64_cmp);
+        } break;
+        case K_CDR3LEN: {                                                                                                                         /* :292-320 */
+            for (uint32_t h = h0; h < h1; h++) PUSH(((int64_t)pk->left[h] << 32) | pk->cdr3_aa_len[h]);
+            qsort(r->k, (size_t)r->len, sizeof(int64_t), i64_cmp);
+        } break;
+        case K_CDR3HLEN: for (uint32_t h = h0; h < h1; h++) if (pk->left[h]) PUSH(pk->cdr3_aa_len[h]); qsort(r->k, (size_t)r->len, sizeof(int64_t), i64_cmp); break;   /* :322-384 */
+        case K_CDR3LLEN: for (uint32_t h = h0; h < h1; h++) if (!pk->left[h]) PUSH(pk->cdr3_aa_len[h]); qsort(r->k, (size_t)r->len, sizeof(int64_t), i64_cmp); break;
+    }
+#undef PUSH
+}
+
+static void key_pass(const egroup_pack_t *pk, int kind, groups_t *G) {
+    groups_t out = { 0, 0, 0 };
+    for (size_t gi = 0; gi < G->n; gi++) {
+        const uvec_t *g = &G->g[gi];
+        keyrec_t *all = (keyrec_t *)malloc(sizeof(keyrec_t) * (g->n ? g->n : 1));
+        for (size_t t = 0; t < g->n; t++) make_key(pk, kind, g->v[t], &all[t]);
+        qsort(all, g->n, sizeof(keyrec_t), key_cmp);
+        size_t i = 0;
+        while (i < g->n) {
+            size_t j = i + 1;
+            while (j < g->n && key_eq(&all[i], &all[j])) j++;
+            if (all[i].lonely) for (size_t k = i; k < j; k++) uv_push(gr_new(&out), all[k].idx);            /* :156-161 */
+            else { uvec_t *ng = gr_new(&out); for (size_t k = i; k < j; k++) uv_push(ng, all[k].idx); }
+            i = j;
+        }
+        free(all);
+    }
+    gr_free(G);
+    *G = out;
+}
+
+/* ---- distance passes ---- */
+enum { D_SEQ, D_HF, D_AA, D_CDR3, D_CDR3AA };
+typedef struct { const egroup_pack_t *pk; int kind; int want_left; double min_r; const double *penalty /* [27*27] */; uint64_t evals; } dctx_t;
+
+static int chain_pair_ok(dctx_t *cx, uint32_t h1, uint32_t h2) {
+    const egroup_pack_t *pk = cx->pk;
+    const uint8_t *s1 = pk->seq_arena + pk->seq_off[h1], *s2 = pk->seq_arena + pk->seq_off[h2];
+    const uint32_t n1 = pk->seq_len[h1], n2 = pk->seq_len[h2];
+    const uint8_t *a1 = pk->aa_arena + pk->cdr3_aa_off[h1], *a2 = pk->aa_arena + pk->cdr3_aa_off[h2];
+    const uint32_t m1 = pk->cdr3_aa_len[h1], m2 = pk->cdr3_aa_len[h2];
+    cx->evals++;
+    switch (cx->kind) {
+        case D_SEQ: {                                                                        /* :426-436 */
+            const uint32_t d = levenshtein(s1, n1, s2, n2);
+            double r1 = (double)(d <= n1 ? n1 - d : 0) / (double)n1, r2 = (double)(d <= n2 ? n2 - d : 0) / (double)n2;
+            return r1 >= cx->min_r || r2 >= cx->min_r;
+        }
+        case D_AA: {                                                                         /* :576-590 */
+            uint8_t *t1 = (uint8_t *)malloc(n1 / 3 + 1), *t2 = (uint8_t *)malloc(n2 / 3 + 1);
+            const uint32_t k1 = translate(s1, n1, t1), k2 = translate(s2, n2, t2);
+            const uint32_t d = levenshtein(t1, k1, t2, k2);
+            free(t1); free(t2);
+            double r1 = (double)(d <= k1 ? k1 - d : 0) / (double)k1, r2 = (double)(d <= k2 ? k2 - d : 0) / (double)k2;
+            return r1 >= cx->min_r || r2 >= cx->min_r;
+        }
+        case D_HF: {                                                                         /* :499-512 */
+            if (m1 != m2) return 0;
+            double err = 0.0;
+            for (uint32_t k = 0; k < m1; k++) { const unsigned x = (unsigned)(a1[k] - (uint8_t)0x41), y = (unsigned)(a2[k] - (uint8_t)0x41); err += cx->penalty[(x < 27 ? x : 26) * 27 + (y < 27 ? y : 26)]; }
+            err /= (double)m1;
+            return err <= 1.0 - cx->min_r;
+        }
+        case D_CDR3: {                                                                       /* :648-664 */
+            const uint32_t st1 = pk->cdr3_start[h1], st2 = pk->cdr3_start[h2], l1 = 3 * m1, l2 = 3 * m2;
+            const double d_max_f = (1.0 - cx->min_r) * (double)(l1 < l2 ? l1 : l2);
+            const uint32_t d_max = (uint32_t)floor(d_max_f);
+            return levenshtein(s1 + st1, l1, s2 + st2, l2) <= d_max;                         /* levenshtein_simd_k(..).is_some() */
+        }
+        default: {                                                                           /* D_CDR3AA, :724-735 */
+            const double d_max_f = (1.0 - cx->min_r) * (double)(m1 < m2 ? m1 : m2);
+            const uint32_t d_max = (uint32_t)floor(d_max_f);
+            return levenshtein(a1, m1, a2, m2) <= d_max;
+        }
+    }
+}
+
+/* the loop nest of :406-438: any (u1, u2, p1, p2) with the right chain kind that satisfies the criterion */
+static int clono_pair_ok(dctx_t *cx, uint32_t g1, uint32_t g2) {
+    const egroup_pack_t *pk = cx->pk;
+    for (uint32_t x1 = pk->clono_exact_off[g1]; x1 < pk->clono_exact_off[g1 + 1]; x1++)
+        for (uint32_t x2 = pk->clono_exact_off[g2]; x2 < pk->clono_exact_off[g2 + 1]; x2++) {
+            const uint32_t u1 = pk->clono_exact[x1], u2 = pk->clono_exact[x2];
+            for (uint32_t p1 = pk->exact_chain_off[u1]; p1 < pk->exact_chain_off[u1 + 1]; p1++) {
+                if ((cx->want_left != 0) != (pk->left[p1] != 0)) continue;
+                for (uint32_t p2 = pk->exact_chain_off[u2]; p2 < pk->exact_chain_off[u2 + 1]; p2++) {
+                    if ((cx->want_left != 0) != (pk->left[p2] != 0)) continue;
+                    if (chain_pair_ok(cx, p1, p2)) return 1;
+                }
+            }
+        }
+    return 0;
+}
+
+static void dist_pass(dctx_t *cx, groups_t *G) {
+    groups_t out = { 0, 0, 0 };
+    for (size_t gi = 0; gi < G->n; gi++) {
+        const uvec_t *g = &G->g[gi];
+        const int32_t m = (int32_t)g->n;
+        eq_t ee;
+        eq_init(&ee, m);
+        for (int32_t i1 = 0; i1 < m; i1++)
+            for (int32_t i2 = i1 + 1; i2 < m; i2++) {
+                if (eq_class(&ee, i1) == eq_class(&ee, i2)) continue;                        /* :408-410 */
+                if (clono_pair_ok(cx, g->v[i1], g->v[i2])) eq_join(&ee, i1, i2);
+            }
+        /* :441-452 — orbit(i) for i < #orbits, as the source has it */
+        int32_t nreps = 0;
+        for (int32_t i = 0; i < m; i++) nreps += eq_class(&ee, i) == i;
+        for (int32_t i = 0; i < nreps; i++) {
+            const int32_t c = eq_class(&ee, i);
+            uvec_t *ng = gr_new(&out);
+            for (int32_t j = 0; j < m; j++) if (eq_class(&ee, j) == c) uv_push(ng, g->v[j]);
+        }
+        free(ee.p);
+    }
+    gr_free(G);
+    *G = out;
+}
+
+int oracle_group(const egroup_pack_t *pk, const egroup_opts_t *op, uint32_t *group_of, uint64_t *evals_out) {
+    const uint32_t n = pk->n_clono;
+    groups_t G = { 0, 0, 0 };
+    uvec_t *g0 = gr_new(&G);
+    for (uint32_t i = 0; i < n; i++) uv_push(g0, i);
+    if (op->vj_refname) key_pass(pk, K_VJ, &G);
+    if (op->vdj_refname) key_pass(pk, K_VDJ, &G);
+    if (op->v_heavy_refname) key_pass(pk, K_VH, &G);
+    if (op->vj_heavy_refname) key_pass(pk, K_VJH, &G);
+    if (op->vdj_heavy_refname) key_pass(pk, K_VDJH, &G);
+    if (op->vj_len) key_pass(pk, K_VJLEN, &G);
+    if (op->cdr3_len) key_pass(pk, K_CDR3LEN, &G);
+    if (op->cdr3_heavy_len) key_pass(pk, K_CDR3HLEN, &G);
+    if (op->cdr3_light_len) key_pass(pk, K_CDR3LLEN, &G);
+    uint64_t evals = 0;
+    double penalty[27 * 27];
+    memset(penalty, 0, sizeof(penalty));
+    if (op->cdr3_heavy_pc_hf >= 0.0) {                                                       /* :463-472 */
+        static const char *aa = "ACDEFGHIKLMNPQRSTVWY";
+        for (int i1 = 0; i1 < 20; i1++)
+            for (int i2 = 0; i2 < 20; i2++) penalty[(aa[i1] - 'A') * 27 + (aa[i2] - 'A')] = op->hf_matrix[i1 * 20 + i2];
+    }
+    const struct { double pc; int kind, left; } passes[] = {
+        { op->heavy_pc, D_SEQ, 1 }, { op->light_pc, D_SEQ, 0 }, { op->cdr3_heavy_pc_hf, D_HF, 1 }, { op->aa_heavy_pc, D_AA, 1 }, { op->aa_light_pc, D_AA, 0 },
+        { op->cdr3_heavy_pc, D_CDR3, 1 }, { op->cdr3_light_pc, D_CDR3, 0 }, { op->cdr3_aa_heavy_pc, D_CDR3AA, 1 }, { op->cdr3_aa_light_pc, D_CDR3AA, 0 } };
+    for (size_t p = 0; p < sizeof(passes) / sizeof(passes[0]); p++) {
+        if (passes[p].pc < 0.0) continue;
+        dctx_t cx = { pk, passes[p].kind, passes[p].left, passes[p].pc / 100.0, penalty, 0 };
+        dist_pass(&cx, &G);
+        evals += cx.evals;
+    }
+    /* :760-766 */
+    eq_t e;
+    eq_init(&e, (int32_t)n);
+    for (size_t gi = 0; gi < G.n; gi++)
+        for (size_t i = 0; i + 1 < G.g[gi].n; i++) eq_join(&e, (int32_t)G.g[gi].v[i], (int32_t)G.g[gi].v[i + 1]);
+    for (uint32_t i = 0; i < n; i++) group_of[i] = (uint32_t)eq_class(&e, (int32_t)i);
+    free(e.p);
+    gr_free(&G);
+    if (evals_out) *evals_out = evals;
+    return 0;
+}

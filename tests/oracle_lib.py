@@ -52,8 +52,20 @@ def lib():
         L.oracle_set_row_limit.argtypes = [C.c_uint32]
         L.oracle_ref_positions_differing.argtypes = [C.POINTER(EjoinPack), C.c_uint32, C.c_uint32]
         L.oracle_ref_positions_differing.restype = C.c_int
+        from enclone_b200.group import EgroupOpts, EgroupPack
+        L.oracle_group.restype = C.c_int
+        L.oracle_group.argtypes = [C.POINTER(EgroupPack), C.POINTER(EgroupOpts), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
+
+
+def group(pack, opts_struct):
+    """oracle/grouper_oracle.c: (group_of, chain-pair evaluations)"""
+    out = np.zeros(max(pack.n_clono, 1), np.uint32)
+    ev = C.c_uint64(0)
+    rc = lib().oracle_group(C.byref(pack.struct), C.byref(opts_struct), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(ev))
+    assert rc == 0
+    return out[:pack.n_clono], ev.value
 
 
 def p1(k, d, n):

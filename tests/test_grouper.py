@@ -1,0 +1,208 @@
+"""Symmetric grouping: oracle/grouper_oracle.c against hand-derived answers (CPU), the GPU path against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from enclone_b200 import group as G
+
+
+def tiny_pack(heavy, light=None, cdr3=(3, 4), names=None):
+    """one exact subclonotype per clonotype, chains: heavy[i] (and light[i])"""
+    n = len(heavy)
+    light = light or [None] * n
+    coff, cex, xoff = [0], [], [0]
+    left, seqs, starts, aas, col_off, cv, cj, cd, cl = [], [], [], [], [0], [], [], [], []
+    for i in range(n):
+        cex.append(i)
+        for s, is_left in ((heavy[i], 1), (light[i], 0)):
+            if s is None:
+                continue
+            left.append(is_left); seqs.append(s); starts.append(cdr3[0]); aas.append(G.translate(s[cdr3[0]:cdr3[0] + 3 * cdr3[1]]))
+            nm = names[i] if names else (0, 0, 0)
+            cv.append(nm[0] + (0 if is_left else 100)); cj.append(nm[1]); cd.append(nm[2]); cl.append(is_left)
+        xoff.append(len(left)); coff.append(len(cex)); col_off.append(len(cv))
+    so, ao, sa, aa = [], [], bytearray(), bytearray()
+    for s, a in zip(seqs, aas):
+        so.append(len(sa)); sa += s.encode(); ao.append(len(aa)); aa += a.encode()
+    return G.GroupPack(dict(clono_exact_off=coff, clono_exact=cex, exact_chain_off=xoff, left=left, seq_off=so, seq_len=[len(s) for s in seqs],
+                            seq_del_len=[len(s) for s in seqs], cdr3_start=starts, cdr3_aa_off=ao, cdr3_aa_len=[len(a) for a in aas],
+                            seq_arena=np.frombuffer(bytes(sa), np.uint8), aa_arena=np.frombuffer(bytes(aa), np.uint8), col_off=col_off, col_vname=cv,
+                            col_jname=cj, col_dname=cd, col_left=cl))
+
+
+def opts(**kw):
+    hf = kw.pop("hf_matrix", None)
+    o, keep = G.make_opts(hf_matrix=hf, **kw)
+    o._keep = keep
+    return o
+
+
+BASE = "GCTGCTGCAAAACCCGGGTTTGCTGCAGCTGCTGCAGCTGCTGCAGCTGCTGCAGCTGCT"        # 60 nt
+
+
+def mutated(k):
+    s = list(BASE)
+    for i in range(k):
+        s[5 + 7 * i] = "T" if s[5 + 7 * i] != "T" else "A"
+    return "".join(s)
+
+
+def test_oracle_heavy_pc_threshold():
+    # distances 0, 3, 6 substitutions of 60: identities 1.0, 0.95, 0.90 against the first one; 3 vs 6 differ at 3 positions
+    pk = tiny_pack([mutated(0), mutated(3), mutated(6)])
+    g, ev = oracle_lib.group(pk, opts(heavy_pc=95.0))
+    assert g.tolist() == [0, 0, 0]            # 0-1 at 95%, 1-2 at 95% (transitively)
+    g, _ = oracle_lib.group(pk, opts(heavy_pc=96.0))
+    assert g.tolist() == [0, 1, 2]
+    pk = tiny_pack([mutated(0), mutated(6), mutated(0)[:57]])
+    g, _ = oracle_lib.group(pk, opts(heavy_pc=95.0))
+    assert g.tolist() == [0, 1, 0]            # a 3-base deletion: d = 3, r2 = 54/57 < 0.95 but r1 = 57/60 >= 0.95 (either ratio accepts)
+
+
+def test_oracle_key_passes():
+    names = [(1, 1, 1), (1, 1, 2), (2, 1, 1), (1, 1, 1)]
+    pk = tiny_pack([BASE] * 4, [BASE] * 4, names=names)
+    assert oracle_lib.group(pk, opts())[0].tolist() == [0, 0, 0, 0]
+    assert oracle_lib.group(pk, opts(vj_refname=1))[0].tolist() == [0, 0, 2, 0]
+    assert oracle_lib.group(pk, opts(vdj_refname=1))[0].tolist() == [0, 1, 2, 0]
+    assert oracle_lib.group(pk, opts(v_heavy_refname=1))[0].tolist() == [0, 0, 2, 0]
+    # a clonotype without a heavy chain is alone in a *_heavy_refname pass (grouper.rs:156-161)
+    pk = tiny_pack([BASE, None, None], [BASE, BASE, BASE])
+    assert oracle_lib.group(pk, opts(v_heavy_refname=1))[0].tolist() == [0, 1, 2]
+    assert oracle_lib.group(pk, opts(vj_refname=1))[0].tolist() == [0, 1, 1]
+
+
+def test_oracle_orbit_idiom():
+    """grouper.rs:441-452 lists `ee.orbit(i)` for i < #orbits (not orbit(reps[i])): with classes {0,1} and {2,3} it lists
+    {0,1} twice and never {2,3}, so 2 and 3 stay apart in the final partition.  The oracle does what the source does."""
+    far = "".join({"A": "C", "C": "A", "G": "T", "T": "G"}[c] for c in BASE)
+    pk = tiny_pack([BASE, mutated(1), far, far])
+    assert oracle_lib.group(pk, opts(heavy_pc=95.0))[0].tolist() == [0, 0, 2, 3]
+    # the same four with the far pair first: classes {0,1} {2,3} again, by symmetry the same outcome
+    pk = tiny_pack([far, far, BASE, mutated(1)])
+    assert oracle_lib.group(pk, opts(heavy_pc=95.0))[0].tolist() == [0, 0, 2, 3]
+    # classes {0,2} and {1,3}: orbit(0) and orbit(1) list both
+    pk = tiny_pack([BASE, far, mutated(1), far])
+    assert oracle_lib.group(pk, opts(heavy_pc=95.0))[0].tolist() == [0, 1, 0, 1]
+
+
+def test_oracle_cdr3_passes():
+    # CDR3 = 4 codons from position 3: AAA ACC CGG GTT -> KTRV
+    a = BASE[:3] + "AAAACCCGGGTT" + BASE[15:]
+    b = BASE[:3] + "AAAACCCGGGTA" + BASE[15:]      # one nt differs inside the CDR3 (V -> V? GTA = V): aa identical
+    c = BASE[:3] + "AAATCCCGGGTT" + BASE[15:]      # T -> S
+    pk = tiny_pack([a, b, c])
+    assert G.translate(b[3:15]) == "KTRV" and G.translate(c[3:15]) == "KSRV"
+    # cdr3_heavy_pc 90%: d_max = floor(0.1 * 12) = 1 -> all within one substitution of a
+    assert oracle_lib.group(pk, opts(cdr3_heavy_pc=90.0))[0].tolist() == [0, 0, 0]
+    # 92%: d_max = floor(0.96) = 0 -> nothing joins
+    assert oracle_lib.group(pk, opts(cdr3_heavy_pc=92.0))[0].tolist() == [0, 1, 2]
+    # amino acids, 75%: d_max = floor(0.25 * 4) = 1
+    assert oracle_lib.group(pk, opts(cdr3_aa_heavy_pc=75.0))[0].tolist() == [0, 0, 0]
+    assert oracle_lib.group(pk, opts(cdr3_aa_heavy_pc=80.0))[0].tolist() == [0, 0, 2]
+    # penalty matrix: T<->S costs 0.4 -> err = 0.1 over 4 residues
+    m = np.zeros((20, 20)); i, j = G.HF_ORDER.index("T"), G.HF_ORDER.index("S"); m[i, j] = m[j, i] = 0.4
+    assert oracle_lib.group(pk, opts(cdr3_heavy_pc_hf=89.0, hf_matrix=m))[0].tolist() == [0, 0, 0]
+    # at 90 the source's own f64 expression decides: err = 0.1 > 1.0 - 0.9 = 0.09999999999999998
+    assert oracle_lib.group(pk, opts(cdr3_heavy_pc_hf=90.0, hf_matrix=m))[0].tolist() == [0, 0, 2]
+    # whole-chain amino acids: 20 residues, one differs in c -> 0.95
+    assert oracle_lib.group(pk, opts(aa_heavy_pc=95.0))[0].tolist() == [0, 0, 0]
+    assert oracle_lib.group(pk, opts(aa_heavy_pc=96.0))[0].tolist() == [0, 0, 2]
+
+
+def test_oracle_synthetic_is_nontrivial():
+    pk = G.synth_group_pack(300, seed=3)
+    g, ev = oracle_lib.group(pk, opts(vj_refname=1, heavy_pc=96.0))
+    ncls = len(set(g.tolist()))
+    assert 10 < ncls < 300 and ev > 300
+
+
+def test_symbols_exported():
+    L = C.CDLL(G._lib.SO_PATH)
+    for name in ("egroup_opts_default", "egroup_run", "egroup_last_error"):
+        assert hasattr(L, name)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    pk = tiny_pack([BASE, mutated(1)])
+    with pytest.raises(G._lib.EjoinError) as ei:
+        G.group_clonotypes(pk, heavy_pc=95.0)
+    assert ei.value.code == -3
+    # key partitions alone are host work and need no device
+    g, _ = G.group_clonotypes(tiny_pack([BASE] * 3, names=[(1, 1, 1), (2, 1, 1), (1, 1, 1)]), vj_refname=1)
+    assert g.tolist() == [0, 1, 0]
+
+
+OPTION_SETS = [
+    dict(heavy_pc=96.0), dict(light_pc=97.0), dict(vj_refname=1, heavy_pc=95.0, light_pc=95.0), dict(aa_heavy_pc=94.0), dict(aa_light_pc=96.0),
+    dict(cdr3_heavy_pc=85.0), dict(cdr3_light_pc=90.0), dict(cdr3_aa_heavy_pc=80.0), dict(cdr3_aa_light_pc=85.0), dict(cdr3_heavy_pc_hf=90.0, hf=True),
+    dict(vdj_refname=1, cdr3_len=1, cdr3_aa_heavy_pc=70.0), dict(v_heavy_refname=1, vj_len=1), dict(vj_heavy_refname=1, cdr3_heavy_len=1, cdr3_heavy_pc=80.0),
+    dict(vdj_heavy_refname=1, cdr3_light_len=1, heavy_pc=90.0, cdr3_aa_light_pc=75.0), dict(heavy_pc=98.0, aa_heavy_pc=90.0, cdr3_heavy_pc=70.0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", range(len(OPTION_SETS)))
+def test_gpu_grouping_equals_oracle(case):
+    kw = dict(OPTION_SETS[case])
+    hf = G.hf_matrix_example() if kw.pop("hf", False) else None
+    heavy = any(k in kw for k in ("heavy_pc", "light_pc", "aa_heavy_pc", "aa_light_pc"))          # whole-chain passes: the oracle's DP is slow
+    keyed = any(k in G.KEY_FLAGS for k in kw)
+    n = (1200 if keyed else 140) if heavy else 1500
+    pk = G.synth_group_pack(n, seed=case, n_families=max(2, n // (4 + case)))
+    want, ev = oracle_lib.group(pk, opts(hf_matrix=hf, **kw))
+    got, st = G.group_clonotypes(pk, hf_matrix=hf, **kw)
+    assert np.array_equal(got, want)
+    assert 1 < len(set(want.tolist())) < n
+    if any(k.endswith("_pc") or k.endswith("_hf") for k in kw):
+        assert st["gpu_launches"] > 0 and st["pairs_evaluated"] > 0
+
+
+@pytest.mark.gpu
+def test_gpu_grouping_hand_cases():
+    far = "".join({"A": "C", "C": "A", "G": "T", "T": "G"}[c] for c in BASE)
+    pk = tiny_pack([BASE, mutated(1), far, far])
+    assert G.group_clonotypes(pk, heavy_pc=95.0)[0].tolist() == [0, 0, 2, 3]
+    pk = tiny_pack([mutated(0), mutated(6), mutated(0)[:57]])
+    assert G.group_clonotypes(pk, heavy_pc=95.0)[0].tolist() == [0, 1, 0]
+    assert G.group_clonotypes(tiny_pack([]), heavy_pc=95.0)[0].tolist() == []
+    assert G.group_clonotypes(tiny_pack([BASE]), heavy_pc=95.0)[0].tolist() == [0]
+
+
+@pytest.mark.gpu
+def test_gpu_levenshtein_long_and_ragged():
+    """lengths across the 64-row block boundaries of the bit-parallel kernel, with insertions and deletions"""
+    rng = np.random.default_rng(5)
+    heavy = []
+    for n in (1, 2, 63, 64, 65, 127, 128, 129, 191, 192, 256, 300, 383, 384, 385, 448, 511, 512):
+        s = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, n))
+        heavy.append(s)
+        t = list(s)
+        for _ in range(max(1, n // 40)):
+            p = int(rng.integers(0, len(t)))
+            op = int(rng.integers(0, 3))
+            if op == 0: t[p] = "ACGT"[int(rng.integers(0, 4))]
+            elif op == 1 and len(t) > 1: del t[p]
+            else: t.insert(p, "G")
+        heavy.append("".join(t)[:512])
+    pk = tiny_pack(heavy, cdr3=(0, 0))
+    for pc in (90.0, 95.0, 97.0, 98.5, 99.5):
+        want, _ = oracle_lib.group(pk, opts(heavy_pc=pc))
+        got, _ = G.group_clonotypes(pk, heavy_pc=pc)
+        assert np.array_equal(got, want), pc
+        want, _ = oracle_lib.group(pk, opts(aa_heavy_pc=pc))
+        got, _ = G.group_clonotypes(pk, aa_heavy_pc=pc)
+        assert np.array_equal(got, want), pc
+
+
+@pytest.mark.gpu
+def test_gpu_grouping_too_long_is_an_error():
+    s = "ACGT" * 200                                   # 800 nt > 512 on both sides
+    pk = tiny_pack([s, s[:-1] + "A"], cdr3=(0, 0))
+    with pytest.raises(G._lib.EjoinError):
+        G.group_clonotypes(pk, heavy_pc=95.0)
