@@ -206,3 +206,14 @@ def test_gpu_grouping_too_long_is_an_error():
     pk = tiny_pack([s, s[:-1] + "A"], cdr3=(0, 0))
     with pytest.raises(G._lib.EjoinError):
         G.group_clonotypes(pk, heavy_pc=95.0)
+
+
+def test_kernel_levenshtein_arithmetic_on_host(tmp_path):
+    """egroup_myers.h compiles for the host too: fuzz the kernel's bit-parallel distance against the DP (no GPU needed)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "myers_fuzz")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tests", "myers_fuzz.cpp")])
+    out = subprocess.run([exe, "4000"], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
