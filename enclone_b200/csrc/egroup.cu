@@ -44,6 +44,7 @@ struct GDev {                      // device copies of the pack's tables
 struct GCounters { unsigned long long pairs_evaluated, chain_compares; unsigned int err; };
 
 #define ERR_TOO_LONG 1u
+#define ERR_BAD_BYTE 2u
 
 __device__ __forceinline__ uint32_t uf_find(uint32_t *p, uint32_t x) {
     for (;;) {
@@ -85,17 +86,15 @@ __device__ bool chain_pair_ok(const GDev &d, int kind, double min_r, const doubl
     switch (kind) {
         case D_SEQ: {
             if (min(n1, n2) > 64 * MAXW) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
-            const uint32_t dist = lev_nt(s1, n1, s2, n2);
-            const double r1 = __ddiv_rn((double)(dist <= n1 ? n1 - dist : 0u), (double)n1), r2 = __ddiv_rn((double)(dist <= n2 ? n2 - dist : 0u), (double)n2);
-            return r1 >= min_r || r2 >= min_r;
+            const int dm = dmax_ratio(n1, n2, min_r);               // r1 >= min_r || r2 >= min_r  <=>  distance <= dm
+            return dm >= 0 && lev_within<7, false>(s1, n1, s2, n2, (uint32_t)dm);
         }
         case D_AA: {
             if (min(n1, n2) / 3 > 64 * MAXW || max(n1, n2) > 3 * 512) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
             uint8_t t1[512], t2[512];
             const uint32_t k1 = translate(s1, n1, t1), k2 = translate(s2, n2, t2);
-            const uint32_t dist = lev_aa(t1, k1, t2, k2);
-            const double r1 = __ddiv_rn((double)(dist <= k1 ? k1 - dist : 0u), (double)k1), r2 = __ddiv_rn((double)(dist <= k2 ? k2 - dist : 0u), (double)k2);
-            return r1 >= min_r || r2 >= min_r;
+            const int dm = dmax_ratio(k1, k2, min_r);
+            return dm >= 0 && lev_within<32, true>(t1, k1, t2, k2, (uint32_t)dm);
         }
         case D_HF: {
             if (m1 != m2) return false;
@@ -112,13 +111,13 @@ __device__ bool chain_pair_ok(const GDev &d, int kind, double min_r, const doubl
             if (min(l1, l2) > 64 * MAXW) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
             const double d_max_f = __dmul_rn(__dsub_rn(1.0, min_r), (double)min(l1, l2));
             const uint32_t d_max = (uint32_t)floor(d_max_f);
-            return lev_nt(s1 + d.cdr3_start[h1], l1, s2 + d.cdr3_start[h2], l2) <= d_max;
+            return lev_within<7, false>(s1 + d.cdr3_start[h1], l1, s2 + d.cdr3_start[h2], l2, d_max);
         }
         default: {
             if (min(m1, m2) > 64 * MAXW) { atomicOr(&ctr->err, ERR_TOO_LONG); return false; }
             const double d_max_f = __dmul_rn(__dsub_rn(1.0, min_r), (double)min(m1, m2));
             const uint32_t d_max = (uint32_t)floor(d_max_f);
-            return lev_aa(a1, m1, a2, m2) <= d_max;
+            return lev_within<32, true>(a1, m1, a2, m2, d_max);
         }
     }
 }
@@ -161,6 +160,12 @@ __global__ void __launch_bounds__(128) k_group_pairs(GDev d, int kind, int want_
     }
     for (int o = 16; o > 0; o >>= 1) { evaluated += __shfl_xor_sync(0xFFFFFFFFu, evaluated, o); compares += __shfl_xor_sync(0xFFFFFFFFu, compares, o); }
     if ((threadIdx.x & 31) == 0 && (evaluated | compares)) { atomicAdd(&ctr->pairs_evaluated, evaluated); atomicAdd(&ctr->chain_compares, compares); }
+}
+// every byte the nucleotide criteria compare must be one of ACGT, N, - (the symbol map of the bit-parallel kernel); 0 pads
+__global__ void k_validate_nt(const uint8_t *__restrict__ a, unsigned long long n, GCounters *ctr) {
+    bool bad = false;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) bad = bad || (a[i] != 0 && sym_nt(a[i]) == 6);
+    if (bad) atomicOr(&ctr->err, ERR_BAD_BYTE);
 }
 __global__ void k_iota(uint32_t *p, uint32_t n) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
 __global__ void k_flatten(uint32_t *label, uint32_t n, uint32_t *out) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = uf_find(label, i); }
@@ -209,26 +214,29 @@ void key_pass(const egroup_pack_t *pk, int kind, Groups &G) {
     G.swap(out);
 }
 
-struct DevMem {
+struct DevMem {                    // stream-ordered allocations from the device's default pool (kept warm across calls)
+    cudaStream_t st;
     std::vector<void *> ptrs;
-    ~DevMem() { for (void *p : ptrs) cudaFree(p); }
-    template <typename T> cudaError_t up(const T *&dst, const T *src, size_t count, cudaStream_t st) {
-        void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T) + 64);
-        if (e != cudaSuccess) return e;
-        ptrs.push_back(p);
-        dst = (const T *)p;
-        return count ? cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st) : cudaSuccess;
-    }
+    explicit DevMem(cudaStream_t s) : st(s) {}
+    ~DevMem() { for (void *p : ptrs) cudaFreeAsync(p, st); }
     template <typename T> cudaError_t take(T *&dst, size_t count) {
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T) + 64);
+        cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T) + 64, st);
         if (e != cudaSuccess) return e;
         ptrs.push_back(p);
         dst = (T *)p;
         return cudaSuccess;
     }
+    template <typename T> cudaError_t up(const T *&dst, const T *src, size_t count) {
+        T *p = nullptr;
+        cudaError_t e = take(p, count);
+        if (e != cudaSuccess) return e;
+        dst = p;
+        return count ? cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st) : cudaSuccess;
+    }
 };
+
+struct StreamBox { cudaStream_t s = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr; ~StreamBox() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } };
 
 double now_ms() { using namespace std::chrono; return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count(); }
 
@@ -273,25 +281,21 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return gfail(-3, "no usable CUDA device (the distance passes have no CPU fallback)"); }
         GCK(cudaSetDevice(device));
-        // every byte the nucleotide criteria compare must be one of ACGT, N, - (the symbol map of the bit-parallel kernel)
-        for (uint64_t i = 0; i < pk->seq_arena_bytes; i++) {
-            const uint8_t b = pk->seq_arena[i];
-            if (!(b == 'A' || b == 'C' || b == 'G' || b == 'T' || b == 'N' || b == '-' || b == 0)) return gfail(-4, "a nucleotide sequence holds a byte outside ACGTN-");
-        }
-        cudaStream_t s;
-        GCK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        DevMem M;
+        StreamBox box;                                               // destroyed after the allocations below are returned to the pool
+        GCK(cudaStreamCreateWithFlags(&box.s, cudaStreamNonBlocking));
+        cudaStream_t s = box.s;
+        DevMem M(s);
         GDev d;
         int sm = 148;
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
-        GCK(M.up(d.clono_exact_off, pk->clono_exact_off, (size_t)n + 1, s));
-        GCK(M.up(d.clono_exact, pk->clono_exact, pk->clono_exact_off[n], s));
-        GCK(M.up(d.exact_chain_off, pk->exact_chain_off, (size_t)pk->n_exact + 1, s));
-        GCK(M.up(d.left, pk->left, pk->n_chain, s));
-        GCK(M.up(d.seq_off, pk->seq_off, pk->n_chain, s)); GCK(M.up(d.seq_len, pk->seq_len, pk->n_chain, s));
-        GCK(M.up(d.cdr3_start, pk->cdr3_start, pk->n_chain, s));
-        GCK(M.up(d.cdr3_aa_off, pk->cdr3_aa_off, pk->n_chain, s)); GCK(M.up(d.cdr3_aa_len, pk->cdr3_aa_len, pk->n_chain, s));
-        GCK(M.up(d.seq_arena, pk->seq_arena, pk->seq_arena_bytes, s)); GCK(M.up(d.aa_arena, pk->aa_arena, pk->aa_arena_bytes, s));
+        GCK(M.up(d.clono_exact_off, pk->clono_exact_off, (size_t)n + 1));
+        GCK(M.up(d.clono_exact, pk->clono_exact, pk->clono_exact_off[n]));
+        GCK(M.up(d.exact_chain_off, pk->exact_chain_off, (size_t)pk->n_exact + 1));
+        GCK(M.up(d.left, pk->left, pk->n_chain));
+        GCK(M.up(d.seq_off, pk->seq_off, pk->n_chain)); GCK(M.up(d.seq_len, pk->seq_len, pk->n_chain));
+        GCK(M.up(d.cdr3_start, pk->cdr3_start, pk->n_chain));
+        GCK(M.up(d.cdr3_aa_off, pk->cdr3_aa_off, pk->n_chain)); GCK(M.up(d.cdr3_aa_len, pk->cdr3_aa_len, pk->n_chain));
+        GCK(M.up(d.seq_arena, pk->seq_arena, pk->seq_arena_bytes)); GCK(M.up(d.aa_arena, pk->aa_arena, pk->aa_arena_bytes));
         double penalty_h[27 * 27];
         memset(penalty_h, 0, sizeof(penalty_h));
         if (op->cdr3_heavy_pc_hf >= 0.0) {                                   // grouper.rs:463-472
@@ -300,12 +304,17 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
                 for (int i2 = 0; i2 < 20; i2++) penalty_h[(aa[i1] - 'A') * 27 + (aa[i2] - 'A')] = op->hf_matrix[i1 * 20 + i2];
         }
         const double *d_penalty = nullptr;
-        GCK(M.up(d_penalty, penalty_h, 27 * 27, s));
+        GCK(M.up(d_penalty, penalty_h, 27 * 27));
         GCounters *d_ctr = nullptr;
         GCK(M.take(d_ctr, 1));
         GCK(cudaMemsetAsync(d_ctr, 0, sizeof(GCounters), s));
-        cudaEvent_t e0, e1;
-        GCK(cudaEventCreate(&e0)); GCK(cudaEventCreate(&e1));
+        if (pk->seq_arena_bytes) { k_validate_nt<<<sm * 4, 256, 0, s>>>(d.seq_arena, pk->seq_arena_bytes, d_ctr); st.gpu_launches++; }
+        {   // keep the pool's memory between calls
+            cudaMemPool_t pool; unsigned long long keep = ~0ull;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        GCK(cudaEventCreate(&box.e0)); GCK(cudaEventCreate(&box.e1));
+        cudaEvent_t e0 = box.e0, e1 = box.e1;
         GCK(cudaEventRecord(e0, s));
         for (const auto &p : passes) {
             if (p.pc < 0.0) continue;
@@ -318,11 +327,11 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
             st.pairs_candidate += np;
             std::vector<uint32_t> lab(nm);
             if (np) {
-                DevMem P;
+                DevMem P(s);
                 const uint32_t *d_members = nullptr, *d_grp_off = nullptr;
                 const unsigned long long *d_pair_off = nullptr;
                 uint32_t *d_label = nullptr, *d_flat = nullptr;
-                GCK(P.up(d_members, members.data(), nm, s)); GCK(P.up(d_grp_off, grp_off.data(), ng, s)); GCK(P.up(d_pair_off, pair_off.data(), ng, s));
+                GCK(P.up(d_members, members.data(), nm)); GCK(P.up(d_grp_off, grp_off.data(), ng)); GCK(P.up(d_pair_off, pair_off.data(), ng));
                 GCK(P.take(d_label, nm)); GCK(P.take(d_flat, nm));
                 k_iota<<<(nm + 255) / 256, 256, 0, s>>>(d_label, nm);
                 const unsigned long long want = (np + 127) / 128;
@@ -354,7 +363,7 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         st.ms_device = ms; st.pairs_evaluated = hc.pairs_evaluated; st.chain_compares = hc.chain_compares;
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+        if (hc.err & ERR_BAD_BYTE) return gfail(-4, "a nucleotide sequence holds a byte outside ACGTN-");
         if (hc.err & ERR_TOO_LONG) return gfail(-4, "a sequence compared by a distance pass is longer than 512 symbols");
     }
     // grouper.rs:760-766: join consecutive members of every group; labels = smallest member

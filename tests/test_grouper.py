@@ -206,6 +206,10 @@ def test_gpu_grouping_too_long_is_an_error():
     pk = tiny_pack([s, s[:-1] + "A"], cdr3=(0, 0))
     with pytest.raises(G._lib.EjoinError):
         G.group_clonotypes(pk, heavy_pc=95.0)
+    pk = tiny_pack([BASE, BASE[:10] + "R" + BASE[11:]])          # a byte outside ACGTN-
+    with pytest.raises(G._lib.EjoinError):
+        G.group_clonotypes(pk, heavy_pc=95.0)
+    assert G.group_clonotypes(tiny_pack([BASE, BASE[:10] + "N" + BASE[11:], BASE[:10] + "-" + BASE[11:]]), heavy_pc=98.0)[0].tolist() == [0, 0, 0]
 
 
 def test_kernel_levenshtein_arithmetic_on_host(tmp_path):
