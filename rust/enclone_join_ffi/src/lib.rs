@@ -124,5 +124,34 @@ extern "C" {
     pub fn ejoin_stage_time(h: *const c_void, index: c_int, name: *mut *const c_char, ms: *mut f64) -> c_int;
     pub fn ejoin_p1(k: u32, d: u32, n: u32) -> f64;
 }
+
+// ---- include/enclone_group.h: the symmetric grouping (enclone_tail/src/grouper.rs, Case 1) ----
+#[repr(C)]
+pub struct egroup_pack_t {
+    pub abi_version: u32, pub n_clono: u32, pub n_exact: u32, pub n_chain: u32,
+    pub clono_exact_off: *const u32, pub clono_exact: *const u32, pub exact_chain_off: *const u32,
+    pub left: *const u8, pub seq_off: *const u64, pub seq_len: *const u32, pub seq_del_len: *const u32,
+    pub cdr3_start: *const u32, pub cdr3_aa_off: *const u64, pub cdr3_aa_len: *const u32,
+    pub seq_arena: *const u8, pub seq_arena_bytes: u64, pub aa_arena: *const u8, pub aa_arena_bytes: u64,
+    pub col_off: *const u32, pub col_vname: *const u32, pub col_jname: *const u32, pub col_dname: *const u32, pub col_left: *const u8,
+}
+#[repr(C)]
+pub struct egroup_opts_t {
+    pub vj_refname: i32, pub vdj_refname: i32, pub v_heavy_refname: i32, pub vj_heavy_refname: i32, pub vdj_heavy_refname: i32,
+    pub vj_len: i32, pub cdr3_len: i32, pub cdr3_heavy_len: i32, pub cdr3_light_len: i32, pub reserved: [i32; 3],
+    pub heavy_pc: f64, pub light_pc: f64, pub cdr3_heavy_pc_hf: f64, pub hf_matrix: *const f64,
+    pub aa_heavy_pc: f64, pub aa_light_pc: f64, pub cdr3_heavy_pc: f64, pub cdr3_light_pc: f64, pub cdr3_aa_heavy_pc: f64, pub cdr3_aa_light_pc: f64,
+}
+#[repr(C)]
+pub struct egroup_stats_t {
+    pub pairs_candidate: u64, pub pairs_evaluated: u64, pub chain_compares: u64, pub gpu_launches: u64, pub n_groups: u64,
+    pub ms_device: f64, pub ms_total: f64,
+}
+#[link(name = "enclone_join")]
+extern "C" {
+    pub fn egroup_opts_default(o: *mut egroup_opts_t);
+    pub fn egroup_run(pack: *const egroup_pack_t, opts: *const egroup_opts_t, device: c_int, group_of: *mut u32, stats: *mut egroup_stats_t) -> c_int;
+    pub fn egroup_last_error() -> *const c_char;
+}
 // The safe wrapper `join_exacts(..) -> EquivRel` with `Flat::pack` is sketched in INTEGRATION.md §1-§3;
 // enclone_b200/host/join_exacts.hpp is the same logic in C++ and is compiled and tested in this repository.
