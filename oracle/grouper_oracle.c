@@ -12,6 +12,10 @@
  *   :614-687  cdr3_heavy_pc / cdr3_light_pc: Levenshtein distance over the CDR3 nucleotides, bounded by d_max
  *   :689-758  cdr3_aa_heavy_pc / cdr3_aa_light_pc: the same over the CDR3 amino acids
  *   :760-766  e.join over consecutive members of every group; the partition of e is the result
+ * PINNED on real enclone output: tests/golden/gtest_pins.json holds the clonotypes (CDR3 amino acids, gene names and, for
+ * gtest17, the two full 448-base heavy V..J sequences) that five of the reference's goldens print as ONE group
+ * (enclone_gtest5/7/8/17/19_output; commands enclone_exec/tests/enclone_test2.rs:176-270); tests/test_grouper.py checks that this
+ * restatement groups them under the same options (heavy>=96.6% sits 0.05 % under the pair's identity of 433/448).
  * Not restated: keeper_group and the ordering of groups by cell count (:762-820, presentation), Case 2 (asymmetric).
  *
  * Each distance pass ends with the reference's own idiom (:441-452 and its four copies):

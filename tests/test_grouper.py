@@ -221,3 +221,76 @@ def test_kernel_levenshtein_arithmetic_on_host(tmp_path):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tests", "myers_fuzz.cpp")])
     out = subprocess.run([exe, "4000"], capture_output=True, text=True)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
+
+
+# ---- pins on real enclone output: tests/golden/gtest_pins.json (made by tests/golden/make_gtest_pins.py from the reference's goldens) ----
+def _pin_pack(pin):
+    import json  # noqa: F401
+    ids = {}
+
+    def nid(s):
+        return ids.setdefault(s, len(ids) + 1)
+
+    coff, cex, xoff = [0], [], [0]
+    left, seqs, starts, aas, col_off, cv, cj, cd, cl = [], [], [], [], [0], [], [], [], []
+    for c in pin["clonotypes"]:
+        nm = c["names"]
+        hv, rest = nm[0], nm[1:]
+        hd = rest.pop(0) if rest[0].startswith("IGHD") else "null"
+        hj, lv, lj = rest
+        cv += [nid(hv), nid(lv)]; cj += [nid(hj), nid(lj)]; cd += [nid(hd), nid("null")]; cl += [1, 0]
+        col_off.append(len(cv))
+        for e in c["exacts"]:
+            cex.append(len(xoff) - 1)
+            for cdr3, is_left in ((e["heavy_cdr3"], 1), (e["light_cdr3"], 0)):
+                if cdr3 is None:
+                    continue
+                s = c["vj_seq1"] if (is_left and c.get("vj_seq1")) else "ACG" * (len(cdr3) + 20)
+                left.append(is_left); seqs.append(s); starts.append(30); aas.append(cdr3)
+            xoff.append(len(left))
+        coff.append(len(cex))
+    so, ao, sa, aa = [], [], bytearray(), bytearray()
+    for s, a in zip(seqs, aas):
+        so.append(len(sa)); sa += s.encode(); ao.append(len(aa)); aa += a.encode()
+    return G.GroupPack(dict(clono_exact_off=coff, clono_exact=cex, exact_chain_off=xoff, left=left, seq_off=so, seq_len=[len(s) for s in seqs],
+                            seq_del_len=[len(s) for s in seqs], cdr3_start=starts, cdr3_aa_off=ao, cdr3_aa_len=[len(a) for a in aas],
+                            seq_arena=np.frombuffer(bytes(sa), np.uint8), aa_arena=np.frombuffer(bytes(aa), np.uint8), col_off=col_off, col_vname=cv,
+                            col_jname=cj, col_dname=cd, col_left=cl))
+
+
+def _pins():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gtest_pins.json")))
+
+
+# options under which the pinned clonotypes must come apart again — derived from the golden's own data, not printed by enclone
+SPLITS = {"gtest17": dict(vj_refname=1, heavy_pc=96.7),                    # distance 15 of 448: identity 0.96652
+          "gtest5": dict(vj_refname=1, cdr3_aa_heavy_pc=80.0, cdr3_aa_light_pc=85.0),   # light CDR3s differ at 2 of 12: floor(0.15 * 12) = 1
+          "gtest7": dict(cdr3_aa_heavy_pc=100.0, cdr3_aa_light_pc=100.0),
+          "gtest19": dict(vj_refname=1, cdr3_light_len=1, cdr3_heavy_len=1)}
+
+
+def test_oracle_reproduces_the_groups_of_enclones_goldens():
+    pins = _pins()
+    assert set(pins) == {"gtest5", "gtest7", "gtest8", "gtest17", "gtest19"}
+    for name, pin in pins.items():
+        pk = _pin_pack(pin)
+        g, _ = oracle_lib.group(pk, opts(**pin["opts"]))
+        assert g.tolist() == [0] * pk.n_clono, (name, g.tolist())          # one group, as the golden prints it
+        if name in SPLITS:
+            g, _ = oracle_lib.group(pk, opts(**SPLITS[name]))
+            assert len(set(g.tolist())) == pk.n_clono, (name, g.tolist())
+    a, b = (c["vj_seq1"] for c in pins["gtest17"]["clonotypes"])
+    assert len(a) == len(b) == 448
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_the_groups_of_enclones_goldens():
+    for name, pin in _pins().items():
+        pk = _pin_pack(pin)
+        g, _ = G.group_clonotypes(pk, **pin["opts"])
+        assert g.tolist() == [0] * pk.n_clono, (name, g.tolist())
+        if name in SPLITS:
+            g, _ = G.group_clonotypes(pk, **SPLITS[name])
+            assert len(set(g.tolist())) == pk.n_clono, (name, g.tolist())
