@@ -459,7 +459,7 @@ def main():
     roofline["other_kernels"] = {k2: {kk: v for kk, v in c.items() if kk in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")} for k2, c in cand.items() if k2 != dom}
     roofline["stage_ms"] = {k2: round(v, 4) for k2, v in stages.items()}
     t2ms = max(ms.get("ms_kernel_tier2", 0), 1e-9)
-    roofline["scoring_group"] = {"kernels": "k_phase_a, k_phase_a_pending, k_phaseb_split, k_tier2 x2, k_tier2_generic x2", "ms": ms.get("ms_kernel_tier2", 0),
+    roofline["scoring_group"] = {"kernels": "k_phase_a, k_phaseb_split, k_tier2 x2, k_tier2_generic x2", "ms": ms.get("ms_kernel_tier2", 0),
                                  "algorithmic_bytes": int(st["alg_bytes_tier2"]), "achieved_gbs": st["alg_bytes_tier2"] / t2ms / 1e6,
                                  "frac_of_hbm": st["alg_bytes_tier2"] / t2ms / 1e6 / peak_hbm,
                                  "note": "latency-bound gathers of cold rows (two 128-byte records + two t2 rows per scored pair)"}

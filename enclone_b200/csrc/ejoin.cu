@@ -989,7 +989,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sv.firstk = firstk; sv.cnt = surv_cnt; sv.xk = xk; sv.xcnt = xcnt; sv.gid_incl = gid; sv.groups = groups; sv.stride = stride; sv.phase = phase;
         k_phase_a<<<(n + 127) / 128, 128, 0, st>>>(h->din, tbs, pr, ctr, sv, force, parent, f0_key, f0_val, cand, ccap);
         mark(h, "k_phase_a");
-        h->launches += 6;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a, k_phase_a_pending
+        h->launches += 6;                           // k_pack_c3, k_init_rows, k_sweep, k_meta, k_pack_t2, k_phase_a
         // phase B round 1: entries that gave up in phase A get all their survivors scored; the smallest
         // accepted partner becomes the tree edge (atomicMin on the parent)
         k_phaseb_split<<<h->sm_count * 8, 256, 0, st>>>(cand, ccap, parent, force, ctr, todo, cap, rest, rcap);
