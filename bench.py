@@ -236,6 +236,12 @@ def group_main(args):
             "roofline": {"bound": "int_alu", "achieved": stats["chain_compares"] * mean_len * mean_len / (stats["ms_device"] * 1e-3) / 1e9 if stats["ms_device"] > 0 else None,
                          "peak": None, "unit": "GCUPS (cells of the full DP matrices the comparisons stand for)", "frac": None, "traffic": None, "kernel": "k_group_pairs"},
             "clocks": clocks}
+    try:
+        if args.group_n == 20000 and args.group_opts == "vj_refname=1,heavy_pc=96":
+            line["roofline"]["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("k_group_pairs")
+            line["roofline"]["traffic_source"] = "ncu --set full capture of this workload, profiles/r02_traffic.json (mostly the per-thread match vectors spilling through L2: local memory)"
+    except Exception:
+        pass
     if not args.no_cpu_baseline:
         import oracle_lib
         sub = G.synth_group_pack(min(args.group_n, 1500), seed=1, n_families=max(2, min(args.group_n, 1500) // 50))
@@ -435,7 +441,7 @@ def main():
                            "hbm_equivalent": {"achieved": st["alg_bytes_tier1"] / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
                                               "note": "2 x 8W bytes per compared pair as if streamed: rows are staged in shared memory by TMA and reused ~n_group "
                                                       "times on chip, so this exceeds the HBM peak; it only shows HBM is not the binding roof"},
-                           "note": "all-pairs CDR3 XOR/popcount; ncu: XU pipe 75 %, ALU 71 %, issue slots 66 % busy, DRAM 2 % (profiles/r02l_ncu_metrics.json)"}
+                           "note": "all-pairs CDR3 XOR/popcount; ncu: XU pipe 75 %, ALU 71 %, issue slots 66 % busy, DRAM 2 % (profiles/r02z_ncu_metrics.json)"}
     if stages.get("k_pack_t2"):
         t = stages["k_pack_t2"] * 1e-3
         cand["k_pack_t2"] = {"bound": "hbm", "kernel": "k_pack_t2_2bit (+ k_pack_t2 for the entries with an ASCII chain)", "achieved": st["alg_bytes_pack_t2"] / t / 1e9,

@@ -32,7 +32,7 @@ def main():
         for r in rows[hdr + 2:]:
             if len(r) != len(names):
                 continue
-            k = re.sub(r"\(.*", "", re.sub(r"<.*", "", r[kcol])).replace("void ", "")
+            k = re.sub(r"\(.*", "", re.sub(r"<.*", "", r[kcol].replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))).replace("void ", "")
             out[k] = {m: (r[names.index(m)] + " " + units[names.index(m)]).strip() for m in KEEP if m in names}
     json.dump(out, sys.stdout, indent=1)
 
