@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -175,39 +176,67 @@ typedef std::vector<std::vector<uint32_t>> Groups;
 
 enum { K_VJ, K_VDJ, K_VH, K_VJH, K_VDJH, K_VJLEN, K_CDR3LEN, K_CDR3HLEN, K_CDR3LLEN };
 
-// the key of clonotype i for a key partition (grouper.rs:64-384); `lonely` = no heavy chain in a *_heavy_refname pass
-std::vector<int64_t> make_key(const egroup_pack_t *pk, int kind, uint32_t i, bool *lonely) {
-    std::vector<int64_t> k;
-    *lonely = false;
+// the key of clonotype i for a key partition (grouper.rs:64-384), appended to `k`; returns `lonely` = no heavy chain in a
+// *_heavy_refname pass.  Names are interned ids: equal strings <=> equal ids, which is all the partition depends on.
+bool append_key(const egroup_pack_t *pk, int kind, uint32_t i, std::vector<int64_t> &k) {
+    const size_t at = k.size();
     const uint32_t c0 = pk->col_off[i], c1 = pk->col_off[i + 1];
     const uint32_t ex0 = pk->clono_exact[pk->clono_exact_off[i]];
     const uint32_t h0 = pk->exact_chain_off[ex0], h1 = pk->exact_chain_off[ex0 + 1];
+    bool lonely = false;
     switch (kind) {
         case K_VJ: for (uint32_t c = c0; c < c1; c++) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_jname[c]); } break;
         case K_VDJ: for (uint32_t c = c0; c < c1; c++) { k.push_back(pk->col_vname[c]); if (pk->col_left[c]) k.push_back(pk->col_dname[c]); k.push_back(pk->col_jname[c]); } break;
-        case K_VH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) k.push_back(pk->col_vname[c]); *lonely = k.empty(); break;
-        case K_VJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_jname[c]); } *lonely = k.empty(); break;
-        case K_VDJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_dname[c]); k.push_back(pk->col_jname[c]); } *lonely = k.empty(); break;
-        case K_VJLEN: for (uint32_t h = h0; h < h1; h++) k.push_back(((int64_t)pk->left[h] << 32) | pk->seq_del_len[h]); std::sort(k.begin(), k.end()); break;
-        case K_CDR3LEN: for (uint32_t h = h0; h < h1; h++) k.push_back(((int64_t)pk->left[h] << 32) | pk->cdr3_aa_len[h]); std::sort(k.begin(), k.end()); break;
-        case K_CDR3HLEN: for (uint32_t h = h0; h < h1; h++) if (pk->left[h]) k.push_back(pk->cdr3_aa_len[h]); std::sort(k.begin(), k.end()); break;
-        case K_CDR3LLEN: for (uint32_t h = h0; h < h1; h++) if (!pk->left[h]) k.push_back(pk->cdr3_aa_len[h]); std::sort(k.begin(), k.end()); break;
+        case K_VH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) k.push_back(pk->col_vname[c]); lonely = k.size() == at; break;
+        case K_VJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_jname[c]); } lonely = k.size() == at; break;
+        case K_VDJH: for (uint32_t c = c0; c < c1; c++) if (pk->col_left[c]) { k.push_back(pk->col_vname[c]); k.push_back(pk->col_dname[c]); k.push_back(pk->col_jname[c]); } lonely = k.size() == at; break;
+        case K_VJLEN: for (uint32_t h = h0; h < h1; h++) k.push_back(((int64_t)pk->left[h] << 32) | pk->seq_del_len[h]); std::sort(k.begin() + at, k.end()); break;
+        case K_CDR3LEN: for (uint32_t h = h0; h < h1; h++) k.push_back(((int64_t)pk->left[h] << 32) | pk->cdr3_aa_len[h]); std::sort(k.begin() + at, k.end()); break;
+        case K_CDR3HLEN: for (uint32_t h = h0; h < h1; h++) if (pk->left[h]) k.push_back(pk->cdr3_aa_len[h]); std::sort(k.begin() + at, k.end()); break;
+        case K_CDR3LLEN: for (uint32_t h = h0; h < h1; h++) if (!pk->left[h]) k.push_back(pk->cdr3_aa_len[h]); std::sort(k.begin() + at, k.end()); break;
     }
-    return k;
+    return lonely;
 }
 
+// one key partition: inside every group sort by (key, index), runs of equal keys become the new groups
 void key_pass(const egroup_pack_t *pk, int kind, Groups &G) {
     Groups out;
-    struct Rec { std::vector<int64_t> key; uint32_t idx; bool lonely; };
+    std::vector<int64_t> buf;
+    std::vector<uint32_t> off, order;
+    std::vector<uint8_t> lonely;
+    std::vector<std::pair<uint64_t, uint64_t>> hk;
     for (const auto &g : G) {
-        std::vector<Rec> all(g.size());
-        for (size_t t = 0; t < g.size(); t++) { all[t].idx = g[t]; all[t].key = make_key(pk, kind, g[t], &all[t].lonely); }
-        std::sort(all.begin(), all.end(), [](const Rec &a, const Rec &b) { return a.key != b.key ? a.key < b.key : a.idx < b.idx; });
-        for (size_t i = 0; i < all.size();) {
-            size_t j = i + 1;
-            while (j < all.size() && all[j].key == all[i].key) j++;
-            if (all[i].lonely) for (size_t k = i; k < j; k++) out.push_back({ all[k].idx });
-            else { out.emplace_back(); for (size_t k = i; k < j; k++) out.back().push_back(all[k].idx); }
+        const uint32_t m = (uint32_t)g.size();
+        buf.clear(); off.assign(1, 0); lonely.clear(); order.resize(m);
+        for (uint32_t t = 0; t < m; t++) { lonely.push_back(append_key(pk, kind, g[t], buf)); off.push_back((uint32_t)buf.size()); order[t] = t; }
+        const int64_t *B = buf.data();
+        auto cmp3 = [&](uint32_t a, uint32_t b) {              // lexicographic, shorter prefix first (Vec<T>'s Ord)
+            const uint32_t la = off[a + 1] - off[a], lb = off[b + 1] - off[b], l = std::min(la, lb);
+            for (uint32_t i = 0; i < l; i++) { const int64_t x = B[off[a] + i], y = B[off[b] + i]; if (x != y) return x < y ? -1 : 1; }
+            return la == lb ? 0 : (la < lb ? -1 : 1);
+        };
+        // Only equality of keys matters for the partition (the order of the groups does not): sort by a 64-bit hash of the
+        // key, then by index, and fall back to the full comparison inside a run of equal hashes that holds different keys.
+        hk.resize(m);
+        for (uint32_t t = 0; t < m; t++) {
+            uint64_t h = 0x9E3779B97F4A7C15ull ^ (off[t + 1] - off[t]);
+            for (uint32_t i = off[t]; i < off[t + 1]; i++) { h ^= (uint64_t)B[i]; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29; }
+            hk[t] = { h, ((uint64_t)g[t] << 32) | t };
+        }
+        std::sort(hk.begin(), hk.end());
+        for (uint32_t i = 0; i < m;) {
+            uint32_t j = i + 1;
+            bool mixed = false;
+            while (j < m && hk[j].first == hk[i].first) { mixed = mixed || cmp3((uint32_t)hk[i].second, (uint32_t)hk[j].second) != 0; j++; }
+            for (uint32_t k = i; k < j; k++) order[k] = (uint32_t)hk[k].second;
+            if (mixed) std::sort(order.begin() + i, order.begin() + j, [&](uint32_t a, uint32_t b) { const int c = cmp3(a, b); return c ? c < 0 : g[a] < g[b]; });
+            i = j;
+        }
+        for (uint32_t i = 0; i < m;) {
+            uint32_t j = i + 1;
+            while (j < m && cmp3(order[i], order[j]) == 0) j++;
+            if (lonely[order[i]]) for (uint32_t k = i; k < j; k++) out.push_back({ g[order[k]] });
+            else { out.emplace_back(); out.back().reserve(j - i); for (uint32_t k = i; k < j; k++) out.back().push_back(g[order[k]]); }
             i = j;
         }
     }
@@ -263,6 +292,8 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
     Groups G(1);
     for (uint32_t i = 0; i < n; i++) G[0].push_back(i);
     if (n == 0) G.clear();
+    const bool dbg = getenv("EGROUP_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "[egroup] init %.3f ms\n", now_ms() - t0);
     if (op->vj_refname) key_pass(pk, K_VJ, G);
     if (op->vdj_refname) key_pass(pk, K_VDJ, G);
     if (op->v_heavy_refname) key_pass(pk, K_VH, G);
@@ -272,6 +303,7 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
     if (op->cdr3_len) key_pass(pk, K_CDR3LEN, G);
     if (op->cdr3_heavy_len) key_pass(pk, K_CDR3HLEN, G);
     if (op->cdr3_light_len) key_pass(pk, K_CDR3LLEN, G);
+    if (dbg) fprintf(stderr, "[egroup] key partitions done %.3f ms, %zu groups\n", now_ms() - t0, G.size());
     const struct { double pc; int kind, left; } passes[] = {
         { op->heavy_pc, D_SEQ, 1 }, { op->light_pc, D_SEQ, 0 }, { op->cdr3_heavy_pc_hf, D_HF, 1 }, { op->aa_heavy_pc, D_AA, 1 }, { op->aa_light_pc, D_AA, 0 },
         { op->cdr3_heavy_pc, D_CDR3, 1 }, { op->cdr3_light_pc, D_CDR3, 0 }, { op->cdr3_aa_heavy_pc, D_CDR3AA, 1 }, { op->cdr3_aa_light_pc, D_CDR3AA, 0 } };
@@ -366,6 +398,7 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
         if (hc.err & ERR_BAD_BYTE) return gfail(-4, "a nucleotide sequence holds a byte outside ACGTN-");
         if (hc.err & ERR_TOO_LONG) return gfail(-4, "a sequence compared by a distance pass is longer than 512 symbols");
     }
+    if (dbg) fprintf(stderr, "[egroup] distance passes done %.3f ms\n", now_ms() - t0);
     // grouper.rs:760-766: join consecutive members of every group; labels = smallest member
     std::vector<uint32_t> parent(n);
     for (uint32_t i = 0; i < n; i++) parent[i] = i;
