@@ -171,6 +171,102 @@ __global__ void k_validate_nt(const uint8_t *__restrict__ a, unsigned long long 
 __global__ void k_iota(uint32_t *p, uint32_t n) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
 __global__ void k_flatten(uint32_t *label, uint32_t n, uint32_t *out) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = uf_find(label, i); }
 
+
+// ---- Case 2: asymmetric grouping (grouper.rs:828-928) ---------------------------------------------------------------
+#define ASYM_INF 1000000000u
+#define ASYM_BINS 2048             // distances of real pairs are <= 2 * 512; everything else is ASYM_INF
+
+// distance(center c, clonotype j), grouper.rs:856-889: integers throughout (the source's f64 values are these integers)
+__device__ uint32_t asym_dist(const GDev &d, uint32_t c, uint32_t j, GCounters *ctr, unsigned long long &compares) {
+    uint32_t best = ASYM_INF;
+    for (uint32_t x1 = d.clono_exact_off[c]; x1 < d.clono_exact_off[c + 1]; x1++)
+        for (uint32_t x2 = d.clono_exact_off[j]; x2 < d.clono_exact_off[j + 1]; x2++) {
+            const uint32_t u1 = d.clono_exact[x1], u2 = d.clono_exact[x2];
+            uint32_t heavy = ASYM_INF, light = ASYM_INF;
+            for (uint32_t m1 = d.exact_chain_off[u1]; m1 < d.exact_chain_off[u1 + 1]; m1++)
+                for (uint32_t m2 = d.exact_chain_off[u2]; m2 < d.exact_chain_off[u2 + 1]; m2++) {
+                    if ((d.left[m1] != 0) != (d.left[m2] != 0)) continue;
+                    const uint32_t l1 = d.cdr3_aa_len[m1], l2 = d.cdr3_aa_len[m2];
+                    if (min(l1, l2) > 64 * MAXW || max(l1, l2) > 512) { atomicOr(&ctr->err, ERR_TOO_LONG); continue; }
+                    const uint32_t x = lev_aa(d.aa_arena + d.cdr3_aa_off[m1], l1, d.aa_arena + d.cdr3_aa_off[m2], l2);
+                    compares++;
+                    if (d.left[m1]) heavy = min(heavy, x); else light = min(light, x);
+                }
+            best = min(best, heavy + light);
+        }
+    return best;
+}
+
+// max=D / no bound: every (center, clonotype) pair is a thread; the ones within the bound are appended to one list
+__global__ void __launch_bounds__(128) k_asym_max(GDev d, const uint32_t *__restrict__ center, uint32_t n_center, uint32_t n, uint32_t dcut,
+                                                  uint4 *out, unsigned long long cap, unsigned long long *n_out, GCounters *ctr) {
+    unsigned long long compares = 0, pairs = 0;
+    const unsigned long long total = (unsigned long long)n_center * n;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(t / n), j = (uint32_t)(t % n);
+        const uint32_t dist = asym_dist(d, center[i], j, ctr, compares);
+        pairs++;
+        if (dist <= dcut) {
+            const unsigned long long w = atomicAdd(n_out, 1ull);
+            if (w < cap) out[w] = make_uint4(i, j, dist, 0u);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { compares += __shfl_xor_sync(0xFFFFFFFFu, compares, o); pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o); }
+    if ((threadIdx.x & 31) == 0 && (compares | pairs)) { atomicAdd(&ctr->chain_compares, compares); atomicAdd(&ctr->pairs_evaluated, pairs); }
+}
+
+// top=N: one CTA per center.  Pass 1 computes the center's row of distances (kept in `row`) and a histogram of them in
+// shared memory; the histogram gives the distance d* at which the sorted order reaches position N and how many entries of
+// distance d* are still needed; pass 2 walks the row in ascending index order and emits everything below d* plus the first
+// `r` entries at d* — the N+1 smallest by (distance, index), the order of id.sort_by at grouper.rs:908.
+__global__ void __launch_bounds__(256) k_asym_top(GDev d, const uint32_t *__restrict__ center, uint32_t n_center, uint32_t n, uint32_t need,
+                                                  uint32_t *row_all, uint2 *out, GCounters *ctr) {
+    __shared__ uint32_t hist[ASYM_BINS];
+    __shared__ uint32_t s_dstar, s_r, s_base_take, s_base_eq;
+    __shared__ uint32_t scan_take[256], scan_eq[256];
+    uint32_t *row = row_all + (size_t)blockIdx.x * n;
+    unsigned long long compares = 0, pairs = 0;
+    for (uint32_t i = blockIdx.x; i < n_center; i += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < ASYM_BINS; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        const uint32_t c = center[i];
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint32_t dist = asym_dist(d, c, j, ctr, compares);
+            pairs++;
+            row[j] = dist;
+            atomicAdd(&hist[min(dist, (uint32_t)ASYM_BINS - 1)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cum = 0, b = 0;
+            for (; b < ASYM_BINS; b++) { if (cum + hist[b] >= need) break; cum += hist[b]; }
+            s_dstar = b; s_r = need - cum; s_base_take = 0; s_base_eq = 0;
+        }
+        __syncthreads();
+        const uint32_t dstar = s_dstar, r = s_r;
+        for (uint32_t j0 = 0; j0 < n; j0 += blockDim.x) {
+            const uint32_t j = j0 + threadIdx.x;
+            const uint32_t code = j < n ? min(row[j], (uint32_t)ASYM_BINS - 1) : 0xFFFFFFFFu;
+            const uint32_t eq = code == dstar ? 1u : 0u, below = code < dstar ? 1u : 0u;
+            scan_eq[threadIdx.x] = eq;
+            __syncthreads();
+            // inclusive scans over the chunk (Hillis-Steele; 256 entries)
+            for (uint32_t o = 1; o < blockDim.x; o <<= 1) { const uint32_t v = threadIdx.x >= o ? scan_eq[threadIdx.x - o] : 0u; __syncthreads(); scan_eq[threadIdx.x] += v; __syncthreads(); }
+            const uint32_t eq_rank = s_base_eq + scan_eq[threadIdx.x] - eq;           // entries at d* before this one
+            const uint32_t take = below | (eq && eq_rank < r ? 1u : 0u);
+            scan_take[threadIdx.x] = take;
+            __syncthreads();
+            for (uint32_t o = 1; o < blockDim.x; o <<= 1) { const uint32_t v = threadIdx.x >= o ? scan_take[threadIdx.x - o] : 0u; __syncthreads(); scan_take[threadIdx.x] += v; __syncthreads(); }
+            if (take) out[(size_t)i * need + s_base_take + scan_take[threadIdx.x] - 1] = make_uint2(j, row[j]);
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) { s_base_take += scan_take[threadIdx.x]; s_base_eq += scan_eq[threadIdx.x]; }
+            __syncthreads();
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { compares += __shfl_xor_sync(0xFFFFFFFFu, compares, o); pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o); }
+    if ((threadIdx.x & 31) == 0 && (compares | pairs)) { atomicAdd(&ctr->chain_compares, compares); atomicAdd(&ctr->pairs_evaluated, pairs); }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 typedef std::vector<std::vector<uint32_t>> Groups;
 
@@ -269,6 +365,29 @@ struct StreamBox { cudaStream_t s = nullptr; cudaEvent_t e0 = nullptr, e1 = null
 
 double now_ms() { using namespace std::chrono; return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count(); }
 
+int upload_pack(DevMem &M, const egroup_pack_t *pk, GDev &d) {
+    const uint32_t n = pk->n_clono;
+    GCK(M.up(d.clono_exact_off, pk->clono_exact_off, (size_t)n + 1));
+    GCK(M.up(d.clono_exact, pk->clono_exact, pk->clono_exact_off[n]));
+    GCK(M.up(d.exact_chain_off, pk->exact_chain_off, (size_t)pk->n_exact + 1));
+    GCK(M.up(d.left, pk->left, pk->n_chain));
+    GCK(M.up(d.seq_off, pk->seq_off, pk->n_chain)); GCK(M.up(d.seq_len, pk->seq_len, pk->n_chain));
+    GCK(M.up(d.cdr3_start, pk->cdr3_start, pk->n_chain));
+    GCK(M.up(d.cdr3_aa_off, pk->cdr3_aa_off, pk->n_chain)); GCK(M.up(d.cdr3_aa_len, pk->cdr3_aa_len, pk->n_chain));
+    GCK(M.up(d.seq_arena, pk->seq_arena, pk->seq_arena_bytes)); GCK(M.up(d.aa_arena, pk->aa_arena, pk->aa_arena_bytes));
+    return 0;
+}
+
+int check_group_pack(const egroup_pack_t *pk) {
+    if (pk->abi_version != EGROUP_ABI_VERSION) return gfail(-1, "abi_version mismatch");
+    if (pk->n_clono && (!pk->clono_exact_off || !pk->clono_exact || !pk->exact_chain_off || !pk->left || !pk->seq_off || !pk->seq_len || !pk->seq_del_len ||
+                        !pk->cdr3_start || !pk->cdr3_aa_off || !pk->cdr3_aa_len || !pk->seq_arena || !pk->aa_arena || !pk->col_off))
+        return gfail(-1, "null array in pack");
+    return 0;
+}
+
+struct AsymOwner { std::vector<uint64_t> off; std::vector<uint32_t> member; std::vector<double> dist; };
+
 }  // namespace
 
 extern "C" const char *egroup_last_error(void) { return g_err.c_str(); }
@@ -280,11 +399,8 @@ extern "C" void egroup_opts_default(egroup_opts_t *o) {
 
 extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int device, uint32_t *group_of, egroup_stats_t *stats) {
     if (!pk || !op || (pk->n_clono && !group_of)) return gfail(-1, "null argument");
-    if (pk->abi_version != EGROUP_ABI_VERSION) return gfail(-1, "abi_version mismatch");
+    if (int rc = check_group_pack(pk)) return rc;
     const uint32_t n = pk->n_clono;
-    if (n && (!pk->clono_exact_off || !pk->clono_exact || !pk->exact_chain_off || !pk->left || !pk->seq_off || !pk->seq_len || !pk->seq_del_len ||
-              !pk->cdr3_start || !pk->cdr3_aa_off || !pk->cdr3_aa_len || !pk->seq_arena || !pk->aa_arena || !pk->col_off))
-        return gfail(-1, "null array in pack");
     if (op->cdr3_heavy_pc_hf >= 0.0 && !op->hf_matrix) return gfail(-1, "cdr3_heavy_pc_hf without its penalty matrix");
     const double t0 = now_ms();
     egroup_stats_t st;
@@ -320,14 +436,7 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
         GDev d;
         int sm = 148;
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
-        GCK(M.up(d.clono_exact_off, pk->clono_exact_off, (size_t)n + 1));
-        GCK(M.up(d.clono_exact, pk->clono_exact, pk->clono_exact_off[n]));
-        GCK(M.up(d.exact_chain_off, pk->exact_chain_off, (size_t)pk->n_exact + 1));
-        GCK(M.up(d.left, pk->left, pk->n_chain));
-        GCK(M.up(d.seq_off, pk->seq_off, pk->n_chain)); GCK(M.up(d.seq_len, pk->seq_len, pk->n_chain));
-        GCK(M.up(d.cdr3_start, pk->cdr3_start, pk->n_chain));
-        GCK(M.up(d.cdr3_aa_off, pk->cdr3_aa_off, pk->n_chain)); GCK(M.up(d.cdr3_aa_len, pk->cdr3_aa_len, pk->n_chain));
-        GCK(M.up(d.seq_arena, pk->seq_arena, pk->seq_arena_bytes)); GCK(M.up(d.aa_arena, pk->aa_arena, pk->aa_arena_bytes));
+        if (int rc = upload_pack(M, pk, d)) return rc;
         double penalty_h[27 * 27];
         memset(penalty_h, 0, sizeof(penalty_h));
         if (op->cdr3_heavy_pc_hf >= 0.0) {                                   // grouper.rs:463-472
@@ -410,5 +519,133 @@ extern "C" int egroup_run(const egroup_pack_t *pk, const egroup_opts_t *op, int 
     st.n_groups = ncls;
     st.ms_total = now_ms() - t0;
     if (stats) *stats = st;
+    return 0;
+}
+
+extern "C" void egroup_asym_free(egroup_asym_result_t *r) {
+    if (!r) return;
+    delete (AsymOwner *)r->owner;
+    memset(r, 0, sizeof(*r));
+}
+
+extern "C" int egroup_run_asym(const egroup_pack_t *pk, const uint8_t *in_center, const egroup_asym_opts_t *op, int device,
+                               egroup_asym_result_t *out, egroup_stats_t *stats) {
+    if (!pk || !op || !out || (pk->n_clono && !in_center)) return gfail(-1, "null argument");
+    if (int rc = check_group_pack(pk)) return rc;
+    if (op->bound_kind < EGROUP_BOUND_TOP || op->bound_kind > EGROUP_BOUND_NONE) return gfail(-1, "bound_kind");
+    memset(out, 0, sizeof(*out));
+    const double t0 = now_ms();
+    egroup_stats_t st;
+    memset(&st, 0, sizeof(st));
+    const uint32_t n = pk->n_clono;
+    std::vector<uint32_t> center;
+    for (uint32_t i = 0; i < n; i++) if (in_center[i]) center.push_back(i);             // grouper.rs:832-853
+    const uint32_t nc = (uint32_t)center.size();
+    AsymOwner *own = new AsymOwner();
+    out->owner = own;
+    struct Guard { egroup_asym_result_t *o; bool ok; ~Guard() { if (!ok) egroup_asym_free(o); } } guard{ out, false };
+    // per center: the (index, distance) candidates the walk of grouper.rs:909-920 can reach, unsorted
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> cand(nc);                   // (distance, index)
+    if (nc) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return gfail(-3, "no usable CUDA device (the distance matrix has no CPU fallback)"); }
+        GCK(cudaSetDevice(device));
+        StreamBox box;
+        GCK(cudaStreamCreateWithFlags(&box.s, cudaStreamNonBlocking));
+        cudaStream_t s = box.s;
+        DevMem M(s);
+        GDev d;
+        int sm = 148;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+        if (int rc = upload_pack(M, pk, d)) return rc;
+        const uint32_t *d_center = nullptr;
+        GCK(M.up(d_center, center.data(), nc));
+        GCounters *d_ctr = nullptr;
+        GCK(M.take(d_ctr, 1));
+        GCK(cudaMemsetAsync(d_ctr, 0, sizeof(GCounters), s));
+        GCK(cudaEventCreate(&box.e0)); GCK(cudaEventCreate(&box.e1));
+        GCK(cudaEventRecord(box.e0, s));
+        st.pairs_candidate = (uint64_t)nc * n;
+        if (op->bound_kind == EGROUP_BOUND_TOP) {
+            const uint32_t need = (uint32_t)std::min<uint64_t>((uint64_t)op->top + 1, n);
+            // one row of distances per resident CTA; the grid is cut so that the rows stay under 512 MB
+            unsigned blocks = (unsigned)std::min<uint64_t>(nc, (uint64_t)sm * 4);
+            blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (512ull << 20) / (4ull * n)));
+            uint32_t *d_row = nullptr;
+            uint2 *d_out = nullptr;
+            GCK(M.take(d_row, (size_t)blocks * n));
+            GCK(M.take(d_out, (size_t)nc * need));
+            k_asym_top<<<blocks, 256, 0, s>>>(d, d_center, nc, n, need, d_row, d_out, d_ctr);
+            st.gpu_launches++;
+            GCK(cudaGetLastError());
+            std::vector<uint2> h((size_t)nc * need);
+            GCK(cudaMemcpyAsync(h.data(), d_out, sizeof(uint2) * h.size(), cudaMemcpyDeviceToHost, s));
+            GCK(cudaStreamSynchronize(s));
+            for (uint32_t i = 0; i < nc; i++)
+                for (uint32_t k = 0; k < need; k++) cand[i].push_back({ h[(size_t)i * need + k].y, h[(size_t)i * need + k].x });
+        } else {
+            // d <= D for integer d  <=>  d <= floor(D); no bound: everything (distances never exceed ASYM_INF)
+            uint32_t dcut = ASYM_INF;
+            bool none = false;
+            if (op->bound_kind == EGROUP_BOUND_MAX) {
+                if (!(op->max_dist >= 0.0)) none = true;
+                else dcut = op->max_dist >= (double)ASYM_INF ? ASYM_INF : (uint32_t)std::floor(op->max_dist);
+            }
+            if (!none) {
+                unsigned long long *d_n = nullptr;
+                GCK(M.take(d_n, 1));
+                unsigned long long cap = std::max<unsigned long long>(1ull << 20, 64ull * nc), got = 0;
+                const unsigned long long total = (unsigned long long)nc * n;
+                cap = std::min(cap, total);
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    uint4 *d_out = nullptr;
+                    GCK(M.take(d_out, cap));
+                    GCK(cudaMemsetAsync(d_n, 0, 8, s));
+                    const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 127) / 128, (unsigned long long)sm * 16);
+                    k_asym_max<<<blocks, 128, 0, s>>>(d, d_center, nc, n, dcut, d_out, cap, d_n, d_ctr);
+                    st.gpu_launches++;
+                    GCK(cudaGetLastError());
+                    GCK(cudaMemcpyAsync(&got, d_n, 8, cudaMemcpyDeviceToHost, s));
+                    GCK(cudaStreamSynchronize(s));
+                    if (got <= cap) {
+                        std::vector<uint4> h(got);
+                        GCK(cudaMemcpyAsync(h.data(), d_out, sizeof(uint4) * got, cudaMemcpyDeviceToHost, s));
+                        GCK(cudaStreamSynchronize(s));
+                        for (const uint4 &e : h) cand[e.x].push_back({ e.z, e.y });
+                        break;
+                    }
+                    cap = got;                                   // the list was too small: once more with the size it asked for
+                }
+            }
+        }
+        GCK(cudaEventRecord(box.e1, s));
+        GCounters hc;
+        GCK(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
+        GCK(cudaStreamSynchronize(s));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, box.e0, box.e1);
+        st.ms_device = ms; st.pairs_evaluated = hc.pairs_evaluated; st.chain_compares = hc.chain_compares;
+        if (hc.err & ERR_TOO_LONG) return gfail(-4, "a CDR3 amino acid sequence longer than 512");
+    }
+    // grouper.rs:891-925
+    own->off.push_back(0);
+    for (uint32_t i = 0; i < nc; i++) {
+        auto &id = cand[i];
+        std::sort(id.begin(), id.end());                                                  // (distance, index), :908
+        const size_t start = own->member.size();
+        own->member.push_back(center[i]); own->dist.push_back(0.0);                       // :903
+        for (size_t p = 0; p < id.size(); p++) {
+            if (op->bound_kind == EGROUP_BOUND_TOP && p > op->top) break;
+            if (op->bound_kind == EGROUP_BOUND_MAX && (double)id[p].first > op->max_dist) break;
+            if (id[p].second != center[i]) { own->member.push_back(id[p].second); own->dist.push_back((double)id[p].first); }
+        }
+        if (own->member.size() - start >= op->min_group) own->off.push_back(own->member.size());
+        else { own->member.resize(start); own->dist.resize(start); }
+    }
+    out->n_groups = own->off.size() - 1; out->group_off = own->off.data(); out->member = own->member.data(); out->dist = own->dist.data();
+    st.n_groups = out->n_groups;
+    st.ms_total = now_ms() - t0;
+    if (stats) *stats = st;
+    guard.ok = true;
     return 0;
 }

@@ -41,6 +41,17 @@ class EgroupStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class EgroupAsymOpts(C.Structure):
+    _fields_ = [("bound_kind", C.c_int32), ("top", C.c_uint32), ("max_dist", C.c_double), ("min_group", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class EgroupAsymResult(C.Structure):
+    _fields_ = [("n_groups", C.c_uint64), ("group_off", C.POINTER(C.c_uint64)), ("member", C.POINTER(C.c_uint32)), ("dist", C.POINTER(C.c_double)),
+                ("owner", C.c_void_p)]
+
+
+BOUND_TOP, BOUND_MAX, BOUND_NONE = 0, 1, 2
+
 KEY_FLAGS = ("vj_refname", "vdj_refname", "v_heavy_refname", "vj_heavy_refname", "vdj_heavy_refname", "vj_len", "cdr3_len", "cdr3_heavy_len", "cdr3_light_len")
 DIST_OPTS = ("heavy_pc", "light_pc", "cdr3_heavy_pc_hf", "aa_heavy_pc", "aa_light_pc", "cdr3_heavy_pc", "cdr3_light_pc", "cdr3_aa_heavy_pc", "cdr3_aa_light_pc")
 
@@ -103,6 +114,9 @@ def _bind():
         L.egroup_run.argtypes = [C.POINTER(EgroupPack), C.POINTER(EgroupOpts), C.c_int, C.POINTER(C.c_uint32), C.POINTER(EgroupStats)]
         L.egroup_run.restype = C.c_int
         L.egroup_last_error.restype = C.c_char_p
+        L.egroup_run_asym.argtypes = [C.POINTER(EgroupPack), C.POINTER(C.c_uint8), C.POINTER(EgroupAsymOpts), C.c_int, C.POINTER(EgroupAsymResult), C.POINTER(EgroupStats)]
+        L.egroup_run_asym.restype = C.c_int
+        L.egroup_asym_free.argtypes = [C.POINTER(EgroupAsymResult)]
         _bound = True
     return L
 
@@ -118,6 +132,43 @@ def group_clonotypes(pack, device=0, hf_matrix=None, **opts):
         raise _lib.EjoinError(rc, (L.egroup_last_error() or b"").decode())
     del keep
     return out[:pack.n_clono], st.as_dict()
+
+
+def asym_opts(top=None, max_dist=None, min_group=1):
+    """AG_DIST_BOUND=top=N or max=D (one of them, as in the reference; neither = no bound), MIN_GROUP"""
+    o = EgroupAsymOpts()
+    if top is not None and max_dist is not None:
+        raise TypeError("AG_DIST_BOUND is top=N or max=D, not both")
+    o.bound_kind = BOUND_TOP if top is not None else (BOUND_MAX if max_dist is not None else BOUND_NONE)
+    o.top = int(top or 0)
+    o.max_dist = float(max_dist if max_dist is not None else 0.0)
+    o.min_group = int(min_group)
+    return o
+
+
+def result_groups(res):
+    """[[(clonotype, distance), ...], ...] — the center first, with distance 0"""
+    out = []
+    for g in range(res.n_groups):
+        a, b = res.group_off[g], res.group_off[g + 1]
+        out.append([(int(res.member[k]), float(res.dist[k])) for k in range(a, b)])
+    return out
+
+
+def group_asymmetric(pack, in_center, top=None, max_dist=None, min_group=1, device=0):
+    """Case 2 of grouper() (AGROUP): (groups, stats); in_center[i] != 0 marks the center clonotypes."""
+    L = _bind()
+    o = asym_opts(top, max_dist, min_group)
+    cen = np.ascontiguousarray(in_center, np.uint8)
+    assert cen.size == pack.n_clono
+    res, st = EgroupAsymResult(), EgroupStats()
+    rc = L.egroup_run_asym(C.byref(pack.struct), cen.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(o), device, C.byref(res), C.byref(st))
+    if rc != 0:
+        raise _lib.EjoinError(rc, (L.egroup_last_error() or b"").decode())
+    try:
+        return result_groups(res), st.as_dict()
+    finally:
+        L.egroup_asym_free(C.byref(res))
 
 
 # ---- synthetic workload ----------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@
  * cdr3_light_pc :614-687, cdr3_aa_heavy_pc / cdr3_aa_light_pc :689-758) run on the GPU (bit-parallel Levenshtein, one
  * thread per clonotype pair, GPU union-find); the key partitions (:64-384) are host-side sorts.  The result is the
  * partition of the final EquivRel `e` (:760-766) as min-member labels; keeper_group, the ordering of groups by cell
- * count and Case 2 (asymmetric) stay with the caller.  Each distance pass reproduces the reference's own orbit idiom,
+ * count stay with the caller.  Case 2 (asymmetric grouping) is egroup_run_asym below.  Each distance pass reproduces the reference's own orbit idiom,
  * including `ee.orbit(i)` for i < #orbits (:441-452; see oracle/grouper_oracle.c).
  *
  * Flat view of (exacts, exact_clonotypes, rsi, opt_d_val, refdata.name): clonotype i = exacts[i] (a list of exact
@@ -78,6 +78,34 @@ void egroup_opts_default(egroup_opts_t *o);      /* nothing asked for */
  * without a CUDA device when a distance pass is asked for: there is no CPU fallback for those. */
 int  egroup_run(const egroup_pack_t *pack, const egroup_opts_t *opts, int device, uint32_t *group_of, egroup_stats_t *stats);
 const char *egroup_last_error(void);
+
+/* ---- Case 2: asymmetric grouping (grouper.rs:828-928; AGROUP, AG_CENTER, AG_DIST_FORMULA=cdr3_edit_distance, AG_DIST_BOUND) ----
+ * center = the clonotypes with in_center[i] != 0 (:832-853).  distance(center c, clonotype j) = min(1e9, min over the pairs of
+ * exact subclonotypes of (heavy + light)), heavy / light = the smallest Levenshtein distance between heavy / light CDR3 amino acid
+ * strings of the two, 1e9 when there is no such pair of chains (:856-889).  Per center the clonotypes are sorted by (distance,
+ * index); with top=N the sorted positions 0..N are taken, with max=D the ones with distance <= D; the center itself is listed
+ * first with distance 0 and skipped in the walk; groups smaller than min_group are dropped (:891-925).  The distance matrix and
+ * the selection run on the GPU; the result arrays belong to the library until egroup_asym_free. */
+#define EGROUP_BOUND_TOP 0
+#define EGROUP_BOUND_MAX 1
+#define EGROUP_BOUND_NONE 2          /* neither: every clonotype is in every group */
+typedef struct egroup_asym_opts {
+    int32_t  bound_kind;
+    uint32_t top;                    /* AG_DIST_BOUND=top=N */
+    double   max_dist;               /* AG_DIST_BOUND=max=D */
+    uint32_t min_group;              /* ctl.clono_group_opt.min_group */
+    uint32_t reserved;
+} egroup_asym_opts_t;
+typedef struct egroup_asym_result {
+    uint64_t  n_groups;
+    uint64_t *group_off;             /* [n_groups + 1] into member / dist */
+    uint32_t *member;                /* member[group_off[g]] is the group's center */
+    double   *dist;                  /* the number printed as "distance = {}" */
+    void     *owner;
+} egroup_asym_result_t;
+int  egroup_run_asym(const egroup_pack_t *pack, const uint8_t *in_center, const egroup_asym_opts_t *opts, int device,
+                     egroup_asym_result_t *out, egroup_stats_t *stats);
+void egroup_asym_free(egroup_asym_result_t *r);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,8 @@
  * gtest17, the two full 448-base heavy V..J sequences) that five of the reference's goldens print as ONE group
  * (enclone_gtest5/7/8/17/19_output; commands enclone_exec/tests/enclone_test2.rs:176-270); tests/test_grouper.py checks that this
  * restatement groups them under the same options (heavy>=96.6% sits 0.05 % under the pair's identity of 433/448).
- * Not restated: keeper_group and the ordering of groups by cell count (:762-820, presentation), Case 2 (asymmetric).
+ * Not restated: keeper_group and the ordering of groups by cell count (:768-826, presentation).  Case 2 (asymmetric grouping,
+ * :828-928) is oracle_group_asym at the end of this file, pinned on the distances enclone_gtest10/11/12_output print.
  *
  * Each distance pass ends with the reference's own idiom (:441-452 and its four copies):
  *     ee.orbit_reps(&mut reps);  for i in 0..reps.len() { ee.orbit(i as i32, &mut o); ... }
@@ -282,3 +283,60 @@ int oracle_group(const egroup_pack_t *pk, const egroup_opts_t *op, uint32_t *gro
     if (evals_out) *evals_out = evals;
     return 0;
 }
+
+/* ---- Case 2: asymmetric grouping, grouper.rs:828-928 ---- */
+static double asym_dist(const egroup_pack_t *pk, uint32_t c, uint32_t j, uint64_t *evals) {
+    const double infinity = 1000000000.0;
+    double best = infinity;                                                              /* :856-859 */
+    for (uint32_t x1 = pk->clono_exact_off[c]; x1 < pk->clono_exact_off[c + 1]; x1++)
+        for (uint32_t x2 = pk->clono_exact_off[j]; x2 < pk->clono_exact_off[j + 1]; x2++) {
+            const uint32_t u1 = pk->clono_exact[x1], u2 = pk->clono_exact[x2];
+            double heavy = infinity, light = infinity;                                   /* :867 */
+            for (uint32_t m1 = pk->exact_chain_off[u1]; m1 < pk->exact_chain_off[u1 + 1]; m1++)
+                for (uint32_t m2 = pk->exact_chain_off[u2]; m2 < pk->exact_chain_off[u2 + 1]; m2++) {
+                    if ((pk->left[m1] != 0) != (pk->left[m2] != 0)) continue;
+                    const double x = (double)levenshtein(pk->aa_arena + pk->cdr3_aa_off[m1], pk->cdr3_aa_len[m1], pk->aa_arena + pk->cdr3_aa_off[m2], pk->cdr3_aa_len[m2]);
+                    (*evals)++;
+                    if (pk->left[m1]) { if (x < heavy) heavy = x; } else { if (x < light) light = x; }   /* :873-880 */
+                }
+            if (heavy + light < best) best = heavy + light;                              /* :883 */
+        }
+    return best;
+}
+typedef struct { double d; uint32_t j; } dj_t;
+static int dj_cmp(const void *a, const void *b) {
+    const dj_t *x = (const dj_t *)a, *y = (const dj_t *)b;
+    if (x->d != y->d) return x->d < y->d ? -1 : 1;
+    return x->j < y->j ? -1 : (x->j > y->j ? 1 : 0);
+}
+int oracle_group_asym(const egroup_pack_t *pk, const uint8_t *in_center, const egroup_asym_opts_t *op, egroup_asym_result_t *out, uint64_t *evals_out) {
+    const uint32_t n = pk->n_clono;
+    uint64_t evals = 0, ng = 0, nm = 0, cap_g = 16, cap_m = 64;
+    uint64_t *goff = (uint64_t *)malloc(sizeof(uint64_t) * (cap_g + 1));
+    uint32_t *mem = (uint32_t *)malloc(sizeof(uint32_t) * cap_m);
+    double *dist = (double *)malloc(sizeof(double) * cap_m);
+    dj_t *id = (dj_t *)malloc(sizeof(dj_t) * (n ? n : 1));
+    for (uint32_t c = 0; c < n; c++) {
+        if (!in_center[c]) continue;                                                      /* :832-853 */
+        for (uint32_t j = 0; j < n; j++) { id[j].d = asym_dist(pk, c, j, &evals); id[j].j = j; }
+        qsort(id, n, sizeof(dj_t), dj_cmp);                                               /* :908 */
+        const uint64_t start = nm;
+#define PUSH_M(a, b) do { if (nm == cap_m) { cap_m *= 2; mem = (uint32_t *)realloc(mem, sizeof(uint32_t) * cap_m); dist = (double *)realloc(dist, sizeof(double) * cap_m); } mem[nm] = (a); dist[nm] = (b); nm++; } while (0)
+        PUSH_M(c, 0.0);                                                                   /* :903 */
+        for (uint32_t p = 0; p < n; p++) {
+            if (op->bound_kind == EGROUP_BOUND_TOP && p > op->top) break;                 /* :910-912 */
+            if (op->bound_kind == EGROUP_BOUND_MAX && id[p].d > op->max_dist) break;      /* :913-916 */
+            if (id[p].j != c) PUSH_M(id[p].j, id[p].d);                                   /* :917-919 */
+        }
+        if (nm - start >= op->min_group) {                                                /* :921 */
+            if (ng == cap_g) { cap_g *= 2; goff = (uint64_t *)realloc(goff, sizeof(uint64_t) * (cap_g + 1)); }
+            goff[ng++] = start;
+        } else nm = start;
+    }
+    goff[ng] = nm;
+    free(id);
+    out->n_groups = ng; out->group_off = goff; out->member = mem; out->dist = dist; out->owner = NULL;
+    if (evals_out) *evals_out = evals;
+    return 0;
+}
+void oracle_group_asym_free(egroup_asym_result_t *r) { free(r->group_off); free(r->member); free(r->dist); r->group_off = NULL; r->member = NULL; r->dist = NULL; }

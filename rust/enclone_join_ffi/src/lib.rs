@@ -152,6 +152,13 @@ extern "C" {
     pub fn egroup_opts_default(o: *mut egroup_opts_t);
     pub fn egroup_run(pack: *const egroup_pack_t, opts: *const egroup_opts_t, device: c_int, group_of: *mut u32, stats: *mut egroup_stats_t) -> c_int;
     pub fn egroup_last_error() -> *const c_char;
+    pub fn egroup_run_asym(pack: *const egroup_pack_t, in_center: *const u8, opts: *const egroup_asym_opts_t, device: c_int,
+                           out: *mut egroup_asym_result_t, stats: *mut egroup_stats_t) -> c_int;
+    pub fn egroup_asym_free(r: *mut egroup_asym_result_t);
 }
+#[repr(C)]
+pub struct egroup_asym_opts_t { pub bound_kind: i32, pub top: u32, pub max_dist: f64, pub min_group: u32, pub reserved: u32 }
+#[repr(C)]
+pub struct egroup_asym_result_t { pub n_groups: u64, pub group_off: *mut u64, pub member: *mut u32, pub dist: *mut f64, pub owner: *mut c_void }
 // The safe wrapper `join_exacts(..) -> EquivRel` with `Flat::pack` is sketched in INTEGRATION.md §1-§3;
 // enclone_b200/host/join_exacts.hpp is the same logic in C++ and is compiled and tested in this repository.

@@ -25,7 +25,8 @@ def clonotypes(t):
                 extra.append(ln.strip())
         hdr = [ln for ln in b.split("\n") if "|IG" in ln]
         names = re.findall(r"\|(IG[A-Z0-9/-]+)", hdr[0]) if hdr else []
-        res.append(dict(rows=rows, seqs=extra, names=names))
+        m = re.search(r"^distance = ([0-9.]+)$", b, re.M)
+        res.append(dict(rows=rows, seqs=extra, names=names, distance=float(m.group(1)) if m else None))
     return res
 
 
@@ -42,6 +43,12 @@ for t, opts, src in ((5, dict(vj_refname=1, cdr3_aa_heavy_pc=80.0, cdr3_aa_light
     pins[f"gtest{t}"] = dict(source=src, golden=f"enclone_gtest{t}_output", opts=opts,
                              clonotypes=[dict(names=c["names"], exacts=[dict(heavy_cdr3=cdr3(h), light_cdr3=cdr3(l)) for h, l in c["rows"]],
                                               vj_seq1=c["seqs"][0] if c["seqs"] else None) for c in cl])
+# Case 2 (AGROUP): the goldens print the distance of every member from the center (the first clonotype)
+for t, bound, src in ((10, dict(top=2), "enclone_test2.rs:210"), (11, dict(max_dist=14.0), "enclone_test2.rs:216"), (12, dict(max_dist=13.0), "enclone_test2.rs:222")):
+    cl = clonotypes(t)
+    pins[f"gtest{t}"] = dict(source=src, golden=f"enclone_gtest{t}_output", asym=bound,
+                             clonotypes=[dict(names=c["names"], exacts=[dict(heavy_cdr3=cdr3(h), light_cdr3=cdr3(l)) for h, l in c["rows"]],
+                                              vj_seq1=None, distance=c["distance"]) for c in cl])
 json.dump(pins, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "gtest_pins.json"), "w"), indent=1)
 for k, v in pins.items():
-    print(k, v["opts"], [(c["names"], [(e["heavy_cdr3"], e["light_cdr3"]) for e in c["exacts"]], len(c["vj_seq1"] or "")) for c in v["clonotypes"]])
+    print(k, v.get("opts") or v.get("asym"), [(c["names"], [(e["heavy_cdr3"], e["light_cdr3"]) for e in c["exacts"]], len(c["vj_seq1"] or ""), c.get("distance")) for c in v["clonotypes"]])

@@ -52,7 +52,10 @@ def lib():
         L.oracle_set_row_limit.argtypes = [C.c_uint32]
         L.oracle_ref_positions_differing.argtypes = [C.POINTER(EjoinPack), C.c_uint32, C.c_uint32]
         L.oracle_ref_positions_differing.restype = C.c_int
-        from enclone_b200.group import EgroupOpts, EgroupPack
+        from enclone_b200.group import EgroupAsymOpts, EgroupAsymResult, EgroupOpts, EgroupPack
+        L.oracle_group_asym.restype = C.c_int
+        L.oracle_group_asym.argtypes = [C.POINTER(EgroupPack), C.POINTER(C.c_uint8), C.POINTER(EgroupAsymOpts), C.POINTER(EgroupAsymResult), C.POINTER(C.c_uint64)]
+        L.oracle_group_asym_free.argtypes = [C.POINTER(EgroupAsymResult)]
         L.oracle_group.restype = C.c_int
         L.oracle_group.argtypes = [C.POINTER(EgroupPack), C.POINTER(EgroupOpts), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         _lib = L
@@ -124,3 +127,15 @@ def accept_graph(pack_struct, params, i, j):
     out = _edges_to_numpy(ep, n.value)
     lib().oracle_free(ep)
     return out
+
+
+def group_asym(pack, in_center, opts_struct):
+    """oracle/grouper_oracle.c, Case 2: ([[(clonotype, distance), ...], ...], distance evaluations)"""
+    from enclone_b200.group import EgroupAsymResult, result_groups
+    cen = np.ascontiguousarray(in_center, np.uint8)
+    res, ev = EgroupAsymResult(), C.c_uint64(0)
+    rc = lib().oracle_group_asym(C.byref(pack.struct), cen.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(opts_struct), C.byref(res), C.byref(ev))
+    assert rc == 0
+    out = result_groups(res)
+    lib().oracle_group_asym_free(C.byref(res))
+    return out, ev.value

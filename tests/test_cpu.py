@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, s), s
     ghdr = open(os.path.join(ROOT, "include", "enclone_group.h")).read()
     gdecl = set(re.findall(r"\b(egroup_[a-z0-9_]+)\s*\(", ghdr))
-    assert gdecl == {"egroup_opts_default", "egroup_run", "egroup_last_error"}
+    assert gdecl == {"egroup_opts_default", "egroup_run", "egroup_last_error", "egroup_run_asym", "egroup_asym_free"}
     for s in gdecl:
         assert hasattr(L, s), s
 
@@ -129,7 +129,7 @@ def test_rust_ffi_crate_declares_the_same_symbols():
     rs = open(os.path.join(ROOT, "rust", "enclone_join_ffi", "src", "lib.rs")).read()
     bound = set(re.findall(r"pub fn (ejoin_[a-z0-9_]+)\(", rs))
     assert bound == set(_lib.EXPORTS), bound ^ set(_lib.EXPORTS)
-    assert set(re.findall(r"pub fn (egroup_[a-z0-9_]+)\(", rs)) == {"egroup_opts_default", "egroup_run", "egroup_last_error"}
+    assert set(re.findall(r"pub fn (egroup_[a-z0-9_]+)\(", rs)) == {"egroup_opts_default", "egroup_run", "egroup_last_error", "egroup_run_asym", "egroup_asym_free"}
 
 
 def test_tier1_work_decomposition_arithmetic(tmp_path):

@@ -121,7 +121,7 @@ def test_oracle_synthetic_is_nontrivial():
 
 def test_symbols_exported():
     L = C.CDLL(G._lib.SO_PATH)
-    for name in ("egroup_opts_default", "egroup_run", "egroup_last_error"):
+    for name in ("egroup_opts_default", "egroup_run", "egroup_last_error", "egroup_run_asym", "egroup_asym_free"):
         assert hasattr(L, name)
 
 
@@ -132,6 +132,9 @@ def test_no_gpu_fails_loudly():
     pk = tiny_pack([BASE, mutated(1)])
     with pytest.raises(G._lib.EjoinError) as ei:
         G.group_clonotypes(pk, heavy_pc=95.0)
+    assert ei.value.code == -3
+    with pytest.raises(G._lib.EjoinError) as ei:
+        G.group_asymmetric(pk, np.ones(2, np.uint8), top=1)
     assert ei.value.code == -3
     # key partitions alone are host work and need no device
     g, _ = G.group_clonotypes(tiny_pack([BASE] * 3, names=[(1, 1, 1), (2, 1, 1), (1, 1, 1)]), vj_refname=1)
@@ -272,7 +275,7 @@ SPLITS = {"gtest17": dict(vj_refname=1, heavy_pc=96.7),                    # dis
 
 
 def test_oracle_reproduces_the_groups_of_enclones_goldens():
-    pins = _pins()
+    pins = {k: v for k, v in _pins().items() if "opts" in v}
     assert set(pins) == {"gtest5", "gtest7", "gtest8", "gtest17", "gtest19"}
     for name, pin in pins.items():
         pk = _pin_pack(pin)
@@ -288,9 +291,81 @@ def test_oracle_reproduces_the_groups_of_enclones_goldens():
 @pytest.mark.gpu
 def test_gpu_reproduces_the_groups_of_enclones_goldens():
     for name, pin in _pins().items():
+        if "opts" not in pin:
+            continue
         pk = _pin_pack(pin)
         g, _ = G.group_clonotypes(pk, **pin["opts"])
         assert g.tolist() == [0] * pk.n_clono, (name, g.tolist())
         if name in SPLITS:
             g, _ = G.group_clonotypes(pk, **SPLITS[name])
             assert len(set(g.tolist())) == pk.n_clono, (name, g.tolist())
+
+
+# ---- Case 2 (asymmetric grouping): distances printed by enclone_gtest10/11/12_output ----
+DECOY = dict(names=["IGHV1-2", "IGHJ1", "IGKV1-5", "IGKJ1"], exacts=[dict(heavy_cdr3="CWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWWW", light_cdr3="CMMMMMMMMMMMMMMMMMMMMMMMMMW")], vj_seq1=None)
+
+
+def _asym_cases():
+    pins = _pins()
+    p10, p11, p12 = pins["gtest10"], pins["gtest11"], pins["gtest12"]
+    assert p12["clonotypes"][0]["exacts"] == p11["clonotypes"][0]["exacts"]          # gtest12 = gtest11's center under max=13
+    out = []
+    for pin, bound, want in ((p10, p10["asym"], [d["distance"] for d in p10["clonotypes"]]), (p11, p11["asym"], [d["distance"] for d in p11["clonotypes"]]),
+                             (p11, p12["asym"], [0.0])):
+        full = dict(clonotypes=pin["clonotypes"] + [DECOY, DECOY])
+        out.append((_pin_pack(full), bound, want))
+    return out
+
+
+def test_oracle_reproduces_the_distances_of_enclones_agroup_goldens():
+    for pk, bound, want in _asym_cases():
+        cen = np.zeros(pk.n_clono, np.uint8); cen[0] = 1
+        groups, ev = oracle_lib.group_asym(pk, cen, G.asym_opts(**bound))
+        assert len(groups) == 1
+        assert groups[0] == [(i, d) for i, d in enumerate(want)], groups     # center first, then the members at 13 / 14 in index order
+
+
+def test_oracle_asym_walk_semantics():
+    pk = G.synth_group_pack(80, seed=4)
+    cen = np.zeros(80, np.uint8); cen[::7] = 1
+    g_all, _ = oracle_lib.group_asym(pk, cen, G.asym_opts())
+    assert len(g_all) == int(cen.sum()) and all(len(g) >= 80 - 1 for g in g_all)           # no bound: everybody, the center listed once
+    g_top, _ = oracle_lib.group_asym(pk, cen, G.asym_opts(top=5))
+    for g in g_top:
+        assert 6 <= len(g) <= 7 and g[0][1] == 0.0                                        # positions 0..5 of the sorted row, the center skipped if among them
+        assert [d for _, d in g[1:]] == sorted(d for _, d in g[1:])
+    g_min, _ = oracle_lib.group_asym(pk, cen, G.asym_opts(max_dist=0.0, min_group=2))
+    assert all(len(g) >= 2 and all(d == 0.0 for _, d in g) for g in g_min)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_the_distances_of_enclones_agroup_goldens():
+    for pk, bound, want in _asym_cases():
+        cen = np.zeros(pk.n_clono, np.uint8); cen[0] = 1
+        groups, st = G.group_asymmetric(pk, cen, **bound)
+        assert groups == [[(i, d) for i, d in enumerate(want)]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bound", [dict(top=0), dict(top=3), dict(top=40), dict(top=5000), dict(max_dist=0.0), dict(max_dist=6.5), dict(max_dist=30.0, min_group=3),
+                                   dict(max_dist=2e9), dict(max_dist=-1.0), dict(), dict(top=2, min_group=4)])
+def test_gpu_asymmetric_grouping_equals_oracle(bound):
+    for n, seed, step in ((300, 11, 9), (1200, 12, 1)):
+        if step == 1 and not bound:
+            continue                                            # no bound with every clonotype a center: n^2 members, pointless
+        pk = G.synth_group_pack(n, seed=seed)
+        cen = np.zeros(n, np.uint8); cen[::step] = 1
+        want, ev = oracle_lib.group_asym(pk, cen, G.asym_opts(**bound))
+        got, st = G.group_asymmetric(pk, cen, **bound)
+        assert got == want
+        assert st["gpu_launches"] >= 1 and st["pairs_evaluated"] == int(cen.sum()) * n
+
+
+@pytest.mark.gpu
+def test_gpu_asymmetric_edge_cases():
+    pk = G.synth_group_pack(50, seed=3)
+    assert G.group_asymmetric(pk, np.zeros(50, np.uint8), top=3)[0] == []                 # no center: no group, no device work
+    pk0 = tiny_pack([])
+    assert G.group_asymmetric(pk0, np.zeros(0, np.uint8), max_dist=3.0)[0] == []
+    one = tiny_pack([BASE])
+    assert G.group_asymmetric(one, np.ones(1, np.uint8), top=2)[0] == oracle_lib.group_asym(one, np.ones(1, np.uint8), G.asym_opts(top=2))[0]
