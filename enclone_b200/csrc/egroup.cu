@@ -601,6 +601,7 @@ extern "C" int egroup_run_asym(const egroup_pack_t *pk, const uint8_t *in_center
                     uint4 *d_out = nullptr;
                     GCK(M.take(d_out, cap));
                     GCK(cudaMemsetAsync(d_n, 0, 8, s));
+                    GCK(cudaMemsetAsync(d_ctr, 0, sizeof(GCounters), s));      // a second attempt recounts
                     const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 127) / 128, (unsigned long long)sm * 16);
                     k_asym_max<<<blocks, 128, 0, s>>>(d, d_center, nc, n, dcut, d_out, cap, d_n, d_ctr);
                     st.gpu_launches++;
