@@ -358,7 +358,8 @@ def test_gpu_asymmetric_grouping_equals_oracle(bound):
         want, ev = oracle_lib.group_asym(pk, cen, G.asym_opts(**bound))
         got, st = G.group_asymmetric(pk, cen, **bound)
         assert got == want
-        assert st["gpu_launches"] >= 1 and st["pairs_evaluated"] == int(cen.sum()) * n
+        if bound.get("max_dist", 0.0) >= 0.0:                   # a negative bound needs no distances at all
+            assert st["gpu_launches"] >= 1 and st["pairs_evaluated"] == int(cen.sum()) * n
 
 
 @pytest.mark.gpu
