@@ -14,6 +14,31 @@ import numpy as np
 from enclone_b200 import group as G
 
 
+def asym_main(a):
+    pk = G.synth_group_pack(a.n, seed=1, n_families=a.families or max(2, a.n // 50))
+    cen = np.zeros(a.n, np.uint8); cen[::a.center_step] = 1
+    k, v = a.asym.split("=")
+    bound = dict(top=int(v)) if k == "top" else dict(max_dist=float(v))
+    best, wall = None, []
+    for _ in range(a.reps):
+        groups, st = G.group_asymmetric(pk, cen, **bound)
+        wall.append(round(st["ms_total"], 2))
+        if best is None or st["ms_device"] < best["ms_device"]:
+            best = st
+    out = dict(asym=bound, n_clono=a.n, n_center=int(cen.sum()), ms_total_per_rep=wall, stats=best, members=int(sum(len(g) for g in groups)),
+               pairs_per_s=round(best["pairs_candidate"] / (best["ms_device"] * 1e-3), 1))
+    if a.cpu_sample:
+        import oracle_lib
+        sub = G.synth_group_pack(a.cpu_sample, seed=1, n_families=max(2, a.cpu_sample // 50))
+        c2 = np.zeros(a.cpu_sample, np.uint8); c2[::a.center_step] = 1
+        t0 = time.time()
+        want, ev = oracle_lib.group_asym(sub, c2, G.asym_opts(**bound))
+        dt = time.time() - t0
+        got, _ = G.group_asymmetric(sub, c2, **bound)
+        out["cpu_oracle"] = dict(n_clono=a.cpu_sample, n_center=int(c2.sum()), s=round(dt, 3), pairs_per_s=round(int(c2.sum()) * a.cpu_sample / dt, 1), parity=bool(got == want))
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=20000)
@@ -21,7 +46,11 @@ def main():
     ap.add_argument("--opts", default="vj_refname=1,heavy_pc=96")
     ap.add_argument("--cpu-sample", type=int, default=150)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--asym", default="", help="asymmetric grouping instead: 'top=10' or 'max=6'; every --center-step-th clonotype is a center")
+    ap.add_argument("--center-step", type=int, default=10)
     a = ap.parse_args()
+    if a.asym:
+        return asym_main(a)
     kw = {}
     for t in a.opts.split(","):
         k, v = t.split("=")
