@@ -22,6 +22,11 @@ def main():
         print(f"rank {rank}/{world}: device {st['ms_device']:.3f} ms  sweep {st['ms_kernel_tier1']:.3f}  pack_t2 {st['ms_kernel_pack_t2']:.3f}  "
               f"scoring {st['ms_kernel_tier2']:.3f}  other {st['ms_kernel_other']:.3f}  compared {st['pairs_compared']}  "
               f"tier2 {st['pairs_tier2']}  accepted {st['pairs_accepted']}", flush=True)
+        if os.environ.get("STAGES") and rank in (0, world - 1):
+            j.set_stage_timing(True)
+            j.run_resident(); j.run_resident()
+            print("    stages: " + ", ".join(f"{n} {ms:.3f}" for n, ms in j.stage_times()), flush=True)
+            j.set_stage_timing(False)
     j.close()
 
 
