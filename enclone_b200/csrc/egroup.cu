@@ -197,18 +197,88 @@ __device__ uint32_t asym_dist(const GDev &d, uint32_t c, uint32_t j, GCounters *
     return best;
 }
 
-// max=D / no bound: every (center, clonotype) pair is a thread; the ones within the bound are appended to one list
-__global__ void __launch_bounds__(128) k_asym_max(GDev d, const uint32_t *__restrict__ center, uint32_t n_center, uint32_t n, uint32_t dcut,
+// The center's side of every comparison is the same for a whole row of the distance matrix: its chains' match vectors are
+// built once per CTA into shared memory (CDR3s of up to 64 amino acids, up to ASYM_MAXCH chains; anything else takes the
+// generic path), and a comparison is then the one-word recurrence over the other clonotype's string alone.
+#define ASYM_MAXCH 16
+struct CenterCache {
+    unsigned long long peq[ASYM_MAXCH][32];
+    uint32_t present[ASYM_MAXCH], gid[ASYM_MAXCH];
+    uint16_t len[ASYM_MAXCH];
+    uint8_t left[ASYM_MAXCH], ex_off[ASYM_MAXCH + 1];
+    uint32_t n_ex, n_ch;
+    int fast;
+};
+__device__ void load_center(const GDev &d, uint32_t c, CenterCache &cc) {        // block-wide; ends with a barrier
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t nch = 0, nex = 0;
+        bool ok = true;
+        for (uint32_t x = d.clono_exact_off[c]; x < d.clono_exact_off[c + 1] && ok; x++) {
+            const uint32_t u = d.clono_exact[x];
+            if (nex >= ASYM_MAXCH) { ok = false; break; }
+            cc.ex_off[nex++] = (uint8_t)nch;
+            for (uint32_t m = d.exact_chain_off[u]; m < d.exact_chain_off[u + 1]; m++) {
+                if (nch >= ASYM_MAXCH || d.cdr3_aa_len[m] > 64) { ok = false; break; }
+                cc.gid[nch] = m; cc.len[nch] = (uint16_t)d.cdr3_aa_len[m]; cc.left[nch] = d.left[m] != 0; nch++;
+            }
+        }
+        cc.ex_off[nex < ASYM_MAXCH ? nex : ASYM_MAXCH] = (uint8_t)nch;
+        cc.n_ex = nex; cc.n_ch = nch; cc.fast = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (cc.fast && threadIdx.x < cc.n_ch) {
+        const uint32_t t = threadIdx.x, m = cc.gid[t];
+        const uint8_t *p = d.aa_arena + d.cdr3_aa_off[m];
+        uint32_t present = 0;
+        for (uint32_t i = 0; i < cc.len[t]; i++) {
+            const uint32_t sy = sym_aa(p[i]);
+            if (!((present >> sy) & 1u)) { cc.peq[t][sy] = 0ull; present |= 1u << sy; }
+            cc.peq[t][sy] |= 1ull << i;
+        }
+        cc.present[t] = present;
+    }
+    __syncthreads();
+}
+__device__ uint32_t asym_dist_cached(const GDev &d, const CenterCache &cc, uint32_t c, uint32_t j, GCounters *ctr, unsigned long long &compares) {
+    if (!cc.fast) return asym_dist(d, c, j, ctr, compares);
+    uint32_t best = ASYM_INF;
+    for (uint32_t e = 0; e < cc.n_ex; e++)
+        for (uint32_t x2 = d.clono_exact_off[j]; x2 < d.clono_exact_off[j + 1]; x2++) {
+            const uint32_t u2 = d.clono_exact[x2];
+            uint32_t heavy = ASYM_INF, light = ASYM_INF;
+            for (uint32_t ci = cc.ex_off[e]; ci < cc.ex_off[e + 1]; ci++)
+                for (uint32_t m2 = d.exact_chain_off[u2]; m2 < d.exact_chain_off[u2 + 1]; m2++) {
+                    if ((cc.left[ci] != 0) != (d.left[m2] != 0)) continue;
+                    const uint32_t l2 = d.cdr3_aa_len[m2];
+                    if (l2 > 512) { atomicOr(&ctr->err, ERR_TOO_LONG); continue; }
+                    const uint32_t x = myers64_aa(cc.peq[ci], cc.present[ci], cc.len[ci], d.aa_arena + d.cdr3_aa_off[m2], l2);
+                    compares++;
+                    if (cc.left[ci]) heavy = min(heavy, x); else light = min(light, x);
+                }
+            best = min(best, heavy + light);
+        }
+    return best;
+}
+
+// max=D / no bound: a CTA takes (center, slice of the clonotypes); the pairs within the bound are appended to one list
+__global__ void __launch_bounds__(256) k_asym_max(GDev d, const uint32_t *__restrict__ center, uint32_t n_center, uint32_t n, uint32_t slices, uint32_t dcut,
                                                   uint4 *out, unsigned long long cap, unsigned long long *n_out, GCounters *ctr) {
+    __shared__ CenterCache cc;
     unsigned long long compares = 0, pairs = 0;
-    const unsigned long long total = (unsigned long long)n_center * n;
-    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t i = (uint32_t)(t / n), j = (uint32_t)(t % n);
-        const uint32_t dist = asym_dist(d, center[i], j, ctr, compares);
-        pairs++;
-        if (dist <= dcut) {
-            const unsigned long long w = atomicAdd(n_out, 1ull);
-            if (w < cap) out[w] = make_uint4(i, j, dist, 0u);
+    const uint32_t per = (n + slices - 1) / slices;
+    uint32_t loaded = 0xFFFFFFFFu;
+    for (unsigned long long vb = blockIdx.x; vb < (unsigned long long)n_center * slices; vb += gridDim.x) {
+        const uint32_t i = (uint32_t)(vb / slices), sl = (uint32_t)(vb % slices);
+        if (i != loaded) { load_center(d, center[i], cc); loaded = i; }
+        const uint32_t j1 = min(n, (sl + 1) * per);
+        for (uint32_t j = sl * per + threadIdx.x; j < j1; j += blockDim.x) {
+            const uint32_t dist = asym_dist_cached(d, cc, center[i], j, ctr, compares);
+            pairs++;
+            if (dist <= dcut) {
+                const unsigned long long w = atomicAdd(n_out, 1ull);
+                if (w < cap) out[w] = make_uint4(i, j, dist, 0u);
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) { compares += __shfl_xor_sync(0xFFFFFFFFu, compares, o); pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o); }
@@ -224,14 +294,15 @@ __global__ void __launch_bounds__(256) k_asym_top(GDev d, const uint32_t *__rest
     __shared__ uint32_t hist[ASYM_BINS];
     __shared__ uint32_t s_dstar, s_r, s_base_take, s_base_eq;
     __shared__ uint32_t scan_take[256], scan_eq[256];
+    __shared__ CenterCache cc;
     uint32_t *row = row_all + (size_t)blockIdx.x * n;
     unsigned long long compares = 0, pairs = 0;
     for (uint32_t i = blockIdx.x; i < n_center; i += gridDim.x) {
         for (uint32_t b = threadIdx.x; b < ASYM_BINS; b += blockDim.x) hist[b] = 0;
-        __syncthreads();
         const uint32_t c = center[i];
+        load_center(d, c, cc);
         for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-            const uint32_t dist = asym_dist(d, c, j, ctr, compares);
+            const uint32_t dist = asym_dist_cached(d, cc, c, j, ctr, compares);
             pairs++;
             row[j] = dist;
             atomicAdd(&hist[min(dist, (uint32_t)ASYM_BINS - 1)], 1u);
@@ -602,8 +673,10 @@ extern "C" int egroup_run_asym(const egroup_pack_t *pk, const uint8_t *in_center
                     GCK(M.take(d_out, cap));
                     GCK(cudaMemsetAsync(d_n, 0, 8, s));
                     GCK(cudaMemsetAsync(d_ctr, 0, sizeof(GCounters), s));      // a second attempt recounts
-                    const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 127) / 128, (unsigned long long)sm * 16);
-                    k_asym_max<<<blocks, 128, 0, s>>>(d, d_center, nc, n, dcut, d_out, cap, d_n, d_ctr);
+                    // enough (center, slice) work items to fill the GPU a few times over, slices of at least 256 clonotypes
+                    const uint32_t slices = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)sm * 8 + nc - 1) / nc, ((uint64_t)n + 255) / 256));
+                    const unsigned blocks = (unsigned)std::min<unsigned long long>((unsigned long long)nc * slices, (unsigned long long)sm * 8);
+                    k_asym_max<<<blocks, 256, 0, s>>>(d, d_center, nc, n, slices, dcut, d_out, cap, d_n, d_ctr);
                     st.gpu_launches++;
                     GCK(cudaGetLastError());
                     GCK(cudaMemcpyAsync(&got, d_n, 8, cudaMemcpyDeviceToHost, s));

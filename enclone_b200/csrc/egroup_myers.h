@@ -16,12 +16,18 @@ EG_HD inline uint32_t sym_nt(uint8_t b) {
 EG_HD inline uint32_t sym_aa(uint8_t b) { return b & 31u; }
 
 // Match vectors of a pattern: peq[s] bit i = (pat[i] has symbol s); one spare zero word for the banded variant's window.
+// Only the rows of symbols the pattern contains are initialised (a short CDR3 touches ~10 of the 32 amino-acid rows, and
+// clearing the table would cost more than the distance itself); the returned mask says which rows are valid.
 template <int NSYM, bool AA>
-EG_HD inline void build_peq(unsigned long long (*peq)[MAXW + 1], const uint8_t *pat, uint32_t m) {
+EG_HD inline uint32_t build_peq(unsigned long long (*peq)[MAXW + 1], const uint8_t *pat, uint32_t m) {
     const uint32_t W = (m + 63) / 64;
-    for (int s = 0; s < NSYM; s++)
-        for (uint32_t b = 0; b <= W; b++) peq[s][b] = 0ull;
-    for (uint32_t i = 0; i < m; i++) { const uint32_t s = AA ? sym_aa(pat[i]) : sym_nt(pat[i]); peq[s][i >> 6] |= 1ull << (i & 63); }
+    uint32_t present = 0;
+    for (uint32_t i = 0; i < m; i++) {
+        const uint32_t s = AA ? sym_aa(pat[i]) : sym_nt(pat[i]);
+        if (!((present >> s) & 1u)) { for (uint32_t b = 0; b <= W; b++) peq[s][b] = 0ull; present |= 1u << s; }
+        peq[s][i >> 6] |= 1ull << (i & 63);
+    }
+    return present;
 }
 
 // Levenshtein distance (unit costs, global) of pat[0..m) and txt[0..n), 0 < m <= 64 * MAXW: Myers' bit-vector algorithm in
@@ -30,16 +36,17 @@ EG_HD inline void build_peq(unsigned long long (*peq)[MAXW + 1], const uint8_t *
 // sees +1 (D[0][j] = j).  `score` follows the bottom row of the last block; the rows below the pattern's last one are
 // then walked back with their vertical deltas.
 template <int NSYM, bool AA>
-EG_HD inline uint32_t myers_full(const unsigned long long (*peq)[MAXW + 1], uint32_t m, const uint8_t *txt, uint32_t n) {
+EG_HD inline uint32_t myers_full(const unsigned long long (*peq)[MAXW + 1], uint32_t present, uint32_t m, const uint8_t *txt, uint32_t n) {
     const uint32_t W = (m + 63) / 64;
     unsigned long long Pv[MAXW], Mv[MAXW];
     for (uint32_t b = 0; b < W; b++) { Pv[b] = ~0ull; Mv[b] = 0ull; }
     int score = (int)(64 * W);
     for (uint32_t j = 0; j < n; j++) {
         const uint32_t s = AA ? sym_aa(txt[j]) : sym_nt(txt[j]);
+        const bool has = (present >> s) & 1u;
         int hin = 1;
         for (uint32_t b = 0; b < W; b++) {
-            unsigned long long Eq = peq[s][b];
+            unsigned long long Eq = has ? peq[s][b] : 0ull;
             const unsigned long long pv = Pv[b], mv = Mv[b];
             const unsigned long long hneg = hin < 0 ? 1ull : 0ull;
             const unsigned long long Xv = Eq | mv;
@@ -71,7 +78,7 @@ EG_HD inline uint32_t myers_full(const unsigned long long (*peq)[MAXW + 1], uint
 // tiling): at column j bit b is row j + k - 63 + b.  The score is followed down the band's lowest diagonal (row j + k) until it reaches the last row,
 // then along the last row; a score above 2k + n - m cannot come back under k.  Exact whenever the answer is yes.
 template <int NSYM, bool AA>
-EG_HD inline bool myers_band_within(const unsigned long long (*peq)[MAXW + 1], uint32_t m, const uint8_t *txt, uint32_t n, uint32_t k) {
+EG_HD inline bool myers_band_within(const unsigned long long (*peq)[MAXW + 1], uint32_t present, uint32_t m, const uint8_t *txt, uint32_t n, uint32_t k) {
     // column 0 in the coordinates of column 1 (bit b = row k - 62 + b): rows 1 .. k+1 step +1 (bits 63-k .. 63); the rows
     // <= 0 are virtual, all equal to j in column j (vertical delta 0, no matches), which leaves D[0][j] = j
     unsigned long long VP = ~0ull << (63 - k), VN = 0ull;
@@ -82,7 +89,8 @@ EG_HD inline bool myers_band_within(const unsigned long long (*peq)[MAXW + 1], u
         const uint32_t s = AA ? sym_aa(txt[i]) : sym_nt(txt[i]);
         const int start = (int)i + (int)k - 63;                    // pattern index of bit 0
         unsigned long long X;
-        if (start < 0) X = peq[s][0] << (-start);
+        if (!((present >> s) & 1u)) X = 0ull;
+        else if (start < 0) X = peq[s][0] << (-start);
         else {
             const uint32_t w = (uint32_t)start >> 6, o = (uint32_t)start & 63;
             X = peq[s][w] >> o;
@@ -110,17 +118,39 @@ EG_HD inline bool lev_within(const uint8_t *a, uint32_t n, const uint8_t *b, uin
     if (m - n > k) return false;
     if (n == 0) return true;                                       // distance m <= k
     unsigned long long peq[NSYM][MAXW + 1];
-    build_peq<NSYM, AA>(peq, a, n);
-    if (k <= 31) return myers_band_within<NSYM, AA>(peq, n, b, m, k);
-    return myers_full<NSYM, AA>(peq, n, b, m) <= k;
+    const uint32_t present = build_peq<NSYM, AA>(peq, a, n);
+    if (k <= 31) return myers_band_within<NSYM, AA>(peq, present, n, b, m, k);
+    return myers_full<NSYM, AA>(peq, present, n, b, m) <= k;
 }
 template <int NSYM, bool AA>
 EG_HD inline uint32_t myers(const uint8_t *pat, uint32_t m, const uint8_t *txt, uint32_t n) {
     if (m == 0) return n;
     if (n == 0) return m;
     unsigned long long peq[NSYM][MAXW + 1];
-    build_peq<NSYM, AA>(peq, pat, m);
-    return myers_full<NSYM, AA>(peq, m, txt, n);
+    const uint32_t present = build_peq<NSYM, AA>(peq, pat, m);
+    return myers_full<NSYM, AA>(peq, present, m, txt, n);
+}
+
+// Amino-acid strings against a pattern of at most 64 symbols whose match vectors are already at hand (peq32[s], one word
+// per symbol, valid where `present` says so): the classic one-word form, the score read at the pattern's last row.
+EG_HD inline uint32_t myers64_aa(const unsigned long long *peq32, uint32_t present, uint32_t m, const uint8_t *txt, uint32_t n) {
+    if (m == 0) return n;
+    unsigned long long Pv = ~0ull, Mv = 0ull;
+    const unsigned long long top = 1ull << (m - 1);
+    uint32_t score = m;
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t s = sym_aa(txt[j]);
+        const unsigned long long Eq = ((present >> s) & 1u) ? peq32[s] : 0ull;
+        const unsigned long long Xv = Eq | Mv;
+        const unsigned long long Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        unsigned long long Ph = Mv | ~(Xh | Pv), Mh = Pv & Xh;
+        if (Ph & top) score++;
+        if (Mh & top) score--;
+        Ph = (Ph << 1) | 1ull; Mh <<= 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+    }
+    return score;
 }
 
 // largest d with (n1 - d) / n1 >= min_r || (n2 - d) / n2 >= min_r, the acceptance test of grouper.rs:427-431 in its own

@@ -26,6 +26,7 @@ int main(int argc, char **argv) {
     for (int it = 0; it < iters; it++) {
         uint32_t n = rand() % 513, m = rand() % 700;
         if (it % 7 == 0) n = 64 * (rand() % 9), m = n + rand() % 3;             // block boundaries
+        if (it % 3 == 1) n = rand() % 65, m = rand() % 90;                       // CDR3-sized
         std::vector<uint8_t> a(n + 1), b(m + 1);
         const int mode = rand() % 3;
         for (auto &x : a) x = al[rand() % (mode ? 4 : 6)];
@@ -40,6 +41,12 @@ int main(int argc, char **argv) {
         for (uint32_t i = 0; i < m; i++) b[i] = (rand() % 4 && i < n) ? a[i] : aa[rand() % 22];
         const uint32_t daa = dp(a.data(), n, b.data(), m);
         if (lev_aa(a.data(), n, b.data(), m) != daa) bad++;
+        if (n <= 64) {                                                           // the one-word form with a prebuilt table (asymmetric grouping)
+            unsigned long long pq[32], tab[32][MAXW + 1];
+            const uint32_t present = build_peq<32, true>(tab, a.data(), n);
+            for (int q = 0; q < 32; q++) pq[q] = tab[q][0];
+            if (myers64_aa(pq, present, n, b.data(), m) != daa) { bad++; if (bad < 6) printf("myers64 n=%u m=%u\n", n, m); }
+        }
         for (int q = 0; q < 4; q++) {                                            // d <= k, around the true distance and at random
             const uint32_t k = q < 2 ? (daa + (uint32_t)(rand() % 5) >= 2 ? daa + (uint32_t)(rand() % 5) - 2 : 0) : (uint32_t)(rand() % 48);
             if ((n <= 512 || m <= 512) && lev_within<32, true>(a.data(), n, b.data(), m, k) != (daa <= k)) { bad++; if (bad < 6) printf("aa within n=%u m=%u d=%u k=%u\n", n, m, daa, k); }
