@@ -130,6 +130,7 @@ struct ejoin_handle {
     RecOut rec_out;
     int is_bcr = 1;
     int tables_is_bcr = -1;
+    bool tables_built = false;       // prepare_tables has run on this handle: later joins do not wait for the key pass (device_pipeline)
     int sm_count = 148;
     int bor_grid = 0;          // cooperative grid of k_boruvka
     // resident input + work buffers
@@ -812,6 +813,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     if (const char *e = getenv("EJOIN_SEG_MIN")) seg_min = (uint32_t)std::max(1, atoi(e));
     if (h->xrow_cap == 0 || h->xrow_seg != seg_min) { h->xrow_cap = 1024 + (unsigned long long)(n / T1_TILE) * (16 / std::min(16u, seg_min)); h->xrow_seg = seg_min; }
     if (n == 0) return 0;
+    bool tables_retry = false;
     for (int attempt = 0; attempt < 6; attempt++) {
         const unsigned long long ccap = h->cand_cap, rcap = h->rest_cap;
         const unsigned long long xcap = h->xrow_cap;
@@ -903,9 +905,19 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_entry_keys<<<std::min(nb256, (unsigned)h->sm_count * 4u), 256, 0, st>>>(h->din, bucket_start, keys, vals, (uint32_t *)h->d_presL.p, (uint32_t *)h->d_presC.p, ctr);
         h->launches += 2;
         CK(cudaGetLastError());
-        int rc = prepare_tables(h, is_bcr);         // one sync; cached after the first run
-        if (rc) return rc;
-        const DevCounters first = h->counters;
+        // Tables (p1 per total length, multipliers per CDR3 length pair) are cached on the handle.  Once a handle has built
+        // tables, the key pass is not waited for any more: the pipeline runs on, a pair that finds its table missing raises
+        // ERR_TABLES_MISSING (decide_score), and the check after the forest builds what is missing and reruns the join.
+        const bool optimistic = h->tables_built && h->tables_is_bcr == is_bcr && !tables_retry && getenv("EJOIN_SYNC_TABLES") == nullptr;
+        DevCounters first;
+        memset(&first, 0, sizeof(first));
+        if (!optimistic) {
+            int rc = prepare_tables(h, is_bcr);     // one sync
+            if (rc) return rc;
+            first = h->counters;
+            h->tables_built = true;
+            tables_retry = false;
+        }
         mark(h, "keys (+tables first run)");
         tb = cub_bytes;
         cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys, keys_out, vals, perm, (int)n, 0, ENTRY_KEY_BITS, st);
@@ -1030,10 +1042,29 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             h->launches += 2;
         }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
         mark(h, "boruvka");
+        // The collect kernels run before the host has looked at the counters (they are bounded by the capacities, so an
+        // overflowed list cannot hurt them): one wait instead of two.
+        if (device_final) {
+            CK(cudaMemsetAsync(comp_size, 0, 4 * (size_t)n, st));
+            k_comp_size<<<nb256, 256, 0, st>>>(parent, ctr, comp_size);
+            k_final_collect<<<h->sm_count * 8, 256, 0, st>>>(h->din, f0_key, f0_val, n, acc, ctr, cap, k_to_s, 0, parent, comp_size, pr.easy, pk_in, pv_in);
+            h->launches += 2;
+        } else {
+            k_collect<<<h->sm_count * 8, 256, 0, st>>>(f0_key, f0_val, n, acc, ctr, cap, pk_in, pv_in);
+            h->launches += 1;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h->counters, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        mark(h, "comp size + collect");
         CK(cudaStreamSynchronize(st));
-        h->counters.pairs_candidate = first.pairs_candidate; h->counters.n_buckets = first.n_buckets;
+        if (optimistic) {
+            // what prepare_tables checks at its own sync
+            if (h->counters.err & ERR_CDR3_TOO_LONG) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 exceeds 255 nt (or 256 nt for both chains)");
+            if (h->counters.err & ERR_LEN_TOO_LARGE) return fail(h, EJOIN_E_UNSUPPORTED, "V..J lengths of one entry sum to 8192 or more");
+            if (h->counters.err & ERR_BAD_EXACT) return fail(h, EJOIN_E_ARG, "exact_id outside [0, n_exact)");
+            if (h->counters.err & ERR_TABLES_MISSING) { tables_retry = true; continue; }       // the next attempt takes the waiting path and builds them
+        } else { h->counters.pairs_candidate = first.pairs_candidate; h->counters.n_buckets = first.n_buckets; }
         if (h->counters.err & ERR_CDR3_BAD_CHAR) return fail(h, EJOIN_E_UNSUPPORTED, "a CDR3 contains a character outside ACGT");
         if (h->counters.err & ERR_BAD_REFSEQ) return fail(h, EJOIN_E_ARG, "vs_seq/js_seq index outside the germline table");
         if (h->counters.err & ERR_ARENA_RANGE) return fail(h, EJOIN_E_ARG, "an arena offset lies outside the slice of its shard (arenas must be laid out in entry order) or outside the arena");
@@ -1051,19 +1082,6 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
             if (k.n_xrows > xcap) { h->xrow_cap = k.n_xrows + 64; retry = true; }
             if (retry) continue;
         }
-        if (device_final) {
-            CK(cudaMemsetAsync(comp_size, 0, 4 * (size_t)n, st));
-            k_comp_size<<<nb256, 256, 0, st>>>(parent, (uint32_t)h->counters.n_valid, comp_size);
-            k_final_collect<<<h->sm_count * 8, 256, 0, st>>>(h->din, f0_key, f0_val, n, acc, ctr, cap, k_to_s, 0, parent, comp_size, pr.easy, pk_in, pv_in);
-            h->launches += 2;
-        } else {
-            k_collect<<<h->sm_count * 8, 256, 0, st>>>(f0_key, f0_val, n, acc, ctr, cap, pk_in, pv_in);
-            h->launches += 1;
-        }
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h->counters.n_kept, &ctr->n_kept, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        mark(h, "comp size + collect");
-        CK(cudaStreamSynchronize(st));
         const unsigned long long nk = h->counters.n_kept;
         if (nk) {
             // keys are (k1 << 32 | k2) with k < n: only the bits that can differ are sorted
@@ -1648,7 +1666,7 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
                 CK(cudaLaunchCooperativeKernel((void *)k_boruvka, dim3(h->bor_grid), dim3(256), args, 0, st));
             }
             CK(cudaMemsetAsync(h->w_comp_size, 0, 4 * (size_t)n, st));
-            k_comp_size<<<nb256, 256, 0, st>>>(h->w_parent, (uint32_t)h->counters.n_valid, h->w_comp_size);
+            k_comp_size<<<nb256, 256, 0, st>>>(h->w_parent, (const DevCounters *)h->d_counters.p, h->w_comp_size);
             k_final_collect<<<h->sm_count * 8, 256, 0, st>>>(h->din, h->w_f0_key, h->w_f0_val, n, acc, ctr, total, h->k_to_s, 0, h->w_parent, h->w_comp_size,
                                                              h->params.easy, sk_in, sv_in);
             h->launches += 7;

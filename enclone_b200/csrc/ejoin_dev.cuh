@@ -30,6 +30,7 @@
 #define ERR_K_TOO_LARGE 8u
 #define ERR_LEN_TOO_LARGE 16u
 #define ERR_ARENA_RANGE 128u      // an entry's bytes / words lie outside the uploaded slice of their arena
+#define ERR_TABLES_MISSING 256u    // a scored pair needed a p1 / multiplier table the handle has not built yet (optimistic run)
 #define ERR_BAD_EXACT 64u         // exact_id[k] >= n_exact
 #define ERR_GROUP_TOO_LARGE 32u   // a comparison group of more than 65535 tiles (8.3 M entries with equal lengths)
 

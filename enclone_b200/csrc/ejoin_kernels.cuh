@@ -765,6 +765,9 @@ __device__ __forceinline__ int decide_score(const DevParams &pr, const DevTables
                                             const PairCounts &pc, DevCounters *ctr, const double *p1tab_L, const MultInfo mi2, int *kout,
                                             int *dout, int *mo_out, double *p1o, double *multo, double *scoreo) {
     const int cd = pc.cd0 + pc.cd1;
+    // The host no longer waits for the key pass to learn which tables an input needs (one sync per join): a pair whose
+    // table is not there yet raises a flag, the pipeline's results are dropped, the tables are built and the join reruns.
+    if (p1tab_L == nullptr || mi2.off == 0xFFFFFFFFu) { atomicOr(&ctr->err, ERR_TABLES_MISSING); return 0; }
     if (pc.nrefs == 2) {            // MAX_DEGRADATION, both readings (include/enclone_join.h: degradation_mode)
         if (pr.degradation_mode == 1) { int df = pc.shares[0] - pc.shares[1]; if (df < 0) df = -df; if (df > pr.max_degradation) return 0; }
         else if (pc.refdiff > pr.max_degradation) return 0;
@@ -1999,9 +2002,9 @@ __global__ void __launch_bounds__(256) k_boruvka(ejoin_raw_edge_t *acc, DevCount
     }
     if (first == 0) ctr->bor_active = 0;
 }
-__global__ void k_comp_size(uint32_t *parent, uint32_t n_valid, uint32_t *size) {
+__global__ void k_comp_size(uint32_t *parent, const DevCounters *ctr, uint32_t *size) {       // n_valid read on the device: no host round trip before this launch
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n_valid) atomicAdd(&size[uf_find(parent, s)], 1u);
+    if (s < (uint32_t)ctr->n_valid) atomicAdd(&size[uf_find(parent, s)], 1u);
 }
 // Final edge list: tree edges + selected cross edges, minus the two-cell rule (help1.rs:349-353):
 // an orbit of exactly two entries whose exact subclonotypes total two cells keeps its join only if

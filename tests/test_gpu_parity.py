@@ -157,6 +157,29 @@ def test_handle_reuse_and_resident_runs():
     j.close()
 
 
+def test_tables_are_built_on_demand_without_waiting_for_the_key_pass(monkeypatch):
+    """A handle that has tables does not wait for the key pass any more: an input with lengths it has no tables for
+    runs, finds them missing (ERR_TABLES_MISSING), builds them and reruns — same result as the waiting path."""
+    small, _ = synth.generate(n_cells=1500, n_donors=1, seed=31)
+    big, _ = synth.generate(n_cells=30000, n_donors=3, seed=32)            # many more (len0 + len1) and CDR3 length pairs
+    j = Joiner(default_params())
+    j.run(small.struct)                                                    # first run on the handle: the waiting path
+    r_big = j.run(big.struct)                                              # optimistic run, tables missing, rebuilt, rerun
+    oe, oc, _ = O.join_exacts(big.struct, threads=4)
+    assert_same_join(r_big, oe, oc, what="tables-on-demand")
+    assert r_big.stats["pairs_candidate"] > 0 and r_big.stats["n_buckets"] > 0      # the key-pass counters survive the merged sync
+    r_again = j.run(big.struct)                                            # now fully optimistic
+    assert np.array_equal(r_big.edges, r_again.edges) and np.array_equal(r_big.class_of, r_again.class_of)
+    assert r_again.stats["pairs_candidate"] == r_big.stats["pairs_candidate"] and r_again.stats["n_buckets"] == r_big.stats["n_buckets"]
+    j.close()
+    monkeypatch.setenv("EJOIN_SYNC_TABLES", "1")
+    j2 = Joiner(default_params())
+    j2.run(small.struct)
+    r_sync = j2.run(big.struct)
+    assert np.array_equal(r_big.edges, r_sync.edges) and r_sync.stats["pairs_candidate"] == r_big.stats["pairs_candidate"]
+    j2.close()
+
+
 def test_sharded_run_equals_single():
     pack, _ = synth.generate(n_cells=12000, n_donors=2, seed=31)
     single = join_exacts(pack)
