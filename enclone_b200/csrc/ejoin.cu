@@ -849,7 +849,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take((size_t)n + 1024); sz.take(8 * ((size_t)n + 1024));                                           // work items: cost class, sorted list (items <= n)
         sz.take(4 * (size_t)xcap * PHASE_A_K * T1_TILE); sz.take(4 * (size_t)xcap * T1_TILE);                   // extra slot rows (segments q >= 1)
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
-        sz.take(8 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                   // Boruvka: best, ends, component sizes
+        sz.take(16 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                  // Boruvka: two bid tables, ends, component sizes
         sz.take(cub_bytes + 256);
         sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1)); sz.take(4 * (size_t)n + 64);   // payload staging (taken later)
         sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)h->din.n_exact + 64);   // union-find labels (in, out), first entry per exact
@@ -882,7 +882,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         ejoin_raw_edge_t *acc = A.take<ejoin_raw_edge_t>(cap);
         unsigned long long *pk_in = A.take<unsigned long long>(cap), *pv_in = A.take<unsigned long long>(cap);
         unsigned long long *pk_out = A.take<unsigned long long>(cap), *pv_out = A.take<unsigned long long>(cap);
-        unsigned long long *best = A.take<unsigned long long>(n);
+        unsigned long long *best = A.take<unsigned long long>(2 * (size_t)n);   // two bid tables (k_boruvka alternates)
         uint2 *ends = A.take<uint2>(cap);
         uint32_t *comp_size = A.take<uint32_t>(n);
         void *cub_tmp = A.take<char>(cub_bytes + 256);
@@ -920,7 +920,9 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         }
         mark(h, "keys (+tables first run)");
         tb = cub_bytes;
-        cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys, keys_out, vals, perm, (int)n, 0, ENTRY_KEY_BITS, st);
+        int entry_bits = 17;                        // 16 bits of CDR3 lengths + the bits of a bucket's first index (invalid entries: all ones, behind every valid key)
+        while (entry_bits < 48 && (1ull << (entry_bits - 16)) < (unsigned long long)n) entry_bits++;
+        cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys, keys_out, vals, perm, (int)n, 0, entry_bits, st);
         mark(h, "sort entries");
         tb = cub_bytes;
         cub::DeviceRunLengthEncode::Encode(cub_tmp, tb, keys_out, uniq, counts, num_runs, (int)n, st);
@@ -1027,7 +1029,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         const bool device_final = stride == 1;      // stride mode: the forest needs every rank's edges -> host replay after the gather
         h->device_final = device_final;
         if (device_final) {
-            k_fill_u64<<<nb256, 256, 0, st>>>(best, ~0ull, n);
+            k_fill_u64<<<2 * nb256, 256, 0, st>>>(best, ~0ull, 2 * (size_t)n);
             {   // all Boruvka rounds in one cooperative launch (grid = what is resident at once)
                 if (h->bor_grid == 0) {
                     int occ = 1;
@@ -1035,8 +1037,8 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
                     h->bor_grid = occ >= 1 ? h->sm_count : 1;          // one CTA per SM: the grid-wide barriers are the cost, not the edge loop
                 }
                 ejoin_raw_edge_t *a_acc = acc; DevCounters *a_ctr = ctr; unsigned long long a_cap = cap; const uint32_t *a_kts = k_to_s;
-                uint32_t *a_par = parent; unsigned long long *a_best = best; uint2 *a_ends = ends;
-                void *args[] = { &a_acc, &a_ctr, &a_cap, &a_kts, &a_par, &a_best, &a_ends };
+                uint32_t *a_par = parent; unsigned long long *a_best = best; uint2 *a_ends = ends; uint32_t a_n = n;
+                void *args[] = { &a_acc, &a_ctr, &a_cap, &a_kts, &a_par, &a_best, &a_ends, &a_n };
                 CK(cudaLaunchCooperativeKernel((void *)k_boruvka, dim3(h->bor_grid), dim3(256), args, 0, st));
             }
             h->launches += 2;
@@ -1657,12 +1659,12 @@ extern "C" int ejoin_run_sharded(ejoin_handle_t *h, const ejoin_pack_t *pk, ejoi
             if (total) k_kv_to_acc<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gk, gv, total, acc);
             k_iota_parent<<<nb256, 256, 0, st>>>(h->w_parent, h->w_f0_key, n);
             k_set_accept<<<1, 1, 0, st>>>(ctr, total);
-            k_fill_u64<<<nb256, 256, 0, st>>>(h->w_best, ~0ull, n);
+            k_fill_u64<<<2 * nb256, 256, 0, st>>>(h->w_best, ~0ull, 2 * (size_t)n);
             {
                 if (h->bor_grid == 0) { int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_boruvka, 256, 0); h->bor_grid = occ >= 1 ? h->sm_count : 1; }
                 ejoin_raw_edge_t *a_acc = acc; DevCounters *a_ctr = ctr; unsigned long long a_cap = total; const uint32_t *a_kts = h->k_to_s;
-                uint32_t *a_par = h->w_parent; unsigned long long *a_best = h->w_best; uint2 *a_ends = gends;
-                void *args[] = { &a_acc, &a_ctr, &a_cap, &a_kts, &a_par, &a_best, &a_ends };
+                uint32_t *a_par = h->w_parent; unsigned long long *a_best = h->w_best; uint2 *a_ends = gends; uint32_t a_n = n;
+                void *args[] = { &a_acc, &a_ctr, &a_cap, &a_kts, &a_par, &a_best, &a_ends, &a_n };
                 CK(cudaLaunchCooperativeKernel((void *)k_boruvka, dim3(h->bor_grid), dim3(256), args, 0, st));
             }
             CK(cudaMemsetAsync(h->w_comp_size, 0, 4 * (size_t)n, st));

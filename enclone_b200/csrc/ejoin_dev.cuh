@@ -21,7 +21,6 @@
 #define T1_TILE 128          // entries per tier-1 tile side; CTA = 128 threads
 #define T1_WMAX 8            // 32-base words per plane of the concatenated CDR3s (<= 256 nt)
 #define C3_MAX_TOTAL (32 * T1_WMAX)
-#define ENTRY_KEY_BITS 42    // sort key of an entry: len0:13 | len1:13 | cdr3len0:8 | cdr3len1:8 (invalid entries: ~0)
 #define FLAG_GENERIC0 1u     // chain 0 needs the bytewise path (has_del, non-ACGT, overlapping windows)
 #define FLAG_GENERIC1 2u
 #define ERR_CDR3_TOO_LONG 1u

@@ -43,7 +43,10 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
             else if (l0 + l1 >= 8192) { atomicOr(&ctr->err, ERR_LEN_TOO_LARGE); valid = false; }
         }
         if (valid) {
-            key = ((unsigned long long)l0 << 29) | ((unsigned long long)l1 << 16) | ((unsigned long long)c0 << 8) | c1;   // 13|13|8|8 bits: ENTRY_KEY_BITS
+            // bucket | cdr3len0:8 | cdr3len1:8, the bucket named by the index of its first entry (info is in bucket order and the
+            // sort is stable, so this orders exactly as len0 | len1 | ... would, in 16 + log2(n) key bits instead of 42: one
+            // radix pass fewer; two separate runs of equal lens stay two buckets, as in the reference's bucket scan)
+            key = ((unsigned long long)bucket_start[k] << 16) | ((unsigned long long)c0 << 8) | c1;
             uint32_t L = l0 + l1, cc = (c0 << 8) | c1;
             // test before set: after the first hit per value these are plain cached loads, not serialized atomics
             if (!(presL[L >> 5] & (1u << (L & 31)))) atomicOr(&presL[L >> 5], 1u << (L & 31));
@@ -1958,16 +1961,21 @@ __global__ void k_fill_u64(unsigned long long *p, unsigned long long v, size_t n
     if (i < n) p[i] = v;
 }
 
-// All rounds in ONE cooperative launch, grid-wide barriers between the three steps of a round: (1) every live edge finds its two
-// components and bids for them (64-bit atomicMin of its (k1,k2) key); (2) the winning edges are selected and their components
-// merged; (3) the bids are cleared where they were placed.  Stops when a round finds no edge between two components.
+// All rounds in ONE cooperative launch, two grid-wide barriers per round: (1) every live edge finds its two components and bids
+// for them (64-bit atomicMin of its (k1,k2) key); (2) the winning edges are selected and their components merged.  The bids
+// alternate between two tables (`best2` holds both, nent entries each): while step (2) of round r reads table r & 1, every live
+// edge clears its two components' entries in the other table, which is the one round r + 1 bids into.  A component that is bid
+// for in round r + 1 is a round-r root that either stayed alone (its own live edge cleared it) or is an end of a selected edge
+// (which cleared it), so its entry is clean; entries of absorbed components are never read again.  This took the third barrier
+// (a clearing pass) out of every round.  Stops when a round finds no edge between two components.
 __global__ void __launch_bounds__(256) k_boruvka(ejoin_raw_edge_t *acc, DevCounters *ctr, unsigned long long cap, const uint32_t *k_to_s,
-                                                 uint32_t *parent, unsigned long long *best, uint2 *ends) {
+                                                 uint32_t *parent, unsigned long long *best2, uint2 *ends, uint32_t nent) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     unsigned long long n = ctr->n_accept;
     if (n > cap) n = cap;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (unsigned int round = 1; round < 4096; round++) {
+        unsigned long long *best = best2 + (size_t)(round & 1u) * nent, *other = best2 + (size_t)((round + 1u) & 1u) * nent;
         for (unsigned long long i = first; i < n; i += stride) {
             const ejoin_raw_edge_t e = acc[i];
             if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
@@ -1986,17 +1994,11 @@ __global__ void __launch_bounds__(256) k_boruvka(ejoin_raw_edge_t *acc, DevCount
             if (e.k1 == ACC_DEAD || (e.flags & ACC_SELECTED)) continue;
             const uint2 c = ends[i];
             const unsigned long long key = ((unsigned long long)e.k1 << 32) | e.k2;
+            other[c.x] = ~0ull; other[c.y] = ~0ull;                  // next round's table, clean where this round's components are
             if (best[c.x] == key || best[c.y] == key) {
                 acc[i].flags = e.flags | ACC_SELECTED;
                 uf_union(parent, c.x, c.y);
             }
-        }
-        grid.sync();
-        for (unsigned long long i = first; i < n; i += stride) {
-            const ejoin_raw_edge_t e = acc[i];
-            if (e.k1 == ACC_DEAD) continue;
-            const uint2 c = ends[i];
-            best[c.x] = ~0ull; best[c.y] = ~0ull;
         }
         grid.sync();
     }

@@ -160,5 +160,33 @@ extern "C" {
 pub struct egroup_asym_opts_t { pub bound_kind: i32, pub top: u32, pub max_dist: f64, pub min_group: u32, pub reserved: u32 }
 #[repr(C)]
 pub struct egroup_asym_result_t { pub n_groups: u64, pub group_off: *mut u64, pub member: *mut u32, pub dist: *mut f64, pub owner: *mut c_void }
+// ---- include/enclone_refine.h: the post-join refinement (define_mat, doublet / signature / weak-chain filters) ----
+#[repr(C)]
+pub struct erefine_pack_t {
+    pub abi_version: u32, pub n_info: u32, pub n_exact: u32, pub n_chain: u32,
+    pub exact_id: *const u32, pub exact_cols: [*const u8; 2], pub class_of: *const u32,
+    pub n_joins: u64, pub join_k1: *const u32, pub join_k2: *const u32,
+    pub chain_off: *const u32, pub ncells: *const u32, pub origin_rank: *const u32,
+    pub seq_id: *const u32, pub cdr3_id: *const u32, pub order_rank: *const u32, pub left: *const u8,
+    pub seq_len: *const u32, pub seq_off: *const u64, pub seq_arena: *const u8, pub seq_arena_bytes: u64,
+}
+#[repr(C)]
+pub struct erefine_opts_t {
+    pub doublet: i32, pub signature: i32, pub weak_chains: i32, pub doublet_mult: i32, pub signature_mult: i32,
+    pub weak_max_cells: i32, pub weak_mult: i32, pub third_chain_diffs: i32, pub reserved: [i32; 4],
+}
+#[repr(C)]
+pub struct erefine_stats_t {
+    pub n_clonotypes_in: u64, pub n_clonotypes_out: u64, pub n_pure: u64, pub n_doublet: u64, pub n_signature: u64, pub n_weak: u64,
+    pub triples_tested: u64, pub gpu_launches: u64, pub ms_device: f64, pub ms_total: f64,
+}
+#[repr(C)]
+pub struct erefine_result_t { pub fate: *mut u8, pub clonotype_of: *mut u32, pub column_of: *mut u32, pub n_columns: *mut u32 }
+#[link(name = "enclone_join")]
+extern "C" {
+    pub fn erefine_opts_default(o: *mut erefine_opts_t);
+    pub fn erefine_run(pack: *const erefine_pack_t, opts: *const erefine_opts_t, device: c_int, out: *mut erefine_result_t, stats: *mut erefine_stats_t) -> c_int;
+    pub fn erefine_last_error() -> *const c_char;
+}
 // The safe wrapper `join_exacts(..) -> EquivRel` with `Flat::pack` is sketched in INTEGRATION.md §1-§3;
 // enclone_b200/host/join_exacts.hpp is the same logic in C++ and is compiled and tested in this repository.

@@ -139,3 +139,25 @@ def group_asym(pack, in_center, opts_struct):
     out = result_groups(res)
     lib().oracle_group_asym_free(C.byref(res))
     return out, ev.value
+
+
+def refine(pack, opts_struct):
+    """oracle/refine_oracle.c: (RefineResult, stats dict) of the post-join refinement"""
+    from enclone_b200.refine import ErefineOpts, ErefinePack, ErefineResult, ErefineStats, RefineResult
+    L = lib()
+    L.oracle_refine.restype = C.c_int
+    L.oracle_refine.argtypes = [C.POINTER(ErefinePack), C.POINTER(ErefineOpts), C.POINTER(ErefineResult), C.POINTER(ErefineStats)]
+    res, st = RefineResult(pack.n_exact, pack.n_chain), ErefineStats()
+    rc = L.oracle_refine(C.byref(pack.struct), C.byref(opts_struct), C.byref(res.struct), C.byref(st))
+    assert rc == 0, rc
+    return res.trim(), st.as_dict()
+
+
+def refine_opts(**kw):
+    from enclone_b200.refine import ErefineOpts
+    o = ErefineOpts()
+    lib().oracle_refine_opts_default.argtypes = [C.POINTER(ErefineOpts)]
+    lib().oracle_refine_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, int(v))
+    return o

@@ -28,6 +28,11 @@ def test_library_exports_every_declared_symbol():
     assert gdecl == {"egroup_opts_default", "egroup_run", "egroup_last_error", "egroup_run_asym", "egroup_asym_free"}
     for s in gdecl:
         assert hasattr(L, s), s
+    rhdr = open(os.path.join(ROOT, "include", "enclone_refine.h")).read()
+    rdecl = set(re.findall(r"\b(erefine_[a-z0-9_]+)\s*\(", rhdr))
+    assert rdecl == {"erefine_opts_default", "erefine_run", "erefine_last_error"}
+    for s in rdecl:
+        assert hasattr(L, s), s
 
 
 def test_no_gpu_fails_loudly():
@@ -130,6 +135,7 @@ def test_rust_ffi_crate_declares_the_same_symbols():
     bound = set(re.findall(r"pub fn (ejoin_[a-z0-9_]+)\(", rs))
     assert bound == set(_lib.EXPORTS), bound ^ set(_lib.EXPORTS)
     assert set(re.findall(r"pub fn (egroup_[a-z0-9_]+)\(", rs)) == {"egroup_opts_default", "egroup_run", "egroup_last_error", "egroup_run_asym", "egroup_asym_free"}
+    assert set(re.findall(r"pub fn (erefine_[a-z0-9_]+)\(", rs)) == {"erefine_opts_default", "erefine_run", "erefine_last_error"}
 
 
 def test_tier1_work_decomposition_arithmetic(tmp_path):
