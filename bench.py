@@ -254,6 +254,80 @@ def group_main(args):
     print(json.dumps(line))
 
 
+def refine_main(args):
+    """The post-join refinement (include/enclone_refine.h) on a synthetic repertoire: one step = one erefine_run()
+    call with HOST buffers (uploads, chain grouping + the three filters with their break-ups on the GPU, results back).
+    value = exact subclonotypes per second of device time (CUDA events inside the library), e2e = per second of wall clock
+    around the call.  One GPU; not the north-star metric (that is the default --path join)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    from enclone_b200 import refine as R
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    base = R.synth_refine_pack(args.refine_families, seed=1)
+    pk = R.tile_pack(base, args.refine_tiles)
+    config = {"workload": f"{args.refine_tiles} independent copies of a synthetic repertoire of {args.refine_families} clonal families "
+                          f"(enclone_b200.refine.synth_refine_pack, seed 1): {pk.n_exact} exact subclonotypes, {pk.n_chain} chains, {pk.n_info} info entries, "
+                          f"{len(pk.a['join_k1'])} raw joins", "filters": "doublet, signature, weak chains (enclone defaults)"}
+    in_bytes = int(sum(v.nbytes for v in pk.a.values()))
+    out_bytes = int(pk.n_exact * 9 + pk.n_chain * 4)
+    if args.impl == "reference":
+        import oracle_lib
+        sub = R.tile_pack(base, max(1, args.refine_tiles // 4))
+        ts = []
+        for i in range(W + K):
+            t0 = time.perf_counter(); res, st = oracle_lib.refine(sub, oracle_lib.refine_opts()); ts.append(time.perf_counter() - t0)
+        dt = sum(ts[W:]) / K
+        val = sub.n_exact / dt
+        print(json.dumps({"impl": "reference", "path": "refine", "metric": "exact subclonotypes refined/sec", "value": val, "unit": "exacts/s", "n_gpus": 1, "steps": K,
+                          "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 / u64 integer", "data": "synthetic",
+                          "config": config, "cpu_baseline": {"value": val, "unit": "exacts/s", "cores": 1, "kind": "port",
+                                                             "sample": f"{max(1, args.refine_tiles // 4)} of the {args.refine_tiles} copies ({sub.n_exact} exact subclonotypes); the reference itself runs one rayon task per clonotype"},
+                          "e2e": {"value": val, "unit": "exacts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the refinement has no CPU fallback)")
+    sampler = ClockSampler(0)
+    for _ in range(W):
+        R.refine_clonotypes(pk)
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, stats, res = 0.0, None, None
+    for _ in range(K):
+        res, stats = R.refine_clonotypes(pk)
+        dev_ms += stats["ms_device"]
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6561.6))
+    stages = 1 + sum(1 for k in ("n_doublet", "n_signature", "n_weak") if stats[k])
+    alg = (int(stats["h2d_bytes"]) + out_bytes) * stages   # every stage reads the tables once and rewrites labels / columns once
+    line = {"path": "refine", "metric": "exact subclonotypes refined/sec", "value": pk.n_exact * K / (dev_ms * 1e-3), "unit": "exacts/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": wall / K * 1e3, "ms_device_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 / u64 integer", "data": "synthetic", "config": config,
+            "e2e": {"value": pk.n_exact * K / wall, "unit": "exacts/s", "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": out_bytes,
+                    "pack_bytes": in_bytes, "note": "pageable numpy buffers; of the pack's V..J arena only the third chains the rule compares are uploaded"},
+            "gpu_launches": int(stats["gpu_launches"]) * K, "stats": {k: (round(v, 3) if isinstance(v, float) else int(v)) for k, v in stats.items()},
+            "roofline": {"bound": "hbm", "achieved": alg / (dev_ms / K * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (dev_ms / K * 1e-3) / 1e9 / hbm, "traffic": None,
+                         "kernel": "whole refinement (no kernel holds a quarter of it: ~20 CUB radix sorts of 64-bit keys and ~70 small kernels)",
+                         "algorithmic_bytes_per_step": alg, "note": f"pack + result bytes x {stages} stages (one per filter that deleted something, plus the first); sorts re-read their keys once per 8-bit digit, so the traffic is several times this"},
+            "clocks": clocks}
+    if not args.no_cpu_baseline:
+        import oracle_lib
+        sub = R.tile_pack(base, max(1, args.refine_tiles // 4))
+        t0 = time.perf_counter(); want, wst = oracle_lib.refine(sub, oracle_lib.refine_opts()); dt = time.perf_counter() - t0
+        got, gst = R.refine_clonotypes(sub)
+        line["cpu_baseline"] = {"value": sub.n_exact / dt, "unit": "exacts/s", "cores": 1, "kind": "port",
+                                "sample": f"{max(1, args.refine_tiles // 4)} of the {args.refine_tiles} copies ({sub.n_exact} exact subclonotypes) in {dt:.2f} s",
+                                "parity_on_sample": bool(got.same_as(want))}
+    print(json.dumps(line))
+
+
 def _group_pairs(pk, g, kw, G):
     """candidate pairs of the first distance pass = pairs inside the groups the key partitions leave"""
     keys = {k: v for k, v in kw.items() if k in G.KEY_FLAGS}
@@ -273,12 +347,17 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-from-structs", action="store_true")
-    ap.add_argument("--path", default="join", choices=["join", "group"], help="join: the north-star path (default); group: the symmetric grouping, SURVEY §8(f)3")
+    ap.add_argument("--path", default="join", choices=["join", "group", "refine"],
+                    help="join: the north-star path (default); group: the symmetric grouping, SURVEY §8(f)3; refine: the post-join refinement, §8(f)2")
+    ap.add_argument("--refine-families", type=int, default=3000)
+    ap.add_argument("--refine-tiles", type=int, default=60)
     ap.add_argument("--group-n", type=int, default=20000)
     ap.add_argument("--group-opts", default="vj_refname=1,heavy_pc=96")
     args = ap.parse_args()
     if args.path == "group":
         return group_main(args)
+    if args.path == "refine":
+        return refine_main(args)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -47,7 +47,7 @@ struct RDev {
     uint32_t n, nx, nc; u64 nj;
     const uint32_t *exact_id, *class_of, *jk1, *jk2, *chain_off, *ncells, *origin_rank, *seq_id, *cdr3_id, *order_rank, *seq_len;
     const uint8_t *cols0, *cols1, *left, *seq_arena;
-    const u64 *seq_off; u64 arena_bytes;
+    const uint32_t *off2;          // offsets into the compacted sequence bytes (third chains only)
 };
 struct RCounters { u64 n_del, triples, n_pure; unsigned int err, pad; };
 
@@ -84,10 +84,7 @@ __global__ void k_r_xof(RDev d, uint32_t *xof, RCounters *ctr) {
     if (x >= d.nx) return;
     const uint32_t lo = d.chain_off[x], hi = d.chain_off[x + 1];
     if (hi < lo || hi > d.nc || hi - lo > EREFINE_MAX_CHAINS) { atomicOr(&ctr->err, RERR_RANGE); return; }
-    for (uint32_t c = lo; c < hi; c++) {
-        xof[c] = (uint32_t)x;
-        if (d.seq_off[c] + d.seq_len[c] > d.arena_bytes) atomicOr(&ctr->err, RERR_RANGE);
-    }
+    for (uint32_t c = lo; c < hi; c++) xof[c] = (uint32_t)x;
 }
 __global__ void k_r_key_origin(RDev d, const uint32_t *xof, u64 *keys, uint32_t *vals) {
     const size_t c = TID;
@@ -125,8 +122,43 @@ __global__ void k_r_check_joins(RDev d, RCounters *ctr) {
 
 // ---- one stage ----
 __global__ void k_r_iota(uint32_t *p, uint32_t n) { const size_t i = TID; if (i < n) p[i] = (uint32_t)i; }
-// S2 + S3 (oracle/refine_oracle.c): the raw joins' chain correspondences and the third-chain rule
-__global__ void k_r_joins(RDev d, const uint8_t *alive, uint32_t *cp, int third_diffs) {
+// S3 (oracle/refine_oracle.c), once per call: the third chains of a raw join between two three-chain exact subclonotypes.  The rule
+// does not depend on which exact subclonotypes are still alive, so it is evaluated once per join (third8) and the stages only read
+// the answer; the sequences it compares are the only V..J bytes the refinement ever reads, so only those go to the device.
+__device__ __forceinline__ bool third_pair(const RDev &d, size_t j, uint32_t *t1, uint32_t *t2) {
+    const uint32_t k1 = d.jk1[j], k2 = d.jk2[j];
+    const uint32_t x1 = d.exact_id[k1], x2 = d.exact_id[k2];
+    const uint32_t o1 = d.chain_off[x1], o2 = d.chain_off[x2];
+    const uint8_t a0 = d.cols0[k1], a1 = d.cols1[k1], b0 = d.cols0[k2], b1 = d.cols1[k2];
+    if (d.chain_off[x1 + 1] - o1 != 3 || d.chain_off[x2 + 1] - o2 != 3 || a0 >= 3 || a1 >= 3 || a0 == a1 || b0 >= 3 || b1 >= 3 || b0 == b1) return false;
+    *t1 = o1 + (3 - a0 - a1); *t2 = o2 + (3 - b0 - b1);
+    return d.left[*t1] == d.left[*t2] && d.seq_len[*t1] == d.seq_len[*t2];
+}
+__global__ void k_r_third_need(RDev d, uint8_t *need) {
+    const size_t j = TID;
+    uint32_t t1, t2;
+    if (j < d.nj && third_pair(d, j, &t1, &t2)) { need[t1] = 1; need[t2] = 1; }
+}
+__global__ void k_r_need_len(RDev d, const uint8_t *need, uint32_t *len) {
+    const size_t c = TID;
+    if (c < d.nc) len[c] = need[c] ? d.seq_len[c] : 0u;
+}
+__global__ void k_r_third(RDev d, int third_diffs, uint8_t *third8) {
+    const size_t j = TID;
+    if (j >= d.nj) return;
+    uint32_t t1, t2;
+    uint8_t ok = 0;
+    if (third_pair(d, j, &t1, &t2)) {
+        const uint8_t *s1 = d.seq_arena + d.off2[t1], *s2 = d.seq_arena + d.off2[t2];
+        const uint32_t len = d.seq_len[t1];
+        int diffs = 0;
+        for (uint32_t i = 0; i < len && diffs <= third_diffs; i++) diffs += s1[i] != s2[i];
+        ok = diffs <= third_diffs;
+    }
+    third8[j] = ok;
+}
+// S2 + S3 per stage: the raw joins' chain correspondences, and the third chains where k_r_third said yes
+__global__ void k_r_joins(RDev d, const uint8_t *alive, const uint8_t *third8, uint32_t *cp) {
     const size_t j = TID;
     if (j >= d.nj) return;
     const uint32_t k1 = d.jk1[j], k2 = d.jk2[j];
@@ -136,16 +168,7 @@ __global__ void k_r_joins(RDev d, const uint8_t *alive, uint32_t *cp, int third_
     const uint8_t a0 = d.cols0[k1], a1 = d.cols1[k1], b0 = d.cols0[k2], b1 = d.cols1[k2];
     uf_union(cp, o1 + a0, o2 + b0);
     if (a1 != 0xFF && b1 != 0xFF) uf_union(cp, o1 + a1, o2 + b1);
-    if (d.chain_off[x1 + 1] - o1 == 3 && d.chain_off[x2 + 1] - o2 == 3 && a0 < 3 && a1 < 3 && a0 != a1 && b0 < 3 && b1 < 3 && b0 != b1) {
-        const uint32_t t1 = o1 + (3 - a0 - a1), t2 = o2 + (3 - b0 - b1);
-        if (d.left[t1] == d.left[t2] && d.seq_len[t1] == d.seq_len[t2]) {
-            const uint8_t *s1 = d.seq_arena + d.seq_off[t1], *s2 = d.seq_arena + d.seq_off[t2];
-            const uint32_t len = d.seq_len[t1];
-            int diffs = 0;
-            for (uint32_t i = 0; i < len && diffs <= third_diffs; i++) diffs += s1[i] != s2[i];
-            if (diffs <= third_diffs) uf_union(cp, t1, t2);
-        }
-    }
+    if (third8[j]) uf_union(cp, o1 + (3 - a0 - a1), o2 + (3 - b0 - b1));
 }
 // S4: chains keyed by (clonotype, V..J sequence id)
 __global__ void k_r_seq_keys(RDev d, const uint32_t *xof, const uint8_t *alive, const uint32_t *label, u64 *keys, uint32_t *vals) {
@@ -159,17 +182,22 @@ __global__ void k_r_heads(const u64 *keys, uint32_t n, u64 mask, uint32_t *head)
     const size_t i = TID;
     if (i < n) head[i] = (i == 0 || (keys[i] & mask) != (keys[i - 1] & mask)) ? (uint32_t)i : 0u;
 }
-__global__ void k_r_onesie_flag(RDev d, const u64 *keys, const uint32_t *perm, const uint32_t *xof, const uint32_t *run_head, uint8_t *flag) {
+// S4 per stage, on the order sorted ONCE by (clonotype the join left, sequence id): a later stage's clonotypes only split the earlier
+// ones, and chains that an alive onesie tied together in one stage are in one clonotype in the next, so the runs of the first sort
+// serve every stage; only "is there an alive onesie in the run" changes.
+__global__ void k_r_onesie_first(RDev d, const uint32_t *perm, const uint32_t *xof, const uint8_t *alive, const uint32_t *run_head, uint32_t *first) {
     const size_t i = TID;
-    if (i >= d.nc || keys[i] == ~0ull) return;
-    const uint32_t x = xof[perm[i]];
-    if (d.chain_off[x + 1] - d.chain_off[x] == 1) flag[run_head[i]] = 1;
+    if (i >= d.nc) return;
+    const uint32_t c = perm[i], x = xof[c];
+    if (alive[x] && d.chain_off[x + 1] - d.chain_off[x] == 1) atomicMin(&first[run_head[i]], c);
 }
-__global__ void k_r_onesie_join(RDev d, const u64 *keys, const uint32_t *perm, const uint32_t *run_head, const uint8_t *flag, uint32_t *cp) {
+__global__ void k_r_onesie_join(RDev d, const uint32_t *perm, const uint32_t *xof, const uint8_t *alive, const uint32_t *run_head, const uint32_t *first, uint32_t *cp) {
     const size_t i = TID;
-    if (i >= d.nc || keys[i] == ~0ull) return;
-    const uint32_t h = run_head[i];
-    if (h != i && flag[h]) uf_union(cp, perm[h], perm[i]);
+    if (i >= d.nc) return;
+    const uint32_t c = perm[i];
+    if (!alive[xof[c]]) return;
+    const uint32_t f = first[run_head[i]];
+    if (f != NONE32 && f != c) uf_union(cp, c, f);
 }
 // S6: exact subclonotypes that share a column are one clonotype
 __global__ void k_r_link_exacts(RDev d, const uint32_t *xof, const uint8_t *alive, uint32_t *cp, uint32_t *xp) {
@@ -196,11 +224,11 @@ __global__ void k_r_orbit_stats(RDev d, const uint8_t *alive, uint32_t *cp, cons
         if (cnt > 1 || mm[r[a]] == 0) atomicMax(&mm[r[a]], cnt);
     }
 }
-__global__ void k_r_orbit_keys(RDev d, const uint32_t *xof, const uint8_t *alive, const uint32_t *label, const uint32_t *cp, const u64 *rep, u64 *keys, uint32_t *vals) {
+__global__ void k_r_orbit_keys(RDev d, const uint32_t *xof, const uint8_t *alive, const uint32_t *label, const uint32_t *cp, const u64 *rep, int pb, u64 *keys, uint32_t *vals) {
     const size_t c = TID;
     if (c >= d.nc) return;
     const bool root = alive[xof[c]] && cp[c] == c;
-    keys[c] = root ? (((u64)label[xof[c]] << 32) | (rep[c] & 0xFFFFFFFFull)) : ~0ull;
+    keys[c] = root ? (((u64)label[xof[c]] << pb) | (rep[c] & 0xFFFFFFFFull)) : ~0ull;       // pb = bits of a chain position
     vals[c] = (uint32_t)c;
 }
 __global__ void k_r_gather_mm(RDev d, const u64 *keys, const uint32_t *perm, const uint32_t *mm, uint32_t *out) {
@@ -210,10 +238,10 @@ __global__ void k_r_gather_mm(RDev d, const u64 *keys, const uint32_t *perm, con
 // column base of every orbit = (global exclusive sum of mm) - (the same at the first orbit of its clonotype); the global number
 // of a clonotype's first column and its column count go to tables indexed by the clonotype's name (an exact id)
 __global__ void k_r_orbit_base(RDev d, const u64 *keys, const uint32_t *perm, const uint32_t *run_head, const uint32_t *gsum, const uint32_t *mms,
-                               uint32_t *base, uint32_t *gbase, uint32_t *ncols_label) {
+                               int pb, uint32_t *base, uint32_t *gbase, uint32_t *ncols_label) {
     const size_t i = TID;
     if (i >= d.nc || keys[i] == ~0ull) return;
-    const uint32_t h = run_head[i], lab = (uint32_t)(keys[i] >> 32);
+    const uint32_t h = run_head[i], lab = (uint32_t)(keys[i] >> pb);
     base[perm[i]] = gsum[i] - gsum[h];
     if (h == i) gbase[lab] = gsum[i];
     atomicAdd(&ncols_label[lab], mms[i]);
@@ -400,7 +428,7 @@ __global__ void k_r_outputs(RDev d, const uint8_t *alive, const uint32_t *label,
 }
 
 struct Pool {          // stream-ordered allocations, all returned at the end
-    cudaStream_t st = nullptr; std::vector<void *> ptrs; bool failed = false; std::string msg;
+    cudaStream_t st = nullptr; std::vector<void *> ptrs; bool failed = false; std::string msg; unsigned long long h2d = 0;
     template <typename T> T *get(size_t n) {
         void *p = nullptr;
         cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T) + 64, st);
@@ -410,6 +438,7 @@ struct Pool {          // stream-ordered allocations, all returned at the end
     }
     template <typename T> T *up(const T *h, size_t n) {
         T *p = get<T>(n);
+        h2d += n * sizeof(T);
         if (p && n && cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) { failed = true; msg = "H2D copy"; }
         return p;
     }
@@ -452,17 +481,18 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
     Pool P;
     RCK(cudaStreamCreateWithFlags(&P.st, cudaStreamNonBlocking));
     cudaStream_t st = P.st;
-    cudaEvent_t ev0, ev1;
-    RCK(cudaEventCreate(&ev0)); RCK(cudaEventCreate(&ev1));
-    struct EvBox { cudaEvent_t a, b; ~EvBox() { cudaEventDestroy(a); cudaEventDestroy(b); } } evbox{ ev0, ev1 };
+    cudaEvent_t ev0, ev1, evA, evB;
+    RCK(cudaEventCreate(&ev0)); RCK(cudaEventCreate(&ev1)); RCK(cudaEventCreate(&evA)); RCK(cudaEventCreate(&evB));
+    struct EvBox { cudaEvent_t a, b, c, d; ~EvBox() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); } } evbox{ ev0, ev1, evA, evB };
+    bool host_gap = false;
 
     RDev d;
-    d.n = n; d.nx = nx; d.nc = nc; d.nj = nj; d.arena_bytes = pk->seq_arena_bytes;
+    d.n = n; d.nx = nx; d.nc = nc; d.nj = nj; d.seq_arena = nullptr; d.off2 = nullptr;
     d.exact_id = P.up(pk->exact_id, n); d.cols0 = P.up(pk->exact_cols[0], n); d.cols1 = P.up(pk->exact_cols[1], n); d.class_of = P.up(pk->class_of, n);
     d.jk1 = P.up(pk->join_k1, nj); d.jk2 = P.up(pk->join_k2, nj);
     d.chain_off = P.up(pk->chain_off, (size_t)nx + 1); d.ncells = P.up(pk->ncells, nx); d.origin_rank = P.up(pk->origin_rank, nx);
     d.seq_id = P.up(pk->seq_id, nc); d.cdr3_id = P.up(pk->cdr3_id, nc); d.order_rank = P.up(pk->order_rank, nc); d.left = P.up(pk->left, nc);
-    d.seq_len = P.up(pk->seq_len, nc); d.seq_off = (const u64 *)P.up(pk->seq_off, nc); d.seq_arena = P.up(pk->seq_arena, pk->seq_arena_bytes);
+    d.seq_len = P.up(pk->seq_len, nc);          // the V..J bytes themselves: only the third chains', gathered below
     const size_t big = std::max<size_t>(std::max<size_t>(nc, nx), n) + 1;
     size_t cub_bytes = 0, tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (u64 *)nullptr, (u64 *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)big); cub_bytes = std::max(cub_bytes, tb);
@@ -482,6 +512,8 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
     uint32_t *by_c_pure = P.get<uint32_t>(big), *n_uniq = P.get<uint32_t>(4);
     RCounters *ctr = P.get<RCounters>(1);
     uint32_t *o_clon = P.get<uint32_t>(nx), *o_ncols = P.get<uint32_t>(nx);
+    uint32_t *seq_perm = P.get<uint32_t>(nc), *seq_head = P.get<uint32_t>(nc), *first = P.get<uint32_t>(nc), *off2 = P.get<uint32_t>((size_t)nc + 1);
+    uint8_t *need8 = P.get<uint8_t>(nc), *third8 = P.get<uint8_t>(nj);
     if (P.failed) return rfail(-5, "device allocation: " + P.msg);
     u64 launches = 0;
     RCK(cudaEventRecord(ev0, st));
@@ -507,22 +539,59 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
         k_r_scatter_pos<<<blocks(nc), 256, 0, st>>>(v_out, nc, pos);
         launches += 4;
     }
-    const u64 hi32 = 0xFFFFFFFF00000000ull;
     int lb = 33;                                  // bits of a (clonotype name << 32 | 32-bit field) key; dead entries are all ones and sort last
+    while (lb < 64 && (1ull << (lb - 32)) < (u64)nx + 1) lb++;
+    int pb = 1;                                   // bits of a chain position
+    while (pb < 32 && (1ull << pb) < (u64)nc + 1) pb++;
+    const int ob = pb + (lb - 32);                // bits of an orbit key (clonotype name << pb | position)
+    // S3 once: which chains' bytes are needed, those bytes gathered on the host in chain order, the verdict per join
+    RCK(cudaMemsetAsync(third8, 0, std::max<u64>(nj, 1), st));
+    static thread_local std::vector<uint8_t> need_h, gathered;      // kept between calls: no page faults on a second call's gather
+    if (nj && nc) {
+        RCK(cudaMemsetAsync(need8, 0, nc, st));
+        k_r_third_need<<<blocks(nj), 256, 0, st>>>(d, need8);
+        k_r_need_len<<<blocks(nc), 256, 0, st>>>(d, need8, t32a);
+        tb = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t32a, off2, (int)nc, st);
+        if (need_h.size() < nc) need_h.resize(nc);
+        RCK(cudaMemcpyAsync(need_h.data(), need8, nc, cudaMemcpyDeviceToHost, st));
+        RCK(cudaEventRecord(evA, st));
+        RCK(cudaStreamSynchronize(st));
+        host_gap = true;
+        u64 total = 0;
+        for (uint32_t c = 0; c < nc; c++) if (need_h[c]) {
+            if (pk->seq_off[c] + pk->seq_len[c] > pk->seq_arena_bytes) return rfail(-1, "seq_off + seq_len of a chain lies outside seq_arena");
+            total += pk->seq_len[c];
+        }
+        if (total >= 0xFFFFFFFFull) return rfail(-4, "third chains of joined three-chain exact subclonotypes hold 4 GiB of sequence or more");
+        if (gathered.size() < total + 16) gathered.resize(total + 16);
+        u64 o = 0;
+        for (uint32_t c = 0; c < nc; c++) if (need_h[c]) { memcpy(gathered.data() + o, pk->seq_arena + pk->seq_off[c], pk->seq_len[c]); o += pk->seq_len[c]; }
+        RCK(cudaEventRecord(evB, st));          // the host's gather is not device time
+        d.seq_arena = P.up(gathered.data(), (size_t)total + 16);
+        d.off2 = off2;
+        if (P.failed) return rfail(-5, "device allocation: " + P.msg);
+        if (total) k_r_third<<<blocks(nj), 256, 0, st>>>(d, op->third_chain_diffs, third8);
+        launches += 3;
+    }
+    // S4 once: chains sorted by (clonotype the join left, sequence id), run heads
+    if (nc) {
+        k_r_seq_keys<<<blocks(nc), 256, 0, st>>>(d, xof, alive, label, k_in, v_in);
+        tb = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k_in, k_out, v_in, seq_perm, (int)nc, 0, lb, st);
+        k_r_heads<<<blocks(nc), 256, 0, st>>>(k_out, nc, ~0ull, t32a);
+        tb = cub_bytes; cub::DeviceScan::InclusiveScan(cub_tmp, tb, t32a, seq_head, RMax(), (int)nc, st);
+        launches += 2;
+    }
+    if (int lbx = 0) (void)lbx;                                  // bits of a (clonotype name << 32 | 32-bit field) key; dead entries are all ones and sort last
     while (lb < 64 && (1ull << (lb - 32)) < (u64)nx + 1) lb++;
     auto stage = [&]() -> int {
         RCK(cudaMemsetAsync(&ctr->n_pure, 0, 8, st));
         k_r_iota<<<blocks(nc), 256, 0, st>>>(cp, nc);
         k_r_iota<<<blocks(nx), 256, 0, st>>>(xp, nx);
-        if (nj) k_r_joins<<<blocks(nj), 256, 0, st>>>(d, alive, cp, op->third_chain_diffs);
+        if (nj) k_r_joins<<<blocks(nj), 256, 0, st>>>(d, alive, third8, cp);
         // S4
-        k_r_seq_keys<<<blocks(nc), 256, 0, st>>>(d, xof, alive, label, k_in, v_in);
-        tb = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k_in, k_out, v_in, v_out, (int)nc, 0, lb, st);
-        k_r_heads<<<blocks(nc), 256, 0, st>>>(k_out, nc, ~0ull, t32a);
-        tb = cub_bytes; cub::DeviceScan::InclusiveScan(cub_tmp, tb, t32a, t32b, RMax(), (int)nc, st);
-        RCK(cudaMemsetAsync(flag8, 0, nc, st));
-        k_r_onesie_flag<<<blocks(nc), 256, 0, st>>>(d, k_out, v_out, xof, t32b, flag8);
-        k_r_onesie_join<<<blocks(nc), 256, 0, st>>>(d, k_out, v_out, t32b, flag8, cp);
+        RCK(cudaMemsetAsync(first, 0xFF, 4 * (size_t)nc, st));
+        k_r_onesie_first<<<blocks(nc), 256, 0, st>>>(d, seq_perm, xof, alive, seq_head, first);
+        k_r_onesie_join<<<blocks(nc), 256, 0, st>>>(d, seq_perm, xof, alive, seq_head, first, cp);
         // S6
         k_r_link_exacts<<<blocks(nc), 256, 0, st>>>(d, xof, alive, cp, xp);
         k_r_labels<<<blocks(nx), 256, 0, st>>>(d, alive, xp, label);
@@ -530,13 +599,13 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
         RCK(cudaMemsetAsync(rep, 0xFF, 8 * (size_t)nc, st)); RCK(cudaMemsetAsync(mm, 0, 4 * (size_t)nc, st));
         RCK(cudaMemsetAsync(ncols_label, 0, 4 * (size_t)nx, st)); RCK(cudaMemsetAsync(gbase, 0, 4 * (size_t)nx, st));
         k_r_orbit_stats<<<blocks(nx), 256, 0, st>>>(d, alive, cp, pos, pos2, rep, mm);
-        k_r_orbit_keys<<<blocks(nc), 256, 0, st>>>(d, xof, alive, label, cp, rep, k_in, v_in);
-        tb = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k_in, k_out, v_in, v_out, (int)nc, 0, lb, st);
+        k_r_orbit_keys<<<blocks(nc), 256, 0, st>>>(d, xof, alive, label, cp, rep, pb, k_in, v_in);
+        tb = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k_in, k_out, v_in, v_out, (int)nc, 0, ob, st);
         k_r_gather_mm<<<blocks(nc), 256, 0, st>>>(d, k_out, v_out, mm, t32c);
         tb = cub_bytes; cub::DeviceScan::ExclusiveSum(cub_tmp, tb, t32c, t32a, (int)nc, st);
-        k_r_heads<<<blocks(nc), 256, 0, st>>>(k_out, nc, hi32, v_in);
+        k_r_heads<<<blocks(nc), 256, 0, st>>>(k_out, nc, ~((1ull << pb) - 1ull), v_in);
         tb = cub_bytes; cub::DeviceScan::InclusiveScan(cub_tmp, tb, v_in, t32b, RMax(), (int)nc, st);
-        k_r_orbit_base<<<blocks(nc), 256, 0, st>>>(d, k_out, v_out, t32b, t32a, t32c, base, gbase, ncols_label);
+        k_r_orbit_base<<<blocks(nc), 256, 0, st>>>(d, k_out, v_out, t32b, t32a, t32c, pb, base, gbase, ncols_label);
         // columns, S7
         k_r_columns<<<blocks(nx), 256, 0, st>>>(d, alive, label, cp, base, col, k2_in, v_in);
         tb = cub_bytes; cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k2_in, k2_out, v_in, v_out, (int)nx, 0, 64, st);
@@ -544,7 +613,7 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
         tb = cub_bytes; cub::DeviceScan::InclusiveSum(cub_tmp, tb, t32a, t32b, (int)nx, st);
         RCK(cudaMemsetAsync(npure, 0, 8 * (size_t)nx, st));
         k_r_pure_ids<<<blocks(nx), 256, 0, st>>>(d, k2_out, v_out, t32b, pure, npure, pure_hash, ctr);
-        launches += 17 + (nj ? 1 : 0);
+        launches += 15 + (nj ? 1 : 0);
         RCK(cudaGetLastError());
         return 0;
     };
@@ -561,11 +630,8 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
         }
         return 0;
     };
-    if (int rc = stage()) return rc;
-    RCK(cudaMemcpyAsync(&hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
-    RCK(cudaStreamSynchronize(st));
-    S.n_pure = hc.n_pure;
-    {   // clonotypes coming in: names that are their own label (counted on the host from the labels is a copy too many: one small kernel)
+    {   // clonotypes coming in (the classes of class_of, before any break-up): names that are their own label
+        RCK(cudaMemsetAsync(ncols_label, 0, 4 * (size_t)nx, st));
         k_r_outputs<<<blocks(nx), 256, 0, st>>>(d, alive, label, ncols_label, o_clon, o_ncols, ctr);
         RCK(cudaMemcpyAsync(&hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
         RCK(cudaStreamSynchronize(st));
@@ -573,6 +639,10 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
         RCK(cudaMemsetAsync(&ctr->n_del, 0, 8, st));
         launches += 1;
     }
+    if (int rc = stage()) return rc;
+    RCK(cudaMemcpyAsync(&hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    RCK(cudaStreamSynchronize(st));
+    S.n_pure = hc.n_pure;
     if (op->doublet) {
         RCK(cudaMemsetAsync(del, 0, nx, st)); RCK(cudaMemsetAsync(pdel, 0, nx, st));
         k_r_content<<<blocks(nc), 256, 0, st>>>(d, xof, alive, pure, k_in);
@@ -617,7 +687,9 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
     S.n_clonotypes_out = hc.n_del;
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
+    if (host_gap) { float gap = 0; cudaEventElapsedTime(&gap, evA, evB); ms -= gap; }
     S.ms_device = ms;
+    S.h2d_bytes = P.h2d;
     S.gpu_launches = launches;
     S.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (stats) *stats = S;

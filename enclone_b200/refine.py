@@ -36,7 +36,7 @@ class ErefineOpts(C.Structure):
 
 class ErefineStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_clonotypes_in", "n_clonotypes_out", "n_pure", "n_doublet", "n_signature", "n_weak",
-                                          "triples_tested", "gpu_launches")] + [("ms_device", C.c_double), ("ms_total", C.c_double)]
+                                          "triples_tested", "gpu_launches", "h2d_bytes")] + [("ms_device", C.c_double), ("ms_total", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -88,7 +88,8 @@ typedef struct erefine_stats {
     uint64_t n_doublet, n_signature, n_weak;   /* exact subclonotypes deleted by each filter             */
     uint64_t triples_tested;         /* (p0, p1, p2) candidates examined by the doublet filter           */
     uint64_t gpu_launches;
-    double   ms_device, ms_total;
+    uint64_t h2d_bytes;              /* bytes uploaded: the tables, and of seq_arena only the third chains the rule compares */
+    double   ms_device, ms_total;    /* device: CUDA events around the device work (the host's gather of those bytes taken out) */
 } erefine_stats_t;
 
 /* Caller-allocated result arrays. */

@@ -178,7 +178,7 @@ pub struct erefine_opts_t {
 #[repr(C)]
 pub struct erefine_stats_t {
     pub n_clonotypes_in: u64, pub n_clonotypes_out: u64, pub n_pure: u64, pub n_doublet: u64, pub n_signature: u64, pub n_weak: u64,
-    pub triples_tested: u64, pub gpu_launches: u64, pub ms_device: f64, pub ms_total: f64,
+    pub triples_tested: u64, pub gpu_launches: u64, pub h2d_bytes: u64, pub ms_device: f64, pub ms_total: f64,
 }
 #[repr(C)]
 pub struct erefine_result_t { pub fate: *mut u8, pub clonotype_of: *mut u32, pub column_of: *mut u32, pub n_columns: *mut u32 }
