@@ -133,6 +133,7 @@ struct ejoin_handle {
     bool tables_built = false;       // prepare_tables has run on this handle: later joins do not wait for the key pass (device_pipeline)
     int sm_count = 148;
     int bor_grid = 0;          // cooperative grid of k_boruvka
+    int mma_grid = 0;          // grid of k_sweep_mma (resident CTAs)
     // resident input + work buffers
     Arena in_arena, work;
     DevIn din;
@@ -811,6 +812,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
     // items than the GPU has CTA slots and the sweep's time is the time of its longest item)
     uint32_t seg_min = n >= 1000000u ? SEG_MIN : 4u;       // measured on eighths of the 1.6 M-cell join: 8 -> 4 halves the sweep; 2 and 1 cost phase A more than they save
     if (const char *e = getenv("EJOIN_SEG_MIN")) seg_min = (uint32_t)std::max(1, atoi(e));
+    uint32_t mma_min_tiles = MMA_MIN_TILES_DEFAULT;        // groups of at least this many tiles (and CDR3s of at most MMA_MAX_BASES bases) sweep on the tensor cores; 0 = never
+    if (const char *e = getenv("EJOIN_MMA_MIN_TILES")) mma_min_tiles = (uint32_t)std::max(0, atoi(e));
+    unsigned long long i8_cap_tiles = mma_min_tiles ? (unsigned long long)n / T1_TILE + 64 : 0;      // groups that find no slot left stay with the popcount sweep
+    if (const char *e = getenv("EJOIN_MMA_CAP_TILES")) if (mma_min_tiles) i8_cap_tiles = (unsigned long long)std::max(1, atoi(e));
     if (h->xrow_cap == 0 || h->xrow_seg != seg_min) { h->xrow_cap = 1024 + (unsigned long long)(n / T1_TILE) * (16 / std::min(16u, seg_min)); h->xrow_seg = seg_min; }
     if (n == 0) return 0;
     bool tables_retry = false;
@@ -851,6 +856,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap); sz.take(8 * cap);                             // edge keys/vals in+out
         sz.take(16 * (size_t)n); sz.take(8 * cap); sz.take(4 * (size_t)n);                                  // Boruvka: two bid tables, ends, component sizes
         sz.take(cub_bytes + 256);
+        sz.take(i8_cap_tiles * MMA_TILE_BYTES + 256);                                                       // int8 tiles of the tensor-core groups
         sz.take(8 * (size_t)n + 64); sz.take(sizeof(ejoin_edge_t) * ((size_t)n + 1)); sz.take(4 * (size_t)n + 64);   // payload staging (taken later)
         sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)n + 64); sz.take(4 * (size_t)h->din.n_exact + 64);   // union-find labels (in, out), first entry per exact
         CK(h->work.buf.ensure(sz.off + 4096));
@@ -886,6 +892,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         uint2 *ends = A.take<uint2>(cap);
         uint32_t *comp_size = A.take<uint32_t>(n);
         void *cub_tmp = A.take<char>(cub_bytes + 256);
+        int8_t *i8_tiles = A.take<int8_t>(i8_cap_tiles * MMA_TILE_BYTES + 256);
         h->meta = meta; h->c3 = c3; h->t2 = t2; h->k_to_s = k_to_s; h->kept_keys = pk_out; h->kept_vals = pv_out;
         h->w_parent = parent; h->w_best = best; h->w_comp_size = comp_size; h->w_f0_key = f0_key; h->w_f0_val = f0_val;
         DevCounters *ctr = (DevCounters *)h->d_counters.p;
@@ -933,7 +940,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumB, sumB, (int)n, st);
         tb = cub_bytes;
         cub::DeviceScan::ExclusiveSum(cub_tmp, tb, sumC, sumC, (int)n, st);
-        k_group_build<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, groups, ctr, seg_min);
+        k_group_build<<<nb256, 256, 0, st>>>(uniq, counts, num_runs, (const uint16_t *)h->d_cdmax.p, sumA, sumB, sumC, groups, ctr, seg_min, mma_min_tiles, i8_cap_tiles);
         h->launches += 2;                           // k_group_vals, k_group_build (own kernels only: CUB's sort / RLE / scan passes are never counted)
         mark(h, "rle + group table");
         k_item_hist<<<h->sm_count, 256, 0, st>>>(groups, ctr, item_cls, item_cap, stride, phase);
@@ -953,6 +960,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_pack_c3<<<(unsigned)(((size_t)n * 4 + 255) / 256), 256, 0, st>>>(h->din, perm, gid, groups, ctr, c3);
         // stride mode: the gathered edges of the other ranks need this rank's rows too -> pack every entry
         k_init_rows<<<nb256, 256, 0, st>>>(parent, f0_key, surv_cnt, needed, force, n, stride > 1 ? 1 : 0);
+        if (mma_min_tiles) { k_pack_i8<<<nb256, 256, 0, st>>>(c3, gid, groups, ctr, i8_tiles); h->launches += 1; }     // returns at once without a tensor-core group
         CK(cudaEventRecord(h->ev[2], st));
         mark(h, "k_pack_c3 + k_init_rows");
         // tier 1: needs only the c3 rows, so it runs while the V..J arena is still on its way
@@ -960,6 +968,20 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_occ, k_sweep, T1_TILE, 0);
         if (rows_occ < 1) rows_occ = 1;
         k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, order, cand, ccap, firstk, surv_cnt, xk, xcnt, xcap, needed);
+        if (mma_min_tiles) {
+            // the large groups of short CDR3s on the tensor cores (the kernel returns at once when the group table flagged none)
+            const size_t mma_smem = 3 * (size_t)MMA_TILE_BYTES;
+            if (h->mma_grid == 0) {
+                CK(cudaFuncSetAttribute(k_sweep_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem));
+                CK(cudaFuncSetAttribute(k_sweep_mma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                // two CTAs per SM: 2 x 113 KB of shared memory, 2 x 256 of the 512 TMEM columns.  (Measured with the prototype: two per SM
+                // sweep 1.67x faster than one, although the occupancy API answers 1 for this kernel; CTAs beyond what is resident
+                // would only find the work list empty.)
+                h->mma_grid = h->sm_count * 2;
+            }
+            k_sweep_mma<<<h->mma_grid, T1_TILE, mma_smem, st>>>(i8_tiles, groups, ctr, order, cand, ccap, firstk, surv_cnt, xk, xcnt, xcap, needed);
+            h->launches += 1;
+        }
         CK(cudaEventRecord(h->ev[3], st));
         mark(h, "k_sweep");
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)

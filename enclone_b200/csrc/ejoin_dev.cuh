@@ -61,6 +61,14 @@ static_assert(sizeof(EntryMeta) == 128, "EntryMeta must be 128 bytes");
 // "extra row" of slots, numbered xoff + item_index - T.
 #define SEG_MIN 8u           // A tiles per segment (small groups) on a big input; large groups: ceil(T / SEG_QMAX).  Small inputs (a
                              // rank's share of a sharded join) use 4 or 2, so that there are still more work items than CTA slots
+// Tier 1 on the tensor cores (k_sweep_mma; tools/micro/hamming_mma.cu is the stand-alone prototype): a group whose two CDR3s total
+// at most MMA_MAX_BASES bases and that has at least `mma_min_tiles` tiles gets its rows a second time as int8 tetrahedron vectors
+// (3 values per base), one shared-memory image of MMA_TILE_BYTES per tile of 128 entries.
+#define MMA_NONE 0xFFFFFFFFu
+#define MMA_MAX_BASES 96u
+#define MMA_KMAX 288u                               // 3 * MMA_MAX_BASES, a multiple of 32
+#define MMA_TILE_BYTES (T1_TILE * MMA_KMAX)         // [K/16 chunks][128 rows][16 bytes]; a group with fewer bases uses a prefix
+#define MMA_MIN_TILES_DEFAULT 16u
 #define SEG_QMAX 32u         // at most this many segments per row
 struct GroupInfo {           // one comparison group = one run of equal sort keys
     uint32_t start;          // first sorted position
@@ -72,7 +80,7 @@ struct GroupInfo {           // one comparison group = one run of equal sort key
     uint16_t cdmax;          // largest cd that passes the CDR3 gates
     uint16_t tiles;
     uint16_t seg;            // A tiles per segment
-    uint32_t pad;
+    uint32_t mma;            // MMA_NONE, or (bases of both CDR3s << 23 | first int8 tile slot): the group's tier-1 runs on the tensor cores (k_sweep_mma)
 };
 static_assert(sizeof(GroupInfo) == 32, "GroupInfo is 32 bytes");
 __host__ __device__ __forceinline__ uint32_t seg_of_tiles(uint32_t T, uint32_t seg_min = SEG_MIN) { uint32_t s = (T + SEG_QMAX - 1) / SEG_QMAX; return s < seg_min ? seg_min : s; }
@@ -95,6 +103,8 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned long long n_xrows;      // extra slot rows asked for by the group table
     unsigned long long n_items;      // tier-1 work items of this rank (after the cost sort)
     unsigned int cls_count[64], cls_cursor[64];   // counting sort of the work items by cost class
+    unsigned long long work_next_mma;               // k_sweep_mma's own cursor over the same item list
+    unsigned int i8_tiles, pad2;                    // int8 tile slots handed to tensor-core groups (k_group_build)
 };
 
 struct DevParams {           // ejoin_params_t plus run constants, by value to kernels

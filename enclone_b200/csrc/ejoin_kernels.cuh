@@ -48,9 +48,10 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
             // radix pass fewer; two separate runs of equal lens stay two buckets, as in the reference's bucket scan)
             key = ((unsigned long long)bucket_start[k] << 16) | ((unsigned long long)c0 << 8) | c1;
             uint32_t L = l0 + l1, cc = (c0 << 8) | c1;
-            // test before set: after the first hit per value these are plain cached loads, not serialized atomics
-            if (!(presL[L >> 5] & (1u << (L & 31)))) atomicOr(&presL[L >> 5], 1u << (L & 31));
-            if (!(presC[cc >> 5] & (1u << (cc & 31)))) atomicOr(&presC[cc >> 5], 1u << (cc & 31));
+            // test before set, reading through L2 (__ldcg): a line cached in L1 before the bit was set would stay stale for the whole
+            // kernel and every entry of that SM would go on issuing the same-address atomic
+            if (!(__ldcg(&presL[L >> 5]) & (1u << (L & 31)))) atomicOr(&presL[L >> 5], 1u << (L & 31));
+            if (!(__ldcg(&presC[cc >> 5]) & (1u << (cc & 31)))) atomicOr(&presC[cc >> 5], 1u << (cc & 31));
         }
         keys[k] = key;
         vals[k] = k;
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(256) k_group_vals(const unsigned long long *__
 __global__ void __launch_bounds__(256) k_group_build(const unsigned long long *__restrict__ uniq, const uint32_t *__restrict__ counts,
                                                      const uint32_t *num_runs, const uint16_t *__restrict__ cdmax_tab,
                                                      const unsigned long long *__restrict__ sumA, const unsigned long long *__restrict__ sumB,
-                                                     const uint32_t *__restrict__ sumC, GroupInfo *__restrict__ groups, DevCounters *ctr, uint32_t seg_min) {
+                                                     const uint32_t *__restrict__ sumC, GroupInfo *__restrict__ groups, DevCounters *ctr, uint32_t seg_min,
+                                                     uint32_t mma_min_tiles, unsigned long long i8_cap_tiles) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nr = *num_runs;
     if (r >= nr) return;
@@ -142,7 +144,14 @@ __global__ void __launch_bounds__(256) k_group_build(const unsigned long long *_
         g.c3base = (uint32_t)b;
         g.work_off = (uint32_t)(a >> 32);
         g.xoff = x;
-        g.W = (uint16_t)gv.W; g.cdmax = (uint16_t)gv.cdm; g.tiles = (uint16_t)gv.T; g.seg = (uint16_t)seg_of_tiles(gv.T, seg_min); g.pad = 0;
+        g.W = (uint16_t)gv.W; g.cdmax = (uint16_t)gv.cdm; g.tiles = (uint16_t)gv.T; g.seg = (uint16_t)seg_of_tiles(gv.T, seg_min); g.mma = MMA_NONE;
+        {   // large groups of short CDR3s: tier 1 on the tensor cores, if int8 tile slots are left (none left: the popcount sweep takes it)
+            const uint32_t total = (uint32_t)((uniq[r] >> 8) & 0xFF) + (uint32_t)(uniq[r] & 0xFF);
+            if (mma_min_tiles && gv.T >= mma_min_tiles && gv.T <= 65535u && total >= 1 && total <= MMA_MAX_BASES && g.n >= 2 && gv.cdm != 0xFFFF && 3 * total > 4 * gv.cdm) {
+                const uint32_t slot = atomicAdd(&ctr->i8_tiles, gv.T);
+                if ((unsigned long long)slot + gv.T <= i8_cap_tiles && slot + gv.T < (1u << 23)) g.mma = (total << 23) | slot;
+            }
+        }
         groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
     }
     if (r == nr - 1) {               // totals = exclusive prefix of the last run + its own values
@@ -1609,11 +1618,40 @@ __device__ __forceinline__ void sweep_flush(SweepCtx &cx, uint4 *stage, uint32_t
     fill = 0;
 }
 
+// What a thread does with the survivor mask of its entry b against one block of 32 a's (posA = sorted position of the block's
+// first a): needed flags, the first PHASE_A_K survivors of the segment into b's slots, the rest as one 16-byte record on the
+// survivor list.  Warp-collective: every lane of the warp calls it with its own mask (0 = nothing).
+template <uint32_t STAGE_CAP>
+__device__ __forceinline__ void sweep_emit(SweepCtx &cx, uint32_t bits, uint32_t posA, uint32_t posB, uint32_t &mycnt, uint4 *stage, uint32_t &fill,
+                                           uint32_t *slot, uint32_t slot_stride) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t col = __reduce_or_sync(0xFFFFFFFFu, bits);      // a's with a survivor partner in this warp
+    if (!col) return;
+    if ((col >> lane) & 1u) cx.needed[posA + lane] = 1;
+    // the first PHASE_A_K survivors of b, in ascending a, go to its slot array
+    while (bits && mycnt < PHASE_A_K) {
+        const uint32_t aa = __ffs(bits) - 1;
+        bits &= bits - 1;
+        slot[(size_t)mycnt * slot_stride] = posA + aa;
+        mycnt++;
+    }
+    // the rest: one record per (b, block of 32 a's) on the global survivor list, through the warp's staging buffer (one
+    // atomic per STAGE_CAP records and coalesced 16-byte stores)
+    const uint32_t have = __ballot_sync(0xFFFFFFFFu, bits != 0);
+    if (have) {
+        mycnt += __popc(bits);
+        const uint32_t totalc = __popc(have);
+        if (fill + totalc > STAGE_CAP) sweep_flush(cx, stage, fill);
+        if (bits) stage[fill + __popc(have & ((1u << lane) - 1u))] = make_uint4(posA, posB, bits, 0u);
+        fill += totalc;
+    }
+}
+
 template <int W>
 __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restrict__ sA, uint32_t rowsA, bool diag, uint32_t cdmax,
                                           const uint32_t (&bH)[W], const uint32_t (&bL)[W], bool validB, uint32_t posA0, uint32_t posB,
                                           uint32_t &mycnt, uint4 *stage, uint32_t &fill, uint32_t *slot, uint32_t slot_stride) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tid = threadIdx.x;
     if (!__any_sync(0xFFFFFFFFu, validB)) return;          // a warp beyond the end of a short B tile
     for (uint32_t a0 = 0; a0 < rowsA; a0 += 32) {
         // on the diagonal tile only a < b counts: a warp whose b's all precede this block is done
@@ -1633,26 +1671,7 @@ __device__ __forceinline__ void row_sweep(SweepCtx &cx, const uint32_t *__restri
             if (tid <= a0) bits = 0;
             else if (tid - a0 < 32) bits &= (1u << (tid - a0)) - 1u;
         }
-        const uint32_t col = __reduce_or_sync(0xFFFFFFFFu, bits);      // a's with a survivor partner in this warp
-        if (!col) continue;
-        if ((col >> lane) & 1u) cx.needed[posA0 + a0 + lane] = 1;
-        // the first PHASE_A_K survivors of b, in ascending a, go to its slot array
-        while (bits && mycnt < PHASE_A_K) {
-            const uint32_t aa = __ffs(bits) - 1;
-            bits &= bits - 1;
-            slot[(size_t)mycnt * slot_stride] = posA0 + a0 + aa;
-            mycnt++;
-        }
-        // the rest: one record per (b, block of 32 a's) on the global survivor list, through the warp's staging buffer (one
-        // atomic per SWEEP_STAGE records and coalesced 16-byte stores)
-        const uint32_t have = __ballot_sync(0xFFFFFFFFu, bits != 0);
-        if (have) {
-            mycnt += __popc(bits);
-            const uint32_t totalc = __popc(have);
-            if (fill + totalc > SWEEP_STAGE) sweep_flush(cx, stage, fill);
-            if (bits) stage[fill + __popc(have & ((1u << lane) - 1u))] = make_uint4(posA0 + a0, posB, bits, 0u);
-            fill += totalc;
-        }
+        sweep_emit<SWEEP_STAGE>(cx, bits, posA0 + a0, posB, mycnt, stage, fill, slot, slot_stride);
     }
 }
 
@@ -1729,6 +1748,7 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ 
         if (w >= nitems) break;
         const uint2 it = order[w];             // longest items first (k_item_scatter)
         const GroupInfo g = groups[it.x];
+        if (g.mma != MMA_NONE) continue;       // k_sweep_mma's
         const uint32_t q = it.y >> 16, ib = it.y & 0xFFFFu;
         switch (g.W) {
             case 1: row_item<1>(cx, g, ib, q, c3, sA, bar, parity, stage, fill); break;
@@ -1742,6 +1762,216 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ 
         }
     }
     sweep_flush(cx, stage, fill);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tier 1 on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) for large groups of short CDR3s.
+// A base becomes a vertex of the regular tetrahedron in {+1,-1}^3 — v_g . v_h = 3 if g == h, -1 otherwise — so for two rows of one
+// group (T bases each)  dot = 3 (T - d) - d = 3T - 4d  and  d <= cdmax  <=>  dot >= 3T - 4 cdmax,  exact in s32.  The CTA keeps
+// the B tile (128 entries = the M rows of the MMA) in shared memory and sweeps the A tiles of the work item (128 entries = the N
+// columns) exactly as k_sweep does; the tiles arrive by 1-D bulk TMA copies in the image the MMA wants (K-major, no swizzle: [K/16][128
+// rows][16 bytes]; descriptor LBO = 2048 B between the two 16-byte K chunks of one instruction, SBO = 128 B between groups of 8
+// rows), one thread issues the K/32 instructions of a tile pair and commits them to an mbarrier, two accumulator buffers of 128 TMEM
+// columns let the MMA of tile i+1 run under the epilogue of tile i, and the epilogue (tcgen05.ld 32x32b.x32) hands thread b = TMEM
+// lane the dot products of 32 consecutive a's: the 32-bit survivor mask of (b, block of 32 a's) that sweep_emit takes.
+// tools/micro/hamming_mma.cu is the stand-alone prototype of this kernel (same instructions, checked against a popcount kernel).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// shared-memory matrix descriptor, K-major, no swizzle: start address, leading (K chunk) and stride (8-row group) byte offsets in 16-byte
+// units, descriptor version 1 (Blackwell), layout type 0
+__device__ __forceinline__ unsigned long long umma_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, unsigned long long da, unsigned long long db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                   "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+
+// int8 rows of the tensor-core groups from their c3 rows: one thread per sorted entry, 16-byte stores (32 consecutive entries write 512
+// contiguous bytes of one K chunk).  Positions behind the group's base count stay zero.
+__global__ void __launch_bounds__(256) k_pack_i8(const uint32_t *__restrict__ c3, const uint32_t *__restrict__ gid_incl, const GroupInfo *__restrict__ groups,
+                                                 const DevCounters *ctr, int8_t *__restrict__ tiles) {
+    if (ctr->i8_tiles == 0) return;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= (uint32_t)ctr->n_valid) return;
+    const GroupInfo g = groups[gid_incl[s] - 1];
+    if (g.mma == MMA_NONE) return;
+    const uint32_t total = g.mma >> 23, slot0 = g.mma & 0x7FFFFFu, W = g.W;
+    const uint32_t rel = s - g.start, ib = rel / T1_TILE, row = rel % T1_TILE;
+    const uint32_t *rp = c3 + g.c3base + (size_t)rel * 2 * W;
+    uint32_t H[3], L[3];
+#pragma unroll
+    for (int w = 0; w < 3; w++) { H[w] = w < (int)W ? rp[w] : 0u; L[w] = w < (int)W ? rp[W + w] : 0u; }
+    int8_t *dst = tiles + (size_t)(slot0 + ib) * MMA_TILE_BYTES + (size_t)row * 16;
+    const uint32_t chunks = (3 * total + 31) / 32 * 2;
+    for (uint32_t j = 0; j < chunks; j++) {
+        uint32_t v[4] = { 0, 0, 0, 0 };
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const uint32_t k = j * 16 + q, p = k / 3, c = k - 3 * p;
+            uint32_t x = 0;
+            if (p < total) {
+                const uint32_t code = (((H[p >> 5] >> (p & 31)) & 1u) << 1) | ((L[p >> 5] >> (p & 31)) & 1u);
+                // codes 0..3 -> (1,1,1) (1,-1,-1) (-1,1,-1) (-1,-1,1)
+                const bool neg = (code == 1 && c != 0) || (code == 2 && c != 1) || (code == 3 && c != 2);
+                x = neg ? 0xFFu : 0x01u;
+            }
+            v[q >> 2] |= x << (8 * (q & 3));
+        }
+        *reinterpret_cast<uint4 *>(dst + (size_t)j * T1_TILE * 16) = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+#define MMA_STAGE 32u          // survivor records staged per warp (shared memory is the tiles')
+__global__ void __launch_bounds__(T1_TILE) k_sweep_mma(const int8_t *__restrict__ tiles, const GroupInfo *__restrict__ groups, DevCounters *ctr,
+                                                       const uint2 *__restrict__ order, uint4 *cand, unsigned long long cand_cap, uint32_t *firstk,
+                                                       uint32_t *cnt, uint32_t *xk, uint32_t *xcnt, unsigned long long xcap, uint8_t *needed) {
+    if (ctr->i8_tiles == 0) return;                       // no tensor-core group in this input
+    extern __shared__ __align__(128) uint8_t mma_smem[];  // B tile | A tile 0 | A tile 1
+    __shared__ __align__(8) uint64_t bar_full[2], bar_done[2], bar_b;
+    __shared__ uint32_t s_tmem, s_item;
+    __shared__ uint4 s_stage[T1_TILE / 32][MMA_STAGE];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    uint8_t *sB = mma_smem, *sA0 = mma_smem + MMA_TILE_BYTES, *sA1 = mma_smem + 2 * MMA_TILE_BYTES;
+    uint4 *stage = s_stage[warp];
+    uint32_t fill = 0;
+    if (tid == 0) { mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1); mbar_init(&bar_b, 1); fence_barrier_init(); }
+    if (warp == 0) {                                      // two accumulator buffers of 128 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    // instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8 bit (bits 7-9, 10-12 = 1), both K-major, N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t ph_full = 0, ph_done = 0, ph_b = 0;          // bit s = phase of the barrier of buffer s
+    SweepCtx cx;
+    cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap; cx.firstk = firstk; cx.cnt = cnt; cx.xk = xk; cx.xcnt = xcnt; cx.xcap = xcap;
+    cx.needed = needed;
+    const unsigned long long nitems = ctr->n_items;
+    for (;;) {
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&ctr->work_next_mma, 1ull);
+        __syncthreads();
+        const unsigned long long w = s_item;
+        __syncthreads();
+        if (w >= nitems) break;
+        const uint2 it = order[w];
+        const GroupInfo g = groups[it.x];
+        if (g.mma == MMA_NONE) continue;                  // k_sweep's
+        const uint32_t q = it.y >> 16, ib = it.y & 0xFFFFu;
+        const uint32_t total = g.mma >> 23, slot0 = g.mma & 0x7FFFFFu;
+        const uint32_t ksteps = (3 * total + 31) / 32, tile_bytes = ksteps * 32 * T1_TILE;
+        const int thr = (int)(3 * total) - 4 * (int)g.cdmax;
+        const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
+        const bool validB = tid < rowsB;
+        const uint32_t posB = g.start + ib * T1_TILE + tid;
+        const uint32_t S = g.seg, ia_lo = q * S, ia_hi = min(ia_lo + S - 1, ib);
+        uint32_t *slot = cx.firstk + (size_t)posB * PHASE_A_K, slot_stride = 1;
+        unsigned long long xrow = 0;
+        bool slots_ok = true;
+        if (q) {
+            xrow = (unsigned long long)g.xoff + seg_item_off(g.tiles, S, q) + (g.tiles - 1 - ib) - g.tiles;
+            slots_ok = xrow < cx.xcap;
+            slot = cx.xk + (size_t)(slots_ok ? xrow : 0) * PHASE_A_K * T1_TILE + tid; slot_stride = T1_TILE;
+        }
+        uint32_t mycnt = 0;
+        const int8_t *gt = tiles + (size_t)slot0 * MMA_TILE_BYTES;
+        auto issue_mma = [&](uint32_t sbuf) {             // thread 0: one tile pair into accumulator buffer sbuf
+            const uint32_t a_addr = smem_u32(sB), b_addr = smem_u32(sbuf ? sA1 : sA0);
+            for (uint32_t k = 0; k < ksteps; k++)
+                umma_i8(tmem + sbuf * 128, umma_smem_desc(a_addr + k * 2 * T1_TILE * 16, T1_TILE * 16, 128),
+                        umma_smem_desc(b_addr + k * 2 * T1_TILE * 16, T1_TILE * 16, 128), idesc, k ? 1u : 0u);
+            umma_commit(&bar_done[sbuf]);
+        };
+        auto load_a = [&](uint32_t ia, uint32_t sbuf) {
+            mbar_expect_tx(&bar_full[sbuf], tile_bytes);
+            tma_load_1d(sbuf ? sA1 : sA0, gt + (size_t)ia * MMA_TILE_BYTES, tile_bytes, &bar_full[sbuf]);
+        };
+        if (slots_ok) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&bar_b, tile_bytes);
+                tma_load_1d(sB, gt + (size_t)ib * MMA_TILE_BYTES, tile_bytes, &bar_b);
+                load_a(ia_lo, 0);
+                if (ia_lo + 1 <= ia_hi) load_a(ia_lo + 1, 1);
+                mbar_wait(&bar_b, ph_b & 1u);
+                mbar_wait(&bar_full[0], ph_full & 1u); ph_full ^= 1u;
+                tc_fence_after();
+                issue_mma(0);
+            }
+            ph_b ^= 1u;
+            for (uint32_t ia = ia_lo; ia <= ia_hi; ia++) {
+                const uint32_t sbuf = (ia - ia_lo) & 1u;
+                mbar_wait(&bar_done[sbuf], (ph_done >> sbuf) & 1u);      // MMA(ia) complete: accumulator sbuf ready, smem buffer sbuf free
+                ph_done ^= 1u << sbuf;
+                tc_fence_after();
+                if (tid == 0) {
+                    if (ia + 2 <= ia_hi) { fence_proxy_async(); load_a(ia + 2, sbuf); }
+                    if (ia + 1 <= ia_hi) {
+                        mbar_wait(&bar_full[sbuf ^ 1u], (ph_full >> (sbuf ^ 1u)) & 1u); ph_full ^= 1u << (sbuf ^ 1u);
+                        tc_fence_after();
+                        issue_mma(sbuf ^ 1u);                             // runs under the epilogue below
+                    }
+                }
+                __syncwarp();
+                const bool diag = ia == ib;
+                const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
+                uint32_t nblk = (rowsA + 31) / 32;
+                if (diag) nblk = min(nblk, ((tid | 31u) >> 5) + 1u);     // warp-uniform: blocks that can hold an a < b
+                if (!__any_sync(0xFFFFFFFFu, validB)) nblk = 0;          // a warp beyond the end of a short B tile
+                uint32_t r[4][32];
+                const uint32_t trow = tmem + ((warp * 32u) << 16) + sbuf * 128;
+                if (nblk > 0) tmem_ld32_nowait(trow, r[0]);
+                if (nblk > 1) tmem_ld32_nowait(trow + 32, r[1]);
+                if (nblk > 2) tmem_ld32_nowait(trow + 64, r[2]);
+                if (nblk > 3) tmem_ld32_nowait(trow + 96, r[3]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (uint32_t blk = 0; blk < 4; blk++) {
+                    if (blk >= nblk) break;
+                    const uint32_t a0 = blk * 32;
+                    uint32_t bits = 0;
+                    // bit j = (dot >= thr): the sign bit of (thr - 1 - dot), one funnel shift per element, four independent chains of eight
+                    uint32_t part[4] = { 0, 0, 0, 0 };
+#pragma unroll
+                    for (int j = 7; j >= 0; j--)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) part[c] = __funnelshift_l((uint32_t)(thr - 1 - (int)r[blk][8 * c + j]), part[c], 1);
+                    bits = part[0] | (part[1] << 8) | (part[2] << 16) | (part[3] << 24);
+                    if (rowsA - a0 < 32) bits &= (1u << (rowsA - a0)) - 1u;
+                    if (!validB) bits = 0;
+                    if (diag) {                                           // keep a < b
+                        if (tid <= a0) bits = 0;
+                        else if (tid - a0 < 32) bits &= (1u << (tid - a0)) - 1u;
+                    }
+                    sweep_emit<MMA_STAGE>(cx, bits, g.start + ia * T1_TILE + a0, posB, mycnt, stage, fill, slot, slot_stride);
+                }
+                tc_fence_before();
+                __syncthreads();                                          // accumulator sbuf drained before MMA(ia + 2) may overwrite it
+            }
+        }
+        if (q == 0) { if (validB && mycnt) cx.cnt[posB] = mycnt; }
+        else if (slots_ok) cx.xcnt[(size_t)xrow * T1_TILE + tid] = validB ? mycnt : 0u;
+        if (validB && mycnt) cx.needed[posB] = 1;
+    }
+    sweep_flush(cx, stage, fill);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -601,3 +601,21 @@ def test_compact_input_dnastring_words(monkeypatch):
     oe, oc, _ = O.join_exacts(pack.struct, default_params(), threads=8)
     assert_same_join(g, oe, oc, what="compact, DnaString words")
     cp.close(); cp2.close()
+
+
+@pytest.mark.parametrize("name,scale,min_tiles", [("C2", 0.3, 1), ("C3", 0.03, 1), ("C4", 0.06, 1), ("C4", 0.06, 3), ("C5", 0.05, 1)])
+def test_tensor_core_sweep_equals_popcount_sweep_and_oracle(monkeypatch, name, scale, min_tiles):
+    """Tier 1 on the tensor cores (k_sweep_mma: int8 tetrahedron rows, tcgen05.mma, survivor masks read back from TMEM) forced onto every
+    group it can take — from one partial tile up, diagonal tiles, several segments, groups mixed with popcount-swept ones — against
+    the popcount sweep (tensor-core path off) and the oracle: identical joins, payloads and partition, identical survivor counts."""
+    pack, _ = synth.generate_config(name, scale)
+    monkeypatch.setenv("EJOIN_MMA_MIN_TILES", "0")
+    ref = join_exacts(pack)
+    monkeypatch.setenv("EJOIN_MMA_MIN_TILES", str(min_tiles))
+    monkeypatch.setenv("EJOIN_MMA_CAP_TILES", "20000" if name != "C5" else "40")       # C5: most groups find no slot and stay with the popcount sweep
+    got = join_exacts(pack)
+    assert np.array_equal(ref.edges, got.edges) and np.array_equal(ref.class_of, got.class_of)
+    for k in ("pairs_candidate", "pairs_compared", "pairs_tier2"):
+        assert ref.stats[k] == got.stats[k], k
+    oe, oc, ost = O.join_exacts(pack.struct, default_params(), threads=8)
+    assert_same_join(got, oe, oc, what=f"{name} mma>={min_tiles}")
