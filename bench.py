@@ -521,6 +521,18 @@ def main():
                                               "note": "2 x 8W bytes per compared pair as if streamed: rows are staged in shared memory by TMA and reused ~n_group "
                                                       "times on chip, so this exceeds the HBM peak; it only shows HBM is not the binding roof"},
                            "note": "all-pairs CDR3 XOR/popcount; ncu: XU pipe 75 %, ALU 71 %, issue slots 66 % busy, DRAM 2 % (profiles/r02z_ncu_metrics.json)"}
+    if stages.get("k_sweep_mma") and st.get("mma_macs"):
+        # the large groups of short CDR3s: tier 1 as an int8 contraction on the tensor cores (tcgen05.mma kind::i8).  MEASURED_PEAKS.json has
+        # no int8 figure: the roof used is twice its measured dense bf16 rate (the int8 : bf16 ratio of the B200 tensor cores)
+        t = stages["k_sweep_mma"] * 1e-3
+        peak_i8 = 2.0 * float(peaks.get("bf16_tflops", 1655.3))
+        tops = 2.0 * st["mma_macs"] / t / 1e12
+        cand["k_sweep_mma"] = {"bound": "tensor", "kernel": "k_sweep_mma", "achieved": tops, "peak": peak_i8, "unit": "TOP/s (int8, dense)", "frac": tops / peak_i8,
+                               "algorithmic_ops_per_launch": 2.0 * st["mma_macs"], "kernel_ms": stages["k_sweep_mma"], "pairs": int(st["mma_pairs"]),
+                               "pairs_per_s": st["mma_pairs"] / t,
+                               "note": "CDR3 Hamming distance as an int8 contraction: 3 values in {+1,-1} per base (tetrahedron vertices), dot = 3L - 4d, exact in s32; "
+                                       "128 x 128 x K tile pairs by tcgen05.mma.cta_group::1.kind::i8 into TMEM, survivor masks read back with tcgen05.ld; "
+                                       "the time does not depend on K (DESIGN.md 13): the epilogue's 128 compares per thread and tile pair bound it, not the MMA"}
     if stages.get("k_pack_t2"):
         t = stages["k_pack_t2"] * 1e-3
         cand["k_pack_t2"] = {"bound": "hbm", "kernel": "k_pack_t2_2bit (+ k_pack_t2 for the entries with an ASCII chain)", "achieved": st["alg_bytes_pack_t2"] / t / 1e9,
@@ -531,7 +543,8 @@ def main():
     dom = max(cand, key=lambda k2: cand[k2]["kernel_ms"]) if cand else None
     roofline = dict(cand[dom]) if dom else {"bound": "hbm", "achieved": 0.0, "peak": peak_hbm, "unit": "GB/s", "frac": None}
     roofline["peak_source"] = ("MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)") if roofline["bound"] == "hbm" \
-        else "16 POPC lanes per SM and clock x 148 SMs x the SM clock sampled under load"
+        else ("2 x MEASURED_PEAKS.json bf16_tflops (burst): int8 dense runs at twice the bf16 rate" if roofline["bound"] == "tensor"
+              else "16 POPC lanes per SM and clock x 148 SMs x the SM clock sampled under load")
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))

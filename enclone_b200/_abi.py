@@ -105,7 +105,7 @@ class EjoinStats(C.Structure):
         (n, C.c_double) for n in (
             "ms_h2d", "ms_device", "ms_d2h", "ms_host_post", "ms_total",
             "ms_kernel_tier1", "ms_kernel_tier2", "ms_kernel_pack", "ms_kernel_other")] + [
-        ("alg_bytes_pack_t2", C.c_uint64), ("ms_kernel_pack_t2", C.c_double)]
+        ("alg_bytes_pack_t2", C.c_uint64), ("ms_kernel_pack_t2", C.c_double), ("mma_pairs", C.c_uint64), ("mma_macs", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -968,9 +968,10 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_occ, k_sweep, T1_TILE, 0);
         if (rows_occ < 1) rows_occ = 1;
         k_sweep<<<h->sm_count * rows_occ, T1_TILE, 0, st>>>(c3, groups, ctr, order, cand, ccap, firstk, surv_cnt, xk, xcnt, xcap, needed);
+        mark(h, "k_sweep");
         if (mma_min_tiles) {
             // the large groups of short CDR3s on the tensor cores (the kernel returns at once when the group table flagged none)
-            const size_t mma_smem = 3 * (size_t)MMA_TILE_BYTES;
+            const size_t mma_smem = (1 + MMA_NA) * (size_t)MMA_TILE_BYTES;
             if (h->mma_grid == 0) {
                 CK(cudaFuncSetAttribute(k_sweep_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem));
                 CK(cudaFuncSetAttribute(k_sweep_mma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -979,11 +980,11 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
                 // would only find the work list empty.)
                 h->mma_grid = h->sm_count * 2;
             }
-            k_sweep_mma<<<h->mma_grid, T1_TILE, mma_smem, st>>>(i8_tiles, groups, ctr, order, cand, ccap, firstk, surv_cnt, xk, xcnt, xcap, needed);
+            k_sweep_mma<<<h->mma_grid, MMA_THREADS, mma_smem, st>>>(i8_tiles, groups, ctr, order, cand, ccap, firstk, surv_cnt, xk, xcnt, xcap, needed);
             h->launches += 1;
         }
         CK(cudaEventRecord(h->ev[3], st));
-        mark(h, "k_sweep");
+        mark(h, "k_sweep_mma");
         if (h->copy_pending) CK(cudaStreamWaitEvent(st, h->ev_small, 0));          // the late arrays (ids, offsets, bounds, germlines)
         if (h->recs_pending) {
             k_unpack_recs<<<nb256, 256, 0, st>>>(h->d_rec, n, h->rec_out);
@@ -1145,7 +1146,7 @@ void fill_stats(ejoin_handle *h, ejoin_stats_t *s) {
     s->pairs_tier2 = c.pairs_tier2; s->pairs_accepted = c.n_accept; s->pairs_generic = c.n_generic; s->edges_after_prune = c.n_kept;
     s->gpu_launches = h->launches; s->h2d_bytes = h->h2d_bytes;
     if (h->tigs_in_place) { unsigned long long ib = 0; for (int i = 0; i < 32; i++) ib += c.inplace_bytes[i]; s->h2d_bytes += ib; }   // bytes k_pack_t2 pulled over PCIe
-    s->alg_bytes_tier1 = c.t1_alg_bytes; s->alg_bytes_tier2 = c.t2_alg_bytes;
+    s->alg_bytes_tier1 = c.t1_alg_bytes; s->alg_bytes_tier2 = c.t2_alg_bytes; s->mma_pairs = c.mma_pairs; s->mma_macs = c.mma_macs;
     { unsigned long long pb = 0; for (int i = 0; i < 32; i++) pb += c.pack_bytes[i]; s->alg_bytes_pack_t2 = pb; }
     s->ms_kernel_pack_t2 = h->stats.ms_kernel_pack_t2;
     s->alg_bytes_pack = h->tig_bytes + c.n_valid * sizeof(EntryMeta) + c.c3_words * 4 + c.t2_units * 16;

@@ -68,7 +68,7 @@ static_assert(sizeof(EntryMeta) == 128, "EntryMeta must be 128 bytes");
 #define MMA_MAX_BASES 96u
 #define MMA_KMAX 288u                               // 3 * MMA_MAX_BASES, a multiple of 32
 #define MMA_TILE_BYTES (T1_TILE * MMA_KMAX)         // [K/16 chunks][128 rows][16 bytes]; a group with fewer bases uses a prefix
-#define MMA_MIN_TILES_DEFAULT 16u
+#define MMA_MIN_TILES_DEFAULT 128u                     // 16,384 entries: below that the int8 pack and the second kernel cost more than the popcount sweep of the group (C3: +0.15 ms with 16)
 #define SEG_QMAX 32u         // at most this many segments per row
 struct GroupInfo {           // one comparison group = one run of equal sort keys
     uint32_t start;          // first sorted position
@@ -105,6 +105,7 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned int cls_count[64], cls_cursor[64];   // counting sort of the work items by cost class
     unsigned long long work_next_mma;               // k_sweep_mma's own cursor over the same item list
     unsigned int i8_tiles, pad2;                    // int8 tile slots handed to tensor-core groups (k_group_build)
+    unsigned long long mma_pairs, mma_macs;         // pairs of the tensor-core groups; int8 multiply-accumulates their tile pairs stand for
 };
 
 struct DevParams {           // ejoin_params_t plus run constants, by value to kernels

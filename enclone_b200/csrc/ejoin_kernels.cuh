@@ -149,7 +149,12 @@ __global__ void __launch_bounds__(256) k_group_build(const unsigned long long *_
             const uint32_t total = (uint32_t)((uniq[r] >> 8) & 0xFF) + (uint32_t)(uniq[r] & 0xFF);
             if (mma_min_tiles && gv.T >= mma_min_tiles && gv.T <= 65535u && total >= 1 && total <= MMA_MAX_BASES && g.n >= 2 && gv.cdm != 0xFFFF && 3 * total > 4 * gv.cdm) {
                 const uint32_t slot = atomicAdd(&ctr->i8_tiles, gv.T);
-                if ((unsigned long long)slot + gv.T <= i8_cap_tiles && slot + gv.T < (1u << 23)) g.mma = (total << 23) | slot;
+                if ((unsigned long long)slot + gv.T <= i8_cap_tiles && slot + gv.T < (1u << 23)) {
+                    g.mma = (total << 23) | slot;
+                    atomicAdd(&ctr->mma_pairs, gv.v[3]);
+                    atomicAdd(&ctr->mma_macs, (unsigned long long)gv.T * (gv.T + 1) / 2 * T1_TILE * T1_TILE * ((3 * total + 31) / 32 * 32));
+                    atomicAdd(&ctr->t1_alg_bytes, 0ull - gv.v[4]);            // not popcount work (k_group_vals counted every group)
+                }
             }
         }
         groups[r] = g;               // valid runs precede the ~0 run, so r is the group id
@@ -1835,21 +1840,54 @@ __global__ void __launch_bounds__(256) k_pack_i8(const uint32_t *__restrict__ c3
 }
 
 #define MMA_STAGE 32u          // survivor records staged per warp (shared memory is the tiles')
-__global__ void __launch_bounds__(T1_TILE) k_sweep_mma(const int8_t *__restrict__ tiles, const GroupInfo *__restrict__ groups, DevCounters *ctr,
-                                                       const uint2 *__restrict__ order, uint4 *cand, unsigned long long cand_cap, uint32_t *firstk,
-                                                       uint32_t *cnt, uint32_t *xk, uint32_t *xcnt, unsigned long long xcap, uint8_t *needed) {
+#define MMA_THREADS 192u       // warps 0-3: epilogue (thread = row b); warp 4 lane 0: MMA issuer; warp 5 lane 0: TMA producer
+#define MMA_NA 2u              // shared-memory stages of A tiles
+#define MMA_NACC 2u            // accumulator stages in TMEM (128 columns each)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+// The three roles walk the same sequence of work items (the cost-sorted list dealt round-robin to the CTAs, the popcount groups' items
+// skipped) and of A tiles inside an item, each with its own running tile counter t: stage t % MMA_NA of shared memory, accumulator
+// t % MMA_NACC, barrier phase (t / stages) & 1.  Producer: waits until the MMAs that read a stage are complete (bar_sfree), loads the
+// next A tile into it.  Issuer: waits for the tile (bar_full) and for the epilogue to have read the accumulator (bar_empty), issues the
+// K/32 instructions, commits to bar_sfree and bar_done — it never waits for an MMA to finish, so the next tile pair queues behind the
+// running one.  Epilogue: waits bar_done, loads its 128 dot products from TMEM, releases the accumulator (bar_empty, one arrival per
+// warp) and only then turns them into survivor masks.
+struct MmaItem {
+    GroupInfo g; uint32_t q, ib, total, slot0, ksteps, tile_bytes, ia_lo, ia_hi; unsigned long long xrow; bool slots_ok;
+};
+__device__ __forceinline__ bool mma_item(const GroupInfo *__restrict__ groups, const uint2 *__restrict__ order, unsigned long long w, unsigned long long xcap, MmaItem &m) {
+    const uint2 it = order[w];
+    m.g = groups[it.x];
+    if (m.g.mma == MMA_NONE) return false;                // k_sweep's
+    m.q = it.y >> 16; m.ib = it.y & 0xFFFFu;
+    m.total = m.g.mma >> 23; m.slot0 = m.g.mma & 0x7FFFFFu;
+    m.ksteps = (3 * m.total + 31) / 32; m.tile_bytes = m.ksteps * 32 * T1_TILE;
+    const uint32_t S = m.g.seg;
+    m.ia_lo = m.q * S; m.ia_hi = min(m.ia_lo + S - 1, m.ib);
+    m.xrow = 0; m.slots_ok = true;
+    if (m.q) {
+        m.xrow = (unsigned long long)m.g.xoff + seg_item_off(m.g.tiles, S, m.q) + (m.g.tiles - 1 - m.ib) - m.g.tiles;
+        m.slots_ok = m.xrow < xcap;                       // too small: the host sees n_xrows > cap and retries (every role skips the item)
+    }
+    return m.slots_ok;
+}
+__global__ void __launch_bounds__(MMA_THREADS, 2) k_sweep_mma(const int8_t *__restrict__ tiles, const GroupInfo *__restrict__ groups, DevCounters *ctr,
+                                                           const uint2 *__restrict__ order, uint4 *cand, unsigned long long cand_cap, uint32_t *firstk,
+                                                           uint32_t *cnt, uint32_t *xk, uint32_t *xcnt, unsigned long long xcap, uint8_t *needed) {
     if (ctr->i8_tiles == 0) return;                       // no tensor-core group in this input
-    extern __shared__ __align__(128) uint8_t mma_smem[];  // B tile | A tile 0 | A tile 1
-    __shared__ __align__(8) uint64_t bar_full[2], bar_done[2], bar_b;
-    __shared__ uint32_t s_tmem, s_item;
+    extern __shared__ __align__(128) uint8_t mma_smem[];  // B tile | A stages
+    __shared__ __align__(8) uint64_t bar_full[MMA_NA], bar_sfree[MMA_NA], bar_done[MMA_NACC], bar_empty[MMA_NACC], bar_bfull, bar_bfree;
+    __shared__ uint32_t s_tmem;
     __shared__ uint4 s_stage[T1_TILE / 32][MMA_STAGE];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    uint8_t *sB = mma_smem, *sA0 = mma_smem + MMA_TILE_BYTES, *sA1 = mma_smem + 2 * MMA_TILE_BYTES;
-    uint4 *stage = s_stage[warp];
-    uint32_t fill = 0;
-    if (tid == 0) { mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1); mbar_init(&bar_b, 1); fence_barrier_init(); }
-    if (warp == 0) {                                      // two accumulator buffers of 128 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u) : "memory");
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *sB = mma_smem;
+    if (tid == 0) {
+        for (uint32_t i = 0; i < MMA_NA; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_sfree[i], 1); }
+        for (uint32_t i = 0; i < MMA_NACC; i++) { mbar_init(&bar_done[i], 1); mbar_init(&bar_empty[i], T1_TILE / 32); }
+        mbar_init(&bar_bfull, 1); mbar_init(&bar_bfree, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(MMA_NACC * 128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -1858,100 +1896,97 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep_mma(const int8_t *__restrict_
     const uint32_t tmem = s_tmem;
     // instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8 bit (bits 7-9, 10-12 = 1), both K-major, N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-    uint32_t ph_full = 0, ph_done = 0, ph_b = 0;          // bit s = phase of the barrier of buffer s
-    SweepCtx cx;
-    cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap; cx.firstk = firstk; cx.cnt = cnt; cx.xk = xk; cx.xcnt = xcnt; cx.xcap = xcap;
-    cx.needed = needed;
     const unsigned long long nitems = ctr->n_items;
-    for (;;) {
-        if (tid == 0) s_item = (uint32_t)atomicAdd(&ctr->work_next_mma, 1ull);
-        __syncthreads();
-        const unsigned long long w = s_item;
-        __syncthreads();
-        if (w >= nitems) break;
-        const uint2 it = order[w];
-        const GroupInfo g = groups[it.x];
-        if (g.mma == MMA_NONE) continue;                  // k_sweep's
-        const uint32_t q = it.y >> 16, ib = it.y & 0xFFFFu;
-        const uint32_t total = g.mma >> 23, slot0 = g.mma & 0x7FFFFFu;
-        const uint32_t ksteps = (3 * total + 31) / 32, tile_bytes = ksteps * 32 * T1_TILE;
-        const int thr = (int)(3 * total) - 4 * (int)g.cdmax;
-        const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - ib * T1_TILE);
-        const bool validB = tid < rowsB;
-        const uint32_t posB = g.start + ib * T1_TILE + tid;
-        const uint32_t S = g.seg, ia_lo = q * S, ia_hi = min(ia_lo + S - 1, ib);
-        uint32_t *slot = cx.firstk + (size_t)posB * PHASE_A_K, slot_stride = 1;
-        unsigned long long xrow = 0;
-        bool slots_ok = true;
-        if (q) {
-            xrow = (unsigned long long)g.xoff + seg_item_off(g.tiles, S, q) + (g.tiles - 1 - ib) - g.tiles;
-            slots_ok = xrow < cx.xcap;
-            slot = cx.xk + (size_t)(slots_ok ? xrow : 0) * PHASE_A_K * T1_TILE + tid; slot_stride = T1_TILE;
-        }
-        uint32_t mycnt = 0;
-        const int8_t *gt = tiles + (size_t)slot0 * MMA_TILE_BYTES;
-        auto issue_mma = [&](uint32_t sbuf) {             // thread 0: one tile pair into accumulator buffer sbuf
-            const uint32_t a_addr = smem_u32(sB), b_addr = smem_u32(sbuf ? sA1 : sA0);
-            for (uint32_t k = 0; k < ksteps; k++)
-                umma_i8(tmem + sbuf * 128, umma_smem_desc(a_addr + k * 2 * T1_TILE * 16, T1_TILE * 16, 128),
-                        umma_smem_desc(b_addr + k * 2 * T1_TILE * 16, T1_TILE * 16, 128), idesc, k ? 1u : 0u);
-            umma_commit(&bar_done[sbuf]);
-        };
-        auto load_a = [&](uint32_t ia, uint32_t sbuf) {
-            mbar_expect_tx(&bar_full[sbuf], tile_bytes);
-            tma_load_1d(sbuf ? sA1 : sA0, gt + (size_t)ia * MMA_TILE_BYTES, tile_bytes, &bar_full[sbuf]);
-        };
-        if (slots_ok) {
-            if (tid == 0) {
+    MmaItem m;
+    if (warp == 5) {                                      // ---- TMA producer ----
+        if (lane == 0) {
+            uint32_t t = 0, item_no = 0;
+            for (unsigned long long w = blockIdx.x; w < nitems; w += gridDim.x) {
+                if (!mma_item(groups, order, w, xcap, m)) continue;
+                const int8_t *gt = tiles + (size_t)m.slot0 * MMA_TILE_BYTES;
+                mbar_wait(&bar_bfree, (item_no & 1u) ^ 1u);             // the MMAs of the previous item are done with the B tile
                 fence_proxy_async();
-                mbar_expect_tx(&bar_b, tile_bytes);
-                tma_load_1d(sB, gt + (size_t)ib * MMA_TILE_BYTES, tile_bytes, &bar_b);
-                load_a(ia_lo, 0);
-                if (ia_lo + 1 <= ia_hi) load_a(ia_lo + 1, 1);
-                mbar_wait(&bar_b, ph_b & 1u);
-                mbar_wait(&bar_full[0], ph_full & 1u); ph_full ^= 1u;
-                tc_fence_after();
-                issue_mma(0);
-            }
-            ph_b ^= 1u;
-            for (uint32_t ia = ia_lo; ia <= ia_hi; ia++) {
-                const uint32_t sbuf = (ia - ia_lo) & 1u;
-                mbar_wait(&bar_done[sbuf], (ph_done >> sbuf) & 1u);      // MMA(ia) complete: accumulator sbuf ready, smem buffer sbuf free
-                ph_done ^= 1u << sbuf;
-                tc_fence_after();
-                if (tid == 0) {
-                    if (ia + 2 <= ia_hi) { fence_proxy_async(); load_a(ia + 2, sbuf); }
-                    if (ia + 1 <= ia_hi) {
-                        mbar_wait(&bar_full[sbuf ^ 1u], (ph_full >> (sbuf ^ 1u)) & 1u); ph_full ^= 1u << (sbuf ^ 1u);
-                        tc_fence_after();
-                        issue_mma(sbuf ^ 1u);                             // runs under the epilogue below
-                    }
+                mbar_expect_tx(&bar_bfull, m.tile_bytes);
+                tma_load_1d(sB, gt + (size_t)m.ib * MMA_TILE_BYTES, m.tile_bytes, &bar_bfull);
+                for (uint32_t ia = m.ia_lo; ia <= m.ia_hi; ia++, t++) {
+                    const uint32_t st = t % MMA_NA;
+                    mbar_wait(&bar_sfree[st], ((t / MMA_NA) & 1u) ^ 1u);
+                    mbar_expect_tx(&bar_full[st], m.tile_bytes);
+                    tma_load_1d(mma_smem + (size_t)(1 + st) * MMA_TILE_BYTES, gt + (size_t)ia * MMA_TILE_BYTES, m.tile_bytes, &bar_full[st]);
                 }
-                __syncwarp();
-                const bool diag = ia == ib;
+                item_no++;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4) {                               // ---- MMA issuer ----
+        if (lane == 0) {
+            uint32_t t = 0, item_no = 0;
+            for (unsigned long long w = blockIdx.x; w < nitems; w += gridDim.x) {
+                if (!mma_item(groups, order, w, xcap, m)) continue;
+                mbar_wait(&bar_bfull, item_no & 1u);
+                for (uint32_t ia = m.ia_lo; ia <= m.ia_hi; ia++, t++) {
+                    const uint32_t st = t % MMA_NA, ac = t % MMA_NACC;
+                    mbar_wait(&bar_full[st], (t / MMA_NA) & 1u);
+                    mbar_wait(&bar_empty[ac], ((t / MMA_NACC) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sB), b_addr = smem_u32(mma_smem + (size_t)(1 + st) * MMA_TILE_BYTES);
+                    for (uint32_t k = 0; k < m.ksteps; k++)
+                        umma_i8(tmem + ac * 128, umma_smem_desc(a_addr + k * 2 * T1_TILE * 16, T1_TILE * 16, 128),
+                                umma_smem_desc(b_addr + k * 2 * T1_TILE * 16, T1_TILE * 16, 128), idesc, k ? 1u : 0u);
+                    umma_commit(&bar_sfree[st]);
+                    umma_commit(&bar_done[ac]);
+                }
+                umma_commit(&bar_bfree);
+                item_no++;
+            }
+        }
+        __syncwarp();
+    } else {                                              // ---- epilogue: thread = entry b of the B tile = TMEM lane ----
+        uint4 *stage = s_stage[warp];
+        uint32_t fill = 0, t = 0;
+        SweepCtx cx;
+        cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap; cx.firstk = firstk; cx.cnt = cnt; cx.xk = xk; cx.xcnt = xcnt; cx.xcap = xcap;
+        cx.needed = needed;
+        for (unsigned long long w = blockIdx.x; w < nitems; w += gridDim.x) {
+            if (!mma_item(groups, order, w, xcap, m)) continue;
+            const GroupInfo &g = m.g;
+            const int thr = (int)(3 * m.total) - 4 * (int)g.cdmax;
+            const uint32_t rowsB = min((uint32_t)T1_TILE, g.n - m.ib * T1_TILE);
+            const bool validB = tid < rowsB;
+            const uint32_t posB = g.start + m.ib * T1_TILE + tid;
+            uint32_t *slot = cx.firstk + (size_t)posB * PHASE_A_K, slot_stride = 1;
+            if (m.q) { slot = cx.xk + (size_t)m.xrow * PHASE_A_K * T1_TILE + tid; slot_stride = T1_TILE; }
+            uint32_t mycnt = 0;
+            for (uint32_t ia = m.ia_lo; ia <= m.ia_hi; ia++, t++) {
+                const uint32_t ac = t % MMA_NACC;
+                mbar_wait(&bar_done[ac], (t / MMA_NACC) & 1u);
+                tc_fence_after();
+                const bool diag = ia == m.ib;
                 const uint32_t rowsA = min((uint32_t)T1_TILE, g.n - ia * T1_TILE);
                 uint32_t nblk = (rowsA + 31) / 32;
                 if (diag) nblk = min(nblk, ((tid | 31u) >> 5) + 1u);     // warp-uniform: blocks that can hold an a < b
                 if (!__any_sync(0xFFFFFFFFu, validB)) nblk = 0;          // a warp beyond the end of a short B tile
                 uint32_t r[4][32];
-                const uint32_t trow = tmem + ((warp * 32u) << 16) + sbuf * 128;
+                const uint32_t trow = tmem + ((warp * 32u) << 16) + ac * 128;
                 if (nblk > 0) tmem_ld32_nowait(trow, r[0]);
                 if (nblk > 1) tmem_ld32_nowait(trow + 32, r[1]);
                 if (nblk > 2) tmem_ld32_nowait(trow + 64, r[2]);
                 if (nblk > 3) tmem_ld32_nowait(trow + 96, r[3]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[ac]);              // this warp has its 32 rows of the accumulator in registers
 #pragma unroll
                 for (uint32_t blk = 0; blk < 4; blk++) {
                     if (blk >= nblk) break;
                     const uint32_t a0 = blk * 32;
-                    uint32_t bits = 0;
                     // bit j = (dot >= thr): the sign bit of (thr - 1 - dot), one funnel shift per element, four independent chains of eight
                     uint32_t part[4] = { 0, 0, 0, 0 };
 #pragma unroll
                     for (int j = 7; j >= 0; j--)
 #pragma unroll
                         for (int c = 0; c < 4; c++) part[c] = __funnelshift_l((uint32_t)(thr - 1 - (int)r[blk][8 * c + j]), part[c], 1);
-                    bits = part[0] | (part[1] << 8) | (part[2] << 16) | (part[3] << 24);
+                    uint32_t bits = part[0] | (part[1] << 8) | (part[2] << 16) | (part[3] << 24);
                     if (rowsA - a0 < 32) bits &= (1u << (rowsA - a0)) - 1u;
                     if (!validB) bits = 0;
                     if (diag) {                                           // keep a < b
@@ -1960,18 +1995,16 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep_mma(const int8_t *__restrict_
                     }
                     sweep_emit<MMA_STAGE>(cx, bits, g.start + ia * T1_TILE + a0, posB, mycnt, stage, fill, slot, slot_stride);
                 }
-                tc_fence_before();
-                __syncthreads();                                          // accumulator sbuf drained before MMA(ia + 2) may overwrite it
             }
+            if (m.q == 0) { if (validB && mycnt) cx.cnt[posB] = mycnt; }
+            else cx.xcnt[(size_t)m.xrow * T1_TILE + tid] = validB ? mycnt : 0u;
+            if (validB && mycnt) cx.needed[posB] = 1;
         }
-        if (q == 0) { if (validB && mycnt) cx.cnt[posB] = mycnt; }
-        else if (slots_ok) cx.xcnt[(size_t)xrow * T1_TILE + tid] = validB ? mycnt : 0u;
-        if (validB && mycnt) cx.needed[posB] = 1;
+        sweep_flush(cx, stage, fill);
     }
-    sweep_flush(cx, stage, fill);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MMA_NACC * 128u) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

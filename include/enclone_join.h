@@ -211,6 +211,9 @@ typedef struct ejoin_stats {
     double   ms_kernel_tier1, ms_kernel_tier2, ms_kernel_pack, ms_kernel_other; /* CUDA events */
     uint64_t alg_bytes_pack_t2;  /* k_pack_t2 alone: V..J bytes read + t2 row bytes written, needed entries only */
     double   ms_kernel_pack_t2;  /* k_pack_t2 alone (CUDA events); with a chunked or in-place upload it includes the wait for the bytes */
+    uint64_t mma_pairs;          /* of pairs_compared, the pairs of groups whose tier 1 ran on the tensor cores (k_sweep_mma): large groups whose
+                                  * two CDR3s total at most 96 bases; alg_bytes_tier1 counts the other groups only */
+    uint64_t mma_macs;           /* int8 multiply-accumulates of those groups' tile pairs (128 x 128 x K each, K = 3 * bases rounded up to 32) */
 } ejoin_stats_t;
 
 typedef struct ejoin_result {

@@ -68,7 +68,7 @@ pub struct ejoin_stats_t {
     pub d2h_bytes: u64, pub alg_bytes_tier1: u64, pub alg_bytes_tier2: u64, pub alg_bytes_pack: u64,
     pub ms_h2d: f64, pub ms_device: f64, pub ms_d2h: f64, pub ms_host_post: f64, pub ms_total: f64,
     pub ms_kernel_tier1: f64, pub ms_kernel_tier2: f64, pub ms_kernel_pack: f64, pub ms_kernel_other: f64,
-    pub alg_bytes_pack_t2: u64, pub ms_kernel_pack_t2: f64,
+    pub alg_bytes_pack_t2: u64, pub ms_kernel_pack_t2: f64, pub mma_pairs: u64, pub mma_macs: u64,
 }
 
 #[repr(C)]

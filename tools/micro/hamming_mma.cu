@@ -133,7 +133,8 @@ __global__ void k_ref_popc(const uint32_t *rows, uint32_t n, uint32_t W, uint32_
 }
 
 // The tensor-core sweep.  dynamic smem: sB [128 x K] | sA[0] | sA[1]
-__global__ void __launch_bounds__(128) k_hamming_mma(const int8_t *__restrict__ tiles, uint32_t n, uint32_t K, int thr, u64 *work_next, Tally *out) {
+// dbg: bit 0 = every A tile load fetches tile 0 again (same bytes, always L2 hits on one line set); bit 1 = skip the compares (TMEM loads kept): timing experiments only
+__global__ void __launch_bounds__(128) k_hamming_mma(const int8_t *__restrict__ tiles, uint32_t n, uint32_t K, int thr, u64 *work_next, Tally *out, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[2], bar_done[2], bar_b;
     __shared__ uint32_t s_tmem, s_item;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(128) k_hamming_mma(const int8_t *__restrict__ 
     };
     auto load_a = [&](uint32_t ia, uint32_t s) {
         mbar_expect_tx(&bar_full[s], tile_bytes);
-        tma_load_1d(s ? sA1 : sA0, tiles + (size_t)ia * tile_bytes, tile_bytes, &bar_full[s]);
+        tma_load_1d(s ? sA1 : sA0, tiles + (size_t)((dbg & 1) ? 0 : ia) * tile_bytes, tile_bytes, &bar_full[s]);
     };
 
     for (;;) {
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(128) k_hamming_mma(const int8_t *__restrict__ 
 #pragma unroll
             for (uint32_t blk = 0; blk < 4; blk++) {
                 if (blk >= nblk) break;
+                if (dbg & 2) { if (r[blk][0] == 0x7FFFFFFF) pairs++; continue; }
                 const uint32_t c0 = blk * 32;
                 uint32_t bits = 0;
                 // bit q = (dot >= thr): the sign bit of (thr - 1 - dot), shifted in by one funnel shift per element
@@ -247,11 +249,134 @@ __global__ void __launch_bounds__(128) k_hamming_mma(const int8_t *__restrict__ 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
+// Version 2: warp-specialised.  Warps 0-3 = epilogue (thread = row b), warp 4 lane 0 = MMA issuer, warp 5 lane 0 = TMA producer; NA
+// shared-memory stages for the A tiles and NACC accumulator stages in TMEM, so the issuer queues the MMAs of the next tiles
+// behind the running one instead of waiting for it (version 1 waits for MMA(i) before it issues MMA(i+1)), and the epilogue
+// frees an accumulator as soon as it has read it.  Items (B tiles) are dealt round-robin, longest first; every role walks the
+// same item sequence with its own stage counter.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+template <uint32_t NA, uint32_t NACC>
+__global__ void __launch_bounds__(192) k_hamming_mma2(const int8_t *__restrict__ tiles, uint32_t n, uint32_t K, int thr, Tally *out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[NA], bar_sfree[NA], bar_done[NACC], bar_empty[NACC], bar_bfull, bar_bfree;
+    __shared__ uint32_t s_tmem;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tile_bytes = TILE * K;
+    uint8_t *sB = smem;
+    const uint32_t n_tiles = (n + TILE - 1) / TILE;
+    if (tid == 0) {
+        for (uint32_t i = 0; i < NA; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_sfree[i], 1); }
+        for (uint32_t i = 0; i < NACC; i++) { mbar_init(&bar_done[i], 1); mbar_init(&bar_empty[i], 4); }
+        mbar_init(&bar_bfull, 1); mbar_init(&bar_bfree, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(NACC * 128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t ksteps = K / 32;
+    if (warp == 5) {                                     // ---- TMA producer ----
+        if (lane == 0) {
+            uint32_t t = 0, item_no = 0;
+            for (uint32_t item = blockIdx.x; item < n_tiles; item += gridDim.x, item_no++) {
+                const uint32_t ib = n_tiles - 1 - item;
+                mbar_wait(&bar_bfree, (item_no & 1u) ^ 1u);                 // the MMAs of the previous item are done with sB
+                fence_proxy_async();
+                mbar_expect_tx(&bar_bfull, tile_bytes);
+                tma_load_1d(sB, tiles + (size_t)ib * tile_bytes, tile_bytes, &bar_bfull);
+                for (uint32_t ia = 0; ia <= ib; ia++, t++) {
+                    const uint32_t st = t % NA;
+                    mbar_wait(&bar_sfree[st], ((t / NA) & 1u) ^ 1u);
+                    mbar_expect_tx(&bar_full[st], tile_bytes);
+                    tma_load_1d(smem + (size_t)(1 + st) * tile_bytes, tiles + (size_t)ia * tile_bytes, tile_bytes, &bar_full[st]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4) {                              // ---- MMA issuer ----
+        if (lane == 0) {
+            uint32_t t = 0, item_no = 0;
+            for (uint32_t item = blockIdx.x; item < n_tiles; item += gridDim.x, item_no++) {
+                const uint32_t ib = n_tiles - 1 - item;
+                mbar_wait(&bar_bfull, item_no & 1u);
+                for (uint32_t ia = 0; ia <= ib; ia++, t++) {
+                    const uint32_t st = t % NA, ac = t % NACC;
+                    mbar_wait(&bar_full[st], (t / NA) & 1u);
+                    mbar_wait(&bar_empty[ac], ((t / NACC) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sB), b_addr = smem_u32(smem + (size_t)(1 + st) * tile_bytes);
+                    for (uint32_t k = 0; k < ksteps; k++)
+                        mma_i8(tmem + ac * 128, smem_desc(a_addr + k * 2 * TILE * 16, TILE * 16, 128), smem_desc(b_addr + k * 2 * TILE * 16, TILE * 16, 128), idesc, k ? 1u : 0u);
+                    mma_commit(&bar_sfree[st]);
+                    mma_commit(&bar_done[ac]);
+                }
+                mma_commit(&bar_bfree);
+            }
+        }
+        __syncwarp();
+    } else {                                             // ---- epilogue: thread = row b ----
+        u64 pairs = 0, sum_a = 0, sum_b = 0;
+        uint32_t t = 0;
+        for (uint32_t item = blockIdx.x; item < n_tiles; item += gridDim.x) {
+            const uint32_t ib = n_tiles - 1 - item;
+            const uint32_t b = ib * TILE + tid;
+            for (uint32_t ia = 0; ia <= ib; ia++, t++) {
+                const uint32_t ac = t % NACC;
+                mbar_wait(&bar_done[ac], (t / NACC) & 1u);
+                tc_fence_after();
+                const bool diag = ia == ib;
+                uint32_t r[4][32];
+                const uint32_t nblk = diag ? min(4u, ((tid | 31u) >> 5) + 1u) : 4u;
+                const uint32_t trow = tmem + ((warp * 32u) << 16) + ac * 128;
+                tmem_ld32_nowait(trow, r[0]);
+                if (nblk > 1) tmem_ld32_nowait(trow + 32, r[1]);
+                if (nblk > 2) tmem_ld32_nowait(trow + 64, r[2]);
+                if (nblk > 3) tmem_ld32_nowait(trow + 96, r[3]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[ac]);                 // this warp has its 32 rows of the accumulator in registers
+#pragma unroll
+                for (uint32_t blk = 0; blk < 4; blk++) {
+                    if (blk >= nblk) break;
+                    const uint32_t c0 = blk * 32;
+                    uint32_t part[4] = { 0, 0, 0, 0 };
+#pragma unroll
+                    for (int q = 7; q >= 0; q--)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) part[c] = __funnelshift_l((uint32_t)(thr - 1 - (int)r[blk][8 * c + q]), part[c], 1);
+                    uint32_t bits = part[0] | (part[1] << 8) | (part[2] << 16) | (part[3] << 24);
+                    const uint32_t a0 = ia * TILE + c0;
+                    if (b >= n) bits = 0;
+                    if (a0 + 32 > n) bits &= a0 < n ? (0xFFFFFFFFu >> (a0 + 32 - n)) : 0u;
+                    if (diag) {
+                        if (tid <= c0) bits = 0;
+                        else if (tid - c0 < 32) bits &= (1u << (tid - c0)) - 1u;
+                    }
+                    while (bits) { const uint32_t q = __ffs(bits) - 1; bits &= bits - 1; pairs++; sum_a += a0 + q; sum_b += b; }
+                }
+            }
+        }
+        for (int o = 16; o; o >>= 1) { pairs += __shfl_down_sync(~0u, pairs, o); sum_a += __shfl_down_sync(~0u, sum_a, o); sum_b += __shfl_down_sync(~0u, sum_b, o); }
+        if (lane == 0 && pairs) { atomicAdd(&out->pairs, pairs); atomicAdd(&out->sum_a, sum_a); atomicAdd(&out->sum_b, sum_b); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(NACC * 128u) : "memory");
+}
+
 int main(int argc, char **argv) {
     const uint32_t n = argc > 1 ? (uint32_t)atoi(argv[1]) : 200000u;
     const uint32_t L = argc > 2 ? (uint32_t)atoi(argv[2]) : 84u;
     const uint32_t cdmax = argc > 3 ? (uint32_t)atoi(argv[3]) : 12u;
     const int reps = argc > 4 ? atoi(argv[4]) : 5;
+    const int dbg = argc > 6 ? atoi(argv[6]) : 0;
+    const int version = argc > 7 ? atoi(argv[7]) : 2;
     if (L == 0 || L > 128 || n == 0) { fprintf(stderr, "1 <= L <= 128\n"); return 2; }
     const uint32_t K = (3 * L + 31) / 32 * 32, W = (L + 31) / 32;
     const uint32_t n_tiles = (n + TILE - 1) / TILE;
@@ -278,7 +403,10 @@ int main(int argc, char **argv) {
     k_pack_planes<<<(n + 255) / 256, 256>>>(d_bases, n, L, W, d_rows);
     CK(cudaDeviceSynchronize());
     float ms_pack = 0; cudaEventElapsedTime(&ms_pack, e0, e1);
-    const size_t smem = 3 * (size_t)TILE * K;
+    const size_t smem = 3 * (size_t)TILE * K, smem2 = 4 * (size_t)TILE * K;
+    CK(cudaFuncSetAttribute(k_hamming_mma2<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_hamming_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_hamming_mma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int dev = 0, sms = 0, occ = 0;
@@ -294,7 +422,9 @@ int main(int argc, char **argv) {
     for (int r = 0; r < reps + 1; r++) {
         CK(cudaMemset(d_work, 0, 8)); CK(cudaMemset(d_t, 0, sizeof(Tally)));
         CK(cudaEventRecord(e0));
-        k_hamming_mma<<<sms * occ, 128, smem>>>(d_tiles, n, K, thr, d_work, d_t);
+        if (version == 2) k_hamming_mma2<3, 4><<<sms, 192, smem2>>>(d_tiles, n, K, thr, d_t);
+        else if (version == 3) k_hamming_mma2<2, 2><<<sms * 2, 192, smem>>>(d_tiles, n, K, thr, d_t);
+        else k_hamming_mma<<<sms * occ, 128, smem>>>(d_tiles, n, K, thr, d_work, d_t, dbg);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -311,7 +441,8 @@ int main(int argc, char **argv) {
     const bool same = got.pairs == want.pairs && got.sum_a == want.sum_a && got.sum_b == want.sum_b;
     const double pair_count = (double)n * (n - 1) / 2, macs = (double)n_tiles * (n_tiles + 1) / 2 * TILE * TILE * K;
     printf("{\"tool\": \"hamming_mma\", \"n\": %u, \"L\": %u, \"K\": %u, \"cdmax\": %u, \"ctas_per_sm\": %d, \"ms_mma_sweep\": %.3f, \"ms_pack_i8\": %.3f, \"pairs_per_s\": %.4g, "
-           "\"int8_tmacs\": %.1f, \"survivors\": %llu, \"survivors_ref\": %llu, \"same_survivor_set\": %s, \"ms_ref_plain_popc_kernel\": %.3f}\n",
-           n, L, K, cdmax, occ, best, ms_pack, pair_count / (best * 1e-3), macs / (best * 1e-3) / 1e12, got.pairs, want.pairs, same ? "true" : "false", ms_ref);
+           "\"int8_tmacs\": %.1f, \"survivors\": %llu, \"survivors_ref\": %llu, \"same_survivor_set\": %s, \"ms_ref_plain_popc_kernel\": %.3f, \"dbg\": %d, \"version\": %d}\n",
+           n, L, K, cdmax, occ, best, ms_pack, pair_count / (best * 1e-3), macs / (best * 1e-3) / 1e12, got.pairs, want.pairs, same ? "true" : "false", ms_ref, dbg, version);
+    if (dbg) return 0;
     return same ? 0 : 1;
 }
