@@ -63,10 +63,11 @@ static_assert(sizeof(EntryMeta) == 128, "EntryMeta must be 128 bytes");
                              // rank's share of a sharded join) use 4 or 2, so that there are still more work items than CTA slots
 // Tier 1 on the tensor cores (k_sweep_mma; tools/micro/hamming_mma.cu is the stand-alone prototype): a group whose two CDR3s total
 // at most MMA_MAX_BASES bases and that has at least `mma_min_tiles` tiles gets its rows a second time as int8 tetrahedron vectors
-// (3 values per base), one shared-memory image of MMA_TILE_BYTES per tile of 128 entries.
+// (3 values per base, then the a side of two threshold slots: 16, 1), one shared-memory image of MMA_TILE_BYTES per tile of 128 entries.
 #define MMA_NONE 0xFFFFFFFFu
-#define MMA_MAX_BASES 96u
-#define MMA_KMAX 288u                               // 3 * MMA_MAX_BASES, a multiple of 32
+#define MMA_MAX_BASES 95u                           // 3 * 95 + 2 threshold slots <= MMA_KMAX
+#define MMA_KMAX 288u                               // 3 values per base + 2 threshold slots, rounded up to a multiple of 32
+#define MMA_KSTEPS(total) ((3u * (total) + 2u + 31u) / 32u)   // tcgen05.mma instructions (K = 32 each) per tile pair
 #define MMA_TILE_BYTES (T1_TILE * MMA_KMAX)         // [K/16 chunks][128 rows][16 bytes]; a group with fewer bases uses a prefix
 #define MMA_MIN_TILES_DEFAULT 128u                     // 16,384 entries: below that the int8 pack and the second kernel cost more than the popcount sweep of the group (C3: +0.15 ms with 16)
 #define SEG_QMAX 32u         // at most this many segments per row

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_group_build(const unsigned long long *_
                 if ((unsigned long long)slot + gv.T <= i8_cap_tiles && slot + gv.T < (1u << 23)) {
                     g.mma = (total << 23) | slot;
                     atomicAdd(&ctr->mma_pairs, gv.v[3]);
-                    atomicAdd(&ctr->mma_macs, (unsigned long long)gv.T * (gv.T + 1) / 2 * T1_TILE * T1_TILE * ((3 * total + 31) / 32 * 32));
+                    atomicAdd(&ctr->mma_macs, (unsigned long long)gv.T * (gv.T + 1) / 2 * T1_TILE * T1_TILE * (MMA_KSTEPS(total) * 32));
                     atomicAdd(&ctr->t1_alg_bytes, 0ull - gv.v[4]);            // not popcount work (k_group_vals counted every group)
                 }
             }
@@ -1772,7 +1772,8 @@ __global__ void __launch_bounds__(T1_TILE) k_sweep(const uint32_t *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // Tier 1 on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) for large groups of short CDR3s.
 // A base becomes a vertex of the regular tetrahedron in {+1,-1}^3 — v_g . v_h = 3 if g == h, -1 otherwise — so for two rows of one
-// group (T bases each)  dot = 3 (T - d) - d = 3T - 4d  and  d <= cdmax  <=>  dot >= 3T - 4 cdmax,  exact in s32.  The CTA keeps
+// group (T bases each)  dot = 3 (T - d) - d = 3T - 4d  and  d <= cdmax  <=>  dot >= thr := 3T - 4 cdmax,  exact in s32; two more K slots
+// — (16, 1) in every row, (-thr / 16, -thr % 16) patched into the B tile — put -thr into the contraction, so a survivor is a clear sign bit.  The CTA keeps
 // the B tile (128 entries = the M rows of the MMA) in shared memory and sweeps the A tiles of the work item (128 entries = the N
 // columns) exactly as k_sweep does; the tiles arrive by 1-D bulk TMA copies in the image the MMA wants (K-major, no swizzle: [K/16][128
 // rows][16 bytes]; descriptor LBO = 2048 B between the two 16-byte K chunks of one instruction, SBO = 128 B between groups of 8
@@ -1820,7 +1821,7 @@ __global__ void __launch_bounds__(256) k_pack_i8(const uint32_t *__restrict__ c3
 #pragma unroll
     for (int w = 0; w < 3; w++) { H[w] = w < (int)W ? rp[w] : 0u; L[w] = w < (int)W ? rp[W + w] : 0u; }
     int8_t *dst = tiles + (size_t)(slot0 + ib) * MMA_TILE_BYTES + (size_t)row * 16;
-    const uint32_t chunks = (3 * total + 31) / 32 * 2;
+    const uint32_t chunks = MMA_KSTEPS(total) * 2;
     for (uint32_t j = 0; j < chunks; j++) {
         uint32_t v[4] = { 0, 0, 0, 0 };
 #pragma unroll
@@ -1833,6 +1834,8 @@ __global__ void __launch_bounds__(256) k_pack_i8(const uint32_t *__restrict__ c3
                 const bool neg = (code == 1 && c != 0) || (code == 2 && c != 1) || (code == 3 && c != 2);
                 x = neg ? 0xFFu : 0x01u;
             }
+            if (k == 3 * total) x = 16u;               // the a side of the two threshold slots: with (-thr / 16, -thr % 16) patched into the B tile
+            if (k == 3 * total + 1) x = 1u;            // (k_sweep_mma) the accumulator is dot - thr and a survivor is a clear sign bit
             v[q >> 2] |= x << (8 * (q & 3));
         }
         *reinterpret_cast<uint4 *>(dst + (size_t)j * T1_TILE * 16) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -1860,7 +1863,7 @@ __device__ __forceinline__ bool mma_item(const GroupInfo *__restrict__ groups, c
     if (m.g.mma == MMA_NONE) return false;                // k_sweep's
     m.q = it.y >> 16; m.ib = it.y & 0xFFFFu;
     m.total = m.g.mma >> 23; m.slot0 = m.g.mma & 0x7FFFFFu;
-    m.ksteps = (3 * m.total + 31) / 32; m.tile_bytes = m.ksteps * 32 * T1_TILE;
+    m.ksteps = MMA_KSTEPS(m.total); m.tile_bytes = m.ksteps * 32 * T1_TILE;
     const uint32_t S = m.g.seg;
     m.ia_lo = m.q * S; m.ia_hi = min(m.ia_lo + S - 1, m.ib);
     m.xrow = 0; m.slots_ok = true;
@@ -1875,7 +1878,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_sweep_mma(const int8_t *__re
                                                            uint32_t *cnt, uint32_t *xk, uint32_t *xcnt, unsigned long long xcap, uint8_t *needed) {
     if (ctr->i8_tiles == 0) return;                       // no tensor-core group in this input
     extern __shared__ __align__(128) uint8_t mma_smem[];  // B tile | A stages
-    __shared__ __align__(8) uint64_t bar_full[MMA_NA], bar_sfree[MMA_NA], bar_done[MMA_NACC], bar_empty[MMA_NACC], bar_bfull, bar_bfree;
+    __shared__ __align__(8) uint64_t bar_full[MMA_NA], bar_sfree[MMA_NA], bar_done[MMA_NACC], bar_empty[MMA_NACC], bar_bfull, bar_bfree, bar_bpatch;
     __shared__ uint32_t s_tmem;
     __shared__ uint4 s_stage[T1_TILE / 32][MMA_STAGE];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1883,7 +1886,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_sweep_mma(const int8_t *__re
     if (tid == 0) {
         for (uint32_t i = 0; i < MMA_NA; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_sfree[i], 1); }
         for (uint32_t i = 0; i < MMA_NACC; i++) { mbar_init(&bar_done[i], 1); mbar_init(&bar_empty[i], T1_TILE / 32); }
-        mbar_init(&bar_bfull, 1); mbar_init(&bar_bfree, 1);
+        mbar_init(&bar_bfull, 1); mbar_init(&bar_bfree, 1); mbar_init(&bar_bpatch, T1_TILE / 32);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -1923,7 +1926,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_sweep_mma(const int8_t *__re
             uint32_t t = 0, item_no = 0;
             for (unsigned long long w = blockIdx.x; w < nitems; w += gridDim.x) {
                 if (!mma_item(groups, order, w, xcap, m)) continue;
-                mbar_wait(&bar_bfull, item_no & 1u);
+                mbar_wait(&bar_bpatch, item_no & 1u);                    // the B tile has landed and carries its threshold slots
                 for (uint32_t ia = m.ia_lo; ia <= m.ia_hi; ia++, t++) {
                     const uint32_t st = t % MMA_NA, ac = t % MMA_NACC;
                     mbar_wait(&bar_full[st], (t / MMA_NA) & 1u);
@@ -1943,7 +1946,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_sweep_mma(const int8_t *__re
         __syncwarp();
     } else {                                              // ---- epilogue: thread = entry b of the B tile = TMEM lane ----
         uint4 *stage = s_stage[warp];
-        uint32_t fill = 0, t = 0;
+        uint32_t fill = 0, t = 0, item_no = 0;
         SweepCtx cx;
         cx.ctr = ctr; cx.cand = cand; cx.cand_cap = cand_cap; cx.firstk = firstk; cx.cnt = cnt; cx.xk = xk; cx.xcnt = xcnt; cx.xcap = xcap;
         cx.needed = needed;
@@ -1957,6 +1960,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_sweep_mma(const int8_t *__re
             uint32_t *slot = cx.firstk + (size_t)posB * PHASE_A_K, slot_stride = 1;
             if (m.q) { slot = cx.xk + (size_t)m.xrow * PHASE_A_K * T1_TILE + tid; slot_stride = T1_TILE; }
             uint32_t mycnt = 0;
+            {   // the threshold rides in the contraction: the b side of the two threshold slots, into this thread's row of the B tile
+                mbar_wait(&bar_bfull, item_no & 1u);
+                const uint32_t k0 = 3 * m.total, k1 = 3 * m.total + 1;
+                sB[(k0 / 16) * T1_TILE * 16 + tid * 16 + (k0 % 16)] = (uint8_t)(int8_t)(-(thr / 16));
+                sB[(k1 / 16) * T1_TILE * 16 + tid * 16 + (k1 % 16)] = (uint8_t)(int8_t)(-(thr % 16));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_bpatch);
+                item_no++;
+            }
             for (uint32_t ia = m.ia_lo; ia <= m.ia_hi; ia++, t++) {
                 const uint32_t ac = t % MMA_NACC;
                 mbar_wait(&bar_done[ac], (t / MMA_NACC) & 1u);
@@ -1980,13 +1993,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) k_sweep_mma(const int8_t *__re
                 for (uint32_t blk = 0; blk < 4; blk++) {
                     if (blk >= nblk) break;
                     const uint32_t a0 = blk * 32;
-                    // bit j = (dot >= thr): the sign bit of (thr - 1 - dot), one funnel shift per element, four independent chains of eight
+                    // the accumulator is dot - thr: bit j = its sign bit, gathered with one funnel shift per element (four independent chains of
+                    // eight); a survivor is a CLEAR sign bit
                     uint32_t part[4] = { 0, 0, 0, 0 };
 #pragma unroll
                     for (int j = 7; j >= 0; j--)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) part[c] = __funnelshift_l((uint32_t)(thr - 1 - (int)r[blk][8 * c + j]), part[c], 1);
-                    uint32_t bits = part[0] | (part[1] << 8) | (part[2] << 16) | (part[3] << 24);
+                        for (int c = 0; c < 4; c++) part[c] = __funnelshift_l(r[blk][8 * c + j], part[c], 1);
+                    uint32_t bits = ~(part[0] | (part[1] << 8) | (part[2] << 16) | (part[3] << 24));
                     if (rowsA - a0 < 32) bits &= (1u << (rowsA - a0)) - 1u;
                     if (!validB) bits = 0;
                     if (diag) {                                           // keep a < b

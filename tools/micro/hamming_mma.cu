@@ -79,7 +79,7 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 struct Tally { u64 pairs, sum_a, sum_b; };
 
 // bases: [n][L] values 0..3.  tiles: [n_tiles][K/16][128][16] int8 (the shared-memory image of one operand tile)
-__global__ void k_pack_i8(const uint8_t *bases, uint32_t n, uint32_t L, uint32_t K, int8_t *tiles) {
+__global__ void k_pack_i8(const uint8_t *bases, uint32_t n, uint32_t L, uint32_t K, int8_t *tiles, int extra) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;       // one thread per (entry slot, 16-byte chunk)
     const uint32_t chunks = K / 16;
     const size_t slots = (size_t)((n + TILE - 1) / TILE) * TILE;
@@ -96,6 +96,8 @@ __global__ void k_pack_i8(const uint8_t *bases, uint32_t n, uint32_t L, uint32_t
             const bool neg = (g == 1 && c != 0) || (g == 2 && c != 1) || (g == 3 && c != 2);
             x = neg ? -1 : 1;
         }
+        if (extra && k == 3 * L) x = 16;            // version 4: the a side of the two threshold slots (the b side is patched in shared memory)
+        if (extra && k == 3 * L + 1) x = 1;
         v[q] = x;
     }
     int8_t *dst = tiles + (size_t)(e / TILE) * TILE * K + (size_t)j * TILE * 16 + (size_t)(e % TILE) * 16;
@@ -255,10 +257,13 @@ __global__ void __launch_bounds__(128) k_hamming_mma(const int8_t *__restrict__ 
 // frees an accumulator as soon as it has read it.  Items (B tiles) are dealt round-robin, longest first; every role walks the
 // same item sequence with its own stage counter.
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-template <uint32_t NA, uint32_t NACC>
-__global__ void __launch_bounds__(192) k_hamming_mma2(const int8_t *__restrict__ tiles, uint32_t n, uint32_t K, int thr, Tally *out) {
+// SIGN (version 4): the threshold rides in the contraction — two extra K slots hold (16, 1) on the a side and (-thr / 16, -thr % 16) on the
+// b side (patched into the B tile in shared memory by the epilogue threads), so the accumulator is dot - thr and a survivor is a clear sign bit:
+// one funnel shift per element instead of a subtraction and a shift.
+template <uint32_t NA, uint32_t NACC, bool SIGN>
+__global__ void __launch_bounds__(192) k_hamming_mma2(const int8_t *__restrict__ tiles, uint32_t n, uint32_t K, int thr, Tally *out, uint32_t L) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[NA], bar_sfree[NA], bar_done[NACC], bar_empty[NACC], bar_bfull, bar_bfree;
+    __shared__ __align__(8) uint64_t bar_full[NA], bar_sfree[NA], bar_done[NACC], bar_empty[NACC], bar_bfull, bar_bfree, bar_bpatch;
     __shared__ uint32_t s_tmem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tile_bytes = TILE * K;
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(192) k_hamming_mma2(const int8_t *__restrict__
     if (tid == 0) {
         for (uint32_t i = 0; i < NA; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_sfree[i], 1); }
         for (uint32_t i = 0; i < NACC; i++) { mbar_init(&bar_done[i], 1); mbar_init(&bar_empty[i], 4); }
-        mbar_init(&bar_bfull, 1); mbar_init(&bar_bfree, 1);
+        mbar_init(&bar_bfull, 1); mbar_init(&bar_bfree, 1); mbar_init(&bar_bpatch, 4);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(192) k_hamming_mma2(const int8_t *__restrict__
             uint32_t t = 0, item_no = 0;
             for (uint32_t item = blockIdx.x; item < n_tiles; item += gridDim.x, item_no++) {
                 const uint32_t ib = n_tiles - 1 - item;
-                mbar_wait(&bar_bfull, item_no & 1u);
+                mbar_wait(SIGN ? &bar_bpatch : &bar_bfull, item_no & 1u);
                 for (uint32_t ia = 0; ia <= ib; ia++, t++) {
                     const uint32_t st = t % NA, ac = t % NACC;
                     mbar_wait(&bar_full[st], (t / NA) & 1u);
@@ -321,10 +326,19 @@ __global__ void __launch_bounds__(192) k_hamming_mma2(const int8_t *__restrict__
         __syncwarp();
     } else {                                             // ---- epilogue: thread = row b ----
         u64 pairs = 0, sum_a = 0, sum_b = 0;
-        uint32_t t = 0;
-        for (uint32_t item = blockIdx.x; item < n_tiles; item += gridDim.x) {
+        uint32_t t = 0, item_no = 0;
+        for (uint32_t item = blockIdx.x; item < n_tiles; item += gridDim.x, item_no++) {
             const uint32_t ib = n_tiles - 1 - item;
             const uint32_t b = ib * TILE + tid;
+            if (SIGN) {                                  // the b side of the threshold slots, into this thread's row of the B tile
+                mbar_wait(&bar_bfull, item_no & 1u);
+                const uint32_t k0 = 3 * L, k1 = 3 * L + 1;
+                sB[(k0 / 16) * TILE * 16 + tid * 16 + (k0 % 16)] = (uint8_t)(int8_t)(-(thr / 16));
+                sB[(k1 / 16) * TILE * 16 + tid * 16 + (k1 % 16)] = (uint8_t)(int8_t)(-(thr % 16));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_bpatch);
+            }
             for (uint32_t ia = 0; ia <= ib; ia++, t++) {
                 const uint32_t ac = t % NACC;
                 mbar_wait(&bar_done[ac], (t / NACC) & 1u);
@@ -349,8 +363,9 @@ __global__ void __launch_bounds__(192) k_hamming_mma2(const int8_t *__restrict__
 #pragma unroll
                     for (int q = 7; q >= 0; q--)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) part[c] = __funnelshift_l((uint32_t)(thr - 1 - (int)r[blk][8 * c + q]), part[c], 1);
+                        for (int c = 0; c < 4; c++) part[c] = __funnelshift_l(SIGN ? r[blk][8 * c + q] : (uint32_t)(thr - 1 - (int)r[blk][8 * c + q]), part[c], 1);
                     uint32_t bits = part[0] | (part[1] << 8) | (part[2] << 16) | (part[3] << 24);
+                    if (SIGN) bits = ~bits;                  // a survivor is a clear sign bit of dot - thr
                     const uint32_t a0 = ia * TILE + c0;
                     if (b >= n) bits = 0;
                     if (a0 + 32 > n) bits &= a0 < n ? (0xFFFFFFFFu >> (a0 + 32 - n)) : 0u;
@@ -378,7 +393,7 @@ int main(int argc, char **argv) {
     const int dbg = argc > 6 ? atoi(argv[6]) : 0;
     const int version = argc > 7 ? atoi(argv[7]) : 2;
     if (L == 0 || L > 128 || n == 0) { fprintf(stderr, "1 <= L <= 128\n"); return 2; }
-    const uint32_t K = (3 * L + 31) / 32 * 32, W = (L + 31) / 32;
+    const uint32_t K = (3 * L + 2 + 31) / 32 * 32, W = (L + 31) / 32;      // room for the two threshold slots of version 4
     const uint32_t n_tiles = (n + TILE - 1) / TILE;
     // a giant bucket: families of near-identical CDR3s (a few substitutions from a founder) among unrelated ones
     std::vector<uint8_t> h((size_t)n * L);
@@ -398,15 +413,17 @@ int main(int argc, char **argv) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0));
-    k_pack_i8<<<(unsigned)((pack_threads + 255) / 256), 256>>>(d_bases, n, L, K, d_tiles);
+    k_pack_i8<<<(unsigned)((pack_threads + 255) / 256), 256>>>(d_bases, n, L, K, d_tiles, version == 4);
     CK(cudaEventRecord(e1));
     k_pack_planes<<<(n + 255) / 256, 256>>>(d_bases, n, L, W, d_rows);
     CK(cudaDeviceSynchronize());
     float ms_pack = 0; cudaEventElapsedTime(&ms_pack, e0, e1);
     const size_t smem = 3 * (size_t)TILE * K, smem2 = 4 * (size_t)TILE * K;
-    CK(cudaFuncSetAttribute(k_hamming_mma2<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_hamming_mma2<3, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_hamming_mma2<2, 2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_hamming_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_hamming_mma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int dev = 0, sms = 0, occ = 0;
@@ -422,8 +439,9 @@ int main(int argc, char **argv) {
     for (int r = 0; r < reps + 1; r++) {
         CK(cudaMemset(d_work, 0, 8)); CK(cudaMemset(d_t, 0, sizeof(Tally)));
         CK(cudaEventRecord(e0));
-        if (version == 2) k_hamming_mma2<3, 4><<<sms, 192, smem2>>>(d_tiles, n, K, thr, d_t);
-        else if (version == 3) k_hamming_mma2<2, 2><<<sms * 2, 192, smem>>>(d_tiles, n, K, thr, d_t);
+        if (version == 2) k_hamming_mma2<3, 4, false><<<sms, 192, smem2>>>(d_tiles, n, K, thr, d_t, L);
+        else if (version == 3) k_hamming_mma2<2, 2, false><<<sms * 2, 192, smem>>>(d_tiles, n, K, thr, d_t, L);
+        else if (version == 4) k_hamming_mma2<2, 2, true><<<sms * 2, 192, smem>>>(d_tiles, n, K, thr, d_t, L);
         else k_hamming_mma<<<sms * occ, 128, smem>>>(d_tiles, n, K, thr, d_work, d_t, dbg);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
