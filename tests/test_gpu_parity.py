@@ -567,10 +567,13 @@ def test_compact_full_size_c3():
     cp.close()
 
 
-@pytest.mark.parametrize("name,scale,stride,compact", [("C3", 0.2, 0, 1), ("C3", 0.2, 0, 0), ("C4", 0.05, 1, 1), ("C3", 0.05, 1, 0), ("C5", 0.05, 0, 1)])
-def test_two_rank_nccl_sharded_join(name, scale, stride, compact):
+@pytest.mark.parametrize("name,scale,stride,compact,mma", [("C3", 0.2, 0, 1, 0), ("C3", 0.2, 0, 0, 0), ("C4", 0.05, 1, 1, 0), ("C3", 0.05, 1, 0, 0), ("C5", 0.05, 0, 1, 0),
+                                                          ("C4", 0.1, 1, 1, 1), ("C3", 0.2, 0, 1, 1)])
+def test_two_rank_nccl_sharded_join(name, scale, stride, compact, mma):
     """Real NCCL, one process per GPU (torchrun, 2 ranks): contiguous bucket ranges and the shared giant bucket (stride
-    mode), the exchange inside the library; rank 0 checks the gathered result against the one-GPU join and the oracle."""
+    mode), the exchange inside the library; rank 0 checks the gathered result against the one-GPU join and the oracle.
+    mma = 1: tier 1 forced onto the tensor cores for every group that qualifies (in stride mode each rank sweeps its rows of the
+    one group with k_sweep_mma)."""
     import os
     import subprocess
     import sys
@@ -581,7 +584,10 @@ def test_two_rank_nccl_sharded_join(name, scale, stride, compact):
     port = 29500 + (os.getpid() % 400)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(here, "mgpu_worker.py"), name, str(scale), str(stride), str(compact)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if mma:
+        env["EJOIN_MMA_MIN_TILES"], env["EJOIN_MMA_CAP_TILES"] = "1", "20000"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
