@@ -909,7 +909,7 @@ int device_pipeline(ejoin_handle *h, int is_bcr, uint32_t stride, uint32_t phase
         k_bucket_heads<<<nb256, 256, 0, st>>>(h->din, head_pos);
         size_t tb = cub_bytes;
         cub::DeviceScan::InclusiveScan(cub_tmp, tb, head_pos, bucket_start, MaxOp(), (int)n, st);
-        k_entry_keys<<<std::min(nb256, (unsigned)h->sm_count * 8u), 256, 0, st>>>(h->din, bucket_start, keys, vals, (uint32_t *)h->d_presL.p, (uint32_t *)h->d_presC.p, ctr);
+        k_entry_keys<<<std::min(nb256, (unsigned)h->sm_count * 4u), 256, 0, st>>>(h->din, bucket_start, keys, vals, (uint32_t *)h->d_presL.p, (uint32_t *)h->d_presC.p, ctr);
         h->launches += 2;
         CK(cudaGetLastError());
         // Tables (p1 per total length, multipliers per CDR3 length pair) are cached on the handle.  Once a handle has built

@@ -48,10 +48,10 @@ __global__ void k_entry_keys(DevIn in, const uint32_t *bucket_start, unsigned lo
             // radix pass fewer; two separate runs of equal lens stay two buckets, as in the reference's bucket scan)
             key = ((unsigned long long)bucket_start[k] << 16) | ((unsigned long long)c0 << 8) | c1;
             uint32_t L = l0 + l1, cc = (c0 << 8) | c1;
-            // test before set, reading through L2 (__ldcg): a line cached in L1 before the bit was set would stay stale for the whole
-            // kernel and every entry of that SM would go on issuing the same-address atomic
-            if (!(__ldcg(&presL[L >> 5]) & (1u << (L & 31)))) atomicOr(&presL[L >> 5], 1u << (L & 31));
-            if (!(__ldcg(&presC[cc >> 5]) & (1u << (cc & 31)))) atomicOr(&presC[cc >> 5], 1u << (cc & 31));
+            // test before set: after the first hit per value these are plain cached loads, not serialized atomics.  (Measured: reading the
+            // bitmaps through L2 with __ldcg instead, or twice as many blocks, each made the keys stage 0.02 ms slower.)
+            if (!(presL[L >> 5] & (1u << (L & 31)))) atomicOr(&presL[L >> 5], 1u << (L & 31));
+            if (!(presC[cc >> 5] & (1u << (cc & 31)))) atomicOr(&presC[cc >> 5], 1u << (cc & 31));
         }
         keys[k] = key;
         vals[k] = k;
