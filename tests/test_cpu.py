@@ -202,3 +202,31 @@ def test_pack_compact_round_trip():
             assert r.hcomp == int(a["hcomp"][k]) and r.fr3_start == int(a["fr3_start"][k])
         assert n_ascii > 0
         cp.close()
+
+
+def test_tetrahedron_contraction_is_the_cdr3_hamming_test():
+    """The arithmetic k_sweep_mma rests on, checked in numpy: bases as tetrahedron vertices in {+1,-1}^3 give
+    dot = 3L - 4d; with the two threshold slots ((16, 1) on the a side, (-thr // 16, -thr % 16) on the b side) the accumulator is
+    dot - thr and `d <= cdmax` is exactly a clear sign bit; every value fits int8 and K = 3L + 2 fits the 288-byte row for L <= 95."""
+    rng = np.random.default_rng(7)
+    V = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], np.int32)
+    assert np.array_equal(V @ V.T, 4 * np.eye(4, dtype=np.int32) - 1)            # 3 on the diagonal, -1 elsewhere
+    for L, cdmax in ((1, 0), (36, 5), (84, 12), (95, 14), (95, 0)):
+        K = (3 * L + 2 + 31) // 32 * 32
+        assert K <= 288
+        thr = 3 * L - 4 * cdmax
+        assert 0 < thr and thr // 16 <= 127
+        a = rng.integers(0, 4, (64, L))
+        b = a[rng.integers(0, 64, 64)].copy()                                     # relatives: a few substitutions
+        for r in range(64):
+            for p in rng.integers(0, L, rng.integers(0, cdmax + 6)):
+                b[r, p] = rng.integers(0, 4)
+        ra = np.zeros((64, K), np.int32); rb = np.zeros((64, K), np.int32)
+        ra[:, :3 * L] = V[a].reshape(64, 3 * L); rb[:, :3 * L] = V[b].reshape(64, 3 * L)
+        ra[:, 3 * L], ra[:, 3 * L + 1] = 16, 1
+        rb[:, 3 * L], rb[:, 3 * L + 1] = -(thr // 16), -(thr % 16)
+        assert np.abs(ra).max() <= 127 and np.abs(rb).max() <= 127
+        acc = rb @ ra.T                                                           # rows = b (the patched B tile), columns = a
+        d = (b[:, None, :] != a[None, :, :]).sum(-1)
+        assert np.array_equal(acc, 3 * L - 4 * d - thr)
+        assert np.array_equal(acc >= 0, d <= cdmax)
