@@ -241,3 +241,168 @@ def test_gpu_rejects_malformed_packs():
     nine = dict(ncells=1, chains=[_chain("IGK", f"c{i}") for i in range(9)], entries=[(0, 1)])
     with pytest.raises(RuntimeError, match="-1"):
         R.refine_clonotypes(R.pack_from_exacts([nine], []))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A second, independent restatement in plain Python — written clonotype by clonotype, the way the reference works (a
+# matrix per clonotype, literal enumeration of the doublet triples) — against the flat C oracle.
+# ------------------------------------------------------------------------------------------------------------------
+def _py_refine(exacts, joins, links, doublet=True, signature=True, weak=True, third=10, dmult=5, smult=20, wmax=20, wmult=8):
+    import itertools
+    nx = len(exacts)
+    alive = [bool(e["entries"]) for e in exacts]
+    fate = [0] * nx
+    # clonotypes the join left: components of joins + links over exact subclonotypes
+    lab = list(range(nx))
+
+    def find(p, a):
+        while p[a] != a:
+            a = p[a]
+        return a
+    for (x1, _), (x2, _) in list(joins) + list(links):
+        a, b = find(lab, x1), find(lab, x2)
+        lab[max(a, b)] = min(a, b)
+    label = [find(lab, x) if alive[x] else None for x in range(nx)]
+    okey = lambda ch: ((("TRX" + ch["chain_type"][3:]) if ch["chain_type"].startswith("TRB") else ("TRY" + ch["chain_type"][3:]) if ch["chain_type"].startswith("TRA")
+                        else ch["chain_type"]) + ":" + ch["cdr3_aa"], len(ch["seq"]))
+    origins = sorted({tuple(e.get("origin", (0,))) for e in exacts})
+
+    def stage():
+        """per clonotype: columns of every chain (dict (x, m) -> col), new labels, number of columns"""
+        col, ncols, newlab = {}, {}, {}
+        for L in sorted({l for l in label if l is not None}):
+            members = sorted((x for x in range(nx) if alive[x] and label[x] == L), key=lambda x: (origins.index(tuple(exacts[x].get("origin", (0,)))), x))
+            chains = [(x, m) for x in members for m in range(len(exacts[x]["chains"]))]
+            par = {c: c for c in chains}
+
+            def fnd(c):
+                while par[c] != c:
+                    c = par[c]
+                return c
+
+            def join(a, b):
+                a, b = fnd(a), fnd(b)
+                if a != b:
+                    par[max(a, b, key=chains.index)] = min(a, b, key=chains.index)
+            for (x1, e1), (x2, e2) in joins:
+                if not (alive[x1] and alive[x2] and label[x1] == L):
+                    continue
+                c1, c2 = exacts[x1]["entries"][e1], exacts[x2]["entries"][e2]
+                for h in range(2):
+                    if c1[h] is not None and c2[h] is not None:
+                        join((x1, c1[h]), (x2, c2[h]))
+                if len(exacts[x1]["chains"]) == 3 and len(exacts[x2]["chains"]) == 3 and None not in c1 and None not in c2 and c1[0] != c1[1] and c2[0] != c2[1]:
+                    t1, t2 = 3 - c1[0] - c1[1], 3 - c2[0] - c2[1]
+                    a, b = exacts[x1]["chains"][t1], exacts[x2]["chains"][t2]
+                    heavy = lambda ch: ch["chain_type"][:3] in ("IGH", "TRB")
+                    if heavy(a) == heavy(b) and len(a["seq"]) == len(b["seq"]) and sum(p != q for p, q in zip(a["seq"], b["seq"])) <= third:
+                        join((x1, t1), (x2, t2))
+            for c in chains:                                  # onesies: identical V..J
+                if len(exacts[c[0]]["chains"]) == 1:
+                    for d in chains:
+                        if d != c and exacts[d[0]]["chains"][d[1]]["seq"] == exacts[c[0]]["chains"][0]["seq"]:
+                            join(c, d)
+            # the break-up: exact subclonotypes sharing a column
+            xp = {x: x for x in members}
+
+            def xf(x):
+                while xp[x] != x:
+                    x = xp[x]
+                return x
+            for c in chains:
+                a, b = xf(c[0]), xf(fnd(c)[0])
+                if a != b:
+                    xp[max(a, b)] = min(a, b)
+            for comp in sorted({xf(x) for x in members}):
+                mem = [x for x in members if xf(x) == comp]
+                cch = [c for c in chains if c[0] in mem]
+                srt = sorted(cch, key=lambda c: (okey(exacts[c[0]]["chains"][c[1]]), members.index(c[0]), c[1]))
+                orbits = {}
+                for c in cch:
+                    orbits.setdefault(fnd(c), []).append(c)
+                order = sorted(orbits, key=lambda r: srt.index(min(orbits[r], key=cch.index)))
+                base, run = {}, 0
+                for r in order:
+                    base[r] = run
+                    run += max(sum(1 for c in orbits[r] if c[0] == x) for x in mem)
+                for x in mem:
+                    newlab[x] = comp; ncols[x] = run
+                    for m in range(len(exacts[x]["chains"])):
+                        r = fnd((x, m))
+                        col[(x, m)] = base[r] + sum(1 for mm in range(m) if fnd((x, mm)) == r)
+        return col, ncols, newlab
+
+    def pures(col):
+        groups = {}
+        for x in range(nx):
+            if alive[x]:
+                groups.setdefault((label[x], tuple(sorted(col[(x, m)] for m in range(len(exacts[x]["chains"]))))), []).append(x)
+        return groups
+
+    def apply(dead, code):
+        for x in dead:
+            alive[x] = False; fate[x] = code
+    col, ncols, newlab = stage()
+    for x in range(nx):
+        label[x] = newlab.get(x) if alive[x] else None
+    if doublet:
+        P = list(pures(col).values())
+        cells = [sum(exacts[x]["ncells"] for x in p) for p in P]
+        cd = [{ch["cdr3_dna"] for x in p for ch in exacts[x]["chains"]} for p in P]
+        dead = []
+        for i0 in range(len(P)):
+            part = [j for j in range(len(P)) if j != i0 and cd[j] & cd[i0] and dmult * cells[i0] <= cells[j]]
+            if any(not (cd[a] & cd[b]) for a, b in itertools.combinations(part, 2)):
+                dead += P[i0]
+        if dead:
+            apply(dead, 1); col, ncols, newlab = stage()
+            for x in range(nx):
+                label[x] = newlab.get(x) if alive[x] else None
+    if signature:
+        G = pures(col)
+        dead = []
+        for (L, sig), p in G.items():
+            if len(sig) < 2:
+                continue
+            tot = sum(sum(exacts[x]["ncells"] for x in q) for (L2, s2), q in G.items() if L2 == L and s2 != sig and len(s2) == 2 and set(s2) & set(sig))
+            if tot >= smult * sum(exacts[x]["ncells"] for x in p):
+                dead += p
+        if dead:
+            apply(dead, 2); col, ncols, newlab = stage()
+            for x in range(nx):
+                label[x] = newlab.get(x) if alive[x] else None
+    if weak:
+        dead = set()
+        for L in {l for l in label if l is not None}:
+            mem = [x for x in range(nx) if alive[x] and label[x] == L]
+            if ncols[mem[0]] < 3:
+                continue
+            total = sum(exacts[x]["ncells"] for x in mem)
+            for c in range(ncols[mem[0]]):
+                sup = [x for x in mem if any(col[(x, m)] == c for m in range(len(exacts[x]["chains"])))]
+                w = sum(exacts[x]["ncells"] for x in sup)
+                if w <= wmax and wmult * w < total:
+                    dead |= set(sup)
+        if dead:
+            apply(sorted(dead), 3); col, ncols, newlab = stage()
+            for x in range(nx):
+                label[x] = newlab.get(x) if alive[x] else None
+    clon = [label[x] if alive[x] else NONE for x in range(nx)]
+    cols = [col[(x, m)] if alive[x] else NONE for x in range(nx) for m in range(len(exacts[x]["chains"]))]
+    return fate, clon, cols, [ncols[x] if alive[x] else 0 for x in range(nx)]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_matches_an_independent_python_restatement(seed):
+    kw = dict(frac_doublet=0.2, frac_three=0.3, frac_onesie=0.3, frac_weak=0.1, frac_sig=0.1, big=0.3)
+    exacts, joins, links = R.synth_exacts(14, seed=100 + seed, **kw)
+    pk = R.pack_from_exacts(exacts, joins, links)
+    for opts in (dict(), dict(doublet=0), dict(signature=0, weak_chains=0), dict(doublet_mult=1, signature_mult=2, weak_max_cells=6, weak_mult=2, third_chain_diffs=20)):
+        res, _ = O.refine(pk, O.refine_opts(**opts))
+        fate, clon, cols, ncols = _py_refine(exacts, joins, links, doublet=opts.get("doublet", 1), signature=opts.get("signature", 1), weak=opts.get("weak_chains", 1),
+                                             third=opts.get("third_chain_diffs", 10), dmult=opts.get("doublet_mult", 5), smult=opts.get("signature_mult", 20),
+                                             wmax=opts.get("weak_max_cells", 20), wmult=opts.get("weak_mult", 8))
+        assert list(res.fate) == fate, (seed, opts)
+        assert list(res.clonotype_of) == clon, (seed, opts)
+        assert list(res.n_columns) == ncols, (seed, opts)
+        assert list(res.column_of) == cols, (seed, opts)
