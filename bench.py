@@ -265,7 +265,7 @@ def refine_main(args):
     from enclone_b200 import refine as R
     W, K = max(args.warmup, 0), max(args.steps, 1)
     base = R.synth_refine_pack(args.refine_families, seed=1)
-    pk = R.tile_pack(base, args.refine_tiles)
+    pk = R.tile_pack(base, args.refine_tiles, pinned=args.impl != "reference")      # page-locked tables and result arrays, as the join's bench uses
     config = {"workload": f"{args.refine_tiles} independent copies of a synthetic repertoire of {args.refine_families} clonal families "
                           f"(enclone_b200.refine.synth_refine_pack, seed 1): {pk.n_exact} exact subclonotypes, {pk.n_chain} chains, {pk.n_info} info entries, "
                           f"{len(pk.a['join_k1'])} raw joins", "filters": "doublet, signature, weak chains (enclone defaults)"}
@@ -289,13 +289,14 @@ def refine_main(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the refinement has no CPU fallback)")
     sampler = ClockSampler(0)
+    out = R.RefineResult(pk.n_exact, pk.n_chain, pinned=True)
     for _ in range(W):
-        R.refine_clonotypes(pk)
+        R.refine_clonotypes(pk, result=out)
     sampler.start()
     t0 = time.perf_counter()
     dev_ms, stats, res = 0.0, None, None
     for _ in range(K):
-        res, stats = R.refine_clonotypes(pk)
+        res, stats = R.refine_clonotypes(pk, result=out)
         dev_ms += stats["ms_device"]
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -311,7 +312,7 @@ def refine_main(args):
             "ms_per_step": wall / K * 1e3, "ms_device_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 / u64 integer", "data": "synthetic", "config": config,
             "e2e": {"value": pk.n_exact * K / wall, "unit": "exacts/s", "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": out_bytes,
-                    "pack_bytes": in_bytes, "note": "pageable numpy buffers; of the pack's V..J arena only the third chains the rule compares are uploaded"},
+                    "pack_bytes": in_bytes, "note": "tables and result arrays in page-locked memory; of the pack's V..J arena (pageable) only the third chains the rule compares are gathered and uploaded"},
             "gpu_launches": int(stats["gpu_launches"]) * K, "stats": {k: (round(v, 3) if isinstance(v, float) else int(v)) for k, v in stats.items()},
             "roofline": {"bound": "hbm", "achieved": alg / (dev_ms / K * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (dev_ms / K * 1e-3) / 1e9 / hbm, "traffic": None,
                          "kernel": "whole refinement (no kernel holds a quarter of it: ~20 CUB radix sorts of 64-bit keys and ~70 small kernels)",

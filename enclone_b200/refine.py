@@ -54,11 +54,46 @@ _FIELDS = (("exact_id", np.uint32), ("exact_cols0", np.uint8), ("exact_cols1", n
 _CT = {np.uint8: C.c_uint8, np.uint32: C.c_uint32, np.uint64: C.c_uint64}
 
 
-class RefinePack:
-    """The flat view of (exact_clonotypes, info, raw_joins, eq) the refinement reads; owns its numpy arrays."""
+class _Pinned:
+    """numpy arrays in page-locked host memory (ejoin_host_alloc): uploads from them run at the copy engine's rate instead of
+    going through the driver's staging buffer.  Falls back to ordinary arrays where there is no device to pin for."""
 
-    def __init__(self, arrays):
+    def __init__(self):
+        self.ptrs = []
+
+    def copy(self, arr):
+        arr = np.ascontiguousarray(arr)
+        if arr.nbytes == 0:
+            return arr
+        lib = _lib.load()
+        p = lib.ejoin_host_alloc(arr.nbytes)
+        if not p:
+            return arr
+        self.ptrs.append(p)
+        out = np.frombuffer((C.c_uint8 * arr.nbytes).from_address(p), dtype=arr.dtype).reshape(arr.shape)
+        out[...] = arr
+        return out
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for p in self.ptrs:
+                lib.ejoin_host_free(p)
+        except Exception:
+            pass
+        self.ptrs = []
+
+
+class RefinePack:
+    """The flat view of (exact_clonotypes, info, raw_joins, eq) the refinement reads; owns its numpy arrays
+    (pinned=True: in page-locked memory, except the V..J arena, of which the library reads a few percent)."""
+
+    def __init__(self, arrays, pinned=False):
         self.a = {k: np.ascontiguousarray(arrays[k], dt) for k, dt in _FIELDS}
+        self._pin = None
+        if pinned:
+            self._pin = _Pinned()
+            self.a = {k: (v if k == "seq_arena" else self._pin.copy(v)) for k, v in self.a.items()}
         a = self.a
         st = ErefinePack()
         st.abi_version = EREFINE_ABI_VERSION
@@ -78,11 +113,13 @@ class RefinePack:
 
 
 class RefineResult:
-    def __init__(self, n_exact, n_chain):
-        self.fate = np.zeros(max(n_exact, 1), np.uint8)
-        self.clonotype_of = np.zeros(max(n_exact, 1), np.uint32)
-        self.column_of = np.zeros(max(n_chain, 1), np.uint32)
-        self.n_columns = np.zeros(max(n_exact, 1), np.uint32)
+    def __init__(self, n_exact, n_chain, pinned=False):
+        self._pin = _Pinned() if pinned else None
+        mk = (lambda n, dt: self._pin.copy(np.empty(n, dt))) if pinned else (lambda n, dt: np.zeros(n, dt))
+        self.fate = mk(max(n_exact, 1), np.uint8)
+        self.clonotype_of = mk(max(n_exact, 1), np.uint32)
+        self.column_of = mk(max(n_chain, 1), np.uint32)
+        self.n_columns = mk(max(n_exact, 1), np.uint32)
         self.n_exact, self.n_chain = n_exact, n_chain
         st = ErefineResult()
         st.fate = self.fate.ctypes.data_as(C.POINTER(C.c_uint8))
@@ -91,8 +128,10 @@ class RefineResult:
         self.struct = st
 
     def trim(self):
-        self.fate, self.clonotype_of, self.n_columns = self.fate[:self.n_exact], self.clonotype_of[:self.n_exact], self.n_columns[:self.n_exact]
-        self.column_of = self.column_of[:self.n_chain]
+        if not hasattr(self, "_full"):
+            self._full = (self.fate, self.clonotype_of, self.column_of, self.n_columns)      # kept for a later call that reuses this object
+        self.fate, self.clonotype_of, self.n_columns = self._full[0][:self.n_exact], self._full[1][:self.n_exact], self._full[3][:self.n_exact]
+        self.column_of = self._full[2][:self.n_chain]
         return self
 
     def same_as(self, other):
@@ -128,11 +167,13 @@ def _bind():
     return lib
 
 
-def refine_clonotypes(pack, device=0, **opts):
-    """(RefineResult, stats): fate / final clonotype / table column of every exact subclonotype and chain."""
+def refine_clonotypes(pack, device=0, result=None, **opts):
+    """(RefineResult, stats): fate / final clonotype / table column of every exact subclonotype and chain.
+    `result`: a RefineResult to fill (e.g. a pinned one kept between calls) instead of a fresh one."""
     lib = _bind()
     o = make_opts(**opts)
-    res, st = RefineResult(pack.n_exact, pack.n_chain), ErefineStats()
+    res, st = result or RefineResult(pack.n_exact, pack.n_chain), ErefineStats()
+    res.fate, res.clonotype_of, res.column_of, res.n_columns = res._full if hasattr(res, "_full") else (res.fate, res.clonotype_of, res.column_of, res.n_columns)
     rc = lib.erefine_run(C.byref(pack.struct), C.byref(o), device, C.byref(res.struct), C.byref(st))
     if rc != 0:
         raise RuntimeError(f"erefine_run: {rc}: {lib.erefine_last_error().decode()}")
@@ -316,7 +357,7 @@ def synth_refine_pack(n_families, seed=1, **kw):
     return pack_from_exacts(*synth_exacts(n_families, seed, **kw))
 
 
-def tile_pack(pack, times):
+def tile_pack(pack, times, pinned=False):
     """`times` independent copies of a pack side by side (ids shifted): the bench's way to a large input."""
     a, out = pack.a, {}
     n, nx, nc = pack.n_info, pack.n_exact, pack.n_chain
@@ -335,4 +376,4 @@ def tile_pack(pack, times):
     out["order_rank"], out["left"], out["seq_len"] = np.tile(a["order_rank"], times), np.tile(a["left"], times), np.tile(a["seq_len"], times)
     out["seq_off"] = rep(a["seq_off"], nbytes, np.uint64)
     out["seq_arena"] = np.tile(a["seq_arena"], times)
-    return RefinePack(out)
+    return RefinePack(out, pinned=pinned)
