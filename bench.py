@@ -15,6 +15,9 @@ Workload: BASELINE.json configs[2] (the ~1.6M-cell pooled BCR run the metric's t
 sentence names), which fits one GPU; N > 1 shards its buckets over the ranks (strong scaling).
 
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C3] [--scale S]
+With --workload C4 (one 200,000-entry bucket) tier 1 runs on the tensor cores and the roofline entry is k_sweep_mma's (bound: tensor).
+Two more paths, each with its own metric (not the north star): --path group (symmetric grouping) and --path refine
+(post-join refinement); both take --impl reference for their CPU restatements.
 """
 import argparse
 import ctypes as C
