@@ -505,7 +505,7 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
     uint32_t *xof = P.get<uint32_t>(nc), *pos = P.get<uint32_t>(nc), *pos2 = P.get<uint32_t>(nc), *cp = P.get<uint32_t>(nc), *xp = P.get<uint32_t>(nx);
     uint32_t *label = P.get<uint32_t>(nx), *cmin = P.get<uint32_t>(n), *col = P.get<uint32_t>(nc), *base = P.get<uint32_t>(nc), *mm = P.get<uint32_t>(nc);
     uint32_t *gbase = P.get<uint32_t>(nx), *ncols_label = P.get<uint32_t>(nx), *pure = P.get<uint32_t>(nx);
-    uint8_t *alive = P.get<uint8_t>(nx), *fate = P.get<uint8_t>(nx), *del = P.get<uint8_t>(nx), *flag8 = P.get<uint8_t>(big), *pdel = P.get<uint8_t>(nx);
+    uint8_t *alive = P.get<uint8_t>(nx), *fate = P.get<uint8_t>(nx), *del = P.get<uint8_t>(nx), *pdel = P.get<uint8_t>(nx);
     u64 *k_in = P.get<u64>(big), *k_out = P.get<u64>(big), *k2_in = P.get<u64>(big), *k2_out = P.get<u64>(big), *rep = P.get<u64>(nc);
     uint32_t *v_in = P.get<uint32_t>(big), *v_out = P.get<uint32_t>(big), *t32a = P.get<uint32_t>(big), *t32b = P.get<uint32_t>(big), *t32c = P.get<uint32_t>(big);
     u64 *npure = P.get<u64>(nx), *pure_hash = P.get<u64>(nx), *A = P.get<u64>(nc), *T = P.get<u64>(nx), *by_c = P.get<u64>(big), *by_p = P.get<u64>(big);
@@ -581,8 +581,6 @@ extern "C" int erefine_run(const erefine_pack_t *pk, const erefine_opts_t *op, i
         tb = cub_bytes; cub::DeviceScan::InclusiveScan(cub_tmp, tb, t32a, seq_head, RMax(), (int)nc, st);
         launches += 2;
     }
-    if (int lbx = 0) (void)lbx;                                  // bits of a (clonotype name << 32 | 32-bit field) key; dead entries are all ones and sort last
-    while (lb < 64 && (1ull << (lb - 32)) < (u64)nx + 1) lb++;
     auto stage = [&]() -> int {
         RCK(cudaMemsetAsync(&ctr->n_pure, 0, 8, st));
         k_r_iota<<<blocks(nc), 256, 0, st>>>(cp, nc);
