@@ -104,7 +104,7 @@ struct DevCounters {         // device-resident scalars (one struct, copied back
     unsigned long long n_xrows;      // extra slot rows asked for by the group table
     unsigned long long n_items;      // tier-1 work items of this rank (after the cost sort)
     unsigned int cls_count[64], cls_cursor[64];   // counting sort of the work items by cost class
-    unsigned long long work_next_mma;               // k_sweep_mma's own cursor over the same item list
+    unsigned long long work_next_mma;               // (unused since k_sweep_mma deals the item list round-robin to its CTAs; kept for the struct layout)
     unsigned int i8_tiles, pad2;                    // int8 tile slots handed to tensor-core groups (k_group_build)
     unsigned long long mma_pairs, mma_macs;         // pairs of the tensor-core groups; int8 multiply-accumulates their tile pairs stand for
 };
